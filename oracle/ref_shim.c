@@ -1,0 +1,315 @@
+/*
+ * oracle/ref_shim.c -- TEST INFRASTRUCTURE ONLY.
+ *
+ * A thin harness around the UNMODIFIED reference sources (compiled where they lie under
+ * /root/reference by oracle/Makefile into oracle/_ref/libj2kref.so).  It replaces the three
+ * entry points of libavcodec's generic layer that the native jpeg2000 decoder needs
+ * (ff_thread_get_buffer, ff_set_dimensions, av_codec_is_encoder) and exposes plain-C entry
+ * points that tests/ and bench.py's reference arm load with ctypes:
+ *
+ *   ref_decode()        whole codestream -> pixels, through ff_jpeg2000_decoder.cb.decode
+ *                       (libavcodec/jpeg2000dec.c:2825-2908, FFCodec at :2926-2939)
+ *   ref_ht_block()      one HT code-block -> int32 sign-magnitude coefficients, through
+ *                       ff_jpeg2000_decode_htj2k (libavcodec/jpeg2000htdec.c:1188-1336)
+ *   ref_idwt()          ff_jpeg2000_dwt_init + ff_dwt_decode (libavcodec/jpeg2000dwt.c:539-620)
+ *   ref_mct()           Jpeg2000DSPContext.mct_decode[] (libavcodec/jpeg2000dsp.c:43-104)
+ *   ref_decode_bench()  the CPU baseline: N codestreams decoded by T threads, one decoder
+ *                       context per thread (what `ffmpeg -threads T` frame threading does,
+ *                       libavcodec/pthread_frame.c:248-295), wall-clock seconds returned.
+ *
+ * Nothing in the product (ffmpeg-ht_b200/) may link or load this file.
+ */
+#include <pthread.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "libavutil/imgutils.h"
+#include "libavutil/log.h"
+#include "libavutil/mem.h"
+#include "libavutil/pixdesc.h"
+#include "libavcodec/avcodec.h"
+#include "libavcodec/codec_internal.h"
+#include "libavcodec/jpeg2000.h"
+#include "libavcodec/jpeg2000dec.h"
+#include "libavcodec/jpeg2000dsp.h"
+#include "libavcodec/jpeg2000dwt.h"
+#include "libavcodec/jpeg2000htdec.h"
+#include "libavcodec/thread.h"
+
+extern const FFCodec ff_jpeg2000_decoder;
+
+/* ---- the three generic-layer functions the decoder calls ------------------------------ */
+
+int av_codec_is_encoder(const AVCodec *codec) { (void)codec; return 0; }
+
+int ff_set_dimensions(AVCodecContext *s, int width, int height)
+{
+    int ret = av_image_check_size2(width, height, s->max_pixels, AV_PIX_FMT_NONE, 0, s);
+    if (ret < 0)
+        width = height = 0;
+    s->coded_width  = width;
+    s->coded_height = height;
+    s->width        = width;
+    s->height       = height;
+    return ret;
+}
+
+int ff_thread_get_buffer(AVCodecContext *avctx, AVFrame *f, int flags)
+{
+    (void)flags;
+    f->width  = avctx->width;
+    f->height = avctx->height;
+    f->format = avctx->pix_fmt;
+    /* 64-byte line alignment: same class of padded linesize the real pool hands out */
+    int ret = av_image_alloc(f->data, f->linesize, f->width, f->height, avctx->pix_fmt, 64);
+    return ret < 0 ? ret : 0;
+}
+
+static int serial_execute2(AVCodecContext *c,
+                           int (*func)(AVCodecContext *c2, void *arg, int jobnr, int threadnr),
+                           void *arg2, int *ret, int count)
+{
+    for (int i = 0; i < count; i++) {
+        int r = func(c, arg2, i, 0);
+        if (ret)
+            ret[i] = r;
+    }
+    return 0;
+}
+
+/* ---- decoder context handling ---------------------------------------------------------- */
+
+static int g_loglevel_set;
+
+static AVCodecContext *ctx_open(int bitexact)
+{
+    if (!g_loglevel_set) {
+        av_log_set_level(AV_LOG_FATAL);
+        g_loglevel_set = 1;
+    }
+    AVCodecContext *avctx = av_mallocz(sizeof(*avctx));
+    if (!avctx)
+        return NULL;
+    avctx->codec      = &ff_jpeg2000_decoder.p;
+    avctx->codec_id   = AV_CODEC_ID_JPEG2000;
+    avctx->codec_type = AVMEDIA_TYPE_VIDEO;
+    avctx->pix_fmt    = AV_PIX_FMT_NONE;
+    avctx->max_pixels = INT32_MAX;
+    avctx->execute2   = serial_execute2;
+    avctx->flags      = bitexact ? AV_CODEC_FLAG_BITEXACT : 0;
+    avctx->priv_data  = av_mallocz(ff_jpeg2000_decoder.priv_data_size);
+    if (!avctx->priv_data) {
+        av_free(avctx);
+        return NULL;
+    }
+    *(const AVClass **)avctx->priv_data = ff_jpeg2000_decoder.p.priv_class;
+    if (ff_jpeg2000_decoder.init(avctx) < 0) {
+        av_free(avctx->priv_data);
+        av_free(avctx);
+        return NULL;
+    }
+    return avctx;
+}
+
+static void ctx_close(AVCodecContext *avctx)
+{
+    if (!avctx)
+        return;
+    av_free(avctx->priv_data);
+    av_free(avctx);
+}
+
+/* copy the visible bytes of every plane, tightly packed, into out */
+static int64_t pack_frame(const AVCodecContext *avctx, const AVFrame *f, uint8_t *out, int64_t cap)
+{
+    int64_t pos = 0;
+    int linesizes[4];
+    if (av_image_fill_linesizes(linesizes, avctx->pix_fmt, f->width) < 0)
+        return -1;
+    const AVPixFmtDescriptor *d = av_pix_fmt_desc_get(avctx->pix_fmt);
+    for (int p = 0; p < 4 && f->data[p]; p++) {
+        int h = f->height;
+        if (p == 1 || p == 2)
+            h = AV_CEIL_RSHIFT(f->height, d->log2_chroma_h);
+        if ((d->flags & AV_PIX_FMT_FLAG_PAL) && p == 1) {
+            if (pos + 1024 > cap)
+                return -2;
+            memcpy(out + pos, f->data[1], 1024);
+            pos += 1024;
+            continue;
+        }
+        for (int y = 0; y < h; y++) {
+            if (pos + linesizes[p] > cap)
+                return -2;
+            memcpy(out + pos, f->data[p] + (int64_t)y * f->linesize[p], linesizes[p]);
+            pos += linesizes[p];
+        }
+    }
+    return pos;
+}
+
+/*
+ * info[0]=width info[1]=height info[2]=AVPixelFormat info[3]=bytes written info[4]=decode return
+ * returns 0 on success, the negative AVERROR otherwise.
+ */
+int ref_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint8_t *out, int64_t cap)
+{
+    AVCodecContext *avctx = ctx_open(bitexact);
+    if (!avctx)
+        return -12;
+    uint8_t *padded = av_mallocz(len + AV_INPUT_BUFFER_PADDING_SIZE);
+    memcpy(padded, cs, len);
+    AVPacket pkt;
+    memset(&pkt, 0, sizeof(pkt));
+    pkt.data = padded;
+    pkt.size = (int)len;
+    AVFrame *frame = av_mallocz(sizeof(AVFrame));
+    int got = 0;
+    int ret = ff_jpeg2000_decoder.cb.decode(avctx, frame, &got, &pkt);
+    info[4] = ret;
+    if (ret >= 0 && got) {
+        info[0] = frame->width;
+        info[1] = frame->height;
+        info[2] = avctx->pix_fmt;
+        info[3] = pack_frame(avctx, frame, out, cap);
+        ret = info[3] < 0 ? -1 : 0;
+    } else if (ret >= 0) {
+        ret = -1;
+    }
+    if (frame->data[0])
+        av_freep(&frame->data[0]);
+    av_free(frame);
+    av_free(padded);
+    ctx_close(avctx);
+    return ret;
+}
+
+const char *ref_pix_fmt_name(int fmt) { return av_get_pix_fmt_name(fmt); }
+
+/* ---- stage-level entry points ---------------------------------------------------------- */
+
+/*
+ * One HT code-block.  data = Dcup||Dref (length bytes); returns the reference's return code and
+ * fills out[h*w] with t1.data (sign-magnitude, libavcodec/jpeg2000htdec.c:1318-1331).
+ */
+int ref_ht_block(const uint8_t *data, int length, int npasses, int Lcup, int Lref, int zbp,
+                 int w, int h, int M_b, int roi_shift, int vsc, int32_t *out)
+{
+    static _Thread_local Jpeg2000T1Context t1;
+    Jpeg2000DecoderContext s;
+    Jpeg2000CodingStyle codsty;
+    Jpeg2000Cblk cblk;
+    AVCodecContext *avctx = ctx_open(0);
+    memset(&s, 0, sizeof(s));
+    memset(&codsty, 0, sizeof(codsty));
+    memset(&cblk, 0, sizeof(cblk));
+    s.avctx = avctx;
+    int l2w = 2;
+    while ((1 << l2w) < w)
+        l2w++;
+    t1.stride = (1 << l2w) + 2;           /* jpeg2000dec.c:2227 */
+    cblk.data = av_mallocz(length + 8);
+    memcpy(cblk.data, data, length);
+    cblk.length          = length;
+    cblk.npasses         = npasses;
+    cblk.pass_lengths[0] = Lcup;
+    cblk.pass_lengths[1] = Lref;
+    cblk.zbp             = zbp;
+    cblk.modes           = JPEG2000_CTSY_HTJ2K_F | (vsc ? JPEG2000_CBLK_VSC : 0);
+    int ret = ff_jpeg2000_decode_htj2k(&s, &codsty, &t1, &cblk, w, h, M_b, roi_shift);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++)
+            out[y * w + x] = t1.data[y * t1.stride + x];
+    av_free(cblk.data);
+    ctx_close(avctx);
+    return ret;
+}
+
+/* type: 0 = FF_DWT97 (float), 1 = FF_DWT53, 2 = FF_DWT97_INT; border = {x0,x1,y0,y1} */
+int ref_idwt(int type, const int *border, int levels, void *data)
+{
+    DWTContext d;
+    int b[2][2] = { { border[0], border[1] }, { border[2], border[3] } };
+    memset(&d, 0, sizeof(d));
+    int ret = ff_jpeg2000_dwt_init(&d, b, levels, type);
+    if (ret < 0)
+        return ret;
+    ret = ff_dwt_decode(&d, data);
+    ff_dwt_destroy(&d);
+    return ret;
+}
+
+int ref_mct(int type, void *p0, void *p1, void *p2, int n)
+{
+    Jpeg2000DSPContext c;
+    ff_jpeg2000dsp_init(&c);
+    c.mct_decode[type](p0, p1, p2, n);
+    return 0;
+}
+
+/* ---- CPU baseline ---------------------------------------------------------------------- */
+
+typedef struct BenchJob {
+    const uint8_t *const *cs;
+    const int64_t *len;
+    int nframes, first, step, bitexact, reps;
+    int errors;
+} BenchJob;
+
+static void *bench_worker(void *arg)
+{
+    BenchJob *j = arg;
+    AVCodecContext *avctx = ctx_open(j->bitexact);
+    for (int r = 0; r < j->reps; r++) {
+        for (int i = j->first; i < j->nframes; i += j->step) {
+            uint8_t *padded = av_mallocz(j->len[i] + AV_INPUT_BUFFER_PADDING_SIZE);
+            memcpy(padded, j->cs[i], j->len[i]);
+            AVPacket pkt;
+            memset(&pkt, 0, sizeof(pkt));
+            pkt.data = padded;
+            pkt.size = (int)j->len[i];
+            AVFrame *frame = av_mallocz(sizeof(AVFrame));
+            int got = 0;
+            avctx->pix_fmt = AV_PIX_FMT_NONE;
+            if (ff_jpeg2000_decoder.cb.decode(avctx, frame, &got, &pkt) < 0 || !got)
+                j->errors++;
+            if (frame->data[0])
+                av_freep(&frame->data[0]);
+            av_free(frame);
+            av_free(padded);
+        }
+    }
+    ctx_close(avctx);
+    return NULL;
+}
+
+/* decodes every codestream `reps` times using `threads` decoder contexts; returns seconds (<0 on error) */
+double ref_decode_bench(const uint8_t *const *cs, const int64_t *len, int nframes, int threads,
+                        int reps, int bitexact)
+{
+    if (threads < 1)
+        threads = 1;
+    if (threads > 256)
+        threads = 256;
+    pthread_t th[256];
+    BenchJob jobs[256];
+    struct timespec t0, t1;
+    /* make sure one-time init (LUTs, log level) is outside the timed region */
+    ctx_close(ctx_open(bitexact));
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (BenchJob){ cs, len, nframes, t, threads, bitexact, reps, 0 };
+        pthread_create(&th[t], NULL, bench_worker, &jobs[t]);
+    }
+    int errors = 0;
+    for (int t = 0; t < threads; t++) {
+        pthread_join(th[t], NULL);
+        errors += jobs[t].errors;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (errors)
+        return -1.0;
+    return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+}
