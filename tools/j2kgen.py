@@ -1,0 +1,170 @@
+"""Synthetic HTJ2K workload generator (test + benchmark infrastructure, CPU only).
+
+`synth_image()` makes the seeded content model of SURVEY.md section 8(d) (band-limited texture +
+gradients + filtered noise); `encode()` turns planes into an HTJ2K codestream with tools/htj2k_enc.c
+(built on demand with gcc into tools/libj2kgen.so).  `CONFIGS` names the BASELINE.json workloads.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from dataclasses import dataclass, field
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+
+class _Params(ctypes.Structure):
+    _fields_ = [
+        ("width", ctypes.c_int32), ("height", ctypes.c_int32), ("ncomp", ctypes.c_int32),
+        ("bitdepth", ctypes.c_int32), ("tile_w", ctypes.c_int32), ("tile_h", ctypes.c_int32),
+        ("levels", ctypes.c_int32), ("cbw_log2", ctypes.c_int32), ("cbh_log2", ctypes.c_int32),
+        ("reversible", ctypes.c_int32), ("mct", ctypes.c_int32), ("prog", ctypes.c_int32),
+        ("use_precincts", ctypes.c_int32), ("prec_exps", ctypes.c_int32 * 33),
+        ("guard_bits", ctypes.c_int32), ("npasses", ctypes.c_int32), ("sop", ctypes.c_int32),
+        ("eph", ctypes.c_int32), ("vsc", ctypes.c_int32), ("base_step", ctypes.c_float),
+        ("x_off", ctypes.c_int32), ("y_off", ctypes.c_int32), ("stats_blocks", ctypes.c_int32),
+        ("stats_max_lcup", ctypes.c_int32), ("error", ctypes.c_int32),
+    ]
+
+
+def build(force: bool = False) -> Path:
+    so = _HERE / "libj2kgen.so"
+    src = _HERE / "htj2k_enc.c"
+    if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
+        subprocess.check_call(["gcc", "-std=c11", "-O2", "-fPIC", "-shared", "-o", str(so), str(src), "-lm"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(str(build()))
+        _LIB.j2kgen_encode.restype = ctypes.c_int64
+        _LIB.j2kgen_encode.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(_Params),
+                                       ctypes.c_void_p, ctypes.c_int64]
+        _LIB.j2kgen_encode_block.restype = ctypes.c_int
+        _LIB.j2kgen_encode_block.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                             ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    return _LIB
+
+
+@dataclass
+class EncParams:
+    levels: int = 5
+    cblk: tuple = (64, 64)
+    reversible: bool = True
+    mct: bool = True
+    prog: int = 0                 # 0 LRCP 1 RLCP 2 RPCL 3 PCRL 4 CPRL
+    precincts: list | None = None  # [(PPx, PPy)] for r = 0..levels
+    guard_bits: int = 2
+    npasses: int = 1
+    sop: bool = False
+    eph: bool = False
+    vsc: bool = False
+    base_step: float = 1.0
+    tile: tuple = (0, 0)
+    offset: tuple = (0, 0)
+    stats: dict = field(default_factory=dict)
+
+
+def encode(planes, bitdepth: int, p: EncParams) -> bytes:
+    """planes: list of 2-D integer arrays (same shape), unsigned samples of `bitdepth` bits."""
+    L = lib()
+    planes = [np.ascontiguousarray(a, dtype=np.int32) for a in planes]
+    h, w = planes[0].shape
+    guard = p.guard_bits
+    while True:
+        P = _Params()
+        P.width, P.height, P.ncomp, P.bitdepth = w, h, len(planes), bitdepth
+        P.tile_w, P.tile_h = p.tile
+        P.levels = p.levels
+        P.cbw_log2, P.cbh_log2 = int(np.log2(p.cblk[0])), int(np.log2(p.cblk[1]))
+        P.reversible, P.mct, P.prog = int(p.reversible), int(p.mct and len(planes) >= 3), p.prog
+        if p.precincts:
+            P.use_precincts = 1
+            for r in range(p.levels + 1):
+                px, py = p.precincts[min(r, len(p.precincts) - 1)]
+                P.prec_exps[r] = px | (py << 4)
+        P.guard_bits, P.npasses, P.sop, P.eph, P.vsc = guard, p.npasses, int(p.sop), int(p.eph), int(p.vsc)
+        P.base_step = p.base_step
+        P.x_off, P.y_off = p.offset
+        cap = int(w * h * len(planes) * 4 + (1 << 20))
+        out = np.empty(cap, np.uint8)
+        ptrs = (ctypes.c_void_p * len(planes))(*[a.ctypes.data for a in planes])
+        n = L.j2kgen_encode(ptrs, ctypes.byref(P), out.ctypes.data, cap)
+        if n == -1 and guard < 7:      # exponent bound exceeded: one more guard bit
+            guard += 1
+            continue
+        if n < 0:
+            raise RuntimeError(f"j2kgen_encode failed: {n}")
+        p.stats = {"blocks": P.stats_blocks, "max_lcup": P.stats_max_lcup, "guard_bits": guard, "bytes": int(n)}
+        return out[:n].tobytes()
+
+
+def encode_block(coef: np.ndarray, npasses: int = 1, vsc: bool = False, maxbp: int = 31):
+    """One HT code-block from signed integer coefficients -> (bytes, Lcup, Lref)."""
+    L = lib()
+    coef = np.ascontiguousarray(coef, dtype=np.int32)
+    h, w = coef.shape
+    out = np.empty(w * h * 8 + 1024, np.uint8)
+    lc, lr = ctypes.c_int(), ctypes.c_int()
+    n = L.j2kgen_encode_block(coef.ctypes.data, w, h, npasses, int(vsc), maxbp, out.ctypes.data, out.size,
+                              ctypes.byref(lc), ctypes.byref(lr))
+    if n < 0:
+        raise RuntimeError(f"encode_block failed: {n}")
+    return out[:n].tobytes(), lc.value, lr.value
+
+
+def synth_image(w: int, h: int, ncomp: int, bitdepth: int, seed: int, phase: float = 0.0):
+    """Seeded content model: sinusoid texture + gradients + 1/f-ish noise, sigma_noise ~ 2^(bitdepth-9)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    full = float((1 << bitdepth) - 1)
+    planes = []
+    for c in range(ncomp):
+        img = np.full((h, w), 0.5, np.float32)
+        for _ in range(6):
+            fx, fy = rng.uniform(-0.08, 0.08, 2)
+            amp = rng.uniform(0.02, 0.10)
+            ph = rng.uniform(0, 2 * np.pi) + phase * rng.uniform(0.5, 2.0)
+            img += amp * np.sin(2 * np.pi * (fx * xx + fy * yy) + ph).astype(np.float32)
+        img += 0.15 * (xx / max(w - 1, 1) - 0.5) * rng.uniform(-1, 1) + 0.15 * (yy / max(h - 1, 1) - 0.5) * rng.uniform(-1, 1)
+        # cheap 1/f-like noise: white noise at three scales, box-upsampled
+        noise = np.zeros((h, w), np.float32)
+        for s, a in ((1, 1.0), (4, 1.5), (16, 2.0)):
+            hh, ww = -(-h // s), -(-w // s)
+            n = rng.standard_normal((hh, ww)).astype(np.float32)
+            noise += a * np.kron(n, np.ones((s, s), np.float32))[:h, :w]
+        img += noise * (2.0 ** (bitdepth - 9)) / full / 2.0
+        planes.append(np.clip(np.rint(img * full), 0, full).astype(np.int32))
+    return planes
+
+
+# BASELINE.json configs (index = position in `configs`, 1-based in SURVEY.md section 8d)
+CONFIGS = {
+    "cfg1": dict(w=2048, h=1080, ncomp=3, bitdepth=12, seed=1, enc=dict(levels=5, cblk=(64, 64), reversible=True, mct=True)),
+    "cfg2": dict(w=3840, h=2160, ncomp=3, bitdepth=10, seed=2, enc=dict(levels=5, cblk=(64, 64), reversible=False, mct=True, base_step=1.0)),
+    "cfg3": dict(w=7680, h=4320, ncomp=1, bitdepth=16, seed=3, enc=dict(levels=5, cblk=(64, 64), reversible=True, mct=False, tile=(3840, 2160))),
+    "cfg4": dict(w=3840, h=2160, ncomp=3, bitdepth=12, seed=4, enc=dict(levels=5, cblk=(64, 64), reversible=True, mct=True)),
+    "cfg5": dict(w=2048, h=1080, ncomp=3, bitdepth=12, seed=5, enc=dict(levels=5, cblk=(32, 32), reversible=True, mct=True, prog=2, npasses=3,
+                                                                     precincts=[(7, 7)] + [(8, 8)] * 5)),
+    "target8k": dict(w=7680, h=4320, ncomp=1, bitdepth=16, seed=6, enc=dict(levels=5, cblk=(64, 64), reversible=True, mct=False)),
+}
+
+
+def make_config(name: str, scale: int = 1, phase: float = 0.0, seed_offset: int = 0):
+    """Returns (codestream bytes, planes, EncParams).  scale > 1 shrinks width/height for quick tests."""
+    c = CONFIGS[name]
+    w, h = c["w"] // scale, c["h"] // scale
+    planes = synth_image(w, h, c["ncomp"], c["bitdepth"], c["seed"] + seed_offset, phase)
+    enc = dict(c["enc"])
+    if "tile" in enc and scale > 1:
+        enc["tile"] = (enc["tile"][0] // scale, enc["tile"][1] // scale)
+    p = EncParams(**enc)
+    return encode(planes, c["bitdepth"], p), planes, p
