@@ -1,0 +1,1305 @@
+/*
+ * oracle/j2k_oracle_codestream.c -- TEST INFRASTRUCTURE ONLY (see j2k_oracle.h).
+ *
+ * A deliberately plain, pointer-tree decoder for the HT subset of the reference's native jpeg2000
+ * decoder: marker segments, geometry, tier-2 packet headers, then per tile the hot path
+ * (H0 tile_codeblocks, D1-D3 dequantisation, W ff_dwt_decode, M mct_decode, P1 write_frame).
+ *
+ *   marker segments      libavcodec/jpeg2000dec.c:197-1014, main loop :2425-2637
+ *   geometry             libavcodec/jpeg2000.c:214-577, init_tile jpeg2000dec.c:1016-1070
+ *   bit reader / tag tree jpeg2000dec.c:70-131
+ *   packet headers (HT)  jpeg2000dec.c:1136-1542
+ *   progression orders   jpeg2000dec.c:1544-1833
+ *   dequantisation       jpeg2000dec.c:2098-2181
+ *   tile_codeblocks      jpeg2000dec.c:2212-2299
+ *   write_frame          jpeg2000dec.c:2301-2366
+ *
+ * Not handled (returns ORACLE_ERR_PATCH): Part-1 MQ code-blocks, MIXED/HTDECLARED sets, POC, PPM/PPT,
+ * JP2 wrapper, lowres, tile-part COD/QCD.  Those are outside SURVEY.md section 8's first bar.
+ */
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "j2k_oracle.h"
+
+#define MAXC 4
+#define MAXRES 33
+
+typedef struct Rect { int x0, x1, y0, y1; } Rect;
+
+typedef struct TagNode { int val, vis; struct TagNode *parent; } TagNode;
+
+typedef struct Cblk {
+    int x0, x1, y0, y1;          /* plane coordinates relative to band origin, Mallat offset included */
+    int npasses, zbp, incl, lblock, plhd;
+    int Lcup, Lref;
+    uint8_t *data;
+    int length, cap;
+} Cblk;
+
+typedef struct Prec {
+    int ncw, nch, decoded_layers;
+    Cblk *cb;
+    TagNode *incl, *zb;
+} Prec;
+
+typedef struct Band {
+    Rect c;
+    int l2cw, l2ch;
+    float fstep;
+    int istep;
+    Prec *prec;
+} Band;
+
+typedef struct Res {
+    Rect c;
+    int ppx, ppy, npx, npy, nbands;
+    Band band[3];
+} Res;
+
+typedef struct CodSty {
+    int nres, l2cw, l2ch, cblk_style, transform, csty, nlayers, prog, mct, init;
+    int ppx[MAXRES], ppy[MAXRES];
+} CodSty;
+
+typedef struct QntSty {
+    int expn[100], mant[100], style, nguard;
+} QntSty;
+
+typedef struct Comp {
+    Rect c;
+    Res *res;
+    void *data;
+    int roi_shift;
+} Comp;
+
+typedef struct TilePart { const uint8_t *p, *end; } TilePart;
+
+typedef struct Tile {
+    Rect c;
+    Comp comp[MAXC];
+    TilePart part[32];
+    int nparts;
+} Tile;
+
+typedef struct Dec {
+    const uint8_t *cs, *end;
+    int bitexact;
+    int W, H, X0, Y0, TW, TH, TX0, TY0, ncomp, precision;
+    int cbps[MAXC], cdx[MAXC], cdy[MAXC], roi[MAXC];
+    int isHT, cap_b05, cap_b14;
+    CodSty cod[MAXC];
+    QntSty qnt[MAXC];
+    int had_coc[MAXC], had_qcc[MAXC];
+    int ntx, nty;
+    Tile *tile;
+    int pix, out_w, out_h;
+    /* packet header bit reader */
+    const uint8_t *bp, *bend;
+    int bit_index;
+    int64_t nblocks;
+} Dec;
+
+static inline int ceildiv(int a, int b) { return (int)(((int64_t)a + b - 1) / b); }
+static inline int ceildivpow2(int a, int b) { return (int)(-((-(int64_t)a) >> b)); }
+static inline int imin(int a, int b) { return a < b ? a : b; }
+static inline int imax(int a, int b) { return a > b ? a : b; }
+static inline int clip(int v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : v; }
+static inline int clip64(int64_t v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : (int)v; }
+static inline int ilog2(unsigned v) { int n = 0; while (v >>= 1) n++; return n; }
+
+static inline unsigned rd16(const uint8_t *p) { return (p[0] << 8) | p[1]; }
+static inline uint32_t rd32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | (p[1] << 16) | (p[2] << 8) | p[3]; }
+
+/* ---- packet-header bits (jpeg2000dec.c:70-90) ------------------------------------------------------ */
+static inline unsigned hb_getbyte(Dec *d) { return d->bp < d->bend ? *d->bp++ : 0; }
+static inline unsigned hb_peekbyte(Dec *d) { return d->bp < d->bend ? *d->bp : 0; }
+
+static int hb_bits(Dec *d, int n)
+{
+    int res = 0;
+    while (--n >= 0) {
+        res <<= 1;
+        if (d->bit_index == 0)
+            d->bit_index = 7 + (hb_getbyte(d) != 0xFF);
+        d->bit_index--;
+        res |= (hb_peekbyte(d) >> d->bit_index) & 1;
+    }
+    return res;
+}
+
+static void hb_flush(Dec *d)
+{
+    if (hb_getbyte(d) == 0xFF && d->bp < d->bend)
+        d->bp++;
+    d->bit_index = 8;
+}
+
+/* ---- tag trees (jpeg2000.c:41-94, jpeg2000dec.c:93-131) ------------------------------------------- */
+static TagNode *tagtree_new(int w, int h)
+{
+    int total = 1, ww = w, hh = h;
+    while (ww > 1 || hh > 1) {
+        total += ww * hh;
+        ww = (ww + 1) >> 1;
+        hh = (hh + 1) >> 1;
+    }
+    TagNode *t = calloc((size_t)total, sizeof(*t)), *lvl = t;
+    while (w > 1 || h > 1) {
+        int pw = (w + 1) >> 1;
+        TagNode *up = lvl + w * h;
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+                lvl[y * w + x].parent = &up[(y >> 1) * pw + (x >> 1)];
+        lvl = up;
+        w = pw;
+        h = (h + 1) >> 1;
+    }
+    return t;
+}
+
+static int tagtree_decode(Dec *d, TagNode *node, int threshold)
+{
+    TagNode *stack[32];
+    int sp = -1;
+    while (node && !node->vis) {
+        stack[++sp] = node;
+        node = node->parent;
+    }
+    int cur = node ? node->val : stack[sp]->val;
+    while (cur < threshold && sp >= 0) {
+        if (cur < stack[sp]->val)
+            cur = stack[sp]->val;
+        while (cur < threshold) {
+            if (hb_bits(d, 1)) {
+                stack[sp]->vis++;
+                break;
+            }
+            cur++;
+        }
+        stack[sp]->val = cur;
+        sp--;
+    }
+    return cur;
+}
+
+/* ---- marker segments -------------------------------------------------------------------------------- */
+static int parse_cox(Dec *d, const uint8_t *p, const uint8_t *end, CodSty *c)
+{
+    if (end - p < 5)
+        return ORACLE_ERR_INVALID;
+    c->nres = p[0] + 1;
+    if (c->nres >= MAXRES)
+        return ORACLE_ERR_INVALID;
+    c->l2cw = (p[1] & 15) + 2;
+    c->l2ch = (p[2] & 15) + 2;
+    if (c->l2cw > 10 || c->l2ch > 10 || c->l2cw + c->l2ch > 12)
+        return ORACLE_ERR_INVALID;
+    c->cblk_style = p[3];
+    c->transform = p[4];                                  /* 0 = 9/7, 1 = 5/3 */
+    if (d->bitexact && c->transform == ORACLE_DWT97)
+        c->transform = ORACLE_DWT97_INT;                  /* jpeg2000dec.c:543-544 */
+    p += 5;
+    if (c->csty & 1) {
+        for (int i = 0; i < c->nres; i++) {
+            if (p >= end)
+                return ORACLE_ERR_INVALID;
+            c->ppx[i] = *p & 15;
+            c->ppy[i] = *p >> 4;
+            p++;
+            if (i && (!c->ppx[i] || !c->ppy[i]))
+                return ORACLE_ERR_INVALID;
+        }
+    } else {
+        for (int i = 0; i < MAXRES; i++)
+            c->ppx[i] = c->ppy[i] = 15;
+    }
+    return 0;
+}
+
+static int parse_qcx(const uint8_t *p, int n, QntSty *q)
+{
+    if (n < 1)
+        return ORACLE_ERR_INVALID;
+    q->nguard = p[0] >> 5;
+    q->style = p[0] & 31;
+    p++;
+    n--;
+    if (q->style == 0) {
+        if (n > 96)
+            return ORACLE_ERR_INVALID;
+        for (int i = 0; i < n; i++)
+            q->expn[i] = p[i] >> 3;
+    } else if (q->style == 1) {
+        if (n < 2)
+            return ORACLE_ERR_INVALID;
+        unsigned x = rd16(p);
+        q->expn[0] = x >> 11;
+        q->mant[0] = x & 0x7FF;
+        for (int i = 1; i < 96; i++) {
+            q->expn[i] = imax(0, q->expn[0] - (i - 1) / 3);
+            q->mant[i] = q->mant[0];
+        }
+    } else {
+        n >>= 1;
+        if (n > 96)
+            return ORACLE_ERR_INVALID;
+        for (int i = 0; i < n; i++) {
+            unsigned x = rd16(p + 2 * i);
+            q->expn[i] = x >> 11;
+            q->mant[i] = x & 0x7FF;
+        }
+    }
+    return 0;
+}
+
+/* pixel format choice for a raw codestream (jpeg2000dec.c:134-193, :335-363) */
+static int choose_pix(Dec *d)
+{
+    int sub = 0;
+    for (int i = 0; i < d->ncomp; i++)
+        sub |= d->cdx[i] != 1 || d->cdy[i] != 1;
+    int wide = d->precision > 8;
+    if (d->precision > 16)
+        return 0;
+    if (!sub) {
+        switch (d->ncomp) {
+        case 1: return wide ? ORACLE_PIX_GRAY16 : ORACLE_PIX_GRAY8;
+        case 2: return wide ? ORACLE_PIX_YA16 : ORACLE_PIX_YA8;
+        case 3: return wide ? ORACLE_PIX_RGB48 : ORACLE_PIX_RGB24;
+        case 4: return wide ? ORACLE_PIX_RGBA64 : ORACLE_PIX_RGBA;
+        }
+        return 0;
+    }
+    if (d->ncomp == 3 && d->cdx[0] == 1 && d->cdy[0] == 1 && d->cdx[1] == d->cdx[2] && d->cdy[1] == d->cdy[2]) {
+        int cx = d->cdx[1], cy = d->cdy[1];
+        int ok = (cx == 2 && cy == 2) || (cx == 2 && cy == 1) || (cx == 1 && cy == 2);
+        if (!wide)
+            ok |= (cx == 4 && cy == 1) || (cx == 4 && cy == 4);
+        if (ok)
+            return wide ? ORACLE_PIX_PLANAR16 : ORACLE_PIX_PLANAR8;
+    }
+    return 0;
+}
+
+static int parse_headers(Dec *d)
+{
+    const uint8_t *p = d->cs;
+    while (d->end - p >= 3 && rd16(p) != 0xFF4F)
+        p++;
+    if (d->end - p < 2 || rd16(p) != 0xFF4F)
+        return ORACLE_ERR_INVALID;
+    p += 2;
+    int cur_tile = -1, cur_tp = 0;
+    const uint8_t *tp_end = NULL;
+    for (;;) {
+        if (d->end - p < 2)
+            break;                                        /* "Missing EOC" is tolerated */
+        unsigned marker = rd16(p);
+        p += 2;
+        if (marker >= 0xFF30 && marker <= 0xFF3F)
+            continue;
+        if (marker == 0xFF93) {                           /* SOD */
+            if (!d->tile || cur_tile < 0 || tp_end < p)
+                return ORACLE_ERR_INVALID;
+            Tile *t = &d->tile[cur_tile];
+            t->part[cur_tp].p = p;
+            t->part[cur_tp].end = tp_end;
+            if (cur_tp + 1 > t->nparts)
+                t->nparts = cur_tp + 1;
+            p = tp_end;
+            continue;
+        }
+        if (marker == 0xFFD9)
+            break;
+        if (d->end - p < 2)
+            break;
+        int len = rd16(p);
+        if (len < 2 || d->end - p < len)
+            break;
+        const uint8_t *seg = p + 2, *segend = p + len;
+        int ret = 0;
+        switch (marker) {
+        case 0xFF51: {                                    /* SIZ */
+            if (d->ncomp)
+                return ORACLE_ERR_INVALID;
+            if (segend - seg < 36)
+                return ORACLE_ERR_INVALID;
+            unsigned rsiz = rd16(seg);
+            d->W = rd32(seg + 2); d->H = rd32(seg + 6); d->X0 = rd32(seg + 10); d->Y0 = rd32(seg + 14);
+            d->TW = rd32(seg + 18); d->TH = rd32(seg + 22); d->TX0 = rd32(seg + 26); d->TY0 = rd32(seg + 30);
+            int nc = rd16(seg + 34);
+            if (d->W <= 0 || d->H <= 0 || (int64_t)d->W * d->H > INT32_MAX)
+                return ORACLE_ERR_PATCH;
+            if (nc <= 0)
+                return ORACLE_ERR_INVALID;
+            if (nc > 4)
+                return ORACLE_ERR_PATCH;
+            if (rsiz == 3 || rsiz == 4)
+                return ORACLE_ERR_PATCH;                  /* D-Cinema profiles -> XYZ12: outside the HT path */
+            if (d->TX0 < 0 || d->TY0 < 0 || d->X0 < d->TX0 || d->Y0 < d->TY0 ||
+                d->TW + (int64_t)d->TX0 <= d->X0 || d->TH + (int64_t)d->TY0 <= d->Y0)
+                return ORACLE_ERR_INVALID;
+            if (d->X0 >= d->W || d->Y0 >= d->H || d->TW <= 0 || d->TH <= 0)
+                return ORACLE_ERR_INVALID;
+            if (segend - seg < 36 + 3 * nc)
+                return ORACLE_ERR_INVALID;
+            d->ncomp = nc;
+            for (int i = 0; i < nc; i++) {
+                unsigned x = seg[36 + 3 * i];
+                d->cbps[i] = (x & 0x7F) + 1;
+                d->precision = imax(d->precision, d->cbps[i]);
+                d->cdx[i] = seg[37 + 3 * i];
+                d->cdy[i] = seg[38 + 3 * i];
+                if (!d->cdx[i] || d->cdx[i] == 3 || d->cdx[i] > 4 || !d->cdy[i] || d->cdy[i] == 3 || d->cdy[i] > 4)
+                    return ORACLE_ERR_INVALID;
+            }
+            d->ntx = ceildiv(d->W - d->TX0, d->TW);
+            d->nty = ceildiv(d->H - d->TY0, d->TH);
+            if ((int64_t)d->ntx * d->nty * 14 > d->end - d->cs)
+                return ORACLE_ERR_EINVAL;
+            d->tile = calloc((size_t)d->ntx * d->nty, sizeof(Tile));
+            int ow = d->W - d->X0, oh = d->H - d->Y0;
+            d->out_w = ceildiv(ow, d->cdx[0]);
+            d->out_h = ceildiv(oh, d->cdy[0]);
+            for (int i = 1; i < nc; i++) {
+                d->out_w = imax(d->out_w, ceildiv(ow, d->cdx[i]));
+                d->out_h = imax(d->out_h, ceildiv(oh, d->cdy[i]));
+            }
+            d->pix = choose_pix(d);
+            if (!d->pix)
+                return ORACLE_ERR_PATCH;
+            seg += 36 + 3 * nc;
+            break;
+        }
+        case 0xFF50: {                                    /* CAP (jpeg2000dec.c:424-489) */
+            if (segend - seg < 6)
+                return ORACLE_ERR_INVALID;
+            uint32_t pcap = rd32(seg);
+            seg += 4;
+            unsigned ccap15 = 0;
+            d->isHT = (pcap >> 17) & 1;
+            for (int i = 0; i < 32; i++)
+                if ((pcap >> (31 - i)) & 1) {
+                    if (segend - seg < 2)
+                        return ORACLE_ERR_INVALID;
+                    if (i == 14)
+                        ccap15 = rd16(seg);
+                    seg += 2;
+                }
+            if (d->isHT) {
+                d->cap_b14 = (ccap15 >> 14) & 3;
+                if (d->cap_b14 == 2)
+                    return ORACLE_ERR_EINVAL;
+                if ((ccap15 >> 13) & 1)
+                    return ORACLE_ERR_PATCH;
+                d->cap_b05 = (ccap15 >> 5) & 1;
+                int P = ccap15 & 31, B = !P ? 8 : P < 20 ? P + 8 : P < 31 ? 4 * (P - 19) + 27 : 74;
+                if (B > 31)
+                    return ORACLE_ERR_PATCH;
+            }
+            break;
+        }
+        case 0xFF52: {                                    /* COD */
+            if (cur_tile >= 0)
+                return ORACLE_ERR_INVALID;                /* HOMOGENEOUS set: no tile-part COD (:2514-2520) */
+            if (segend - seg < 5)
+                return ORACLE_ERR_INVALID;
+            CodSty tmp;
+            memset(&tmp, 0, sizeof(tmp));
+            tmp.csty = seg[0];
+            tmp.prog = seg[1];
+            tmp.nlayers = rd16(seg + 2);
+            tmp.mct = seg[4];
+            if (tmp.mct && d->ncomp < 3)
+                return ORACLE_ERR_INVALID;
+            if ((ret = parse_cox(d, seg + 5, segend, &tmp)) < 0)
+                return ret;
+            tmp.init = 1;
+            for (int c = 0; c < d->ncomp; c++)
+                if (!d->had_coc[c])
+                    d->cod[c] = tmp;
+            seg += 10 + ((tmp.csty & 1) ? tmp.nres : 0);
+            break;
+        }
+        case 0xFF53: {                                    /* COC */
+            if (cur_tile >= 0)
+                return ORACLE_ERR_INVALID;
+            if (segend - seg < 2)
+                return ORACLE_ERR_INVALID;
+            int c = seg[0];
+            if (c >= d->ncomp)
+                return ORACLE_ERR_INVALID;
+            CodSty *cs = &d->cod[c];
+            int keep = cs->csty & 6;
+            cs->csty = seg[1] | keep;
+            if ((ret = parse_cox(d, seg + 2, segend, cs)) < 0)
+                return ret;
+            d->had_coc[c] = 1;
+            cs->init = 1;
+            seg += 7 + ((cs->csty & 1) ? cs->nres : 0);
+            break;
+        }
+        case 0xFF5C: {                                    /* QCD */
+            if (cur_tile >= 0)
+                return ORACLE_ERR_INVALID;
+            QntSty tmp;
+            memset(&tmp, 0, sizeof(tmp));
+            if ((ret = parse_qcx(seg, len - 2, &tmp)) < 0)
+                return ret;
+            for (int c = 0; c < d->ncomp; c++)
+                if (!d->had_qcc[c])
+                    d->qnt[c] = tmp;
+            seg = segend;
+            break;
+        }
+        case 0xFF5D: {                                    /* QCC */
+            if (cur_tile >= 0)
+                return ORACLE_ERR_INVALID;
+            if (segend - seg < 1)
+                return ORACLE_ERR_INVALID;
+            int c = seg[0];
+            if (c >= d->ncomp)
+                return ORACLE_ERR_INVALID;
+            d->had_qcc[c] = 1;
+            if ((ret = parse_qcx(seg + 1, len - 3, &d->qnt[c])) < 0)
+                return ret;
+            seg = segend;
+            break;
+        }
+        case 0xFF5E: {                                    /* RGN */
+            if (segend - seg < 3 || seg[1] != 0 || seg[0] >= d->ncomp)
+                return ORACLE_ERR_INVALID;
+            if (seg[2] > 30)
+                return ORACLE_ERR_PATCH;
+            if (cur_tile < 0)
+                d->roi[seg[0]] = seg[2];
+            else
+                d->tile[cur_tile].comp[seg[0]].roi_shift = seg[2];
+            seg += 3;
+            break;
+        }
+        case 0xFF90: {                                    /* SOT (:822-873) */
+            if (!d->tile || segend - seg < 8)
+                return ORACLE_ERR_INVALID;
+            int isot = rd16(seg);
+            if (isot >= d->ntx * d->nty)
+                return ORACLE_ERR_INVALID;
+            uint32_t psot = rd32(seg + 2);
+            int tpsot = seg[6];
+            int64_t left = d->end - (seg + 8);
+            if (!psot)
+                psot = (uint32_t)(left + len + 2);
+            if ((int64_t)psot > left + len + 2)
+                return ORACLE_ERR_INVALID;
+            if (tpsot >= 32)
+                return ORACLE_ERR_PATCH;
+            cur_tile = isot;
+            cur_tp = tpsot;
+            tp_end = seg + 8 + psot - len - 2;
+            seg += 8;
+            break;
+        }
+        case 0xFF5F: case 0xFF60: case 0xFF61:            /* POC, PPM, PPT */
+            return ORACLE_ERR_PATCH;
+        default:                                          /* COM, TLM, PLT, PLM, CRG, CPF, unknown: skipped */
+            seg = segend;
+            break;
+        }
+        if (seg != segend)
+            return -1;                                    /* declared length must equal what was consumed */
+        p = segend;
+    }
+    return 0;
+}
+
+/* ---- geometry -------------------------------------------------------------------------------------- */
+
+/* jpeg2000.c:214-272 -- same operations in the same types so that the float result is identical */
+static void band_stepsize(Band *b, const CodSty *c, const QntSty *q, int bandno, int gbandno, int r, int cbps)
+{
+    float f;
+    if (q->style == 0) {
+        f = 1;
+    } else {
+        union { uint32_t u; float f; } e;
+        e.u = (uint32_t)((cbps - q->expn[gbandno]) + 127) << 23;
+        f = e.f;
+        f *= q->mant[gbandno] / 2048.0 + 1.0;
+    }
+    if (c->transform != ORACLE_DWT53) {
+        int lband = 0;
+        switch (bandno + (r > 0)) {
+        case 1: case 2:
+            f *= 0.812893066115961f * 2;
+            lband = 1;
+            break;
+        case 3:
+            f *= 0.812893066115961f * 0.812893066115961f * 4;
+            break;
+        }
+        f *= pow(1.230174104914001f, 2 * (c->nres - r) + lband - 2);
+    }
+    if (f > (INT32_MAX >> 15))
+        f = 0;
+    b->fstep = f;
+    b->istep = (int)floorf(f * (1 << 15));
+}
+
+/* init_tile (jpeg2000dec.c:1016-1070) + ff_jpeg2000_init_component / init_band / init_prec
+ * (jpeg2000.c:274-577) */
+static int init_tile(Dec *d, int tileno)
+{
+    Tile *t = &d->tile[tileno];
+    const int tx = tileno % d->ntx, ty = tileno / d->ntx;
+    t->c.x0 = clip64((int64_t)tx * d->TW + d->TX0, d->X0, d->W);
+    t->c.x1 = clip64((int64_t)(tx + 1) * d->TW + d->TX0, d->X0, d->W);
+    t->c.y0 = clip64((int64_t)ty * d->TH + d->TY0, d->Y0, d->H);
+    t->c.y1 = clip64((int64_t)(ty + 1) * d->TH + d->TY0, d->Y0, d->H);
+
+    for (int c = 0; c < d->ncomp; c++) {
+        Comp *comp = &t->comp[c];
+        const CodSty *cs = &d->cod[c];
+        const QntSty *qs = &d->qnt[c];
+        if (!cs->init)
+            return ORACLE_ERR_INVALID;
+        if (d->isHT && !d->cap_b05 && !cs->transform)
+            return ORACLE_ERR_INVALID;                    /* 9/7 inside an HTREV set */
+        if (d->isHT && d->cap_b14 != (cs->cblk_style >> 6) && d->cap_b14 != 0)
+            return ORACLE_ERR_INVALID;
+        comp->c.x0 = ceildiv(t->c.x0, d->cdx[c]);
+        comp->c.x1 = ceildiv(t->c.x1, d->cdx[c]);
+        comp->c.y0 = ceildiv(t->c.y0, d->cdy[c]);
+        comp->c.y1 = ceildiv(t->c.y1, d->cdy[c]);
+        if (!comp->roi_shift)
+            comp->roi_shift = d->roi[c];
+        const int cw = comp->c.x1 - comp->c.x0, ch = comp->c.y1 - comp->c.y0;
+        if (cw > 32768 || ch > 32768)
+            return ORACLE_ERR_PATCH;
+        comp->data = calloc((size_t)cw * ch + 16, 4);
+        comp->res = calloc((size_t)cs->nres, sizeof(Res));
+        int gband = 0;
+        for (int r = 0; r < cs->nres; r++) {
+            Res *rl = &comp->res[r];
+            const int decl = cs->nres - r;               /* N_L - r + 1 */
+            rl->c.x0 = ceildivpow2(comp->c.x0, decl - 1);
+            rl->c.x1 = ceildivpow2(comp->c.x1, decl - 1);
+            rl->c.y0 = ceildivpow2(comp->c.y0, decl - 1);
+            rl->c.y1 = ceildivpow2(comp->c.y1, decl - 1);
+            rl->ppx = cs->ppx[r];
+            rl->ppy = cs->ppy[r];
+            rl->nbands = r == 0 ? 1 : 3;
+            rl->npx = rl->c.x1 == rl->c.x0 ? 0 : ceildivpow2(rl->c.x1, rl->ppx) - (rl->c.x0 >> rl->ppx);
+            rl->npy = rl->c.y1 == rl->c.y0 ? 0 : ceildivpow2(rl->c.y1, rl->ppy) - (rl->c.y0 >> rl->ppy);
+            for (int b = 0; b < rl->nbands; b++, gband++) {
+                Band *bd = &rl->band[b];
+                band_stepsize(bd, cs, qs, b, gband, r, d->cbps[c]);
+                int bppx, bppy;
+                if (r == 0) {
+                    bd->c = rl->c;
+                    bppx = rl->ppx;
+                    bppy = rl->ppy;
+                } else {
+                    const int xo = (b + 1) & 1, yo = ((b + 1) >> 1) & 1;
+                    bd->c.x0 = ceildivpow2(comp->c.x0 - (xo << (decl - 1)), decl);
+                    bd->c.x1 = ceildivpow2(comp->c.x1 - (xo << (decl - 1)), decl);
+                    bd->c.y0 = ceildivpow2(comp->c.y0 - (yo << (decl - 1)), decl);
+                    bd->c.y1 = ceildivpow2(comp->c.y1 - (yo << (decl - 1)), decl);
+                    bppx = rl->ppx - 1;
+                    bppy = rl->ppy - 1;
+                }
+                bd->l2cw = imin(cs->l2cw, bppx);
+                bd->l2ch = imin(cs->l2ch, bppy);
+                const int nprec = rl->npx * rl->npy;
+                bd->prec = calloc((size_t)imax(nprec, 1), sizeof(Prec));
+                for (int pn = 0; pn < nprec; pn++) {
+                    Prec *pr = &bd->prec[pn];
+                    Rect pc;
+                    pc.x0 = ((rl->c.x0 >> rl->ppx) + pn % rl->npx) * (1 << bppx);
+                    pc.y0 = ((rl->c.y0 >> rl->ppy) + pn / rl->npx) * (1 << bppy);
+                    pc.x1 = pc.x0 + (1 << bppx);
+                    pc.y1 = pc.y0 + (1 << bppy);
+                    pc.x0 = imax(pc.x0, bd->c.x0); pc.x1 = imin(pc.x1, bd->c.x1);
+                    pc.y0 = imax(pc.y0, bd->c.y0); pc.y1 = imin(pc.y1, bd->c.y1);
+                    pr->ncw = ceildivpow2(pc.x1, bd->l2cw) - (pc.x0 >> bd->l2cw);
+                    pr->nch = ceildivpow2(pc.y1, bd->l2ch) - (pc.y0 >> bd->l2ch);
+                    if (pr->ncw < 0 || pr->nch < 0)
+                        pr->ncw = pr->nch = 0;             /* empty intersection (the reference would fail to allocate) */
+                    pr->incl = tagtree_new(pr->ncw, pr->nch);
+                    pr->zb = tagtree_new(pr->ncw, pr->nch);
+                    const int n = pr->ncw * pr->nch;
+                    pr->cb = calloc((size_t)imax(n, 1), sizeof(Cblk));
+                    for (int k = 0; k < n; k++) {
+                        Cblk *cb = &pr->cb[k];
+                        int gx = ((pc.x0 >> bd->l2cw) << bd->l2cw) + ((k % pr->ncw) << bd->l2cw);
+                        int gy = ((pc.y0 >> bd->l2ch) << bd->l2ch) + ((k / pr->ncw) << bd->l2ch);
+                        cb->x0 = imax(gx, pc.x0); cb->x1 = imin(gx + (1 << bd->l2cw), pc.x1);
+                        cb->y0 = imax(gy, pc.y0); cb->y1 = imin(gy + (1 << bd->l2ch), pc.y1);
+                        /* Mallat placement: shift by the size of the next-lower resolution (jpeg2000.c:365-376) */
+                        if ((b + !!r) & 1) {
+                            int off = comp->res[r - 1].c.x1 - comp->res[r - 1].c.x0;
+                            cb->x0 += off; cb->x1 += off;
+                        }
+                        if ((b + !!r) & 2) {
+                            int off = comp->res[r - 1].c.y1 - comp->res[r - 1].c.y0;
+                            cb->y0 += off; cb->y1 += off;
+                        }
+                        cb->lblock = 3;
+                    }
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+static void free_tile(Dec *d, Tile *t)
+{
+    for (int c = 0; c < d->ncomp; c++) {
+        Comp *comp = &t->comp[c];
+        if (comp->res) {
+            for (int r = 0; r < d->cod[c].nres; r++)
+                for (int b = 0; b < comp->res[r].nbands; b++) {
+                    Band *bd = &comp->res[r].band[b];
+                    if (!bd->prec)
+                        continue;
+                    for (int pn = 0; pn < comp->res[r].npx * comp->res[r].npy; pn++) {
+                        Prec *pr = &bd->prec[pn];
+                        for (int k = 0; k < pr->ncw * pr->nch; k++)
+                            free(pr->cb[k].data);
+                        free(pr->cb);
+                        free(pr->incl);
+                        free(pr->zb);
+                    }
+                    free(bd->prec);
+                }
+            free(comp->res);
+        }
+        free(comp->data);
+        comp->res = NULL;
+        comp->data = NULL;
+    }
+}
+
+/* ---- tier-2 ---------------------------------------------------------------------------------------- */
+
+typedef struct PktState { Tile *t; int tp; } PktState;
+
+/* select_stream (jpeg2000dec.c:1110-1133): continue in the current tile-part, hop over exhausted ones */
+static void select_part(Dec *d, PktState *ps, int csty)
+{
+    Tile *t = ps->t;
+    d->bp = t->part[ps->tp].p;
+    d->bend = t->part[ps->tp].end;
+    while (d->bp >= d->bend && d->bit_index == 8 && ps->tp < 31) {
+        ps->tp++;
+        d->bp = t->part[ps->tp].p;
+        d->bend = t->part[ps->tp].end;
+        if (!d->bp) {
+            d->bp = d->bend = d->end;
+            break;
+        }
+    }
+    if (csty & 2)                                         /* SOP */
+        if (d->bend - d->bp >= 6 && rd32(d->bp) == 0xFF910004u)
+            d->bp += 6;
+}
+
+static int getnpasses(Dec *d)
+{
+    if (!hb_bits(d, 1)) return 1;
+    if (!hb_bits(d, 1)) return 2;
+    int n = hb_bits(d, 2);
+    if (n != 3) return 3 + n;
+    n = hb_bits(d, 5);
+    if (n != 31) return 6 + n;
+    return 37 + hb_bits(d, 7);
+}
+
+/* jpeg2000_decode_packet, HT-only paths (jpeg2000dec.c:1136-1542) */
+static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int precno, int layno,
+                         const int *expn, int nguard, int roi0)
+{
+    if (layno < rl->band[0].prec[precno].decoded_layers)
+        return 0;
+    rl->band[0].prec[precno].decoded_layers = layno + 1;
+    select_part(d, ps, cs->csty);
+
+    struct Inc { Cblk *cb; int nseg; int seg[8]; } *incs = NULL;
+    int ninc = 0, capinc = 0;
+    int ret = 0;
+
+    if (!hb_bits(d, 1)) {
+        hb_flush(d);
+        goto finish;
+    }
+    for (int b = 0; b < rl->nbands; b++) {
+        Band *bd = &rl->band[b];
+        if (bd->c.x0 == bd->c.x1 || bd->c.y0 == bd->c.y1)
+            continue;
+        Prec *pr = &bd->prec[precno];
+        for (int k = 0; k < pr->ncw * pr->nch; k++) {
+            Cblk *cb = &pr->cb[k];
+            int incl;
+            if (!cb->incl) {
+                cb->plhd = 1;
+                if (layno > 0)
+                    tagtree_decode(d, pr->incl + k, 1);
+                incl = tagtree_decode(d, pr->incl + k, layno + 1) == layno;
+                if (incl) {
+                    int zbp = tagtree_decode(d, pr->zb + k, 100);
+                    int v = expn[b] + nguard - 1 - (zbp - roi0);
+                    if (v < 0 || v > 30) {
+                        ret = ORACLE_ERR_INVALID;
+                        goto fail;
+                    }
+                    cb->incl = 1;
+                    cb->zbp = zbp;
+                    cb->lblock = 3;
+                }
+            } else {
+                incl = hb_bits(d, 1);
+            }
+            if (!incl)
+                continue;
+            int newpasses = getnpasses(d);
+            if (cb->npasses + newpasses >= 100) {
+                ret = ORACLE_ERR_PATCH;
+                goto fail;
+            }
+            int llen = 0;
+            while (hb_bits(d, 1))
+                llen++;
+            if (cb->lblock + llen + ilog2(newpasses) > 16) {
+                ret = ORACLE_ERR_PATCH;
+                goto fail;
+            }
+            cb->lblock += llen;
+            if (ninc == capinc) {
+                capinc = capinc ? 2 * capinc : 64;
+                incs = realloc(incs, sizeof(*incs) * capinc);
+            }
+            struct Inc *in = &incs[ninc++];
+            in->cb = cb;
+            in->nseg = 0;
+
+            int segment_passes, next_segment_passes = 0, bits;
+            unsigned segment_bytes = 0;
+            if (cb->plhd) {                               /* :1256-1340, non-MIXED */
+                int href = (cb->npasses + newpasses - 1) % 3;
+                segment_passes = newpasses - href;
+                int pass_bound = 2;
+                bits = cb->lblock;
+                if (segment_passes < 1) {
+                    segment_passes = newpasses;
+                    while (pass_bound <= segment_passes) { bits++; pass_bound += pass_bound; }
+                    segment_bytes = hb_bits(d, bits);
+                } else {
+                    while (pass_bound <= segment_passes) { bits++; pass_bound += pass_bound; }
+                    segment_bytes = hb_bits(d, bits);
+                    if (segment_bytes) {
+                        next_segment_passes = 2;
+                        cb->plhd = 0;
+                        cb->Lcup = segment_bytes;
+                    } else {
+                        segment_passes = newpasses;
+                        if (pass_bound <= segment_passes)
+                            for (;;) {
+                                bits++;
+                                pass_bound += pass_bound;
+                                segment_bytes = (segment_bytes << 1) + hb_bits(d, 1);
+                                if (pass_bound > segment_passes)
+                                    break;
+                            }
+                    }
+                }
+            } else {                                      /* :1341-1362 later contributions of an HT block */
+                segment_passes = cb->npasses % 3;
+                bits = 0;
+                if (segment_passes == 0) {
+                    segment_passes = 1;
+                    next_segment_passes = 2;
+                } else {
+                    segment_passes = newpasses > 1 ? 3 - segment_passes : 1;
+                    next_segment_passes = 1;
+                    bits = ilog2(segment_passes);
+                }
+                bits += cb->lblock;
+                segment_bytes = hb_bits(d, bits);
+                cb->Lref += segment_bytes;
+            }
+            cb->npasses = (cb->npasses + segment_passes) & 0xFF;
+            in->seg[in->nseg++] = segment_bytes;
+            newpasses -= segment_passes & 0xFF;
+            if (!cb->plhd) {                              /* :1404-1418 */
+                while (newpasses > 0) {
+                    segment_passes = newpasses > 1 ? next_segment_passes : 1;
+                    next_segment_passes = 3 - next_segment_passes;
+                    bits = cb->lblock + ilog2(segment_passes);
+                    segment_bytes = hb_bits(d, bits);
+                    newpasses -= segment_passes;
+                    cb->Lref += segment_bytes;
+                    cb->npasses = (cb->npasses + segment_passes) & 0xFF;
+                    if (in->nseg < 8)
+                        in->seg[in->nseg++] = segment_bytes;
+                }
+            } else {
+                while (newpasses > 0) {                   /* :1419-1438 with no termination modes */
+                    segment_bytes = hb_bits(d, cb->lblock);
+                    newpasses -= 1;
+                    cb->npasses = (cb->npasses + 1) & 0xFF;
+                    if (in->nseg < 8)
+                        in->seg[in->nseg++] = segment_bytes;
+                }
+            }
+        }
+    }
+    hb_flush(d);
+finish:
+    if (cs->csty & 4)                                     /* EPH */
+        if (d->bend - d->bp >= 2 && rd16(d->bp) == 0xFF92)
+            d->bp += 2;
+    for (int i = 0; i < ninc; i++) {
+        Cblk *cb = incs[i].cb;
+        for (int s = 0; s < incs[i].nseg; s++) {
+            int n = incs[i].seg[s];
+            if (d->bend - d->bp < n || cb->length + n > 65535) {
+                ret = ORACLE_ERR_INVALID;
+                goto fail;
+            }
+            if (cb->length + n + 8 > cb->cap) {
+                cb->cap = imax(2 * cb->cap, cb->length + n + 8);
+                cb->data = realloc(cb->data, (size_t)cb->cap);
+            }
+            memcpy(cb->data + cb->length, d->bp, (size_t)n);
+            d->bp += n;
+            cb->length += n;
+        }
+    }
+    ps->t->part[ps->tp].p = d->bp;
+    free(incs);
+    return 0;
+fail:
+    free(incs);
+    return ret;
+}
+
+/* does (x, y) on the reference grid start a precinct of this resolution?  (jpeg2000dec.c:1700-1722) */
+static int precinct_at(Dec *d, Tile *t, int c, int r, int x, int y, int cprl_rule)
+{
+    const CodSty *cs = &d->cod[c];
+    Res *rl = &t->comp[c].res[r];
+    const int red = cs->nres - 1 - r;
+    if (cprl_rule) {                                      /* the CPRL loop uses a weaker test (:1642-1648) */
+        int xc = x / d->cdx[c], yc = y / d->cdy[c];
+        if (yc % (1LL << (rl->ppy + red)) && y != t->c.y0)
+            return -1;
+        if (xc % (1LL << (rl->ppx + red)) && x != t->c.x0)
+            return -1;
+        unsigned px = (unsigned)(ceildivpow2(xc, red) >> rl->ppx) - (unsigned)(ceildivpow2(t->comp[c].c.x0, red) >> rl->ppx);
+        unsigned py = (unsigned)(ceildivpow2(yc, red) >> rl->ppy) - (unsigned)(ceildivpow2(t->comp[c].c.y0, red) >> rl->ppy);
+        if (px >= (unsigned)rl->npx || py >= (unsigned)rl->npy)
+            return -1;
+        return (int)(px + rl->npx * py);
+    }
+    int64_t trx0 = ((int64_t)t->c.x0 + ((int64_t)d->cdx[c] << red) - 1) / ((int64_t)d->cdx[c] << red);
+    int64_t try0 = ((int64_t)t->c.y0 + ((int64_t)d->cdy[c] << red) - 1) / ((int64_t)d->cdy[c] << red);
+    if (!(y % ((uint64_t)d->cdy[c] << (rl->ppy + red)) == 0 ||
+          (y == t->c.y0 && ((try0 << red) % (1LL << (red + rl->ppy))))))
+        return -1;
+    if (!(x % ((uint64_t)d->cdx[c] << (rl->ppx + red)) == 0 ||
+          (x == t->c.x0 && ((trx0 << red) % (1LL << (red + rl->ppx))))))
+        return -1;
+    unsigned px = (unsigned)(((int64_t)x + ((int64_t)d->cdx[c] << red) - 1) / ((int64_t)d->cdx[c] << red) >> rl->ppx);
+    unsigned py = (unsigned)(((int64_t)y + ((int64_t)d->cdy[c] << red) - 1) / ((int64_t)d->cdy[c] << red) >> rl->ppy);
+    px -= (unsigned)(ceildivpow2(t->comp[c].c.x0, red) >> rl->ppx);
+    py -= (unsigned)(ceildivpow2(t->comp[c].c.y0, red) >> rl->ppy);
+    if (px >= (unsigned)rl->npx || py >= (unsigned)rl->npy)
+        return -1;
+    return (int)(px + rl->npx * py);
+}
+
+#define PACKET(c, r, pn, l)                                                                           \
+    do {                                                                                              \
+        int e_ = decode_packet(d, &ps, &d->cod[c], &t->comp[c].res[r], pn, l,                         \
+                               d->qnt[c].expn + ((r) ? 3 * ((r) - 1) + 1 : 0), d->qnt[c].nguard,      \
+                               t->comp[0].roi_shift);                                                 \
+        if (e_ < 0)                                                                                   \
+            return e_;                                                                                \
+    } while (0)
+
+/* jpeg2000_decode_packets_po_iteration with the default (no POC) bounds (jpeg2000dec.c:1544-1869) */
+static int decode_packets(Dec *d, Tile *t)
+{
+    PktState ps = { t, 0 };
+    const int nlayers = d->cod[0].nlayers, C = d->ncomp;
+    int maxres = 0;
+    for (int c = 0; c < C; c++)
+        maxres = imax(maxres, d->cod[c].nres);
+    d->bit_index = 8;
+    switch (d->cod[0].prog) {
+    case 0: /* LRCP */
+        for (int l = 0; l < nlayers; l++)
+            for (int r = 0; r < maxres; r++)
+                for (int c = 0; c < C; c++)
+                    if (r < d->cod[c].nres)
+                        for (int pn = 0; pn < t->comp[c].res[r].npx * t->comp[c].res[r].npy; pn++)
+                            PACKET(c, r, pn, l);
+        break;
+    case 1: /* RLCP */
+        for (int r = 0; r < maxres; r++)
+            for (int l = 0; l < nlayers; l++)
+                for (int c = 0; c < C; c++)
+                    if (r < d->cod[c].nres)
+                        for (int pn = 0; pn < t->comp[c].res[r].npx * t->comp[c].res[r].npy; pn++)
+                            PACKET(c, r, pn, l);
+        break;
+    case 2: /* RPCL */
+        for (int r = 0; r < maxres; r++) {
+            int sx = 30, sy = 30;
+            for (int c = 0; c < C; c++)
+                if (r < d->cod[c].nres) {
+                    int red = d->cod[c].nres - 1 - r;
+                    sx = imin(sx, t->comp[c].res[r].ppx + red);
+                    sy = imin(sy, t->comp[c].res[r].ppy + red);
+                }
+            sx = 1 << sx;
+            sy = 1 << sy;
+            for (int y = t->c.y0; y < t->c.y1; y = (y / sy + 1) * sy)
+                for (int x = t->c.x0; x < t->c.x1; x = (x / sx + 1) * sx)
+                    for (int c = 0; c < C; c++) {
+                        if (r >= d->cod[c].nres)
+                            continue;
+                        int pn = precinct_at(d, t, c, r, x, y, 0);
+                        if (pn < 0)
+                            continue;
+                        for (int l = 0; l < nlayers; l++)
+                            PACKET(c, r, pn, l);
+                    }
+        }
+        break;
+    case 3: { /* PCRL */
+        int sx = 32, sy = 32;
+        for (int c = 0; c < C; c++)
+            for (int r = 0; r < d->cod[c].nres; r++) {
+                int red = d->cod[c].nres - 1 - r;
+                sx = imin(sx, t->comp[c].res[r].ppx + red);
+                sy = imin(sy, t->comp[c].res[r].ppy + red);
+            }
+        if (sx >= 31 || sy >= 31)
+            return ORACLE_ERR_PATCH;
+        sx = 1 << sx;
+        sy = 1 << sy;
+        for (int y = t->c.y0; y < t->c.y1; y = (y / sy + 1) * sy)
+            for (int x = t->c.x0; x < t->c.x1; x = (x / sx + 1) * sx)
+                for (int c = 0; c < C; c++)
+                    for (int r = 0; r < d->cod[c].nres; r++) {
+                        int pn = precinct_at(d, t, c, r, x, y, 0);
+                        if (pn < 0)
+                            continue;
+                        for (int l = 0; l < nlayers; l++)
+                            PACKET(c, r, pn, l);
+                    }
+        break;
+    }
+    case 4: /* CPRL */
+        for (int c = 0; c < C; c++) {
+            int sx = 32, sy = 32;
+            for (int r = 0; r < d->cod[c].nres; r++) {
+                int red = d->cod[c].nres - 1 - r;
+                sx = imin(sx, t->comp[c].res[r].ppx + red);
+                sy = imin(sy, t->comp[c].res[r].ppy + red);
+            }
+            if (sx >= 31 || sy >= 31)
+                return ORACLE_ERR_PATCH;
+            sx = 1 << sx;
+            sy = 1 << sy;
+            for (int y = t->c.y0; y < t->c.y1; y = (y / sy + 1) * sy)
+                for (int x = t->c.x0; x < t->c.x1; x = (x / sx + 1) * sx)
+                    for (int r = 0; r < d->cod[c].nres; r++) {
+                        int pn = precinct_at(d, t, c, r, x, y, 1);
+                        if (pn < 0)
+                            continue;
+                        for (int l = 0; l < nlayers; l++)
+                            PACKET(c, r, pn, l);
+                    }
+        }
+        break;
+    default:
+        break;
+    }
+    return 0;
+}
+
+/* ---- the hot path, per tile ------------------------------------------------------------------------- */
+
+/* D1-D3 (jpeg2000dec.c:2098-2181): t1 = sign-magnitude block, scatter into the component plane */
+static void dequantise(const int32_t *t1, int bw, int bh, void *plane, int W, int x, int y,
+                       int transform, const Band *band, int M_b)
+{
+    const int downshift = 31 - M_b;
+    if (transform == ORACLE_DWT97) {
+        float fscale = band->fstep;
+        fscale /= (float)(1 << downshift);
+        float *dst = plane;
+        for (int j = 0; j < bh; j++)
+            for (int i = 0; i < bw; i++) {
+                int32_t v = t1[j * bw + i];
+                if (v < 0)
+                    v = -(v & INT32_MAX);
+                dst[(size_t)W * (y + j) + x + i] = (float)v * fscale;
+            }
+    } else if (transform == ORACLE_DWT97_INT) {
+        float fscale = band->fstep;
+        fscale /= (float)(1 << downshift);
+        fscale *= (float)(1 << 6);
+        fscale *= (float)(1 << (16 + 8));
+        int scale = (int)(fscale + 0.5);
+        int32_t *dst = plane;
+        for (int j = 0; j < bh; j++)
+            for (int i = 0; i < bw; i++) {
+                int32_t v = t1[j * bw + i];
+                if (v < 0)
+                    v = -(v & INT32_MAX);
+                v = (v + (1 << 5)) >> 6;
+                int64_t m = v * (int64_t)scale;
+                /* RSHIFT(m, 16): libavutil/common.h, rounds half away from zero */
+                dst[(size_t)W * (y + j) + x + i] = (int32_t)(m > 0 ? (m + (1 << 15)) >> 16 : (m + (1 << 15) - 1) >> 16);
+            }
+    } else {
+        int32_t *dst = plane;
+        for (int j = 0; j < bh; j++)
+            for (int i = 0; i < bw; i++) {
+                int32_t v = t1[j * bw + i];
+                if (v < 0)
+                    v = -((v & INT32_MAX) >> downshift);
+                else
+                    v >>= downshift;
+                if (band->istep != 32768)
+                    v = (int32_t)((v * (int64_t)band->istep) / 65536);
+                dst[(size_t)W * (y + j) + x + i] = v;
+            }
+    }
+}
+
+/* H0 tile_codeblocks + M mct_decode + P1 write_frame */
+static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int strides[4])
+{
+    int32_t *t1 = malloc(sizeof(int32_t) * 4096);
+    for (int c = 0; c < d->ncomp; c++) {
+        Comp *comp = &t->comp[c];
+        const CodSty *cs = &d->cod[c];
+        const QntSty *qs = &d->qnt[c];
+        const int W = comp->c.x1 - comp->c.x0;
+        int coded = 0, subband = 0;
+        for (int r = 0; r < cs->nres; r++) {
+            Res *rl = &comp->res[r];
+            for (int b = 0; b < rl->nbands; b++, subband++) {
+                Band *bd = &rl->band[b];
+                const int M_b = qs->expn[subband] + qs->nguard - 1;
+                if (bd->c.x0 == bd->c.x1 || bd->c.y0 == bd->c.y1)
+                    continue;
+                if (M_b >= 31) {
+                    free(t1);
+                    return ORACLE_ERR_PATCH;
+                }
+                for (int pn = 0; pn < rl->npx * rl->npy; pn++) {
+                    Prec *pr = &bd->prec[pn];
+                    for (int k = 0; k < pr->ncw * pr->nch; k++) {
+                        Cblk *cb = &pr->cb[k];
+                        const int bw = cb->x1 - cb->x0, bh = cb->y1 - cb->y0;
+                        if (!(cs->cblk_style & 0x40)) {
+                            free(t1);
+                            return ORACLE_ERR_PATCH;      /* Part-1 MQ block: outside this path */
+                        }
+                        static const uint8_t none[8];
+                        int ret = oracle_ht_block(cb->data ? cb->data : none, cb->length, cb->npasses, cb->Lcup,
+                                                  cb->Lref, cb->zbp, bw, bh, M_b, comp->roi_shift,
+                                                  cs->cblk_style & 8, t1);
+                        if (!ret)
+                            continue;
+                        coded = 1;
+                        d->nblocks++;
+                        dequantise(t1, bw, bh, comp->data, W, cb->x0 - bd->c.x0, cb->y0 - bd->c.y0,
+                                   cs->transform, bd, M_b);
+                    }
+                }
+            }
+        }
+        if (coded) {
+            int border[4] = { comp->c.x0, comp->c.x1, comp->c.y0, comp->c.y1 };
+            oracle_idwt(cs->transform, border, cs->nres - 1, comp->data);
+        }
+    }
+    free(t1);
+
+    if (d->cod[0].mct) {                                  /* mct_decode (jpeg2000dec.c:2183-2209) */
+        int ok = 1;
+        for (int i = 1; i < 3; i++)
+            ok &= d->cod[0].transform == d->cod[i].transform && !memcmp(&t->comp[0].c, &t->comp[i].c, sizeof(Rect));
+        if (ok)
+            oracle_mct(d->cod[0].transform, t->comp[0].data, t->comp[1].data, t->comp[2].data,
+                       (t->comp[0].c.x1 - t->comp[0].c.x0) * (t->comp[0].c.y1 - t->comp[0].c.y0));
+    }
+
+    /* write_frame_8/16 (jpeg2000dec.c:2301-2366) */
+    const int planar = d->pix == ORACLE_PIX_PLANAR8 || d->pix == ORACLE_PIX_PLANAR16;
+    const int wide = d->precision > 8;
+    const int pixelsize = planar ? 1 : d->ncomp;
+    const int msb16 = d->pix == ORACLE_PIX_RGB48 || d->pix == ORACLE_PIX_RGBA64 || d->pix == ORACLE_PIX_GRAY16;
+    const int precision = !wide ? 8 : msb16 ? 16 : d->precision;
+    for (int c = 0; c < d->ncomp; c++) {
+        Comp *comp = &t->comp[c];
+        const int cbps = d->cbps[c];
+        const int plane = planar ? c : 0;
+        const int w = comp->c.x1 - ceildiv(d->X0, d->cdx[c]);
+        const int h = comp->c.y1 - ceildiv(d->Y0, d->cdy[c]);
+        const float *fp = comp->data;
+        const int32_t *ip = comp->data;
+        size_t k = 0;
+        for (int y = comp->c.y0 - ceildiv(d->Y0, d->cdy[c]); y < h; y++) {
+            uint8_t *line = planes[plane] + (size_t)y * strides[plane];
+            for (int x = comp->c.x0 - ceildiv(d->X0, d->cdx[c]); x < w; x++, k++) {
+                int val = d->cod[c].transform == ORACLE_DWT97 ? (int)lrintf(fp[k]) : ip[k];
+                val += 1 << (cbps - 1);
+                val = clip(val, 0, (1 << cbps) - 1);
+                val <<= precision - cbps;
+                size_t idx = (size_t)x * pixelsize + (planar ? 0 : c);
+                if (wide)
+                    ((uint16_t *)line)[idx] = (uint16_t)val;
+                else
+                    line[idx] = (uint8_t)val;
+            }
+        }
+    }
+    return 0;
+}
+
+static void free_dec(Dec *d)
+{
+    if (d->tile) {
+        for (int i = 0; i < d->ntx * d->nty; i++)
+            free_tile(d, &d->tile[i]);
+        free(d->tile);
+    }
+}
+
+int oracle_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint8_t *out, int64_t cap)
+{
+    Dec d;
+    memset(&d, 0, sizeof(d));
+    d.cs = cs;
+    d.end = cs + len;
+    d.bitexact = bitexact;
+    int ret = parse_headers(&d);
+    if (ret < 0)
+        goto end;
+    if (!d.tile || !d.ncomp) {
+        ret = ORACLE_ERR_INVALID;
+        goto end;
+    }
+    /* output planes, tightly packed */
+    {
+        const int bps = d.precision > 8 ? 2 : 1;
+        const int planar = d.pix == ORACLE_PIX_PLANAR8 || d.pix == ORACLE_PIX_PLANAR16;
+        uint8_t *planes[4] = { 0 };
+        int strides[4] = { 0 };
+        int64_t pos = 0;
+        if (!planar) {
+            strides[0] = d.out_w * d.ncomp * bps;
+            planes[0] = out;
+            pos = (int64_t)strides[0] * d.out_h;
+        } else {
+            for (int c = 0; c < d.ncomp; c++) {
+                int pw = c ? ceildiv(d.out_w, d.cdx[c]) : d.out_w, ph = c ? ceildiv(d.out_h, d.cdy[c]) : d.out_h;
+                strides[c] = pw * bps;
+                planes[c] = out + pos;
+                pos += (int64_t)strides[c] * ph;
+            }
+        }
+        if (pos > cap) {
+            ret = ORACLE_ERR_NOMEM;
+            goto end;
+        }
+        memset(out, 0, (size_t)pos);
+        for (int i = 0; i < d.ntx * d.nty; i++) {
+            if ((ret = init_tile(&d, i)) < 0)
+                goto end;
+            if ((ret = decode_packets(&d, &d.tile[i])) < 0)
+                goto end;
+        }
+        for (int i = 0; i < d.ntx * d.nty; i++)
+            if ((ret = decode_tile(&d, &d.tile[i], planes, strides)) < 0)
+                goto end;
+        info[0] = d.out_w;
+        info[1] = d.out_h;
+        info[2] = d.pix;
+        info[3] = pos;
+        info[4] = d.nblocks;
+        info[5] = d.ncomp;
+        info[6] = d.precision;
+        ret = 0;
+    }
+end:
+    free_dec(&d);
+    return ret;
+}
+
+/* ---- CPU baseline ("port") -------------------------------------------------------------------------- */
+typedef struct Job {
+    const uint8_t *const *cs;
+    const int64_t *len;
+    int nframes, first, step, reps, bitexact, errors;
+} Job;
+
+static void *bench_worker(void *arg)
+{
+    Job *j = arg;
+    int64_t info[8];
+    size_t cap = 0;
+    uint8_t *out = NULL;
+    for (int r = 0; r < j->reps; r++)
+        for (int i = j->first; i < j->nframes; i += j->step) {
+            if (!out) {
+                cap = 1u << 20;
+                out = malloc(cap);
+            }
+            int ret = oracle_decode(j->cs[i], j->len[i], j->bitexact, info, out, (int64_t)cap);
+            while (ret == ORACLE_ERR_NOMEM && cap < ((size_t)1 << 32)) {
+                cap *= 4;
+                out = realloc(out, cap);
+                ret = oracle_decode(j->cs[i], j->len[i], j->bitexact, info, out, (int64_t)cap);
+            }
+            if (ret < 0)
+                j->errors++;
+        }
+    free(out);
+    return NULL;
+}
+
+double oracle_decode_bench(const uint8_t *const *cs, const int64_t *len, int nframes, int threads,
+                           int reps, int bitexact)
+{
+    if (threads < 1) threads = 1;
+    if (threads > 256) threads = 256;
+    pthread_t th[256];
+    Job jobs[256];
+    struct timespec a, b;
+    clock_gettime(CLOCK_MONOTONIC, &a);
+    for (int t = 0; t < threads; t++) {
+        jobs[t] = (Job){ cs, len, nframes, t, threads, reps, bitexact, 0 };
+        pthread_create(&th[t], NULL, bench_worker, &jobs[t]);
+    }
+    int errors = 0;
+    for (int t = 0; t < threads; t++) {
+        pthread_join(th[t], NULL);
+        errors += jobs[t].errors;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &b);
+    if (errors)
+        return -1.0;
+    return (b.tv_sec - a.tv_sec) + 1e-9 * (b.tv_nsec - a.tv_nsec);
+}

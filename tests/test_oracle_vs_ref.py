@@ -1,0 +1,171 @@
+"""Pins the oracle (oracle/*.c restatement) against the UNMODIFIED reference compiled by oracle/Makefile
+(oracle/_ref/libj2kref.so).  Runs wherever that library exists (this container; the GPU box gets the
+prebuilt .so with the snapshot); elsewhere the golden fixtures in tests/golden do the same job
+(tests/test_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+import j2kgen
+from helpers import have_ref, ht_block, oracle, oracle_decode, ref, ref_decode, sm_to_int, ORACLE_PIX
+
+pytestmark = pytest.mark.skipif(not have_ref(), reason="oracle/_ref/libj2kref.so not built (needs /root/reference)")
+
+
+def test_ht_block_random_bytes_bit_exact():
+    """Damaged / random segments: same return code and same coefficients (zeros on error, quirk Q1)."""
+    rng = np.random.default_rng(1234)
+    decoded = 0
+    for _ in range(1500):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        Lcup = int(rng.integers(2, 300))
+        npasses = int(rng.choice([0, 1, 1, 2, 3, 3, 4, 5, 6, 7]))
+        Lref = int(rng.integers(0, 60)) if npasses % 3 != 1 else 0
+        data = bytearray(rng.integers(0, 256, Lcup + Lref, dtype=np.uint8).tobytes())
+        if rng.random() < 0.9:   # mostly valid suffix lengths, otherwise nearly everything stops at Scup
+            scup = int(rng.integers(2, min(Lcup, 200) + 1))
+            data[Lcup - 1] = scup >> 4
+            data[Lcup - 2] = (data[Lcup - 2] & 0xF0) | (scup & 15)
+        M_b = int(rng.integers(2, 28))
+        zbp = int(rng.integers(0, M_b))
+        vsc = int(rng.integers(0, 2))
+        ra, a = ht_block(ref().ref_ht_block, bytes(data), npasses, Lcup, Lref, zbp, w, h, M_b, 0, vsc)
+        rb, b = ht_block(oracle().oracle_ht_block, bytes(data), npasses, Lcup, Lref, zbp, w, h, M_b, 0, vsc)
+        assert ra == rb, (w, h, npasses, Lcup, Lref, zbp, M_b)
+        assert np.array_equal(a, b), (w, h, npasses, Lcup, Lref, zbp, M_b)
+        decoded += ra == 1
+    assert decoded > 100
+
+
+@pytest.mark.parametrize("npasses", [1, 2, 3])
+def test_ht_block_valid_segments(npasses):
+    """Dense valid code-blocks from the test encoder, all sizes incl. odd ones, with ROI shift."""
+    rng = np.random.default_rng(99 + npasses)
+    n = 0
+    for _ in range(250):
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        bits = int(rng.integers(1, 14))
+        coef = (rng.standard_normal((h, w)) * rng.uniform(0.3, 2 ** bits)).astype(np.int32)
+        if rng.random() < 0.3:
+            coef[rng.random((h, w)) < 0.8] = 0
+        refine = npasses > 1
+        if not np.any(np.abs(coef) >> refine):
+            continue
+        M_b = bits + 6
+        zbp = M_b - 1 - refine
+        vsc = int(rng.integers(0, 2))
+        roi = int(rng.choice([0, 0, 3]))
+        data, Lcup, Lref = j2kgen.encode_block(coef, npasses, bool(vsc), zbp + 1)
+        ra, a = ht_block(ref().ref_ht_block, data, npasses, Lcup, Lref, zbp, w, h, M_b, roi, vsc)
+        rb, b = ht_block(oracle().oracle_ht_block, data, npasses, Lcup, Lref, zbp, w, h, M_b, roi, vsc)
+        assert ra == 1 and rb == 1
+        assert np.array_equal(a, b)
+        if npasses == 1 and roi == 0:
+            assert np.array_equal(sm_to_int(a, M_b), coef)
+        n += 1
+    assert n > 150
+
+
+@pytest.mark.parametrize("dwt_type", [0, 1, 2])
+def test_idwt_bit_exact(dwt_type):
+    """W1-W4 on random borders (odd/even origins, lengths down to 1, 0..6 levels), compared as raw bits."""
+    rng = np.random.default_rng(7 + dwt_type)
+    for _ in range(200):
+        x0, y0 = int(rng.integers(0, 40)), int(rng.integers(0, 40))
+        w, h = int(rng.integers(1, 48)), int(rng.integers(1, 48))
+        levels = int(rng.integers(0, 7))
+        border = np.array([x0, x0 + w, y0, y0 + h], np.int32)
+        if dwt_type == 0:
+            a = (rng.standard_normal(w * h) * 1000).astype(np.float32)
+        else:
+            a = rng.integers(-(1 << 20), 1 << 20, w * h).astype(np.int32)
+        b = a.copy()
+        assert ref().ref_idwt(dwt_type, border.ctypes.data, levels, a.ctypes.data) == 0
+        assert oracle().oracle_idwt(dwt_type, border.ctypes.data, levels, b.ctypes.data) == 0
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (x0, y0, w, h, levels)
+
+
+@pytest.mark.parametrize("dwt_type", [0, 1, 2])
+def test_mct_bit_exact(dwt_type):
+    rng = np.random.default_rng(17 + dwt_type)
+    n = 4099
+    if dwt_type == 0:
+        p = [(rng.standard_normal(n) * 3000).astype(np.float32) for _ in range(3)]
+    else:
+        p = [rng.integers(-(1 << 30), 1 << 30, n).astype(np.int32) for _ in range(3)]
+    q = [x.copy() for x in p]
+    ref().ref_mct(dwt_type, *[x.ctypes.data for x in p], n)
+    oracle().oracle_mct(dwt_type, *[x.ctypes.data for x in q], n)
+    for a, b in zip(p, q):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+STREAMS = [
+    dict(w=64, h=64, nc=1, bd=8, levels=0),
+    dict(w=256, h=256, nc=1, bd=8, levels=3, reversible=False, mct=False, base_step=1.0),
+    dict(w=256, h=200, nc=3, bd=10, levels=5, reversible=False, base_step=2.0),
+    dict(w=250, h=131, nc=3, bd=12, levels=5, tile=(128, 64)),
+    dict(w=250, h=131, nc=3, bd=12, levels=5, offset=(3, 5)),
+    dict(w=250, h=131, nc=3, bd=12, levels=4, offset=(13, 7), tile=(100, 50)),
+    dict(w=250, h=131, nc=3, bd=10, levels=4, offset=(13, 7), tile=(100, 50), reversible=False, base_step=0.5),
+    dict(w=256, h=256, nc=3, bd=12, levels=3, cblk=(32, 32), precincts=[(7, 7), (8, 8)], prog=2),
+    dict(w=256, h=256, nc=3, bd=12, levels=3, cblk=(32, 32), precincts=[(6, 6), (7, 7)], prog=3),
+    dict(w=256, h=256, nc=3, bd=12, levels=3, cblk=(32, 32), precincts=[(6, 6), (7, 7)], prog=4),
+    dict(w=256, h=256, nc=3, bd=12, levels=3, cblk=(32, 32), precincts=[(6, 6), (7, 7)], prog=1, sop=True, eph=True),
+    dict(w=256, h=256, nc=3, bd=12, levels=3, cblk=(32, 32), npasses=3),
+    dict(w=255, h=253, nc=3, bd=12, levels=3, cblk=(32, 32), npasses=3, vsc=True),
+    dict(w=255, h=253, nc=1, bd=16, levels=5, npasses=2),
+    dict(w=300, h=200, nc=1, bd=16, levels=5, cblk=(128, 32)),
+    dict(w=300, h=200, nc=1, bd=8, levels=5, cblk=(4, 4)),
+    dict(w=300, h=200, nc=2, bd=8, levels=5, cblk=(1024, 4), mct=False),
+    dict(w=300, h=200, nc=4, bd=12, levels=2, cblk=(16, 16)),
+    dict(w=1, h=1, nc=1, bd=8, levels=0),
+    dict(w=3, h=2, nc=1, bd=8, levels=2),
+    dict(w=17, h=1, nc=3, bd=9, levels=5),
+    dict(w=1, h=33, nc=1, bd=12, levels=3),
+]
+
+
+@pytest.mark.parametrize("cfg", STREAMS, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
+def test_frame_decode_bit_exact(cfg):
+    """Whole codestreams: oracle pixels == reference pixels, float 9/7 path included (compared as bytes),
+    and the integer 9/7 path the reference takes under AV_CODEC_FLAG_BITEXACT."""
+    cfg = dict(cfg)
+    w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=11)
+    p = j2kgen.EncParams(**cfg)
+    cs = j2kgen.encode(planes, bd, p)
+    for bitexact in ((0,) if p.reversible else (0, 1)):
+        r1, info1, out1, name = ref_decode(cs, bitexact)
+        r2, info2, out2 = oracle_decode(cs, bitexact)
+        assert r1 == 0 and r2 == 0
+        assert info1[:2] == info2[:2]
+        assert ORACLE_PIX[info2[2]] == name
+        assert np.array_equal(out1, out2)
+    if p.reversible and p.npasses == 1:
+        bps = 2 if bd > 8 else 1
+        img = out2.view(np.uint16 if bps == 2 else np.uint8).reshape(h, w, nc)
+        shift = (16 - bd) if (bps == 2 and nc != 2) else 0
+        assert np.array_equal(img >> shift, np.stack(planes, -1))
+
+
+def test_error_codes_match():
+    """Truncated / damaged codestreams: both fail, or both succeed with identical pixels."""
+    planes = j2kgen.synth_image(96, 80, 3, 12, seed=3)
+    cs = j2kgen.encode(planes, 12, j2kgen.EncParams(levels=3, cblk=(32, 32)))
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        bad = bytearray(cs)
+        mode = rng.integers(0, 3)
+        if mode == 0:
+            bad = bad[: int(rng.integers(2, len(bad)))]
+        elif mode == 1:
+            for _ in range(3):
+                bad[int(rng.integers(110, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            pos = int(rng.integers(110, len(bad) - 8))
+            bad[pos:pos + 8] = rng.integers(0, 256, 8, dtype=np.uint8).tobytes()
+        r1, _, out1, _ = ref_decode(bytes(bad))
+        r2, _, out2 = oracle_decode(bytes(bad))
+        assert (r1 == 0) == (r2 == 0), (mode, r1, r2)
+        if r1 == 0:
+            assert np.array_equal(out1, out2)
