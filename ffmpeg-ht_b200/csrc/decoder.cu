@@ -1,0 +1,690 @@
+/*
+ * decoder.cu -- the C ABI (include/b200j2k.h): decoder contexts, slots, staging and the launch sequence.
+ *
+ * One b200j2k_decoder corresponds to one AVCodecContext of the reference (jpeg2000_decode_init /
+ * jpeg2000_decode_frame, libavcodec/jpeg2000dec.c:2807-2908).  Per slot: a CUDA stream, one pinned
+ * staging blob (descriptor tables + codestream bytes), device buffers that only grow, and the queue
+ *     H2D blob -> ht_decode (cleanup-only blocks) -> ht_decode (blocks with refinement passes)
+ *              -> idwt levels -> fused last level + MCT + pack -> D2H picture.
+ * Nothing here falls back to the CPU: without a device every call returns B200J2K_ERR_DEVICE.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "../../include/b200j2k.h"
+#include "j2k_kernels.h"
+#include "j2k_parse.h"
+#include "j2k_plan.h"
+
+using namespace b200j2k;
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap)
+            return 0;
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 4096;
+        if (cudaMalloc(&p, want) != cudaSuccess) {
+            cudaGetLastError();
+            return B200J2K_ERR_NOMEM;
+        }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostBuf {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n)
+    {
+        if (n <= cap)
+            return 0;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 4096;
+        if (cudaHostAlloc((void **)&p, want, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            return B200J2K_ERR_NOMEM;
+        }
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    Parser parser;
+    HostBuf stage;          /* pinned: tables + bytes */
+    HostBuf out_stage;      /* pinned: picture when the caller's planes are pageable */
+    DevBuf d_blob, d_coefA, d_coefB, d_coefC, d_picture, d_status;
+    /* offsets inside the blob */
+    size_t off_cblk = 0, off_bands = 0, off_tcs = 0, off_groups = 0, off_order = 0, off_bytes = 0, blob_bytes = 0;
+    int n_plain = 0, n_refine = 0;
+    int maxL_plain = 0, maxL_refine = 0;
+    bool busy = false, staged = false;
+    int launches = 0;
+    /* pending output */
+    uint8_t *dst[4] = { nullptr, nullptr, nullptr, nullptr };
+    int dst_linesize[4] = { 0, 0, 0, 0 };
+    bool direct = false;
+    uint64_t seq = 0;
+};
+
+}  // namespace
+
+struct b200j2k_decoder {
+    int device = 0;
+    int flags = 0;
+    std::vector<Slot> slots;
+    uint64_t seq = 0;
+};
+
+namespace {
+
+int device_ok()
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+void fill_info(const Parser &p, b200j2k_frame_info *info)
+{
+    if (!info)
+        return;
+    memset(info, 0, sizeof(*info));
+    info->width = p.hdr.out_w;
+    info->height = p.hdr.out_h;
+    info->pix_fmt = p.hdr.pix;
+    info->ncomponents = p.hdr.ncomp;
+    info->precision = p.hdr.precision;
+    info->lossless = p.hdr.lossless;
+    info->profile = p.hdr.rsiz;
+    info->nplanes = p.nplanes;
+    for (int i = 0; i < 4; i++) {
+        info->plane_width[i] = p.plane_w[i];
+        info->plane_height[i] = p.plane_h[i];
+        info->plane_row_bytes[i] = p.plane_row_bytes[i];
+    }
+    info->ntiles = p.hdr.ntx * p.hdr.nty;
+    info->ncodeblocks = (int32_t)p.cblk.size();
+    info->bytes_consumed = p.consumed;
+}
+
+/* host parse + build the staging blob + H2D */
+int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size, b200j2k_frame_info *info)
+{
+    int ret = s.parser.parse(pkt, size, dec->flags, false);
+    if (ret < 0)
+        return ret;
+    Parser &p = s.parser;
+    fill_info(p, info);
+    const size_t ncb = p.cblk.size();
+    /* split the descriptor list: cleanup-only (and empty) blocks vs blocks with refinement passes */
+    std::vector<uint32_t> order(ncb);
+    s.n_plain = s.n_refine = 0;
+    s.maxL_plain = s.maxL_refine = 0;
+    {
+        size_t a = 0, b = ncb;
+        for (size_t i = 0; i < ncb; i++) {
+            const CblkDesc &d = p.cblk[i];
+            const bool refine = d.npasses && (d.npasses % 3) != 1;
+            if (refine) {
+                order[--b] = (uint32_t)i;
+                if (d.Lcup > s.maxL_refine) s.maxL_refine = d.Lcup;
+            } else {
+                order[a++] = (uint32_t)i;
+                if (d.npasses && d.Lcup > s.maxL_plain) s.maxL_plain = d.Lcup;
+            }
+        }
+        s.n_plain = (int)a;
+        s.n_refine = (int)(ncb - a);
+    }
+    size_t off = 0;
+    s.off_cblk = off;   off = align_up(off + ncb * sizeof(CblkDesc), 256);
+    s.off_bands = off;  off = align_up(off + p.bands.size() * sizeof(BandDesc), 256);
+    s.off_tcs = off;    off = align_up(off + p.tcs.size() * sizeof(TileCompDesc), 256);
+    s.off_groups = off; off = align_up(off + p.groups.size() * sizeof(PackGroup), 256);
+    s.off_order = off;  off = align_up(off + ncb * sizeof(uint32_t), 256);
+    s.off_bytes = off;  off = align_up(off + (size_t)size + p.extra.size() + 64, 256);
+    s.blob_bytes = off;
+    if ((ret = s.stage.ensure(off)) < 0)
+        return ret;
+    uint8_t *h = s.stage.p;
+    memcpy(h + s.off_cblk, p.cblk.data(), ncb * sizeof(CblkDesc));
+    memcpy(h + s.off_bands, p.bands.data(), p.bands.size() * sizeof(BandDesc));
+    memcpy(h + s.off_tcs, p.tcs.data(), p.tcs.size() * sizeof(TileCompDesc));
+    memcpy(h + s.off_groups, p.groups.data(), p.groups.size() * sizeof(PackGroup));
+    memcpy(h + s.off_order, order.data(), ncb * sizeof(uint32_t));
+    memcpy(h + s.off_bytes, pkt, (size_t)size);
+    if (!p.extra.empty())
+        memcpy(h + s.off_bytes + size, p.extra.data(), p.extra.size());
+    memset(h + s.off_bytes + size + p.extra.size(), 0, 64);
+
+    if ((ret = s.d_blob.ensure(off)) < 0) return ret;
+    if ((ret = s.d_coefA.ensure(p.coef_elems * 4 + 256)) < 0) return ret;
+    if (p.max_levels >= 2) {
+        if ((ret = s.d_coefB.ensure(p.ll_elems * 4 + 256)) < 0) return ret;
+        if ((ret = s.d_coefC.ensure(p.ll_elems * 4 + 256)) < 0) return ret;
+    }
+    if ((ret = s.d_picture.ensure(p.picture_bytes + 256)) < 0) return ret;
+    if ((ret = s.d_status.ensure(ncb * 4 + 256)) < 0) return ret;
+    if (cudaMemcpyAsync(s.d_blob.p, h, off, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    s.staged = true;
+    return 0;
+}
+
+/* queue every kernel of the frame on the slot's stream */
+int run_kernels(Slot &s)
+{
+    Parser &p = s.parser;
+    const uint8_t *blob = (const uint8_t *)s.d_blob.p;
+    const CblkDesc *d_cblk = (const CblkDesc *)(blob + s.off_cblk);
+    const BandDesc *d_bands = (const BandDesc *)(blob + s.off_bands);
+    const TileCompDesc *d_tcs = (const TileCompDesc *)(blob + s.off_tcs);
+    const PackGroup *d_groups = (const PackGroup *)(blob + s.off_groups);
+    const uint32_t *d_order = (const uint32_t *)(blob + s.off_order);
+    const uint8_t *d_bytes = blob + s.off_bytes;
+    int launches = 0, r;
+    r = launch_ht_decode(s.stream, false, d_cblk, d_order, s.n_plain, d_bytes, d_bands, s.d_coefA.p,
+                         (int32_t *)s.d_status.p, s.maxL_plain, (int)p.max_w, (int)p.max_h);
+    if (r < 0) return B200J2K_ERR_DEVICE;
+    launches += r;
+    r = launch_ht_decode(s.stream, true, d_cblk, d_order + s.n_plain, s.n_refine, d_bytes, d_bands, s.d_coefA.p,
+                         (int32_t *)s.d_status.p, s.maxL_refine, (int)p.max_w, (int)p.max_h);
+    if (r < 0) return B200J2K_ERR_DEVICE;
+    launches += r;
+    IdwtFrame f;
+    memset(&f, 0, sizeof(f));
+    f.d_tcs = d_tcs;
+    f.d_groups = d_groups;
+    f.h_tcs = p.tcs.data();
+    f.h_groups = p.groups.data();
+    f.ntcs = (int)p.tcs.size();
+    f.ngroups = (int)p.groups.size();
+    f.coefA = s.d_coefA.p;
+    f.coefB = s.d_coefB.p;
+    f.coefC = s.d_coefC.p;
+    f.picture = (uint8_t *)s.d_picture.p;
+    for (int i = 0; i < 4; i++) {
+        f.plane_off[i] = p.plane_off[i];
+        f.plane_row_bytes[i] = p.plane_row_bytes[i];
+    }
+    r = launch_idwt_frame(s.stream, f);
+    if (r < 0) return B200J2K_ERR_DEVICE;
+    launches += r;
+    s.launches = launches;
+    return 0;
+}
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+int queue_output(Slot &s, uint8_t *const data[4], const int linesize[4])
+{
+    Parser &p = s.parser;
+    bool direct = true;
+    for (int i = 0; i < p.nplanes; i++) {
+        if (!data[i] || linesize[i] < p.plane_row_bytes[i])
+            return B200J2K_ERR_EINVAL;
+        direct = direct && is_pinned(data[i]);
+        s.dst[i] = data[i];
+        s.dst_linesize[i] = linesize[i];
+    }
+    s.direct = direct;
+    const uint8_t *pic = (const uint8_t *)s.d_picture.p;
+    if (direct) {
+        for (int i = 0; i < p.nplanes; i++)
+            if (cudaMemcpy2DAsync(data[i], (size_t)linesize[i], pic + p.plane_off[i], (size_t)p.plane_row_bytes[i],
+                                  (size_t)p.plane_row_bytes[i], (size_t)p.plane_h[i], cudaMemcpyDeviceToHost,
+                                  s.stream) != cudaSuccess)
+                return B200J2K_ERR_DEVICE;
+    } else {
+        int ret = s.out_stage.ensure(p.picture_bytes);
+        if (ret < 0)
+            return ret;
+        if (cudaMemcpyAsync(s.out_stage.p, pic, p.picture_bytes, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
+            return B200J2K_ERR_DEVICE;
+    }
+    return 0;
+}
+
+int finish_slot(Slot &s)
+{
+    if (!s.busy)
+        return 0;
+    cudaError_t e = cudaStreamSynchronize(s.stream);
+    s.busy = false;
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return B200J2K_ERR_DEVICE;
+    }
+    if (!s.direct && s.dst[0]) {
+        Parser &p = s.parser;
+        for (int i = 0; i < p.nplanes; i++) {
+            const uint8_t *src = s.out_stage.p + p.plane_off[i];
+            for (int y = 0; y < p.plane_h[i]; y++)
+                memcpy(s.dst[i] + (size_t)y * s.dst_linesize[i], src + (size_t)y * p.plane_row_bytes[i],
+                       (size_t)p.plane_row_bytes[i]);
+        }
+    }
+    s.dst[0] = nullptr;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200j2k_device_count(void) { return device_ok(); }
+
+int b200j2k_create(b200j2k_decoder **out, int device, int slots, int flags)
+{
+    if (!out)
+        return B200J2K_ERR_EINVAL;
+    *out = nullptr;
+    const int n = device_ok();
+    if (n <= 0 || device < 0 || device >= n)
+        return B200J2K_ERR_DEVICE;
+    if (slots < 1) slots = 1;
+    if (slots > 64) slots = 64;
+    if (cudaSetDevice(device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    b200j2k_decoder *d = new (std::nothrow) b200j2k_decoder();
+    if (!d)
+        return B200J2K_ERR_NOMEM;
+    d->device = device;
+    d->flags = flags;
+    d->slots.resize(slots);
+    for (auto &s : d->slots) {
+        if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming) != cudaSuccess) {
+            b200j2k_destroy(d);
+            return B200J2K_ERR_DEVICE;
+        }
+    }
+    *out = d;
+    return 0;
+}
+
+void b200j2k_destroy(b200j2k_decoder *d)
+{
+    if (!d)
+        return;
+    cudaSetDevice(d->device);
+    for (auto &s : d->slots) {
+        if (s.stream)
+            cudaStreamSynchronize(s.stream);
+        s.stage.release();
+        s.out_stage.release();
+        s.d_blob.release(); s.d_coefA.release(); s.d_coefB.release(); s.d_coefC.release();
+        s.d_picture.release(); s.d_status.release();
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    delete d;
+}
+
+int b200j2k_probe(const uint8_t *pkt, int64_t pkt_size, int flags, b200j2k_frame_info *info)
+{
+    Parser p;
+    int ret = p.parse(pkt, pkt_size, flags, true);
+    if (ret < 0)
+        return ret;
+    fill_info(p, info);
+    return 0;
+}
+
+int b200j2k_submit(b200j2k_decoder *d, const uint8_t *pkt, int64_t pkt_size, uint8_t *const data[4],
+                   const int linesize[4], b200j2k_frame_info *info)
+{
+    if (!d || !pkt || !data || !linesize)
+        return B200J2K_ERR_EINVAL;
+    if (cudaSetDevice(d->device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    /* pick a free slot, else the oldest busy one */
+    int pick = -1;
+    for (size_t i = 0; i < d->slots.size(); i++)
+        if (!d->slots[i].busy) { pick = (int)i; break; }
+    if (pick < 0) {
+        pick = 0;
+        for (size_t i = 1; i < d->slots.size(); i++)
+            if (d->slots[i].seq < d->slots[pick].seq) pick = (int)i;
+        int r = finish_slot(d->slots[pick]);
+        if (r < 0)
+            return r;
+    }
+    Slot &s = d->slots[pick];
+    int ret = stage_frame(d, s, pkt, pkt_size, info);
+    if (ret < 0)
+        return ret;
+    if ((ret = run_kernels(s)) < 0)
+        return ret;
+    if ((ret = queue_output(s, data, linesize)) < 0)
+        return ret;
+    s.busy = true;
+    s.seq = ++d->seq;
+    return pick;
+}
+
+int b200j2k_wait(b200j2k_decoder *d, int slot)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size())
+        return B200J2K_ERR_EINVAL;
+    if (cudaSetDevice(d->device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    return finish_slot(d->slots[slot]);
+}
+
+int64_t b200j2k_decode(b200j2k_decoder *d, const uint8_t *pkt, int64_t pkt_size, uint8_t *const data[4],
+                       const int linesize[4], b200j2k_frame_info *info)
+{
+    b200j2k_frame_info local;
+    int slot = b200j2k_submit(d, pkt, pkt_size, data, linesize, &local);
+    if (slot < 0)
+        return slot;
+    int r = b200j2k_wait(d, slot);
+    if (r < 0)
+        return r;
+    if (info)
+        *info = local;
+    return local.bytes_consumed;
+}
+
+int b200j2k_stage(b200j2k_decoder *d, int slot, const uint8_t *pkt, int64_t pkt_size, b200j2k_frame_info *info)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size())
+        return B200J2K_ERR_EINVAL;
+    if (cudaSetDevice(d->device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    Slot &s = d->slots[slot];
+    int r = finish_slot(s);
+    if (r < 0)
+        return r;
+    r = stage_frame(d, s, pkt, pkt_size, info);
+    if (r < 0)
+        return r;
+    return cudaStreamSynchronize(s.stream) == cudaSuccess ? 0 : B200J2K_ERR_DEVICE;
+}
+
+int b200j2k_run_staged(b200j2k_decoder *d, int slot)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size() || !d->slots[slot].staged)
+        return B200J2K_ERR_EINVAL;
+    if (cudaSetDevice(d->device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    return run_kernels(d->slots[slot]);
+}
+
+int b200j2k_sync(b200j2k_decoder *d, int slot)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size())
+        return B200J2K_ERR_EINVAL;
+    cudaError_t e = cudaStreamSynchronize(d->slots[slot].stream);
+    if (e != cudaSuccess) {
+        fprintf(stderr, "b200j2k: CUDA error: %s\n", cudaGetErrorString(e));
+        return B200J2K_ERR_DEVICE;
+    }
+    return 0;
+}
+
+int b200j2k_fetch(b200j2k_decoder *d, int slot, uint8_t *const data[4], const int linesize[4])
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size() || !d->slots[slot].staged)
+        return B200J2K_ERR_EINVAL;
+    if (cudaSetDevice(d->device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    Slot &s = d->slots[slot];
+    int r = queue_output(s, data, linesize);
+    if (r < 0)
+        return r;
+    s.busy = true;
+    return finish_slot(s);
+}
+
+void *b200j2k_slot_stream(b200j2k_decoder *d, int slot)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size())
+        return nullptr;
+    return (void *)d->slots[slot].stream;
+}
+
+void *b200j2k_slot_output(b200j2k_decoder *d, int slot, int64_t *bytes)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size())
+        return nullptr;
+    if (bytes)
+        *bytes = (int64_t)d->slots[slot].parser.picture_bytes;
+    return d->slots[slot].d_picture.p;
+}
+
+int b200j2k_slot_launches(b200j2k_decoder *d, int slot)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size())
+        return 0;
+    return d->slots[slot].launches;
+}
+
+/* ---- stage-level entry points -------------------------------------------------------------------------- */
+int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const int32_t *par, int n,
+                      int32_t *out, int32_t *status)
+{
+    if (device_ok() <= 0 || cudaSetDevice(device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    if (n <= 0)
+        return 0;
+    std::vector<CblkDesc> descs(n);
+    std::vector<uint32_t> order(n);
+    BandDesc band;
+    memset(&band, 0, sizeof(band));
+    band.i_stepsize = 32768;
+    size_t total = 0;
+    int maxw = 1, maxh = 1, maxL[2] = { 0, 0 };
+    size_t a = 0, b = n;
+    for (int i = 0; i < n; i++) {
+        const int32_t *q = par + 10 * i;
+        CblkDesc &d = descs[i];
+        memset(&d, 0, sizeof(d));
+        d.npasses = (uint8_t)q[0];
+        d.Lcup = (uint16_t)q[1];
+        d.Lref = (uint16_t)q[2];
+        d.zbp = (uint8_t)q[3];
+        d.w = (uint16_t)q[4];
+        d.h = (uint16_t)q[5];
+        d.M_b = 31;                  /* downshift 0 + identity step: the raw sign-magnitude word survives */
+        d.roi_shift = 0;
+        d.flags = (uint8_t)((q[8] ? 1 : 0) | (3 << 1));   /* dequant mode 3 = raw (see below) */
+        d.data_off = (uint32_t)q[9];
+        d.length = (uint32_t)(q[1] + q[2]);
+        d.dst_off = (uint32_t)total;
+        d.dst_stride = d.w;
+        total += (size_t)d.w * d.h;
+        if (d.w > maxw) maxw = d.w;
+        if (d.h > maxh) maxh = d.h;
+        const bool refine = d.npasses && (d.npasses % 3) != 1;
+        if (refine) order[--b] = (uint32_t)i; else order[a++] = (uint32_t)i;
+        if (d.npasses && d.Lcup > maxL[refine]) maxL[refine] = d.Lcup;
+        if ((int64_t)d.data_off + d.length > data_size)
+            return B200J2K_ERR_EINVAL;
+    }
+    /* the stage-level entry wants t1->data, i.e. the sample BEFORE dequantisation but after the ROI shift:
+     * run with M_b/roi of the caller and an identity "dequant" (mode 3, handled as raw in the kernel) */
+    for (int i = 0; i < n; i++) {
+        descs[i].M_b = (uint8_t)par[10 * i + 6];
+        descs[i].roi_shift = (uint8_t)par[10 * i + 7];
+    }
+    uint8_t *d_bytes = nullptr;
+    CblkDesc *d_descs = nullptr;
+    uint32_t *d_order = nullptr, *d_out = nullptr;
+    BandDesc *d_band = nullptr;
+    int32_t *d_status = nullptr;
+    int ret = 0;
+    cudaStream_t st = nullptr;
+    if (cudaStreamCreate(&st) != cudaSuccess) return B200J2K_ERR_DEVICE;
+    if (cudaMalloc(&d_bytes, (size_t)data_size + 64) != cudaSuccess || cudaMalloc(&d_descs, n * sizeof(CblkDesc)) != cudaSuccess ||
+        cudaMalloc(&d_order, n * 4) != cudaSuccess || cudaMalloc(&d_out, total * 4 + 4) != cudaSuccess ||
+        cudaMalloc(&d_band, sizeof(BandDesc)) != cudaSuccess || cudaMalloc(&d_status, n * 4) != cudaSuccess) {
+        ret = B200J2K_ERR_NOMEM;
+    } else {
+        cudaMemsetAsync(d_bytes, 0, (size_t)data_size + 64, st);
+        cudaMemcpyAsync(d_bytes, data, (size_t)data_size, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_descs, descs.data(), n * sizeof(CblkDesc), cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_order, order.data(), n * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_band, &band, sizeof(band), cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(d_out, 0x55, total * 4 + 4, st);
+        int r1 = launch_ht_decode(st, false, d_descs, d_order, (int)a, d_bytes, d_band, d_out, d_status, maxL[0], maxw, maxh);
+        int r2 = launch_ht_decode(st, true, d_descs, d_order + a, (int)(n - a), d_bytes, d_band, d_out, d_status, maxL[1], maxw, maxh);
+        if (r1 < 0 || r2 < 0) ret = B200J2K_ERR_DEVICE;
+        cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, st);
+        if (status) cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "b200j2k_ht_blocks: CUDA error: %s\n", cudaGetErrorString(e));
+            ret = B200J2K_ERR_DEVICE;
+        }
+    }
+    cudaFree(d_bytes); cudaFree(d_descs); cudaFree(d_order); cudaFree(d_out); cudaFree(d_band); cudaFree(d_status);
+    cudaStreamDestroy(st);
+    return ret;
+}
+
+int b200j2k_idwt(int device, int type, const int32_t *border, int levels, void *plane)
+{
+    if (device_ok() <= 0 || cudaSetDevice(device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    if (type < 0 || type > 2 || levels < 0 || levels > J2K_MAX_LEVELS)
+        return B200J2K_ERR_EINVAL;
+    const size_t n = (size_t)(border[1] - border[0]) * (size_t)(border[3] - border[2]);
+    if (!n || !levels)
+        return 0;
+    void *dA = nullptr, *dB = nullptr, *dC = nullptr;
+    TileCompDesc *dtc = nullptr;
+    int ret = 0;
+    if (cudaMalloc(&dA, n * 4 + 256) != cudaSuccess || cudaMalloc(&dB, n * 4 + 256) != cudaSuccess ||
+        cudaMalloc(&dC, n * 4 + 256) != cudaSuccess || cudaMalloc(&dtc, sizeof(TileCompDesc)) != cudaSuccess) {
+        ret = B200J2K_ERR_NOMEM;
+    } else {
+        cudaMemcpy(dA, plane, n * 4, cudaMemcpyHostToDevice);
+        if (launch_idwt_plane(nullptr, type, border, levels, dA, dB, dC, dtc) < 0)
+            ret = B200J2K_ERR_DEVICE;
+        cudaError_t e = cudaMemcpy(plane, dA, n * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            fprintf(stderr, "b200j2k_idwt: CUDA error: %s\n", cudaGetErrorString(e));
+            ret = B200J2K_ERR_DEVICE;
+        }
+    }
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dtc);
+    return ret;
+}
+
+void *b200j2k_host_alloc(int64_t bytes)
+{
+    void *p = nullptr;
+    if (device_ok() <= 0 || cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void b200j2k_host_free(void *p) { if (p) cudaFreeHost(p); }
+int b200j2k_host_register(void *p, int64_t bytes)
+{
+    if (device_ok() <= 0)
+        return B200J2K_ERR_DEVICE;
+    return cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault) == cudaSuccess ? 0 : B200J2K_ERR_EINVAL;
+}
+int b200j2k_host_unregister(void *p) { return cudaHostUnregister(p) == cudaSuccess ? 0 : B200J2K_ERR_EINVAL; }
+
+const char *b200j2k_pix_fmt_name(int pix) { return pix_fmt_name(pix); }
+const char *b200j2k_version(void) { return "b200j2k 0.1 (sm_100a)"; }
+
+/* ---- introspection of the host plan (CPU only; used by the not-gpu tests to check the parser) ---------- */
+static thread_local Parser *g_plan = nullptr;
+
+int b200j2k_plan_build(const uint8_t *pkt, int64_t pkt_size, int flags, b200j2k_frame_info *info)
+{
+    if (!g_plan)
+        g_plan = new Parser();
+    int ret = g_plan->parse(pkt, pkt_size, flags, false);
+    if (ret < 0)
+        return ret;
+    fill_info(*g_plan, info);
+    return 0;
+}
+
+/* which: 0 CblkDesc, 1 BandDesc, 2 TileCompDesc, 3 PackGroup, 4 gathered extra bytes */
+const void *b200j2k_plan_table(int which, int64_t *count, int32_t *elem_size)
+{
+    if (!g_plan)
+        return nullptr;
+    switch (which) {
+    case 0: *count = (int64_t)g_plan->cblk.size(); *elem_size = sizeof(CblkDesc); return g_plan->cblk.data();
+    case 1: *count = (int64_t)g_plan->bands.size(); *elem_size = sizeof(BandDesc); return g_plan->bands.data();
+    case 2: *count = (int64_t)g_plan->tcs.size(); *elem_size = sizeof(TileCompDesc); return g_plan->tcs.data();
+    case 3: *count = (int64_t)g_plan->groups.size(); *elem_size = sizeof(PackGroup); return g_plan->groups.data();
+    case 4: *count = (int64_t)g_plan->extra.size(); *elem_size = 1; return g_plan->extra.data();
+    }
+    return nullptr;
+}
+
+int64_t b200j2k_plan_scalar(int which)
+{
+    if (!g_plan)
+        return -1;
+    switch (which) {
+    case 0: return (int64_t)g_plan->coef_elems;
+    case 1: return (int64_t)g_plan->picture_bytes;
+    case 2: return g_plan->max_levels;
+    case 3: return g_plan->plane_off[1];
+    case 4: return g_plan->plane_off[2];
+    case 5: return g_plan->plane_off[3];
+    }
+    return -1;
+}
+
+}  // extern "C"

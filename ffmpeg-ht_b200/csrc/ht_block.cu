@@ -1,0 +1,712 @@
+/*
+ * ht_block.cu -- HT (Rec. ITU-T T.814) code-block decoder for sm_100a, one code-block per warp, with the
+ * dequantisation fused into the coefficient write-back.
+ *
+ * Replaces, for the HT path, ff_jpeg2000_decode_htj2k (libavcodec/jpeg2000htdec.c:1188-1336) and
+ * dequantization_{int,float,int_97} (libavcodec/jpeg2000dec.c:2098-2181) as called from tile_codeblocks
+ * (:2212-2299).  SURVEY.md section 8(a) rows H1-H9, D1-D3.
+ *
+ * Work split inside a warp (codeblock-per-warp, BASELINE.json north_star):
+ *   1. all lanes: copy the cleanup segment's suffix (MEL + VLC bytes) to shared memory and UN-STUFF the
+ *      MagSgn byte stream in parallel (warp prefix sum over 7/8-bit byte lengths) into a contiguous
+ *      bit array in shared memory;
+ *   2. per quad row, in segments of 32 quads: the context-adaptive part (MEL run decoder, CxtVLC table
+ *      look-ups from shared memory, U-VLC) is inherently serial -- every lane executes it redundantly on
+ *      warp-uniform data (shared-memory broadcasts, no divergence) and lane j keeps quad j's result;
+ *   3. then lane j owns quad j: exponent predictor from the row above, warp prefix sum over the quads'
+ *      MagSgn bit counts gives each lane its bit offset, four samples are extracted, dequantised and
+ *      stored (two coalesced row segments per quad row);
+ *   4. SigProp / MagRef refinement (only for blocks that carry them) runs on a shared-memory copy.
+ * The CxtVLC tables (2 x 1024 x u16, cxtvlc_tables.h) are staged in shared memory per CTA.
+ * Integer/bit work throughout: no tensor cores (nothing here is a contraction).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define CXTVLC_TABLE_ATTR __device__
+#include "cxtvlc_tables.h"
+#include "j2k_kernels.h"
+#include "j2k_plan.h"
+
+namespace b200j2k {
+
+namespace {
+
+constexpr int WARPS_PER_CTA = 4;
+constexpr unsigned FULL = 0xFFFFFFFFu;
+
+__device__ __constant__ uint8_t c_mel_exp[13] = { 0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 4, 5 };
+
+/* ---- H3: MEL (jpeg2000htdec.c:429-440, :462-495): MSB-first bits over Dcup[Pcup..Lcup), 7 bits after
+ * 0xFF, 0xFF past the end.  sc[] is the shared-memory copy of the suffix with modDcup applied. */
+struct Mel {
+    int pos, left;
+    unsigned cur;
+    int k, run, one;
+};
+
+__device__ __forceinline__ int mel_bit(Mel &m, const uint8_t *sc, int sclen)
+{
+    if (m.left == 0) {
+        m.left = m.cur == 0xFF ? 7 : 8;
+        m.cur = m.pos < sclen ? sc[m.pos] : 0xFF;
+        m.pos += m.pos < sclen;
+    }
+    m.left--;
+    return (m.cur >> m.left) & 1;
+}
+
+__device__ __forceinline__ int mel_symbol(Mel &m, const uint8_t *sc, int sclen)
+{
+    if (m.run == 0 && !m.one) {
+        int e = c_mel_exp[m.k];
+        if (mel_bit(m, sc, sclen)) {
+            m.run = 1 << e;
+            m.k = min(12, m.k + 1);
+        } else {
+            int r = 0;
+            while (e-- > 0)
+                r = 2 * r + mel_bit(m, sc, sclen);
+            m.run = r;
+            m.k = max(0, m.k - 1);
+            m.one = 1;
+        }
+    }
+    if (m.run > 0) {
+        m.run--;
+        return 0;
+    }
+    m.one = 0;
+    return 1;
+}
+
+/* ---- H2: backward VLC reader (jpeg2000htdec.c:145-201, :283-295): bytes from Dcup[Lcup-2] down to
+ * Dcup[Pcup]; a byte whose low 7 bits are ones gives 7 bits when the byte read before it is > 0x8F.
+ * Below Pcup the stream reads as zeros. */
+struct Vlc {
+    int pos;
+    unsigned prev;
+    uint64_t acc;
+    int n;
+};
+
+__device__ __forceinline__ void vlc_fill(Vlc &v, const uint8_t *sc)
+{
+    while (v.n <= 56) {
+        unsigned b = v.pos >= 0 ? sc[v.pos] : 0;
+        v.pos--;
+        int nb = ((b & 0x7F) == 0x7F && v.prev > 0x8F) ? 7 : 8;
+        v.acc |= (uint64_t)(b & ((1u << nb) - 1)) << v.n;
+        v.n += nb;
+        v.prev = b;
+    }
+}
+
+__device__ __forceinline__ unsigned vlc_peek(const Vlc &v, int nb) { return (unsigned)v.acc & ((1u << nb) - 1); }
+__device__ __forceinline__ void vlc_drop(Vlc &v, int nb) { v.acc >>= nb; v.n -= nb; }
+
+/* ---- H5: U-VLC (jpeg2000htdec.c:338-388) ------------------------------------------------------------ */
+__device__ __forceinline__ int uvlc_prefix(Vlc &v)
+{
+    unsigned b = (unsigned)v.acc & 7;
+    int len, val;
+    if (b & 1) { len = 1; val = 1; }
+    else if (b & 2) { len = 2; val = 2; }
+    else if (b & 4) { len = 3; val = 3; }
+    else { len = 3; val = 5; }
+    vlc_drop(v, len);
+    return val;
+}
+
+__device__ __forceinline__ int uvlc_suffix(Vlc &v, int pfx)
+{
+    if (pfx < 3)
+        return 0;
+    unsigned b = (unsigned)v.acc & 31;
+    if (pfx == 3) {
+        vlc_drop(v, 1);
+        return b & 1;
+    }
+    vlc_drop(v, 5);
+    return b;
+}
+
+__device__ __forceinline__ int uvlc_ext(Vlc &v, int sfx)
+{
+    if (sfx < 28)
+        return 0;
+    int e = (unsigned)v.acc & 15;
+    vlc_drop(v, 4);
+    return e;
+}
+
+__device__ __forceinline__ int uvlc_whole(Vlc &v)
+{
+    int p = uvlc_prefix(v);
+    int s = uvlc_suffix(v, p);
+    return p + s + 4 * uvlc_ext(v, s);
+}
+
+/* ---- H4: one quad (jpeg2000htdec.c:300-331, :510-531) ------------------------------------------------ */
+__device__ __forceinline__ unsigned decode_quad(Mel &mel, Vlc &vlc, const uint16_t *table, int ctx,
+                                                const uint8_t *sc, int sclen)
+{
+    if (ctx == 0 && mel_symbol(mel, sc, sclen) == 0)
+        return 0;
+    unsigned e = table[vlc_peek(vlc, 7) | ((unsigned)ctx << 7)];
+    vlc_drop(vlc, e & 7);
+    return e >> 3;          /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 */
+}
+
+/* read nb (1..31) bits at bit position pos of the un-stuffed MagSgn array */
+__device__ __forceinline__ uint32_t ms_read(const uint32_t *ms, uint32_t pos, int nb)
+{
+    uint32_t w = pos >> 5, s = pos & 31;
+    uint32_t lo = ms[w], hi = ms[w + 1];
+    uint32_t v = __funnelshift_r(lo, hi, s);
+    return v & ((1u << nb) - 1);
+}
+
+/* D1-D3: sign-magnitude sample -> plane value (as raw 32 bits) */
+__device__ __forceinline__ uint32_t dequant(uint32_t sm, int mode, int M_b, int roi_shift, const BandDesc &bd)
+{
+    /* ROI up-shift, then "val | sign" (jpeg2000htdec.c:1318-1331) */
+    uint32_t t = sm & 0x7FFFFFFFu;
+    if (roi_shift) {
+        const uint32_t mask = 0xFFFFFFFFu >> (M_b + 1);
+        if ((t & ~mask) == 0)
+            t <<= roi_shift;
+    }
+    const uint32_t c = t | (sm & 0x80000000u);
+    const bool neg = (c >> 31) != 0;
+    const uint32_t mag = c & 0x7FFFFFFFu;
+    if (mode == 3)                                   /* stage-level entry point: t1->data as is */
+        return c;
+    if (mode == J2K_DWT53) {
+        int32_t v = (int32_t)(mag >> (31 - M_b));
+        if (neg)
+            v = -v;
+        if (bd.i_stepsize != 32768)
+            v = (int32_t)(((int64_t)v * bd.i_stepsize) / 65536);
+        return (uint32_t)v;
+    } else if (mode == J2K_DWT97) {
+        int32_t v = neg ? -(int32_t)mag : (int32_t)mag;
+        return __float_as_uint(__fmul_rn((float)v, bd.fscale));
+    } else {
+        int32_t v = neg ? -(int32_t)mag : (int32_t)mag;
+        v = (v + 32) >> 6;
+        int64_t m = (int64_t)v * bd.iscale;
+        m = m > 0 ? (m + 32768) >> 16 : (m + 32767) >> 16;   /* RSHIFT(m, 16) */
+        return (uint32_t)(int32_t)m;
+    }
+}
+
+/* sample state bits in the refinement path (jpeg2000htdec.c:62-65) */
+constexpr unsigned ST_SIGMA = 1, ST_NEWSIG = 8, ST_SCANNED = 16;
+
+/* SigProp bit reader (jpeg2000htdec.c:442-460), global memory, lane 0 only */
+struct SpBits {
+    const uint8_t *d;
+    int len, pos, left;
+    unsigned cur, last;
+};
+__device__ __forceinline__ int sp_bit(SpBits &s)
+{
+    if (s.left == 0) {
+        s.left = s.last == 0xFF ? 7 : 8;
+        s.cur = s.pos < s.len ? s.d[s.pos++] : 0;
+        s.last = s.cur;
+    }
+    int b = s.cur & 1;
+    s.cur >>= 1;
+    s.left--;
+    return b;
+}
+
+}  // namespace
+
+/*
+ * Shared memory per CTA: [tables 4 KiB][per-warp region] x WARPS_PER_CTA.
+ * Per-warp region (32-bit words):
+ *   ms   [ms_words]          un-stuffed MagSgn bits (+2 words of ones)
+ *   sc   [sc_words]          suffix bytes Dcup[Pcup..Lcup) with modDcup applied
+ *   row  [2][maxQW + 2]      per-quad (rho | E1<<8 | E3<<16) of the previous / current quad row
+ *   REFINE only:
+ *   samp [maxw * maxh]       sign-magnitude samples
+ *   st   [(maxh+3)*(maxw+3)] bytes, sample states with a one-sample apron
+ * ms and sc share one allocation of `stream_words`: ms takes what Pcup needs, sc the rest.
+ */
+template <bool REFINE>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order, int nblocks,
+                 const uint8_t *__restrict__ bytes, const BandDesc *__restrict__ bands,
+                 uint32_t *__restrict__ coef, int32_t *__restrict__ status,
+                 int stream_words, int maxQW, int maxw, int maxh)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    uint16_t *tab = reinterpret_cast<uint16_t *>(smem);
+    for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+        tab[i] = CXTVLC_FIRST_ROW[i];
+        tab[1024 + i] = CXTVLC_OTHER_ROWS[i];
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row_words = 2 * (maxQW + 2);
+    int per_warp = stream_words + row_words;
+    if (REFINE)
+        per_warp += maxw * maxh + ((maxh + 3) * (maxw + 3) + 3) / 4;
+    uint32_t *wbase = smem + 1024 + (size_t)warp * per_warp;
+    uint32_t *streams = wbase;
+    uint32_t *rowbuf = wbase + stream_words;
+    uint32_t *samp = rowbuf + row_words;
+    uint8_t *st = reinterpret_cast<uint8_t *>(samp + maxw * maxh);
+
+    const int gw = blockIdx.x * WARPS_PER_CTA + warp;
+    if (gw >= nblocks)
+        return;
+    const uint32_t bi = order ? order[gw] : (uint32_t)gw;
+    const CblkDesc d = descs[bi];
+    const BandDesc bd = bands[d.band];
+    const int w = d.w, h = d.h;
+    const int mode = (d.flags >> 1) & 3;
+    const int M_b = d.M_b;
+    uint32_t *dst = coef + d.dst_off;
+    const uint32_t dstride = d.dst_stride;
+
+    /* ---- H1: pass bookkeeping (jpeg2000htdec.c:1237-1278) ---- */
+    int result = 1;
+    int z_blk = 0, p0 = 0;
+    if (d.npasses == 0) {
+        result = 0;
+    } else {
+        int rem = d.npasses % 3;
+        int plhd = rem ? d.npasses - rem : d.npasses - 3;
+        p0 = plhd / 3;
+        z_blk = d.npasses - plhd;
+        if (z_blk <= 0)
+            result = 0;
+    }
+    const int Lcup = d.Lcup, Lref = d.Lref;
+    const uint8_t *Dcup = bytes + d.data_off;
+    int Scup = 0, Pcup = 0;
+    const int S_blk = (p0 + d.zbp) & 0xFF;
+    const int pLSB = 30 - S_blk;
+    const int maxbp = S_blk + 1;
+    if (result > 0) {
+        if (Lcup < 2) {
+            result = B200J2K_KERR_INVALID;
+        } else {
+            Scup = (Dcup[Lcup - 1] << 4) + (Dcup[Lcup - 2] & 0x0F);
+            if (Scup < 2 || Scup > Lcup || Scup > 4079)
+                result = B200J2K_KERR_INVALID;
+            else if (maxbp >= 32 || pLSB < 1)
+                result = B200J2K_KERR_INVALID;
+            else if (4 * stream_words < Lcup + 24)
+                result = B200J2K_KERR_INVALID;          /* launch sized too small: host bug guard */
+        }
+        Pcup = Lcup - Scup;
+    }
+
+    if (result <= 0) {
+        /* nothing decoded or damaged: the block is all zeros (quirk Q1) */
+        for (int y = 0; y < h; y++)
+            for (int x = lane; x < w; x += 32)
+                dst[(size_t)y * dstride + x] = 0;
+        if (lane == 0 && status)
+            status[bi] = result;
+        return;
+    }
+
+    /* ---- stage the streams ---- */
+    const int ms_words = (Pcup + 3) / 4 + 2;
+    uint32_t *ms = streams;
+    uint8_t *sc = reinterpret_cast<uint8_t *>(streams + ms_words);
+    for (int i = lane; i < ms_words; i += 32)
+        ms[i] = 0;
+    for (int i = lane; i < Scup; i += 32) {
+        unsigned b = Dcup[Pcup + i];
+        if (i == Scup - 1) b = 0xFF;                     /* modDcup (:1277-1278) */
+        if (i == Scup - 2) b |= 0x0F;
+        sc[i] = (uint8_t)b;
+    }
+    __syncwarp();
+    /* un-stuff MagSgn: byte after 0xFF carries 7 bits (:207-221); bit 7 of such a byte is OR-ed into the
+     * next byte's bit 0 exactly as the reference's 64-bit accumulator does */
+    uint32_t ms_bits = 0;
+    {
+        unsigned carry = 0;
+        for (int chunk = 0; chunk < Pcup; chunk += 128) {
+            const int idx = chunk + lane * 4;
+            unsigned b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                b[k] = idx + k < Pcup ? Dcup[idx + k] : 0;
+            unsigned before = __shfl_up_sync(FULL, b[3], 1);
+            if (lane == 0)
+                before = carry;
+            uint64_t v = 0;
+            int tot = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                int nb = idx + k < Pcup ? (before == 0xFF ? 7 : 8) : 0;
+                v |= (uint64_t)b[k] << tot;
+                tot += nb;
+                before = b[k];
+            }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            const uint32_t off = ms_bits + (uint32_t)(incl - tot);
+            if (tot) {
+                const uint32_t wd = off >> 5, s = off & 31;
+                const uint64_t sh = v << s;
+                atomicOr(&ms[wd], (uint32_t)sh);
+                if ((uint32_t)(sh >> 32))
+                    atomicOr(&ms[wd + 1], (uint32_t)(sh >> 32));
+            }
+            ms_bits += (uint32_t)__shfl_sync(FULL, incl, 31);
+            carry = __shfl_sync(FULL, b[3], 31);
+        }
+        __syncwarp();
+        /* past the end the decoder reads ones */
+        if (lane == 0) {
+            ms[ms_bits >> 5] |= 0xFFFFFFFFu << (ms_bits & 31);
+            for (int i = (int)(ms_bits >> 5) + 1; i < ms_words; i++)
+                ms[i] = 0xFFFFFFFFu;
+        }
+        __syncwarp();
+    }
+
+    const int QW = (w + 1) >> 1, QH = (h + 1) >> 1;
+    uint32_t *rowprev = rowbuf, *rowcur = rowbuf + (maxQW + 2);
+    for (int i = lane; i < 2 * (maxQW + 2); i += 32)
+        rowbuf[i] = 0;
+    if (REFINE) {
+        for (int i = lane; i < (h + 3) * (w + 3); i += 32)
+            st[i] = 0;
+    }
+    __syncwarp();
+
+    Mel mel = { 0, 0, 0, 0, 0, 0 };
+    Vlc vlc = { Scup - 2, 0xFF, 0, 0 };
+    vlc_fill(vlc, sc);
+    vlc_drop(vlc, 4);
+    uint32_t ms_pos = 0;
+    bool bad = false;
+    const int SW = w + 3;                                /* state row stride (REFINE) */
+
+    for (int qy = 0; qy < QH && !bad; qy++) {
+        const uint16_t *table = qy == 0 ? tab : tab + 1024;
+        int ctxrun = 0;                                  /* first row: context from the previous quad */
+        int west = 0;                                    /* other rows: (sigma_W[3] | sigma_W[2]) */
+        for (int qb = 0; qb < QW; qb += 32) {
+            const int nq = min(32, QW - qb);
+            const int qx = qb + lane;
+            unsigned mA = 0, mC = 0;
+            if (qy > 0) {
+                /* row[] is stored with a +1 offset and zero sentinels at both ends */
+                unsigned n = qx < QW ? rowprev[qx + 1] : 0, nw = qx < QW ? rowprev[qx] : 0,
+                         ne = qx < QW ? rowprev[qx + 2] : 0;
+                mA = __ballot_sync(FULL, ((n >> 1) | (nw >> 3)) & 1);      /* sigma_N[1] | sigma_NW[3] */
+                mC = __ballot_sync(FULL, ((n >> 3) | (ne >> 1)) & 1);      /* sigma_N[3] | sigma_NE[1] */
+            }
+            unsigned mine = 0;                           /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16 */
+            /* ---- serial, warp-uniform: MEL + CxtVLC + U-VLC for up to 16 quad pairs ---- */
+            for (int j = 0; j < nq; j += 2) {
+                const int np = j + 1 < nq ? 2 : 1;
+                vlc_fill(vlc, sc);
+                unsigned q0, q1 = 0;
+                int ctx;
+                if (qy == 0)
+                    ctx = ctxrun;
+                else
+                    ctx = ((mA >> j) & 1) | (west << 1) | (((mC >> j) & 1) << 2);
+                q0 = decode_quad(mel, vlc, table, ctx, sc, Scup);
+                {
+                    unsigned rho = (q0 >> 1) & 15;
+                    ctxrun = ((rho & 3) ? 1 : 0) | ((rho >> 1) & 6);
+                    west = (rho >> 2) ? 1 : 0;
+                }
+                if (np == 2) {
+                    if (qy == 0)
+                        ctx = ctxrun;
+                    else
+                        ctx = ((mA >> (j + 1)) & 1) | (west << 1) | (((mC >> (j + 1)) & 1) << 2);
+                    q1 = decode_quad(mel, vlc, table, ctx, sc, Scup);
+                    unsigned rho = (q1 >> 1) & 15;
+                    ctxrun = ((rho & 3) ? 1 : 0) | ((rho >> 1) & 6);
+                    west = (rho >> 2) ? 1 : 0;
+                }
+                int u0 = 0, u1 = 0;
+                const int uo0 = q0 & 1, uo1 = q1 & 1;
+                if (uo0 & uo1) {
+                    if (qy == 0) {                       /* :671-704 */
+                        if (mel_symbol(mel, sc, Scup)) {
+                            int p0_ = uvlc_prefix(vlc), p1_ = uvlc_prefix(vlc);
+                            int s0 = uvlc_suffix(vlc, p0_), s1 = uvlc_suffix(vlc, p1_);
+                            int e0 = uvlc_ext(vlc, s0), e1 = uvlc_ext(vlc, s1);
+                            u0 = 2 + p0_ + s0 + 4 * e0;
+                            u1 = 2 + p1_ + s1 + 4 * e1;
+                        } else {
+                            int p0_ = uvlc_prefix(vlc);
+                            if (p0_ > 2) {
+                                u1 = (int)vlc_peek(vlc, 1) + 1;
+                                vlc_drop(vlc, 1);
+                                int s0 = uvlc_suffix(vlc, p0_);
+                                u0 = p0_ + s0 + 4 * uvlc_ext(vlc, s0);
+                            } else {
+                                int p1_ = uvlc_prefix(vlc);
+                                int s0 = uvlc_suffix(vlc, p0_), s1 = uvlc_suffix(vlc, p1_);
+                                int e0 = uvlc_ext(vlc, s0), e1 = uvlc_ext(vlc, s1);
+                                u0 = p0_ + s0 + 4 * e0;
+                                u1 = p1_ + s1 + 4 * e1;
+                            }
+                        }
+                    } else {                             /* :833-845 */
+                        int p0_ = uvlc_prefix(vlc), p1_ = uvlc_prefix(vlc);
+                        int s0 = uvlc_suffix(vlc, p0_), s1 = uvlc_suffix(vlc, p1_);
+                        int e0 = uvlc_ext(vlc, s0), e1 = uvlc_ext(vlc, s1);
+                        u0 = p0_ + s0 + 4 * e0;
+                        u1 = p1_ + s1 + 4 * e1;
+                    }
+                } else if (uo0) {
+                    u0 = uvlc_whole(vlc);
+                } else if (uo1) {
+                    u1 = uvlc_whole(vlc);
+                }
+                if (lane == j)
+                    mine = (q0 & 0xFFFF) | ((unsigned)u0 << 16);
+                if (lane == j + 1)
+                    mine = (q1 & 0xFFFF) | ((unsigned)u1 << 16);
+            }
+            /* ---- parallel: lane = quad.  exponent predictor, MagSgn, write-back ---- */
+            const bool act = lane < nq;
+            const unsigned rho = act ? (mine >> 1) & 15 : 0;
+            const unsigned ek = (mine >> 5) & 15, e1 = (mine >> 9) & 15;
+            const int u = (int)(mine >> 16);
+            int kappa = 1;
+            if (qy > 0 && act) {                         /* :855-885 */
+                unsigned n = rowprev[qx + 1], nw = rowprev[qx], ne = rowprev[qx + 2];
+                int m = max(max((int)((n >> 8) & 63), (int)((n >> 16) & 63)),
+                            max((int)((nw >> 16) & 63), (int)((ne >> 8) & 63)));
+                int gamma = (rho & (rho - 1)) != 0;
+                kappa = max(1, gamma * (m - 1));
+            }
+            const int U = kappa + u;
+            if (__any_sync(FULL, act && U > maxbp)) {    /* :715, :889 */
+                bad = true;
+                break;
+            }
+            int mlen[4];
+            int tot = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                mlen[i] = act ? (int)((rho >> i) & 1) * U - (int)((ek >> i) & 1) : 0;
+                tot += max(mlen[i], 0);
+            }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            uint32_t pos = ms_pos + (uint32_t)(incl - tot);
+            ms_pos += (uint32_t)__shfl_sync(FULL, incl, 31);
+            uint32_t mu[4];
+            unsigned E1 = 0, E3 = 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t v = 0, val = 0;
+                const int m = mlen[i];
+                if (m > 0) {
+                    uint32_t p = min(pos, ms_bits);      /* past the end: ones */
+                    v = ms_read(ms, p, m) + (((e1 >> i) & 1u) << m);
+                    pos += m;
+                }
+                if (m != 0) {                            /* :419-425 */
+                    unsigned E = 32 - __clz(v | 1);
+                    if (i == 1) E1 = E;
+                    if (i == 3) E3 = E;
+                    val = (uint32_t)(((int32_t)v >> 1) + 1) << pLSB;
+                    val |= 1u << (pLSB - 1);
+                    val |= (v & 1u) << 31;
+                }
+                mu[i] = val;
+            }
+            if (act)
+                rowcur[qx + 1] = rho | (E1 << 8) | (E3 << 16);
+            /* samples of quad (qy, qx): i=0 (y,x) i=1 (y+1,x) i=2 (y,x+1) i=3 (y+1,x+1) */
+            const int y = 2 * qy, x = 2 * qx;
+            if (!REFINE) {
+                if (act) {
+                    if (x < w) {
+                        dst[(size_t)y * dstride + x] = dequant(mu[0], mode, M_b, d.roi_shift, bd);
+                        if (y + 1 < h)
+                            dst[(size_t)(y + 1) * dstride + x] = dequant(mu[1], mode, M_b, d.roi_shift, bd);
+                    }
+                    if (x + 1 < w) {
+                        dst[(size_t)y * dstride + x + 1] = dequant(mu[2], mode, M_b, d.roi_shift, bd);
+                        if (y + 1 < h)
+                            dst[(size_t)(y + 1) * dstride + x + 1] = dequant(mu[3], mode, M_b, d.roi_shift, bd);
+                    }
+                }
+            } else if (act) {
+                /* quad -> raster with the reference's odd-edge masks (:975-1007, quirk Q2) */
+                const int keep_row = qy != QH - 1 || !(h & 1);
+                const int keep_col = qx != QW - 1 || !(w & 1);
+                const int keep[4] = { 1, keep_row, keep_col, keep_row | keep_col };
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int yy = y + (i & 1), xx = x + (i >> 1);
+                    if (keep[i]) {
+                        st[(yy + 1) * SW + xx + 1] |= (rho >> i) & 1;
+                        if (yy < h && xx < w)
+                            samp[yy * w + xx] = mu[i];
+                    } else if (yy < h && xx < w) {
+                        samp[yy * w + xx] = 0;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        uint32_t *t = rowprev;
+        rowprev = rowcur;
+        rowcur = t;
+    }
+
+    if (bad) {
+        __syncwarp();
+        for (int y = 0; y < h; y++)
+            for (int x = lane; x < w; x += 32)
+                dst[(size_t)y * dstride + x] = 0;
+        if (lane == 0 && status)
+            status[bi] = B200J2K_KERR_INVALID;
+        return;
+    }
+
+    if (REFINE) {
+        __syncwarp();
+        const int p = pLSB - 1;
+        const uint8_t *Dref = Dcup + Lcup;
+        if (lane == 0) {
+            if (z_blk > 1) {
+                /* H7 SigProp (:1034-1131): stripes of 4 rows, 4-column groups, column-major */
+                SpBits sp = { Dref, Lref, 0, 0, 0, 0 };
+                const int causal = d.flags & 1;
+                for (int y0 = 0; y0 < h; y0 += 4) {
+                    const int sh = min(4, h - y0);
+                    for (int x0 = 0; x0 < w; x0 += 4) {
+                        const int sw = min(4, w - x0);
+                        for (int x = x0; x < x0 + sw; x++)
+                            for (int y = y0; y < y0 + sh; y++) {
+                                uint8_t *c = &st[(y + 1) * SW + x + 1];
+                                int member = 0;
+                                if (!(c[0] & ST_SIGMA)) {
+                                    const int below_ok = !causal || y != y0 + sh - 1;
+                                    unsigned up = c[-SW - 1] | c[-SW] | c[-SW + 1];
+                                    unsigned mid = c[-1] | c[1];
+                                    unsigned dn = c[SW - 1] | c[SW] | c[SW + 1];
+                                    unsigned m = up | mid | (below_ok ? dn : 0);
+                                    m |= ((up >> 3) & (up >> 4)) | ((mid >> 3) & (mid >> 4));
+                                    if (below_ok)
+                                        m |= (dn >> 3) & (dn >> 4);
+                                    member = m & 1;
+                                }
+                                unsigned s = c[0] | ST_SCANNED;
+                                if (member) {
+                                    const unsigned bit = sp_bit(sp);
+                                    if (bit)
+                                        s |= ST_NEWSIG;
+                                    samp[y * w + x] |= (bit << p) | (bit << (p - 1));
+                                }
+                                c[0] = (uint8_t)s;
+                            }
+                        for (int x = x0; x < x0 + sw; x++)
+                            for (int y = y0; y < y0 + sh; y++)
+                                if (st[(y + 1) * SW + x + 1] & ST_NEWSIG)
+                                    samp[y * w + x] |= (uint32_t)sp_bit(sp) << 31;
+                    }
+                }
+            }
+            if (z_blk > 2) {
+                /* H8 MagRef (:1136-1185): bits read backwards from the end of Dref; byte Dref[Lref] reads 0xFF */
+                int pos = Lref - 1;
+                unsigned prev = 0xFF;
+                uint32_t acc = 0;
+                int n = 0;
+                for (int y0 = 0; y0 < h; y0 += 4) {
+                    const int sh = min(4, h - y0);
+                    for (int x = 0; x < w; x++)
+                        for (int y = y0; y < y0 + sh; y++) {
+                            if (!(st[(y + 1) * SW + x + 1] & ST_SIGMA))
+                                continue;
+                            if (n == 0) {
+                                unsigned b = pos >= 0 ? Dref[pos] : 0;
+                                pos--;
+                                n = ((b & 0x7F) == 0x7F && prev > 0x8F) ? 7 : 8;
+                                acc = b & ((1u << n) - 1);
+                                prev = b;
+                            }
+                            const uint32_t bit = acc & 1;
+                            acc >>= 1;
+                            n--;
+                            const uint32_t keepm = (0xFFFFFFFEu | bit) << p;
+                            samp[y * w + x] = (samp[y * w + x] & keepm) | (1u << (p - 1));
+                        }
+                }
+            }
+        }
+        __syncwarp();
+        for (int y = 0; y < h; y++)
+            for (int x = lane; x < w; x += 32)
+                dst[(size_t)y * dstride + x] = dequant(samp[y * w + x], mode, M_b, d.roi_shift, bd);
+    }
+    if (lane == 0 && status)
+        status[bi] = 1;
+}
+
+/* ---- host-side launcher ------------------------------------------------------------------------------ */
+size_t ht_smem_bytes(bool refine, int stream_words, int maxQW, int maxw, int maxh)
+{
+    size_t per_warp = (size_t)stream_words + 2 * (size_t)(maxQW + 2);
+    if (refine)
+        per_warp += (size_t)maxw * maxh + ((size_t)(maxh + 3) * (maxw + 3) + 3) / 4;
+    return 4096 + per_warp * 4 * WARPS_PER_CTA;
+}
+
+int launch_ht_decode(cudaStream_t stream, bool refine, const CblkDesc *descs, const uint32_t *order, int nblocks,
+                     const uint8_t *bytes, const BandDesc *bands, void *coef, int32_t *status,
+                     int max_Lcup, int maxw, int maxh)
+{
+    if (nblocks <= 0)
+        return 0;
+    const int stream_words = (max_Lcup + 3) / 4 + 8;
+    const int maxQW = (maxw + 1) / 2;
+    const size_t smem = ht_smem_bytes(refine, stream_words, maxQW, maxw, maxh);
+    if (smem > 227 * 1024)
+        return -1;
+    const int grid = (nblocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    cudaError_t err;
+    if (refine) {
+        err = cudaFuncSetAttribute(ht_decode_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess)
+            return -2;
+        ht_decode_kernel<true><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(
+            descs, order, nblocks, bytes, bands, (uint32_t *)coef, status, stream_words, maxQW, maxw, maxh);
+    } else {
+        err = cudaFuncSetAttribute(ht_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess)
+            return -2;
+        ht_decode_kernel<false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(
+            descs, order, nblocks, bytes, bands, (uint32_t *)coef, status, stream_words, maxQW, maxw, maxh);
+    }
+    return cudaGetLastError() == cudaSuccess ? 1 : -3;
+}
+
+}  // namespace b200j2k

@@ -1,0 +1,500 @@
+/*
+ * idwt.cu -- inverse DWT (5/3 integer, 9/7 float, 9/7 fixed point), inverse RCT/ICT, DC level shift,
+ * clip and pixel-format pack for sm_100a.
+ *
+ * Replaces ff_dwt_decode (libavcodec/jpeg2000dwt.c:309-537, :601-620), mct_decode /
+ * rct_int / ict_float / ict_int (libavcodec/jpeg2000dec.c:2183-2209, libavcodec/jpeg2000dsp.c:43-91; rows
+ * M1-M3) and write_frame_8/16 (libavcodec/jpeg2000dec.c:2301-2366; row P1).
+ *
+ * One launch per decomposition level, all tile-components of the frame in the grid.  A CTA reconstructs a
+ * TX x TY tile of the level's output: it gathers the four sub-band quadrants (LL from the previous
+ * level's output, HL/LH/HH from the Mallat-layout coefficient plane the HT kernel filled) with coalesced
+ * row-segment loads into an interleaved shared-memory tile with a HALO-sample apron, runs the row
+ * lifting steps then the column lifting steps in shared memory (rows before columns at every level,
+ * which is what makes the 5/3 path bit-exact, quirk Q7), and writes the tile once.  Image borders use
+ * whole-sample symmetric extension by index reflection, bit-identical to the reference's sequential
+ * copies.  The last level is fused with the component transform, level shift, clip
+ * and pack, so the full-resolution planes are never written to HBM: per sample the stage reads 4 B and
+ * writes 2 B (1 B for 8-bit formats) -- the algorithmic traffic SURVEY.md section 8(d) names.
+ *
+ * Float path: every operation is an explicit __fmul_rn / __fadd_rn / __fsub_rn in the reference's order
+ * (a - c*(b+d) as add, multiply, subtract), so no FMA contraction can change a bit; lrintf is
+ * __float2int_rn (round to nearest even).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "j2k_kernels.h"
+#include "j2k_plan.h"
+
+namespace b200j2k {
+
+namespace {
+
+constexpr int THREADS = 256;
+
+__device__ __forceinline__ int reflect(int i, int i0, int i1)
+{
+    const int n = i1 - i0;
+    if (n == 1)
+        return i0;
+    const int period = 2 * (n - 1);
+    int k = (i - i0) % period;
+    if (k < 0)
+        k += period;
+    return i0 + (k < n ? k : period - k);
+}
+
+/* index of absolute position X inside its (low or high) band of a line that starts at absolute u0 */
+__device__ __forceinline__ int band_index(int X, int u0)
+{
+    return (X & 1) ? ((X - 1) >> 1) - (u0 >> 1) : (X >> 1) - ((u0 + 1) >> 1);
+}
+
+template <int TYPE> struct Lift;
+
+/* 5/3: uint32 wrap-around adds, arithmetic shift of the int cast (jpeg2000dwt.c:321-324) */
+template <> struct Lift<J2K_DWT53> {
+    static constexpr int HALO = 2, STEPS = 2;
+    /* step s updates positions of parity (s & 1): step 0 evens, step 1 odds */
+    static __device__ __forceinline__ uint32_t apply(int s, uint32_t c, uint32_t a, uint32_t b)
+    {
+        if (s == 0)
+            return c - (uint32_t)((int32_t)(a + b + 2) >> 2);
+        return c + (uint32_t)((int32_t)(a + b) >> 1);
+    }
+    static __device__ __forceinline__ uint32_t single(uint32_t c, int odd)
+    {
+        return odd ? (uint32_t)((int32_t)c >> 1) : c;
+    }
+};
+
+/* 9/7 float (jpeg2000dwt.c:376-401) */
+template <> struct Lift<J2K_DWT97> {
+    static constexpr int HALO = 4, STEPS = 4;
+    static __device__ __forceinline__ uint32_t apply(int s, uint32_t c, uint32_t a, uint32_t b)
+    {
+        const float fc = __uint_as_float(c);
+        const float sum = __fadd_rn(__uint_as_float(a), __uint_as_float(b));
+        float r;
+        if (s == 0) r = __fsub_rn(fc, __fmul_rn(0.443506852043971f, sum));
+        else if (s == 1) r = __fsub_rn(fc, __fmul_rn(0.882911075530934f, sum));
+        else if (s == 2) r = __fadd_rn(fc, __fmul_rn(0.052980118572961f, sum));
+        else r = __fadd_rn(fc, __fmul_rn(1.586134342059924f, sum));
+        return __float_as_uint(r);
+    }
+    static __device__ __forceinline__ uint32_t single(uint32_t c, int odd)
+    {
+        const float f = __uint_as_float(c);
+        return __float_as_uint(odd ? __fmul_rn(f, 1.230174104914001f / 2) : __fmul_rn(f, 0.812893066115961f));
+    }
+};
+
+/* 9/7 16.16 fixed point (jpeg2000dwt.c:453-481) */
+template <> struct Lift<J2K_DWT97_INT> {
+    static constexpr int HALO = 4, STEPS = 4;
+    static __device__ __forceinline__ uint32_t apply(int s, uint32_t c, uint32_t a, uint32_t b)
+    {
+        const int64_t sum = (int64_t)(int32_t)a + (int64_t)(int32_t)b;
+        int32_t v = (int32_t)c;
+        if (s == 0) v -= (int32_t)((29066ll * sum + (1 << 15)) >> 16);
+        else if (s == 1) v -= (int32_t)((57862ll * sum + (1 << 15)) >> 16);
+        else if (s == 2) v += (int32_t)((3472ll * sum + (1 << 15)) >> 16);
+        else {
+            v += (int32_t)sum;
+            v += (int32_t)((38413ll * sum + (1 << 15)) >> 16);
+        }
+        return (uint32_t)v;
+    }
+    static __device__ __forceinline__ uint32_t single(uint32_t c, int odd)
+    {
+        const int32_t v = (int32_t)c;
+        return odd ? (uint32_t)(int32_t)((v * 80621ll + (1 << 16)) >> 17)
+                   : (uint32_t)(int32_t)((v * 53274ll + (1 << 15)) >> 16);
+    }
+};
+
+/*
+ * Load one interleaved tile (with apron) of resolution `lev_out` of tile-component tc into shared memory,
+ * run the lifting steps, leave the result in tile[] (valid region = the TX x TY centre).
+ * tile is SH x SWD words, SWD = TX + 2*HALO (+1 pad), SH = TY + 2*HALO.
+ */
+template <int TYPE, int TX, int TY>
+__device__ void reconstruct_tile(uint32_t *tile, const TileCompDesc &tc, int j, const uint32_t *coefA,
+                                 const uint32_t *coefIn, int XT, int YT)
+{
+    using L = Lift<TYPE>;
+    constexpr int HALO = L::HALO;
+    constexpr int SWD = TX + 2 * HALO + 1, SH = TY + 2 * HALO, SWV = TX + 2 * HALO;
+    const LevelDesc o = tc.lev[j + 1];
+    const int u0 = o.u0, u1 = o.u1, v0 = o.v0, v1 = o.v1;
+    const int lh = u1 - u0, lv = v1 - v0;
+    const int nLh = ((u1 + 1) >> 1) - ((u0 + 1) >> 1), nLv = ((v1 + 1) >> 1) - ((v0 + 1) >> 1);
+    const int W = tc.width;
+    const uint32_t *A = coefA + tc.coef_off;
+    /* LL comes from the plane itself at the coarsest level, else from the compact ping-pong buffer */
+    const uint32_t *LLp = j == 0 ? A : coefIn + tc.coef_off;
+    const int LLstride = j == 0 ? W : nLh;
+    const int XS = XT - HALO, YS = YT - HALO;
+
+    /* ---- gather: band-major order inside a row so that global reads are contiguous ---- */
+    const int nE = (SWV + ((XS & 1) ? 0 : 1)) >> 1;          /* even positions in [XS, XS+SWV) */
+    const int XE0 = XS + (XS & 1), XO0 = XS + 1 - (XS & 1);
+    for (int idx = threadIdx.x; idx < SH * SWV; idx += THREADS) {
+        const int r = idx / SWV, cc = idx - r * SWV;
+        const int X = cc < nE ? XE0 + 2 * cc : XO0 + 2 * (cc - nE);
+        const int Y = YS + r;
+        const int Xr = reflect(X, u0, u1), Yr = reflect(Y, v0, v1);
+        const int kx = band_index(Xr, u0), ky = band_index(Yr, v0);
+        uint32_t v;
+        if (!((Xr | Yr) & 1))
+            v = LLp[(size_t)ky * LLstride + kx];
+        else
+            v = A[(size_t)(ky + ((Yr & 1) ? nLv : 0)) * W + kx + ((Xr & 1) ? nLh : 0)];
+        tile[r * SWD + (X - XS)] = v;
+    }
+    __syncthreads();
+
+    /* ---- HOR_SD: row lifting ---- */
+    if (lh > 1) {
+#pragma unroll
+        for (int s = 0; s < L::STEPS; s++) {
+            /* step s is valid on [XS + s + 1, XS + SWV - s - 1), positions of parity (s & 1) */
+            const int lo = XS + s + 1, hi = XS + SWV - s - 1;
+            const int first = lo + (((lo & 1) != (s & 1)) ? 1 : 0);
+            const int cnt = hi > first ? (hi - first + 1) >> 1 : 0;
+            for (int idx = threadIdx.x; idx < SH * cnt; idx += THREADS) {
+                const int r = idx / cnt, k = idx - r * cnt;
+                uint32_t *p = tile + r * SWD + (first + 2 * k - XS);
+                p[0] = L::apply(s, p[0], p[-1], p[1]);
+            }
+            __syncthreads();
+        }
+    } else {
+        const int odd = u0 & 1;
+        for (int idx = threadIdx.x; idx < SH * SWV; idx += THREADS) {
+            const int r = idx / SWV, cc = idx - r * SWV;
+            tile[r * SWD + cc] = L::single(tile[r * SWD + cc], odd);
+        }
+        __syncthreads();
+    }
+    /* ---- VER_SD: column lifting (only the TX centre columns are needed) ---- */
+    if (lv > 1) {
+#pragma unroll
+        for (int s = 0; s < L::STEPS; s++) {
+            const int lo = YS + s + 1, hi = YS + SH - s - 1;
+            const int first = lo + (((lo & 1) != (s & 1)) ? 1 : 0);
+            const int cnt = hi > first ? (hi - first + 1) >> 1 : 0;
+            for (int idx = threadIdx.x; idx < cnt * TX; idx += THREADS) {
+                const int k = idx / TX, cx = idx - k * TX;
+                uint32_t *p = tile + (first + 2 * k - YS) * SWD + HALO + cx;
+                p[0] = L::apply(s, p[0], p[-SWD], p[SWD]);
+            }
+            __syncthreads();
+        }
+    } else {
+        const int odd = v0 & 1;
+        for (int idx = threadIdx.x; idx < SH * TX; idx += THREADS) {
+            const int r = idx / TX, cx = idx - r * TX;
+            tile[r * SWD + HALO + cx] = L::single(tile[r * SWD + HALO + cx], odd);
+        }
+        __syncthreads();
+    }
+}
+
+/* ---- intermediate level: write the reconstructed resolution to the compact ping-pong buffer ---------- */
+template <int TYPE, int TX, int TY>
+__global__ void __launch_bounds__(THREADS)
+idwt_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint32_t *__restrict__ coefA,
+                  const uint32_t *__restrict__ coefIn, uint32_t *__restrict__ coefOut, int to_plane)
+{
+    using L = Lift<TYPE>;
+    constexpr int HALO = L::HALO, SWD = TX + 2 * HALO + 1, SH = TY + 2 * HALO;
+    __shared__ uint32_t tile[SH * SWD];
+    const TileCompDesc &tc = tcs[blockIdx.z];
+    if (tc.transform != TYPE || j >= tc.nlevels)
+        return;
+    /* the last level of a plane is done by the fused pack kernel, unless the caller wants the plane */
+    if (!to_plane && j == tc.nlevels - 1)
+        return;
+    const LevelDesc o = tc.lev[j + 1];
+    const int lh = o.u1 - o.u0, lv = o.v1 - o.v0;
+    const int XT = o.u0 + blockIdx.x * TX, YT = o.v0 + blockIdx.y * TY;
+    if (XT >= o.u1 || YT >= o.v1)
+        return;
+    reconstruct_tile<TYPE, TX, TY>(tile, tc, j, coefA, coefIn, XT, YT);
+    uint32_t *out = coefOut + tc.coef_off;
+    const int ostride = (to_plane && j == tc.nlevels - 1) ? tc.width : lh;
+    for (int idx = threadIdx.x; idx < TX * TY; idx += THREADS) {
+        const int r = idx / TX, cx = idx - r * TX;
+        const int X = XT + cx, Y = YT + r;
+        if (X < o.u1 && Y < o.v1)
+            out[(size_t)(Y - o.v0) * ostride + (X - o.u0)] = tile[(r + HALO) * SWD + HALO + cx];
+    }
+    (void)lv;
+}
+
+/* final fixed-point rescale of the 9/7 integer path when the plane itself is the output (jpeg2000dwt.c:534-536) */
+__global__ void rescale97i_kernel(uint32_t *p, size_t n)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n)
+        p[i] = (uint32_t)((int32_t)((int64_t)(int32_t)p[i] + 128) >> 8);
+}
+
+/* ---- last level fused with MCT + level shift + clip + pack -------------------------------------------- */
+template <int TYPE> __device__ __forceinline__ void mct(uint32_t &a, uint32_t &b, uint32_t &c)
+{
+    if (TYPE == J2K_DWT53) {                     /* rct_int, jpeg2000dsp.c:78-91 */
+        const uint32_t g = a - (uint32_t)((int32_t)(c + b) >> 2);
+        const uint32_t r = g + c, bl = g + b;
+        a = r; b = g; c = bl;
+    } else if (TYPE == J2K_DWT97) {              /* ict_float, :43-59 */
+        const float y = __uint_as_float(a), cb = __uint_as_float(b), cr = __uint_as_float(c);
+        const float r = __fadd_rn(y, __fmul_rn(1.402f, cr));
+        const float g = __fsub_rn(__fsub_rn(y, __fmul_rn(0.34413f, cb)), __fmul_rn(0.71414f, cr));
+        const float bl = __fadd_rn(y, __fmul_rn(1.772f, cb));
+        a = __float_as_uint(r); b = __float_as_uint(g); c = __float_as_uint(bl);
+    } else {                                     /* ict_int, :61-76 */
+        const int32_t y = (int32_t)a, cb = (int32_t)b, cr = (int32_t)c;
+        const int32_t r = y + cr + ((int32_t)(26345u * (uint32_t)cr + (1u << 15)) >> 16);
+        const int32_t g = y - ((int32_t)(22553u * (uint32_t)cb + (1u << 15)) >> 16)
+                            - ((int32_t)(46802u * (uint32_t)cr + (1u << 15)) >> 16);
+        const int32_t bl = y + 2 * cb + ((int32_t)((uint32_t)-14942 * (uint32_t)cb + (1u << 15)) >> 16);
+        a = (uint32_t)r; b = (uint32_t)g; c = (uint32_t)bl;
+    }
+}
+
+template <int TYPE> __device__ __forceinline__ int to_pixel(uint32_t raw, int cbps, int shift)
+{
+    int val;
+    if (TYPE == J2K_DWT97)
+        val = __float2int_rn(__uint_as_float(raw));
+    else if (TYPE == J2K_DWT97_INT)
+        val = (int32_t)((int64_t)(int32_t)raw + 128) >> 8;       /* undo I_PRESHIFT (jpeg2000dwt.c:534-536) */
+    else
+        val = (int32_t)raw;
+    val += 1 << (cbps - 1);
+    val = min(max(val, 0), (1 << cbps) - 1);
+    return val << shift;
+}
+
+template <int TYPE, int TX, int TY>
+__global__ void __launch_bounds__(THREADS)
+idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__restrict__ groups,
+                       const uint32_t *__restrict__ coefA, const uint32_t *__restrict__ coefIn0,
+                       const uint32_t *__restrict__ coefIn1, uint8_t *__restrict__ picture,
+                       uint64_t po0, uint64_t po1, uint64_t po2, uint64_t po3, int rb0, int rb1, int rb2, int rb3)
+{
+    using L = Lift<TYPE>;
+    constexpr int HALO = L::HALO, SWD = TX + 2 * HALO + 1, SH = TY + 2 * HALO;
+    extern __shared__ __align__(16) uint32_t dyn[];
+    const PackGroup &g = groups[blockIdx.z];
+    const TileCompDesc &t0 = tcs[g.tc[0]];
+    if (t0.transform != TYPE)
+        return;
+    const int nl = t0.nlevels;
+    const LevelDesc o = t0.lev[nl];
+    const int XT = o.u0 + blockIdx.x * TX, YT = o.v0 + blockIdx.y * TY;
+    if (XT >= o.u1 || YT >= o.v1)
+        return;
+    for (int c = 0; c < g.ncomp; c++) {
+        uint32_t *tile = dyn + (size_t)c * SH * SWD;
+        const TileCompDesc &tc = tcs[g.tc[c]];
+        if (nl > 0) {
+            /* LL of the last level is the output of level nl-2: ping-pong parity */
+            const uint32_t *in = ((nl - 1) & 1) ? coefIn0 : coefIn1;
+            reconstruct_tile<TYPE, TX, TY>(tile, tc, nl - 1, coefA, in, XT, YT);
+        } else {
+            const uint32_t *A = coefA + tc.coef_off;
+            for (int idx = threadIdx.x; idx < TX * TY; idx += THREADS) {
+                const int r = idx / TX, cx = idx - r * TX;
+                const int X = XT + cx, Y = YT + r;
+                if (X < o.u1 && Y < o.v1)
+                    tile[(r + HALO) * SWD + HALO + cx] = A[(size_t)(Y - o.v0) * tc.width + (X - o.u0)];
+            }
+            __syncthreads();
+        }
+    }
+    const uint64_t poff = g.plane == 0 ? po0 : g.plane == 1 ? po1 : g.plane == 2 ? po2 : po3;
+    const int rb = g.plane == 0 ? rb0 : g.plane == 1 ? rb1 : g.plane == 2 ? rb2 : rb3;
+    uint8_t *plane = picture + poff;
+    for (int idx = threadIdx.x; idx < TX * TY; idx += THREADS) {
+        const int r = idx / TX, cx = idx - r * TX;
+        const int X = XT + cx, Y = YT + r;
+        if (X >= o.u1 || Y >= o.v1)
+            continue;
+        uint32_t v[J2K_MAX_COMP];
+#pragma unroll
+        for (int c = 0; c < J2K_MAX_COMP; c++)
+            v[c] = c < g.ncomp ? dyn[(size_t)c * SH * SWD + (r + HALO) * SWD + HALO + cx] : 0;
+        if (g.mct)
+            mct<TYPE>(v[0], v[1], v[2]);
+        const size_t px = (size_t)(t0.out_x + X - o.u0) * g.pixel_stride;
+        uint8_t *row = plane + (size_t)(t0.out_y + Y - o.v0) * rb;
+#pragma unroll
+        for (int c = 0; c < J2K_MAX_COMP; c++) {
+            if (c < g.ncomp) {
+                const int pv = to_pixel<TYPE>(v[c], tcs[g.tc[c]].cbps, g.shift[c]);
+                if (g.wide)
+                    reinterpret_cast<uint16_t *>(row)[px + g.sample_off[c]] = (uint16_t)pv;
+                else
+                    row[px + g.sample_off[c]] = (uint8_t)pv;
+            }
+        }
+    }
+}
+
+template <int TYPE, int TX, int TY> constexpr size_t final_smem(int ncomp)
+{
+    return (size_t)ncomp * (TY + 2 * Lift<TYPE>::HALO) * (TX + 2 * Lift<TYPE>::HALO + 1) * 4;
+}
+
+constexpr int LTX = 128, LTY = 32;   /* intermediate levels */
+constexpr int FTX = 64, FTY = 32;    /* fused last level */
+
+template <int TYPE>
+int run_levels(cudaStream_t stream, const IdwtFrame &f, int max_levels, bool any_type, int max_w[], int max_h[],
+               int to_plane)
+{
+    int launches = 0;
+    if (!any_type)
+        return 0;
+    for (int j = 0; j < max_levels; j++) {
+        if (max_w[j] <= 0)
+            continue;
+        dim3 grid((max_w[j] + LTX - 1) / LTX, (max_h[j] + LTY - 1) / LTY, f.ntcs);
+        const void *in = (j & 1) ? f.coefB : f.coefC;        /* level j reads what level j-1 wrote */
+        void *out = (j & 1) ? f.coefC : f.coefB;
+        idwt_level_kernel<TYPE, LTX, LTY><<<grid, THREADS, 0, stream>>>(
+            f.d_tcs, j, (const uint32_t *)f.coefA, (const uint32_t *)in, (uint32_t *)out, to_plane);
+        launches++;
+    }
+    return launches;
+}
+
+}  // namespace
+
+int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f)
+{
+    int launches = 0;
+    /* grid extents per level and per transform type (host copies of the tables) */
+    for (int type = 0; type < 3; type++) {
+        int mw[J2K_MAX_LEVELS] = { 0 }, mh[J2K_MAX_LEVELS] = { 0 };
+        int maxlev = 0;
+        bool any = false;
+        for (int i = 0; i < f.ntcs; i++) {
+            const TileCompDesc &tc = f.h_tcs[i];
+            if (tc.transform != type)
+                continue;
+            any = true;
+            /* levels 0 .. nlevels-2 go through the level kernel */
+            for (int j = 0; j + 1 < tc.nlevels; j++) {
+                const LevelDesc &o = tc.lev[j + 1];
+                if (o.u1 - o.u0 > mw[j]) mw[j] = o.u1 - o.u0;
+                if (o.v1 - o.v0 > mh[j]) mh[j] = o.v1 - o.v0;
+                if (j + 1 > maxlev) maxlev = j + 1;
+            }
+        }
+        if (type == J2K_DWT53) launches += run_levels<J2K_DWT53>(stream, f, maxlev, any, mw, mh, 0);
+        if (type == J2K_DWT97) launches += run_levels<J2K_DWT97>(stream, f, maxlev, any, mw, mh, 0);
+        if (type == J2K_DWT97_INT) launches += run_levels<J2K_DWT97_INT>(stream, f, maxlev, any, mw, mh, 0);
+        /* fused last level */
+        int gw = 0, gh = 0, maxc = 0;
+        bool anyg = false;
+        for (int i = 0; i < f.ngroups; i++) {
+            const PackGroup &g = f.h_groups[i];
+            const TileCompDesc &tc = f.h_tcs[g.tc[0]];
+            if (tc.transform != type)
+                continue;
+            anyg = true;
+            const LevelDesc &o = tc.lev[tc.nlevels];
+            if (o.u1 - o.u0 > gw) gw = o.u1 - o.u0;
+            if (o.v1 - o.v0 > gh) gh = o.v1 - o.v0;
+            if (g.ncomp > maxc) maxc = g.ncomp;
+        }
+        if (anyg && gw > 0 && gh > 0) {
+            dim3 grid((gw + FTX - 1) / FTX, (gh + FTY - 1) / FTY, f.ngroups);
+#define LAUNCH_FINAL(T)                                                                                     \
+    do {                                                                                                    \
+        size_t sm = final_smem<T, FTX, FTY>(maxc);                                                          \
+        cudaFuncSetAttribute(idwt_final_pack_kernel<T, FTX, FTY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                             (int)sm);                                                                      \
+        idwt_final_pack_kernel<T, FTX, FTY><<<grid, THREADS, sm, stream>>>(                                 \
+            f.d_tcs, f.d_groups, (const uint32_t *)f.coefA, (const uint32_t *)f.coefB,                      \
+            (const uint32_t *)f.coefC, f.picture, f.plane_off[0], f.plane_off[1], f.plane_off[2],           \
+            f.plane_off[3], f.plane_row_bytes[0], f.plane_row_bytes[1], f.plane_row_bytes[2],               \
+            f.plane_row_bytes[3]);                                                                          \
+    } while (0)
+            if (type == J2K_DWT53) LAUNCH_FINAL(J2K_DWT53);
+            if (type == J2K_DWT97) LAUNCH_FINAL(J2K_DWT97);
+            if (type == J2K_DWT97_INT) LAUNCH_FINAL(J2K_DWT97_INT);
+#undef LAUNCH_FINAL
+            launches++;
+        }
+    }
+    return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+/* stage-level entry: one plane, result written back into the plane (Mallat -> image), used by tests */
+int launch_idwt_plane(cudaStream_t stream, int type, const int32_t *border, int levels, void *plane,
+                      void *scratchB, void *scratchC, TileCompDesc *d_tc)
+{
+    if (levels <= 0)
+        return 0;
+    TileCompDesc tc;
+    memset(&tc, 0, sizeof(tc));
+    tc.coef_off = 0;
+    tc.width = border[1] - border[0];
+    tc.height = border[3] - border[2];
+    tc.x0 = border[0];
+    tc.y0 = border[2];
+    tc.nlevels = levels;
+    tc.transform = type;
+    int b[4] = { border[0], border[1], border[2], border[3] };
+    for (int k = levels; k >= 0; k--) {
+        tc.lev[k] = LevelDesc{ b[0], b[1], b[2], b[3] };
+        for (int i = 0; i < 4; i++)
+            b[i] = (b[i] + 1) >> 1;
+    }
+    if (cudaMemcpyAsync(d_tc, &tc, sizeof(tc), cudaMemcpyHostToDevice, stream) != cudaSuccess)
+        return -1;
+    IdwtFrame f;
+    memset(&f, 0, sizeof(f));
+    f.d_tcs = d_tc;
+    f.ntcs = 1;
+    f.coefA = plane;
+    f.coefB = scratchB;
+    f.coefC = scratchC;
+    int launches = 0;
+    for (int j = 0; j < levels; j++) {
+        const LevelDesc &o = tc.lev[j + 1];
+        const int lw = o.u1 - o.u0, lhh = o.v1 - o.v0;
+        if (lw <= 0 || lhh <= 0)
+            continue;
+        dim3 grid((lw + LTX - 1) / LTX, (lhh + LTY - 1) / LTY, 1);
+        const void *in = (j & 1) ? f.coefB : f.coefC;
+        /* the last level cannot go to the plane in place (other CTAs still read its quadrants): use the
+         * ping-pong buffer with the plane's stride and copy back */
+        void *out = (j & 1) ? f.coefC : f.coefB;
+#define LAUNCH_LEVEL(T)                                                                                     \
+    idwt_level_kernel<T, LTX, LTY><<<grid, THREADS, 0, stream>>>(d_tc, j, (const uint32_t *)plane,          \
+                                                                 (const uint32_t *)in, (uint32_t *)out, 1)
+        if (type == J2K_DWT53) LAUNCH_LEVEL(J2K_DWT53);
+        else if (type == J2K_DWT97) LAUNCH_LEVEL(J2K_DWT97);
+        else LAUNCH_LEVEL(J2K_DWT97_INT);
+#undef LAUNCH_LEVEL
+        launches++;
+    }
+    const void *last = ((levels - 1) & 1) ? f.coefC : f.coefB;
+    const size_t n = (size_t)tc.width * tc.height;
+    if (cudaMemcpyAsync(plane, last, n * 4, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+        return -1;
+    if (type == J2K_DWT97_INT) {
+        rescale97i_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>((uint32_t *)plane, n);
+        launches++;
+    }
+    return cudaGetLastError() == cudaSuccess ? launches : -1;
+}
+
+}  // namespace b200j2k

@@ -1,0 +1,43 @@
+/* j2k_kernels.h -- launchers of the sm_100a kernels (ht_block.cu, idwt.cu), host-callable. */
+#ifndef B200J2K_KERNELS_H
+#define B200J2K_KERNELS_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "j2k_plan.h"
+
+#define B200J2K_KERR_INVALID (-1094995529)
+
+namespace b200j2k {
+
+/* HT block decode + dequantisation.  order: optional list of descriptor indices (nullptr = 0..n-1).
+ * refine = blocks carrying SigProp/MagRef passes (needs the shared-memory sample copy).
+ * Returns 1 when a kernel was queued, 0 when there was nothing to do, < 0 on launch failure. */
+int launch_ht_decode(cudaStream_t stream, bool refine, const CblkDesc *descs, const uint32_t *order, int nblocks,
+                     const uint8_t *bytes, const BandDesc *bands, void *coef, int32_t *status,
+                     int max_Lcup, int maxw, int maxh);
+size_t ht_smem_bytes(bool refine, int stream_words, int maxQW, int maxw, int maxh);
+
+/* Inverse DWT levels + final MCT / level shift / clip / pack.
+ * tcs/groups: device copies of the plan tables.  coefA: HT output (Mallat layout), coefB/coefC: LL
+ * ping-pong, picture: packed output.  Returns the number of kernels queued or < 0. */
+struct IdwtFrame {
+    const TileCompDesc *d_tcs;    /* device */
+    const PackGroup *d_groups;    /* device */
+    const TileCompDesc *h_tcs;    /* host copies, for grid sizing */
+    const PackGroup *h_groups;
+    int ntcs, ngroups;
+    void *coefA, *coefB, *coefC;
+    uint8_t *picture;
+    uint64_t plane_off[4];
+    int plane_row_bytes[4];
+};
+int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f);
+
+/* one plane, all levels, result left in `plane` (stage-level entry point for parity tests) */
+int launch_idwt_plane(cudaStream_t stream, int type, const int32_t *border, int levels, void *plane,
+                      void *scratchB, void *scratchC, TileCompDesc *d_tc_scratch);
+
+}  // namespace b200j2k
+#endif

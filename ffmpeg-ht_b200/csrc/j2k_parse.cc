@@ -1,0 +1,1144 @@
+/*
+ * j2k_parse.cc -- codestream -> flat frame plan (host, serial work).  See j2k_parse.h.
+ *
+ * Reference behaviour restated here (file:line in libavcodec/ of sandflow/ffmpeg-ht):
+ *   SIZ jpeg2000dec.c:197-422   CAP :424-489   COD/COC :492-641   QCD/QCC :676-758   RGN :643-674
+ *   SOT :822-873   main loop / SOD bookkeeping :2425-2637   pixel format choice :134-193, :335-363
+ *   init_tile :1016-1070   component/band/precinct/code-block geometry jpeg2000.c:274-577
+ *   step sizes jpeg2000.c:214-272   packet headers jpeg2000dec.c:1136-1542 (HT paths)
+ *   progression orders :1544-1833
+ * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 MQ blocks, MIXED/HTDECLARED sets, POC,
+ * PPM/PPT, JP2 wrapper, lowres -- SURVEY.md section 8(f) "next".
+ */
+#include "j2k_parse.h"
+
+#include <cmath>
+#include <cstring>
+
+#include "../../include/b200j2k.h"
+
+namespace b200j2k {
+
+namespace {
+
+inline int ceildiv(int a, int b) { return (int)(((int64_t)a + b - 1) / b); }
+inline int ceildivpow2(int a, int b) { return (int)(-((-(int64_t)a) >> b)); }
+inline int imin(int a, int b) { return a < b ? a : b; }
+inline int imax(int a, int b) { return a > b ? a : b; }
+inline int clip64(int64_t v, int lo, int hi) { return v < lo ? lo : v > hi ? hi : (int)v; }
+inline int ilog2(unsigned v) { int n = 0; while (v >>= 1) n++; return n; }
+inline unsigned rd16(const uint8_t *p) { return (unsigned)(p[0] << 8) | p[1]; }
+inline uint32_t rd32(const uint8_t *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+
+int parse_cox(const uint8_t *p, const uint8_t *end, CodSty *c, int flags)
+{
+    if (end - p < 5)
+        return B200J2K_ERR_INVALIDDATA;
+    c->nres = p[0] + 1;
+    if (c->nres > J2K_MAX_LEVELS)
+        return B200J2K_ERR_INVALIDDATA;
+    c->l2cw = (p[1] & 15) + 2;
+    c->l2ch = (p[2] & 15) + 2;
+    if (c->l2cw > 10 || c->l2ch > 10 || c->l2cw + c->l2ch > 12)
+        return B200J2K_ERR_INVALIDDATA;
+    c->cblk_style = p[3];
+    c->transform = p[4];
+    if (c->transform > 1)
+        return B200J2K_ERR_INVALIDDATA;
+    if ((flags & B200J2K_FLAG_BITEXACT) && c->transform == J2K_DWT97)
+        c->transform = J2K_DWT97_INT;
+    p += 5;
+    if (c->csty & 1) {
+        for (int i = 0; i < c->nres; i++) {
+            if (p >= end)
+                return B200J2K_ERR_INVALIDDATA;
+            c->ppx[i] = *p & 15;
+            c->ppy[i] = *p >> 4;
+            p++;
+            if (i && (!c->ppx[i] || !c->ppy[i]))
+                return B200J2K_ERR_INVALIDDATA;
+        }
+    } else {
+        memset(c->ppx, 15, sizeof(c->ppx));
+        memset(c->ppy, 15, sizeof(c->ppy));
+    }
+    return 0;
+}
+
+int parse_qcx(const uint8_t *p, int n, QntSty *q)
+{
+    if (n < 1)
+        return B200J2K_ERR_INVALIDDATA;
+    q->nguard = p[0] >> 5;
+    q->style = p[0] & 31;
+    p++;
+    n--;
+    if (q->style == 0) {
+        if (n > 96)
+            return B200J2K_ERR_INVALIDDATA;
+        for (int i = 0; i < n; i++)
+            q->expn[i] = p[i] >> 3;
+    } else if (q->style == 1) {
+        if (n < 2)
+            return B200J2K_ERR_INVALIDDATA;
+        unsigned x = rd16(p);
+        q->expn[0] = x >> 11;
+        q->mant[0] = x & 0x7FF;
+        for (int i = 1; i < 96; i++) {
+            q->expn[i] = (uint8_t)imax(0, q->expn[0] - (i - 1) / 3);
+            q->mant[i] = q->mant[0];
+        }
+    } else {
+        n >>= 1;
+        if (n > 96)
+            return B200J2K_ERR_INVALIDDATA;
+        for (int i = 0; i < n; i++) {
+            unsigned x = rd16(p + 2 * i);
+            q->expn[i] = x >> 11;
+            q->mant[i] = x & 0x7FF;
+        }
+    }
+    return 0;
+}
+
+/* raw codestream => all_pix_fmts order: first format with enough depth and matching subsampling */
+int choose_pix(const Header &h)
+{
+    bool sub = false;
+    for (int i = 0; i < h.ncomp; i++)
+        sub |= h.cdx[i] != 1 || h.cdy[i] != 1;
+    bool wide = h.precision > 8;
+    if (h.precision > 16)
+        return B200J2K_PIX_NONE;
+    if (!sub) {
+        switch (h.ncomp) {
+        case 1: return wide ? B200J2K_PIX_GRAY16 : B200J2K_PIX_GRAY8;
+        case 2: return wide ? B200J2K_PIX_YA16 : B200J2K_PIX_YA8;
+        case 3: return wide ? B200J2K_PIX_RGB48 : B200J2K_PIX_RGB24;
+        case 4: return wide ? B200J2K_PIX_RGBA64 : B200J2K_PIX_RGBA;
+        }
+        return B200J2K_PIX_NONE;
+    }
+    if (h.ncomp == 3 && h.cdx[0] == 1 && h.cdy[0] == 1 && h.cdx[1] == h.cdx[2] && h.cdy[1] == h.cdy[2]) {
+        int cx = h.cdx[1], cy = h.cdy[1];
+        bool ok = (cx == 2 && cy == 2) || (cx == 2 && cy == 1) || (cx == 1 && cy == 2);
+        if (!wide)
+            ok |= (cx == 4 && cy == 1) || (cx == 4 && cy == 4);
+        if (ok)
+            return wide ? B200J2K_PIX_PLANAR16 : B200J2K_PIX_PLANAR8;
+    }
+    return B200J2K_PIX_NONE;
+}
+
+/* band step size, float path, same operation order as jpeg2000.c:214-272 */
+float band_stepsize(const CodSty &c, const QntSty &q, int bandno, int gbandno, int r, int cbps)
+{
+    float f;
+    if (q.style == 0) {
+        f = 1;
+    } else {
+        union { uint32_t u; float f; } e;
+        e.u = (uint32_t)((cbps - q.expn[gbandno]) + 127) << 23;
+        f = e.f;
+        f *= q.mant[gbandno] / 2048.0 + 1.0;
+    }
+    if (c.transform != J2K_DWT53) {
+        int lband = 0;
+        switch (bandno + (r > 0)) {
+        case 1: case 2:
+            f *= 0.812893066115961f * 2;
+            lband = 1;
+            break;
+        case 3:
+            f *= 0.812893066115961f * 0.812893066115961f * 4;
+            break;
+        }
+        f *= pow(1.230174104914001f, 2 * (c.nres - r) + lband - 2);
+    }
+    if (f > (INT32_MAX >> 15))
+        f = 0;
+    return f;
+}
+
+uint32_t tagtree_nodes(int w, int h)
+{
+    uint32_t n = 1;
+    while (w > 1 || h > 1) {
+        n += (uint32_t)w * h;
+        w = (w + 1) >> 1;
+        h = (h + 1) >> 1;
+    }
+    return n;
+}
+
+}  // namespace
+
+const char *pix_fmt_name(int pix)
+{
+    switch (pix) {
+    case B200J2K_PIX_GRAY8: return "gray";
+    case B200J2K_PIX_GRAY16: return "gray16le";
+    case B200J2K_PIX_YA8: return "ya8";
+    case B200J2K_PIX_YA16: return "ya16le";
+    case B200J2K_PIX_RGB24: return "rgb24";
+    case B200J2K_PIX_RGB48: return "rgb48le";
+    case B200J2K_PIX_RGBA: return "rgba";
+    case B200J2K_PIX_RGBA64: return "rgba64le";
+    case B200J2K_PIX_PLANAR8: return "planar8";
+    case B200J2K_PIX_PLANAR16: return "planar16";
+    }
+    return "none";
+}
+
+/* ---- marker segments -------------------------------------------------------------------------------- */
+int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *main_header_len)
+{
+    const uint8_t *p = pkt, *end = pkt + size;
+    Header &h = hdr;
+    h = Header();
+    parts_.clear();
+    *main_header_len = 0;
+    if (size >= 12 && rd32(p) == 12 && rd32(p + 4) == 0x6A502020u)
+        return B200J2K_ERR_PATCHWELCOME;                  /* JP2 wrapper: next row N3 */
+    while (end - p >= 3 && rd16(p) != 0xFF4F)
+        p++;
+    if (end - p < 2 || rd16(p) != 0xFF4F)
+        return B200J2K_ERR_INVALIDDATA;
+    p += 2;
+    int cur_tile = -1, cur_tp = 0;
+    const uint8_t *tp_end = nullptr;
+    for (;;) {
+        if (end - p < 2)
+            break;
+        unsigned marker = rd16(p);
+        const uint8_t *marker_pos = p;
+        p += 2;
+        if (marker >= 0xFF30 && marker <= 0xFF3F)
+            continue;
+        if (marker == 0xFF93) {                           /* SOD */
+            if (parts_.empty() || cur_tile < 0 || tp_end < p)
+                return B200J2K_ERR_INVALIDDATA;
+            auto &pv = parts_[cur_tile];
+            if ((int)pv.size() <= cur_tp)
+                pv.resize(cur_tp + 1, TilePart{ nullptr, nullptr });
+            pv[cur_tp] = TilePart{ p, tp_end };
+            p = tp_end;
+            continue;
+        }
+        if (marker == 0xFFD9)
+            break;
+        if (end - p < 2)
+            break;
+        int len = (int)rd16(p);
+        if (len < 2 || end - p < len)
+            break;
+        const uint8_t *seg = p + 2, *segend = p + len;
+        int ret = 0;
+        switch (marker) {
+        case 0xFF51: {
+            if (h.ncomp || segend - seg < 36)
+                return B200J2K_ERR_INVALIDDATA;
+            h.rsiz = (int)rd16(seg);
+            h.W = (int)rd32(seg + 2); h.H = (int)rd32(seg + 6); h.X0 = (int)rd32(seg + 10); h.Y0 = (int)rd32(seg + 14);
+            h.TW = (int)rd32(seg + 18); h.TH = (int)rd32(seg + 22); h.TX0 = (int)rd32(seg + 26); h.TY0 = (int)rd32(seg + 30);
+            int nc = (int)rd16(seg + 34);
+            if (h.W <= 0 || h.H <= 0 || (int64_t)h.W * h.H > INT32_MAX)
+                return B200J2K_ERR_PATCHWELCOME;
+            if (nc <= 0)
+                return B200J2K_ERR_INVALIDDATA;
+            if (nc > 4)
+                return B200J2K_ERR_PATCHWELCOME;
+            if (h.rsiz == 3 || h.rsiz == 4)
+                return B200J2K_ERR_PATCHWELCOME;          /* D-Cinema => XYZ12, not an HT profile */
+            if (h.TX0 < 0 || h.TY0 < 0 || h.X0 < h.TX0 || h.Y0 < h.TY0 ||
+                h.TW + (int64_t)h.TX0 <= h.X0 || h.TH + (int64_t)h.TY0 <= h.Y0)
+                return B200J2K_ERR_INVALIDDATA;
+            if (h.X0 >= h.W || h.Y0 >= h.H || h.TW <= 0 || h.TH <= 0)
+                return B200J2K_ERR_INVALIDDATA;
+            if (segend - seg < 36 + 3 * nc)
+                return B200J2K_ERR_INVALIDDATA;
+            h.ncomp = nc;
+            for (int i = 0; i < nc; i++) {
+                unsigned x = seg[36 + 3 * i];
+                h.cbps[i] = (int)(x & 0x7F) + 1;
+                h.precision = imax(h.precision, h.cbps[i]);
+                h.cdx[i] = seg[37 + 3 * i];
+                h.cdy[i] = seg[38 + 3 * i];
+                if (!h.cdx[i] || h.cdx[i] == 3 || h.cdx[i] > 4 || !h.cdy[i] || h.cdy[i] == 3 || h.cdy[i] > 4)
+                    return B200J2K_ERR_INVALIDDATA;
+            }
+            h.ntx = ceildiv(h.W - h.TX0, h.TW);
+            h.nty = ceildiv(h.H - h.TY0, h.TH);
+            if ((int64_t)h.ntx * h.nty * 14 > size)
+                return B200J2K_ERR_EINVAL;
+            parts_.assign((size_t)h.ntx * h.nty, {});
+            int ow = h.W - h.X0, oh = h.H - h.Y0;
+            h.out_w = ceildiv(ow, h.cdx[0]);
+            h.out_h = ceildiv(oh, h.cdy[0]);
+            for (int i = 1; i < nc; i++) {
+                h.out_w = imax(h.out_w, ceildiv(ow, h.cdx[i]));
+                h.out_h = imax(h.out_h, ceildiv(oh, h.cdy[i]));
+            }
+            h.pix = choose_pix(h);
+            if (!h.pix)
+                return B200J2K_ERR_PATCHWELCOME;
+            seg += 36 + 3 * nc;
+            break;
+        }
+        case 0xFF50: {
+            if (segend - seg < 6)
+                return B200J2K_ERR_INVALIDDATA;
+            uint32_t pcap = rd32(seg);
+            seg += 4;
+            unsigned ccap15 = 0;
+            h.isHT = (pcap >> 17) & 1;
+            for (int i = 0; i < 32; i++)
+                if ((pcap >> (31 - i)) & 1) {
+                    if (segend - seg < 2)
+                        return B200J2K_ERR_INVALIDDATA;
+                    if (i == 14)
+                        ccap15 = rd16(seg);
+                    seg += 2;
+                }
+            if (h.isHT) {
+                h.cap_b14 = (ccap15 >> 14) & 3;
+                if (h.cap_b14 == 2)
+                    return B200J2K_ERR_EINVAL;
+                if ((ccap15 >> 13) & 1)
+                    return B200J2K_ERR_PATCHWELCOME;
+                h.cap_b05 = (ccap15 >> 5) & 1;
+                int P = ccap15 & 31, B = !P ? 8 : P < 20 ? P + 8 : P < 31 ? 4 * (P - 19) + 27 : 74;
+                if (B > 31)
+                    return B200J2K_ERR_PATCHWELCOME;
+            }
+            break;
+        }
+        case 0xFF52: {
+            if (cur_tile >= 0 || segend - seg < 5)
+                return B200J2K_ERR_INVALIDDATA;
+            CodSty tmp;
+            tmp.csty = seg[0];
+            tmp.prog = seg[1];
+            tmp.nlayers = (int)rd16(seg + 2);
+            tmp.mct = seg[4];
+            if (tmp.mct && h.ncomp < 3)
+                return B200J2K_ERR_INVALIDDATA;
+            if ((ret = parse_cox(seg + 5, segend, &tmp, flags)) < 0)
+                return ret;
+            tmp.init = 1;
+            for (int c = 0; c < h.ncomp; c++)
+                if (!h.had_coc[c])
+                    h.cod[c] = tmp;
+            seg += 10 + ((tmp.csty & 1) ? tmp.nres : 0);
+            break;
+        }
+        case 0xFF53: {
+            if (cur_tile >= 0 || segend - seg < 2)
+                return B200J2K_ERR_INVALIDDATA;
+            int c = seg[0];
+            if (c >= h.ncomp)
+                return B200J2K_ERR_INVALIDDATA;
+            CodSty *cs = &h.cod[c];
+            int keep = cs->csty & 6;
+            cs->csty = seg[1] | keep;
+            if ((ret = parse_cox(seg + 2, segend, cs, flags)) < 0)
+                return ret;
+            h.had_coc[c] = 1;
+            cs->init = 1;
+            seg += 7 + ((cs->csty & 1) ? cs->nres : 0);
+            break;
+        }
+        case 0xFF5C: {
+            if (cur_tile >= 0)
+                return B200J2K_ERR_INVALIDDATA;
+            QntSty tmp;
+            memset(&tmp, 0, sizeof(tmp));
+            if ((ret = parse_qcx(seg, len - 2, &tmp)) < 0)
+                return ret;
+            for (int c = 0; c < h.ncomp; c++)
+                if (!h.had_qcc[c])
+                    h.qnt[c] = tmp;
+            seg = segend;
+            break;
+        }
+        case 0xFF5D: {
+            if (cur_tile >= 0 || segend - seg < 1)
+                return B200J2K_ERR_INVALIDDATA;
+            int c = seg[0];
+            if (c >= h.ncomp)
+                return B200J2K_ERR_INVALIDDATA;
+            h.had_qcc[c] = 1;
+            if ((ret = parse_qcx(seg + 1, len - 3, &h.qnt[c])) < 0)
+                return ret;
+            seg = segend;
+            break;
+        }
+        case 0xFF5E: {
+            if (segend - seg < 3 || seg[1] != 0 || seg[0] >= h.ncomp)
+                return B200J2K_ERR_INVALIDDATA;
+            if (seg[2] > 30)
+                return B200J2K_ERR_PATCHWELCOME;
+            if (cur_tile >= 0)
+                return B200J2K_ERR_PATCHWELCOME;          /* tile-specific ROI: not in the first bar */
+            h.roi[seg[0]] = seg[2];
+            seg += 3;
+            break;
+        }
+        case 0xFF90: {
+            if (parts_.empty() || segend - seg < 8)
+                return B200J2K_ERR_INVALIDDATA;
+            if (cur_tile < 0)
+                *main_header_len = (size_t)(marker_pos - pkt);
+            int isot = (int)rd16(seg);
+            if (isot >= h.ntx * h.nty)
+                return B200J2K_ERR_INVALIDDATA;
+            uint32_t psot = rd32(seg + 2);
+            int tpsot = seg[6];
+            int64_t left = end - (seg + 8);
+            if (!psot)
+                psot = (uint32_t)(left + len + 2);
+            if ((int64_t)psot > left + len + 2)
+                return B200J2K_ERR_INVALIDDATA;
+            if (tpsot >= 32)
+                return B200J2K_ERR_PATCHWELCOME;
+            cur_tile = isot;
+            cur_tp = tpsot;
+            tp_end = seg + 8 + psot - len - 2;
+            seg += 8;
+            break;
+        }
+        case 0xFF5F: case 0xFF60: case 0xFF61:            /* POC, PPM, PPT */
+            return B200J2K_ERR_PATCHWELCOME;
+        default:
+            seg = segend;
+            break;
+        }
+        if (seg != segend)
+            return -1;
+        p = segend;
+    }
+    consumed = (int64_t)(p - pkt);
+    if (!h.ncomp || parts_.empty())
+        return B200J2K_ERR_INVALIDDATA;
+    if (!*main_header_len)
+        *main_header_len = (size_t)(p - pkt);
+    for (int c = 0; c < h.ncomp; c++) {
+        if (!h.cod[c].init)
+            return B200J2K_ERR_INVALIDDATA;
+        if (h.cod[c].transform == J2K_DWT53)
+            h.lossless = 1;
+    }
+    /* output planes */
+    const int bps = h.precision > 8 ? 2 : 1;
+    const bool planar = h.pix == B200J2K_PIX_PLANAR8 || h.pix == B200J2K_PIX_PLANAR16;
+    picture_bytes = 0;
+    if (!planar) {
+        nplanes = 1;
+        plane_w[0] = h.out_w;
+        plane_h[0] = h.out_h;
+        plane_row_bytes[0] = h.out_w * h.ncomp * bps;
+        plane_off[0] = 0;
+        picture_bytes = (uint64_t)plane_row_bytes[0] * h.out_h;
+    } else {
+        nplanes = h.ncomp;
+        for (int c = 0; c < h.ncomp; c++) {
+            plane_w[c] = c ? ceildiv(h.out_w, h.cdx[c]) : h.out_w;
+            plane_h[c] = c ? ceildiv(h.out_h, h.cdy[c]) : h.out_h;
+            plane_row_bytes[c] = plane_w[c] * bps;
+            plane_off[c] = picture_bytes;
+            picture_bytes += (uint64_t)plane_row_bytes[c] * plane_h[c];
+        }
+    }
+    return 0;
+}
+
+/* ---- geometry (cached) ------------------------------------------------------------------------------ */
+int Parser::build_geometry(int flags)
+{
+    const Header &h = hdr;
+    tiles_.clear(); res_.clear(); precs_.clear(); cblk_template_.clear();
+    bands.clear(); tcs.clear(); groups.clear();
+    tag_total_ = 0;
+    coef_elems = 0;
+    ll_elems = 0;
+    max_levels = 0;
+    max_w = max_h = 0;
+    const int ntiles = h.ntx * h.nty;
+    tiles_.resize(ntiles);
+    const bool planar = h.pix == B200J2K_PIX_PLANAR8 || h.pix == B200J2K_PIX_PLANAR16;
+    const bool wide = h.precision > 8;
+    const bool msb16 = h.pix == B200J2K_PIX_RGB48 || h.pix == B200J2K_PIX_RGBA64 || h.pix == B200J2K_PIX_GRAY16;
+    const int out_precision = !wide ? 8 : msb16 ? 16 : h.precision;
+
+    for (int tileno = 0; tileno < ntiles; tileno++) {
+        TileGeom &t = tiles_[tileno];
+        const int tx = tileno % h.ntx, ty = tileno / h.ntx;
+        t.c.x0 = clip64((int64_t)tx * h.TW + h.TX0, h.X0, h.W);
+        t.c.x1 = clip64((int64_t)(tx + 1) * h.TW + h.TX0, h.X0, h.W);
+        t.c.y0 = clip64((int64_t)ty * h.TH + h.TY0, h.Y0, h.H);
+        t.c.y1 = clip64((int64_t)(ty + 1) * h.TH + h.TY0, h.Y0, h.H);
+        const int first_tc = (int)tcs.size();
+        for (int c = 0; c < h.ncomp; c++) {
+            const CodSty &cs = h.cod[c];
+            const QntSty &qs = h.qnt[c];
+            if (h.isHT && !h.cap_b05 && !cs.transform)
+                return B200J2K_ERR_INVALIDDATA;
+            if (h.isHT && h.cap_b14 != (cs.cblk_style >> 6) && h.cap_b14 != 0)
+                return B200J2K_ERR_INVALIDDATA;
+            if (!(cs.cblk_style & 0x40) || (cs.cblk_style & 0x80))
+                return B200J2K_ERR_PATCHWELCOME;          /* Part-1 MQ or MIXED code-blocks */
+            Rect cc;
+            cc.x0 = ceildiv(t.c.x0, h.cdx[c]); cc.x1 = ceildiv(t.c.x1, h.cdx[c]);
+            cc.y0 = ceildiv(t.c.y0, h.cdy[c]); cc.y1 = ceildiv(t.c.y1, h.cdy[c]);
+            t.comp[c] = cc;
+            const int cw = cc.x1 - cc.x0, ch = cc.y1 - cc.y0;
+            if (cw > 32768 || ch > 32768)
+                return B200J2K_ERR_PATCHWELCOME;
+
+            TileCompDesc tc;
+            memset(&tc, 0, sizeof(tc));
+            tc.coef_off = (uint32_t)coef_elems;
+            tc.width = cw; tc.height = ch;
+            tc.x0 = cc.x0; tc.y0 = cc.y0;
+            tc.nlevels = cs.nres - 1;
+            tc.transform = cs.transform;
+            tc.comp = c;
+            tc.out_x = cc.x0 - ceildiv(h.X0, h.cdx[c]);
+            tc.out_y = cc.y0 - ceildiv(h.Y0, h.cdy[c]);
+            tc.cbps = h.cbps[c];
+            {
+                int b[4] = { cc.x0, cc.x1, cc.y0, cc.y1 };
+                for (int k = tc.nlevels; k >= 0; k--) {
+                    tc.lev[k] = LevelDesc{ b[0], b[1], b[2], b[3] };
+                    for (int i = 0; i < 4; i++)
+                        b[i] = (b[i] + 1) >> 1;
+                }
+            }
+            max_levels = imax(max_levels, tc.nlevels);
+            if ((uint64_t)coef_elems + (uint64_t)cw * ch + 64 > 0xFFFFFFFFull)
+                return B200J2K_ERR_PATCHWELCOME;
+            coef_elems += ((uint64_t)cw * ch + 63) & ~63ull;
+
+            t.res_base[c] = (uint32_t)res_.size();
+            res_.resize(res_.size() + cs.nres);
+            int gband = 0;
+            for (int r = 0; r < cs.nres; r++) {
+                ResGeom &rl = res_[t.res_base[c] + r];
+                const int decl = cs.nres - r;
+                rl.c.x0 = ceildivpow2(cc.x0, decl - 1); rl.c.x1 = ceildivpow2(cc.x1, decl - 1);
+                rl.c.y0 = ceildivpow2(cc.y0, decl - 1); rl.c.y1 = ceildivpow2(cc.y1, decl - 1);
+                rl.ppx = cs.ppx[r]; rl.ppy = cs.ppy[r];
+                rl.nbands = r == 0 ? 1 : 3;
+                rl.npx = rl.c.x1 == rl.c.x0 ? 0 : ceildivpow2(rl.c.x1, rl.ppx) - (rl.c.x0 >> rl.ppx);
+                rl.npy = rl.c.y1 == rl.c.y0 ? 0 : ceildivpow2(rl.c.y1, rl.ppy) - (rl.c.y0 >> rl.ppy);
+                for (int b = 0; b < rl.nbands; b++, gband++) {
+                    BandGeom &bd = rl.band[b];
+                    int bppx, bppy;
+                    if (r == 0) {
+                        bd.c = rl.c;
+                        bppx = rl.ppx; bppy = rl.ppy;
+                    } else {
+                        const int xo = (b + 1) & 1, yo = ((b + 1) >> 1) & 1;
+                        bd.c.x0 = ceildivpow2(cc.x0 - (xo << (decl - 1)), decl);
+                        bd.c.x1 = ceildivpow2(cc.x1 - (xo << (decl - 1)), decl);
+                        bd.c.y0 = ceildivpow2(cc.y0 - (yo << (decl - 1)), decl);
+                        bd.c.y1 = ceildivpow2(cc.y1 - (yo << (decl - 1)), decl);
+                        bppx = rl.ppx - 1; bppy = rl.ppy - 1;
+                    }
+                    bd.empty = bd.c.x0 == bd.c.x1 || bd.c.y0 == bd.c.y1;
+                    const int l2cw = imin(cs.l2cw, bppx), l2ch = imin(cs.l2ch, bppy);
+                    const int M_b = qs.expn[gband] + qs.nguard - 1;
+                    if (!bd.empty && (M_b >= 31 || M_b < 0))
+                        return B200J2K_ERR_PATCHWELCOME;   /* jpeg2000dec.c:2246-2249 */
+                    /* dequantisation constants: D1-D3 */
+                    BandDesc bdesc;
+                    memset(&bdesc, 0, sizeof(bdesc));
+                    {
+                        float fstep = band_stepsize(cs, qs, b, gband, r, h.cbps[c]);
+                        bdesc.i_stepsize = (int32_t)floorf(fstep * (1 << 15));
+                        const int downshift = 31 - imax(M_b, 0);
+                        float fscale = fstep;
+                        fscale /= (float)(1 << imin(downshift, 30));
+                        bdesc.fscale = fscale;
+                        float s = fscale;
+                        s *= (float)(1 << 6);
+                        s *= (float)(1 << (16 + 8));
+                        bdesc.iscale = (int32_t)(s + 0.5);
+                    }
+                    bd.band_index = (int)bands.size();
+                    bands.push_back(bdesc);
+                    bd.prec_base = (uint32_t)precs_.size();
+                    const int nprec = rl.npx * rl.npy;
+                    /* Mallat placement of the band inside the plane (jpeg2000.c:365-376) */
+                    int offx = 0, offy = 0;
+                    if (r > 0) {
+                        const ResGeom &lo = res_[t.res_base[c] + r - 1];
+                        if ((b + 1) & 1) offx = lo.c.x1 - lo.c.x0;
+                        if ((b + 1) & 2) offy = lo.c.y1 - lo.c.y0;
+                    }
+                    for (int pn = 0; pn < nprec; pn++) {
+                        PrecGeom pg;
+                        memset(&pg, 0, sizeof(pg));
+                        pg.cblk_base = (uint32_t)cblk_template_.size();
+                        if (!bd.empty) {
+                            Rect pc;
+                            pc.x0 = ((rl.c.x0 >> rl.ppx) + pn % rl.npx) * (1 << bppx);
+                            pc.y0 = ((rl.c.y0 >> rl.ppy) + pn / rl.npx) * (1 << bppy);
+                            pc.x1 = pc.x0 + (1 << bppx);
+                            pc.y1 = pc.y0 + (1 << bppy);
+                            pc.x0 = imax(pc.x0, bd.c.x0); pc.x1 = imin(pc.x1, bd.c.x1);
+                            pc.y0 = imax(pc.y0, bd.c.y0); pc.y1 = imin(pc.y1, bd.c.y1);
+                            pg.ncw = ceildivpow2(pc.x1, l2cw) - (pc.x0 >> l2cw);
+                            pg.nch = ceildivpow2(pc.y1, l2ch) - (pc.y0 >> l2ch);
+                            if (pg.ncw < 0 || pg.nch < 0 || pc.x1 <= pc.x0 || pc.y1 <= pc.y0)
+                                pg.ncw = pg.nch = 0;
+                            for (int k = 0; k < pg.ncw * pg.nch; k++) {
+                                int gx = ((pc.x0 >> l2cw) << l2cw) + ((k % pg.ncw) << l2cw);
+                                int gy = ((pc.y0 >> l2ch) << l2ch) + ((k / pg.ncw) << l2ch);
+                                int x0 = imax(gx, pc.x0), x1 = imin(gx + (1 << l2cw), pc.x1);
+                                int y0 = imax(gy, pc.y0), y1 = imin(gy + (1 << l2ch), pc.y1);
+                                CblkDesc d;
+                                memset(&d, 0, sizeof(d));
+                                d.w = (uint16_t)(x1 - x0);
+                                d.h = (uint16_t)(y1 - y0);
+                                d.dst_stride = (uint32_t)cw;
+                                d.dst_off = tc.coef_off + (uint32_t)(y0 - bd.c.y0 + offy) * (uint32_t)cw + (uint32_t)(x0 - bd.c.x0 + offx);
+                                d.M_b = (uint8_t)M_b;
+                                d.flags = (uint8_t)(((cs.cblk_style & 8) ? 1 : 0) | (cs.transform << 1));
+                                d.roi_shift = (uint8_t)h.roi[c];
+                                d.band = (uint16_t)bd.band_index;
+                                if (bands.size() > 65535)
+                                    return B200J2K_ERR_PATCHWELCOME;
+                                max_w = max_w > d.w ? max_w : d.w;
+                                max_h = max_h > d.h ? max_h : d.h;
+                                cblk_template_.push_back(d);
+                            }
+                        }
+                        pg.tag_nodes = tagtree_nodes(pg.ncw, pg.nch);
+                        pg.tag_base = tag_total_;
+                        tag_total_ += 2 * pg.tag_nodes;
+                        precs_.push_back(pg);
+                    }
+                }
+            }
+            /* LL ping-pong space: the largest intermediate resolution of this plane */
+            if (tc.nlevels >= 1) {
+                const LevelDesc &l = tc.lev[tc.nlevels - 1];
+                uint64_t n = (uint64_t)(l.u1 - l.u0) * (uint64_t)(l.v1 - l.v0);
+                (void)n;
+            }
+            tcs.push_back(tc);
+        }
+        /* pack groups (mct_decode + write_frame, jpeg2000dec.c:2183-2209, :2301-2366) */
+        if (!planar) {
+            PackGroup g;
+            memset(&g, 0, sizeof(g));
+            g.ncomp = h.ncomp;
+            g.plane = 0;
+            g.pixel_stride = h.ncomp;
+            g.wide = wide;
+            for (int c = 0; c < h.ncomp; c++) {
+                g.tc[c] = first_tc + c;
+                g.sample_off[c] = c;
+                g.shift[c] = out_precision - h.cbps[c];
+                tcs[first_tc + c].group = (int)groups.size();
+            }
+            bool ok = h.cod[0].mct != 0 && h.ncomp >= 3;
+            for (int i = 1; i < 3 && ok; i++)
+                ok = h.cod[0].transform == h.cod[i].transform && !memcmp(&t.comp[0], &t.comp[i], sizeof(Rect));
+            g.mct = ok;
+            groups.push_back(g);
+        } else {
+            for (int c = 0; c < h.ncomp; c++) {
+                PackGroup g;
+                memset(&g, 0, sizeof(g));
+                g.ncomp = 1;
+                g.tc[0] = first_tc + c;
+                g.plane = c;
+                g.pixel_stride = 1;
+                g.shift[0] = out_precision - h.cbps[c];
+                g.wide = wide;
+                tcs[first_tc + c].group = (int)groups.size();
+                groups.push_back(g);
+            }
+        }
+    }
+    ll_elems = coef_elems;   /* same offsets are used in the ping-pong buffers; they only hold <= 1/4 of each plane */
+    (void)flags;
+    return 0;
+}
+
+/* ---- packet-header bit reader (jpeg2000dec.c:70-90) ------------------------------------------------ */
+inline int Parser::bits(int n)
+{
+    int res = 0;
+    while (--n >= 0) {
+        res <<= 1;
+        if (bit_index_ == 0) {
+            unsigned c = bp_ < bend_ ? *bp_++ : 0;
+            bit_index_ = 7 + (c != 0xFF);
+        }
+        bit_index_--;
+        res |= ((bp_ < bend_ ? *bp_ : 0) >> bit_index_) & 1;
+    }
+    return res;
+}
+
+inline void Parser::flush()
+{
+    unsigned c = bp_ < bend_ ? *bp_++ : 0;
+    if (c == 0xFF && bp_ < bend_)
+        bp_++;
+    bit_index_ = 8;
+}
+
+/* tag tree walk on flat per-frame node state (jpeg2000dec.c:93-131) */
+int Parser::tagtree_decode(uint32_t base, int ncw, int nch, int leaf, int threshold)
+{
+    uint32_t stack[16];
+    int sp = -1;
+    int w = ncw, h = nch, x = leaf % ncw, y = leaf / ncw;
+    uint32_t lvl = base;
+    int cur;
+    bool found = false;
+    uint32_t node = 0;
+    for (;;) {
+        node = lvl + (uint32_t)y * w + x;
+        if (tags_[node].vis) {
+            found = true;
+            break;
+        }
+        stack[++sp] = node;
+        if (w <= 1 && h <= 1)
+            break;
+        lvl += (uint32_t)w * h;
+        w = (w + 1) >> 1; h = (h + 1) >> 1;
+        x >>= 1; y >>= 1;
+    }
+    cur = found ? tags_[node].val : tags_[stack[sp]].val;
+    while (cur < threshold && sp >= 0) {
+        TagNodeState &n = tags_[stack[sp]];
+        if (cur < n.val)
+            cur = n.val;
+        while (cur < threshold) {
+            if (bits(1)) {
+                n.vis++;
+                break;
+            }
+            cur++;
+        }
+        n.val = (int16_t)cur;
+        sp--;
+    }
+    return cur;
+}
+
+void Parser::select_part(int tileno, int *tp, int csty)
+{
+    auto &pv = parts_[tileno];
+    if (pv.empty()) {
+        bp_ = bend_ = pkt_ + pkt_size_;
+        return;
+    }
+    bp_ = pv[*tp].p;
+    bend_ = pv[*tp].end;
+    while ((!bp_ || bp_ >= bend_) && bit_index_ == 8 && *tp + 1 < (int)pv.size()) {
+        ++*tp;
+        bp_ = pv[*tp].p;
+        bend_ = pv[*tp].end;
+    }
+    if (!bp_)
+        bp_ = bend_ = pkt_ + pkt_size_;
+    if (csty & 2)
+        if (bend_ - bp_ >= 6 && rd32(bp_) == 0xFF910004u)
+            bp_ += 6;
+}
+
+/* jpeg2000_decode_packet, HT-only paths */
+int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *tp)
+{
+    const CodSty &cs = hdr.cod[c];
+    const QntSty &qs = hdr.qnt[c];
+    const TileGeom &t = tiles_[tileno];
+    const ResGeom &rl = res_[t.res_base[c] + r];
+    const uint8_t *expn = qs.expn + (r ? 3 * (r - 1) + 1 : 0);
+    const int roi0 = hdr.roi[0];                         /* quirk Q6: component 0's shift for every component */
+
+    uint8_t &dl = decoded_layers_[rl.band[0].prec_base + precno];
+    if (layno < dl)
+        return 0;
+    dl = (uint8_t)(layno + 1);
+    select_part(tileno, tp, cs.csty);
+
+    struct Inc { uint32_t cb; int nseg; uint32_t seg[6]; };
+    static thread_local std::vector<Inc> incs;
+    incs.clear();
+
+    if (!bits(1)) {
+        flush();
+    } else {
+        for (int b = 0; b < rl.nbands; b++) {
+            const BandGeom &bd = rl.band[b];
+            if (bd.empty)
+                continue;
+            const PrecGeom &pg = precs_[bd.prec_base + precno];
+            const int n = pg.ncw * pg.nch;
+            for (int k = 0; k < n; k++) {
+                CblkState &cb = state_[pg.cblk_base + k];
+                int incl;
+                if (!cb.incl) {
+                    cb.plhd = 1;
+                    if (layno > 0)
+                        tagtree_decode(pg.tag_base, pg.ncw, pg.nch, k, 1);
+                    incl = tagtree_decode(pg.tag_base, pg.ncw, pg.nch, k, layno + 1) == layno;
+                    if (incl) {
+                        int zbp = tagtree_decode(pg.tag_base + pg.tag_nodes, pg.ncw, pg.nch, k, 100);
+                        int v = expn[b] + qs.nguard - 1 - (zbp - roi0);
+                        if (v < 0 || v > 30)
+                            return B200J2K_ERR_INVALIDDATA;
+                        cb.incl = 1;
+                        cb.zbp = (uint8_t)zbp;
+                        cb.lblock = 3;
+                    }
+                } else {
+                    incl = bits(1);
+                }
+                if (!incl)
+                    continue;
+                int newpasses;
+                if (!bits(1)) newpasses = 1;
+                else if (!bits(1)) newpasses = 2;
+                else {
+                    int nn = bits(2);
+                    if (nn != 3) newpasses = 3 + nn;
+                    else {
+                        nn = bits(5);
+                        newpasses = nn != 31 ? 6 + nn : 37 + bits(7);
+                    }
+                }
+                if (cb.npasses + newpasses >= 100)
+                    return B200J2K_ERR_PATCHWELCOME;
+                int llen = 0;
+                while (bits(1))
+                    llen++;
+                if (cb.lblock + llen + ilog2((unsigned)newpasses) > 16)
+                    return B200J2K_ERR_PATCHWELCOME;
+                cb.lblock = (uint8_t)(cb.lblock + llen);
+                incs.push_back(Inc{ pg.cblk_base + (uint32_t)k, 0, { 0 } });
+                Inc &in = incs.back();
+
+                int segment_passes, next_segment_passes = 0, nb;
+                unsigned segment_bytes = 0;
+                if (cb.plhd) {
+                    int href = (cb.npasses + newpasses - 1) % 3;
+                    segment_passes = newpasses - href;
+                    int pass_bound = 2;
+                    nb = cb.lblock;
+                    if (segment_passes < 1) {
+                        segment_passes = newpasses;
+                        while (pass_bound <= segment_passes) { nb++; pass_bound += pass_bound; }
+                        segment_bytes = (unsigned)bits(nb);
+                    } else {
+                        while (pass_bound <= segment_passes) { nb++; pass_bound += pass_bound; }
+                        segment_bytes = (unsigned)bits(nb);
+                        if (segment_bytes) {
+                            next_segment_passes = 2;
+                            cb.plhd = 0;
+                            cb.Lcup = segment_bytes;
+                        } else {
+                            segment_passes = newpasses;
+                            if (pass_bound <= segment_passes)
+                                for (;;) {
+                                    nb++;
+                                    pass_bound += pass_bound;
+                                    segment_bytes = (segment_bytes << 1) + (unsigned)bits(1);
+                                    if (pass_bound > segment_passes)
+                                        break;
+                                }
+                        }
+                    }
+                } else {
+                    segment_passes = cb.npasses % 3;
+                    nb = 0;
+                    if (segment_passes == 0) {
+                        segment_passes = 1;
+                        next_segment_passes = 2;
+                    } else {
+                        segment_passes = newpasses > 1 ? 3 - segment_passes : 1;
+                        next_segment_passes = 1;
+                        nb = ilog2((unsigned)segment_passes);
+                    }
+                    nb += cb.lblock;
+                    segment_bytes = (unsigned)bits(nb);
+                    cb.Lref += segment_bytes;
+                }
+                cb.npasses = (uint8_t)(cb.npasses + segment_passes);
+                in.seg[in.nseg++] = segment_bytes & 0xFFFF;
+                newpasses -= segment_passes & 0xFF;
+                if (!cb.plhd) {
+                    while (newpasses > 0) {
+                        segment_passes = newpasses > 1 ? next_segment_passes : 1;
+                        next_segment_passes = 3 - next_segment_passes;
+                        nb = cb.lblock + ilog2((unsigned)segment_passes);
+                        segment_bytes = (unsigned)bits(nb);
+                        newpasses -= segment_passes;
+                        cb.Lref += segment_bytes;
+                        cb.npasses = (uint8_t)(cb.npasses + segment_passes);
+                        if (in.nseg < 6)
+                            in.seg[in.nseg++] = segment_bytes & 0xFFFF;
+                    }
+                } else {
+                    while (newpasses > 0) {
+                        segment_bytes = (unsigned)bits(cb.lblock);
+                        newpasses -= 1;
+                        cb.npasses = (uint8_t)(cb.npasses + 1);
+                        if (in.nseg < 6)
+                            in.seg[in.nseg++] = segment_bytes & 0xFFFF;
+                    }
+                }
+            }
+        }
+        flush();
+    }
+    if (cs.csty & 4)
+        if (bend_ - bp_ >= 2 && rd16(bp_) == 0xFF92)
+            bp_ += 2;
+    /* packet body: code-block bytes are referenced in place; a block that already has bytes elsewhere
+     * is gathered into `extra` so that Dcup||Dref stays contiguous for the kernel */
+    for (const Inc &in : incs) {
+        CblkState &cb = state_[in.cb];
+        for (int s = 0; s < in.nseg; s++) {
+            uint32_t n = in.seg[s];
+            if ((uint32_t)(bend_ - bp_) < n || cb.length + n > 65535)
+                return B200J2K_ERR_INVALIDDATA;
+            if (n) {
+                const uint32_t here = (uint32_t)(bp_ - pkt_);
+                if (cb.length == 0) {
+                    cb.data_off = here;
+                } else if (cb.data_off + cb.length != here) {
+                    const uint8_t *old = cb.data_off < (uint64_t)pkt_size_ ? pkt_ + cb.data_off
+                                                                           : extra.data() + (cb.data_off - pkt_size_);
+                    std::vector<uint8_t> tmp(old, old + cb.length);
+                    size_t at = extra.size();
+                    extra.insert(extra.end(), tmp.begin(), tmp.end());
+                    extra.insert(extra.end(), bp_, bp_ + n);
+                    extra.resize((extra.size() + 15) & ~(size_t)15);
+                    cb.data_off = (uint32_t)(pkt_size_ + at);
+                }
+                cb.length += n;
+                bp_ += n;
+            }
+        }
+    }
+    if (!parts_[tileno].empty())
+        parts_[tileno][*tp].p = bp_;
+    return 0;
+}
+
+int Parser::precinct_at(int tileno, int c, int r, int x, int y, bool cprl_rule) const
+{
+    const Header &h = hdr;
+    const TileGeom &t = tiles_[tileno];
+    const ResGeom &rl = res_[t.res_base[c] + r];
+    const int red = h.cod[c].nres - 1 - r;
+    const Rect &cc = t.comp[c];
+    if (cprl_rule) {
+        int xc = x / h.cdx[c], yc = y / h.cdy[c];
+        if (yc % (1LL << (rl.ppy + red)) && y != t.c.y0)
+            return -1;
+        if (xc % (1LL << (rl.ppx + red)) && x != t.c.x0)
+            return -1;
+        unsigned px = (unsigned)(ceildivpow2(xc, red) >> rl.ppx) - (unsigned)(ceildivpow2(cc.x0, red) >> rl.ppx);
+        unsigned py = (unsigned)(ceildivpow2(yc, red) >> rl.ppy) - (unsigned)(ceildivpow2(cc.y0, red) >> rl.ppy);
+        if (px >= (unsigned)rl.npx || py >= (unsigned)rl.npy)
+            return -1;
+        return (int)(px + rl.npx * py);
+    }
+    const int64_t sx = (int64_t)h.cdx[c] << red, sy = (int64_t)h.cdy[c] << red;
+    int64_t trx0 = ((int64_t)t.c.x0 + sx - 1) / sx, try0 = ((int64_t)t.c.y0 + sy - 1) / sy;
+    if (!(y % ((uint64_t)h.cdy[c] << (rl.ppy + red)) == 0 ||
+          (y == t.c.y0 && ((try0 << red) % (1LL << (red + rl.ppy))))))
+        return -1;
+    if (!(x % ((uint64_t)h.cdx[c] << (rl.ppx + red)) == 0 ||
+          (x == t.c.x0 && ((trx0 << red) % (1LL << (red + rl.ppx))))))
+        return -1;
+    unsigned px = (unsigned)((((int64_t)x + sx - 1) / sx) >> rl.ppx);
+    unsigned py = (unsigned)((((int64_t)y + sy - 1) / sy) >> rl.ppy);
+    px -= (unsigned)(ceildivpow2(cc.x0, red) >> rl.ppx);
+    py -= (unsigned)(ceildivpow2(cc.y0, red) >> rl.ppy);
+    if (px >= (unsigned)rl.npx || py >= (unsigned)rl.npy)
+        return -1;
+    return (int)(px + rl.npx * py);
+}
+
+#define PACKET(c, r, pn, l)                                                       \
+    do {                                                                          \
+        int e_ = decode_packet(tileno, c, r, pn, l, &tp);                         \
+        if (e_ < 0)                                                               \
+            return e_;                                                            \
+    } while (0)
+
+int Parser::decode_packets(int tileno)
+{
+    const Header &h = hdr;
+    const TileGeom &t = tiles_[tileno];
+    const int nlayers = h.cod[0].nlayers, C = h.ncomp;
+    int tp = 0, maxres = 0;
+    for (int c = 0; c < C; c++)
+        maxres = imax(maxres, h.cod[c].nres);
+    bit_index_ = 8;
+    auto R = [&](int c, int r) -> const ResGeom & { return res_[t.res_base[c] + r]; };
+    switch (h.cod[0].prog) {
+    case 0:
+        for (int l = 0; l < nlayers; l++)
+            for (int r = 0; r < maxres; r++)
+                for (int c = 0; c < C; c++)
+                    if (r < h.cod[c].nres)
+                        for (int pn = 0; pn < R(c, r).npx * R(c, r).npy; pn++)
+                            PACKET(c, r, pn, l);
+        break;
+    case 1:
+        for (int r = 0; r < maxres; r++)
+            for (int l = 0; l < nlayers; l++)
+                for (int c = 0; c < C; c++)
+                    if (r < h.cod[c].nres)
+                        for (int pn = 0; pn < R(c, r).npx * R(c, r).npy; pn++)
+                            PACKET(c, r, pn, l);
+        break;
+    case 2:
+        for (int r = 0; r < maxres; r++) {
+            int sx = 30, sy = 30;
+            for (int c = 0; c < C; c++)
+                if (r < h.cod[c].nres) {
+                    int red = h.cod[c].nres - 1 - r;
+                    sx = imin(sx, R(c, r).ppx + red);
+                    sy = imin(sy, R(c, r).ppy + red);
+                }
+            sx = 1 << sx; sy = 1 << sy;
+            for (int y = t.c.y0; y < t.c.y1; y = (y / sy + 1) * sy)
+                for (int x = t.c.x0; x < t.c.x1; x = (x / sx + 1) * sx)
+                    for (int c = 0; c < C; c++) {
+                        if (r >= h.cod[c].nres)
+                            continue;
+                        int pn = precinct_at(tileno, c, r, x, y, false);
+                        if (pn < 0)
+                            continue;
+                        for (int l = 0; l < nlayers; l++)
+                            PACKET(c, r, pn, l);
+                    }
+        }
+        break;
+    case 3: {
+        int sx = 32, sy = 32;
+        for (int c = 0; c < C; c++)
+            for (int r = 0; r < h.cod[c].nres; r++) {
+                int red = h.cod[c].nres - 1 - r;
+                sx = imin(sx, R(c, r).ppx + red);
+                sy = imin(sy, R(c, r).ppy + red);
+            }
+        if (sx >= 31 || sy >= 31)
+            return B200J2K_ERR_PATCHWELCOME;
+        sx = 1 << sx; sy = 1 << sy;
+        for (int y = t.c.y0; y < t.c.y1; y = (y / sy + 1) * sy)
+            for (int x = t.c.x0; x < t.c.x1; x = (x / sx + 1) * sx)
+                for (int c = 0; c < C; c++)
+                    for (int r = 0; r < h.cod[c].nres; r++) {
+                        int pn = precinct_at(tileno, c, r, x, y, false);
+                        if (pn < 0)
+                            continue;
+                        for (int l = 0; l < nlayers; l++)
+                            PACKET(c, r, pn, l);
+                    }
+        break;
+    }
+    case 4:
+        for (int c = 0; c < C; c++) {
+            int sx = 32, sy = 32;
+            for (int r = 0; r < h.cod[c].nres; r++) {
+                int red = h.cod[c].nres - 1 - r;
+                sx = imin(sx, R(c, r).ppx + red);
+                sy = imin(sy, R(c, r).ppy + red);
+            }
+            if (sx >= 31 || sy >= 31)
+                return B200J2K_ERR_PATCHWELCOME;
+            sx = 1 << sx; sy = 1 << sy;
+            for (int y = t.c.y0; y < t.c.y1; y = (y / sy + 1) * sy)
+                for (int x = t.c.x0; x < t.c.x1; x = (x / sx + 1) * sx)
+                    for (int r = 0; r < h.cod[c].nres; r++) {
+                        int pn = precinct_at(tileno, c, r, x, y, true);
+                        if (pn < 0)
+                            continue;
+                        for (int l = 0; l < nlayers; l++)
+                            PACKET(c, r, pn, l);
+                    }
+        }
+        break;
+    default:
+        break;
+    }
+    return 0;
+}
+#undef PACKET
+
+int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only)
+{
+    if (!pkt || size < 2)
+        return B200J2K_ERR_INVALIDDATA;
+    if (size > 0x7FFFFFF0ll)
+        return B200J2K_ERR_PATCHWELCOME;
+    pkt_ = pkt;
+    pkt_size_ = size;
+    size_t mh = 0;
+    int ret = parse_headers(pkt, size, flags, &mh);
+    if (ret < 0)
+        return ret;
+    if (headers_only)
+        return 0;
+    /* geometry only depends on the main header: reuse it across a sequence */
+    if (geom_flags_ != flags || geom_key_.size() != mh || memcmp(geom_key_.data(), pkt, mh)) {
+        geom_flags_ = -1;
+        if ((ret = build_geometry(flags)) < 0)
+            return ret;
+        geom_key_.assign(pkt, pkt + mh);
+        geom_flags_ = flags;
+    }
+    /* per-frame tier-2 state */
+    state_.assign(cblk_template_.size(), CblkState{});
+    tags_.assign(tag_total_, TagNodeState{ 0, 0 });
+    decoded_layers_.assign(precs_.size(), 0);
+    extra.clear();
+    for (int tileno = 0; tileno < hdr.ntx * hdr.nty; tileno++)
+        if ((ret = decode_packets(tileno)) < 0)
+            return ret;
+    /* emit the descriptor table */
+    cblk = cblk_template_;
+    max_Lcup = max_Lref = 0;
+    any_refine = 0;
+    for (size_t i = 0; i < cblk.size(); i++) {
+        const CblkState &s = state_[i];
+        CblkDesc &d = cblk[i];
+        d.data_off = s.data_off;
+        d.Lcup = (uint16_t)s.Lcup;
+        d.Lref = (uint16_t)s.Lref;
+        d.npasses = s.npasses;
+        d.zbp = s.zbp;
+        d.length = s.length;
+        if (s.npasses) {
+            /* the decoder reads Dcup[0..Lcup) and Dref[0..Lref): keep both inside the gathered bytes */
+            if ((uint32_t)d.Lcup + d.Lref > s.length) {
+                /* damaged lengths: clamp so that the kernel never leaves the buffer (block decodes as the
+                 * reference would on short data: garbage or error => zeros) */
+                if (d.Lcup > s.length) { d.Lcup = (uint16_t)s.length; d.Lref = 0; }
+                else d.Lref = (uint16_t)(s.length - d.Lcup);
+            }
+            if (d.Lcup > max_Lcup) max_Lcup = d.Lcup;
+            if (d.Lref > max_Lref) max_Lref = d.Lref;
+            int rem = s.npasses % 3;
+            if (rem != 1)
+                any_refine = 1;
+        }
+    }
+    return 0;
+}
+
+}  // namespace b200j2k

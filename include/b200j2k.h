@@ -1,0 +1,145 @@
+/*
+ * b200j2k.h -- C ABI of the B200-native HTJ2K decode path.
+ *
+ * This is the boundary a libavcodec maintainer binds to replace the hot path of the native "jpeg2000"
+ * decoder of sandflow/ffmpeg-ht (FFCodec ff_jpeg2000_decoder, libavcodec/jpeg2000dec.c:2926-2939).
+ * The FFCodec shim that calls it is ffmpeg-ht_b200/ffcodec/jpeg2000_b200.c; INTEGRATION.md shows the
+ * build glue.  Plain C: pointers and sizes only, no C++ or torch types, no exceptions, no global state.
+ *
+ * Division of labour (BASELINE.json north_star):
+ *   host, serial  : codestream/marker parsing, geometry, tag trees, packet headers
+ *                   (jpeg2000dec.c:197-1869, jpeg2000.c:214-577)  -> flat code-block descriptor table +
+ *                   packed segment buffer
+ *   sm_100a CUDA  : HT block decode + dequantisation (jpeg2000htdec.c:1188-1336, jpeg2000dec.c:2098-2181),
+ *                   inverse DWT (jpeg2000dwt.c:309-620), inverse RCT/ICT (jpeg2000dsp.c:43-91),
+ *                   level shift / clip / pack (jpeg2000dec.c:2301-2366)
+ * There is no CPU fallback: every entry point that needs the device fails with B200J2K_ERR_DEVICE when
+ * no CUDA device is usable.
+ *
+ * Return values: >= 0 success, < 0 one of the B200J2K_ERR_* codes, which are numerically the AVERROR
+ * values the reference returns in the same situation (jpeg2000dec.c:2905-2907).
+ */
+#ifndef B200J2K_H
+#define B200J2K_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200J2K_ERR_INVALIDDATA  (-1094995529)   /* AVERROR_INVALIDDATA */
+#define B200J2K_ERR_PATCHWELCOME (-1163346256)   /* AVERROR_PATCHWELCOME */
+#define B200J2K_ERR_NOMEM        (-12)           /* AVERROR(ENOMEM) */
+#define B200J2K_ERR_EINVAL       (-22)           /* AVERROR(EINVAL) */
+#define B200J2K_ERR_DEVICE       (-19)           /* AVERROR(ENODEV): no usable CUDA device / CUDA failure */
+
+/* b200j2k_create flags */
+#define B200J2K_FLAG_BITEXACT 1   /* AV_CODEC_FLAG_BITEXACT: 9/7 runs the fixed-point path (jpeg2000dec.c:543-544) */
+
+/* Output pixel formats.  b200j2k_pix_fmt_name() gives the libavutil name ("rgb48le", ...); the FFCodec
+ * shim maps it to AVPixelFormat with av_get_pix_fmt().  Selection follows jpeg2000dec.c:134-193,:335-363. */
+enum b200j2k_pix_fmt {
+    B200J2K_PIX_NONE = 0,
+    B200J2K_PIX_GRAY8, B200J2K_PIX_GRAY16, B200J2K_PIX_YA8, B200J2K_PIX_YA16,
+    B200J2K_PIX_RGB24, B200J2K_PIX_RGB48, B200J2K_PIX_RGBA, B200J2K_PIX_RGBA64,
+    B200J2K_PIX_PLANAR8, B200J2K_PIX_PLANAR16
+};
+
+/* What jpeg2000_decode_frame() publishes on AVCodecContext / AVFrame before the pixels exist
+ * (jpeg2000dec.c:213, :326, :354-363, :420, :546). */
+typedef struct b200j2k_frame_info {
+    int32_t width, height;          /* ff_set_dimensions() arguments */
+    int32_t pix_fmt;                /* enum b200j2k_pix_fmt */
+    int32_t ncomponents;
+    int32_t precision;              /* bits_per_raw_sample */
+    int32_t lossless;               /* FF_CODEC_PROPERTY_LOSSLESS */
+    int32_t profile;                /* Rsiz */
+    int32_t nplanes;
+    int32_t plane_width[4];         /* samples per row of each output plane */
+    int32_t plane_height[4];
+    int32_t plane_row_bytes[4];     /* minimum linesize */
+    int32_t ntiles;
+    int32_t ncodeblocks;            /* code-blocks handed to the device */
+    int64_t bytes_consumed;         /* decode() return value of the reference: bytestream2_tell() */
+} b200j2k_frame_info;
+
+typedef struct b200j2k_decoder b200j2k_decoder;
+
+/* Number of CUDA devices usable by this library (0 when none: nothing else will work). */
+int b200j2k_device_count(void);
+
+/* jpeg2000_decode_init (jpeg2000dec.c:2807-2823) + device context: one decoder per AVCodecContext.
+ * `slots` frames may be in flight at once (>= 1); each slot owns a CUDA stream, pinned staging and
+ * device buffers that grow on demand. */
+int b200j2k_create(b200j2k_decoder **out, int device, int slots, int flags);
+
+/* FFCodec.close: releases streams, pinned and device memory. */
+void b200j2k_destroy(b200j2k_decoder *dec);
+
+/* Header-only pass (main header + tile-part headers, no packet parsing): what the caller needs to
+ * allocate the AVFrame (ff_thread_get_buffer, jpeg2000dec.c:2877).  Works without a device. */
+int b200j2k_probe(const uint8_t *pkt, int64_t pkt_size, int flags, b200j2k_frame_info *info);
+
+/* Asynchronous decode of one packet (= one codestream, AVPacket.data/size) into caller-owned planes
+ * (AVFrame.data[]/linesize[]).  Host parsing happens in the call; H2D, kernels and D2H are queued on the
+ * slot's stream.  Returns the slot index (>= 0) to pass to b200j2k_wait().  If every slot is busy the
+ * oldest one is waited for first.  The packet may be released when the call returns; the planes must stay
+ * valid until b200j2k_wait().  Planes that were registered with b200j2k_host_register() (or allocated with
+ * b200j2k_host_alloc()) receive the device->host copy directly; others go through pinned staging + memcpy. */
+int b200j2k_submit(b200j2k_decoder *dec, const uint8_t *pkt, int64_t pkt_size,
+                   uint8_t *const data[4], const int linesize[4], b200j2k_frame_info *info);
+
+/* Completes the frame in `slot`: after it returns 0 the planes hold the picture. */
+int b200j2k_wait(b200j2k_decoder *dec, int slot);
+
+/* FF_CODEC_DECODE_CB equivalent: submit + wait.  Returns bytes consumed (>= 0) like the reference. */
+int64_t b200j2k_decode(b200j2k_decoder *dec, const uint8_t *pkt, int64_t pkt_size,
+                       uint8_t *const data[4], const int linesize[4], b200j2k_frame_info *info);
+
+/* Device-resident variants used by tests and by the kernel-only leg of bench.py: the packet has been
+ * parsed and staged once (b200j2k_stage), the kernels are re-run on the resident inputs
+ * (b200j2k_run_staged) with no host<->device traffic, and the output stays on the device. */
+int b200j2k_stage(b200j2k_decoder *dec, int slot, const uint8_t *pkt, int64_t pkt_size, b200j2k_frame_info *info);
+int b200j2k_run_staged(b200j2k_decoder *dec, int slot);
+int b200j2k_sync(b200j2k_decoder *dec, int slot);
+/* copies the staged slot's picture to host planes (synchronous) */
+int b200j2k_fetch(b200j2k_decoder *dec, int slot, uint8_t *const data[4], const int linesize[4]);
+/* CUDA stream of a slot (cudaStream_t as void*), for event timing on the launching stream */
+void *b200j2k_slot_stream(b200j2k_decoder *dec, int slot);
+/* device pointer + byte size of the slot's packed output picture, or NULL */
+void *b200j2k_slot_output(b200j2k_decoder *dec, int slot, int64_t *bytes);
+/* number of kernel launches the last run of `slot` queued */
+int b200j2k_slot_launches(b200j2k_decoder *dec, int slot);
+
+/* Stage-level entry points (parity tests against the oracle; same argument meaning as the reference's
+ * ff_jpeg2000_decode_htj2k / ff_dwt_decode): all buffers are HOST pointers, the work runs on the device.
+ * blocks: n code-blocks described by par[n][10] = {npasses, Lcup, Lref, zbp, w, h, M_b, roi_shift, vsc,
+ * data_offset}; data = concatenated Dcup||Dref segments; out = concatenated w*h int32 sign-magnitude
+ * coefficients; status[n] = 1 decoded / 0 nothing / <0 error (block zeroed, quirk Q1). */
+int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const int32_t *par, int n,
+                      int32_t *out, int32_t *status);
+/* type: 0 = 9/7 float, 1 = 5/3, 2 = 9/7 fixed point; border = {x0,x1,y0,y1}; plane in Mallat layout */
+int b200j2k_idwt(int device, int type, const int32_t *border, int levels, void *plane);
+
+/* pinned host memory helpers for AVFrame pools (get_buffer2) */
+void *b200j2k_host_alloc(int64_t bytes);
+void b200j2k_host_free(void *p);
+int b200j2k_host_register(void *p, int64_t bytes);
+int b200j2k_host_unregister(void *p);
+
+/* Introspection of the host-side plan (CPU only, no device needed): lets tests check the parser's flat
+ * tables.  which: 0 CblkDesc, 1 BandDesc, 2 TileCompDesc, 3 PackGroup (ffmpeg-ht_b200/csrc/j2k_plan.h),
+ * 4 gathered bytes of multi-contribution blocks.  Pointers stay valid until the next plan_build on the
+ * calling thread. */
+int b200j2k_plan_build(const uint8_t *pkt, int64_t pkt_size, int flags, b200j2k_frame_info *info);
+const void *b200j2k_plan_table(int which, int64_t *count, int32_t *elem_size);
+int64_t b200j2k_plan_scalar(int which);
+
+const char *b200j2k_pix_fmt_name(int pix_fmt);
+const char *b200j2k_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200J2K_H */

@@ -1,0 +1,166 @@
+"""Host side of the product (codestream -> flat plan, ffmpeg-ht_b200/csrc/j2k_parse.cc) checked on the
+CPU: the plan's tables are fed through the ORACLE's stage functions (block decode, IDWT, MCT) with a
+numpy restatement of dequantisation and packing, and the picture must equal the oracle's own decode of
+the same codestream -- i.e. offsets, lengths, zbp, M_b, step sizes, Mallat placement, level bounds and
+pack parameters are all what the reference would use.  No GPU."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import ffmpeg_ht_b200 as fb
+import j2kgen
+from helpers import ht_block, oracle, oracle_decode
+from test_oracle_vs_ref import STREAMS
+
+
+def picture_from_plan(cs: bytes, flags: int):
+    P = fb.plan(cs, flags)
+    info = P["info"]
+    data = np.frombuffer(cs, np.uint8)
+    allbytes = np.concatenate([data, P["extra"], np.zeros(64, np.uint8)])
+    coef = np.zeros(int(P["coef_elems"]) + 64, np.uint32)
+    for d in P["cblk"]:
+        w, h, M_b = int(d["w"]), int(d["h"]), int(d["M_b"])
+        seg = allbytes[int(d["data_off"]): int(d["data_off"]) + int(d["length"])].tobytes()
+        ret, sm = ht_block(oracle().oracle_ht_block, seg, int(d["npasses"]), int(d["Lcup"]), int(d["Lref"]),
+                           int(d["zbp"]), w, h, M_b, int(d["roi_shift"]), int(d["flags"]) & 1)
+        band = P["bands"][int(d["band"])]
+        mode = (int(d["flags"]) >> 1) & 3
+        sm = sm.astype(np.int64)
+        mag = sm & 0x7FFFFFFF
+        neg = sm < 0
+        if ret == 0 or ret < 0:
+            vals = np.zeros((h, w), np.uint32)
+        elif mode == 1:
+            v = mag >> (31 - M_b)
+            v = np.where(neg, -v, v)
+            if int(band["i_stepsize"]) != 32768:
+                v = np.trunc(v * int(band["i_stepsize"]) / 65536).astype(np.int64)
+            vals = v.astype(np.int32).view(np.uint32)
+        elif mode == 0:
+            v = np.where(neg, -mag, mag).astype(np.int32).astype(np.float32)
+            vals = (v * np.float32(band["fscale"])).astype(np.float32).view(np.uint32)
+        else:
+            v = np.where(neg, -mag, mag)
+            v = (v + 32) >> 6
+            m = v * int(band["iscale"])
+            vals = np.where(m > 0, (m + 32768) >> 16, (m + 32767) >> 16).astype(np.int32).view(np.uint32)
+        stride, off = int(d["dst_stride"]), int(d["dst_off"])
+        for y in range(h):
+            coef[off + y * stride: off + y * stride + w] = vals[y]
+    planes = []
+    for tc in P["tcs"]:
+        n = int(tc["width"]) * int(tc["height"])
+        pl = coef[int(tc["coef_off"]): int(tc["coef_off"]) + n].copy()
+        lv = tc["lev"][int(tc["nlevels"])]
+        border = np.array([lv["u0"], lv["u1"], lv["v0"], lv["v1"]], np.int32)
+        assert border[1] - border[0] == tc["width"] and border[3] - border[2] == tc["height"]
+        if n:
+            assert oracle().oracle_idwt(int(tc["transform"]), border.ctypes.data, int(tc["nlevels"]), pl.ctypes.data) == 0
+        planes.append(pl)
+    pic = np.zeros(int(P["picture_bytes"]), np.uint8)
+    rowb = [info.plane_row_bytes[i] for i in range(4)]
+    for g in P["groups"]:
+        tcs = [P["tcs"][int(g["tc"][c])] for c in range(int(g["ncomp"]))]
+        pls = [planes[int(g["tc"][c])] for c in range(int(g["ncomp"]))]
+        t = int(tcs[0]["transform"])
+        if int(g["mct"]):
+            oracle().oracle_mct(t, pls[0].ctypes.data, pls[1].ctypes.data, pls[2].ctypes.data, pls[0].size)
+        wide = int(g["wide"])
+        view = pic[P["plane_off"][int(g["plane"])]:]
+        for c, (tc, pl) in enumerate(zip(tcs, pls)):
+            W, H = int(tc["width"]), int(tc["height"])
+            if t == 0:
+                val = np.rint(pl.view(np.float32)).astype(np.int64)
+            else:   # (oracle_idwt already undid the 2^8 pre-shift of the fixed-point 9/7 path)
+                val = pl.view(np.int32).astype(np.int64)
+            cb = int(tc["cbps"])
+            val = np.clip(val + (1 << (cb - 1)), 0, (1 << cb) - 1) << int(g["shift"][c])
+            val = val.reshape(H, W)
+            rb = rowb[int(g["plane"])]
+            ps, so = int(g["pixel_stride"]), int(g["sample_off"][c])
+            for y in range(H):
+                row = view[(int(tc["out_y"]) + y) * rb: (int(tc["out_y"]) + y + 1) * rb]
+                r = row.view(np.uint16) if wide else row
+                r[int(tc["out_x"]) * ps + so: (int(tc["out_x"]) + W) * ps + so: ps] = val[y]
+    return info, pic
+
+
+@pytest.mark.parametrize("cfg", STREAMS, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
+def test_plan_reproduces_oracle_picture(cfg):
+    cfg = dict(cfg)
+    w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=11)
+    p = j2kgen.EncParams(**cfg)
+    cs = j2kgen.encode(planes, bd, p)
+    for bitexact in ((0,) if p.reversible else (0, 1)):
+        r, oinfo, opic = oracle_decode(cs, bitexact)
+        assert r == 0
+        info, pic = picture_from_plan(cs, fb.FLAG_BITEXACT if bitexact else 0)
+        assert (info.width, info.height) == (oinfo[0], oinfo[1])
+        assert info.pix_fmt == oinfo[2]          # same numbering on both sides
+        assert np.array_equal(pic, opic)
+
+
+def test_geometry_cache_across_frames():
+    """Second frame with the same main header reuses the cached geometry; a different header rebuilds."""
+    a = j2kgen.encode(j2kgen.synth_image(96, 64, 3, 12, seed=1), 12, j2kgen.EncParams(levels=3, cblk=(32, 32)))
+    b = j2kgen.encode(j2kgen.synth_image(96, 64, 3, 12, seed=2), 12, j2kgen.EncParams(levels=3, cblk=(32, 32)))
+    c = j2kgen.encode(j2kgen.synth_image(80, 64, 1, 8, seed=3), 8, j2kgen.EncParams(levels=2, cblk=(16, 16)))
+    for cs in (a, b, c, a):
+        r, _, opic = oracle_decode(cs)
+        _, pic = picture_from_plan(cs, 0)
+        assert r == 0 and np.array_equal(pic, opic)
+
+
+def test_error_behaviour_matches_oracle():
+    """Truncated / damaged codestreams: the host parser fails when the reference's front end fails."""
+    planes = j2kgen.synth_image(96, 80, 3, 12, seed=3)
+    cs = j2kgen.encode(planes, 12, j2kgen.EncParams(levels=3, cblk=(32, 32)))
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        bad = bytearray(cs)
+        mode = rng.integers(0, 3)
+        if mode == 0:
+            bad = bad[: int(rng.integers(2, len(bad)))]
+        elif mode == 1:
+            for _ in range(3):
+                bad[int(rng.integers(110, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            pos = int(rng.integers(110, len(bad) - 8))
+            bad[pos:pos + 8] = rng.integers(0, 256, 8, dtype=np.uint8).tobytes()
+        r, _, opic = oracle_decode(bytes(bad))
+        try:
+            _, pic = picture_from_plan(bytes(bad), 0)
+            ok = True
+        except fb.DecodeError as e:
+            ok = False
+            assert e.code < 0
+        assert ok == (r == 0)
+        if ok:
+            assert np.array_equal(pic, opic)
+
+
+def test_library_exports_every_declared_symbol():
+    L = fb.lib()
+    header = (fb._DIR.parent / "include" / "b200j2k.h").read_text()
+    import re
+    declared = set(re.findall(r"\b(b200j2k_[a-z0-9_]+)\s*\(", header))
+    declared -= {"b200j2k_decoder"}
+    assert declared == set(fb.EXPORTS), declared ^ set(fb.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.b200j2k_version().startswith(b"b200j2k")
+
+
+def test_no_device_fails_loudly():
+    """No CPU fallback: without a CUDA device the compute entry points return the device error."""
+    L = fb.lib()
+    if L.b200j2k_device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(fb.DecodeError) as e:
+        fb.Jpeg2000Decoder()
+    assert e.value.code == fb.ERR_DEVICE
+    with pytest.raises(fb.DecodeError):
+        fb.idwt(1, [0, 8, 0, 8], 1, np.zeros(64, np.int32))
