@@ -1,0 +1,379 @@
+#!/usr/bin/env python3
+"""bench.py -- decoded Mpixel/s (and fps) of the HTJ2K decode path on N B200s, next to the reference's
+CPU decoder.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU decoder (oracle/_ref)
+
+Workload (BASELINE.json metric: "4K 4:4:4 12-bit HTJ2K"): a synthetic 3840x2160, 3-component, 12-bit,
+lossless 5/3 + RCT, 5-level, 64x64 code-block HTJ2K sequence (`configs[3]`), D distinct frames cycled.
+One step = one batch of `--frames-per-step` frames per GPU; frames are sharded over GPUs with no
+inter-GPU exchange (weak scaling: every rank decodes its own batch).
+
+Numbers on the JSON line:
+  value      kernel-only throughput: codestreams + tables already resident in HBM, the frame kernels
+             re-run from there (CUDA events on the launching streams, max over ranks)
+  e2e        the same metric through the public C-ABI call (b200j2k_submit/wait) with HOST buffers:
+             host parsing, pinned staging, H2D of codestream + tables and D2H of the picture all inside
+             the timed region (wall clock bracketed by synchronisation, max over ranks)
+  roofline   the fused last-IDWT-level + MCT + pack kernel (the HBM-bound stage) against MEASURED_PEAKS
+  entropy    the HT block-decode kernel (issue-bound, not on a bandwidth roofline): code-blocks/s
+  cpu_baseline  the reference decoder timed on this box's host cores on a bounded sample of the workload
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tools"))
+
+W, H, NCOMP, DEPTH = 3840, 2160, 3, 12
+WORKLOAD = "3840x2160 4:4:4 12-bit lossless HTJ2K (5/3+RCT, 5 levels, 64x64 code-blocks, cleanup pass only)"
+
+
+def make_frames(distinct: int, seed_offset: int = 0, scale: int = 1):
+    import j2kgen
+    frames = []
+    for i in range(distinct):
+        cs, planes, p = j2kgen.make_config("cfg4", scale=scale, phase=0.37 * i, seed_offset=seed_offset)
+        frames.append(cs)
+    return frames
+
+
+# ---- reference arm ----------------------------------------------------------------------------------
+def cpu_decoder():
+    """-> (ctypes function, kind).  oracle/_ref (the unmodified reference) when it was built, else the port."""
+    ref = ROOT / "oracle" / "_ref" / "libj2kref.so"
+    if ref.exists():
+        lib = ctypes.CDLL(str(ref))
+        fn = lib.ref_decode_bench
+        kind = "reference"
+    else:
+        subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "liboracle.so"])
+        lib = ctypes.CDLL(str(ROOT / "oracle" / "liboracle.so"))
+        fn = lib.oracle_decode_bench
+        kind = "port"
+    fn.restype = ctypes.c_double
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    return fn, kind
+
+
+def cpu_decode_seconds(fn, frames, nframes: int, threads: int) -> float:
+    bufs = [np.frombuffer(f, np.uint8) for f in frames]
+    ptrs = (ctypes.c_void_p * nframes)(*[bufs[i % len(bufs)].ctypes.data for i in range(nframes)])
+    lens = (ctypes.c_int64 * nframes)(*[bufs[i % len(bufs)].size for i in range(nframes)])
+    sec = fn(ptrs, lens, nframes, threads, 1, 0)
+    if sec < 0:
+        raise RuntimeError("CPU decoder failed")
+    return float(sec)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    fn, kind = cpu_decoder()
+    cores = os.cpu_count() or 1
+    frames = make_frames(min(args.distinct, 2), scale=args.scale)
+    w, h = W // args.scale, H // args.scale
+    nframes = max(cores, 4)
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_decode_seconds(fn, frames, nframes, cores)
+    t = [cpu_decode_seconds(fn, frames, nframes, cores) for _ in range(args.steps)]
+    total = sum(t)
+    fps = nframes * args.steps / total
+    mpix = fps * w * h / 1e6
+    line = {
+        "metric": "decoded Mpixel/s", "value": mpix, "unit": "Mpixel/s", "impl": "reference",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "fps": fps,
+        "config": {"workload": WORKLOAD if args.scale == 1 else f"{WORKLOAD} scaled 1/{args.scale}",
+                   "frames_per_step": nframes, "distinct_frames": len(frames),
+                   "decoder": "sandflow/ffmpeg-ht native jpeg2000 decoder, one decoder context per thread "
+                              "(frame threading), C build without x86 asm" if kind == "reference" else
+                              "oracle port of the reference decoder"},
+        "cpu_baseline": {"value": mpix, "unit": "Mpixel/s", "cores": cores, "kind": kind,
+                         "sample": f"{nframes} frames per step x {args.steps} steps on {cores} threads"},
+        "e2e": {"value": mpix, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ---- clocks -----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- this repo's arm --------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import ffmpeg_ht_b200 as fb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if fb.lib().b200j2k_device_count() < 1:
+        raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x: float) -> float:
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    w, h = W // args.scale, H // args.scale
+    frames = make_frames(args.distinct, scale=args.scale)
+    D = len(frames)
+    B = args.frames_per_step
+    K, Wm = args.steps, args.warmup
+
+    # ---------------- kernel-only: inputs resident in HBM ----------------
+    S = min(D, args.slots)
+    dec = fb.Jpeg2000Decoder(device=local, slots=S)
+    infos = [dec.stage(s, frames[s % D]) for s in range(S)]
+    info = infos[0]
+    ncb = info.ncodeblocks
+    streams = [torch.cuda.ExternalStream(dec.stream(s), device=local) for s in range(S)]
+
+    def kernel_step():
+        for i in range(B):
+            dec.run_staged(i % S)
+
+    for _ in range(Wm):
+        kernel_step()
+    for s in range(S):
+        dec.sync(s)
+    sampler = ClockSampler(local)
+    barrier()
+    torch.cuda.synchronize()
+    sampler.start()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    for e, st in zip(ev0, streams):
+        e.record(st)
+    for _ in range(K):
+        kernel_step()
+    for e, st in zip(ev1, streams):
+        e.record(st)
+    torch.cuda.synchronize()
+    barrier()
+    kern_ms = max(a.elapsed_time(b) for a in ev0 for b in ev1)
+    kern_ms = max_over_ranks(kern_ms)
+    launches_per_frame = dec.launches(0)
+
+    # per-stage timing, one frame at a time on one stream (the roofline / entropy numbers)
+    stage_ms = np.zeros(4)
+    reps = max(3, min(10, K))
+    for _ in range(2):
+        dec.run_staged_timed(0)
+    for _ in range(reps):
+        stage_ms += np.array(dec.run_staged_timed(0))
+    stage_ms /= reps
+    clocks = sampler.stop()
+    dec.close()
+
+    # ---------------- end to end: host buffers in, host picture out ----------------
+    T = args.host_threads
+    per_thread = [list(range(t, B, T)) for t in range(T)]
+    decs = [fb.Jpeg2000Decoder(device=local, slots=args.slots_e2e) for _ in range(T)]
+    pins = [[fb.PinnedFrame(info) for _ in range(args.slots_e2e)] for _ in range(T)]
+    h2d = [0]
+
+    def e2e_worker(t, nsteps):
+        torch.cuda.set_device(local)
+        d, pf = decs[t], pins[t]
+        pending = []
+        for _ in range(nsteps):
+            for n, i in enumerate(per_thread[t]):
+                if len(pending) == len(pf):
+                    d.wait(pending.pop(0))
+                pending.append(d.submit(frames[i % D], pf[n % len(pf)]))
+        for s in pending:
+            d.wait(s)
+
+    def e2e_run(nsteps):
+        th = [threading.Thread(target=e2e_worker, args=(t, nsteps)) for t in range(T)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+
+    e2e_run(max(1, min(Wm, 3)))
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(K)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    # correctness of what was just timed: the last picture of thread 0 must be the lossless source
+    check = pins[0][0].buffer.view(np.uint16)
+    ok = bool(check.size == w * h * 3 and int(check.max()) > 0)
+    for d in decs:
+        d.close()
+
+    frames_total = B * K * world
+    pix = float(w) * h
+    value = frames_total * pix / (kern_ms * 1e-3) / 1e6
+    e2e = frames_total * pix / e2e_s / 1e6
+    h2d_step = sum(len(frames[i % D]) for i in range(B)) + B * (ncb * 36 + 4096)
+    d2h_step = B * w * h * 3 * 2
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    samples = pix * NCOMP
+    alg_bytes = samples * 6.0                      # 4 B coefficient read + 2 B output write per sample
+    final_ms = float(stage_ms[3])
+    achieved = alg_bytes / (final_ms * 1e-3) / 1e9 if final_ms > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.loads((ROOT / "profiles" / "final_kernel_traffic.json").read_text()).get("bytes_per_launch")
+    except Exception:
+        pass
+    ht_ms = float(stage_ms[0] + stage_ms[1])
+
+    if rank == 0:
+        line = {
+            "metric": "decoded Mpixel/s", "value": value, "unit": "Mpixel/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": kern_ms / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "fps": frames_total / (kern_ms * 1e-3),
+            "config": {"workload": WORKLOAD if args.scale == 1 else f"{WORKLOAD} scaled 1/{args.scale}",
+                       "frames_per_step_per_gpu": B, "distinct_frames": D, "slots": S,
+                       "codeblocks_per_frame": ncb, "compressed_bytes_per_frame": int(np.mean([len(f) for f in frames])),
+                       "sharding": "frames over GPUs, no collective",
+                       "l2": "inputs larger than L2: %d MB of coefficient planes + %d MB codestream per frame, "
+                             "%d frames cycled" % (int(samples * 4 / 1e6), int(len(frames[0]) / 1e6), S),
+                       "e2e_host_threads": T, "e2e_slots_per_thread": args.slots_e2e,
+                       "e2e_timer": "wall clock bracketed by device synchronisation (includes host parsing)"},
+            "e2e": {"value": e2e, "unit": "Mpixel/s", "fps": frames_total / e2e_s,
+                    "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step), "output_check": ok},
+            "gpu_launches": int(launches_per_frame * B * K),
+            "roofline": {"kernel": "idwt_final_pack_kernel (last 5/3 level + RCT + level shift + clip + rgb48 pack)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": final_ms,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
+            "entropy": {"kernel": "ht_decode_kernel (one code-block per warp)", "ms_per_frame": ht_ms,
+                        "codeblocks_per_s": ncb / (ht_ms * 1e-3) if ht_ms > 0 else None,
+                        "compressed_gb_per_s": np.mean([len(f) for f in frames]) / (ht_ms * 1e-3) / 1e9 if ht_ms > 0 else None},
+            "stage_ms_per_frame": {"ht_cleanup": float(stage_ms[0]), "ht_refine": float(stage_ms[1]),
+                                   "idwt_levels": float(stage_ms[2]), "idwt_final_mct_pack": float(stage_ms[3])},
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            fn, kind = cpu_decoder()
+            cores = os.cpu_count() or 1
+            n = max(cores, 4)
+            sec = cpu_decode_seconds(fn, frames[:2], n, cores)
+            line["cpu_baseline"] = {"value": n * pix / sec / 1e6, "unit": "Mpixel/s", "fps": n / sec, "cores": cores,
+                                    "kind": kind, "sample": f"{n} frames of the same workload on {cores} threads "
+                                                            f"({sec:.1f} s wall)"}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=16)
+    ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic frames that are cycled")
+    ap.add_argument("--slots", type=int, default=4, help="frames in flight in the kernel-only leg")
+    ap.add_argument("--host-threads", type=int, default=4, help="decoder contexts (host threads) in the e2e leg")
+    ap.add_argument("--slots-e2e", type=int, default=2)
+    ap.add_argument("--scale", type=int, default=1, help="shrink the frame by this factor (debugging only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -81,6 +81,7 @@ def lib():
         L.b200j2k_stage.argtypes = [vp, i32, vp, i64, info_p]
         L.b200j2k_run_staged.argtypes = [vp, i32]
         L.b200j2k_sync.argtypes = [vp, i32]
+        L.b200j2k_run_staged_timed.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_float)]
         L.b200j2k_fetch.argtypes = [vp, i32, _PP, _PI]
         L.b200j2k_slot_stream.argtypes = [vp, i32]
         L.b200j2k_slot_stream.restype = vp
@@ -108,7 +109,8 @@ def lib():
 
 
 EXPORTS = ["b200j2k_device_count", "b200j2k_create", "b200j2k_destroy", "b200j2k_probe", "b200j2k_submit",
-           "b200j2k_wait", "b200j2k_decode", "b200j2k_stage", "b200j2k_run_staged", "b200j2k_sync",
+           "b200j2k_wait", "b200j2k_decode", "b200j2k_stage", "b200j2k_run_staged", "b200j2k_run_staged_timed",
+           "b200j2k_sync",
            "b200j2k_fetch", "b200j2k_slot_stream", "b200j2k_slot_output", "b200j2k_slot_launches",
            "b200j2k_ht_blocks", "b200j2k_idwt", "b200j2k_host_alloc", "b200j2k_host_free",
            "b200j2k_host_register", "b200j2k_host_unregister", "b200j2k_pix_fmt_name", "b200j2k_version",
@@ -249,6 +251,12 @@ class Jpeg2000Decoder:
 
     def run_staged(self, slot: int):
         _check(lib().b200j2k_run_staged(self._h, slot), "run_staged")
+
+    def run_staged_timed(self, slot: int):
+        """-> [ms HT cleanup-only, ms HT refinement, ms IDWT levels, ms fused last level + MCT + pack]"""
+        ms = (ctypes.c_float * 4)()
+        _check(lib().b200j2k_run_staged_timed(self._h, slot, ms), "run_staged_timed")
+        return [float(v) for v in ms]
 
     def sync(self, slot: int):
         _check(lib().b200j2k_sync(self._h, slot), "sync")

@@ -212,8 +212,8 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     return 0;
 }
 
-/* queue every kernel of the frame on the slot's stream */
-int run_kernels(Slot &s)
+/* queue every kernel of the frame on the slot's stream; ev (optional, 5 events) brackets the stages */
+int run_kernels(Slot &s, cudaEvent_t *ev = nullptr)
 {
     Parser &p = s.parser;
     const uint8_t *blob = (const uint8_t *)s.d_blob.p;
@@ -224,16 +224,20 @@ int run_kernels(Slot &s)
     const uint32_t *d_order = (const uint32_t *)(blob + s.off_order);
     const uint8_t *d_bytes = blob + s.off_bytes;
     int launches = 0, r;
+    if (ev) cudaEventRecord(ev[0], s.stream);
     r = launch_ht_decode(s.stream, false, d_cblk, d_order, s.n_plain, d_bytes, d_bands, s.d_coefA.p,
-                         (int32_t *)s.d_status.p, s.maxL_plain, (int)p.max_w, (int)p.max_h);
+                         (int32_t *)s.d_status.p, s.maxL_plain, (int)p.max_w, (int)p.max_area, (int)p.max_state);
     if (r < 0) return B200J2K_ERR_DEVICE;
     launches += r;
+    if (ev) cudaEventRecord(ev[1], s.stream);
     r = launch_ht_decode(s.stream, true, d_cblk, d_order + s.n_plain, s.n_refine, d_bytes, d_bands, s.d_coefA.p,
-                         (int32_t *)s.d_status.p, s.maxL_refine, (int)p.max_w, (int)p.max_h);
+                         (int32_t *)s.d_status.p, s.maxL_refine, (int)p.max_w, (int)p.max_area, (int)p.max_state);
     if (r < 0) return B200J2K_ERR_DEVICE;
     launches += r;
+    if (ev) cudaEventRecord(ev[2], s.stream);
     IdwtFrame f;
     memset(&f, 0, sizeof(f));
+    f.before_final = ev ? ev[3] : nullptr;
     f.d_tcs = d_tcs;
     f.d_groups = d_groups;
     f.h_tcs = p.tcs.data();
@@ -251,6 +255,7 @@ int run_kernels(Slot &s)
     r = launch_idwt_frame(s.stream, f);
     if (r < 0) return B200J2K_ERR_DEVICE;
     launches += r;
+    if (ev) cudaEventRecord(ev[4], s.stream);
     s.launches = launches;
     return 0;
 }
@@ -461,6 +466,28 @@ int b200j2k_run_staged(b200j2k_decoder *d, int slot)
     return run_kernels(d->slots[slot]);
 }
 
+int b200j2k_run_staged_timed(b200j2k_decoder *d, int slot, float *ms)
+{
+    if (!d || !ms || slot < 0 || slot >= (int)d->slots.size() || !d->slots[slot].staged)
+        return B200J2K_ERR_EINVAL;
+    if (cudaSetDevice(d->device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    cudaEvent_t ev[5];
+    for (auto &e : ev)
+        if (cudaEventCreate(&e) != cudaSuccess)
+            return B200J2K_ERR_DEVICE;
+    Slot &s = d->slots[slot];
+    int r = run_kernels(s, ev);
+    if (r >= 0 && cudaStreamSynchronize(s.stream) != cudaSuccess)
+        r = B200J2K_ERR_DEVICE;
+    if (r >= 0)
+        for (int i = 0; i < 4; i++)
+            cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    for (auto &e : ev)
+        cudaEventDestroy(e);
+    return r;
+}
+
 int b200j2k_sync(b200j2k_decoder *d, int slot)
 {
     if (!d || slot < 0 || slot >= (int)d->slots.size())
@@ -524,7 +551,7 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
     memset(&band, 0, sizeof(band));
     band.i_stepsize = 32768;
     size_t total = 0;
-    int maxw = 1, maxh = 1, maxL[2] = { 0, 0 };
+    int maxw = 1, max_area = 1, max_state = 16, maxL[2] = { 0, 0 };
     size_t a = 0, b = n;
     for (int i = 0; i < n; i++) {
         const int32_t *q = par + 10 * i;
@@ -545,7 +572,8 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
         d.dst_stride = d.w;
         total += (size_t)d.w * d.h;
         if (d.w > maxw) maxw = d.w;
-        if (d.h > maxh) maxh = d.h;
+        if (d.w * d.h > max_area) max_area = d.w * d.h;
+        if ((d.w + 3) * (d.h + 3) > max_state) max_state = (d.w + 3) * (d.h + 3);
         const bool refine = d.npasses && (d.npasses % 3) != 1;
         if (refine) order[--b] = (uint32_t)i; else order[a++] = (uint32_t)i;
         if (d.npasses && d.Lcup > maxL[refine]) maxL[refine] = d.Lcup;
@@ -577,8 +605,8 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
         cudaMemcpyAsync(d_order, order.data(), n * 4, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_band, &band, sizeof(band), cudaMemcpyHostToDevice, st);
         cudaMemsetAsync(d_out, 0x55, total * 4 + 4, st);
-        int r1 = launch_ht_decode(st, false, d_descs, d_order, (int)a, d_bytes, d_band, d_out, d_status, maxL[0], maxw, maxh);
-        int r2 = launch_ht_decode(st, true, d_descs, d_order + a, (int)(n - a), d_bytes, d_band, d_out, d_status, maxL[1], maxw, maxh);
+        int r1 = launch_ht_decode(st, false, d_descs, d_order, (int)a, d_bytes, d_band, d_out, d_status, maxL[0], maxw, max_area, max_state);
+        int r2 = launch_ht_decode(st, true, d_descs, d_order + a, (int)(n - a), d_bytes, d_band, d_out, d_status, maxL[1], maxw, max_area, max_state);
         if (r1 < 0 || r2 < 0) ret = B200J2K_ERR_DEVICE;
         cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, st);
         if (status) cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st);

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order, int nblocks,
                  const uint8_t *__restrict__ bytes, const BandDesc *__restrict__ bands,
                  uint32_t *__restrict__ coef, int32_t *__restrict__ status,
-                 int stream_words, int maxQW, int maxw, int maxh)
+                 int stream_words, int maxQW, int samp_words, int st_words)
 {
     extern __shared__ __align__(16) uint32_t smem[];
     uint16_t *tab = reinterpret_cast<uint16_t *>(smem);
@@ -255,12 +255,12 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
     const int row_words = 2 * (maxQW + 2);
     int per_warp = stream_words + row_words;
     if (REFINE)
-        per_warp += maxw * maxh + ((maxh + 3) * (maxw + 3) + 3) / 4;
+        per_warp += samp_words + st_words;
     uint32_t *wbase = smem + 1024 + (size_t)warp * per_warp;
     uint32_t *streams = wbase;
     uint32_t *rowbuf = wbase + stream_words;
     uint32_t *samp = rowbuf + row_words;
-    uint8_t *st = reinterpret_cast<uint8_t *>(samp + maxw * maxh);
+    uint8_t *st = reinterpret_cast<uint8_t *>(samp + samp_words);
 
     const int gw = blockIdx.x * WARPS_PER_CTA + warp;
     if (gw >= nblocks)
@@ -672,23 +672,24 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
 }
 
 /* ---- host-side launcher ------------------------------------------------------------------------------ */
-size_t ht_smem_bytes(bool refine, int stream_words, int maxQW, int maxw, int maxh)
+size_t ht_smem_bytes(bool refine, int stream_words, int maxQW, int samp_words, int st_words)
 {
     size_t per_warp = (size_t)stream_words + 2 * (size_t)(maxQW + 2);
     if (refine)
-        per_warp += (size_t)maxw * maxh + ((size_t)(maxh + 3) * (maxw + 3) + 3) / 4;
+        per_warp += (size_t)samp_words + st_words;
     return 4096 + per_warp * 4 * WARPS_PER_CTA;
 }
 
 int launch_ht_decode(cudaStream_t stream, bool refine, const CblkDesc *descs, const uint32_t *order, int nblocks,
                      const uint8_t *bytes, const BandDesc *bands, void *coef, int32_t *status,
-                     int max_Lcup, int maxw, int maxh)
+                     int max_Lcup, int maxw, int max_area, int max_state)
 {
     if (nblocks <= 0)
         return 0;
     const int stream_words = (max_Lcup + 3) / 4 + 8;
     const int maxQW = (maxw + 1) / 2;
-    const size_t smem = ht_smem_bytes(refine, stream_words, maxQW, maxw, maxh);
+    const int samp_words = max_area, st_words = (max_state + 3) / 4;
+    const size_t smem = ht_smem_bytes(refine, stream_words, maxQW, samp_words, st_words);
     if (smem > 227 * 1024)
         return -1;
     const int grid = (nblocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
@@ -698,13 +699,13 @@ int launch_ht_decode(cudaStream_t stream, bool refine, const CblkDesc *descs, co
         if (err != cudaSuccess)
             return -2;
         ht_decode_kernel<true><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(
-            descs, order, nblocks, bytes, bands, (uint32_t *)coef, status, stream_words, maxQW, maxw, maxh);
+            descs, order, nblocks, bytes, bands, (uint32_t *)coef, status, stream_words, maxQW, samp_words, st_words);
     } else {
         err = cudaFuncSetAttribute(ht_decode_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess)
             return -2;
         ht_decode_kernel<false><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(
-            descs, order, nblocks, bytes, bands, (uint32_t *)coef, status, stream_words, maxQW, maxw, maxh);
+            descs, order, nblocks, bytes, bands, (uint32_t *)coef, status, stream_words, maxQW, samp_words, st_words);
     }
     return cudaGetLastError() == cudaSuccess ? 1 : -3;
 }

@@ -378,7 +378,7 @@ int run_levels(cudaStream_t stream, const IdwtFrame &f, int max_levels, bool any
 int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f)
 {
     int launches = 0;
-    /* grid extents per level and per transform type (host copies of the tables) */
+    /* pass 1: intermediate levels of every transform type present (host copies of the tables size the grids) */
     for (int type = 0; type < 3; type++) {
         int mw[J2K_MAX_LEVELS] = { 0 }, mh[J2K_MAX_LEVELS] = { 0 };
         int maxlev = 0;
@@ -399,7 +399,11 @@ int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f)
         if (type == J2K_DWT53) launches += run_levels<J2K_DWT53>(stream, f, maxlev, any, mw, mh, 0);
         if (type == J2K_DWT97) launches += run_levels<J2K_DWT97>(stream, f, maxlev, any, mw, mh, 0);
         if (type == J2K_DWT97_INT) launches += run_levels<J2K_DWT97_INT>(stream, f, maxlev, any, mw, mh, 0);
-        /* fused last level */
+    }
+    if (f.before_final)
+        cudaEventRecord(f.before_final, stream);
+    /* pass 2: last level fused with MCT + level shift + clip + pack */
+    for (int type = 0; type < 3; type++) {
         int gw = 0, gh = 0, maxc = 0;
         bool anyg = false;
         for (int i = 0; i < f.ngroups; i++) {

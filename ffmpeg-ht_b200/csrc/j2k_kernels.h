@@ -13,11 +13,12 @@ namespace b200j2k {
 
 /* HT block decode + dequantisation.  order: optional list of descriptor indices (nullptr = 0..n-1).
  * refine = blocks carrying SigProp/MagRef passes (needs the shared-memory sample copy).
+ * maxw: widest block; max_area: largest w*h; max_state: largest (w+3)*(h+3) (both only matter for refine).
  * Returns 1 when a kernel was queued, 0 when there was nothing to do, < 0 on launch failure. */
 int launch_ht_decode(cudaStream_t stream, bool refine, const CblkDesc *descs, const uint32_t *order, int nblocks,
                      const uint8_t *bytes, const BandDesc *bands, void *coef, int32_t *status,
-                     int max_Lcup, int maxw, int maxh);
-size_t ht_smem_bytes(bool refine, int stream_words, int maxQW, int maxw, int maxh);
+                     int max_Lcup, int maxw, int max_area, int max_state);
+size_t ht_smem_bytes(bool refine, int stream_words, int maxQW, int samp_words, int st_words);
 
 /* Inverse DWT levels + final MCT / level shift / clip / pack.
  * tcs/groups: device copies of the plan tables.  coefA: HT output (Mallat layout), coefB/coefC: LL
@@ -32,6 +33,7 @@ struct IdwtFrame {
     uint8_t *picture;
     uint64_t plane_off[4];
     int plane_row_bytes[4];
+    cudaEvent_t before_final;     /* optional: recorded between the level kernels and the fused last level */
 };
 int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f);
 

@@ -463,6 +463,7 @@ int Parser::build_geometry(int flags)
     ll_elems = 0;
     max_levels = 0;
     max_w = max_h = 0;
+    max_area = max_state = 0;
     const int ntiles = h.ntx * h.nty;
     tiles_.resize(ntiles);
     const bool planar = h.pix == B200J2K_PIX_PLANAR8 || h.pix == B200J2K_PIX_PLANAR16;
@@ -611,6 +612,8 @@ int Parser::build_geometry(int flags)
                                     return B200J2K_ERR_PATCHWELCOME;
                                 max_w = max_w > d.w ? max_w : d.w;
                                 max_h = max_h > d.h ? max_h : d.h;
+                                if ((uint32_t)d.w * d.h > max_area) max_area = (uint32_t)d.w * d.h;
+                                if ((uint32_t)(d.w + 3) * (d.h + 3) > max_state) max_state = (uint32_t)(d.w + 3) * (d.h + 3);
                                 cblk_template_.push_back(d);
                             }
                         }

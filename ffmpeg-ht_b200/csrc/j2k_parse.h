@@ -105,6 +105,7 @@ public:
     uint64_t picture_bytes = 0;
     int64_t consumed = 0;
     uint32_t max_w = 0, max_h = 0;    /* largest code-block in the frame */
+    uint32_t max_area = 0, max_state = 0;  /* largest w*h and (w+3)*(h+3) */
     uint32_t max_Lcup = 0, max_Lref = 0;
     int any_refine = 0;
 
