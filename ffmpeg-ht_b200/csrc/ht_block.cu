@@ -38,35 +38,46 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 __device__ __constant__ uint8_t c_mel_exp[13] = { 0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 4, 5 };
 
 /* ---- H3: MEL (jpeg2000htdec.c:429-440, :462-495): MSB-first bits over Dcup[Pcup..Lcup), 7 bits after
- * 0xFF, 0xFF past the end.  sc[] is the shared-memory copy of the suffix with modDcup applied. */
+ * 0xFF, 0xFF past the end.  The few MEL bytes are read straight from global memory (L1-resident after
+ * the first touch); modDcup (:1277-1278) is applied on the fly to the last two bytes. */
 struct Mel {
+    const uint8_t *p;       /* Dcup + Pcup */
+    int len;                /* Scup */
     int pos, left;
     unsigned cur;
     int k, run, one;
 };
 
-__device__ __forceinline__ int mel_bit(Mel &m, const uint8_t *sc, int sclen)
+__device__ __forceinline__ int mel_bit(Mel &m)
 {
     if (m.left == 0) {
         m.left = m.cur == 0xFF ? 7 : 8;
-        m.cur = m.pos < sclen ? sc[m.pos] : 0xFF;
-        m.pos += m.pos < sclen;
+        unsigned b = 0xFF;
+        if (m.pos < m.len) {
+            b = m.p[m.pos];
+            if (m.pos == m.len - 2)
+                b |= 0x0F;
+            else if (m.pos == m.len - 1)
+                b = 0xFF;
+            m.pos++;
+        }
+        m.cur = b;
     }
     m.left--;
     return (m.cur >> m.left) & 1;
 }
 
-__device__ __forceinline__ int mel_symbol(Mel &m, const uint8_t *sc, int sclen)
+__device__ __forceinline__ int mel_symbol(Mel &m)
 {
     if (m.run == 0 && !m.one) {
         int e = c_mel_exp[m.k];
-        if (mel_bit(m, sc, sclen)) {
+        if (mel_bit(m)) {
             m.run = 1 << e;
             m.k = min(12, m.k + 1);
         } else {
             int r = 0;
             while (e-- > 0)
-                r = 2 * r + mel_bit(m, sc, sclen);
+                r = 2 * r + mel_bit(m);
             m.run = r;
             m.k = max(0, m.k - 1);
             m.one = 1;
@@ -80,82 +91,146 @@ __device__ __forceinline__ int mel_symbol(Mel &m, const uint8_t *sc, int sclen)
     return 1;
 }
 
-/* ---- H2: backward VLC reader (jpeg2000htdec.c:145-201, :283-295): bytes from Dcup[Lcup-2] down to
- * Dcup[Pcup]; a byte whose low 7 bits are ones gives 7 bits when the byte read before it is > 0x8F.
- * Below Pcup the stream reads as zeros. */
-struct Vlc {
-    int pos;
-    unsigned prev;
-    uint64_t acc;
-    int n;
-};
-
-__device__ __forceinline__ void vlc_fill(Vlc &v, const uint8_t *sc)
+/* ---- H2: VLC.  The backward byte stream (jpeg2000htdec.c:145-201, :283-295: bytes from Dcup[Lcup-2]
+ * down to Dcup[Pcup]; a byte whose low 7 bits are ones gives 7 bits when the byte read before it is
+ * > 0x8F) is un-stuffed once, in parallel, into a forward LSB-first bit array in shared memory.  The
+ * serial decoder then works on a 32-bit window fetched at a bit position: every "drop" is a 32-bit
+ * shift.  Past the end the stream reads as zeros. */
+__device__ __forceinline__ uint32_t vlc_fetch(const uint32_t *vl, uint32_t pos, uint32_t limit)
 {
-    while (v.n <= 56) {
-        unsigned b = v.pos >= 0 ? sc[v.pos] : 0;
-        v.pos--;
-        int nb = ((b & 0x7F) == 0x7F && v.prev > 0x8F) ? 7 : 8;
-        v.acc |= (uint64_t)(b & ((1u << nb) - 1)) << v.n;
-        v.n += nb;
-        v.prev = b;
+    pos = min(pos, limit);
+    const uint32_t w = pos >> 5, s = pos & 31;
+    return __funnelshift_r(vl[w], vl[w + 1], s);
+}
+
+/* ---- H5: U-VLC (jpeg2000htdec.c:338-388) on a 32-bit window ------------------------------------------ */
+__device__ __forceinline__ int uvlc_prefix(uint32_t &win, int &used)
+{
+    const int f = __ffs((win & 7) | 8);         /* 1..4: position of the first 1 among three bits */
+    const int len = min(f, 3);
+    win >>= len;
+    used += len;
+    return f <= 3 ? f : 5;
+}
+
+__device__ __forceinline__ int uvlc_suffix(uint32_t &win, int &used, int pfx)
+{
+    const int len = pfx < 3 ? 0 : (pfx == 3 ? 1 : 5);
+    const int v = win & ((1u << len) - 1);
+    win >>= len;
+    used += len;
+    return v;
+}
+
+__device__ __forceinline__ int uvlc_ext(uint32_t &win, int &used, int sfx)
+{
+    const int len = sfx >= 28 ? 4 : 0;
+    const int v = win & ((1u << len) - 1);
+    win >>= len;
+    used += len;
+    return v;
+}
+
+__device__ __forceinline__ int uvlc_whole(uint32_t &win, int &used)
+{
+    const int p = uvlc_prefix(win, used);
+    const int s = uvlc_suffix(win, used, p);
+    return p + s + 4 * uvlc_ext(win, used, s);
+}
+
+/*
+ * The serial, warp-uniform part for one segment of up to 32 quads of one quad row: MEL + CxtVLC + U-VLC
+ * (jpeg2000htdec.c:632-768 first row, :784-973 other rows).  Every lane executes it on identical data;
+ * lane j keeps quad j's result in `mine` = u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16.
+ * carry: first row -> context carried from the previous quad; other rows -> (sigma_W[3] | sigma_W[2]).
+ * mA / mC: other rows -> per-quad bits (sigma_N[1] | sigma_NW[3]) and (sigma_N[3] | sigma_NE[1]).
+ */
+template <bool FIRST>
+__device__ __forceinline__ unsigned decode_segment(Mel &mel, const uint32_t *vl, uint32_t &vpos, uint32_t vlimit,
+                                                   const uint16_t *table, int nq, int lane, unsigned mA,
+                                                   unsigned mC, int &carry)
+{
+    unsigned mine = 0;
+    for (int j = 0; j < nq; j += 2) {
+        uint32_t win = vlc_fetch(vl, vpos, vlimit);
+        int used = 0;
+        unsigned q0 = 0, q1 = 0;
+        int ctx = FIRST ? carry : (int)((mA & 1) | (carry << 1) | ((mC & 1) << 2));
+        if (ctx != 0 || mel_symbol(mel)) {
+            const unsigned e = table[(win & 0x7F) | ((unsigned)ctx << 7)];
+            const unsigned l = e & 7;
+            win >>= l;
+            used += l;
+            q0 = e >> 3;
+        }
+        {
+            const unsigned rho = (q0 >> 1) & 15;
+            carry = FIRST ? (int)(((rho & 3) ? 1 : 0) | ((rho >> 1) & 6)) : (int)((rho >> 2) != 0);
+        }
+        if (j + 1 < nq) {
+            ctx = FIRST ? carry : (int)(((mA >> 1) & 1) | (carry << 1) | (((mC >> 1) & 1) << 2));
+            if (ctx != 0 || mel_symbol(mel)) {
+                const unsigned e = table[(win & 0x7F) | ((unsigned)ctx << 7)];
+                const unsigned l = e & 7;
+                win >>= l;
+                used += l;
+                q1 = e >> 3;
+            }
+            const unsigned rho = (q1 >> 1) & 15;
+            carry = FIRST ? (int)(((rho & 3) ? 1 : 0) | ((rho >> 1) & 6)) : (int)((rho >> 2) != 0);
+        }
+        mA >>= 2;
+        mC >>= 2;
+        int u0 = 0, u1 = 0;
+        if ((q0 | q1) & 1) {
+            vpos += used;
+            used = 0;
+            win = vlc_fetch(vl, vpos, vlimit);
+            const int uo0 = q0 & 1, uo1 = q1 & 1;
+            if (uo0 & uo1) {
+                if (FIRST) {                             /* :671-704 */
+                    if (mel_symbol(mel)) {
+                        const int p0 = uvlc_prefix(win, used), p1 = uvlc_prefix(win, used);
+                        const int s0 = uvlc_suffix(win, used, p0), s1 = uvlc_suffix(win, used, p1);
+                        const int e0 = uvlc_ext(win, used, s0), e1 = uvlc_ext(win, used, s1);
+                        u0 = 2 + p0 + s0 + 4 * e0;
+                        u1 = 2 + p1 + s1 + 4 * e1;
+                    } else {
+                        const int p0 = uvlc_prefix(win, used);
+                        if (p0 > 2) {
+                            u1 = (int)(win & 1) + 1;
+                            win >>= 1;
+                            used += 1;
+                            const int s0 = uvlc_suffix(win, used, p0);
+                            u0 = p0 + s0 + 4 * uvlc_ext(win, used, s0);
+                        } else {
+                            const int p1 = uvlc_prefix(win, used);
+                            const int s0 = uvlc_suffix(win, used, p0), s1 = uvlc_suffix(win, used, p1);
+                            const int e0 = uvlc_ext(win, used, s0), e1 = uvlc_ext(win, used, s1);
+                            u0 = p0 + s0 + 4 * e0;
+                            u1 = p1 + s1 + 4 * e1;
+                        }
+                    }
+                } else {                                 /* :833-845 */
+                    const int p0 = uvlc_prefix(win, used), p1 = uvlc_prefix(win, used);
+                    const int s0 = uvlc_suffix(win, used, p0), s1 = uvlc_suffix(win, used, p1);
+                    const int e0 = uvlc_ext(win, used, s0), e1 = uvlc_ext(win, used, s1);
+                    u0 = p0 + s0 + 4 * e0;
+                    u1 = p1 + s1 + 4 * e1;
+                }
+            } else if (uo0) {
+                u0 = uvlc_whole(win, used);
+            } else {
+                u1 = uvlc_whole(win, used);
+            }
+        }
+        vpos += used;
+        if (lane == j)
+            mine = q0 | ((unsigned)u0 << 16);
+        if (lane == j + 1)
+            mine = q1 | ((unsigned)u1 << 16);
     }
-}
-
-__device__ __forceinline__ unsigned vlc_peek(const Vlc &v, int nb) { return (unsigned)v.acc & ((1u << nb) - 1); }
-__device__ __forceinline__ void vlc_drop(Vlc &v, int nb) { v.acc >>= nb; v.n -= nb; }
-
-/* ---- H5: U-VLC (jpeg2000htdec.c:338-388) ------------------------------------------------------------ */
-__device__ __forceinline__ int uvlc_prefix(Vlc &v)
-{
-    unsigned b = (unsigned)v.acc & 7;
-    int len, val;
-    if (b & 1) { len = 1; val = 1; }
-    else if (b & 2) { len = 2; val = 2; }
-    else if (b & 4) { len = 3; val = 3; }
-    else { len = 3; val = 5; }
-    vlc_drop(v, len);
-    return val;
-}
-
-__device__ __forceinline__ int uvlc_suffix(Vlc &v, int pfx)
-{
-    if (pfx < 3)
-        return 0;
-    unsigned b = (unsigned)v.acc & 31;
-    if (pfx == 3) {
-        vlc_drop(v, 1);
-        return b & 1;
-    }
-    vlc_drop(v, 5);
-    return b;
-}
-
-__device__ __forceinline__ int uvlc_ext(Vlc &v, int sfx)
-{
-    if (sfx < 28)
-        return 0;
-    int e = (unsigned)v.acc & 15;
-    vlc_drop(v, 4);
-    return e;
-}
-
-__device__ __forceinline__ int uvlc_whole(Vlc &v)
-{
-    int p = uvlc_prefix(v);
-    int s = uvlc_suffix(v, p);
-    return p + s + 4 * uvlc_ext(v, s);
-}
-
-/* ---- H4: one quad (jpeg2000htdec.c:300-331, :510-531) ------------------------------------------------ */
-__device__ __forceinline__ unsigned decode_quad(Mel &mel, Vlc &vlc, const uint16_t *table, int ctx,
-                                                const uint8_t *sc, int sclen)
-{
-    if (ctx == 0 && mel_symbol(mel, sc, sclen) == 0)
-        return 0;
-    unsigned e = table[vlc_peek(vlc, 7) | ((unsigned)ctx << 7)];
-    vlc_drop(vlc, e & 7);
-    return e >> 3;          /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 */
+    return mine;
 }
 
 /* read nb (1..31) bits at bit position pos of the un-stuffed MagSgn array */
@@ -229,12 +304,12 @@ __device__ __forceinline__ int sp_bit(SpBits &s)
  * Shared memory per CTA: [tables 4 KiB][per-warp region] x WARPS_PER_CTA.
  * Per-warp region (32-bit words):
  *   ms   [ms_words]          un-stuffed MagSgn bits (+2 words of ones)
- *   sc   [sc_words]          suffix bytes Dcup[Pcup..Lcup) with modDcup applied
+ *   vl   [vl_words]          un-stuffed VLC bits, forward order (+2 words of zeros)
  *   row  [2][maxQW + 2]      per-quad (rho | E1<<8 | E3<<16) of the previous / current quad row
  *   REFINE only:
  *   samp [maxw * maxh]       sign-magnitude samples
  *   st   [(maxh+3)*(maxw+3)] bytes, sample states with a one-sample apron
- * ms and sc share one allocation of `stream_words`: ms takes what Pcup needs, sc the rest.
+ * ms and vl share one allocation of `stream_words`: ms takes what Pcup needs, vl what Scup needs.
  */
 template <bool REFINE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
@@ -320,17 +395,58 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
 
     /* ---- stage the streams ---- */
     const int ms_words = (Pcup + 3) / 4 + 2;
+    const int vl_words = (Scup + 3) / 4 + 3;
     uint32_t *ms = streams;
-    uint8_t *sc = reinterpret_cast<uint8_t *>(streams + ms_words);
-    for (int i = lane; i < ms_words; i += 32)
-        ms[i] = 0;
-    for (int i = lane; i < Scup; i += 32) {
-        unsigned b = Dcup[Pcup + i];
-        if (i == Scup - 1) b = 0xFF;                     /* modDcup (:1277-1278) */
-        if (i == Scup - 2) b |= 0x0F;
-        sc[i] = (uint8_t)b;
-    }
+    uint32_t *vl = streams + ms_words;
+    for (int i = lane; i < ms_words + vl_words; i += 32)
+        streams[i] = 0;
     __syncwarp();
+    /* un-stuff VLC: read order k = 0.. is Dcup[Lcup-2-k]; modDcup sets the low nibble of the first byte
+     * and makes the byte "read before it" 0xFF (:1277-1278, :283-295) */
+    uint32_t vl_bits = 0;
+    {
+        const int nv = Scup - 1;                        /* bytes Dcup[Pcup .. Lcup-2] */
+        unsigned carry = 0xFF;
+        for (int chunk = 0; chunk < nv; chunk += 128) {
+            const int idx = chunk + lane * 4;
+            unsigned b[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                b[k] = idx + k < nv ? Dcup[Lcup - 2 - (idx + k)] : 0;
+                if (idx + k == 0)
+                    b[k] |= 0x0F;
+            }
+            unsigned before = __shfl_up_sync(FULL, b[3], 1);
+            if (lane == 0)
+                before = carry;
+            uint64_t v = 0;
+            int tot = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int nb = idx + k < nv ? (((b[k] & 0x7F) == 0x7F && before > 0x8F) ? 7 : 8) : 0;
+                v |= (uint64_t)(b[k] & ((1u << nb) - 1)) << tot;
+                tot += nb;
+                before = b[k];
+            }
+            int incl = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o)
+                    incl += t;
+            }
+            const uint32_t off = vl_bits + (uint32_t)(incl - tot);
+            if (tot) {
+                const uint32_t wd = off >> 5, sft = off & 31;
+                const uint64_t sh = v << sft;
+                atomicOr(&vl[wd], (uint32_t)sh);
+                if ((uint32_t)(sh >> 32))
+                    atomicOr(&vl[wd + 1], (uint32_t)(sh >> 32));
+            }
+            vl_bits += (uint32_t)__shfl_sync(FULL, incl, 31);
+            carry = __shfl_sync(FULL, b[3], 31);
+        }
+    }
     /* un-stuff MagSgn: byte after 0xFF carries 7 bits (:207-221); bit 7 of such a byte is OR-ed into the
      * next byte's bit 0 exactly as the reference's 64-bit accumulator does */
     uint32_t ms_bits = 0;
@@ -392,97 +508,28 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
     }
     __syncwarp();
 
-    Mel mel = { 0, 0, 0, 0, 0, 0 };
-    Vlc vlc = { Scup - 2, 0xFF, 0, 0 };
-    vlc_fill(vlc, sc);
-    vlc_drop(vlc, 4);
+    Mel mel = { Dcup + Pcup, Scup, 0, 0, 0, 0, 0, 0 };
+    uint32_t vpos = 4;                                   /* the Scup nibble is skipped (:283-295) */
+    const uint32_t vlimit = (uint32_t)(vl_words - 2) * 32;
     uint32_t ms_pos = 0;
     bool bad = false;
     const int SW = w + 3;                                /* state row stride (REFINE) */
 
     for (int qy = 0; qy < QH && !bad; qy++) {
-        const uint16_t *table = qy == 0 ? tab : tab + 1024;
-        int ctxrun = 0;                                  /* first row: context from the previous quad */
-        int west = 0;                                    /* other rows: (sigma_W[3] | sigma_W[2]) */
+        int carry = 0;
         for (int qb = 0; qb < QW; qb += 32) {
             const int nq = min(32, QW - qb);
             const int qx = qb + lane;
-            unsigned mA = 0, mC = 0;
-            if (qy > 0) {
+            unsigned mine;                               /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16 */
+            if (qy == 0) {
+                mine = decode_segment<true>(mel, vl, vpos, vlimit, tab, nq, lane, 0, 0, carry);
+            } else {
                 /* row[] is stored with a +1 offset and zero sentinels at both ends */
-                unsigned n = qx < QW ? rowprev[qx + 1] : 0, nw = qx < QW ? rowprev[qx] : 0,
-                         ne = qx < QW ? rowprev[qx + 2] : 0;
-                mA = __ballot_sync(FULL, ((n >> 1) | (nw >> 3)) & 1);      /* sigma_N[1] | sigma_NW[3] */
-                mC = __ballot_sync(FULL, ((n >> 3) | (ne >> 1)) & 1);      /* sigma_N[3] | sigma_NE[1] */
-            }
-            unsigned mine = 0;                           /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16 */
-            /* ---- serial, warp-uniform: MEL + CxtVLC + U-VLC for up to 16 quad pairs ---- */
-            for (int j = 0; j < nq; j += 2) {
-                const int np = j + 1 < nq ? 2 : 1;
-                vlc_fill(vlc, sc);
-                unsigned q0, q1 = 0;
-                int ctx;
-                if (qy == 0)
-                    ctx = ctxrun;
-                else
-                    ctx = ((mA >> j) & 1) | (west << 1) | (((mC >> j) & 1) << 2);
-                q0 = decode_quad(mel, vlc, table, ctx, sc, Scup);
-                {
-                    unsigned rho = (q0 >> 1) & 15;
-                    ctxrun = ((rho & 3) ? 1 : 0) | ((rho >> 1) & 6);
-                    west = (rho >> 2) ? 1 : 0;
-                }
-                if (np == 2) {
-                    if (qy == 0)
-                        ctx = ctxrun;
-                    else
-                        ctx = ((mA >> (j + 1)) & 1) | (west << 1) | (((mC >> (j + 1)) & 1) << 2);
-                    q1 = decode_quad(mel, vlc, table, ctx, sc, Scup);
-                    unsigned rho = (q1 >> 1) & 15;
-                    ctxrun = ((rho & 3) ? 1 : 0) | ((rho >> 1) & 6);
-                    west = (rho >> 2) ? 1 : 0;
-                }
-                int u0 = 0, u1 = 0;
-                const int uo0 = q0 & 1, uo1 = q1 & 1;
-                if (uo0 & uo1) {
-                    if (qy == 0) {                       /* :671-704 */
-                        if (mel_symbol(mel, sc, Scup)) {
-                            int p0_ = uvlc_prefix(vlc), p1_ = uvlc_prefix(vlc);
-                            int s0 = uvlc_suffix(vlc, p0_), s1 = uvlc_suffix(vlc, p1_);
-                            int e0 = uvlc_ext(vlc, s0), e1 = uvlc_ext(vlc, s1);
-                            u0 = 2 + p0_ + s0 + 4 * e0;
-                            u1 = 2 + p1_ + s1 + 4 * e1;
-                        } else {
-                            int p0_ = uvlc_prefix(vlc);
-                            if (p0_ > 2) {
-                                u1 = (int)vlc_peek(vlc, 1) + 1;
-                                vlc_drop(vlc, 1);
-                                int s0 = uvlc_suffix(vlc, p0_);
-                                u0 = p0_ + s0 + 4 * uvlc_ext(vlc, s0);
-                            } else {
-                                int p1_ = uvlc_prefix(vlc);
-                                int s0 = uvlc_suffix(vlc, p0_), s1 = uvlc_suffix(vlc, p1_);
-                                int e0 = uvlc_ext(vlc, s0), e1 = uvlc_ext(vlc, s1);
-                                u0 = p0_ + s0 + 4 * e0;
-                                u1 = p1_ + s1 + 4 * e1;
-                            }
-                        }
-                    } else {                             /* :833-845 */
-                        int p0_ = uvlc_prefix(vlc), p1_ = uvlc_prefix(vlc);
-                        int s0 = uvlc_suffix(vlc, p0_), s1 = uvlc_suffix(vlc, p1_);
-                        int e0 = uvlc_ext(vlc, s0), e1 = uvlc_ext(vlc, s1);
-                        u0 = p0_ + s0 + 4 * e0;
-                        u1 = p1_ + s1 + 4 * e1;
-                    }
-                } else if (uo0) {
-                    u0 = uvlc_whole(vlc);
-                } else if (uo1) {
-                    u1 = uvlc_whole(vlc);
-                }
-                if (lane == j)
-                    mine = (q0 & 0xFFFF) | ((unsigned)u0 << 16);
-                if (lane == j + 1)
-                    mine = (q1 & 0xFFFF) | ((unsigned)u1 << 16);
+                const unsigned n = qx < QW ? rowprev[qx + 1] : 0, nw = qx < QW ? rowprev[qx] : 0,
+                               ne = qx < QW ? rowprev[qx + 2] : 0;
+                const unsigned mA = __ballot_sync(FULL, ((n >> 1) | (nw >> 3)) & 1);   /* sigma_N[1] | sigma_NW[3] */
+                const unsigned mC = __ballot_sync(FULL, ((n >> 3) | (ne >> 1)) & 1);   /* sigma_N[3] | sigma_NE[1] */
+                mine = decode_segment<false>(mel, vl, vpos, vlimit, tab + 1024, nq, lane, mA, mC, carry);
             }
             /* ---- parallel: lane = quad.  exponent predictor, MagSgn, write-back ---- */
             const bool act = lane < nq;

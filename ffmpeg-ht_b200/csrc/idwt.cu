@@ -270,8 +270,6 @@ template <int TYPE> __device__ __forceinline__ int to_pixel(uint32_t raw, int cb
     int val;
     if (TYPE == J2K_DWT97)
         val = __float2int_rn(__uint_as_float(raw));
-    else if (TYPE == J2K_DWT97_INT)
-        val = (int32_t)((int64_t)(int32_t)raw + 128) >> 8;       /* undo I_PRESHIFT (jpeg2000dwt.c:534-536) */
     else
         val = (int32_t)raw;
     val += 1 << (cbps - 1);
@@ -328,6 +326,13 @@ idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__
 #pragma unroll
         for (int c = 0; c < J2K_MAX_COMP; c++)
             v[c] = c < g.ncomp ? dyn[(size_t)c * SH * SWD + (r + HALO) * SWD + HALO + cx] : 0;
+        if (TYPE == J2K_DWT97_INT) {
+            /* undo I_PRESHIFT: the last thing dwt_decode97_int does, i.e. before the component transform
+             * (jpeg2000dwt.c:534-536) */
+#pragma unroll
+            for (int c = 0; c < J2K_MAX_COMP; c++)
+                v[c] = (uint32_t)((int32_t)((int64_t)(int32_t)v[c] + 128) >> 8);
+        }
         if (g.mct)
             mct<TYPE>(v[0], v[1], v[2]);
         const size_t px = (size_t)(t0.out_x + X - o.u0) * g.pixel_stride;
