@@ -33,6 +33,7 @@ namespace b200j2k {
 namespace {
 
 constexpr int WARPS_PER_CTA = 4;
+constexpr int TABLE_WORDS = 1024 + 128;         /* 2 x 1024 x u16 CxtVLC + 256 x u16 U-VLC pair table */
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 __device__ __constant__ uint8_t c_mel_exp[13] = { 0, 0, 0, 1, 1, 1, 2, 2, 2, 3, 3, 4, 5 };
@@ -94,13 +95,22 @@ __device__ __forceinline__ int mel_symbol(Mel &m)
 /* ---- H2: VLC.  The backward byte stream (jpeg2000htdec.c:145-201, :283-295: bytes from Dcup[Lcup-2]
  * down to Dcup[Pcup]; a byte whose low 7 bits are ones gives 7 bits when the byte read before it is
  * > 0x8F) is un-stuffed once, in parallel, into a forward LSB-first bit array in shared memory.  The
- * serial decoder then works on a 32-bit window fetched at a bit position: every "drop" is a 32-bit
- * shift.  Past the end the stream reads as zeros. */
-__device__ __forceinline__ uint32_t vlc_fetch(const uint32_t *vl, uint32_t pos, uint32_t limit)
+ * serial decoder fetches 64 bits at the current bit position once per quad pair (a pair consumes at most
+ * 7 + 7 + 24 bits); everything after that is 32-bit shifts.  Past the end the stream reads as zeros. */
+struct VlcWin {
+    uint32_t lo, hi;
+};
+
+__device__ __forceinline__ VlcWin vlc_fetch(const uint32_t *vl, uint32_t pos, uint32_t limit)
 {
     pos = min(pos, limit);
-    const uint32_t w = pos >> 5, s = pos & 31;
-    return __funnelshift_r(vl[w], vl[w + 1], s);
+    const uint32_t *p = vl + (pos >> 5);
+    const uint32_t s = pos & 31;
+    const uint32_t a = p[0], b = p[1], c = p[2];
+    VlcWin w;
+    w.lo = __funnelshift_r(a, b, s);
+    w.hi = __funnelshift_r(b, c, s);
+    return w;
 }
 
 /* ---- H5: U-VLC (jpeg2000htdec.c:338-388) on a 32-bit window ------------------------------------------ */
@@ -138,99 +148,140 @@ __device__ __forceinline__ int uvlc_whole(uint32_t &win, int &used)
     return p + s + 4 * uvlc_ext(win, used, s);
 }
 
+/* U-VLC pair table for the non-initial quad rows (:833-854): index = mode << 6 | six stream bits, mode =
+ * u_off0 | u_off1 << 1; entry = total prefix length | prefix0 << 3 | prefix1 << 6 | suffix length0 << 9 |
+ * suffix length1 << 12.  Built once per CTA in shared memory. */
+__device__ __forceinline__ uint16_t uvlc_pair_entry(int idx)
+{
+    const int mode = idx >> 6;
+    uint32_t w = idx & 63;
+    int used = 0, p0 = 0, p1 = 0;
+    if (mode & 1)
+        p0 = uvlc_prefix(w, used);
+    if (mode & 2)
+        p1 = uvlc_prefix(w, used);
+    const int s0 = p0 < 3 ? 0 : (p0 == 3 ? 1 : 5), s1 = p1 < 3 ? 0 : (p1 == 3 ? 1 : 5);
+    return (uint16_t)(used | (p0 << 3) | (p1 << 6) | (s0 << 9) | (s1 << 12));
+}
+
 /*
  * The serial, warp-uniform part for one segment of up to 32 quads of one quad row: MEL + CxtVLC + U-VLC
- * (jpeg2000htdec.c:632-768 first row, :784-973 other rows).  Every lane executes it on identical data;
- * lane j keeps quad j's result in `mine` = u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16.
+ * (jpeg2000htdec.c:632-768 first row, :784-973 other rows).  Every lane executes it on identical data and
+ * stores quad j's result in qinfo[j] = u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16 (shared memory,
+ * same-address broadcast stores).
  * carry: first row -> context carried from the previous quad; other rows -> (sigma_W[3] | sigma_W[2]).
  * mA / mC: other rows -> per-quad bits (sigma_N[1] | sigma_NW[3]) and (sigma_N[3] | sigma_NE[1]).
  */
-template <bool FIRST>
-__device__ __forceinline__ unsigned decode_segment(Mel &mel, const uint32_t *vl, uint32_t &vpos, uint32_t vlimit,
-                                                   const uint16_t *table, int nq, int lane, unsigned mA,
-                                                   unsigned mC, int &carry)
+template <bool FIRST, bool PAIR>
+__device__ __forceinline__ void decode_pair(Mel &mel, const uint32_t *vl, uint32_t &vpos, uint32_t vlimit,
+                                            const uint16_t *table, const uint16_t *uvtab, unsigned mA, unsigned mC,
+                                            int &carry, uint32_t *qout)
 {
-    unsigned mine = 0;
-    for (int j = 0; j < nq; j += 2) {
-        uint32_t win = vlc_fetch(vl, vpos, vlimit);
-        int used = 0;
-        unsigned q0 = 0, q1 = 0;
-        int ctx = FIRST ? carry : (int)((mA & 1) | (carry << 1) | ((mC & 1) << 2));
-        if (ctx != 0 || mel_symbol(mel)) {
-            const unsigned e = table[(win & 0x7F) | ((unsigned)ctx << 7)];
-            const unsigned l = e & 7;
-            win >>= l;
-            used += l;
-            q0 = e >> 3;
-        }
-        {
-            const unsigned rho = (q0 >> 1) & 15;
-            carry = FIRST ? (int)(((rho & 3) ? 1 : 0) | ((rho >> 1) & 6)) : (int)((rho >> 2) != 0);
-        }
-        if (j + 1 < nq) {
-            ctx = FIRST ? carry : (int)(((mA >> 1) & 1) | (carry << 1) | (((mC >> 1) & 1) << 2));
-            if (ctx != 0 || mel_symbol(mel)) {
-                const unsigned e = table[(win & 0x7F) | ((unsigned)ctx << 7)];
-                const unsigned l = e & 7;
-                win >>= l;
-                used += l;
-                q1 = e >> 3;
-            }
-            const unsigned rho = (q1 >> 1) & 15;
-            carry = FIRST ? (int)(((rho & 3) ? 1 : 0) | ((rho >> 1) & 6)) : (int)((rho >> 2) != 0);
-        }
-        mA >>= 2;
-        mC >>= 2;
-        int u0 = 0, u1 = 0;
-        if ((q0 | q1) & 1) {
-            vpos += used;
-            used = 0;
-            win = vlc_fetch(vl, vpos, vlimit);
-            const int uo0 = q0 & 1, uo1 = q1 & 1;
-            if (uo0 & uo1) {
-                if (FIRST) {                             /* :671-704 */
-                    if (mel_symbol(mel)) {
-                        const int p0 = uvlc_prefix(win, used), p1 = uvlc_prefix(win, used);
-                        const int s0 = uvlc_suffix(win, used, p0), s1 = uvlc_suffix(win, used, p1);
-                        const int e0 = uvlc_ext(win, used, s0), e1 = uvlc_ext(win, used, s1);
-                        u0 = 2 + p0 + s0 + 4 * e0;
-                        u1 = 2 + p1 + s1 + 4 * e1;
+    const VlcWin vw = vlc_fetch(vl, vpos, vlimit);
+    uint32_t win = vw.lo;
+    int used;
+    unsigned q0, q1 = 0;
+    {
+        const int ctx = FIRST ? carry : (int)((mA & 1) | (carry << 1) | ((mC & 1) << 2));
+        bool coded = ctx != 0;
+        if (!coded)
+            coded = mel_symbol(mel) != 0;
+        unsigned e = table[(win & 0x7F) | ((unsigned)ctx << 7)];
+        e = coded ? e : 0;
+        used = e & 7;
+        win >>= used;
+        q0 = e >> 3;
+        carry = FIRST ? (int)(((q0 & 6) ? 1 : 0) | ((q0 >> 2) & 6)) : (int)((q0 & 0x18) != 0);
+    }
+    if (PAIR) {
+        const int ctx = FIRST ? carry : (int)(((mA >> 1) & 1) | (carry << 1) | (((mC >> 1) & 1) << 2));
+        bool coded = ctx != 0;
+        if (!coded)
+            coded = mel_symbol(mel) != 0;
+        unsigned e = table[(win & 0x7F) | ((unsigned)ctx << 7)];
+        e = coded ? e : 0;
+        const int l = e & 7;
+        used += l;
+        q1 = e >> 3;
+        carry = FIRST ? (int)(((q1 & 6) ? 1 : 0) | ((q1 >> 2) & 6)) : (int)((q1 & 0x18) != 0);
+    }
+    int u0 = 0, u1 = 0;
+    const int mode = (int)((q0 & 1) | ((q1 & 1) << 1));
+    if (mode) {
+        uint32_t uw = __funnelshift_r(vw.lo, vw.hi, used);      /* used <= 14 */
+        if (FIRST) {
+            const int uo0 = mode & 1, uo1 = mode >> 1;
+            if (uo0 & uo1) {                             /* :671-704 */
+                if (mel_symbol(mel)) {
+                    const int p0 = uvlc_prefix(uw, used), p1 = uvlc_prefix(uw, used);
+                    const int s0 = uvlc_suffix(uw, used, p0), s1 = uvlc_suffix(uw, used, p1);
+                    const int e0 = uvlc_ext(uw, used, s0), e1 = uvlc_ext(uw, used, s1);
+                    u0 = 2 + p0 + s0 + 4 * e0;
+                    u1 = 2 + p1 + s1 + 4 * e1;
+                } else {
+                    const int p0 = uvlc_prefix(uw, used);
+                    if (p0 > 2) {
+                        u1 = (int)(uw & 1) + 1;
+                        uw >>= 1;
+                        used += 1;
+                        const int s0 = uvlc_suffix(uw, used, p0);
+                        u0 = p0 + s0 + 4 * uvlc_ext(uw, used, s0);
                     } else {
-                        const int p0 = uvlc_prefix(win, used);
-                        if (p0 > 2) {
-                            u1 = (int)(win & 1) + 1;
-                            win >>= 1;
-                            used += 1;
-                            const int s0 = uvlc_suffix(win, used, p0);
-                            u0 = p0 + s0 + 4 * uvlc_ext(win, used, s0);
-                        } else {
-                            const int p1 = uvlc_prefix(win, used);
-                            const int s0 = uvlc_suffix(win, used, p0), s1 = uvlc_suffix(win, used, p1);
-                            const int e0 = uvlc_ext(win, used, s0), e1 = uvlc_ext(win, used, s1);
-                            u0 = p0 + s0 + 4 * e0;
-                            u1 = p1 + s1 + 4 * e1;
-                        }
+                        const int p1 = uvlc_prefix(uw, used);
+                        const int s0 = uvlc_suffix(uw, used, p0), s1 = uvlc_suffix(uw, used, p1);
+                        const int e0 = uvlc_ext(uw, used, s0), e1 = uvlc_ext(uw, used, s1);
+                        u0 = p0 + s0 + 4 * e0;
+                        u1 = p1 + s1 + 4 * e1;
                     }
-                } else {                                 /* :833-845 */
-                    const int p0 = uvlc_prefix(win, used), p1 = uvlc_prefix(win, used);
-                    const int s0 = uvlc_suffix(win, used, p0), s1 = uvlc_suffix(win, used, p1);
-                    const int e0 = uvlc_ext(win, used, s0), e1 = uvlc_ext(win, used, s1);
-                    u0 = p0 + s0 + 4 * e0;
-                    u1 = p1 + s1 + 4 * e1;
                 }
             } else if (uo0) {
-                u0 = uvlc_whole(win, used);
+                u0 = uvlc_whole(uw, used);
             } else {
-                u1 = uvlc_whole(win, used);
+                u1 = uvlc_whole(uw, used);
+            }
+        } else {                                         /* :833-854, table driven */
+            const unsigned t = uvtab[(mode << 6) | (uw & 63)];
+            const int plen = t & 7, sl0 = (t >> 9) & 7, sl1 = (t >> 12) & 7;
+            uint32_t sw = uw >> plen;
+            const int s0 = sw & ((1u << sl0) - 1);
+            sw >>= sl0;
+            const int s1 = sw & ((1u << sl1) - 1);
+            used += plen + sl0 + sl1;
+            u0 = ((t >> 3) & 7) + s0;
+            u1 = ((t >> 6) & 7) + s1;
+            if ((s0 | s1) >= 28) {                       /* rare: 4-bit extensions, quad 0 first */
+                sw >>= sl1;
+                if (s0 >= 28) {
+                    u0 += 4 * (int)(sw & 15);
+                    sw >>= 4;
+                    used += 4;
+                }
+                if (s1 >= 28) {
+                    u1 += 4 * (int)(sw & 15);
+                    used += 4;
+                }
             }
         }
-        vpos += used;
-        if (lane == j)
-            mine = q0 | ((unsigned)u0 << 16);
-        if (lane == j + 1)
-            mine = q1 | ((unsigned)u1 << 16);
     }
-    return mine;
+    vpos += used;
+    qout[0] = q0 | ((unsigned)u0 << 16);
+    if (PAIR)
+        qout[1] = q1 | ((unsigned)u1 << 16);
+}
+
+template <bool FIRST>
+__device__ __forceinline__ void decode_segment(Mel &mel, const uint32_t *vl, uint32_t &vpos, uint32_t vlimit,
+                                               const uint16_t *table, const uint16_t *uvtab, int nq, unsigned mA,
+                                               unsigned mC, int &carry, uint32_t *qinfo)
+{
+    const int npairs = nq >> 1;
+    for (int j = 0; j < npairs; j++) {
+        decode_pair<FIRST, true>(mel, vl, vpos, vlimit, table, uvtab, mA, mC, carry, qinfo + 2 * j);
+        mA >>= 2;
+        mC >>= 2;
+    }
+    if (nq & 1)
+        decode_pair<FIRST, false>(mel, vl, vpos, vlimit, table, uvtab, mA, mC, carry, qinfo + 2 * npairs);
 }
 
 /* read nb (1..31) bits at bit position pos of the un-stuffed MagSgn array */
@@ -306,6 +357,7 @@ __device__ __forceinline__ int sp_bit(SpBits &s)
  *   ms   [ms_words]          un-stuffed MagSgn bits (+2 words of ones)
  *   vl   [vl_words]          un-stuffed VLC bits, forward order (+2 words of zeros)
  *   row  [2][maxQW + 2]      per-quad (rho | E1<<8 | E3<<16) of the previous / current quad row
+ *   qinfo[32]                the serial decoder's per-quad results of the current segment
  *   REFINE only:
  *   samp [maxw * maxh]       sign-magnitude samples
  *   st   [(maxh+3)*(maxw+3)] bytes, sample states with a one-sample apron
@@ -324,14 +376,17 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
         tab[i] = CXTVLC_FIRST_ROW[i];
         tab[1024 + i] = CXTVLC_OTHER_ROWS[i];
     }
+    uint16_t *uvtab = tab + 2048;
+    for (int i = threadIdx.x; i < 256; i += blockDim.x)
+        uvtab[i] = uvlc_pair_entry(i);
     __syncthreads();
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int row_words = 2 * (maxQW + 2);
+    const int row_words = 2 * (maxQW + 2) + 32;
     int per_warp = stream_words + row_words;
     if (REFINE)
         per_warp += samp_words + st_words;
-    uint32_t *wbase = smem + 1024 + (size_t)warp * per_warp;
+    uint32_t *wbase = smem + TABLE_WORDS + (size_t)warp * per_warp;
     uint32_t *streams = wbase;
     uint32_t *rowbuf = wbase + stream_words;
     uint32_t *samp = rowbuf + row_words;
@@ -377,7 +432,7 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
                 result = B200J2K_KERR_INVALID;
             else if (maxbp >= 32 || pLSB < 1)
                 result = B200J2K_KERR_INVALID;
-            else if (4 * stream_words < Lcup + 24)
+            else if (stream_words < (Lcup - Scup + 3) / 4 + (Scup + 3) / 4 + 6)
                 result = B200J2K_KERR_INVALID;          /* launch sized too small: host bug guard */
         }
         Pcup = Lcup - Scup;
@@ -395,7 +450,7 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
 
     /* ---- stage the streams ---- */
     const int ms_words = (Pcup + 3) / 4 + 2;
-    const int vl_words = (Scup + 3) / 4 + 3;
+    const int vl_words = (Scup + 3) / 4 + 4;
     uint32_t *ms = streams;
     uint32_t *vl = streams + ms_words;
     for (int i = lane; i < ms_words + vl_words; i += 32)
@@ -510,7 +565,8 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
 
     Mel mel = { Dcup + Pcup, Scup, 0, 0, 0, 0, 0, 0 };
     uint32_t vpos = 4;                                   /* the Scup nibble is skipped (:283-295) */
-    const uint32_t vlimit = (uint32_t)(vl_words - 2) * 32;
+    const uint32_t vlimit = (uint32_t)(vl_words - 3) * 32;
+    uint32_t *qinfo = rowbuf + 2 * (maxQW + 2);
     uint32_t ms_pos = 0;
     bool bad = false;
     const int SW = w + 3;                                /* state row stride (REFINE) */
@@ -520,17 +576,19 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
         for (int qb = 0; qb < QW; qb += 32) {
             const int nq = min(32, QW - qb);
             const int qx = qb + lane;
-            unsigned mine;                               /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16 */
             if (qy == 0) {
-                mine = decode_segment<true>(mel, vl, vpos, vlimit, tab, nq, lane, 0, 0, carry);
+                decode_segment<true>(mel, vl, vpos, vlimit, tab, uvtab, nq, 0, 0, carry, qinfo);
             } else {
                 /* row[] is stored with a +1 offset and zero sentinels at both ends */
                 const unsigned n = qx < QW ? rowprev[qx + 1] : 0, nw = qx < QW ? rowprev[qx] : 0,
                                ne = qx < QW ? rowprev[qx + 2] : 0;
                 const unsigned mA = __ballot_sync(FULL, ((n >> 1) | (nw >> 3)) & 1);   /* sigma_N[1] | sigma_NW[3] */
                 const unsigned mC = __ballot_sync(FULL, ((n >> 3) | (ne >> 1)) & 1);   /* sigma_N[3] | sigma_NE[1] */
-                mine = decode_segment<false>(mel, vl, vpos, vlimit, tab + 1024, nq, lane, mA, mC, carry);
+                decode_segment<false>(mel, vl, vpos, vlimit, tab + 1024, uvtab, nq, mA, mC, carry, qinfo);
             }
+            __syncwarp();
+            const unsigned mine = lane < nq ? qinfo[lane] : 0;   /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16 */
+            __syncwarp();
             /* ---- parallel: lane = quad.  exponent predictor, MagSgn, write-back ---- */
             const bool act = lane < nq;
             const unsigned rho = act ? (mine >> 1) & 15 : 0;
@@ -721,10 +779,10 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
 /* ---- host-side launcher ------------------------------------------------------------------------------ */
 size_t ht_smem_bytes(bool refine, int stream_words, int maxQW, int samp_words, int st_words)
 {
-    size_t per_warp = (size_t)stream_words + 2 * (size_t)(maxQW + 2);
+    size_t per_warp = (size_t)stream_words + 2 * (size_t)(maxQW + 2) + 32;
     if (refine)
         per_warp += (size_t)samp_words + st_words;
-    return 4096 + per_warp * 4 * WARPS_PER_CTA;
+    return (size_t)TABLE_WORDS * 4 + per_warp * 4 * WARPS_PER_CTA;
 }
 
 int launch_ht_decode(cudaStream_t stream, bool refine, const CblkDesc *descs, const uint32_t *order, int nblocks,
@@ -733,7 +791,7 @@ int launch_ht_decode(cudaStream_t stream, bool refine, const CblkDesc *descs, co
 {
     if (nblocks <= 0)
         return 0;
-    const int stream_words = (max_Lcup + 3) / 4 + 8;
+    const int stream_words = (max_Lcup + 3) / 4 + 10;
     const int maxQW = (maxw + 1) / 2;
     const int samp_words = max_area, st_words = (max_state + 3) / 4;
     const size_t smem = ht_smem_bytes(refine, stream_words, maxQW, samp_words, st_words);
