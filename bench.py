@@ -115,36 +115,35 @@ def run_reference(args):
 
 # ---- clocks -----------------------------------------------------------------------------------------
 class ClockSampler:
+    """Samples SM clock and throttle reasons with repeated one-shot nvidia-smi queries while the timed
+    region runs (nvidia-smi -lms buffers its output when piped, so it is polled instead)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.proc = None
         self.lines = []
+        self._stop = threading.Event()
+        self.t = None
+
+    def _poll(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                self.lines.extend(x.strip() for x in out.stdout.splitlines() if x.strip())
+            except Exception:
+                return
+            self._stop.wait(0.05)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
+        self._stop.set()
+        if self.t:
+            self.t.join(timeout=6)
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:

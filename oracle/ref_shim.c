@@ -7,7 +7,7 @@
  * (ff_thread_get_buffer, ff_set_dimensions, av_codec_is_encoder) and exposes plain-C entry
  * points that tests/ and bench.py's reference arm load with ctypes:
  *
- *   ref_decode()        whole codestream -> pixels, through ff_jpeg2000_decoder.cb.decode
+ *   ref_decode()        whole codestream -> pixels, through REF_CODEC.cb.decode
  *                       (libavcodec/jpeg2000dec.c:2825-2908, FFCodec at :2926-2939)
  *   ref_ht_block()      one HT code-block -> int32 sign-magnitude coefficients, through
  *                       ff_jpeg2000_decode_htj2k (libavcodec/jpeg2000htdec.c:1188-1336)
@@ -38,7 +38,17 @@
 #include "libavcodec/jpeg2000htdec.h"
 #include "libavcodec/thread.h"
 
-extern const FFCodec ff_jpeg2000_decoder;
+/* The same harness is compiled a second time around the product's FFCodec shim
+ * (ffmpeg-ht_b200/ffcodec/jpeg2000_b200.c, -DREF_CODEC=ff_jpeg2000_b200_decoder -DREF_PREFIX_B200) so that
+ * tests can drive the B200 path through the very FFCodec callbacks libavcodec would call. */
+#ifndef REF_CODEC
+#define REF_CODEC ff_jpeg2000_decoder
+#define REF_NAME(x) ref_##x
+#define REF_STAGE_API 1
+#else
+#define REF_NAME(x) b200shim_##x
+#endif
+extern const FFCodec REF_CODEC;
 
 /* ---- the three generic-layer functions the decoder calls ------------------------------ */
 
@@ -92,20 +102,20 @@ static AVCodecContext *ctx_open(int bitexact)
     AVCodecContext *avctx = av_mallocz(sizeof(*avctx));
     if (!avctx)
         return NULL;
-    avctx->codec      = &ff_jpeg2000_decoder.p;
+    avctx->codec      = &REF_CODEC.p;
     avctx->codec_id   = AV_CODEC_ID_JPEG2000;
     avctx->codec_type = AVMEDIA_TYPE_VIDEO;
     avctx->pix_fmt    = AV_PIX_FMT_NONE;
     avctx->max_pixels = INT32_MAX;
     avctx->execute2   = serial_execute2;
     avctx->flags      = bitexact ? AV_CODEC_FLAG_BITEXACT : 0;
-    avctx->priv_data  = av_mallocz(ff_jpeg2000_decoder.priv_data_size);
+    avctx->priv_data  = av_mallocz(REF_CODEC.priv_data_size);
     if (!avctx->priv_data) {
         av_free(avctx);
         return NULL;
     }
-    *(const AVClass **)avctx->priv_data = ff_jpeg2000_decoder.p.priv_class;
-    if (ff_jpeg2000_decoder.init(avctx) < 0) {
+    *(const AVClass **)avctx->priv_data = REF_CODEC.p.priv_class;
+    if (REF_CODEC.init(avctx) < 0) {
         av_free(avctx->priv_data);
         av_free(avctx);
         return NULL;
@@ -117,6 +127,8 @@ static void ctx_close(AVCodecContext *avctx)
 {
     if (!avctx)
         return;
+    if (REF_CODEC.close)
+        REF_CODEC.close(avctx);
     av_free(avctx->priv_data);
     av_free(avctx);
 }
@@ -154,7 +166,7 @@ static int64_t pack_frame(const AVCodecContext *avctx, const AVFrame *f, uint8_t
  * info[0]=width info[1]=height info[2]=AVPixelFormat info[3]=bytes written info[4]=decode return
  * returns 0 on success, the negative AVERROR otherwise.
  */
-int ref_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint8_t *out, int64_t cap)
+int REF_NAME(decode)(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint8_t *out, int64_t cap)
 {
     AVCodecContext *avctx = ctx_open(bitexact);
     if (!avctx)
@@ -167,7 +179,7 @@ int ref_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint
     pkt.size = (int)len;
     AVFrame *frame = av_mallocz(sizeof(AVFrame));
     int got = 0;
-    int ret = ff_jpeg2000_decoder.cb.decode(avctx, frame, &got, &pkt);
+    int ret = REF_CODEC.cb.decode(avctx, frame, &got, &pkt);
     info[4] = ret;
     if (ret >= 0 && got) {
         info[0] = frame->width;
@@ -186,8 +198,9 @@ int ref_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint
     return ret;
 }
 
-const char *ref_pix_fmt_name(int fmt) { return av_get_pix_fmt_name(fmt); }
+const char *REF_NAME(pix_fmt_name)(int fmt) { return av_get_pix_fmt_name(fmt); }
 
+#ifdef REF_STAGE_API
 /* ---- stage-level entry points ---------------------------------------------------------- */
 
 /*
@@ -249,6 +262,8 @@ int ref_mct(int type, void *p0, void *p1, void *p2, int n)
     return 0;
 }
 
+#endif /* REF_STAGE_API */
+
 /* ---- CPU baseline ---------------------------------------------------------------------- */
 
 typedef struct BenchJob {
@@ -273,7 +288,7 @@ static void *bench_worker(void *arg)
             AVFrame *frame = av_mallocz(sizeof(AVFrame));
             int got = 0;
             avctx->pix_fmt = AV_PIX_FMT_NONE;
-            if (ff_jpeg2000_decoder.cb.decode(avctx, frame, &got, &pkt) < 0 || !got)
+            if (REF_CODEC.cb.decode(avctx, frame, &got, &pkt) < 0 || !got)
                 j->errors++;
             if (frame->data[0])
                 av_freep(&frame->data[0]);
@@ -286,7 +301,7 @@ static void *bench_worker(void *arg)
 }
 
 /* decodes every codestream `reps` times using `threads` decoder contexts; returns seconds (<0 on error) */
-double ref_decode_bench(const uint8_t *const *cs, const int64_t *len, int nframes, int threads,
+double REF_NAME(decode_bench)(const uint8_t *const *cs, const int64_t *len, int nframes, int threads,
                         int reps, int bitexact)
 {
     if (threads < 1)

@@ -1,0 +1,53 @@
+"""The drop-in boundary itself, on the GPU box: the product's FFCodec shim
+(ffmpeg-ht_b200/ffcodec/jpeg2000_b200.c), compiled against the reference's own headers and driven by the
+same harness that drives the reference's ff_jpeg2000_decoder (oracle/ref_shim.c), must give the same
+AVFrame bytes, dimensions and pixel format as the reference decoder."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import j2kgen
+from helpers import ORACLE_DIR, have_ref, ref_decode
+
+SHIM = ORACLE_DIR / "_ref" / "libj2kb200shim.so"
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(not (have_ref() and SHIM.exists()), reason="oracle/_ref not built (needs /root/reference)")]
+
+
+def shim_decode(cs: bytes, bitexact=0):
+    lib = ctypes.CDLL(str(SHIM))
+    lib.b200shim_decode.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                                    ctypes.c_void_p, ctypes.c_int64]
+    info = (ctypes.c_int64 * 8)()
+    out = np.zeros(1 << 26, np.uint8)
+    ret = lib.b200shim_decode(cs, len(cs), bitexact, info, out.ctypes.data, out.size)
+    return ret, list(info), out[: max(info[3], 0)].copy()
+
+
+@pytest.mark.parametrize("kw", [dict(nc=3, bd=12, levels=4, tile=(128, 96)),
+                                dict(nc=1, bd=16, levels=5),
+                                dict(nc=3, bd=10, levels=5, reversible=False, base_step=2.0),
+                                dict(nc=3, bd=8, levels=3, cblk=(32, 32), npasses=3, prog=2, precincts=[(6, 6), (7, 7)]),
+                                dict(nc=4, bd=12, levels=2, cblk=(16, 16))])
+def test_ffcodec_shim_equals_reference(kw):
+    kw = dict(kw)
+    nc, bd = kw.pop("nc"), kw.pop("bd")
+    planes = j2kgen.synth_image(300, 200, nc, bd, seed=9)
+    p = j2kgen.EncParams(**kw)
+    cs = j2kgen.encode(planes, bd, p)
+    for bitexact in ((0,) if p.reversible else (0, 1)):
+        r1, i1, o1, _ = ref_decode(cs, bitexact)
+        r2, i2, o2 = shim_decode(cs, bitexact)
+        assert r1 == 0 and r2 == 0
+        assert i1[:3] == i2[:3]            # width, height, AVPixelFormat
+        assert i1[4] == i2[4]              # bytes consumed (decode() return value)
+        assert np.array_equal(o1, o2)
+
+
+def test_ffcodec_shim_error_codes():
+    planes = j2kgen.synth_image(64, 64, 1, 8, seed=2)
+    cs = j2kgen.encode(planes, 8, j2kgen.EncParams(levels=2))
+    r1, *_ = ref_decode(cs[:40])
+    r2, *_ = shim_decode(cs[:40])
+    assert r1 < 0 and r2 < 0

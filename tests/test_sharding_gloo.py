@@ -1,0 +1,79 @@
+"""N>1 host logic on the CPU: two gloo ranks shard a small sequence round-robin, each runs the host side of
+the path (codestream -> plan) on its shard, and the reduced bookkeeping must cover every frame exactly once
+with the max-over-ranks time.  No GPU, no data-path collective."""
+import os
+import socket
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nframes, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tools"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import torch.distributed as dist
+    import ffmpeg_ht_b200 as fb
+    from ffmpeg_ht_b200 import sharding
+    import j2kgen
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    mine = sharding.shard_indices(nframes, rank, world)
+    blocks = 0
+    for i in mine:
+        planes = j2kgen.synth_image(96, 64, 3, 12, seed=100 + i)
+        cs = j2kgen.encode(planes, 12, j2kgen.EncParams(levels=3, cblk=(32, 32)))
+        plan = fb.plan(cs)
+        blocks += len(plan["cblk"])
+        assert plan["info"].width == 96
+    dist.barrier()
+    elapsed, total = sharding.reduce_stats(0.5 + rank, len(mine), dist)
+    q.put((rank, mine, elapsed, total, blocks))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_a_sequence():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    nframes, world = 7, 2
+    procs = [ctx.Process(target=_worker, args=(r, world, port, nframes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    seen = sorted(i for _, mine, *_ in res for i in mine)
+    assert seen == list(range(nframes))                      # every frame exactly once
+    for rank, mine, elapsed, total, blocks in res:
+        assert elapsed == pytest.approx(0.5 + (world - 1))   # max over ranks
+        assert total == nframes                              # sum over ranks
+        assert blocks > 0
+
+
+def test_shard_indices_properties():
+    sys.path.insert(0, str(ROOT))
+    from ffmpeg_ht_b200 import sharding
+    for world in (1, 2, 4, 8):
+        for n in (0, 1, 4, 7, 960):
+            allu = sorted(i for r in range(world) for i in sharding.shard_indices(n, r, world))
+            assert allu == list(range(n))
+            sizes = [len(sharding.shard_indices(n, r, world)) for r in range(world)]
+            assert max(sizes) - min(sizes) <= 1
+            for u in range(min(n, 16)):
+                assert u in sharding.shard_indices(n, sharding.owner(u, world), world)
+    with pytest.raises(ValueError):
+        sharding.shard_indices(4, 2, 2)
