@@ -220,8 +220,8 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 return B200J2K_ERR_INVALIDDATA;
             auto &pv = parts_[cur_tile];
             if ((int)pv.size() <= cur_tp)
-                pv.resize(cur_tp + 1, TilePart{ nullptr, nullptr });
-            pv[cur_tp] = TilePart{ p, tp_end };
+                pv.resize(cur_tp + 1, TilePart{ nullptr, nullptr, nullptr });
+            pv[cur_tp] = TilePart{ p, tp_end, p };
             p = tp_end;
             continue;
         }
@@ -750,6 +750,7 @@ void Parser::select_part(int tileno, int *tp, int csty)
         bp_ = pv[*tp].p;
         bend_ = pv[*tp].end;
     }
+    cur_part_start_ = pv[*tp].start;
     if (!bp_)
         bp_ = bend_ = pkt_ + pkt_size_;
     if (csty & 2)
@@ -1110,9 +1111,16 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
     tags_.assign(tag_total_, TagNodeState{ 0, 0 });
     decoded_layers_.assign(precs_.size(), 0);
     extra.clear();
+    cur_part_start_ = nullptr;
     for (int tileno = 0; tileno < hdr.ntx * hdr.nty; tileno++)
         if ((ret = decode_packets(tileno)) < 0)
             return ret;
+    /* the reference returns bytestream2_tell() of the LAST tile-part sub-stream it read, after skipping
+     * the 2 EOC bytes if they are inside that sub-stream (jpeg2000dec.c:1865-1866, :2903) */
+    if (cur_part_start_ && bp_ && bp_ >= cur_part_start_) {
+        int64_t left = bend_ - bp_;
+        consumed = (int64_t)(bp_ - cur_part_start_) + (left < 2 ? (left < 0 ? 0 : left) : 2);
+    }
     /* emit the descriptor table */
     cblk = cblk_template_;
     max_Lcup = max_Lref = 0;

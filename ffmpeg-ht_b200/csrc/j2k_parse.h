@@ -85,7 +85,7 @@ struct Header {
     int lossless = 0;
 };
 
-struct TilePart { const uint8_t *p, *end; };
+struct TilePart { const uint8_t *p, *end, *start; };
 
 class Parser {
 public:
@@ -137,6 +137,7 @@ private:
     int parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *main_header_len);
     int build_geometry(int flags);
     int decode_packets(int tileno);
+    const uint8_t *cur_part_start_ = nullptr;
     int decode_packet(int tileno, int comp, int r, int precno, int layno, int *tp);
     int precinct_at(int tileno, int c, int r, int x, int y, bool cprl_rule) const;
     void select_part(int tileno, int *tp, int csty);

@@ -164,3 +164,17 @@ def test_no_device_fails_loudly():
     assert e.value.code == fb.ERR_DEVICE
     with pytest.raises(fb.DecodeError):
         fb.idwt(1, [0, 8, 0, 8], 1, np.zeros(64, np.int32))
+
+
+def test_bytes_consumed_matches_reference():
+    """decode()'s return value: the reference returns bytestream2_tell() of the last tile-part sub-stream."""
+    from helpers import have_ref, ref_decode
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    for cfg in STREAMS:
+        cfg = dict(cfg)
+        w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+        cs = j2kgen.encode(j2kgen.synth_image(w, h, nc, bd, seed=11), bd, j2kgen.EncParams(**cfg))
+        r, info, _, _ = ref_decode(cs, 0)
+        assert r == 0
+        assert fb.plan(cs, 0)["info"].bytes_consumed == info[4]
