@@ -32,6 +32,8 @@ namespace b200j2k {
 namespace {
 
 constexpr int THREADS = 256;
+constexpr int NWARPS = THREADS / 32;
+constexpr unsigned FULLMASK = 0xFFFFFFFFu;
 
 __device__ __forceinline__ int reflect(int i, int i0, int i1)
 {
@@ -114,103 +116,118 @@ template <> struct Lift<J2K_DWT97_INT> {
     }
 };
 
+/* Tile geometry.  A warp reconstructs 32 sample pairs (even position, odd position) of a row at a time with
+ * shuffles; HP pairs at each end of the warp are apron, so a warp iteration yields VP = 32 - 2*HP valid
+ * pairs and a tile row is two iterations wide. */
+template <int TYPE> struct Geo {
+    static constexpr int HALO = Lift<TYPE>::HALO;
+    static constexpr int HP = HALO / 2;
+    static constexpr int VP = 32 - 2 * HP;
+    static constexpr int ITERS = 2;
+    static constexpr int TX = 2 * VP * ITERS;       /* 120 samples for 5/3, 112 for 9/7 */
+};
+
 /*
- * Load one interleaved tile (with apron) of resolution `lev_out` of tile-component tc into shared memory,
- * run the lifting steps, leave the result in tile[] (valid region = the TX x TY centre).
- * tile is SH x SWD words, SWD = TX + 2*HALO (+1 pad), SH = TY + 2*HALO.
+ * HOR_SD for SH rows of a tile, result into tile[SH][TX] (shared memory).
+ * XA: even absolute X of tile column 0; YS: even absolute Y of tile row 0 (apron included).
+ * Lane = one (low, high) coefficient pair of the row: the low-pass sample sits at the even absolute
+ * position 2i, the high-pass one at 2i+1; the lifting steps exchange neighbours with shuffles
+ * (jpeg2000dwt.c:309-325, :376-401, :453-481).  Rows and columns outside the resolution are fetched by
+ * index reflection, which reproduces the reference's symmetric extension.
  */
-template <int TYPE, int TX, int TY>
-__device__ void reconstruct_tile(uint32_t *tile, const TileCompDesc &tc, int j, const uint32_t *coefA,
-                                 const uint32_t *coefIn, int XT, int YT)
+template <int TYPE, int SH>
+__device__ __forceinline__ void hpass(uint32_t *tile, const TileCompDesc &tc, int j, const uint32_t *coefA,
+                                      const uint32_t *coefIn, int XA, int YS)
 {
     using L = Lift<TYPE>;
-    constexpr int HALO = L::HALO;
-    constexpr int SWD = TX + 2 * HALO + 1, SH = TY + 2 * HALO, SWV = TX + 2 * HALO;
+    using G = Geo<TYPE>;
     const LevelDesc o = tc.lev[j + 1];
     const int u0 = o.u0, u1 = o.u1, v0 = o.v0, v1 = o.v1;
-    const int lh = u1 - u0, lv = v1 - v0;
+    const int lh = u1 - u0;
     const int nLh = ((u1 + 1) >> 1) - ((u0 + 1) >> 1), nLv = ((v1 + 1) >> 1) - ((v0 + 1) >> 1);
     const int W = tc.width;
     const uint32_t *A = coefA + tc.coef_off;
     /* LL comes from the plane itself at the coarsest level, else from the compact ping-pong buffer */
     const uint32_t *LLp = j == 0 ? A : coefIn + tc.coef_off;
     const int LLstride = j == 0 ? W : nLh;
-    const int XS = XT - HALO, YS = YT - HALO;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int eoff = (u0 + 1) >> 1, ooff = u0 >> 1;
 
-    /* ---- gather: band-major order inside a row so that global reads are contiguous ---- */
-    const int nE = (SWV + ((XS & 1) ? 0 : 1)) >> 1;          /* even positions in [XS, XS+SWV) */
-    const int XE0 = XS + (XS & 1), XO0 = XS + 1 - (XS & 1);
-    for (int idx = threadIdx.x; idx < SH * SWV; idx += THREADS) {
-        const int r = idx / SWV, cc = idx - r * SWV;
-        const int X = cc < nE ? XE0 + 2 * cc : XO0 + 2 * (cc - nE);
+    for (int r = warp; r < SH; r += NWARPS) {
         const int Y = YS + r;
-        const int Xr = reflect(X, u0, u1), Yr = reflect(Y, v0, v1);
-        const int kx = band_index(Xr, u0), ky = band_index(Yr, v0);
-        uint32_t v;
-        if (!((Xr | Yr) & 1))
-            v = LLp[(size_t)ky * LLstride + kx];
-        else
-            v = A[(size_t)(ky + ((Yr & 1) ? nLv : 0)) * W + kx + ((Xr & 1) ? nLh : 0)];
-        tile[r * SWD + (X - XS)] = v;
-    }
-    __syncthreads();
-
-    /* ---- HOR_SD: row lifting ---- */
-    if (lh > 1) {
+        const int Yr = (Y >= v0 && Y < v1) ? Y : reflect(Y, v0, v1);
+        const int ky = band_index(Yr, v0);
+        const uint32_t *rowL = (Yr & 1) ? A + (size_t)(nLv + ky) * W : LLp + (size_t)ky * LLstride;
+        const uint32_t *rowH = ((Yr & 1) ? A + (size_t)(nLv + ky) * W : A + (size_t)ky * W) + nLh;
+        uint32_t *trow = tile + r * G::TX;
 #pragma unroll
-        for (int s = 0; s < L::STEPS; s++) {
-            /* step s is valid on [XS + s + 1, XS + SWV - s - 1), positions of parity (s & 1) */
-            const int lo = XS + s + 1, hi = XS + SWV - s - 1;
-            const int first = lo + (((lo & 1) != (s & 1)) ? 1 : 0);
-            const int cnt = hi > first ? (hi - first + 1) >> 1 : 0;
-            for (int idx = threadIdx.x; idx < SH * cnt; idx += THREADS) {
-                const int r = idx / cnt, k = idx - r * cnt;
-                uint32_t *p = tile + r * SWD + (first + 2 * k - XS);
-                p[0] = L::apply(s, p[0], p[-1], p[1]);
+        for (int it = 0; it < G::ITERS; it++) {
+            const int pair = (XA >> 1) + it * G::VP - G::HP + lane;
+            int Xe = 2 * pair, Xo = Xe + 1;
+            uint32_t xe, xo;
+            if (lh > 1) {
+                if (Xe < u0 || Xe >= u1) Xe = reflect(Xe, u0, u1);
+                if (Xo < u0 || Xo >= u1) Xo = reflect(Xo, u0, u1);
+                const uint32_t Lc = rowL[(Xe >> 1) - eoff];
+                const uint32_t Hc = rowH[(Xo >> 1) - ooff];
+                if (TYPE == J2K_DWT53) {
+                    const uint32_t Hl = __shfl_up_sync(FULLMASK, Hc, 1);
+                    xe = L::apply(0, Lc, Hl, Hc);
+                    const uint32_t er = __shfl_down_sync(FULLMASK, xe, 1);
+                    xo = L::apply(1, Hc, xe, er);
+                } else {
+                    const uint32_t Hl = __shfl_up_sync(FULLMASK, Hc, 1);
+                    const uint32_t e1 = L::apply(0, Lc, Hl, Hc);
+                    const uint32_t e1r = __shfl_down_sync(FULLMASK, e1, 1);
+                    const uint32_t o1 = L::apply(1, Hc, e1, e1r);
+                    const uint32_t o1l = __shfl_up_sync(FULLMASK, o1, 1);
+                    xe = L::apply(2, e1, o1l, o1);
+                    const uint32_t er = __shfl_down_sync(FULLMASK, xe, 1);
+                    xo = L::apply(3, o1, xe, er);
+                }
+            } else {
+                /* one-sample line (jpeg2000dwt.c:313-317, :380-386, :457-463) */
+                const uint32_t c = (u0 & 1) ? rowH[0] : rowL[0];
+                xe = xo = L::single(c, u0 & 1);
             }
-            __syncthreads();
+            if (lane >= G::HP && lane < 32 - G::HP)
+                *reinterpret_cast<uint2 *>(trow + 2 * (it * G::VP + lane - G::HP)) = make_uint2(xe, xo);
         }
-    } else {
-        const int odd = u0 & 1;
-        for (int idx = threadIdx.x; idx < SH * SWV; idx += THREADS) {
-            const int r = idx / SWV, cc = idx - r * SWV;
-            tile[r * SWD + cc] = L::single(tile[r * SWD + cc], odd);
-        }
-        __syncthreads();
     }
-    /* ---- VER_SD: column lifting (only the TX centre columns are needed) ---- */
+}
+
+/* VER_SD in registers: v[0..R) is one column, v[k] at absolute row (even base + k); the centre
+ * v[HALO .. R-HALO) is valid afterwards. */
+template <int TYPE, int R>
+__device__ __forceinline__ void vlift(uint32_t (&v)[R], int lv, int v0)
+{
+    using L = Lift<TYPE>;
     if (lv > 1) {
 #pragma unroll
         for (int s = 0; s < L::STEPS; s++) {
-            const int lo = YS + s + 1, hi = YS + SH - s - 1;
-            const int first = lo + (((lo & 1) != (s & 1)) ? 1 : 0);
-            const int cnt = hi > first ? (hi - first + 1) >> 1 : 0;
-            for (int idx = threadIdx.x; idx < cnt * TX; idx += THREADS) {
-                const int k = idx / TX, cx = idx - k * TX;
-                uint32_t *p = tile + (first + 2 * k - YS) * SWD + HALO + cx;
-                p[0] = L::apply(s, p[0], p[-SWD], p[SWD]);
-            }
-            __syncthreads();
+#pragma unroll
+            for (int k = s + 1; k < R - s - 1; k++)
+                if ((k & 1) == (s & 1))
+                    v[k] = L::apply(s, v[k], v[k - 1], v[k + 1]);
         }
     } else {
-        const int odd = v0 & 1;
-        for (int idx = threadIdx.x; idx < SH * TX; idx += THREADS) {
-            const int r = idx / TX, cx = idx - r * TX;
-            tile[r * SWD + HALO + cx] = L::single(tile[r * SWD + HALO + cx], odd);
-        }
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < R; k++)
+            v[k] = L::single(v[k], v0 & 1);
     }
 }
 
 /* ---- intermediate level: write the reconstructed resolution to the compact ping-pong buffer ---------- */
-template <int TYPE, int TX, int TY>
+template <int TYPE, int TY>
 __global__ void __launch_bounds__(THREADS)
 idwt_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint32_t *__restrict__ coefA,
                   const uint32_t *__restrict__ coefIn, uint32_t *__restrict__ coefOut, int to_plane)
 {
-    using L = Lift<TYPE>;
-    constexpr int HALO = L::HALO, SWD = TX + 2 * HALO + 1, SH = TY + 2 * HALO;
-    __shared__ uint32_t tile[SH * SWD];
+    using G = Geo<TYPE>;
+    constexpr int HALO = G::HALO, TX = G::TX, SH = TY + 2 * HALO;
+    constexpr int NHALF = 2, RH = TY / NHALF, R = RH + 2 * HALO;
+    static_assert(TX * NHALF <= THREADS, "one thread per (column, half)");
+    __shared__ __align__(16) uint32_t tile[SH * TX];
     const TileCompDesc &tc = tcs[blockIdx.z];
     if (tc.transform != TYPE || j >= tc.nlevels)
         return;
@@ -219,19 +236,30 @@ idwt_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint32_t *_
         return;
     const LevelDesc o = tc.lev[j + 1];
     const int lh = o.u1 - o.u0, lv = o.v1 - o.v0;
-    const int XT = o.u0 + blockIdx.x * TX, YT = o.v0 + blockIdx.y * TY;
-    if (XT >= o.u1 || YT >= o.v1)
+    const int XA = (o.u0 & ~1) + blockIdx.x * TX, YA = (o.v0 & ~1) + blockIdx.y * TY;
+    if (XA >= o.u1 || YA >= o.v1)
         return;
-    reconstruct_tile<TYPE, TX, TY>(tile, tc, j, coefA, coefIn, XT, YT);
+    hpass<TYPE, SH>(tile, tc, j, coefA, coefIn, XA, YA - HALO);
+    __syncthreads();
+    const int col = threadIdx.x % TX, half = threadIdx.x / TX;
+    if (half >= NHALF)
+        return;
+    uint32_t v[R];
+#pragma unroll
+    for (int k = 0; k < R; k++)
+        v[k] = tile[(half * RH + k) * TX + col];
+    vlift<TYPE, R>(v, lv, o.v0);
     uint32_t *out = coefOut + tc.coef_off;
     const int ostride = (to_plane && j == tc.nlevels - 1) ? tc.width : lh;
-    for (int idx = threadIdx.x; idx < TX * TY; idx += THREADS) {
-        const int r = idx / TX, cx = idx - r * TX;
-        const int X = XT + cx, Y = YT + r;
-        if (X < o.u1 && Y < o.v1)
-            out[(size_t)(Y - o.v0) * ostride + (X - o.u0)] = tile[(r + HALO) * SWD + HALO + cx];
+    const int X = XA + col;
+    if (X >= o.u0 && X < o.u1) {
+#pragma unroll
+        for (int k = 0; k < RH; k++) {
+            const int Y = YA + half * RH + k;
+            if (Y >= o.v0 && Y < o.v1)
+                out[(size_t)(Y - o.v0) * ostride + (X - o.u0)] = v[HALO + k];
+        }
     }
-    (void)lv;
 }
 
 /* final fixed-point rescale of the 9/7 integer path when the plane itself is the output (jpeg2000dwt.c:534-536) */
@@ -277,15 +305,16 @@ template <int TYPE> __device__ __forceinline__ int to_pixel(uint32_t raw, int cb
     return val << shift;
 }
 
-template <int TYPE, int TX, int TY>
+template <int TYPE, int TY>
 __global__ void __launch_bounds__(THREADS)
 idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__restrict__ groups,
                        const uint32_t *__restrict__ coefA, const uint32_t *__restrict__ coefIn0,
                        const uint32_t *__restrict__ coefIn1, uint8_t *__restrict__ picture,
                        uint64_t po0, uint64_t po1, uint64_t po2, uint64_t po3, int rb0, int rb1, int rb2, int rb3)
 {
-    using L = Lift<TYPE>;
-    constexpr int HALO = L::HALO, SWD = TX + 2 * HALO + 1, SH = TY + 2 * HALO;
+    using G = Geo<TYPE>;
+    constexpr int HALO = G::HALO, TX = G::TX, SH = TY + 2 * HALO;
+    constexpr int NHALF = 2, RH = TY / NHALF, R = RH + 2 * HALO;
     extern __shared__ __align__(16) uint32_t dyn[];
     const PackGroup &g = groups[blockIdx.z];
     const TileCompDesc &t0 = tcs[g.tc[0]];
@@ -293,70 +322,135 @@ idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__
         return;
     const int nl = t0.nlevels;
     const LevelDesc o = t0.lev[nl];
-    const int XT = o.u0 + blockIdx.x * TX, YT = o.v0 + blockIdx.y * TY;
-    if (XT >= o.u1 || YT >= o.v1)
+    const int XA = (o.u0 & ~1) + blockIdx.x * TX, YA = (o.v0 & ~1) + blockIdx.y * TY;
+    if (XA >= o.u1 || YA >= o.v1)
         return;
-    for (int c = 0; c < g.ncomp; c++) {
-        uint32_t *tile = dyn + (size_t)c * SH * SWD;
-        const TileCompDesc &tc = tcs[g.tc[c]];
-        if (nl > 0) {
-            /* LL of the last level is the output of level nl-2: ping-pong parity */
-            const uint32_t *in = ((nl - 1) & 1) ? coefIn0 : coefIn1;
-            reconstruct_tile<TYPE, TX, TY>(tile, tc, nl - 1, coefA, in, XT, YT);
-        } else {
+    const int ncomp = g.ncomp;
+    if (nl > 0) {
+        /* LL of the last level is the output of level nl-2: ping-pong parity */
+        const uint32_t *in = ((nl - 1) & 1) ? coefIn0 : coefIn1;
+        for (int c = 0; c < ncomp; c++)
+            hpass<TYPE, SH>(dyn + (size_t)c * SH * TX, tcs[g.tc[c]], nl - 1, coefA, in, XA, YA - HALO);
+        __syncthreads();
+        const int col = threadIdx.x % TX, half = threadIdx.x / TX;
+        const int lv = o.v1 - o.v0;
+        for (int c = 0; c < ncomp; c++) {
+            uint32_t *tile = dyn + (size_t)c * SH * TX;
+            uint32_t v[R];
+            if (half < NHALF) {
+#pragma unroll
+                for (int k = 0; k < R; k++)
+                    v[k] = tile[(half * RH + k) * TX + col];
+                vlift<TYPE, R>(v, lv, o.v0);
+            }
+            __syncthreads();                      /* every column has been read: rows can be overwritten */
+            if (half < NHALF) {
+#pragma unroll
+                for (int k = 0; k < RH; k++)
+                    tile[(HALO + half * RH + k) * TX + col] = v[HALO + k];
+            }
+        }
+        __syncthreads();
+    } else {
+        for (int c = 0; c < ncomp; c++) {
+            const TileCompDesc &tc = tcs[g.tc[c]];
             const uint32_t *A = coefA + tc.coef_off;
+            uint32_t *tile = dyn + (size_t)c * SH * TX;
             for (int idx = threadIdx.x; idx < TX * TY; idx += THREADS) {
                 const int r = idx / TX, cx = idx - r * TX;
-                const int X = XT + cx, Y = YT + r;
-                if (X < o.u1 && Y < o.v1)
-                    tile[(r + HALO) * SWD + HALO + cx] = A[(size_t)(Y - o.v0) * tc.width + (X - o.u0)];
+                const int X = XA + cx, Y = YA + r;
+                if (X >= o.u0 && X < o.u1 && Y >= o.v0 && Y < o.v1)
+                    tile[(r + HALO) * TX + cx] = A[(size_t)(Y - o.v0) * tc.width + (X - o.u0)];
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
+    /* ---- MCT + level shift + clip + pack: one thread per pixel pair ---- */
     const uint64_t poff = g.plane == 0 ? po0 : g.plane == 1 ? po1 : g.plane == 2 ? po2 : po3;
     const int rb = g.plane == 0 ? rb0 : g.plane == 1 ? rb1 : g.plane == 2 ? rb2 : rb3;
     uint8_t *plane = picture + poff;
-    for (int idx = threadIdx.x; idx < TX * TY; idx += THREADS) {
-        const int r = idx / TX, cx = idx - r * TX;
-        const int X = XT + cx, Y = YT + r;
-        if (X >= o.u1 || Y >= o.v1)
-            continue;
-        uint32_t v[J2K_MAX_COMP];
+    int cbps[J2K_MAX_COMP], shift[J2K_MAX_COMP], soff[J2K_MAX_COMP];
 #pragma unroll
-        for (int c = 0; c < J2K_MAX_COMP; c++)
-            v[c] = c < g.ncomp ? dyn[(size_t)c * SH * SWD + (r + HALO) * SWD + HALO + cx] : 0;
+    for (int c = 0; c < J2K_MAX_COMP; c++) {
+        cbps[c] = c < ncomp ? tcs[g.tc[c]].cbps : 1;
+        shift[c] = g.shift[c];
+        soff[c] = g.sample_off[c];
+    }
+    const int mct_on = g.mct, wide = g.wide, pstride = g.pixel_stride;
+    constexpr int PPR = TX / 2;                   /* pixel pairs per tile row */
+    for (int idx = threadIdx.x; idx < PPR * TY; idx += THREADS) {
+        const int r = idx / PPR, pp = idx - r * PPR;
+        const int X = XA + 2 * pp, Y = YA + r;
+        if (Y < o.v0 || Y >= o.v1 || X + 1 < o.u0 || X >= o.u1)
+            continue;
+        uint32_t a[J2K_MAX_COMP], b[J2K_MAX_COMP];
+#pragma unroll
+        for (int c = 0; c < J2K_MAX_COMP; c++) {
+            if (c < ncomp) {
+                const uint2 t = *reinterpret_cast<const uint2 *>(dyn + (size_t)c * SH * TX + (r + HALO) * TX + 2 * pp);
+                a[c] = t.x;
+                b[c] = t.y;
+            } else {
+                a[c] = b[c] = 0;
+            }
+        }
         if (TYPE == J2K_DWT97_INT) {
             /* undo I_PRESHIFT: the last thing dwt_decode97_int does, i.e. before the component transform
              * (jpeg2000dwt.c:534-536) */
 #pragma unroll
-            for (int c = 0; c < J2K_MAX_COMP; c++)
-                v[c] = (uint32_t)((int32_t)((int64_t)(int32_t)v[c] + 128) >> 8);
+            for (int c = 0; c < J2K_MAX_COMP; c++) {
+                a[c] = (uint32_t)((int32_t)((int64_t)(int32_t)a[c] + 128) >> 8);
+                b[c] = (uint32_t)((int32_t)((int64_t)(int32_t)b[c] + 128) >> 8);
+            }
         }
-        if (g.mct)
-            mct<TYPE>(v[0], v[1], v[2]);
-        const size_t px = (size_t)(t0.out_x + X - o.u0) * g.pixel_stride;
-        uint8_t *row = plane + (size_t)(t0.out_y + Y - o.v0) * rb;
+        if (mct_on) {
+            mct<TYPE>(a[0], a[1], a[2]);
+            mct<TYPE>(b[0], b[1], b[2]);
+        }
+        int pa[J2K_MAX_COMP], pb[J2K_MAX_COMP];
 #pragma unroll
         for (int c = 0; c < J2K_MAX_COMP; c++) {
-            if (c < g.ncomp) {
-                const int pv = to_pixel<TYPE>(v[c], tcs[g.tc[c]].cbps, g.shift[c]);
-                if (g.wide)
-                    reinterpret_cast<uint16_t *>(row)[px + g.sample_off[c]] = (uint16_t)pv;
-                else
-                    row[px + g.sample_off[c]] = (uint8_t)pv;
+            pa[c] = to_pixel<TYPE>(a[c], cbps[c], shift[c]);
+            pb[c] = to_pixel<TYPE>(b[c], cbps[c], shift[c]);
+        }
+        const bool okA = X >= o.u0, okB = X + 1 < o.u1;
+        uint8_t *row = plane + (size_t)(t0.out_y + Y - o.v0) * rb;
+        const long px = (long)(t0.out_x + X - o.u0) * pstride;      /* sample index of pixel A, component 0 */
+        if (wide && ncomp == 3 && pstride == 3 && okA && okB && soff[1] == 1 && soff[2] == 2 &&
+            ((reinterpret_cast<uintptr_t>(row) + 2 * px) & 3) == 0) {
+            /* rgb48: two pixels = three aligned 32-bit words */
+            uint32_t *w32 = reinterpret_cast<uint32_t *>(row + 2 * px);
+            w32[0] = (uint32_t)pa[0] | ((uint32_t)pa[1] << 16);
+            w32[1] = (uint32_t)pa[2] | ((uint32_t)pb[0] << 16);
+            w32[2] = (uint32_t)pb[1] | ((uint32_t)pb[2] << 16);
+        } else if (wide && ncomp == 1 && pstride == 1 && okA && okB &&
+                   ((reinterpret_cast<uintptr_t>(row) + 2 * px) & 3) == 0) {
+            *reinterpret_cast<uint32_t *>(row + 2 * px) = (uint32_t)pa[0] | ((uint32_t)pb[0] << 16);
+        } else {
+#pragma unroll
+            for (int c = 0; c < J2K_MAX_COMP; c++) {
+                if (c < ncomp) {
+                    if (wide) {
+                        uint16_t *r16 = reinterpret_cast<uint16_t *>(row);
+                        if (okA) r16[px + soff[c]] = (uint16_t)pa[c];
+                        if (okB) r16[px + pstride + soff[c]] = (uint16_t)pb[c];
+                    } else {
+                        if (okA) row[px + soff[c]] = (uint8_t)pa[c];
+                        if (okB) row[px + pstride + soff[c]] = (uint8_t)pb[c];
+                    }
+                }
             }
         }
     }
 }
 
-template <int TYPE, int TX, int TY> constexpr size_t final_smem(int ncomp)
+template <int TYPE, int TY> constexpr size_t final_smem(int ncomp)
 {
-    return (size_t)ncomp * (TY + 2 * Lift<TYPE>::HALO) * (TX + 2 * Lift<TYPE>::HALO + 1) * 4;
+    return (size_t)ncomp * (TY + 2 * Lift<TYPE>::HALO) * Geo<TYPE>::TX * 4;
 }
 
-constexpr int LTX = 128, LTY = 32;   /* intermediate levels */
-constexpr int FTX = 64, FTY = 32;    /* fused last level */
+constexpr int LTY = 64;    /* tile rows, intermediate levels */
+constexpr int FTY = 32;    /* tile rows, fused last level */
 
 template <int TYPE>
 int run_levels(cudaStream_t stream, const IdwtFrame &f, int max_levels, bool any_type, int max_w[], int max_h[],
@@ -368,10 +462,12 @@ int run_levels(cudaStream_t stream, const IdwtFrame &f, int max_levels, bool any
     for (int j = 0; j < max_levels; j++) {
         if (max_w[j] <= 0)
             continue;
-        dim3 grid((max_w[j] + LTX - 1) / LTX, (max_h[j] + LTY - 1) / LTY, f.ntcs);
+        constexpr int LTX = Geo<TYPE>::TX;
+        /* tiles start at even absolute coordinates: one extra sample may precede the resolution */
+        dim3 grid((max_w[j] + 1 + LTX - 1) / LTX, (max_h[j] + 1 + LTY - 1) / LTY, f.ntcs);
         const void *in = (j & 1) ? f.coefB : f.coefC;        /* level j reads what level j-1 wrote */
         void *out = (j & 1) ? f.coefC : f.coefB;
-        idwt_level_kernel<TYPE, LTX, LTY><<<grid, THREADS, 0, stream>>>(
+        idwt_level_kernel<TYPE, LTY><<<grid, THREADS, 0, stream>>>(
             f.d_tcs, j, (const uint32_t *)f.coefA, (const uint32_t *)in, (uint32_t *)out, to_plane);
         launches++;
     }
@@ -423,13 +519,14 @@ int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f)
             if (g.ncomp > maxc) maxc = g.ncomp;
         }
         if (anyg && gw > 0 && gh > 0) {
-            dim3 grid((gw + FTX - 1) / FTX, (gh + FTY - 1) / FTY, f.ngroups);
 #define LAUNCH_FINAL(T)                                                                                     \
     do {                                                                                                    \
-        size_t sm = final_smem<T, FTX, FTY>(maxc);                                                          \
-        cudaFuncSetAttribute(idwt_final_pack_kernel<T, FTX, FTY>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+        constexpr int FTX = Geo<T>::TX;                                                                     \
+        dim3 grid((gw + 1 + FTX - 1) / FTX, (gh + 1 + FTY - 1) / FTY, f.ngroups);                           \
+        size_t sm = final_smem<T, FTY>(maxc);                                                               \
+        cudaFuncSetAttribute(idwt_final_pack_kernel<T, FTY>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
                              (int)sm);                                                                      \
-        idwt_final_pack_kernel<T, FTX, FTY><<<grid, THREADS, sm, stream>>>(                                 \
+        idwt_final_pack_kernel<T, FTY><<<grid, THREADS, sm, stream>>>(                                      \
             f.d_tcs, f.d_groups, (const uint32_t *)f.coefA, (const uint32_t *)f.coefB,                      \
             (const uint32_t *)f.coefC, f.picture, f.plane_off[0], f.plane_off[1], f.plane_off[2],           \
             f.plane_off[3], f.plane_row_bytes[0], f.plane_row_bytes[1], f.plane_row_bytes[2],               \
@@ -481,13 +578,14 @@ int launch_idwt_plane(cudaStream_t stream, int type, const int32_t *border, int 
         const int lw = o.u1 - o.u0, lhh = o.v1 - o.v0;
         if (lw <= 0 || lhh <= 0)
             continue;
-        dim3 grid((lw + LTX - 1) / LTX, (lhh + LTY - 1) / LTY, 1);
+        const int ltx = type == J2K_DWT53 ? Geo<J2K_DWT53>::TX : Geo<J2K_DWT97>::TX;
+        dim3 grid((lw + 1 + ltx - 1) / ltx, (lhh + 1 + LTY - 1) / LTY, 1);
         const void *in = (j & 1) ? f.coefB : f.coefC;
         /* the last level cannot go to the plane in place (other CTAs still read its quadrants): use the
          * ping-pong buffer with the plane's stride and copy back */
         void *out = (j & 1) ? f.coefC : f.coefB;
 #define LAUNCH_LEVEL(T)                                                                                     \
-    idwt_level_kernel<T, LTX, LTY><<<grid, THREADS, 0, stream>>>(d_tc, j, (const uint32_t *)plane,          \
+    idwt_level_kernel<T, LTY><<<grid, THREADS, 0, stream>>>(d_tc, j, (const uint32_t *)plane,               \
                                                                  (const uint32_t *)in, (uint32_t *)out, 1)
         if (type == J2K_DWT53) LAUNCH_LEVEL(J2K_DWT53);
         else if (type == J2K_DWT97) LAUNCH_LEVEL(J2K_DWT97);
