@@ -252,7 +252,10 @@ def run_ours(args):
     per_thread = [list(range(t, B, T)) for t in range(T)]
     decs = [fb.Jpeg2000Decoder(device=local, slots=args.slots_e2e) for _ in range(T)]
     pins = [[fb.PinnedFrame(info) for _ in range(args.slots_e2e)] for _ in range(T)]
-    h2d = [0]
+    # the step's inputs live in pinned host memory (as the contract describes); the H2D copy of every
+    # frame's codestream + tables and the D2H of its picture happen inside the timed region
+    pkts = [fb.PinnedPacket(f) for f in frames]
+    h2d_seen = [0] * T
 
     def e2e_worker(t, nsteps):
         torch.cuda.set_device(local)
@@ -262,7 +265,9 @@ def run_ours(args):
             for n, i in enumerate(per_thread[t]):
                 if len(pending) == len(pf):
                     d.wait(pending.pop(0))
-                pending.append(d.submit(frames[i % D], pf[n % len(pf)]))
+                slot = d.submit(pkts[i % D], pf[n % len(pf)])
+                pending.append(slot)
+                h2d_seen[t] = d.h2d_bytes(slot)
         for s in pending:
             d.wait(s)
 
@@ -292,7 +297,7 @@ def run_ours(args):
     pix = float(w) * h
     value = frames_total * pix / (kern_ms * 1e-3) / 1e6
     e2e = frames_total * pix / e2e_s / 1e6
-    h2d_step = sum(len(frames[i % D]) for i in range(B)) + B * (ncb * 36 + 4096)
+    h2d_step = B * max(h2d_seen)                   # tables + codestream, as counted by the library per submit
     d2h_step = B * w * h * 3 * 2
 
     peaks = {}
@@ -325,6 +330,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2: %d MB of coefficient planes + %d MB codestream per frame, "
                              "%d frames cycled" % (int(samples * 4 / 1e6), int(len(frames[0]) / 1e6), S),
                        "e2e_host_threads": T, "e2e_slots_per_thread": args.slots_e2e,
+                       "e2e_buffers": "codestreams and output pictures in pinned host memory",
                        "e2e_timer": "wall clock bracketed by device synchronisation (includes host parsing)"},
             "e2e": {"value": e2e, "unit": "Mpixel/s", "fps": frames_total / e2e_s,
                     "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step), "output_check": ok},

@@ -88,6 +88,8 @@ def lib():
         L.b200j2k_slot_output.argtypes = [vp, i32, ctypes.POINTER(i64)]
         L.b200j2k_slot_output.restype = vp
         L.b200j2k_slot_launches.argtypes = [vp, i32]
+        L.b200j2k_slot_h2d_bytes.argtypes = [vp, i32]
+        L.b200j2k_slot_h2d_bytes.restype = i64
         L.b200j2k_ht_blocks.argtypes = [i32, vp, i64, vp, i32, vp, vp]
         L.b200j2k_idwt.argtypes = [i32, i32, vp, i32, vp]
         L.b200j2k_host_alloc.argtypes = [i64]
@@ -112,6 +114,7 @@ EXPORTS = ["b200j2k_device_count", "b200j2k_create", "b200j2k_destroy", "b200j2k
            "b200j2k_wait", "b200j2k_decode", "b200j2k_stage", "b200j2k_run_staged", "b200j2k_run_staged_timed",
            "b200j2k_sync",
            "b200j2k_fetch", "b200j2k_slot_stream", "b200j2k_slot_output", "b200j2k_slot_launches",
+           "b200j2k_slot_h2d_bytes",
            "b200j2k_ht_blocks", "b200j2k_idwt", "b200j2k_host_alloc", "b200j2k_host_free",
            "b200j2k_host_register", "b200j2k_host_unregister", "b200j2k_pix_fmt_name", "b200j2k_version",
            "b200j2k_plan_build", "b200j2k_plan_table", "b200j2k_plan_scalar"]
@@ -125,6 +128,8 @@ def _check(ret: int, what: str = "") -> int:
 
 def _buf(b):
     """bytes / bytearray / uint8 ndarray -> (address, length, keep-alive)"""
+    if isinstance(b, PinnedPacket):
+        return b._ptr, b.size, b
     if isinstance(b, np.ndarray):
         a = np.ascontiguousarray(b, dtype=np.uint8)
         return a.ctypes.data, a.size, a
@@ -165,6 +170,33 @@ class PinnedFrame:
         if self._ptr:
             lib().b200j2k_host_free(self._ptr)
             self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PinnedPacket:
+    """A codestream held in pinned host memory: b200j2k_submit DMAs it without a staging copy."""
+
+    def __init__(self, data):
+        addr, n, keep = _buf(data)
+        self.size = n
+        self._ptr = lib().b200j2k_host_alloc(max(n, 1))
+        if not self._ptr:
+            raise DecodeError(ERR_DEVICE, "host_alloc")
+        ctypes.memmove(self._ptr, addr, n)
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * n).from_address(self._ptr))
+
+    def close(self):
+        if self._ptr:
+            lib().b200j2k_host_free(self._ptr)
+            self._ptr = None
+
+    def __len__(self):
+        return self.size
 
     def __del__(self):
         try:
@@ -276,6 +308,9 @@ class Jpeg2000Decoder:
 
     def stream(self, slot: int) -> int:
         return int(lib().b200j2k_slot_stream(self._h, slot) or 0)
+
+    def h2d_bytes(self, slot: int) -> int:
+        return int(lib().b200j2k_slot_h2d_bytes(self._h, slot))
 
     def launches(self, slot: int) -> int:
         return int(lib().b200j2k_slot_launches(self._h, slot))

@@ -96,6 +96,7 @@ struct Slot {
     int n_plain = 0, n_refine = 0;
     int maxL_plain = 0, maxL_refine = 0;
     bool busy = false, staged = false;
+    size_t h2d_bytes = 0;
     int launches = 0;
     /* pending output */
     uint8_t *dst[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -148,6 +149,16 @@ void fill_info(const Parser &p, b200j2k_frame_info *info)
     info->bytes_consumed = p.consumed;
 }
 
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
 /* host parse + build the staging blob + H2D */
 int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size, b200j2k_frame_info *info)
 {
@@ -177,15 +188,24 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
         s.n_plain = (int)a;
         s.n_refine = (int)(ncb - a);
     }
+    /* blob layout on the device: [tables][codestream bytes][gathered bytes][64 B zero slack].  The tables
+     * always go through the pinned staging buffer; the codestream is DMA'd straight from the caller's
+     * packet when that memory is pinned (registered), else it is copied into the staging buffer first. */
+    const bool direct_in = is_pinned(pkt);
     size_t off = 0;
     s.off_cblk = off;   off = align_up(off + ncb * sizeof(CblkDesc), 256);
     s.off_bands = off;  off = align_up(off + p.bands.size() * sizeof(BandDesc), 256);
     s.off_tcs = off;    off = align_up(off + p.tcs.size() * sizeof(TileCompDesc), 256);
     s.off_groups = off; off = align_up(off + p.groups.size() * sizeof(PackGroup), 256);
     s.off_order = off;  off = align_up(off + ncb * sizeof(uint32_t), 256);
-    s.off_bytes = off;  off = align_up(off + (size_t)size + p.extra.size() + 64, 256);
+    s.off_bytes = off;
+    const size_t tail = p.extra.size() + 64;              /* gathered bytes + slack, placed behind the codestream */
+    const size_t off_tail = s.off_bytes + (size_t)size;
+    off = align_up(off_tail + tail, 256);
     s.blob_bytes = off;
-    if ((ret = s.stage.ensure(off)) < 0)
+    /* staging: tables, then (staged path) the codestream, then the tail */
+    const size_t stage_need = direct_in ? s.off_bytes + tail : off;
+    if ((ret = s.stage.ensure(stage_need)) < 0)
         return ret;
     uint8_t *h = s.stage.p;
     memcpy(h + s.off_cblk, p.cblk.data(), ncb * sizeof(CblkDesc));
@@ -193,10 +213,12 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     memcpy(h + s.off_tcs, p.tcs.data(), p.tcs.size() * sizeof(TileCompDesc));
     memcpy(h + s.off_groups, p.groups.data(), p.groups.size() * sizeof(PackGroup));
     memcpy(h + s.off_order, order.data(), ncb * sizeof(uint32_t));
-    memcpy(h + s.off_bytes, pkt, (size_t)size);
+    uint8_t *htail = direct_in ? h + s.off_bytes : h + off_tail;
+    if (!direct_in)
+        memcpy(h + s.off_bytes, pkt, (size_t)size);
     if (!p.extra.empty())
-        memcpy(h + s.off_bytes + size, p.extra.data(), p.extra.size());
-    memset(h + s.off_bytes + size + p.extra.size(), 0, 64);
+        memcpy(htail, p.extra.data(), p.extra.size());
+    memset(htail + p.extra.size(), 0, 64);
 
     if ((ret = s.d_blob.ensure(off)) < 0) return ret;
     if ((ret = s.d_coefA.ensure(p.coef_elems * 4 + 256)) < 0) return ret;
@@ -206,8 +228,20 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     }
     if ((ret = s.d_picture.ensure(p.picture_bytes + 256)) < 0) return ret;
     if ((ret = s.d_status.ensure(ncb * 4 + 256)) < 0) return ret;
-    if (cudaMemcpyAsync(s.d_blob.p, h, off, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
+    uint8_t *dblob = (uint8_t *)s.d_blob.p;
+    cudaError_t e;
+    if (direct_in) {
+        e = cudaMemcpyAsync(dblob, h, s.off_bytes, cudaMemcpyHostToDevice, s.stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dblob + s.off_bytes, pkt, (size_t)size, cudaMemcpyHostToDevice, s.stream);
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dblob + off_tail, htail, tail, cudaMemcpyHostToDevice, s.stream);
+    } else {
+        e = cudaMemcpyAsync(dblob, h, off_tail + tail, cudaMemcpyHostToDevice, s.stream);
+    }
+    if (e != cudaSuccess)
         return B200J2K_ERR_DEVICE;
+    s.h2d_bytes = off_tail + tail;
     s.staged = true;
     return 0;
 }
@@ -258,16 +292,6 @@ int run_kernels(Slot &s, cudaEvent_t *ev = nullptr)
     if (ev) cudaEventRecord(ev[4], s.stream);
     s.launches = launches;
     return 0;
-}
-
-bool is_pinned(const void *p)
-{
-    cudaPointerAttributes a;
-    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
-        cudaGetLastError();
-        return false;
-    }
-    return a.type == cudaMemoryTypeHost;
 }
 
 int queue_output(Slot &s, uint8_t *const data[4], const int linesize[4])
@@ -528,6 +552,13 @@ void *b200j2k_slot_output(b200j2k_decoder *d, int slot, int64_t *bytes)
     if (bytes)
         *bytes = (int64_t)d->slots[slot].parser.picture_bytes;
     return d->slots[slot].d_picture.p;
+}
+
+int64_t b200j2k_slot_h2d_bytes(b200j2k_decoder *d, int slot)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size())
+        return 0;
+    return (int64_t)d->slots[slot].h2d_bytes;
 }
 
 int b200j2k_slot_launches(b200j2k_decoder *d, int slot)

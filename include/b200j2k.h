@@ -84,8 +84,10 @@ int b200j2k_probe(const uint8_t *pkt, int64_t pkt_size, int flags, b200j2k_frame
 /* Asynchronous decode of one packet (= one codestream, AVPacket.data/size) into caller-owned planes
  * (AVFrame.data[]/linesize[]).  Host parsing happens in the call; H2D, kernels and D2H are queued on the
  * slot's stream.  Returns the slot index (>= 0) to pass to b200j2k_wait().  If every slot is busy the
- * oldest one is waited for first.  The packet may be released when the call returns; the planes must stay
- * valid until b200j2k_wait().  Planes that were registered with b200j2k_host_register() (or allocated with
+ * oldest one is waited for first.  A packet in ordinary (pageable) memory is copied into pinned staging and
+ * may be released when the call returns; a packet in pinned memory (b200j2k_host_alloc / _register) is
+ * DMA'd from where it lies and must stay valid until b200j2k_wait().  The planes must stay valid until
+ * b200j2k_wait().  Planes that were registered with b200j2k_host_register() (or allocated with
  * b200j2k_host_alloc()) receive the device->host copy directly; others go through pinned staging + memcpy. */
 int b200j2k_submit(b200j2k_decoder *dec, const uint8_t *pkt, int64_t pkt_size,
                    uint8_t *const data[4], const int linesize[4], b200j2k_frame_info *info);
@@ -113,6 +115,8 @@ int b200j2k_fetch(b200j2k_decoder *dec, int slot, uint8_t *const data[4], const 
 void *b200j2k_slot_stream(b200j2k_decoder *dec, int slot);
 /* device pointer + byte size of the slot's packed output picture, or NULL */
 void *b200j2k_slot_output(b200j2k_decoder *dec, int slot, int64_t *bytes);
+/* bytes the last b200j2k_submit/_stage of `slot` copied host->device (tables + codestream) */
+int64_t b200j2k_slot_h2d_bytes(b200j2k_decoder *dec, int slot);
 /* number of kernel launches the last run of `slot` queued */
 int b200j2k_slot_launches(b200j2k_decoder *dec, int slot);
 

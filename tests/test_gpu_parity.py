@@ -202,6 +202,16 @@ def test_pipelined_submit_wait(dec):
     for (cs, planes), pin in zip(frames, pins):
         img = pin.buffer.view(np.uint16).reshape(96, 160, 3) >> 4
         assert np.array_equal(img, np.stack(planes, -1))
+    # same again with the packets in pinned memory (DMA straight from the caller's buffer)
+    pkts = [fb.PinnedPacket(cs) for cs, _ in frames]
+    for pin in pins:
+        pin.buffer[:] = 0
+    pending = [dec.submit(pk, pin) for pk, pin in zip(pkts[:2], pins[:2])]
+    for s in pending:
+        dec.wait(s)
+    for (cs, planes), pin in zip(frames[:2], pins[:2]):
+        assert np.array_equal(pin.buffer.view(np.uint16).reshape(96, 160, 3) >> 4, np.stack(planes, -1))
+    assert dec.h2d_bytes(pending[0]) > len(frames[0][0])
 
 
 # ---- BASELINE.json configs at full size: lossless round trip (size-independent property) ---------------
