@@ -135,63 +135,125 @@ template <int TYPE> struct Geo {
  * (jpeg2000dwt.c:309-325, :376-401, :453-481).  Rows and columns outside the resolution are fetched by
  * index reflection, which reproduces the reference's symmetric extension.
  */
-template <int TYPE, int SH>
-__device__ __forceinline__ void hpass(uint32_t *tile, const TileCompDesc &tc, int j, const uint32_t *coefA,
-                                      const uint32_t *coefIn, int XA, int YS)
+/* Source rows of one tile row: where its low-pass and high-pass coefficients live */
+struct RowSrc {
+    const uint32_t *rowL, *rowH;
+};
+
+template <int TYPE>
+__device__ __forceinline__ RowSrc row_source(const TileCompDesc &tc, int j, const uint32_t *coefA,
+                                             const uint32_t *coefIn, int Y)
 {
-    using L = Lift<TYPE>;
-    using G = Geo<TYPE>;
     const LevelDesc o = tc.lev[j + 1];
     const int u0 = o.u0, u1 = o.u1, v0 = o.v0, v1 = o.v1;
-    const int lh = u1 - u0;
     const int nLh = ((u1 + 1) >> 1) - ((u0 + 1) >> 1), nLv = ((v1 + 1) >> 1) - ((v0 + 1) >> 1);
     const int W = tc.width;
     const uint32_t *A = coefA + tc.coef_off;
     /* LL comes from the plane itself at the coarsest level, else from the compact ping-pong buffer */
     const uint32_t *LLp = j == 0 ? A : coefIn + tc.coef_off;
     const int LLstride = j == 0 ? W : nLh;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int eoff = (u0 + 1) >> 1, ooff = u0 >> 1;
+    const int Yr = (Y >= v0 && Y < v1) ? Y : reflect(Y, v0, v1);
+    const int ky = band_index(Yr, v0);
+    RowSrc s;
+    s.rowL = (Yr & 1) ? A + (size_t)(nLv + ky) * W : LLp + (size_t)ky * LLstride;
+    s.rowH = ((Yr & 1) ? A + (size_t)(nLv + ky) * W : A + (size_t)ky * W) + nLh;
+    return s;
+}
 
-    for (int r = warp; r < SH; r += NWARPS) {
-        const int Y = YS + r;
-        const int Yr = (Y >= v0 && Y < v1) ? Y : reflect(Y, v0, v1);
-        const int ky = band_index(Yr, v0);
-        const uint32_t *rowL = (Yr & 1) ? A + (size_t)(nLv + ky) * W : LLp + (size_t)ky * LLstride;
-        const uint32_t *rowH = ((Yr & 1) ? A + (size_t)(nLv + ky) * W : A + (size_t)ky * W) + nLh;
-        uint32_t *trow = tile + r * G::TX;
+/* row lifting of one warp-wide group of 32 coefficient pairs (jpeg2000dwt.c:309-325, :376-401, :453-481) */
+template <int TYPE>
+__device__ __forceinline__ void hlift(uint32_t Lc, uint32_t Hc, uint32_t &xe, uint32_t &xo)
+{
+    using L = Lift<TYPE>;
+    if (TYPE == J2K_DWT53) {
+        const uint32_t Hl = __shfl_up_sync(FULLMASK, Hc, 1);
+        xe = L::apply(0, Lc, Hl, Hc);
+        const uint32_t er = __shfl_down_sync(FULLMASK, xe, 1);
+        xo = L::apply(1, Hc, xe, er);
+    } else {
+        const uint32_t Hl = __shfl_up_sync(FULLMASK, Hc, 1);
+        const uint32_t e1 = L::apply(0, Lc, Hl, Hc);
+        const uint32_t e1r = __shfl_down_sync(FULLMASK, e1, 1);
+        const uint32_t o1 = L::apply(1, Hc, e1, e1r);
+        const uint32_t o1l = __shfl_up_sync(FULLMASK, o1, 1);
+        xe = L::apply(2, e1, o1l, o1);
+        const uint32_t er = __shfl_down_sync(FULLMASK, xe, 1);
+        xo = L::apply(3, o1, xe, er);
+    }
+}
+
+/*
+ * HOR_SD for the SH rows of NC tiles (one per component of a pack group), results into tiles[c][SH][TX]
+ * (shared memory).  XA: even absolute X of tile column 0; YS: even absolute Y of tile row 0 (apron
+ * included).  Lane = one (low, high) coefficient pair of a row: the low-pass sample sits at the even
+ * absolute position 2i, the high-pass one at 2i+1; the lifting steps exchange neighbours with shuffles.
+ * Rows and columns outside the resolution are fetched by index reflection, which reproduces the
+ * reference's symmetric extension.  Each warp first issues the loads of a batch of
+ * rows, then lifts them: the batch keeps several kilobytes per warp in flight (the kernel is bound by
+ * HBM latency x parallelism, not by arithmetic).
+ */
+template <int TYPE, int SH, int BATCH>
+__device__ __forceinline__ void hpass(uint32_t *tiles, const TileCompDesc *tcs, const int *tcidx, int ncomp, int j,
+                                      const uint32_t *coefA, const uint32_t *coefIn, int XA, int YS)
+{
+    using L = Lift<TYPE>;
+    using G = Geo<TYPE>;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const LevelDesc o = tcs[tcidx[0]].lev[j + 1];     /* all components of a group share the geometry */
+    const int u0 = o.u0, u1 = o.u1, lh = u1 - u0;
+    const int eoff = (u0 + 1) >> 1, ooff = u0 >> 1;
+    /* column indices of this lane's pairs: identical for every row */
+    int ie[G::ITERS], io[G::ITERS];
 #pragma unroll
-        for (int it = 0; it < G::ITERS; it++) {
-            const int pair = (XA >> 1) + it * G::VP - G::HP + lane;
-            int Xe = 2 * pair, Xo = Xe + 1;
-            uint32_t xe, xo;
-            if (lh > 1) {
-                if (Xe < u0 || Xe >= u1) Xe = reflect(Xe, u0, u1);
-                if (Xo < u0 || Xo >= u1) Xo = reflect(Xo, u0, u1);
-                const uint32_t Lc = rowL[(Xe >> 1) - eoff];
-                const uint32_t Hc = rowH[(Xo >> 1) - ooff];
-                if (TYPE == J2K_DWT53) {
-                    const uint32_t Hl = __shfl_up_sync(FULLMASK, Hc, 1);
-                    xe = L::apply(0, Lc, Hl, Hc);
-                    const uint32_t er = __shfl_down_sync(FULLMASK, xe, 1);
-                    xo = L::apply(1, Hc, xe, er);
-                } else {
-                    const uint32_t Hl = __shfl_up_sync(FULLMASK, Hc, 1);
-                    const uint32_t e1 = L::apply(0, Lc, Hl, Hc);
-                    const uint32_t e1r = __shfl_down_sync(FULLMASK, e1, 1);
-                    const uint32_t o1 = L::apply(1, Hc, e1, e1r);
-                    const uint32_t o1l = __shfl_up_sync(FULLMASK, o1, 1);
-                    xe = L::apply(2, e1, o1l, o1);
-                    const uint32_t er = __shfl_down_sync(FULLMASK, xe, 1);
-                    xo = L::apply(3, o1, xe, er);
+    for (int it = 0; it < G::ITERS; it++) {
+        const int pair = (XA >> 1) + it * G::VP - G::HP + lane;
+        int Xe = 2 * pair, Xo = Xe + 1;
+        if (lh > 1) {
+            if (Xe < u0 || Xe >= u1) Xe = reflect(Xe, u0, u1);
+            if (Xo < u0 || Xo >= u1) Xo = reflect(Xo, u0, u1);
+            ie[it] = (Xe >> 1) - eoff;
+            io[it] = (Xo >> 1) - ooff;
+        } else {
+            ie[it] = io[it] = 0;
+        }
+    }
+    const int nitems = ncomp * SH;
+    for (int base = warp; base < nitems; base += NWARPS * BATCH) {
+        uint32_t Lc[BATCH][G::ITERS], Hc[BATCH][G::ITERS];
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int item = base + b * NWARPS;
+            if (item < nitems) {
+                const int c = item / SH, r = item - c * SH;
+                const RowSrc src = row_source<TYPE>(tcs[tcidx[c]], j, coefA, coefIn, YS + r);
+#pragma unroll
+                for (int it = 0; it < G::ITERS; it++) {
+                    if (lh > 1) {
+                        Lc[b][it] = src.rowL[ie[it]];
+                        Hc[b][it] = src.rowH[io[it]];
+                    } else {
+                        Lc[b][it] = Hc[b][it] = (u0 & 1) ? src.rowH[0] : src.rowL[0];
+                    }
                 }
-            } else {
-                /* one-sample line (jpeg2000dwt.c:313-317, :380-386, :457-463) */
-                const uint32_t c = (u0 & 1) ? rowH[0] : rowL[0];
-                xe = xo = L::single(c, u0 & 1);
             }
-            if (lane >= G::HP && lane < 32 - G::HP)
-                *reinterpret_cast<uint2 *>(trow + 2 * (it * G::VP + lane - G::HP)) = make_uint2(xe, xo);
+        }
+#pragma unroll
+        for (int b = 0; b < BATCH; b++) {
+            const int item = base + b * NWARPS;
+            if (item < nitems) {
+                const int c = item / SH, r = item - c * SH;
+                uint32_t *trow = tiles + ((size_t)c * SH + r) * G::TX;
+#pragma unroll
+                for (int it = 0; it < G::ITERS; it++) {
+                    uint32_t xe, xo;
+                    if (lh > 1)
+                        hlift<TYPE>(Lc[b][it], Hc[b][it], xe, xo);
+                    else     /* one-sample line (jpeg2000dwt.c:313-317, :380-386, :457-463) */
+                        xe = xo = L::single(Lc[b][it], u0 & 1);
+                    if (lane >= G::HP && lane < 32 - G::HP)
+                        *reinterpret_cast<uint2 *>(trow + 2 * (it * G::VP + lane - G::HP)) = make_uint2(xe, xo);
+                }
+            }
         }
     }
 }
@@ -239,7 +301,8 @@ idwt_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint32_t *_
     const int XA = (o.u0 & ~1) + blockIdx.x * TX, YA = (o.v0 & ~1) + blockIdx.y * TY;
     if (XA >= o.u1 || YA >= o.v1)
         return;
-    hpass<TYPE, SH>(tile, tc, j, coefA, coefIn, XA, YA - HALO);
+    const int self = (int)blockIdx.z;
+    hpass<TYPE, SH, 3>(tile, tcs, &self, 1, j, coefA, coefIn, XA, YA - HALO);
     __syncthreads();
     const int col = threadIdx.x % TX, half = threadIdx.x / TX;
     if (half >= NHALF)
@@ -329,8 +392,7 @@ idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__
     if (nl > 0) {
         /* LL of the last level is the output of level nl-2: ping-pong parity */
         const uint32_t *in = ((nl - 1) & 1) ? coefIn0 : coefIn1;
-        for (int c = 0; c < ncomp; c++)
-            hpass<TYPE, SH>(dyn + (size_t)c * SH * TX, tcs[g.tc[c]], nl - 1, coefA, in, XA, YA - HALO);
+        hpass<TYPE, SH, 4>(dyn, tcs, g.tc, ncomp, nl - 1, coefA, in, XA, YA - HALO);
         __syncthreads();
         const int col = threadIdx.x % TX, half = threadIdx.x / TX;
         const int lv = o.v1 - o.v0;
