@@ -135,31 +135,6 @@ template <int TYPE> struct Geo {
  * (jpeg2000dwt.c:309-325, :376-401, :453-481).  Rows and columns outside the resolution are fetched by
  * index reflection, which reproduces the reference's symmetric extension.
  */
-/* Source rows of one tile row: where its low-pass and high-pass coefficients live */
-struct RowSrc {
-    const uint32_t *rowL, *rowH;
-};
-
-template <int TYPE>
-__device__ __forceinline__ RowSrc row_source(const TileCompDesc &tc, int j, const uint32_t *coefA,
-                                             const uint32_t *coefIn, int Y)
-{
-    const LevelDesc o = tc.lev[j + 1];
-    const int u0 = o.u0, u1 = o.u1, v0 = o.v0, v1 = o.v1;
-    const int nLh = ((u1 + 1) >> 1) - ((u0 + 1) >> 1), nLv = ((v1 + 1) >> 1) - ((v0 + 1) >> 1);
-    const int W = tc.width;
-    const uint32_t *A = coefA + tc.coef_off;
-    /* LL comes from the plane itself at the coarsest level, else from the compact ping-pong buffer */
-    const uint32_t *LLp = j == 0 ? A : coefIn + tc.coef_off;
-    const int LLstride = j == 0 ? W : nLh;
-    const int Yr = (Y >= v0 && Y < v1) ? Y : reflect(Y, v0, v1);
-    const int ky = band_index(Yr, v0);
-    RowSrc s;
-    s.rowL = (Yr & 1) ? A + (size_t)(nLv + ky) * W : LLp + (size_t)ky * LLstride;
-    s.rowH = ((Yr & 1) ? A + (size_t)(nLv + ky) * W : A + (size_t)ky * W) + nLh;
-    return s;
-}
-
 /* row lifting of one warp-wide group of 32 coefficient pairs (jpeg2000dwt.c:309-325, :376-401, :453-481) */
 template <int TYPE>
 __device__ __forceinline__ void hlift(uint32_t Lc, uint32_t Hc, uint32_t &xe, uint32_t &xo)
@@ -182,25 +157,54 @@ __device__ __forceinline__ void hlift(uint32_t Lc, uint32_t Hc, uint32_t &xe, ui
     }
 }
 
+/* Per-tile row table (shared memory): where the low-pass and high-pass coefficients of tile row r live.
+ * offL >= 0: element offset into the LL source; offL < 0: ~offL is an element offset into the plane
+ * (LH band).  offH: element offset into the plane (HL or HH band). */
+struct RowTab {
+    int offL, offH;
+};
+
+template <int SH>
+__device__ __forceinline__ void build_rowtab(RowTab *tab, const TileCompDesc &tc, int j, int YS)
+{
+    const LevelDesc o = tc.lev[j + 1];
+    const int u0 = o.u0, u1 = o.u1, v0 = o.v0, v1 = o.v1;
+    const int nLh = ((u1 + 1) >> 1) - ((u0 + 1) >> 1), nLv = ((v1 + 1) >> 1) - ((v0 + 1) >> 1);
+    const int W = tc.width;
+    const int LLstride = j == 0 ? W : nLh;
+    for (int r = threadIdx.x; r < SH; r += THREADS) {
+        const int Y = YS + r;
+        const int Yr = (Y >= v0 && Y < v1) ? Y : reflect(Y, v0, v1);
+        const int ky = band_index(Yr, v0);
+        RowTab t;
+        if (Yr & 1) {
+            t.offL = ~((nLv + ky) * W);
+            t.offH = (nLv + ky) * W + nLh;
+        } else {
+            t.offL = ky * LLstride;
+            t.offH = ky * W + nLh;
+        }
+        tab[r] = t;
+    }
+}
+
 /*
  * HOR_SD for the SH rows of NC tiles (one per component of a pack group), results into tiles[c][SH][TX]
- * (shared memory).  XA: even absolute X of tile column 0; YS: even absolute Y of tile row 0 (apron
- * included).  Lane = one (low, high) coefficient pair of a row: the low-pass sample sits at the even
- * absolute position 2i, the high-pass one at 2i+1; the lifting steps exchange neighbours with shuffles.
- * Rows and columns outside the resolution are fetched by index reflection, which reproduces the
- * reference's symmetric extension.  Each warp first issues the loads of a batch of
- * rows, then lifts them: the batch keeps several kilobytes per warp in flight (the kernel is bound by
- * HBM latency x parallelism, not by arithmetic).
+ * (shared memory).  XA: even absolute X of tile column 0.  Lane = one (low, high) coefficient pair of a
+ * row: the low-pass sample sits at the even absolute position 2i, the high-pass one at 2i+1; the lifting
+ * steps exchange neighbours with shuffles.  Rows and columns outside the resolution are fetched by index
+ * reflection, which reproduces the reference's symmetric extension.  Each warp first
+ * issues the loads of a batch of rows, then lifts them: the batch keeps several kilobytes per warp in
+ * flight (the kernel is bound by HBM latency x parallelism, not by arithmetic).
  */
 template <int TYPE, int SH, int BATCH>
-__device__ __forceinline__ void hpass(uint32_t *tiles, const TileCompDesc *tcs, const int *tcidx, int ncomp, int j,
-                                      const uint32_t *coefA, const uint32_t *coefIn, int XA, int YS)
+__device__ __forceinline__ void hpass(uint32_t *tiles, const RowTab *tab, const uint32_t *const *Ap,
+                                      const uint32_t *const *LLp, int ncomp, int u0, int u1, int XA)
 {
     using L = Lift<TYPE>;
     using G = Geo<TYPE>;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const LevelDesc o = tcs[tcidx[0]].lev[j + 1];     /* all components of a group share the geometry */
-    const int u0 = o.u0, u1 = o.u1, lh = u1 - u0;
+    const int lh = u1 - u0;
     const int eoff = (u0 + 1) >> 1, ooff = u0 >> 1;
     /* column indices of this lane's pairs: identical for every row */
     int ie[G::ITERS], io[G::ITERS];
@@ -225,14 +229,16 @@ __device__ __forceinline__ void hpass(uint32_t *tiles, const TileCompDesc *tcs, 
             const int item = base + b * NWARPS;
             if (item < nitems) {
                 const int c = item / SH, r = item - c * SH;
-                const RowSrc src = row_source<TYPE>(tcs[tcidx[c]], j, coefA, coefIn, YS + r);
+                const RowTab t = tab[r];
+                const uint32_t *rowL = t.offL >= 0 ? LLp[c] + t.offL : Ap[c] + ~t.offL;
+                const uint32_t *rowH = Ap[c] + t.offH;
 #pragma unroll
                 for (int it = 0; it < G::ITERS; it++) {
                     if (lh > 1) {
-                        Lc[b][it] = src.rowL[ie[it]];
-                        Hc[b][it] = src.rowH[io[it]];
+                        Lc[b][it] = rowL[ie[it]];
+                        Hc[b][it] = rowH[io[it]];
                     } else {
-                        Lc[b][it] = Hc[b][it] = (u0 & 1) ? src.rowH[0] : src.rowL[0];
+                        Lc[b][it] = Hc[b][it] = (u0 & 1) ? rowH[0] : rowL[0];
                     }
                 }
             }
@@ -301,8 +307,12 @@ idwt_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint32_t *_
     const int XA = (o.u0 & ~1) + blockIdx.x * TX, YA = (o.v0 & ~1) + blockIdx.y * TY;
     if (XA >= o.u1 || YA >= o.v1)
         return;
-    const int self = (int)blockIdx.z;
-    hpass<TYPE, SH, 3>(tile, tcs, &self, 1, j, coefA, coefIn, XA, YA - HALO);
+    __shared__ RowTab rowtab[SH];
+    build_rowtab<SH>(rowtab, tc, j, YA - HALO);
+    __syncthreads();
+    const uint32_t *Ap[1] = { coefA + tc.coef_off };
+    const uint32_t *LLp[1] = { j == 0 ? Ap[0] : coefIn + tc.coef_off };
+    hpass<TYPE, SH, 3>(tile, rowtab, Ap, LLp, 1, o.u0, o.u1, XA);
     __syncthreads();
     const int col = threadIdx.x % TX, half = threadIdx.x / TX;
     if (half >= NHALF)
@@ -369,7 +379,7 @@ template <int TYPE> __device__ __forceinline__ int to_pixel(uint32_t raw, int cb
 }
 
 template <int TYPE, int TY>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 4)
 idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__restrict__ groups,
                        const uint32_t *__restrict__ coefA, const uint32_t *__restrict__ coefIn0,
                        const uint32_t *__restrict__ coefIn1, uint8_t *__restrict__ picture,
@@ -392,7 +402,17 @@ idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__
     if (nl > 0) {
         /* LL of the last level is the output of level nl-2: ping-pong parity */
         const uint32_t *in = ((nl - 1) & 1) ? coefIn0 : coefIn1;
-        hpass<TYPE, SH, 4>(dyn, tcs, g.tc, ncomp, nl - 1, coefA, in, XA, YA - HALO);
+        __shared__ RowTab rowtab[SH];
+        build_rowtab<SH>(rowtab, t0, nl - 1, YA - HALO);
+        __shared__ const uint32_t *Ap[J2K_MAX_COMP], *LLp[J2K_MAX_COMP];
+        if (threadIdx.x < J2K_MAX_COMP) {
+            const int c = threadIdx.x;
+            const uint32_t off = tcs[g.tc[c < ncomp ? c : 0]].coef_off;
+            Ap[c] = coefA + off;
+            LLp[c] = nl == 1 ? coefA + off : in + off;
+        }
+        __syncthreads();
+        hpass<TYPE, SH, 4>(dyn, rowtab, Ap, LLp, ncomp, o.u0, o.u1, XA);
         __syncthreads();
         const int col = threadIdx.x % TX, half = threadIdx.x / TX;
         const int lv = o.v1 - o.v0;
@@ -440,10 +460,14 @@ idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__
     }
     const int mct_on = g.mct, wide = g.wide, pstride = g.pixel_stride;
     constexpr int PPR = TX / 2;                   /* pixel pairs per tile row */
-    for (int idx = threadIdx.x; idx < PPR * TY; idx += THREADS) {
-        const int r = idx / PPR, pp = idx - r * PPR;
-        const int X = XA + 2 * pp, Y = YA + r;
-        if (Y < o.v0 || Y >= o.v1 || X + 1 < o.u0 || X >= o.u1)
+    constexpr int RGROUPS = THREADS / PPR;        /* row groups: thread = (pixel pair, row group) */
+    const int pp = threadIdx.x % PPR, rg = threadIdx.x / PPR;
+    const int X = XA + 2 * pp;
+    const bool okA = X >= o.u0 && X < o.u1, okB = X + 1 >= o.u0 && X + 1 < o.u1;
+    const long px = (long)(t0.out_x + X - o.u0) * pstride;          /* sample index of pixel A, component 0 */
+    for (int r = rg; r < TY && rg < RGROUPS && (okA || okB); r += RGROUPS) {
+        const int Y = YA + r;
+        if (Y < o.v0 || Y >= o.v1)
             continue;
         uint32_t a[J2K_MAX_COMP], b[J2K_MAX_COMP];
 #pragma unroll
@@ -475,9 +499,7 @@ idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__
             pa[c] = to_pixel<TYPE>(a[c], cbps[c], shift[c]);
             pb[c] = to_pixel<TYPE>(b[c], cbps[c], shift[c]);
         }
-        const bool okA = X >= o.u0, okB = X + 1 < o.u1;
         uint8_t *row = plane + (size_t)(t0.out_y + Y - o.v0) * rb;
-        const long px = (long)(t0.out_x + X - o.u0) * pstride;      /* sample index of pixel A, component 0 */
         if (wide && ncomp == 3 && pstride == 3 && okA && okB && soff[1] == 1 && soff[2] == 2 &&
             ((reinterpret_cast<uintptr_t>(row) + 2 * px) & 3) == 0) {
             /* rgb48: two pixels = three aligned 32-bit words */
