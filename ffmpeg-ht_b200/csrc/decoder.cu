@@ -10,6 +10,7 @@
  */
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -84,17 +85,111 @@ struct HostBuf {
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+/* How the code-blocks of one frame are spread over the HT kernels.  order[] lists descriptor indices as
+ * [coded | zero | wide | refine]:
+ *   coded   cleanup-only blocks with data, <= 64 samples wide  -> split pipeline (ht_cleanup.cu), sorted by
+ *           shape so that the 32 blocks sharing a warp of the lane-per-block VLC kernel run in step
+ *   zero    blocks without data                                -> zero-filled by the MagSgn kernel
+ *   wide    cleanup-only blocks wider than 64 samples          -> general warp-per-block kernel
+ *   refine  blocks with SigProp / MagRef passes                -> general kernel, refinement variant */
+struct HtPlan {
+    std::vector<uint32_t> order, scr_off;
+    int n_coded = 0, n_zero = 0, n_wide = 0, n_refine = 0;
+    int maxL_fast = 0, maxL_wide = 0, maxL_refine = 0;
+    size_t scratch_words = 0;
+    /* descriptor indices sorted by quad-grid shape; depends on the geometry only */
+    std::vector<uint32_t> by_shape;
+    uint64_t shape_serial = ~0ull;
+
+    void build(const CblkDesc *cblk, size_t n, uint64_t serial)
+    {
+        if (serial != shape_serial || by_shape.size() != n) {
+            std::vector<uint32_t> key(n);
+            by_shape.resize(n);
+            for (size_t i = 0; i < n; i++) {
+                by_shape[i] = (uint32_t)i;
+                key[i] = ((uint32_t)(cblk[i].w + 1) >> 1) << 16 | ((uint32_t)(cblk[i].h + 1) >> 1);
+            }
+            std::stable_sort(by_shape.begin(), by_shape.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
+            shape_serial = serial;
+        }
+        order.resize(n);
+        scr_off.resize(n);
+        n_coded = n_zero = n_wide = n_refine = 0;
+        maxL_fast = maxL_wide = maxL_refine = 0;
+        scratch_words = 0;
+        size_t nz = 0, nw = 0, nr = 0;
+        /* first pass: coded blocks in shape order at the front, count the rest */
+        for (size_t k = 0; k < n; k++) {
+            const uint32_t i = by_shape[k];
+            const CblkDesc &d = cblk[i];
+            scr_off[i] = 0;
+            const bool refine = d.npasses && (d.npasses % 3) != 1;
+            if (refine) {
+                nr++;
+            } else if (d.w > 64) {
+                nw++;
+            } else if (d.npasses == 0) {
+                nz++;
+            } else {
+                order[n_coded++] = i;
+                scr_off[i] = (uint32_t)scratch_words;
+                scratch_words += ht_cleanup_scratch_words(d);
+                if (d.Lcup > maxL_fast) maxL_fast = d.Lcup;
+            }
+        }
+        size_t az = n_coded, aw = az + nz, ar = aw + nw;
+        for (size_t i = 0; i < n; i++) {
+            const CblkDesc &d = cblk[i];
+            const bool refine = d.npasses && (d.npasses % 3) != 1;
+            if (refine) {
+                order[ar++] = (uint32_t)i;
+                if (d.Lcup > maxL_refine) maxL_refine = d.Lcup;
+            } else if (d.w > 64) {
+                order[aw++] = (uint32_t)i;
+                if (d.npasses && d.Lcup > maxL_wide) maxL_wide = d.Lcup;
+            } else if (d.npasses == 0) {
+                order[az++] = (uint32_t)i;
+            }
+        }
+        n_zero = (int)nz;
+        n_wide = (int)nw;
+        n_refine = (int)nr;
+    }
+};
+
+/* queue the HT kernels of one plan; returns launches or < 0 */
+int run_ht(cudaStream_t st, const HtPlan &hp, const CblkDesc *d_cblk, const uint32_t *d_order, const uint32_t *d_scr,
+           const uint8_t *d_bytes, const BandDesc *d_bands, void *scratch, void *coef, int32_t *status, int max_w,
+           int max_area, int max_state, cudaEvent_t after_plain = nullptr)
+{
+    int launches = 0, r;
+    r = launch_ht_cleanup(st, d_cblk, d_order, d_scr, hp.n_coded, hp.n_coded + hp.n_zero, d_bytes, d_bands, scratch, coef,
+                          status, hp.maxL_fast);
+    if (r < 0) return r;
+    launches += r;
+    r = launch_ht_decode(st, false, d_cblk, d_order + hp.n_coded + hp.n_zero, hp.n_wide, d_bytes, d_bands, coef, status,
+                         hp.maxL_wide, max_w, max_area, max_state);
+    if (r < 0) return r;
+    launches += r;
+    if (after_plain) cudaEventRecord(after_plain, st);
+    r = launch_ht_decode(st, true, d_cblk, d_order + hp.n_coded + hp.n_zero + hp.n_wide, hp.n_refine, d_bytes, d_bands,
+                         coef, status, hp.maxL_refine, max_w, max_area, max_state);
+    if (r < 0) return r;
+    return launches + r;
+}
+
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
     Parser parser;
     HostBuf stage;          /* pinned: tables + bytes */
     HostBuf out_stage;      /* pinned: picture when the caller's planes are pageable */
-    DevBuf d_blob, d_coefA, d_coefB, d_coefC, d_picture, d_status;
+    DevBuf d_blob, d_coefA, d_coefB, d_coefC, d_picture, d_status, d_scratch;
+    HtPlan ht;
+    size_t off_scr = 0;
     /* offsets inside the blob */
     size_t off_cblk = 0, off_bands = 0, off_tcs = 0, off_groups = 0, off_order = 0, off_bytes = 0, blob_bytes = 0;
-    int n_plain = 0, n_refine = 0;
-    int maxL_plain = 0, maxL_refine = 0;
     bool busy = false, staged = false;
     size_t h2d_bytes = 0;
     int launches = 0;
@@ -168,26 +263,8 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     Parser &p = s.parser;
     fill_info(p, info);
     const size_t ncb = p.cblk.size();
-    /* split the descriptor list: cleanup-only (and empty) blocks vs blocks with refinement passes */
-    std::vector<uint32_t> order(ncb);
-    s.n_plain = s.n_refine = 0;
-    s.maxL_plain = s.maxL_refine = 0;
-    {
-        size_t a = 0, b = ncb;
-        for (size_t i = 0; i < ncb; i++) {
-            const CblkDesc &d = p.cblk[i];
-            const bool refine = d.npasses && (d.npasses % 3) != 1;
-            if (refine) {
-                order[--b] = (uint32_t)i;
-                if (d.Lcup > s.maxL_refine) s.maxL_refine = d.Lcup;
-            } else {
-                order[a++] = (uint32_t)i;
-                if (d.npasses && d.Lcup > s.maxL_plain) s.maxL_plain = d.Lcup;
-            }
-        }
-        s.n_plain = (int)a;
-        s.n_refine = (int)(ncb - a);
-    }
+    s.ht.build(p.cblk.data(), ncb, p.geom_serial);
+    const std::vector<uint32_t> &order = s.ht.order;
     /* blob layout on the device: [tables][codestream bytes][gathered bytes][64 B zero slack].  The tables
      * always go through the pinned staging buffer; the codestream is DMA'd straight from the caller's
      * packet when that memory is pinned (registered), else it is copied into the staging buffer first. */
@@ -198,6 +275,7 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     s.off_tcs = off;    off = align_up(off + p.tcs.size() * sizeof(TileCompDesc), 256);
     s.off_groups = off; off = align_up(off + p.groups.size() * sizeof(PackGroup), 256);
     s.off_order = off;  off = align_up(off + ncb * sizeof(uint32_t), 256);
+    s.off_scr = off;    off = align_up(off + ncb * sizeof(uint32_t), 256);
     s.off_bytes = off;
     const size_t tail = p.extra.size() + 64;              /* gathered bytes + slack, placed behind the codestream */
     const size_t off_tail = s.off_bytes + (size_t)size;
@@ -213,6 +291,7 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     memcpy(h + s.off_tcs, p.tcs.data(), p.tcs.size() * sizeof(TileCompDesc));
     memcpy(h + s.off_groups, p.groups.data(), p.groups.size() * sizeof(PackGroup));
     memcpy(h + s.off_order, order.data(), ncb * sizeof(uint32_t));
+    memcpy(h + s.off_scr, s.ht.scr_off.data(), ncb * sizeof(uint32_t));
     uint8_t *htail = direct_in ? h + s.off_bytes : h + off_tail;
     if (!direct_in)
         memcpy(h + s.off_bytes, pkt, (size_t)size);
@@ -228,6 +307,7 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     }
     if ((ret = s.d_picture.ensure(p.picture_bytes + 256)) < 0) return ret;
     if ((ret = s.d_status.ensure(ncb * 4 + 256)) < 0) return ret;
+    if ((ret = s.d_scratch.ensure(s.ht.scratch_words * 4 + 256)) < 0) return ret;
     uint8_t *dblob = (uint8_t *)s.d_blob.p;
     cudaError_t e;
     if (direct_in) {
@@ -259,13 +339,8 @@ int run_kernels(Slot &s, cudaEvent_t *ev = nullptr)
     const uint8_t *d_bytes = blob + s.off_bytes;
     int launches = 0, r;
     if (ev) cudaEventRecord(ev[0], s.stream);
-    r = launch_ht_decode(s.stream, false, d_cblk, d_order, s.n_plain, d_bytes, d_bands, s.d_coefA.p,
-                         (int32_t *)s.d_status.p, s.maxL_plain, (int)p.max_w, (int)p.max_area, (int)p.max_state);
-    if (r < 0) return B200J2K_ERR_DEVICE;
-    launches += r;
-    if (ev) cudaEventRecord(ev[1], s.stream);
-    r = launch_ht_decode(s.stream, true, d_cblk, d_order + s.n_plain, s.n_refine, d_bytes, d_bands, s.d_coefA.p,
-                         (int32_t *)s.d_status.p, s.maxL_refine, (int)p.max_w, (int)p.max_area, (int)p.max_state);
+    r = run_ht(s.stream, s.ht, d_cblk, d_order, (const uint32_t *)(blob + s.off_scr), d_bytes, d_bands, s.d_scratch.p,
+               s.d_coefA.p, (int32_t *)s.d_status.p, (int)p.max_w, (int)p.max_area, (int)p.max_state, ev ? ev[1] : nullptr);
     if (r < 0) return B200J2K_ERR_DEVICE;
     launches += r;
     if (ev) cudaEventRecord(ev[2], s.stream);
@@ -392,7 +467,7 @@ void b200j2k_destroy(b200j2k_decoder *d)
         s.stage.release();
         s.out_stage.release();
         s.d_blob.release(); s.d_coefA.release(); s.d_coefB.release(); s.d_coefC.release();
-        s.d_picture.release(); s.d_status.release();
+        s.d_picture.release(); s.d_status.release(); s.d_scratch.release();
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -577,13 +652,11 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
     if (n <= 0)
         return 0;
     std::vector<CblkDesc> descs(n);
-    std::vector<uint32_t> order(n);
     BandDesc band;
     memset(&band, 0, sizeof(band));
     band.i_stepsize = 32768;
     size_t total = 0;
-    int maxw = 1, max_area = 1, max_state = 16, maxL[2] = { 0, 0 };
-    size_t a = 0, b = n;
+    int maxw = 1, max_area = 1, max_state = 16;
     for (int i = 0; i < n; i++) {
         const int32_t *q = par + 10 * i;
         CblkDesc &d = descs[i];
@@ -594,9 +667,11 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
         d.zbp = (uint8_t)q[3];
         d.w = (uint16_t)q[4];
         d.h = (uint16_t)q[5];
-        d.M_b = 31;                  /* downshift 0 + identity step: the raw sign-magnitude word survives */
-        d.roi_shift = 0;
-        d.flags = (uint8_t)((q[8] ? 1 : 0) | (3 << 1));   /* dequant mode 3 = raw (see below) */
+        /* the stage-level entry wants t1->data, i.e. the sample BEFORE dequantisation but after the ROI
+         * shift: dequant mode 3 = raw (handled in the kernels) */
+        d.M_b = (uint8_t)q[6];
+        d.roi_shift = (uint8_t)q[7];
+        d.flags = (uint8_t)((q[8] ? 1 : 0) | (3 << 1));
         d.data_off = (uint32_t)q[9];
         d.length = (uint32_t)(q[1] + q[2]);
         d.dst_off = (uint32_t)total;
@@ -605,40 +680,34 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
         if (d.w > maxw) maxw = d.w;
         if (d.w * d.h > max_area) max_area = d.w * d.h;
         if ((d.w + 3) * (d.h + 3) > max_state) max_state = (d.w + 3) * (d.h + 3);
-        const bool refine = d.npasses && (d.npasses % 3) != 1;
-        if (refine) order[--b] = (uint32_t)i; else order[a++] = (uint32_t)i;
-        if (d.npasses && d.Lcup > maxL[refine]) maxL[refine] = d.Lcup;
         if ((int64_t)d.data_off + d.length > data_size)
             return B200J2K_ERR_EINVAL;
     }
-    /* the stage-level entry wants t1->data, i.e. the sample BEFORE dequantisation but after the ROI shift:
-     * run with M_b/roi of the caller and an identity "dequant" (mode 3, handled as raw in the kernel) */
-    for (int i = 0; i < n; i++) {
-        descs[i].M_b = (uint8_t)par[10 * i + 6];
-        descs[i].roi_shift = (uint8_t)par[10 * i + 7];
-    }
+    HtPlan hp;
+    hp.build(descs.data(), (size_t)n, 0);
     uint8_t *d_bytes = nullptr;
     CblkDesc *d_descs = nullptr;
-    uint32_t *d_order = nullptr, *d_out = nullptr;
+    uint32_t *d_order = nullptr, *d_scr = nullptr, *d_out = nullptr, *d_scratch = nullptr;
     BandDesc *d_band = nullptr;
     int32_t *d_status = nullptr;
     int ret = 0;
     cudaStream_t st = nullptr;
     if (cudaStreamCreate(&st) != cudaSuccess) return B200J2K_ERR_DEVICE;
     if (cudaMalloc(&d_bytes, (size_t)data_size + 64) != cudaSuccess || cudaMalloc(&d_descs, n * sizeof(CblkDesc)) != cudaSuccess ||
-        cudaMalloc(&d_order, n * 4) != cudaSuccess || cudaMalloc(&d_out, total * 4 + 4) != cudaSuccess ||
+        cudaMalloc(&d_order, n * 4) != cudaSuccess || cudaMalloc(&d_scr, n * 4) != cudaSuccess ||
+        cudaMalloc(&d_out, total * 4 + 4) != cudaSuccess || cudaMalloc(&d_scratch, hp.scratch_words * 4 + 256) != cudaSuccess ||
         cudaMalloc(&d_band, sizeof(BandDesc)) != cudaSuccess || cudaMalloc(&d_status, n * 4) != cudaSuccess) {
         ret = B200J2K_ERR_NOMEM;
     } else {
         cudaMemsetAsync(d_bytes, 0, (size_t)data_size + 64, st);
         cudaMemcpyAsync(d_bytes, data, (size_t)data_size, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_descs, descs.data(), n * sizeof(CblkDesc), cudaMemcpyHostToDevice, st);
-        cudaMemcpyAsync(d_order, order.data(), n * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_order, hp.order.data(), n * 4, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_scr, hp.scr_off.data(), n * 4, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_band, &band, sizeof(band), cudaMemcpyHostToDevice, st);
         cudaMemsetAsync(d_out, 0x55, total * 4 + 4, st);
-        int r1 = launch_ht_decode(st, false, d_descs, d_order, (int)a, d_bytes, d_band, d_out, d_status, maxL[0], maxw, max_area, max_state);
-        int r2 = launch_ht_decode(st, true, d_descs, d_order + a, (int)(n - a), d_bytes, d_band, d_out, d_status, maxL[1], maxw, max_area, max_state);
-        if (r1 < 0 || r2 < 0) ret = B200J2K_ERR_DEVICE;
+        if (run_ht(st, hp, d_descs, d_order, d_scr, d_bytes, d_band, d_scratch, d_out, d_status, maxw, max_area, max_state) < 0)
+            ret = B200J2K_ERR_DEVICE;
         cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, st);
         if (status) cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
@@ -647,7 +716,8 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
             ret = B200J2K_ERR_DEVICE;
         }
     }
-    cudaFree(d_bytes); cudaFree(d_descs); cudaFree(d_order); cudaFree(d_out); cudaFree(d_band); cudaFree(d_status);
+    cudaFree(d_bytes); cudaFree(d_descs); cudaFree(d_order); cudaFree(d_scr); cudaFree(d_out); cudaFree(d_scratch);
+    cudaFree(d_band); cudaFree(d_status);
     cudaStreamDestroy(st);
     return ret;
 }

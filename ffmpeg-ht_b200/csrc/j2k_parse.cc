@@ -1105,6 +1105,7 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
             return ret;
         geom_key_.assign(pkt, pkt + mh);
         geom_flags_ = flags;
+        geom_serial++;
     }
     /* per-frame tier-2 state */
     state_.assign(cblk_template_.size(), CblkState{});

@@ -108,6 +108,7 @@ public:
     uint32_t max_area = 0, max_state = 0;  /* largest w*h and (w+3)*(h+3) */
     uint32_t max_Lcup = 0, max_Lref = 0;
     int any_refine = 0;
+    uint64_t geom_serial = 0;         /* bumped whenever the geometry tables were rebuilt */
 
     /* flags: B200J2K_FLAG_* ; headers_only: stop after the marker segments */
     int parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only);
