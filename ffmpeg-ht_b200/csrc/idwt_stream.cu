@@ -1,0 +1,621 @@
+/*
+ * idwt_stream.cu -- register-streaming inverse DWT for sm_100a: the fast path of ff_dwt_decode
+ * (libavcodec/jpeg2000dwt.c:309-537, :601-620), fused at the last level with mct_decode
+ * (libavcodec/jpeg2000dec.c:2183-2209, jpeg2000dsp.c:43-91) and write_frame_16 (jpeg2000dec.c:2301-2366).
+ * SURVEY.md section 8(a) rows W1-W4, M1-M3, P1.
+ *
+ * ncu on the shared-memory tiled kernel (idwt.cu; profiles/r1_ncu_full_v1_summary.md) showed it bound by
+ * instruction issue (60 % of issue slots, ~52 instructions per sample), not by HBM.  This kernel removes
+ * the shared-memory round trips and most of the per-sample addressing:
+ *   - a warp owns a strip of 32 x 2NP columns and walks down SEG output rows;
+ *   - per row each lane loads NP low-pass and NP high-pass coefficients per component with ONE 128-bit
+ *     (NP = 4) or 64-bit (NP = 2) load each -- the Mallat quadrants are read as coalesced row segments;
+ *   - horizontal synthesis runs in registers, neighbours across lanes come from one shuffle per lifting
+ *     step; the first and last lane of the warp are apron;
+ *   - vertical synthesis is a sliding window over the rows: 2 (5/3) or 4 (9/7) state values per column
+ *     stay in registers, so every coefficient is read once and no intermediate ever leaves the SM;
+ *   - the last level applies RCT / ICT, level shift, clip and packs rgb48 / gray16 with 128-bit stores.
+ * Rows before columns at every level (quirk Q7), uint32 wrap-around 5/3 arithmetic and un-contracted fp32
+ * 9/7 arithmetic exactly as idwt.cu.  Geometry the fast path does not cover (odd origins, unaligned
+ * strides, one-sample lines, 8-bit or planar output) stays on idwt.cu; launch_idwt_frame picks per launch.
+ */
+#include "idwt_common.cuh"
+
+namespace b200j2k {
+
+namespace {
+
+constexpr int SWARPS = 4;                 /* warps (independent strips) per CTA */
+
+template <int NP> struct VecIO;
+template <> struct VecIO<4> {
+    static __device__ __forceinline__ void load(const uint32_t *p, uint32_t (&v)[4])
+    {
+        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    }
+};
+template <> struct VecIO<2> {
+    static __device__ __forceinline__ void load(const uint32_t *p, uint32_t (&v)[2])
+    {
+        const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
+        v[0] = t.x; v[1] = t.y;
+    }
+};
+
+constexpr int STAGES = 4;                 /* row pairs in flight per warp (cp.async groups) */
+
+template <int NP> __device__ __forceinline__ void cp_async_vec(uint32_t dst, const uint32_t *src)
+{
+    if (NP == 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+template <int NP> __device__ __forceinline__ void lds_vec(uint32_t addr, uint32_t (&v)[NP]);
+template <> __device__ __forceinline__ void lds_vec<4>(uint32_t addr, uint32_t (&v)[4])
+{
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(addr) : "memory");
+}
+template <> __device__ __forceinline__ void lds_vec<2>(uint32_t addr, uint32_t (&v)[2])
+{
+    asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr) : "memory");
+}
+/* bytes of staging shared memory per warp */
+template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_warp() { return STAGES * 4 * NC * 32 * NP * 4; }
+
+/* horizontal synthesis of NP (low, high) pairs per lane; x[2k] = even sample, x[2k+1] = odd sample */
+template <int TYPE, int NP>
+__device__ __forceinline__ void hsyn(const uint32_t (&Lc)[NP], const uint32_t (&Hc)[NP], uint32_t (&x)[2 * NP])
+{
+    using L = Lift<TYPE>;
+    if (TYPE == J2K_DWT53) {
+        const uint32_t hl = __shfl_up_sync(FULLMASK, Hc[NP - 1], 1);
+        uint32_t e[NP + 1];
+#pragma unroll
+        for (int k = 0; k < NP; k++)
+            e[k] = L::apply(0, Lc[k], k ? Hc[k ? k - 1 : 0] : hl, Hc[k]);
+        e[NP] = __shfl_down_sync(FULLMASK, e[0], 1);
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            x[2 * k] = e[k];
+            x[2 * k + 1] = L::apply(1, Hc[k], e[k], e[k + 1]);
+        }
+    } else {
+        const uint32_t hl = __shfl_up_sync(FULLMASK, Hc[NP - 1], 1);
+        uint32_t e1[NP + 1], o1[NP], e2[NP + 1];
+#pragma unroll
+        for (int k = 0; k < NP; k++)
+            e1[k] = L::apply(0, Lc[k], k ? Hc[k ? k - 1 : 0] : hl, Hc[k]);
+        e1[NP] = __shfl_down_sync(FULLMASK, e1[0], 1);
+#pragma unroll
+        for (int k = 0; k < NP; k++)
+            o1[k] = L::apply(1, Hc[k], e1[k], e1[k + 1]);
+        const uint32_t ol = __shfl_up_sync(FULLMASK, o1[NP - 1], 1);
+#pragma unroll
+        for (int k = 0; k < NP; k++)
+            e2[k] = L::apply(2, e1[k], k ? o1[k ? k - 1 : 0] : ol, o1[k]);
+        e2[NP] = __shfl_down_sync(FULLMASK, e2[0], 1);
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            x[2 * k] = e2[k];
+            x[2 * k + 1] = L::apply(3, o1[k], e2[k], e2[k + 1]);
+        }
+    }
+}
+
+/* geometry of one (tile-component, level) seen by a warp */
+struct StripGeo {
+    int u0, u1, v0, v1;
+    int nLh, nLv, W, LLstride;
+    int eoff, ooff;     /* ceil(u0/2), floor(u0/2) */
+    int eoffv, ooffv;   /* ceil(v0/2), floor(v0/2) */
+};
+
+__device__ __forceinline__ StripGeo make_geo(const TileCompDesc &tc, int j)
+{
+    const LevelDesc o = tc.lev[j + 1];
+    StripGeo g;
+    g.u0 = o.u0; g.u1 = o.u1; g.v0 = o.v0; g.v1 = o.v1;
+    g.nLh = ((o.u1 + 1) >> 1) - ((o.u0 + 1) >> 1);
+    g.nLv = ((o.v1 + 1) >> 1) - ((o.v0 + 1) >> 1);
+    g.W = tc.width;
+    g.LLstride = j == 0 ? tc.width : g.nLh;
+    g.eoff = (o.u0 + 1) >> 1;
+    g.ooff = o.u0 >> 1;
+    g.eoffv = (o.v0 + 1) >> 1;
+    g.ooffv = o.v0 >> 1;
+    return g;
+}
+
+/* element offsets of the low-pass / high-pass halves of absolute row Y: offL < 0 means ~offL into the
+ * plane (LH band), else into the LL source; offH into the plane (HL or HH band) */
+__device__ __forceinline__ void row_offsets(const StripGeo &g, int Y, int &offL, int &offH)
+{
+    const int Yr = (Y >= g.v0 && Y < g.v1) ? Y : reflect(Y, g.v0, g.v1);
+    const int ky = band_index(Yr, g.v0);
+    if (Yr & 1) {
+        offL = ~((g.nLv + ky) * g.W);
+        offH = (g.nLv + ky) * g.W + g.nLh;
+    } else {
+        offL = ky * g.LLstride;
+        offH = ky * g.W + g.nLh;
+    }
+}
+
+/* per-lane column bookkeeping: fixed for all rows of the strip */
+template <int NP> struct LaneCols {
+    bool inside;        /* all 2NP samples inside [u0,u1): vector loads */
+    int vcolL, vcolH;   /* first column inside the low / high band */
+    int ie[NP], io[NP]; /* reflected columns (border lanes) */
+};
+
+template <int NP>
+__device__ __forceinline__ LaneCols<NP> make_cols(const StripGeo &g, int p0)
+{
+    LaneCols<NP> lc;
+    lc.inside = 2 * p0 >= g.u0 && 2 * (p0 + NP - 1) + 1 < g.u1;
+    lc.vcolL = p0 - g.eoff;
+    lc.vcolH = p0 - g.ooff;
+#pragma unroll
+    for (int k = 0; k < NP; k++) {
+        int Xe = 2 * (p0 + k), Xo = Xe + 1;
+        if (Xe < g.u0 || Xe >= g.u1) Xe = reflect(Xe, g.u0, g.u1);
+        if (Xo < g.u0 || Xo >= g.u1) Xo = reflect(Xo, g.u0, g.u1);
+        /* reflection preserves parity: an even position stays in the low band, an odd one in the high band */
+        lc.ie[k] = (Xe >> 1) - g.eoff;
+        lc.io[k] = (Xo >> 1) - g.ooff;
+    }
+    return lc;
+}
+
+template <int NP>
+__device__ __forceinline__ void load_row(const uint32_t *rowL, const uint32_t *rowH, const LaneCols<NP> &lc,
+                                         uint32_t (&Lc)[NP], uint32_t (&Hc)[NP])
+{
+    if (lc.inside) {
+        VecIO<NP>::load(rowL + lc.vcolL, Lc);
+        VecIO<NP>::load(rowH + lc.vcolH, Hc);
+    } else {
+#pragma unroll
+        for (int k = 0; k < NP; k++) {
+            Lc[k] = rowL[lc.ie[k]];
+            Hc[k] = rowH[lc.io[k]];
+        }
+    }
+}
+
+/* vertical lifting state of one lane: per component and column the values the next row pair needs */
+template <int TYPE, int NC, int C2> struct VState {
+    uint32_t vh[NC][C2], e1[NC][C2];
+    uint32_t o1[TYPE == J2K_DWT53 ? 1 : NC][TYPE == J2K_DWT53 ? 1 : C2];
+    uint32_t e2[TYPE == J2K_DWT53 ? 1 : NC][TYPE == J2K_DWT53 ? 1 : C2];
+};
+
+/* band_index of the (reflected) absolute row Y */
+__device__ __forceinline__ int row_ky(const StripGeo &g, int Y)
+{
+    const int Yr = (Y >= g.v0 && Y < g.v1) ? Y : reflect(Y, g.v0, g.v1);
+    return band_index(Yr, g.v0);
+}
+
+/* The streaming core: walks row pairs (even row = vertical low-pass, odd row = vertical high-pass), keeps the
+ * vertical lifting state in registers and calls emit(Y, rows[NC][2NP]) for every finished output row.  The
+ * loop is unrolled by two with the state ping-ponging between two register sets, so the sliding window never
+ * costs a register move. */
+template <int TYPE, int NP, int NC, class Emit>
+__device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *(&A)[NC], const uint32_t *(&LL)[NC],
+                                            const LaneCols<NP> &lc, int Ya, int Yb, uint32_t stage_base, Emit &&emit)
+{
+    using L = Lift<TYPE>;
+    constexpr int HP = L::HALO / 2;
+    constexpr int C2 = 2 * NP;
+    constexpr int NV = 4 * NC;
+    constexpr uint32_t VSTRIDE = 32 * NP * 4, SSTRIDE = NV * VSTRIDE;
+    VState<TYPE, NC, C2> S0, S1;
+#pragma unroll
+    for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int k = 0; k < C2; k++) {
+            S0.vh[c][k] = S0.e1[c][k] = 0;
+            if (TYPE != J2K_DWT53)
+                S0.o1[c][k] = S0.e2[c][k] = 0;
+        }
+    const int n0 = (Ya >> 1) - HP, n1 = (Yb >> 1) + HP;     /* iterations [n0, n1) */
+    const int Ylo = max(Ya, g.v0), Yhi = min(Yb, g.v1);     /* rows this warp emits */
+    /* the four quadrant streams of every component, already offset to this lane's first column */
+    const uint32_t *pLL[NC], *pHL[NC], *pLH[NC], *pHH[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        pLL[c] = LL[c] + lc.vcolL;
+        pHL[c] = A[c] + g.nLh + lc.vcolH;
+        pLH[c] = A[c] + (size_t)g.nLv * g.W + lc.vcolL;
+        pHH[c] = A[c] + (size_t)g.nLv * g.W + g.nLh + lc.vcolH;
+    }
+    /* Asynchronous staging: every lane owns NV vector slots per stage in shared memory and fills them with
+     * cp.async STAGES-1 iterations ahead, so the bytes in flight do not cost registers.  A lane only ever
+     * reads back its own slots: no barrier, no bank conflicts.  Border lanes (columns that need reflection)
+     * load synchronously when the row pair is consumed. */
+    auto issue = [&](int n) {
+        if (n < n1 && lc.inside) {
+            /* band_index() of rows 2n / 2n+1 is n - ceil(v0/2) / n - floor(v0/2) unless a row needs reflection */
+            int kyE = n - g.eoffv, kyO = n - g.ooffv;
+            if (2 * n < g.v0 || 2 * n >= g.v1)
+                kyE = row_ky(g, 2 * n);
+            if (2 * n + 1 < g.v0 || 2 * n + 1 >= g.v1)
+                kyO = row_ky(g, 2 * n + 1);
+            const uint32_t st = stage_base + (uint32_t)((n - n0) & (STAGES - 1)) * SSTRIDE;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                cp_async_vec<NP>(st + (4 * c + 0) * VSTRIDE, pLL[c] + kyE * g.LLstride);
+                cp_async_vec<NP>(st + (4 * c + 1) * VSTRIDE, pHL[c] + kyE * g.W);
+                cp_async_vec<NP>(st + (4 * c + 2) * VSTRIDE, pLH[c] + kyO * g.W);
+                cp_async_vec<NP>(st + (4 * c + 3) * VSTRIDE, pHH[c] + kyO * g.W);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto step = [&](int n, const VState<TYPE, NC, C2> &in, VState<TYPE, NC, C2> &out) {
+        issue(n + STAGES - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        uint32_t cLe[NC][NP], cHe[NC][NP], cLo[NC][NP], cHo[NC][NP];
+        if (lc.inside) {
+            const uint32_t st = stage_base + (uint32_t)((n - n0) & (STAGES - 1)) * SSTRIDE;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                lds_vec<NP>(st + (4 * c + 0) * VSTRIDE, cLe[c]);
+                lds_vec<NP>(st + (4 * c + 1) * VSTRIDE, cHe[c]);
+                lds_vec<NP>(st + (4 * c + 2) * VSTRIDE, cLo[c]);
+                lds_vec<NP>(st + (4 * c + 3) * VSTRIDE, cHo[c]);
+            }
+        } else {
+            int oL, oH;
+            row_offsets(g, 2 * n, oL, oH);
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+                load_row<NP>(oL >= 0 ? LL[c] + oL : A[c] + ~oL, A[c] + oH, lc, cLe[c], cHe[c]);
+            row_offsets(g, 2 * n + 1, oL, oH);
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+                load_row<NP>(oL >= 0 ? LL[c] + oL : A[c] + ~oL, A[c] + oH, lc, cLo[c], cHo[c]);
+        }
+        uint32_t rowA[NC][C2];                   /* finished odd row 2n-(2HP-1); the even row 2n-(2HP-2) is out.e1 / out.e2 */
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            uint32_t lo[C2];
+            hsyn<TYPE, NP>(cLe[c], cHe[c], lo);
+            hsyn<TYPE, NP>(cLo[c], cHo[c], out.vh[c]);
+#pragma unroll
+            for (int k = 0; k < C2; k++) {
+                if (TYPE == J2K_DWT53) {
+                    out.e1[c][k] = L::apply(0, lo[k], in.vh[c][k], out.vh[c][k]);
+                    rowA[c][k] = L::apply(1, in.vh[c][k], in.e1[c][k], out.e1[c][k]);
+                } else {
+                    out.e1[c][k] = L::apply(0, lo[k], in.vh[c][k], out.vh[c][k]);
+                    out.o1[c][k] = L::apply(1, in.vh[c][k], in.e1[c][k], out.e1[c][k]);
+                    out.e2[c][k] = L::apply(2, in.e1[c][k], in.o1[c][k], out.o1[c][k]);
+                    rowA[c][k] = L::apply(3, in.o1[c][k], in.e2[c][k], out.e2[c][k]);
+                }
+            }
+        }
+        const int YA = 2 * n - (2 * HP - 1), YB = YA + 1;
+        if (YA >= Ylo && YA < Yhi)
+            emit(YA, rowA);
+        if (YB >= Ylo && YB < Yhi) {
+            if constexpr (TYPE == J2K_DWT53)
+                emit(YB, out.e1);
+            else
+                emit(YB, out.e2);
+        }
+    };
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; s++)
+        issue(n0 + s);
+    int n = n0;
+    for (; n + 1 < n1; n += 2) {
+        step(n, S0, S1);
+        step(n + 1, S1, S0);
+    }
+    if (n < n1)
+        step(n, S0, S1);
+}
+
+/* ---- intermediate level: reconstructed resolution -> compact ping-pong buffer -------------------------- */
+template <int TYPE, int NP>
+__global__ void __launch_bounds__(SWARPS * 32)
+idwt_stream_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint32_t *__restrict__ coefA,
+                         const uint32_t *__restrict__ coefIn, uint32_t *__restrict__ coefOut, int strips, int SEG)
+{
+    extern __shared__ __align__(16) uint32_t stage_smem[];
+    constexpr int C2 = 2 * NP, VALID = 30 * C2;
+    const TileCompDesc &tc = tcs[blockIdx.y];
+    if (tc.transform != TYPE || j >= tc.nlevels - 1)
+        return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x * SWARPS + warp;
+    const int strip = unit % strips, seg = unit / strips;
+    const StripGeo g = make_geo(tc, j);
+    const int XA = (g.u0 & ~1) + strip * VALID - C2;          /* first column of lane 0 (apron lane) */
+    const int Ya = (g.v0 & ~1) + seg * SEG, Yb = min(Ya + SEG, (g.v1 + 1) & ~1);
+    if (XA + C2 >= g.u1 || Ya >= g.v1)
+        return;
+    const int p0 = (XA >> 1) + lane * NP;
+    const LaneCols<NP> lc = make_cols<NP>(g, p0);
+    const uint32_t *A[1] = { coefA + tc.coef_off };
+    const uint32_t *LL[1] = { j == 0 ? A[0] : coefIn + tc.coef_off };
+    uint32_t *out = coefOut + tc.coef_off;
+    const int lh = g.u1 - g.u0;
+    const int X0 = 2 * p0;
+    const bool lane_ok = lane >= 1 && lane <= 30;
+    uint32_t *out_base = out + (X0 - g.u0) - (long)g.v0 * lh;
+    auto emit = [&](int Y, const uint32_t (&row)[1][C2]) {
+        if (!lane_ok)
+            return;
+        uint32_t *o = out_base + (long)Y * lh;
+        if (lc.inside) {
+            if (NP == 4) {
+                reinterpret_cast<uint4 *>(o)[0] = make_uint4(row[0][0], row[0][1], row[0][2], row[0][3]);
+                reinterpret_cast<uint4 *>(o)[1] = make_uint4(row[0][4], row[0][5], row[0][6], row[0][7]);
+            } else {
+                reinterpret_cast<uint4 *>(o)[0] = make_uint4(row[0][0], row[0][1], row[0][2], row[0][3]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < C2; k++)
+                if (X0 + k >= g.u0 && X0 + k < g.u1)
+                    o[k] = row[0][k];
+        }
+    };
+    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage_smem) + warp * stage_bytes_per_warp<NP, 1>() +
+                                lane * (NP * 4);
+    stream_rows<TYPE, NP, 1>(g, A, LL, lc, Ya, Yb, stage_base, emit);
+}
+
+/* ---- last level fused with MCT + level shift + clip + pack (packed 16-bit output) ---------------------- */
+template <int TYPE, int NP, int NC>
+__global__ void __launch_bounds__(SWARPS * 32, NP == 4 ? 2 : (TYPE == J2K_DWT53 ? 4 : 3))
+idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__restrict__ groups,
+                         const uint32_t *__restrict__ coefA, const uint32_t *__restrict__ coefIn0,
+                         const uint32_t *__restrict__ coefIn1, uint8_t *__restrict__ picture,
+                         uint64_t po0, uint64_t po1, uint64_t po2, uint64_t po3, int rb0, int rb1, int rb2, int rb3,
+                         int strips, int SEG)
+{
+    extern __shared__ __align__(16) uint32_t stage_smem[];
+    constexpr int C2 = 2 * NP, VALID = 30 * C2;
+    const PackGroup &gr = groups[blockIdx.y];
+    const TileCompDesc &t0 = tcs[gr.tc[0]];
+    if (t0.transform != TYPE || gr.ncomp != NC)
+        return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int unit = blockIdx.x * SWARPS + warp;
+    const int strip = unit % strips, seg = unit / strips;
+    const int nl = t0.nlevels;
+    const StripGeo g = make_geo(t0, nl - 1);
+    const int XA = (g.u0 & ~1) + strip * VALID - C2;
+    const int Ya = (g.v0 & ~1) + seg * SEG, Yb = min(Ya + SEG, (g.v1 + 1) & ~1);
+    if (XA + C2 >= g.u1 || Ya >= g.v1)
+        return;
+    const int p0 = (XA >> 1) + lane * NP;
+    const LaneCols<NP> lc = make_cols<NP>(g, p0);
+    const uint32_t *in = ((nl - 1) & 1) ? coefIn0 : coefIn1;
+    const uint32_t *A[NC], *LL[NC];
+    int cbps[NC], shift[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        const TileCompDesc &tc = tcs[gr.tc[c]];
+        A[c] = coefA + tc.coef_off;
+        LL[c] = nl == 1 ? A[c] : in + tc.coef_off;
+        cbps[c] = tc.cbps;
+        shift[c] = gr.shift[c];
+    }
+    const uint64_t poff = gr.plane == 0 ? po0 : gr.plane == 1 ? po1 : gr.plane == 2 ? po2 : po3;
+    const int rb = gr.plane == 0 ? rb0 : gr.plane == 1 ? rb1 : gr.plane == 2 ? rb2 : rb3;
+    uint8_t *plane = picture + poff;
+    const int mct_on = gr.mct;
+    const int X0 = 2 * p0;
+    const bool lane_ok = lane >= 1 && lane <= 30;
+    const long px = (long)(t0.out_x + X0 - g.u0) * NC;       /* sample index of the lane's first pixel */
+    int half[NC], vmax[NC];
+    bool same_shift = true;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        half[c] = 1 << (cbps[c] - 1);
+        vmax[c] = (1 << cbps[c]) - 1;
+        same_shift = same_shift && shift[c] == shift[0];
+    }
+    /* byte address of this lane's first sample in output row Y = out_base + Y * rb */
+    uint8_t *out_base = plane + ((long)t0.out_y - g.v0) * rb + 2 * px;
+    auto emit = [&](int Y, const uint32_t (&row)[NC][C2]) {
+        if (!lane_ok)
+            return;
+        uint32_t pix[NC][C2];                    /* level-shifted and clipped, not yet left-aligned */
+#pragma unroll
+        for (int k = 0; k < C2; k++) {
+            uint32_t v[NC];
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                v[c] = row[c][k];
+                if (TYPE == J2K_DWT97_INT)       /* undo I_PRESHIFT before the component transform (jpeg2000dwt.c:534-536) */
+                    v[c] = (uint32_t)((int32_t)((int64_t)(int32_t)v[c] + 128) >> 8);
+            }
+            if (NC == 3 && mct_on)
+                mct<TYPE>(v[0], v[NC > 1 ? 1 : 0], v[NC > 2 ? 2 : 0]);
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const int val = TYPE == J2K_DWT97 ? __float2int_rn(__uint_as_float(v[c])) : (int32_t)v[c];
+                pix[c][k] = (uint32_t)__viaddmin_s32_relu(val, half[c], vmax[c]);    /* clip(val + half, 0, max) */
+            }
+        }
+        uint16_t *r16 = reinterpret_cast<uint16_t *>(out_base + (long)Y * rb);
+        if (lc.inside) {
+            /* 2NP pixels x NC samples x 16 bit: 16-byte (NP = 4) or 8-byte (NP = 2) aligned by construction */
+            uint32_t w[NC * NP];
+#pragma unroll
+            for (int i = 0; i < NC * NP; i++) {
+                const int s0 = 2 * i, s1 = 2 * i + 1;            /* sample indices inside the lane's run */
+                if (same_shift)
+                    w[i] = __byte_perm(pix[s0 % NC][s0 / NC], pix[s1 % NC][s1 / NC], 0x5410) << shift[0];
+                else
+                    w[i] = (pix[s0 % NC][s0 / NC] << shift[s0 % NC]) | (pix[s1 % NC][s1 / NC] << (16 + shift[s1 % NC]));
+            }
+            if (NP == 4) {
+                uint4 *o = reinterpret_cast<uint4 *>(r16);
+#pragma unroll
+                for (int i = 0; i < NC * NP / 4; i++)
+                    o[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
+            } else {                                              /* a lane's run is 8 or 24 bytes: 8-byte aligned */
+                uint2 *o = reinterpret_cast<uint2 *>(r16);
+#pragma unroll
+                for (int i = 0; i < NC * NP / 2; i++)
+                    o[i] = make_uint2(w[2 * i], w[2 * i + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < C2; k++)
+                if (X0 + k >= g.u0 && X0 + k < g.u1)
+#pragma unroll
+                    for (int c = 0; c < NC; c++)
+                        r16[k * NC + c] = (uint16_t)(pix[c][k] << shift[c]);
+        }
+    };
+    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage_smem) + warp * stage_bytes_per_warp<NP, NC>() +
+                                lane * (NP * 4);
+    stream_rows<TYPE, NP, NC>(g, A, LL, lc, Ya, Yb, stage_base, emit);
+}
+
+template <int TYPE> struct StreamCfg {
+#ifndef STREAM_NP53
+#define STREAM_NP53 2
+#endif
+    static constexpr int NP = TYPE == J2K_DWT53 ? STREAM_NP53 : 2;
+};
+/* rows per warp: enough warps to fill the GPU (148 SMs x 8 resident warps), but not so few rows that the
+ * HALO warm-up rows dominate */
+int pick_seg(int strips, int units_z, int rows)
+{
+    const long want = 148L * 16;
+    long seg = ((long)rows * strips * units_z + want - 1) / want;
+    seg = (seg + 1) & ~1L;
+    if (seg < 8) seg = 8;
+    if (seg > 64) seg = 64;
+    return (int)seg;
+}
+
+/* can the fast path reconstruct level j of this tile-component?  (even origin, lines longer than one
+ * sample, 16-byte aligned band rows) */
+bool level_streamable(const TileCompDesc &tc, int j)
+{
+    const LevelDesc &o = tc.lev[j + 1];
+    const int lh = o.u1 - o.u0, lv = o.v1 - o.v0;
+    if (lh <= 1 || lv <= 1)
+        return false;
+    if (o.u0 & 1)
+        return false;
+    const int nLh = ((o.u1 + 1) >> 1) - ((o.u0 + 1) >> 1);
+    const int LLstride = j == 0 ? tc.width : nLh;
+    if ((tc.width & 3) || (nLh & 3) || (LLstride & 3) || (tc.coef_off & 3))
+        return false;
+    return true;
+}
+
+}  // namespace
+
+bool idwt_stream_levels_ok(const TileCompDesc *h_tcs, int ntcs, int type)
+{
+    for (int i = 0; i < ntcs; i++) {
+        const TileCompDesc &tc = h_tcs[i];
+        if (tc.transform != type)
+            continue;
+        for (int j = 0; j + 1 < tc.nlevels; j++) {
+            if (!level_streamable(tc, j))
+                return false;
+            /* the level's output is the next level's LL source: its rows must stay 16-byte aligned */
+            if ((tc.lev[j + 1].u1 - tc.lev[j + 1].u0) & 3)
+                return false;
+        }
+    }
+    return true;
+}
+
+bool idwt_stream_final_ok(const IdwtFrame &f, int type, int *ncomp)
+{
+    int nc = 0;
+    for (int i = 0; i < f.ngroups; i++) {
+        const PackGroup &g = f.h_groups[i];
+        const TileCompDesc &t0 = f.h_tcs[g.tc[0]];
+        if (t0.transform != type)
+            continue;
+        if (t0.nlevels < 1 || !g.wide || (g.ncomp != 1 && g.ncomp != 3) || g.pixel_stride != g.ncomp)
+            return false;
+        if (nc && nc != g.ncomp)
+            return false;
+        nc = g.ncomp;
+        for (int c = 0; c < g.ncomp; c++) {
+            const TileCompDesc &tc = f.h_tcs[g.tc[c]];
+            if (g.sample_off[c] != c || tc.nlevels != t0.nlevels || !level_streamable(tc, tc.nlevels - 1))
+                return false;
+            const LevelDesc &a = tc.lev[tc.nlevels], &b = t0.lev[t0.nlevels];
+            if (a.u0 != b.u0 || a.u1 != b.u1 || a.v0 != b.v0 || a.v1 != b.v1)
+                return false;
+        }
+        if ((t0.out_x & 7) || (f.plane_row_bytes[g.plane] & 15) || (f.plane_off[g.plane] & 15))
+            return false;
+    }
+    *ncomp = nc;
+    return nc != 0;
+}
+
+int launch_idwt_stream_level(cudaStream_t stream, int type, const IdwtFrame &f, int j, int max_w, int max_h,
+                             const void *in, void *out)
+{
+#define LAUNCH(T)                                                                                              \
+    do {                                                                                                       \
+        constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;                                                  \
+        const int strips = (max_w + 1 + VALID - 1) / VALID;                                                    \
+        const int seg = pick_seg(strips, f.ntcs, max_h), segs = (max_h + 1 + seg - 1) / seg;                   \
+        dim3 grid((strips * segs + SWARPS - 1) / SWARPS, f.ntcs);                                              \
+        constexpr int sm = SWARPS * stage_bytes_per_warp<NP, 1>();                                             \
+        static bool attr = false;                                                                              \
+        if (!attr) {                                                                                           \
+            cudaFuncSetAttribute(idwt_stream_level_kernel<T, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
+            attr = true;                                                                                       \
+        }                                                                                                      \
+        idwt_stream_level_kernel<T, NP><<<grid, SWARPS * 32, sm, stream>>>(                                    \
+            f.d_tcs, j, (const uint32_t *)f.coefA, (const uint32_t *)in, (uint32_t *)out, strips, seg);        \
+    } while (0)
+    if (type == J2K_DWT53) LAUNCH(J2K_DWT53);
+    else if (type == J2K_DWT97) LAUNCH(J2K_DWT97);
+    else LAUNCH(J2K_DWT97_INT);
+#undef LAUNCH
+    return 1;
+}
+
+int launch_idwt_stream_final(cudaStream_t stream, int type, int ncomp, const IdwtFrame &f, int max_w, int max_h)
+{
+#define LAUNCH(T, NC)                                                                                          \
+    do {                                                                                                       \
+        constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;                                                  \
+        const int strips = (max_w + 1 + VALID - 1) / VALID;                                                    \
+        const int seg = pick_seg(strips, f.ngroups, max_h), segs = (max_h + 1 + seg - 1) / seg;                \
+        dim3 grid((strips * segs + SWARPS - 1) / SWARPS, f.ngroups);                                           \
+        constexpr int sm = SWARPS * stage_bytes_per_warp<NP, NC>();                                            \
+        cudaFuncSetAttribute(idwt_stream_final_kernel<T, NP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
+        idwt_stream_final_kernel<T, NP, NC><<<grid, SWARPS * 32, sm, stream>>>(                                \
+            f.d_tcs, f.d_groups, (const uint32_t *)f.coefA, (const uint32_t *)f.coefB, (const uint32_t *)f.coefC, \
+            f.picture, f.plane_off[0], f.plane_off[1], f.plane_off[2], f.plane_off[3], f.plane_row_bytes[0],   \
+            f.plane_row_bytes[1], f.plane_row_bytes[2], f.plane_row_bytes[3], strips, seg);                    \
+    } while (0)
+    if (ncomp == 3) {
+        if (type == J2K_DWT53) LAUNCH(J2K_DWT53, 3);
+        else if (type == J2K_DWT97) LAUNCH(J2K_DWT97, 3);
+        else LAUNCH(J2K_DWT97_INT, 3);
+    } else {
+        if (type == J2K_DWT53) LAUNCH(J2K_DWT53, 1);
+        else if (type == J2K_DWT97) LAUNCH(J2K_DWT97, 1);
+        else LAUNCH(J2K_DWT97_INT, 1);
+    }
+#undef LAUNCH
+    return 1;
+}
+
+}  // namespace b200j2k

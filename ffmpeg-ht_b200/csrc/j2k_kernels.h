@@ -50,6 +50,15 @@ struct IdwtFrame {
 };
 int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f);
 
+/* Register-streaming fast path (idwt_stream.cu).  The *_ok functions decide on the host, per launch,
+ * whether every tile-component / pack group of transform `type` fits it (even origins, aligned rows,
+ * packed 16-bit output); launch_idwt_frame falls back to the shared-memory tiled kernels otherwise. */
+bool idwt_stream_levels_ok(const TileCompDesc *h_tcs, int ntcs, int type);
+bool idwt_stream_final_ok(const IdwtFrame &f, int type, int *ncomp);
+int launch_idwt_stream_level(cudaStream_t stream, int type, const IdwtFrame &f, int j, int max_w, int max_h,
+                             const void *in, void *out);
+int launch_idwt_stream_final(cudaStream_t stream, int type, int ncomp, const IdwtFrame &f, int max_w, int max_h);
+
 /* one plane, all levels, result left in `plane` (stage-level entry point for parity tests) */
 int launch_idwt_plane(cudaStream_t stream, int type, const int32_t *border, int levels, void *plane,
                       void *scratchB, void *scratchC, TileCompDesc *d_tc_scratch);
