@@ -12,13 +12,14 @@ hyphen).  Nothing here imports or calls anything under ``oracle/``.
 from __future__ import annotations
 
 import ctypes
+import os
 import subprocess
 from pathlib import Path
 
 import numpy as np
 
 _DIR = Path(__file__).resolve().parent
-LIB_PATH = _DIR / "libb200j2k.so"
+LIB_PATH = Path(os.environ.get("B200J2K_LIB", _DIR / "libb200j2k.so"))   # env override: kernel tuning builds only
 
 ERR_INVALIDDATA = -1094995529
 ERR_PATCHWELCOME = -1163346256

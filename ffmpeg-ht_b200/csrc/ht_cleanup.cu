@@ -428,68 +428,76 @@ __device__ __forceinline__ void zero_block(uint32_t *dst, uint32_t dstride, int 
             dst[(size_t)y * dstride + x] = 0;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order,
-                 const uint32_t *__restrict__ scr_off, int nblocks, const uint8_t *__restrict__ bytes,
-                 const BandDesc *__restrict__ bands, const uint32_t *__restrict__ scratch,
-                 uint32_t *__restrict__ coef, int32_t *__restrict__ status, int stream_words)
+/* dequantisation variants selected per block (warp-uniform): the two common cases skip the ROI / step-size
+ * branches of dequant() */
+enum { DQ_GENERIC = 0, DQ_INT53 = 1, DQ_FLOAT97 = 2 };
+
+template <int DQ>
+__device__ __forceinline__ uint32_t dq(uint32_t mu, int sh53, float fscale, int mode, int M_b, int roi_shift, const BandDesc &bd)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int gw = blockIdx.x * WARPS_PER_CTA + warp;
-    if (gw >= nblocks)
-        return;
-    const uint32_t bi = order[gw];
-    const CblkDesc d = descs[bi];
-    const int w = d.w, h = d.h;
-    uint32_t *dst = coef + d.dst_off;
-    const uint32_t dstride = d.dst_stride;
-    const uint8_t *Dcup = bytes + d.data_off;
-    const int Scup = ht_block_scup(d, Dcup);
-    if (Scup <= 0) {
-        /* nothing decoded or damaged header: the block is all zeros (quirk Q1) */
-        zero_block(dst, dstride, w, h, lane);
-        if (lane == 0 && status)
-            status[bi] = Scup == 0 ? 0 : B200J2K_KERR_INVALID;
-        return;
+    if (DQ == DQ_INT53) {                        /* dequantization_int with i_stepsize == 32768 (jpeg2000dec.c:2120-2151) */
+        const int32_t v = (int32_t)((mu & 0x7FFFFFFFu) >> sh53);
+        return (uint32_t)((int32_t)mu < 0 ? -v : v);
+    } else if (DQ == DQ_FLOAT97) {               /* dequantization_float (:2098-2117) */
+        const int32_t m = (int32_t)(mu & 0x7FFFFFFFu);
+        return __float_as_uint(__fmul_rn((float)((int32_t)mu < 0 ? -m : m), fscale));
     }
-    const BandDesc bd = bands[d.band];
+    return dequant(mu, mode, M_b, roi_shift, bd);
+}
+
+template <int DQ>
+__device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int Scup, const uint8_t *Dcup,
+                                             const BandDesc &bd, const uint32_t *__restrict__ q, uint32_t *ms,
+                                             uint32_t *__restrict__ dst, int32_t *__restrict__ status, int lane)
+{
+    const int w = d.w, h = d.h;
+    const uint32_t dstride = d.dst_stride;
     const int mode = (d.flags >> 1) & 3;
     const int M_b = d.M_b;
+    const int roi_shift = d.roi_shift;
     const int rem = d.npasses % 3;
     const int p0 = (rem ? d.npasses - rem : d.npasses - 3) / 3;
     const int S_blk = (p0 + d.zbp) & 0xFF;
     const int pLSB = 30 - S_blk;
     const int maxbp = S_blk + 1;
     const int Pcup = d.Lcup - Scup;
+    const int sh53 = 31 - M_b;
+    const float fscale = bd.fscale;
 
     /* un-stuff MagSgn: byte after 0xFF carries 7 bits (jpeg2000htdec.c:207-221); bit 7 of such a byte is
-     * OR-ed into the next byte's bit 0 exactly as the reference's 64-bit accumulator does */
-    uint32_t *ms = smem + (size_t)warp * stream_words;
+     * OR-ed into the next byte's bit 0 exactly as the reference's 64-bit accumulator does.  Four bytes per
+     * lane, fetched as two aligned words. */
     const int ms_words = (Pcup + 3) / 4 + 2;
     for (int i = lane; i < ms_words; i += 32)
         ms[i] = 0;
     __syncwarp();
     uint32_t ms_bits = 0;
     {
+        const uint32_t *wbase = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(Dcup) & ~(uintptr_t)3);
+        const int bsh = (int)(reinterpret_cast<uintptr_t>(Dcup) & 3) * 8;
         unsigned carry = 0;
         for (int chunk = 0; chunk < Pcup; chunk += 128) {
             const int idx = chunk + lane * 4;
-            unsigned b[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                b[k] = idx + k < Pcup ? Dcup[idx + k] : 0;
-            unsigned before = __shfl_up_sync(FULL, b[3], 1);
+            uint32_t b4 = 0;
+            const int nvalid = min(4, Pcup - idx);
+            if (nvalid > 0) {
+                const uint32_t w0 = wbase[idx >> 2], w1 = wbase[(idx >> 2) + 1];
+                b4 = __funnelshift_r(w0, w1, bsh);
+                if (nvalid < 4)
+                    b4 &= (1u << (8 * nvalid)) - 1;
+            }
+            unsigned before = __shfl_up_sync(FULL, b4 >> 24, 1);
             if (lane == 0)
                 before = carry;
             uint64_t v = 0;
             int tot = 0;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                int nb = idx + k < Pcup ? (before == 0xFF ? 7 : 8) : 0;
-                v |= (uint64_t)b[k] << tot;
+                const unsigned bk = (b4 >> (8 * k)) & 0xFF;
+                const int nb = k < nvalid ? (before == 0xFF ? 7 : 8) : 0;
+                v |= (uint64_t)bk << tot;
                 tot += nb;
-                before = b[k];
+                before = bk;
             }
             int incl = tot;
 #pragma unroll
@@ -500,14 +508,14 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
             }
             const uint32_t off = ms_bits + (uint32_t)(incl - tot);
             if (tot) {
-                const uint32_t wd = off >> 5, s = off & 31;
-                const uint64_t sh = v << s;
-                atomicOr(&ms[wd], (uint32_t)sh);
-                if ((uint32_t)(sh >> 32))
-                    atomicOr(&ms[wd + 1], (uint32_t)(sh >> 32));
+                const uint32_t wd = off >> 5, sft = off & 31;
+                const uint64_t shv = v << sft;
+                atomicOr(&ms[wd], (uint32_t)shv);
+                if ((uint32_t)(shv >> 32))
+                    atomicOr(&ms[wd + 1], (uint32_t)(shv >> 32));
             }
             ms_bits += (uint32_t)__shfl_sync(FULL, incl, 31);
-            carry = __shfl_sync(FULL, b[3], 31);
+            carry = __shfl_sync(FULL, b4 >> 24, 31);
         }
         __syncwarp();
         if (lane == 0) {                                 /* past the end the decoder reads ones */
@@ -519,7 +527,6 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
     }
 
     const int QW = (w + 1) >> 1, QH = (h + 1) >> 1;
-    const uint32_t *q = scratch + scr_off[bi] + 2 * ht_stream_words(Scup);
     const bool act = lane < QW;
     const bool vec = (((d.dst_off | dstride) & 1) == 0);      /* 8-byte aligned sample pairs */
     uint32_t nextq = act ? q[lane] : 0;
@@ -528,7 +535,7 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
     bool bad = false;
     const int x = 2 * lane;
     for (int qy = 0; qy < QH; qy++) {
-        const unsigned mine = nextq;                     /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16 */
+        const unsigned mine = nextq;                     /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16; 0 in idle lanes */
         if (qy + 1 < QH)
             nextq = act ? q[(qy + 1) * QW + lane] : 0;
         const unsigned rho = (mine >> 1) & 15;
@@ -554,7 +561,7 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
         int tot = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            mlen[i] = act ? (int)((rho >> i) & 1) * U - (int)((ek >> i) & 1) : 0;
+            mlen[i] = (((rho >> i) & 1) ? U : 0) - (int)((ek >> i) & 1);
             tot += max(mlen[i], 0);
         }
         int incl = tot;
@@ -592,8 +599,10 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
         /* samples of quad (qy, lane): i=0 (y,x) i=1 (y+1,x) i=2 (y,x+1) i=3 (y+1,x+1) */
         const int y = 2 * qy;
         if (act) {
-            const uint32_t o0 = dequant(mu[0], mode, M_b, d.roi_shift, bd), o1 = dequant(mu[1], mode, M_b, d.roi_shift, bd),
-                           o2 = dequant(mu[2], mode, M_b, d.roi_shift, bd), o3 = dequant(mu[3], mode, M_b, d.roi_shift, bd);
+            const uint32_t o0 = dq<DQ>(mu[0], sh53, fscale, mode, M_b, roi_shift, bd),
+                           o1 = dq<DQ>(mu[1], sh53, fscale, mode, M_b, roi_shift, bd),
+                           o2 = dq<DQ>(mu[2], sh53, fscale, mode, M_b, roi_shift, bd),
+                           o3 = dq<DQ>(mu[3], sh53, fscale, mode, M_b, roi_shift, bd);
             uint32_t *r0 = dst + (size_t)y * dstride + x, *r1 = r0 + dstride;
             if (vec && x + 1 < w) {
                 *reinterpret_cast<uint2 *>(r0) = make_uint2(o0, o2);
@@ -617,6 +626,41 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
     }
     if (lane == 0 && status)
         status[bi] = bad ? B200J2K_KERR_INVALID : 1;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order,
+                 const uint32_t *__restrict__ scr_off, int nblocks, const uint8_t *__restrict__ bytes,
+                 const BandDesc *__restrict__ bands, const uint32_t *__restrict__ scratch,
+                 uint32_t *__restrict__ coef, int32_t *__restrict__ status, int stream_words)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * WARPS_PER_CTA + warp;
+    if (gw >= nblocks)
+        return;
+    const uint32_t bi = order[gw];
+    const CblkDesc d = descs[bi];
+    uint32_t *dst = coef + d.dst_off;
+    const uint8_t *Dcup = bytes + d.data_off;
+    const int Scup = ht_block_scup(d, Dcup);
+    if (Scup <= 0) {
+        /* nothing decoded or damaged header: the block is all zeros (quirk Q1) */
+        zero_block(dst, d.dst_stride, d.w, d.h, lane);
+        if (lane == 0 && status)
+            status[bi] = Scup == 0 ? 0 : B200J2K_KERR_INVALID;
+        return;
+    }
+    const BandDesc bd = bands[d.band];
+    const int mode = (d.flags >> 1) & 3;
+    const uint32_t *q = scratch + scr_off[bi] + 2 * ht_stream_words(Scup);
+    uint32_t *ms = smem + (size_t)warp * stream_words;
+    if (d.roi_shift == 0 && mode == J2K_DWT53 && bd.i_stepsize == 32768)
+        magsgn_block<DQ_INT53>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane);
+    else if (d.roi_shift == 0 && mode == J2K_DWT97)
+        magsgn_block<DQ_FLOAT97>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane);
+    else
+        magsgn_block<DQ_GENERIC>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane);
 }
 
 }  // namespace

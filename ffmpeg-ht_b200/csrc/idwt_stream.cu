@@ -43,7 +43,16 @@ template <> struct VecIO<2> {
     }
 };
 
-constexpr int STAGES = 4;                 /* row pairs in flight per warp (cp.async groups) */
+#ifndef STREAM_STAGES
+#define STREAM_STAGES 2
+#endif
+#ifndef STREAM_MINB
+#define STREAM_MINB 5
+#endif
+#ifndef STREAM_WANT
+#define STREAM_WANT 20
+#endif
+constexpr int STAGES = STREAM_STAGES;     /* row pairs in flight per warp (cp.async groups) */
 
 template <int NP> __device__ __forceinline__ void cp_async_vec(uint32_t dst, const uint32_t *src)
 {
@@ -244,7 +253,7 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *(
                 kyE = row_ky(g, 2 * n);
             if (2 * n + 1 < g.v0 || 2 * n + 1 >= g.v1)
                 kyO = row_ky(g, 2 * n + 1);
-            const uint32_t st = stage_base + (uint32_t)((n - n0) & (STAGES - 1)) * SSTRIDE;
+            const uint32_t st = stage_base + (uint32_t)((n - n0) % STAGES) * SSTRIDE;
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 cp_async_vec<NP>(st + (4 * c + 0) * VSTRIDE, pLL[c] + kyE * g.LLstride);
@@ -260,7 +269,7 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *(
         asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
         uint32_t cLe[NC][NP], cHe[NC][NP], cLo[NC][NP], cHo[NC][NP];
         if (lc.inside) {
-            const uint32_t st = stage_base + (uint32_t)((n - n0) & (STAGES - 1)) * SSTRIDE;
+            const uint32_t st = stage_base + (uint32_t)((n - n0) % STAGES) * SSTRIDE;
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 lds_vec<NP>(st + (4 * c + 0) * VSTRIDE, cLe[c]);
@@ -373,7 +382,7 @@ idwt_stream_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint
 
 /* ---- last level fused with MCT + level shift + clip + pack (packed 16-bit output) ---------------------- */
 template <int TYPE, int NP, int NC>
-__global__ void __launch_bounds__(SWARPS * 32, NP == 4 ? 2 : (TYPE == J2K_DWT53 ? 4 : 3))
+__global__ void __launch_bounds__(SWARPS * 32, NP == 4 ? 2 : (TYPE == J2K_DWT53 ? STREAM_MINB : 3))
 idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__restrict__ groups,
                          const uint32_t *__restrict__ coefA, const uint32_t *__restrict__ coefIn0,
                          const uint32_t *__restrict__ coefIn1, uint8_t *__restrict__ picture,
@@ -493,7 +502,7 @@ template <int TYPE> struct StreamCfg {
  * HALO warm-up rows dominate */
 int pick_seg(int strips, int units_z, int rows)
 {
-    const long want = 148L * 16;
+    const long want = 148L * STREAM_WANT;
     long seg = ((long)rows * strips * units_z + want - 1) / want;
     seg = (seg + 1) & ~1L;
     if (seg < 8) seg = 8;
