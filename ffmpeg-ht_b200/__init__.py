@@ -286,8 +286,8 @@ class Jpeg2000Decoder:
         _check(lib().b200j2k_run_staged(self._h, slot), "run_staged")
 
     def run_staged_timed(self, slot: int):
-        """-> [ms HT cleanup-only, ms HT refinement, ms IDWT levels, ms fused last level + MCT + pack]"""
-        ms = (ctypes.c_float * 4)()
+        """-> ms of [HT un-stuff, HT VLC, HT MagSgn + dequant, HT refinement blocks, IDWT levels, fused last level]"""
+        ms = (ctypes.c_float * 6)()
         _check(lib().b200j2k_run_staged_timed(self._h, slot, ms), "run_staged_timed")
         return [float(v) for v in ms]
 

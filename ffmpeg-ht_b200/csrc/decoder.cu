@@ -86,20 +86,32 @@ struct HostBuf {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 /* How the code-blocks of one frame are spread over the HT kernels.  order[] lists descriptor indices as
- * [coded | zero | wide | refine]:
- *   coded   cleanup-only blocks with data, <= 64 samples wide  -> split pipeline (ht_cleanup.cu), sorted by
- *           shape so that the 32 blocks sharing a warp of the lane-per-block VLC kernel run in step
- *   zero    blocks without data                                -> zero-filled by the MagSgn kernel
- *   wide    cleanup-only blocks wider than 64 samples          -> general warp-per-block kernel
- *   refine  blocks with SigProp / MagRef passes                -> general kernel, refinement variant */
+ * [refine | coded | zero | wide | rwide]:
+ *   refine  blocks with SigProp / MagRef passes, <= 64 samples wide -> split pipeline + refinement kernels
+ *   coded   cleanup-only blocks with data, <= 64 samples wide      -> split pipeline (ht_cleanup.cu)
+ *   zero    blocks without data                                    -> zero-filled by the MagSgn kernel
+ *   wide    cleanup-only blocks wider than 64 samples              -> general warp-per-block kernel
+ *   rwide   refinement blocks wider than 64 samples                -> general kernel, refinement variant
+ * refine and coded are sorted by shape so that the 32 blocks sharing a warp of the lane-per-block kernels
+ * run in step. */
 struct HtPlan {
     std::vector<uint32_t> order, scr_off;
-    int n_coded = 0, n_zero = 0, n_wide = 0, n_refine = 0;
-    int maxL_fast = 0, maxL_wide = 0, maxL_refine = 0;
+    int n_refine = 0, n_coded = 0, n_zero = 0, n_wide = 0, n_rwide = 0;
+    int maxL_fast = 0, maxLref = 0, maxL_wide = 0, maxL_rwide = 0;
     size_t scratch_words = 0;
     /* descriptor indices sorted by quad-grid shape; depends on the geometry only */
     std::vector<uint32_t> by_shape;
     uint64_t shape_serial = ~0ull;
+
+    static int klass(const CblkDesc &d)
+    {
+        const bool refine = d.npasses && (d.npasses % 3) != 1;
+        if (d.w > 64)
+            return refine ? 4 : 3;
+        if (refine)
+            return 0;
+        return d.npasses ? 1 : 2;
+    }
 
     void build(const CblkDesc *cblk, size_t n, uint64_t serial)
     {
@@ -115,66 +127,62 @@ struct HtPlan {
         }
         order.resize(n);
         scr_off.resize(n);
-        n_coded = n_zero = n_wide = n_refine = 0;
-        maxL_fast = maxL_wide = maxL_refine = 0;
+        maxL_fast = maxLref = maxL_wide = maxL_rwide = 0;
         scratch_words = 0;
-        size_t nz = 0, nw = 0, nr = 0;
-        /* first pass: coded blocks in shape order at the front, count the rest */
+        size_t cnt[5] = { 0, 0, 0, 0, 0 };
+        for (size_t i = 0; i < n; i++)
+            cnt[klass(cblk[i])]++;
+        size_t at[5];
+        at[0] = 0;
+        for (int k = 1; k < 5; k++)
+            at[k] = at[k - 1] + cnt[k - 1];
         for (size_t k = 0; k < n; k++) {
             const uint32_t i = by_shape[k];
             const CblkDesc &d = cblk[i];
+            const int c = klass(d);
+            order[at[c]++] = i;
             scr_off[i] = 0;
-            const bool refine = d.npasses && (d.npasses % 3) != 1;
-            if (refine) {
-                nr++;
-            } else if (d.w > 64) {
-                nw++;
-            } else if (d.npasses == 0) {
-                nz++;
-            } else {
-                order[n_coded++] = i;
+            if (c <= 1) {
                 scr_off[i] = (uint32_t)scratch_words;
                 scratch_words += ht_cleanup_scratch_words(d);
                 if (d.Lcup > maxL_fast) maxL_fast = d.Lcup;
+                if (c == 0 && d.Lref > maxLref) maxLref = d.Lref;
+            } else if (c == 3) {
+                if (d.Lcup > maxL_wide) maxL_wide = d.Lcup;
+            } else if (c == 4) {
+                if (d.Lcup > maxL_rwide) maxL_rwide = d.Lcup;
             }
         }
-        size_t az = n_coded, aw = az + nz, ar = aw + nw;
-        for (size_t i = 0; i < n; i++) {
-            const CblkDesc &d = cblk[i];
-            const bool refine = d.npasses && (d.npasses % 3) != 1;
-            if (refine) {
-                order[ar++] = (uint32_t)i;
-                if (d.Lcup > maxL_refine) maxL_refine = d.Lcup;
-            } else if (d.w > 64) {
-                order[aw++] = (uint32_t)i;
-                if (d.npasses && d.Lcup > maxL_wide) maxL_wide = d.Lcup;
-            } else if (d.npasses == 0) {
-                order[az++] = (uint32_t)i;
-            }
-        }
-        n_zero = (int)nz;
-        n_wide = (int)nw;
-        n_refine = (int)nr;
+        n_refine = (int)cnt[0];
+        n_coded = (int)cnt[1];
+        n_zero = (int)cnt[2];
+        n_wide = (int)cnt[3];
+        n_rwide = (int)cnt[4];
     }
 };
 
 /* queue the HT kernels of one plan; returns launches or < 0 */
 int run_ht(cudaStream_t st, const HtPlan &hp, const CblkDesc *d_cblk, const uint32_t *d_order, const uint32_t *d_scr,
            const uint8_t *d_bytes, const BandDesc *d_bands, void *scratch, void *coef, int32_t *status, int max_w,
-           int max_area, int max_state, cudaEvent_t after_plain = nullptr)
+           int max_area, int max_state, cudaEvent_t *ev = nullptr)
 {
+    /* ev (optional): [1] after un-stuff, [2] after VLC, [3] after MagSgn + wide blocks */
     int launches = 0, r;
-    r = launch_ht_cleanup(st, d_cblk, d_order, d_scr, hp.n_coded, hp.n_coded + hp.n_zero, d_bytes, d_bands, scratch, coef,
-                          status, hp.maxL_fast);
+    r = launch_ht_cleanup(st, d_cblk, d_order, d_scr, hp.n_refine, hp.n_coded, hp.n_zero, d_bytes, d_bands, scratch, coef,
+                          status, hp.maxL_fast, hp.maxLref, ev ? ev[1] : nullptr, ev ? ev[2] : nullptr);
     if (r < 0) return r;
     launches += r;
-    r = launch_ht_decode(st, false, d_cblk, d_order + hp.n_coded + hp.n_zero, hp.n_wide, d_bytes, d_bands, coef, status,
-                         hp.maxL_wide, max_w, max_area, max_state);
+    const uint32_t *o_wide = d_order + hp.n_refine + hp.n_coded + hp.n_zero;
+    r = launch_ht_decode(st, false, d_cblk, o_wide, hp.n_wide, d_bytes, d_bands, coef, status, hp.maxL_wide, max_w, max_area,
+                         max_state);
     if (r < 0) return r;
     launches += r;
-    if (after_plain) cudaEventRecord(after_plain, st);
-    r = launch_ht_decode(st, true, d_cblk, d_order + hp.n_coded + hp.n_zero + hp.n_wide, hp.n_refine, d_bytes, d_bands,
-                         coef, status, hp.maxL_refine, max_w, max_area, max_state);
+    if (ev) cudaEventRecord(ev[3], st);
+    r = launch_ht_refine(st, d_cblk, d_order, d_scr, hp.n_refine, d_bytes, d_bands, scratch, coef, status, hp.maxL_fast);
+    if (r < 0) return r;
+    launches += r;
+    r = launch_ht_decode(st, true, d_cblk, o_wide + hp.n_wide, hp.n_rwide, d_bytes, d_bands, coef, status, hp.maxL_rwide,
+                         max_w, max_area, max_state);
     if (r < 0) return r;
     return launches + r;
 }
@@ -326,7 +334,9 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     return 0;
 }
 
-/* queue every kernel of the frame on the slot's stream; ev (optional, 5 events) brackets the stages */
+/* queue every kernel of the frame on the slot's stream; ev (optional, 7 events) brackets the stages:
+ * [0] start [1] un-stuffed [2] VLC done [3] MagSgn (+ wide blocks) done [4] refinement blocks done
+ * [5] IDWT levels done [6] end */
 int run_kernels(Slot &s, cudaEvent_t *ev = nullptr)
 {
     Parser &p = s.parser;
@@ -340,13 +350,13 @@ int run_kernels(Slot &s, cudaEvent_t *ev = nullptr)
     int launches = 0, r;
     if (ev) cudaEventRecord(ev[0], s.stream);
     r = run_ht(s.stream, s.ht, d_cblk, d_order, (const uint32_t *)(blob + s.off_scr), d_bytes, d_bands, s.d_scratch.p,
-               s.d_coefA.p, (int32_t *)s.d_status.p, (int)p.max_w, (int)p.max_area, (int)p.max_state, ev ? ev[1] : nullptr);
+               s.d_coefA.p, (int32_t *)s.d_status.p, (int)p.max_w, (int)p.max_area, (int)p.max_state, ev);
     if (r < 0) return B200J2K_ERR_DEVICE;
     launches += r;
-    if (ev) cudaEventRecord(ev[2], s.stream);
+    if (ev) cudaEventRecord(ev[4], s.stream);
     IdwtFrame f;
     memset(&f, 0, sizeof(f));
-    f.before_final = ev ? ev[3] : nullptr;
+    f.before_final = ev ? ev[5] : nullptr;
     f.d_tcs = d_tcs;
     f.d_groups = d_groups;
     f.h_tcs = p.tcs.data();
@@ -364,7 +374,7 @@ int run_kernels(Slot &s, cudaEvent_t *ev = nullptr)
     r = launch_idwt_frame(s.stream, f);
     if (r < 0) return B200J2K_ERR_DEVICE;
     launches += r;
-    if (ev) cudaEventRecord(ev[4], s.stream);
+    if (ev) cudaEventRecord(ev[6], s.stream);
     s.launches = launches;
     return 0;
 }
@@ -571,7 +581,7 @@ int b200j2k_run_staged_timed(b200j2k_decoder *d, int slot, float *ms)
         return B200J2K_ERR_EINVAL;
     if (cudaSetDevice(d->device) != cudaSuccess)
         return B200J2K_ERR_DEVICE;
-    cudaEvent_t ev[5];
+    cudaEvent_t ev[7];
     for (auto &e : ev)
         if (cudaEventCreate(&e) != cudaSuccess)
             return B200J2K_ERR_DEVICE;
@@ -580,7 +590,7 @@ int b200j2k_run_staged_timed(b200j2k_decoder *d, int slot, float *ms)
     if (r >= 0 && cudaStreamSynchronize(s.stream) != cudaSuccess)
         r = B200J2K_ERR_DEVICE;
     if (r >= 0)
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 6; i++)
             cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
     for (auto &e : ev)
         cudaEventDestroy(e);
@@ -693,13 +703,17 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
     int ret = 0;
     cudaStream_t st = nullptr;
     if (cudaStreamCreate(&st) != cudaSuccess) return B200J2K_ERR_DEVICE;
-    if (cudaMalloc(&d_bytes, (size_t)data_size + 64) != cudaSuccess || cudaMalloc(&d_descs, n * sizeof(CblkDesc)) != cudaSuccess ||
+    /* 16 bytes in front of the segments: the kernels fetch bytes as aligned words and may touch up to 6 bytes
+     * before a segment (in a frame the descriptor tables sit there) */
+    uint8_t *d_bytes_alloc = nullptr;
+    if (cudaMalloc(&d_bytes_alloc, (size_t)data_size + 16 + 64) != cudaSuccess || cudaMalloc(&d_descs, n * sizeof(CblkDesc)) != cudaSuccess ||
         cudaMalloc(&d_order, n * 4) != cudaSuccess || cudaMalloc(&d_scr, n * 4) != cudaSuccess ||
         cudaMalloc(&d_out, total * 4 + 4) != cudaSuccess || cudaMalloc(&d_scratch, hp.scratch_words * 4 + 256) != cudaSuccess ||
         cudaMalloc(&d_band, sizeof(BandDesc)) != cudaSuccess || cudaMalloc(&d_status, n * 4) != cudaSuccess) {
         ret = B200J2K_ERR_NOMEM;
     } else {
-        cudaMemsetAsync(d_bytes, 0, (size_t)data_size + 64, st);
+        d_bytes = d_bytes_alloc + 16;
+        cudaMemsetAsync(d_bytes_alloc, 0, (size_t)data_size + 16 + 64, st);
         cudaMemcpyAsync(d_bytes, data, (size_t)data_size, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_descs, descs.data(), n * sizeof(CblkDesc), cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_order, hp.order.data(), n * 4, cudaMemcpyHostToDevice, st);
@@ -716,7 +730,7 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
             ret = B200J2K_ERR_DEVICE;
         }
     }
-    cudaFree(d_bytes); cudaFree(d_descs); cudaFree(d_order); cudaFree(d_scr); cudaFree(d_out); cudaFree(d_scratch);
+    cudaFree(d_bytes_alloc); cudaFree(d_descs); cudaFree(d_order); cudaFree(d_scr); cudaFree(d_out); cudaFree(d_scratch);
     cudaFree(d_band); cudaFree(d_status);
     cudaStreamDestroy(st);
     return ret;

@@ -28,6 +28,34 @@ namespace b200j2k {
 
 namespace {
 
+/* scratch layout of a block with refinement passes, word offsets from the block's scratch base.  The
+ * cleanup part comes first: [VLC bits | MEL bits | one word per quad], sized for the largest possible suffix
+ * so that the offsets only depend on the descriptor. */
+struct RefLayout {
+    int rw;             /* words of one un-stuffed Dref bit array */
+    int nst;            /* 4-row stripes (the row below an odd-height block included, quirk Q2) */
+    int sp, mr;         /* un-stuffed SigProp (forward) and MagRef (backward) bits */
+    int sig, nsg, sgn;  /* nibble-layout maps, 8 words per stripe: cleanup significance, newly significant, signs */
+    int total;
+};
+
+__host__ __device__ inline RefLayout ref_layout(const CblkDesc &d)
+{
+    RefLayout r;
+    const int S = d.Lcup < 4079 ? d.Lcup : 4079;
+    const int QW = (d.w + 1) >> 1, QH = (d.h + 1) >> 1;
+    const int cleanup = (2 * ht_stream_words(S) + QW * QH + 1) & ~1;
+    r.rw = ((d.Lref + 3) / 4 + 3 + 1) & ~1;
+    r.nst = (QH + 1) >> 1;
+    r.sp = cleanup;
+    r.mr = r.sp + r.rw;
+    r.sig = r.mr + r.rw;
+    r.nsg = r.sig + 8 * r.nst;
+    r.sgn = r.nsg + 8 * r.nst;
+    r.total = r.sgn + 8 * r.nst;
+    return r;
+}
+
 /* H1 (jpeg2000htdec.c:1237-1273): Scup (>= 2) when the cleanup segment is decodable, 0 when there is
  * nothing to decode, -1 when the segment header is damaged (block = zeros, quirk Q1) */
 __device__ __forceinline__ int ht_block_scup(const CblkDesc &d, const uint8_t *Dcup)
@@ -48,6 +76,153 @@ __device__ __forceinline__ int ht_block_scup(const CblkDesc &d, const uint8_t *D
     if (S_blk + 1 >= 32 || 30 - S_blk < 1)
         return -1;
     return Scup;
+}
+
+/* four bytes p[0..3] (p[0] in the low byte) fetched as two aligned words; the caller guarantees that the
+ * aligned words around p are readable (the byte buffer has 64 bytes of slack and a 256-byte aligned base) */
+__device__ __forceinline__ uint32_t load4(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (int)(a & 3) * 8);
+}
+
+/*
+ * Parallel removal of byte stuffing.  The five bit streams of an HT code-block differ only in direction,
+ * in the stuffing rule and in how a byte's bits are consumed; all become contiguous LSB-first bit arrays
+ * (first bit consumed = bit 0 of word 0):
+ *   US_MAGSGN  Dcup[0..Pcup) forward; 7 bits after 0xFF, bit 7 of such a byte is OR-ed into the next
+ *              byte's bit 0 as the reference's accumulator does (jpeg2000htdec.c:207-221)
+ *   US_MEL     Dcup[Pcup..Lcup) forward, MSB first, 7 bits after 0xFF, modDcup on the last two bytes
+ *              (:429-440, :1277-1278)
+ *   US_VLC     Dcup[Lcup-2] down to Dcup[Pcup]; 7 bits when (b & 0x7F) == 0x7F and the byte read before is
+ *              > 0x8F; first byte |= 0x0F, the byte "read before" it is 0xFF (:145-201, :283-295)
+ *   US_SIGPROP Dref[0..Lref) forward, LSB first, 7 bits after 0xFF (:442-460)
+ *   US_MAGREF  Dref[Lref-1] down to Dref[0], VLC stuffing rule, first "read before" is 0xFF (:123-131)
+ * first: address of the first byte in read order; n: bytes.  Four bytes per lane and chunk, fetched as two
+ * aligned words one chunk ahead; a warp prefix sum over the 7/8-bit lengths places them.  out[] must be
+ * zeroed.  Returns the number of bits written (warp-uniform).
+ */
+enum { US_MAGSGN, US_MEL, US_VLC, US_SIGPROP, US_MAGREF };
+
+/* 0x01 in every byte of x that equals the corresponding byte of y */
+__device__ __forceinline__ uint64_t bytes_eq(uint64_t x, uint64_t y)
+{
+    uint64_t d = x ^ y;                                  /* zero byte <=> equal */
+    d |= d >> 4;
+    d |= d >> 2;
+    d |= d >> 1;
+    return ~d & 0x0101010101010101ull;
+}
+
+/* 0x01 in every byte of x that is > 0x8F */
+__device__ __forceinline__ uint64_t bytes_gt8f(uint64_t x)
+{
+    /* b > 0x8F  <=>  bit 7 set and (b & 0x70) != 0 */
+    const uint64_t hi = x >> 7, any = (x >> 6) | (x >> 5) | (x >> 4);
+    return hi & any & 0x0101010101010101ull;
+}
+
+template <int KIND>
+__device__ __forceinline__ uint32_t unstuff(const uint8_t *first, int n, uint32_t *out, int lane)
+{
+    constexpr bool BACKWARD = KIND == US_VLC || KIND == US_MAGREF;
+    constexpr bool RULE_A = BACKWARD;           /* 7 bits when (b & 0x7F) == 0x7F && before > 0x8F; else: before == 0xFF */
+    constexpr int BPL = 8;                      /* bytes per lane and chunk */
+    uint32_t bits = 0;
+    unsigned carry = RULE_A ? 0xFF : 0;
+    /* eight bytes in read order, first byte read = low byte */
+    auto fetch = [&](int idx) -> uint64_t {
+        if (idx >= n)
+            return 0;
+        const uint8_t *p = BACKWARD ? first - 7 - idx : first + idx;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const int sh = (int)(a & 3) * 8;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        return BACKWARD ? ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123)
+                        : ((uint64_t)hi << 32) | lo;
+    };
+    uint64_t nxt = fetch(lane * BPL);
+    for (int chunk = 0; chunk < n; chunk += 32 * BPL) {
+        const int idx = chunk + lane * BPL;
+        uint64_t x = nxt;
+        nxt = fetch(idx + 32 * BPL);
+        const int nvalid = min(max(n - idx, 0), BPL);
+        const uint64_t vmask = nvalid >= 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
+        x &= vmask;
+        if (KIND == US_VLC && idx == 0)
+            x |= 0x0F;                                   /* modDcup: low nibble of the first byte read */
+        if (KIND == US_MEL) {                            /* modDcup: last two bytes of the segment */
+            const int k2 = n - 2 - idx, k1 = n - 1 - idx;
+            if (k2 >= 0 && k2 < 8)
+                x |= 0x0Full << (8 * k2);
+            if (k1 >= 0 && k1 < 8)
+                x |= 0xFFull << (8 * k1);
+        }
+        /* the byte read before each byte */
+        unsigned before = __shfl_up_sync(FULL, (unsigned)(x >> 56), 1);
+        if (lane == 0)
+            before = carry;
+        const uint64_t prev = (x << 8) | before;
+        /* 0x01 per byte that carries only 7 bits */
+        uint64_t st;
+        if (RULE_A)
+            st = bytes_eq(x | 0x8080808080808080ull, ~0ull) & bytes_gt8f(prev);
+        else
+            st = bytes_eq(prev, ~0ull);
+        st &= vmask;
+        const int tot = 8 * nvalid - __popcll(st);
+        uint64_t v = x;
+        if (KIND == US_MEL) {                            /* consumed MSB first: reverse the bits of every byte */
+            const uint32_t lo = __byte_perm(__brev((uint32_t)x), 0, 0x0123), hi = __byte_perm(__brev((uint32_t)(x >> 32)), 0, 0x0123);
+            v = ((uint64_t)hi << 32) | lo;
+        }
+        /* squeeze out the unused bit of every 7-bit byte, highest byte first so that lower positions stay valid */
+        while (st) {
+            const int k8 = 63 - __clzll((long long)st);  /* bit 8k */
+            st ^= 1ull << k8;
+            const int pos = KIND == US_MEL ? k8 : k8 + 7;
+            const uint64_t low = (1ull << pos) - 1;
+            const uint64_t keep = KIND == US_MAGSGN ? v & (1ull << pos) : 0;    /* OR-ed into the next byte's bit 0 */
+            v = (v & low) | ((v >> 1) & ~low) | keep;
+        }
+        int incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        const uint32_t off = bits + (uint32_t)(incl - tot);
+        if (tot) {
+            const uint32_t wd = off >> 5, sft = off & 31;
+            const uint64_t lo = v << sft;
+            const uint32_t hi = sft ? (uint32_t)(v >> (64 - sft)) : 0;
+            if ((uint32_t)lo)
+                atomicOr(&out[wd], (uint32_t)lo);
+            if ((uint32_t)(lo >> 32))
+                atomicOr(&out[wd + 1], (uint32_t)(lo >> 32));
+            if (hi)
+                atomicOr(&out[wd + 2], hi);
+        }
+        bits += (uint32_t)__shfl_sync(FULL, incl, 31);
+        carry = __shfl_sync(FULL, (unsigned)(x >> 56), 31);
+    }
+    __syncwarp();
+    return bits;
+}
+
+/* fill everything behind `bits` with ones (streams that read 0xFF past their end) */
+__device__ __forceinline__ void ones_behind(uint32_t *out, uint32_t bits, int words, int lane)
+{
+    const int first = (int)(bits >> 5);
+    if (lane == 0)
+        out[first] |= 0xFFFFFFFFu << (bits & 31);
+    for (int i = first + 1 + lane; i < words; i += 32)
+        out[i] = 0xFFFFFFFFu;
+    __syncwarp();
 }
 
 /* ---- K0 ------------------------------------------------------------------------------------------------ */
@@ -75,109 +250,9 @@ ht_unstuff_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict
     for (int i = lane; i < 2 * vlw; i += 32)
         vl[i] = 0;
     __syncwarp();
-    /* VLC: read order k = 0.. is Dcup[Lcup-2-k]; a byte whose low 7 bits are ones carries 7 bits when the
-     * byte read before it is > 0x8F (jpeg2000htdec.c:179-194); modDcup sets the low nibble of the first
-     * byte and makes the byte "read before it" 0xFF (:1277-1278, :283-295) */
-    {
-        const int nv = Scup - 1;
-        uint32_t bits = 0;
-        unsigned carry = 0xFF;
-        for (int chunk = 0; chunk < nv; chunk += 128) {
-            const int idx = chunk + lane * 4;
-            unsigned b[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                b[k] = idx + k < nv ? Dcup[Lcup - 2 - (idx + k)] : 0;
-                if (idx + k == 0)
-                    b[k] |= 0x0F;
-            }
-            unsigned before = __shfl_up_sync(FULL, b[3], 1);
-            if (lane == 0)
-                before = carry;
-            uint64_t v = 0;
-            int tot = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int nb = idx + k < nv ? (((b[k] & 0x7F) == 0x7F && before > 0x8F) ? 7 : 8) : 0;
-                v |= (uint64_t)(b[k] & ((1u << nb) - 1)) << tot;
-                tot += nb;
-                before = b[k];
-            }
-            int incl = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o)
-                    incl += t;
-            }
-            const uint32_t off = bits + (uint32_t)(incl - tot);
-            if (tot) {
-                const uint32_t wd = off >> 5, sft = off & 31;
-                const uint64_t sh = v << sft;
-                atomicOr(&vl[wd], (uint32_t)sh);
-                if ((uint32_t)(sh >> 32))
-                    atomicOr(&vl[wd + 1], (uint32_t)(sh >> 32));
-            }
-            bits += (uint32_t)__shfl_sync(FULL, incl, 31);
-            carry = __shfl_sync(FULL, b[3], 31);
-        }
-    }
-    /* MEL: bytes Dcup[Pcup..Lcup) forward, MSB first, 7 bits from the byte after a 0xFF (:429-440), with
-     * modDcup applied to the last two; stored in consumption order LSB first; ones past the end */
-    {
-        uint32_t bits = 0;
-        unsigned carry = 0;
-        for (int chunk = 0; chunk < Scup; chunk += 128) {
-            const int idx = chunk + lane * 4;
-            unsigned b[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                b[k] = idx + k < Scup ? Dcup[Pcup + idx + k] : 0;
-                if (idx + k == Scup - 2)
-                    b[k] |= 0x0F;
-                else if (idx + k == Scup - 1)
-                    b[k] = 0xFF;
-            }
-            unsigned before = __shfl_up_sync(FULL, b[3], 1);
-            if (lane == 0)
-                before = carry;
-            uint64_t v = 0;
-            int tot = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (idx + k < Scup) {
-                    const int nb = before == 0xFF ? 7 : 8;
-                    v |= (uint64_t)__brev(b[k] << (32 - nb)) << tot;
-                    tot += nb;
-                }
-                before = b[k];
-            }
-            int incl = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o)
-                    incl += t;
-            }
-            const uint32_t off = bits + (uint32_t)(incl - tot);
-            if (tot) {
-                const uint32_t wd = off >> 5, sft = off & 31;
-                const uint64_t sh = v << sft;
-                atomicOr(&ml[wd], (uint32_t)sh);
-                if ((uint32_t)(sh >> 32))
-                    atomicOr(&ml[wd + 1], (uint32_t)(sh >> 32));
-            }
-            bits += (uint32_t)__shfl_sync(FULL, incl, 31);
-            carry = __shfl_sync(FULL, b[3], 31);
-        }
-        __syncwarp();
-        if (lane == 0) {
-            ml[bits >> 5] |= 0xFFFFFFFFu << (bits & 31);
-            for (int i = (int)(bits >> 5) + 1; i < vlw; i++)
-                ml[i] = 0xFFFFFFFFu;
-        }
-    }
-    __syncwarp();
+    unstuff<US_VLC>(Dcup + Lcup - 2, Scup - 1, vl, lane);          /* zeros behind */
+    const uint32_t mbits = unstuff<US_MEL>(Dcup + Pcup, Scup, ml, lane);
+    ones_behind(ml, mbits, vlw, lane);
     uint32_t *out = scratch + scr_off[bi];
     for (int i = lane; i < 2 * vlw; i += 32)
         out[i] = vl[i];
@@ -445,10 +520,16 @@ __device__ __forceinline__ uint32_t dq(uint32_t mu, int sh53, float fscale, int 
     return dequant(mu, mode, M_b, roi_shift, bd);
 }
 
-template <int DQ>
+/* REFINE: the block carries SigProp / MagRef passes.  The samples are stored RAW (sign-magnitude, not
+ * dequantised; ht_refine_apply_kernel finishes them) with the reference's odd-edge masking (quirk Q2), and
+ * the significance map goes to scratch in "stripe nibble" layout: per 4-row stripe 32 bytes, byte j =
+ * sigma of columns 2j (low nibble) and 2j+1 (high nibble), bit i of a nibble = row i of the stripe -- bit
+ * order == the stripe-oriented scan order of jpeg2000htdec.c:1034-1185. */
+template <int DQ, bool REFINE>
 __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int Scup, const uint8_t *Dcup,
                                              const BandDesc &bd, const uint32_t *__restrict__ q, uint32_t *ms,
-                                             uint32_t *__restrict__ dst, int32_t *__restrict__ status, int lane)
+                                             uint32_t *__restrict__ dst, int32_t *__restrict__ status, int lane,
+                                             uint8_t *__restrict__ sigb)
 {
     const int w = d.w, h = d.h;
     const uint32_t dstride = d.dst_stride;
@@ -464,67 +545,13 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
     const int sh53 = 31 - M_b;
     const float fscale = bd.fscale;
 
-    /* un-stuff MagSgn: byte after 0xFF carries 7 bits (jpeg2000htdec.c:207-221); bit 7 of such a byte is
-     * OR-ed into the next byte's bit 0 exactly as the reference's 64-bit accumulator does.  Four bytes per
-     * lane, fetched as two aligned words. */
+    /* un-stuffed MagSgn bits in shared memory; past the end the decoder reads ones */
     const int ms_words = (Pcup + 3) / 4 + 2;
     for (int i = lane; i < ms_words; i += 32)
         ms[i] = 0;
     __syncwarp();
-    uint32_t ms_bits = 0;
-    {
-        const uint32_t *wbase = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(Dcup) & ~(uintptr_t)3);
-        const int bsh = (int)(reinterpret_cast<uintptr_t>(Dcup) & 3) * 8;
-        unsigned carry = 0;
-        for (int chunk = 0; chunk < Pcup; chunk += 128) {
-            const int idx = chunk + lane * 4;
-            uint32_t b4 = 0;
-            const int nvalid = min(4, Pcup - idx);
-            if (nvalid > 0) {
-                const uint32_t w0 = wbase[idx >> 2], w1 = wbase[(idx >> 2) + 1];
-                b4 = __funnelshift_r(w0, w1, bsh);
-                if (nvalid < 4)
-                    b4 &= (1u << (8 * nvalid)) - 1;
-            }
-            unsigned before = __shfl_up_sync(FULL, b4 >> 24, 1);
-            if (lane == 0)
-                before = carry;
-            uint64_t v = 0;
-            int tot = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const unsigned bk = (b4 >> (8 * k)) & 0xFF;
-                const int nb = k < nvalid ? (before == 0xFF ? 7 : 8) : 0;
-                v |= (uint64_t)bk << tot;
-                tot += nb;
-                before = bk;
-            }
-            int incl = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o)
-                    incl += t;
-            }
-            const uint32_t off = ms_bits + (uint32_t)(incl - tot);
-            if (tot) {
-                const uint32_t wd = off >> 5, sft = off & 31;
-                const uint64_t shv = v << sft;
-                atomicOr(&ms[wd], (uint32_t)shv);
-                if ((uint32_t)(shv >> 32))
-                    atomicOr(&ms[wd + 1], (uint32_t)(shv >> 32));
-            }
-            ms_bits += (uint32_t)__shfl_sync(FULL, incl, 31);
-            carry = __shfl_sync(FULL, b4 >> 24, 31);
-        }
-        __syncwarp();
-        if (lane == 0) {                                 /* past the end the decoder reads ones */
-            ms[ms_bits >> 5] |= 0xFFFFFFFFu << (ms_bits & 31);
-            for (int i = (int)(ms_bits >> 5) + 1; i < ms_words; i++)
-                ms[i] = 0xFFFFFFFFu;
-        }
-        __syncwarp();
-    }
+    const uint32_t ms_bits = unstuff<US_MAGSGN>(Dcup, Pcup, ms, lane);
+    ones_behind(ms, ms_bits, ms_words, lane);
 
     const int QW = (w + 1) >> 1, QH = (h + 1) >> 1;
     const bool act = lane < QW;
@@ -534,6 +561,7 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
     uint32_t ms_pos = 0;
     bool bad = false;
     const int x = 2 * lane;
+    unsigned prev_sg = 0;
     for (int qy = 0; qy < QH; qy++) {
         const unsigned mine = nextq;                     /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16; 0 in idle lanes */
         if (qy + 1 < QH)
@@ -598,11 +626,26 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
         pE3 = E3;
         /* samples of quad (qy, lane): i=0 (y,x) i=1 (y+1,x) i=2 (y,x+1) i=3 (y+1,x+1) */
         const int y = 2 * qy;
+        if (REFINE) {
+            /* quad -> raster with the reference's odd-edge masks (:975-1007, quirk Q2) */
+            const unsigned keep_row = qy != QH - 1 || !(h & 1), keep_col = lane != QW - 1 || !(w & 1);
+            const unsigned km = 1u | (keep_row << 1) | (keep_col << 2) | ((keep_row | keep_col) << 3);
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (!((km >> i) & 1))
+                    mu[i] = 0;
+            const unsigned sg = rho & km;
+            if (qy & 1)
+                sigb[(qy >> 1) * 32 + lane] = (uint8_t)((prev_sg & 3) | ((sg & 3) << 2) | (((prev_sg >> 2) & 3) << 4) |
+                                                        (((sg >> 2) & 3) << 6));
+            else
+                prev_sg = sg;
+        }
         if (act) {
-            const uint32_t o0 = dq<DQ>(mu[0], sh53, fscale, mode, M_b, roi_shift, bd),
-                           o1 = dq<DQ>(mu[1], sh53, fscale, mode, M_b, roi_shift, bd),
-                           o2 = dq<DQ>(mu[2], sh53, fscale, mode, M_b, roi_shift, bd),
-                           o3 = dq<DQ>(mu[3], sh53, fscale, mode, M_b, roi_shift, bd);
+            const uint32_t o0 = REFINE ? mu[0] : dq<DQ>(mu[0], sh53, fscale, mode, M_b, roi_shift, bd),
+                           o1 = REFINE ? mu[1] : dq<DQ>(mu[1], sh53, fscale, mode, M_b, roi_shift, bd),
+                           o2 = REFINE ? mu[2] : dq<DQ>(mu[2], sh53, fscale, mode, M_b, roi_shift, bd),
+                           o3 = REFINE ? mu[3] : dq<DQ>(mu[3], sh53, fscale, mode, M_b, roi_shift, bd);
             uint32_t *r0 = dst + (size_t)y * dstride + x, *r1 = r0 + dstride;
             if (vec && x + 1 < w) {
                 *reinterpret_cast<uint2 *>(r0) = make_uint2(o0, o2);
@@ -620,6 +663,8 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
             }
         }
     }
+    if (REFINE && (QH & 1) && !bad)
+        sigb[(QH >> 1) * 32 + lane] = (uint8_t)((prev_sg & 3) | (((prev_sg >> 2) & 3) << 4));
     if (bad) {
         __syncwarp();
         zero_block(dst, dstride, w, h, lane);
@@ -628,6 +673,7 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
         status[bi] = bad ? B200J2K_KERR_INVALID : 1;
 }
 
+template <bool REFINE>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order,
                  const uint32_t *__restrict__ scr_off, int nblocks, const uint8_t *__restrict__ bytes,
@@ -655,13 +701,258 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
     const int mode = (d.flags >> 1) & 3;
     const uint32_t *q = scratch + scr_off[bi] + 2 * ht_stream_words(Scup);
     uint32_t *ms = smem + (size_t)warp * stream_words;
-    if (d.roi_shift == 0 && mode == J2K_DWT53 && bd.i_stepsize == 32768)
-        magsgn_block<DQ_INT53>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane);
-    else if (d.roi_shift == 0 && mode == J2K_DWT97)
-        magsgn_block<DQ_FLOAT97>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane);
-    else
-        magsgn_block<DQ_GENERIC>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane);
+    if (REFINE) {
+        const RefLayout rl = ref_layout(d);
+        uint8_t *sigb = reinterpret_cast<uint8_t *>(const_cast<uint32_t *>(scratch) + scr_off[bi] + rl.sig);
+        magsgn_block<DQ_GENERIC, true>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane, sigb);
+    } else if (d.roi_shift == 0 && mode == J2K_DWT53 && bd.i_stepsize == 32768) {
+        magsgn_block<DQ_INT53, false>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane, nullptr);
+    } else if (d.roi_shift == 0 && mode == J2K_DWT97) {
+        magsgn_block<DQ_FLOAT97, false>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane, nullptr);
+    } else {
+        magsgn_block<DQ_GENERIC, false>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane, nullptr);
+    }
 }
+
+/* ---- refinement passes: K0R un-stuff Dref, K3 SigProp (lane per block), K4 MagRef + apply + dequantise ---- */
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+ht_unstuff_ref_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order,
+                      const uint32_t *__restrict__ scr_off, int nblocks, const uint8_t *__restrict__ bytes,
+                      uint32_t *__restrict__ scratch, int warp_words)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * WARPS_PER_CTA + warp;
+    if (gw >= nblocks)
+        return;
+    const uint32_t bi = order[gw];
+    const CblkDesc d = descs[bi];
+    const RefLayout rl = ref_layout(d);
+    const uint8_t *Dref = bytes + d.data_off + d.Lcup;
+    const int Lref = d.Lref;
+    uint32_t *sp = smem + (size_t)warp * warp_words, *mr = sp + rl.rw;
+    for (int i = lane; i < 2 * rl.rw; i += 32)
+        sp[i] = 0;
+    __syncwarp();
+    unstuff<US_SIGPROP>(Dref, Lref, sp, lane);                    /* zeros behind both */
+    unstuff<US_MAGREF>(Dref + Lref - 1, Lref, mr, lane);
+    uint32_t *out = scratch + scr_off[bi] + rl.sp;
+    for (int i = lane; i < 2 * rl.rw; i += 32)
+        out[i] = sp[i];
+}
+
+constexpr uint64_t NIB0 = 0x1111111111111111ull;
+
+/* horizontal 3-neighbourhood OR over a 64-column stripe in nibble layout (column x = bits 4x..4x+3 of v[x/16]) */
+__device__ __forceinline__ void dilate_cols(const uint64_t (&v)[4], uint64_t (&o)[4])
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        uint64_t t = v[k] | (v[k] << 4) | (v[k] >> 4);
+        if (k > 0)
+            t |= v[k - 1] >> 60;
+        if (k < 3)
+            t |= v[k + 1] << 60;
+        o[k] = t;
+    }
+}
+
+/* H7 SigProp (jpeg2000htdec.c:1016-1131), one code-block per LANE, entirely on bit masks.
+ * A sample is a member when it is insignificant and one of its 8 neighbours is significant: significant in
+ * the cleanup pass, or made significant earlier in this pass's scan (stripes of 4 rows, column by column).
+ * Static members come from dilating the cleanup significance map; the others are added as the scan sets
+ * new bits: a newly significant sample can only recruit the sample below it and the three samples of the
+ * next column (the next stripe sees it through its "row above").  In nibble layout the scan order IS the
+ * bit order, so the scan is a find-first-set loop over the candidate mask. */
+__global__ void __launch_bounds__(32)
+ht_sigprop_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order,
+                  const uint32_t *__restrict__ scr_off, int nblocks, uint32_t *__restrict__ scratch,
+                  const int32_t *__restrict__ status)
+{
+    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gt >= nblocks)
+        return;
+    const uint32_t bi = order[gt];
+    if (status[bi] != 1)
+        return;
+    const CblkDesc d = descs[bi];
+    const RefLayout rl = ref_layout(d);
+    const int w = d.w, h = d.h;
+    const bool causal = d.flags & 1;
+    uint32_t *base = scratch + scr_off[bi];
+    LsbReader sp;
+    sp.init(base + rl.sp, rl.rw, 0);
+    const uint64_t *sig = reinterpret_cast<const uint64_t *>(base + rl.sig);
+    uint64_t *nsg = reinterpret_cast<uint64_t *>(base + rl.nsg), *sgn = reinterpret_cast<uint64_t *>(base + rl.sgn);
+    uint64_t CM[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int cols = min(max(w - 16 * k, 0), 16);
+        CM[k] = cols >= 16 ? ~0ull : ((1ull << (4 * cols)) - 1);
+    }
+    uint64_t ab[4] = { 0, 0, 0, 0 };            /* (sigma | new) of the row above the stripe, at nibble bit 0 */
+    uint64_t cur[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        cur[k] = sig[k];
+    for (int s = 0; s < rl.nst; s++) {
+        uint64_t nx[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            nx[k] = s + 1 < rl.nst ? sig[4 * (s + 1) + k] : 0;
+        const int gh = min(4, h - 4 * s);
+        uint64_t N[4] = { 0, 0, 0, 0 }, SG[4] = { 0, 0, 0, 0 };
+        if (gh > 0) {
+            const uint64_t RM = NIB0 * ((1u << gh) - 1);
+            uint64_t D[4], AD[4], BD[4], bl[4], cand[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                bl[k] = (nx[k] & NIB0) << 3;
+            dilate_cols(cur, D);
+            dilate_cols(ab, AD);
+            dilate_cols(bl, BD);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint64_t up = ((D[k] << 1) & (NIB0 * 0xE)) | AD[k];
+                uint64_t dn = ((D[k] >> 1) & (NIB0 * 0x7)) | BD[k];
+                if (causal)                      /* the row below the stripe's last row is not consulted (:1045) */
+                    dn &= ~(NIB0 << (gh - 1));
+                cand[k] = (D[k] | up | dn) & ~cur[k] & RM & CM[k];
+            }
+            uint64_t carry = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint64_t okm = ~cur[k] & RM & CM[k];
+                uint64_t c = cand[k] | (carry & okm);
+                carry = 0;
+                uint64_t n = 0, sg = 0;
+#pragma unroll 1
+                for (int g = 0; g < 4; g++) {
+                    const uint64_t gm = 0xFFFFull << (16 * g);
+                    uint64_t m;
+                    while ((m = c & gm) != 0) {
+                        const int b = __ffsll((long long)m) - 1;
+                        c &= c - 1;
+                        sp.refill();
+                        const unsigned bit = (unsigned)sp.win & 1;
+                        sp.drop(1);
+                        if (bit) {
+                            n |= 1ull << b;
+                            const int i = b & 3;
+                            uint64_t nc = i < 3 ? 1ull << (b + 1) : 0;
+                            const uint64_t nb3 = ((7u << i) >> 1) & 0xF;       /* rows i-1 .. i+1 of the next column */
+                            const int colpos = (b | 3) + 1;
+                            if (colpos < 64)
+                                nc |= nb3 << colpos;
+                            else
+                                carry |= nb3;
+                            c |= nc & okm;
+                        }
+                    }
+                    /* sign bits of the group's newly significant samples, in scan order (:1066-1076) */
+                    uint64_t ng = n & gm;
+                    while (ng) {
+                        const int b = __ffsll((long long)ng) - 1;
+                        ng &= ng - 1;
+                        sp.refill();
+                        sg |= (uint64_t)((unsigned)sp.win & 1) << b;
+                        sp.drop(1);
+                    }
+                }
+                N[k] = n;
+                SG[k] = sg;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            nsg[4 * s + k] = N[k];
+            sgn[4 * s + k] = SG[k];
+            ab[k] = ((cur[k] | N[k]) >> 3) & NIB0;
+            cur[k] = nx[k];
+        }
+    }
+}
+
+/* H8 MagRef (:1136-1185) + the sample updates of both refinement passes + ROI shift + dequantisation.
+ * Warp per block, lane j = columns 2j, 2j+1 of a stripe (one byte of the nibble-layout maps).  The k-th
+ * cleanup-significant sample in scan order takes the k-th MagRef bit: its rank is a popcount over the
+ * lane's byte plus a warp prefix sum. */
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+ht_refine_apply_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order,
+                       const uint32_t *__restrict__ scr_off, int nblocks, const BandDesc *__restrict__ bands,
+                       const uint32_t *__restrict__ scratch, uint32_t *__restrict__ coef,
+                       const int32_t *__restrict__ status)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * WARPS_PER_CTA + warp;
+    if (gw >= nblocks)
+        return;
+    const uint32_t bi = order[gw];
+    if (status[bi] != 1)
+        return;
+    const CblkDesc d = descs[bi];
+    const BandDesc bd = bands[d.band];
+    const RefLayout rl = ref_layout(d);
+    const int w = d.w, h = d.h;
+    const int mode = (d.flags >> 1) & 3;
+    const int rem = d.npasses % 3;
+    const int plhd = rem ? d.npasses - rem : d.npasses - 3;
+    const int z_blk = d.npasses - plhd;
+    const int S_blk = (plhd / 3 + d.zbp) & 0xFF;
+    const int p = 30 - S_blk - 1;
+    const uint32_t *base = scratch + scr_off[bi];
+    const uint32_t *mr = base + rl.mr;
+    const uint32_t mr_limit = (uint32_t)(rl.rw - 2) * 32;
+    const uint8_t *sigb = reinterpret_cast<const uint8_t *>(base + rl.sig);
+    const uint8_t *nsgb = reinterpret_cast<const uint8_t *>(base + rl.nsg);
+    const uint8_t *sgnb = reinterpret_cast<const uint8_t *>(base + rl.sgn);
+    uint32_t *dst = coef + d.dst_off;
+    const uint32_t dstride = d.dst_stride;
+    const int x = 2 * lane;
+    uint32_t mr_pos = 0;
+    for (int s = 0; s < rl.nst; s++) {
+        const int gh = min(4, h - 4 * s);
+        if (gh <= 0)
+            break;
+        const unsigned sb = sigb[s * 32 + lane], nb = z_blk > 1 ? nsgb[s * 32 + lane] : 0, gb = sgnb[s * 32 + lane];
+        const unsigned rm = (1u << gh) - 1;
+        const unsigned vm = ((x < w ? 0x0Fu : 0) | (x + 1 < w ? 0xF0u : 0)) & (rm | (rm << 4));
+        const unsigned sv = z_blk > 2 ? sb & vm : 0;
+        const int cnt = __popc(sv);
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        const uint32_t pos = min(mr_pos + (uint32_t)(incl - cnt), mr_limit);
+        mr_pos += (uint32_t)__shfl_sync(FULL, incl, 31);
+        const uint32_t win = cnt ? __funnelshift_r(mr[pos >> 5], mr[(pos >> 5) + 1], pos & 31) : 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (i >= gh)
+                break;
+            const int y = 4 * s + i;
+            uint32_t *row = dst + (size_t)y * dstride + x;
+#pragma unroll
+            for (int c = 0; c < 2; c++) {
+                const int bp = 4 * c + i;
+                if (!((vm >> bp) & 1))
+                    continue;
+                uint32_t mu = row[c];
+                if ((nb >> bp) & 1)              /* SigProp: newly significant (:1057-1060, :1066-1076) */
+                    mu |= (1u << p) | (1u << (p - 1)) | (((gb >> bp) & 1u) << 31);
+                if ((sv >> bp) & 1) {            /* MagRef (:1161-1165) */
+                    const uint32_t bit = (win >> __popc(sv & ((1u << bp) - 1))) & 1;
+                    mu = (mu & ((0xFFFFFFFEu | bit) << p)) | (1u << (p - 1));
+                }
+                row[c] = dequant(mu, mode, d.M_b, d.roi_shift, bd);
+            }
+        }
+    }
+}
+
 
 }  // namespace
 
@@ -670,41 +961,88 @@ uint32_t ht_cleanup_scratch_words(const CblkDesc &d)
 {
     if (d.npasses == 0 || d.Lcup < 2)
         return 0;
+    if ((d.npasses % 3) != 1)
+        return (uint32_t)ref_layout(d).total;
     const int S = d.Lcup < 4079 ? d.Lcup : 4079;
     const int QW = (d.w + 1) >> 1, QH = (d.h + 1) >> 1;
-    return (uint32_t)(2 * ht_stream_words(S) + QW * QH);
+    return (uint32_t)((2 * ht_stream_words(S) + QW * QH + 1) & ~1);
+}
+
+static int set_smem(const void *fn, size_t bytes)
+{
+    if (bytes > 227 * 1024)
+        return -1;
+    if (bytes > 48 * 1024 && cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess)
+        return -2;
+    return 0;
 }
 
 int launch_ht_cleanup(cudaStream_t stream, const CblkDesc *descs, const uint32_t *order, const uint32_t *scr_off,
-                      int n_coded, int n_all, const uint8_t *bytes, const BandDesc *bands, void *scratch, void *coef,
-                      int32_t *status, int max_Lcup)
+                      int n_refine, int n_coded, int n_zero, const uint8_t *bytes, const BandDesc *bands, void *scratch,
+                      void *coef, int32_t *status, int max_Lcup, int max_Lref, cudaEvent_t after_unstuff,
+                      cudaEvent_t after_vlc)
 {
-    if (n_all <= 0)
-        return 0;
-    int launches = 0;
-    if (n_coded > 0) {
+    int launches = 0, r;
+    const int n_vlc = n_refine + n_coded;
+    uint32_t *scr = (uint32_t *)scratch;
+    if (n_vlc > 0) {
         const int warp_words = 2 * ht_stream_words(max_Lcup < 4079 ? max_Lcup : 4079);
         const size_t smem0 = (size_t)warp_words * 4 * WARPS_PER_CTA;
-        if (smem0 > 48 * 1024 &&
-            cudaFuncSetAttribute(ht_unstuff_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem0) != cudaSuccess)
-            return -2;
-        ht_unstuff_kernel<<<(n_coded + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, smem0, stream>>>(
-            descs, order, scr_off, n_coded, bytes, (uint32_t *)scratch, warp_words);
-        ht_vlc_kernel<<<(n_coded + VLC_LANES_PER_CTA - 1) / VLC_LANES_PER_CTA, VLC_LANES_PER_CTA, 0, stream>>>(
-            descs, order, scr_off, n_coded, bytes, (uint32_t *)scratch);
-        launches += 2;
+        if ((r = set_smem((const void *)ht_unstuff_kernel, smem0)) < 0)
+            return r;
+        ht_unstuff_kernel<<<(n_vlc + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, smem0, stream>>>(
+            descs, order, scr_off, n_vlc, bytes, scr, warp_words);
+        launches++;
     }
+    if (n_refine > 0) {
+        const int rw = ((max_Lref + 3) / 4 + 3 + 1) & ~1;
+        const size_t smemr = (size_t)2 * rw * 4 * WARPS_PER_CTA;
+        if ((r = set_smem((const void *)ht_unstuff_ref_kernel, smemr)) < 0)
+            return r;
+        ht_unstuff_ref_kernel<<<(n_refine + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, smemr, stream>>>(
+            descs, order, scr_off, n_refine, bytes, scr, 2 * rw);
+        launches++;
+    }
+    if (after_unstuff)
+        cudaEventRecord(after_unstuff, stream);
+    if (n_vlc > 0) {
+        ht_vlc_kernel<<<(n_vlc + VLC_LANES_PER_CTA - 1) / VLC_LANES_PER_CTA, VLC_LANES_PER_CTA, 0, stream>>>(
+            descs, order, scr_off, n_vlc, bytes, scr);
+        launches++;
+    }
+    if (after_vlc)
+        cudaEventRecord(after_vlc, stream);
+    if (n_coded + n_zero > 0) {
+        const int stream_words = (max_Lcup + 3) / 4 + 4;
+        const size_t smem2 = (size_t)stream_words * 4 * WARPS_PER_CTA;
+        if ((r = set_smem((const void *)ht_magsgn_kernel<false>, smem2)) < 0)
+            return r;
+        ht_magsgn_kernel<false><<<(n_coded + n_zero + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, smem2, stream>>>(
+            descs, order + n_refine, scr_off, n_coded + n_zero, bytes, bands, scr, (uint32_t *)coef, status, stream_words);
+        launches++;
+    }
+    return cudaGetLastError() == cudaSuccess ? launches : -3;
+}
+
+int launch_ht_refine(cudaStream_t stream, const CblkDesc *descs, const uint32_t *order, const uint32_t *scr_off,
+                     int n_refine, const uint8_t *bytes, const BandDesc *bands, void *scratch, void *coef,
+                     int32_t *status, int max_Lcup)
+{
+    if (n_refine <= 0)
+        return 0;
+    int r;
+    uint32_t *scr = (uint32_t *)scratch;
     const int stream_words = (max_Lcup + 3) / 4 + 4;
     const size_t smem2 = (size_t)stream_words * 4 * WARPS_PER_CTA;
-    if (smem2 > 227 * 1024)
-        return -1;
-    if (smem2 > 48 * 1024 &&
-        cudaFuncSetAttribute(ht_magsgn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2) != cudaSuccess)
-        return -2;
-    ht_magsgn_kernel<<<(n_all + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, smem2, stream>>>(
-        descs, order, scr_off, n_all, bytes, bands, (const uint32_t *)scratch, (uint32_t *)coef, status, stream_words);
-    launches++;
-    return cudaGetLastError() == cudaSuccess ? launches : -3;
+    if ((r = set_smem((const void *)ht_magsgn_kernel<true>, smem2)) < 0)
+        return r;
+    const int wgrid = (n_refine + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    ht_magsgn_kernel<true><<<wgrid, WARPS_PER_CTA * 32, smem2, stream>>>(descs, order, scr_off, n_refine, bytes, bands, scr,
+                                                                         (uint32_t *)coef, status, stream_words);
+    ht_sigprop_kernel<<<(n_refine + 31) / 32, 32, 0, stream>>>(descs, order, scr_off, n_refine, scr, status);
+    ht_refine_apply_kernel<<<wgrid, WARPS_PER_CTA * 32, 0, stream>>>(descs, order, scr_off, n_refine, bands, scr,
+                                                                     (uint32_t *)coef, status);
+    return cudaGetLastError() == cudaSuccess ? 3 : -3;
 }
 
 }  // namespace b200j2k

@@ -23,15 +23,25 @@ size_t ht_smem_bytes(bool refine, int stream_words, int maxQW, int samp_words, i
 /* Split cleanup pipeline (ht_cleanup.cu) for cleanup-only blocks up to 64 samples wide.
  * Words of one un-stuffed VLC or MEL bit array of a block whose suffix is Scup bytes long. */
 static inline __host__ __device__ int ht_stream_words(int Scup) { return (Scup + 3) / 4 + 3; }
-/* Host: words of HBM scratch a block needs (two un-stuffed bit arrays sized for the largest possible
- * suffix + one word per quad); 0 for blocks without data. */
+/* Host: words of HBM scratch a block needs (un-stuffed bit arrays sized for the largest possible suffix,
+ * one word per quad and -- with refinement passes -- the Dref bit arrays and three significance maps);
+ * always even, 0 for blocks without data. */
 uint32_t ht_cleanup_scratch_words(const CblkDesc &d);
-/* scr_off: device array of scratch word offsets, indexed like descs.  order[0..n_coded) are blocks with
- * data (their headers are validated on the device), order[n_coded..n_all) only need zeros.
+/* scr_off: device array of scratch word offsets, indexed like descs.  order[] = [refine | coded | zero]:
+ *   refine  blocks with SigProp / MagRef passes (<= 64 samples wide): un-stuffed and VLC-decoded here,
+ *           finished by launch_ht_refine
+ *   coded   cleanup-only blocks with data (headers are validated on the device)
+ *   zero    blocks that only need zeros
  * Returns the number of kernels queued or < 0. */
 int launch_ht_cleanup(cudaStream_t stream, const CblkDesc *descs, const uint32_t *order, const uint32_t *scr_off,
-                      int n_coded, int n_all, const uint8_t *bytes, const BandDesc *bands, void *scratch, void *coef,
-                      int32_t *status, int max_Lcup);
+                      int n_refine, int n_coded, int n_zero, const uint8_t *bytes, const BandDesc *bands, void *scratch,
+                      void *coef, int32_t *status, int max_Lcup, int max_Lref, cudaEvent_t after_unstuff = nullptr,
+                      cudaEvent_t after_vlc = nullptr);
+/* MagSgn (raw samples + significance map), SigProp (lane per block), MagRef + apply + dequantise for
+ * order[0..n_refine); status must be a device array (the later kernels skip blocks the earlier ones rejected) */
+int launch_ht_refine(cudaStream_t stream, const CblkDesc *descs, const uint32_t *order, const uint32_t *scr_off,
+                     int n_refine, const uint8_t *bytes, const BandDesc *bands, void *scratch, void *coef,
+                     int32_t *status, int max_Lcup);
 
 /* Inverse DWT levels + final MCT / level shift / clip / pack.
  * tcs/groups: device copies of the plan tables.  coefA: HT output (Mallat layout), coefB/coefC: LL

@@ -105,9 +105,10 @@ int64_t b200j2k_decode(b200j2k_decoder *dec, const uint8_t *pkt, int64_t pkt_siz
 int b200j2k_stage(b200j2k_decoder *dec, int slot, const uint8_t *pkt, int64_t pkt_size, b200j2k_frame_info *info);
 int b200j2k_run_staged(b200j2k_decoder *dec, int slot);
 int b200j2k_sync(b200j2k_decoder *dec, int slot);
-/* like run_staged, but brackets the stages with CUDA events on the slot's stream and waits:
- * ms[0] HT decode (cleanup-only blocks), ms[1] HT decode (blocks with refinement passes),
- * ms[2] intermediate IDWT levels, ms[3] fused last level + MCT + pack */
+/* like run_staged, but brackets the stages with CUDA events on the slot's stream and waits.  ms[6]:
+ * [0] HT un-stuff (VLC + MEL bit arrays), [1] HT MEL/CxtVLC/U-VLC (lane per block), [2] HT MagSgn + dequantisation
+ * (+ blocks wider than 64 samples on the general kernel), [3] HT blocks with refinement passes,
+ * [4] intermediate IDWT levels, [5] fused last level + MCT + pack */
 int b200j2k_run_staged_timed(b200j2k_decoder *dec, int slot, float *ms);
 /* copies the staged slot's picture to host planes (synchronous) */
 int b200j2k_fetch(b200j2k_decoder *dec, int slot, uint8_t *const data[4], const int linesize[4]);

@@ -19,10 +19,10 @@ for name in names:
     cs, planes, p = j2kgen.make_config(name)
     with fb.Jpeg2000Decoder(device=0, slots=1) as dec:
         info = dec.stage(0, cs)
-        ms = np.zeros(4)
+        ms = np.zeros(6)
         dec.run_staged_timed(0)
         for _ in range(runs):
             ms += np.array(dec.run_staged_timed(0))
         ms /= runs
-        print(name, info.width, info.height, info.ncodeblocks, "stage ms [ht plain, ht refine, idwt levels, final]",
+        print(name, info.width, info.height, info.ncodeblocks, "stage ms [unstuff, vlc, magsgn, refine-blocks, idwt levels, final]",
               [round(float(x), 4) for x in ms], "total", round(float(ms.sum()), 4), flush=True)
