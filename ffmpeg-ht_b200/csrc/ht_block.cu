@@ -130,102 +130,23 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
     for (int i = lane; i < ms_words + vl_words; i += 32)
         streams[i] = 0;
     __syncwarp();
-    /* un-stuff VLC: read order k = 0.. is Dcup[Lcup-2-k]; modDcup sets the low nibble of the first byte
-     * and makes the byte "read before it" 0xFF (:1277-1278, :283-295) */
-    uint32_t vl_bits = 0;
+    /* un-stuffed VLC bits (backward reader, with the reference's tail behind them) and MagSgn bits (forward,
+     * ones behind): see unstuff() in ht_common.cuh */
+    BwdTail vtail;
     {
-        const int nv = Scup - 1;                        /* bytes Dcup[Pcup .. Lcup-2] */
-        unsigned carry = 0xFF;
-        for (int chunk = 0; chunk < nv; chunk += 128) {
-            const int idx = chunk + lane * 4;
-            unsigned b[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                b[k] = idx + k < nv ? Dcup[Lcup - 2 - (idx + k)] : 0;
-                if (idx + k == 0)
-                    b[k] |= 0x0F;
-            }
-            unsigned before = __shfl_up_sync(FULL, b[3], 1);
-            if (lane == 0)
-                before = carry;
-            uint64_t v = 0;
-            int tot = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int nb = idx + k < nv ? (((b[k] & 0x7F) == 0x7F && before > 0x8F) ? 7 : 8) : 0;
-                v |= (uint64_t)(b[k] & ((1u << nb) - 1)) << tot;
-                tot += nb;
-                before = b[k];
-            }
-            int incl = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o)
-                    incl += t;
-            }
-            const uint32_t off = vl_bits + (uint32_t)(incl - tot);
-            if (tot) {
-                const uint32_t wd = off >> 5, sft = off & 31;
-                const uint64_t sh = v << sft;
-                atomicOr(&vl[wd], (uint32_t)sh);
-                if ((uint32_t)(sh >> 32))
-                    atomicOr(&vl[wd + 1], (uint32_t)(sh >> 32));
-            }
-            vl_bits += (uint32_t)__shfl_sync(FULL, incl, 31);
-            carry = __shfl_sync(FULL, b[3], 31);
+        const uint32_t vbits = unstuff<US_VLC>(Dcup + Lcup - 2, Scup - 1, vl, lane);
+        unsigned b0 = Dcup[Pcup], b1 = Dcup[Pcup + 1];
+        if (Scup == 2) {
+            b0 |= 0x0F;
+            b1 = 0xFF;
+        } else if (Scup == 3) {
+            b1 |= 0x0F;
         }
+        vtail = bwd_tail_make(vbits, Scup - 1, b0, b1);
+        bwd_tail_fill(vl, vl_words, vtail, lane);
     }
-    /* un-stuff MagSgn: byte after 0xFF carries 7 bits (:207-221); bit 7 of such a byte is OR-ed into the
-     * next byte's bit 0 exactly as the reference's 64-bit accumulator does */
-    uint32_t ms_bits = 0;
-    {
-        unsigned carry = 0;
-        for (int chunk = 0; chunk < Pcup; chunk += 128) {
-            const int idx = chunk + lane * 4;
-            unsigned b[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-                b[k] = idx + k < Pcup ? Dcup[idx + k] : 0;
-            unsigned before = __shfl_up_sync(FULL, b[3], 1);
-            if (lane == 0)
-                before = carry;
-            uint64_t v = 0;
-            int tot = 0;
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                int nb = idx + k < Pcup ? (before == 0xFF ? 7 : 8) : 0;
-                v |= (uint64_t)b[k] << tot;
-                tot += nb;
-                before = b[k];
-            }
-            int incl = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o)
-                    incl += t;
-            }
-            const uint32_t off = ms_bits + (uint32_t)(incl - tot);
-            if (tot) {
-                const uint32_t wd = off >> 5, s = off & 31;
-                const uint64_t sh = v << s;
-                atomicOr(&ms[wd], (uint32_t)sh);
-                if ((uint32_t)(sh >> 32))
-                    atomicOr(&ms[wd + 1], (uint32_t)(sh >> 32));
-            }
-            ms_bits += (uint32_t)__shfl_sync(FULL, incl, 31);
-            carry = __shfl_sync(FULL, b[3], 31);
-        }
-        __syncwarp();
-        /* past the end the decoder reads ones */
-        if (lane == 0) {
-            ms[ms_bits >> 5] |= 0xFFFFFFFFu << (ms_bits & 31);
-            for (int i = (int)(ms_bits >> 5) + 1; i < ms_words; i++)
-                ms[i] = 0xFFFFFFFFu;
-        }
-        __syncwarp();
-    }
+    const uint32_t ms_bits = unstuff<US_MAGSGN>(Dcup, Pcup, ms, lane);
+    ones_behind(ms, ms_bits, ms_words, lane);
 
     const int QW = (w + 1) >> 1, QH = (h + 1) >> 1;
     uint32_t *rowprev = rowbuf, *rowcur = rowbuf + (maxQW + 2);
@@ -239,7 +160,7 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
 
     Mel mel = { Dcup + Pcup, Scup, 0, 0, 0, 0, 0, 0 };
     uint32_t vpos = 4;                                   /* the Scup nibble is skipped (:283-295) */
-    const uint32_t vlimit = (uint32_t)(vl_words - 3) * 32;
+    const VlcArr varr = { vl, vl_words, vtail };
     uint32_t *qinfo = rowbuf + 2 * (maxQW + 2);
     uint32_t ms_pos = 0;
     bool bad = false;
@@ -251,14 +172,14 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
             const int nq = min(32, QW - qb);
             const int qx = qb + lane;
             if (qy == 0) {
-                decode_segment<true>(mel, vl, vpos, vlimit, tab, uvtab, nq, 0, 0, carry, qinfo);
+                decode_segment<true>(mel, varr, vpos, tab, uvtab, nq, 0, 0, carry, qinfo);
             } else {
                 /* row[] is stored with a +1 offset and zero sentinels at both ends */
                 const unsigned n = qx < QW ? rowprev[qx + 1] : 0, nw = qx < QW ? rowprev[qx] : 0,
                                ne = qx < QW ? rowprev[qx + 2] : 0;
                 const unsigned mA = __ballot_sync(FULL, ((n >> 1) | (nw >> 3)) & 1);   /* sigma_N[1] | sigma_NW[3] */
                 const unsigned mC = __ballot_sync(FULL, ((n >> 3) | (ne >> 1)) & 1);   /* sigma_N[3] | sigma_NE[1] */
-                decode_segment<false>(mel, vl, vpos, vlimit, tab + 1024, uvtab, nq, mA, mC, carry, qinfo);
+                decode_segment<false>(mel, varr, vpos, tab + 1024, uvtab, nq, mA, mC, carry, qinfo);
             }
             __syncwarp();
             const unsigned mine = lane < nq ? qinfo[lane] : 0;   /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16 */
@@ -414,9 +335,17 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
                 }
             }
             if (z_blk > 2) {
-                /* H8 MagRef (:1136-1185): bits read backwards from the end of Dref; byte Dref[Lref] reads 0xFF */
-                int pos = Lref - 1;
-                unsigned prev = 0xFF;
+                /* H8 MagRef (:1136-1185): bits read backwards from the end of Dref with the reference's group
+                 * reader (see BwdTail): byte k of its read order and the byte it compares against */
+                auto ref_byte = [&](int i) -> unsigned {
+                    if (i < Lref)
+                        return Dref[i];
+                    const uint32_t at = (uint32_t)Lcup + (uint32_t)i;
+                    return at == d.length ? 0xFFu : (at < d.length ? Dref[i] : 0u);
+                };
+                const int mpad = 4 - (Lref & 3);
+                int mk = 0;
+                unsigned prev = ref_byte(Lref);
                 uint32_t acc = 0;
                 int n = 0;
                 for (int y0 = 0; y0 < h; y0 += 4) {
@@ -426,8 +355,14 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
                             if (!(st[(y + 1) * SW + x + 1] & ST_SIGMA))
                                 continue;
                             if (n == 0) {
-                                unsigned b = pos >= 0 ? Dref[pos] : 0;
-                                pos--;
+                                unsigned b = 0;
+                                if (mk < Lref) {
+                                    b = Dref[Lref - 1 - mk];
+                                } else if (mk >= Lref + mpad && ((mk - Lref - mpad) & 3) == 0) {
+                                    b = ref_byte(0);             /* parked reader: base[0] again, compared with base[1] */
+                                    prev = ref_byte(1);
+                                }
+                                mk++;
                                 n = ((b & 0x7F) == 0x7F && prev > 0x8F) ? 7 : 8;
                                 acc = b & ((1u << n) - 1);
                                 prev = b;

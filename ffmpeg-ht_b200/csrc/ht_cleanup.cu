@@ -78,153 +78,6 @@ __device__ __forceinline__ int ht_block_scup(const CblkDesc &d, const uint8_t *D
     return Scup;
 }
 
-/* four bytes p[0..3] (p[0] in the low byte) fetched as two aligned words; the caller guarantees that the
- * aligned words around p are readable (the byte buffer has 64 bytes of slack and a 256-byte aligned base) */
-__device__ __forceinline__ uint32_t load4(const uint8_t *p)
-{
-    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-    return __funnelshift_r(w[0], w[1], (int)(a & 3) * 8);
-}
-
-/*
- * Parallel removal of byte stuffing.  The five bit streams of an HT code-block differ only in direction,
- * in the stuffing rule and in how a byte's bits are consumed; all become contiguous LSB-first bit arrays
- * (first bit consumed = bit 0 of word 0):
- *   US_MAGSGN  Dcup[0..Pcup) forward; 7 bits after 0xFF, bit 7 of such a byte is OR-ed into the next
- *              byte's bit 0 as the reference's accumulator does (jpeg2000htdec.c:207-221)
- *   US_MEL     Dcup[Pcup..Lcup) forward, MSB first, 7 bits after 0xFF, modDcup on the last two bytes
- *              (:429-440, :1277-1278)
- *   US_VLC     Dcup[Lcup-2] down to Dcup[Pcup]; 7 bits when (b & 0x7F) == 0x7F and the byte read before is
- *              > 0x8F; first byte |= 0x0F, the byte "read before" it is 0xFF (:145-201, :283-295)
- *   US_SIGPROP Dref[0..Lref) forward, LSB first, 7 bits after 0xFF (:442-460)
- *   US_MAGREF  Dref[Lref-1] down to Dref[0], VLC stuffing rule, first "read before" is 0xFF (:123-131)
- * first: address of the first byte in read order; n: bytes.  Four bytes per lane and chunk, fetched as two
- * aligned words one chunk ahead; a warp prefix sum over the 7/8-bit lengths places them.  out[] must be
- * zeroed.  Returns the number of bits written (warp-uniform).
- */
-enum { US_MAGSGN, US_MEL, US_VLC, US_SIGPROP, US_MAGREF };
-
-/* 0x01 in every byte of x that equals the corresponding byte of y */
-__device__ __forceinline__ uint64_t bytes_eq(uint64_t x, uint64_t y)
-{
-    uint64_t d = x ^ y;                                  /* zero byte <=> equal */
-    d |= d >> 4;
-    d |= d >> 2;
-    d |= d >> 1;
-    return ~d & 0x0101010101010101ull;
-}
-
-/* 0x01 in every byte of x that is > 0x8F */
-__device__ __forceinline__ uint64_t bytes_gt8f(uint64_t x)
-{
-    /* b > 0x8F  <=>  bit 7 set and (b & 0x70) != 0 */
-    const uint64_t hi = x >> 7, any = (x >> 6) | (x >> 5) | (x >> 4);
-    return hi & any & 0x0101010101010101ull;
-}
-
-template <int KIND>
-__device__ __forceinline__ uint32_t unstuff(const uint8_t *first, int n, uint32_t *out, int lane)
-{
-    constexpr bool BACKWARD = KIND == US_VLC || KIND == US_MAGREF;
-    constexpr bool RULE_A = BACKWARD;           /* 7 bits when (b & 0x7F) == 0x7F && before > 0x8F; else: before == 0xFF */
-    constexpr int BPL = 8;                      /* bytes per lane and chunk */
-    uint32_t bits = 0;
-    unsigned carry = RULE_A ? 0xFF : 0;
-    /* eight bytes in read order, first byte read = low byte */
-    auto fetch = [&](int idx) -> uint64_t {
-        if (idx >= n)
-            return 0;
-        const uint8_t *p = BACKWARD ? first - 7 - idx : first + idx;
-        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
-        const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-        const int sh = (int)(a & 3) * 8;
-        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
-        return BACKWARD ? ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123)
-                        : ((uint64_t)hi << 32) | lo;
-    };
-    uint64_t nxt = fetch(lane * BPL);
-    for (int chunk = 0; chunk < n; chunk += 32 * BPL) {
-        const int idx = chunk + lane * BPL;
-        uint64_t x = nxt;
-        nxt = fetch(idx + 32 * BPL);
-        const int nvalid = min(max(n - idx, 0), BPL);
-        const uint64_t vmask = nvalid >= 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
-        x &= vmask;
-        if (KIND == US_VLC && idx == 0)
-            x |= 0x0F;                                   /* modDcup: low nibble of the first byte read */
-        if (KIND == US_MEL) {                            /* modDcup: last two bytes of the segment */
-            const int k2 = n - 2 - idx, k1 = n - 1 - idx;
-            if (k2 >= 0 && k2 < 8)
-                x |= 0x0Full << (8 * k2);
-            if (k1 >= 0 && k1 < 8)
-                x |= 0xFFull << (8 * k1);
-        }
-        /* the byte read before each byte */
-        unsigned before = __shfl_up_sync(FULL, (unsigned)(x >> 56), 1);
-        if (lane == 0)
-            before = carry;
-        const uint64_t prev = (x << 8) | before;
-        /* 0x01 per byte that carries only 7 bits */
-        uint64_t st;
-        if (RULE_A)
-            st = bytes_eq(x | 0x8080808080808080ull, ~0ull) & bytes_gt8f(prev);
-        else
-            st = bytes_eq(prev, ~0ull);
-        st &= vmask;
-        const int tot = 8 * nvalid - __popcll(st);
-        uint64_t v = x;
-        if (KIND == US_MEL) {                            /* consumed MSB first: reverse the bits of every byte */
-            const uint32_t lo = __byte_perm(__brev((uint32_t)x), 0, 0x0123), hi = __byte_perm(__brev((uint32_t)(x >> 32)), 0, 0x0123);
-            v = ((uint64_t)hi << 32) | lo;
-        }
-        /* squeeze out the unused bit of every 7-bit byte, highest byte first so that lower positions stay valid */
-        while (st) {
-            const int k8 = 63 - __clzll((long long)st);  /* bit 8k */
-            st ^= 1ull << k8;
-            const int pos = KIND == US_MEL ? k8 : k8 + 7;
-            const uint64_t low = (1ull << pos) - 1;
-            const uint64_t keep = KIND == US_MAGSGN ? v & (1ull << pos) : 0;    /* OR-ed into the next byte's bit 0 */
-            v = (v & low) | ((v >> 1) & ~low) | keep;
-        }
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        const uint32_t off = bits + (uint32_t)(incl - tot);
-        if (tot) {
-            const uint32_t wd = off >> 5, sft = off & 31;
-            const uint64_t lo = v << sft;
-            const uint32_t hi = sft ? (uint32_t)(v >> (64 - sft)) : 0;
-            if ((uint32_t)lo)
-                atomicOr(&out[wd], (uint32_t)lo);
-            if ((uint32_t)(lo >> 32))
-                atomicOr(&out[wd + 1], (uint32_t)(lo >> 32));
-            if (hi)
-                atomicOr(&out[wd + 2], hi);
-        }
-        bits += (uint32_t)__shfl_sync(FULL, incl, 31);
-        carry = __shfl_sync(FULL, (unsigned)(x >> 56), 31);
-    }
-    __syncwarp();
-    return bits;
-}
-
-/* fill everything behind `bits` with ones (streams that read 0xFF past their end) */
-__device__ __forceinline__ void ones_behind(uint32_t *out, uint32_t bits, int words, int lane)
-{
-    const int first = (int)(bits >> 5);
-    if (lane == 0)
-        out[first] |= 0xFFFFFFFFu << (bits & 31);
-    for (int i = first + 1 + lane; i < words; i += 32)
-        out[i] = 0xFFFFFFFFu;
-    __syncwarp();
-}
-
 /* ---- K0 ------------------------------------------------------------------------------------------------ */
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 ht_unstuff_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order,
@@ -250,7 +103,18 @@ ht_unstuff_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict
     for (int i = lane; i < 2 * vlw; i += 32)
         vl[i] = 0;
     __syncwarp();
-    unstuff<US_VLC>(Dcup + Lcup - 2, Scup - 1, vl, lane);          /* zeros behind */
+    const uint32_t vbits = unstuff<US_VLC>(Dcup + Lcup - 2, Scup - 1, vl, lane);
+    {
+        /* base[0], base[1] of the reference's reader = Dcup[Pcup], Dcup[Pcup+1] after modDcup */
+        unsigned b0 = Dcup[Pcup], b1 = Dcup[Pcup + 1];
+        if (Scup == 2) {
+            b0 |= 0x0F;
+            b1 = 0xFF;
+        } else if (Scup == 3) {
+            b1 |= 0x0F;
+        }
+        bwd_tail_fill(vl, vlw, bwd_tail_make(vbits, Scup - 1, b0, b1), lane);
+    }
     const uint32_t mbits = unstuff<US_MEL>(Dcup + Pcup, Scup, ml, lane);
     ones_behind(ml, mbits, vlw, lane);
     uint32_t *out = scratch + scr_off[bi];
@@ -282,6 +146,40 @@ struct LsbReader {
             avail += 32;
             nxt = p < end ? *p : fill;
             p++;
+        }
+    }
+    __device__ __forceinline__ void drop(int n)
+    {
+        win >>= n;
+        avail -= n;
+    }
+};
+
+/* the VLC reader: same window, but behind the array it continues with the reference's periodic tail */
+struct VlcReader {
+    uint64_t win;
+    int avail;
+    const uint32_t *base;
+    int i, words;
+    uint32_t nxt;
+    BwdTail tail;
+    __device__ __forceinline__ void init(const uint32_t *ptr, int w)
+    {
+        win = (uint64_t)ptr[0] | ((uint64_t)ptr[1] << 32);
+        avail = 64;
+        nxt = ptr[2];
+        base = ptr;
+        i = 3;
+        words = w;
+        tail = bwd_tail_unpack(ptr[w - 1]);
+    }
+    __device__ __forceinline__ void refill()
+    {
+        if (avail <= 32) {
+            win |= (uint64_t)nxt << avail;
+            avail += 32;
+            nxt = bwd_word(base, words, tail, i);
+            i++;
         }
     }
     __device__ __forceinline__ void drop(int n)
@@ -329,7 +227,7 @@ __device__ __forceinline__ int mel_symbol_lane(MelLane &m)
  * carry: first row -> context carried from the previous quad; other rows -> (sigma_W[3] | sigma_W[2]).
  * a0/c0, a1/c1: other rows -> (sigma_N[1] | sigma_NW[3]) and (sigma_N[3] | sigma_NE[1]) of the two quads. */
 template <bool FIRST>
-__device__ __forceinline__ void vlc_pair_lane(LsbReader &v, MelLane &mel, const uint16_t *table, const uint16_t *uvtab,
+__device__ __forceinline__ void vlc_pair_lane(VlcReader &v, MelLane &mel, const uint16_t *table, const uint16_t *uvtab,
                                               bool two, unsigned a0, unsigned c0, unsigned a1, unsigned c1,
                                               int &carry, uint32_t &out0, uint32_t &out1)
 {
@@ -452,8 +350,8 @@ ht_vlc_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ o
     const int QW = (d.w + 1) >> 1, QH = (d.h + 1) >> 1; /* QW <= 32: the row's significance fits two words */
     const int vlw = ht_stream_words(Scup);
     uint32_t *base = scratch + scr_off[bi];
-    LsbReader v;
-    v.init(base, vlw, 0);
+    VlcReader v;
+    v.init(base, vlw);
     v.drop(4);                                           /* the Scup nibble (:283-295) */
     MelLane mel;
     mel.r.init(base + vlw, vlw, 0xFFFFFFFFu);
@@ -544,6 +442,10 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
     const int Pcup = d.Lcup - Scup;
     const int sh53 = 31 - M_b;
     const float fscale = bd.fscale;
+    /* DQ_INT53: (x << pLSB | half) >> sh53 as x << dq_up >> dq_dn | dq_half (mag << pLSB never overflows a
+     * valid sample: U <= maxbp keeps it below bit 31) */
+    const int dq_up = pLSB > sh53 ? pLSB - sh53 : 0, dq_dn = pLSB < sh53 ? sh53 - pLSB : 0;
+    const uint32_t dq_half = pLSB - 1 >= sh53 ? 1u << (pLSB - 1 - sh53) : 0;
 
     /* un-stuffed MagSgn bits in shared memory; past the end the decoder reads ones */
     const int ms_words = (Pcup + 3) / 4 + 2;
@@ -562,7 +464,8 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
     bool bad = false;
     const int x = 2 * lane;
     unsigned prev_sg = 0;
-    for (int qy = 0; qy < QH; qy++) {
+    uint32_t *rowp = dst + x;
+    for (int qy = 0; qy < QH; qy++, rowp += 2 * (size_t)dstride) {
         const unsigned mine = nextq;                     /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16; 0 in idle lanes */
         if (qy + 1 < QH)
             nextq = act ? q[(qy + 1) * QW + lane] : 0;
@@ -592,13 +495,7 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
             mlen[i] = (((rho >> i) & 1) ? U : 0) - (int)((ek >> i) & 1);
             tot += max(mlen[i], 0);
         }
-        int incl = tot;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
+        const int incl = warp_scan_add(tot);
         uint32_t pos = ms_pos + (uint32_t)(incl - tot);
         ms_pos += (uint32_t)__shfl_sync(FULL, incl, 31);
         uint32_t mu[4];
@@ -616,9 +513,17 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
                 unsigned E = 32 - __clz(v | 1);
                 if (i == 1) E1 = E;
                 if (i == 3) E3 = E;
-                val = (uint32_t)(((int32_t)v >> 1) + 1) << pLSB;
-                val |= 1u << (pLSB - 1);
-                val |= (v & 1u) << 31;
+                if (DQ == DQ_INT53 && !REFINE) {
+                    /* mu >> (31 - M_b) with mu = ((v >> 1) + 1) << pLSB | 1 << (pLSB - 1), then the sign: the
+                     * shifts are per-block constants (dequantization_int, jpeg2000dec.c:2120-2151) */
+                    const uint32_t mag = (uint32_t)(((int32_t)v >> 1) + 1);
+                    const int32_t r = (int32_t)(((mag << dq_up) >> dq_dn) | dq_half);
+                    val = (uint32_t)((v & 1u) ? -r : r);
+                } else {
+                    val = (uint32_t)(((int32_t)v >> 1) + 1) << pLSB;
+                    val |= 1u << (pLSB - 1);
+                    val |= (v & 1u) << 31;
+                }
             }
             mu[i] = val;
         }
@@ -642,11 +547,12 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
                 prev_sg = sg;
         }
         if (act) {
-            const uint32_t o0 = REFINE ? mu[0] : dq<DQ>(mu[0], sh53, fscale, mode, M_b, roi_shift, bd),
-                           o1 = REFINE ? mu[1] : dq<DQ>(mu[1], sh53, fscale, mode, M_b, roi_shift, bd),
-                           o2 = REFINE ? mu[2] : dq<DQ>(mu[2], sh53, fscale, mode, M_b, roi_shift, bd),
-                           o3 = REFINE ? mu[3] : dq<DQ>(mu[3], sh53, fscale, mode, M_b, roi_shift, bd);
-            uint32_t *r0 = dst + (size_t)y * dstride + x, *r1 = r0 + dstride;
+            constexpr bool RAW = REFINE || DQ == DQ_INT53;   /* already final (or finished later) */
+            const uint32_t o0 = RAW ? mu[0] : dq<DQ>(mu[0], sh53, fscale, mode, M_b, roi_shift, bd),
+                           o1 = RAW ? mu[1] : dq<DQ>(mu[1], sh53, fscale, mode, M_b, roi_shift, bd),
+                           o2 = RAW ? mu[2] : dq<DQ>(mu[2], sh53, fscale, mode, M_b, roi_shift, bd),
+                           o3 = RAW ? mu[3] : dq<DQ>(mu[3], sh53, fscale, mode, M_b, roi_shift, bd);
+            uint32_t *r0 = rowp, *r1 = r0 + dstride;
             if (vec && x + 1 < w) {
                 *reinterpret_cast<uint2 *>(r0) = make_uint2(o0, o2);
                 if (y + 1 < h)
@@ -734,8 +640,19 @@ ht_unstuff_ref_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__rest
     for (int i = lane; i < 2 * rl.rw; i += 32)
         sp[i] = 0;
     __syncwarp();
-    unstuff<US_SIGPROP>(Dref, Lref, sp, lane);                    /* zeros behind both */
-    unstuff<US_MAGREF>(Dref + Lref - 1, Lref, mr, lane);
+    unstuff<US_SIGPROP>(Dref, Lref, sp, lane);                    /* zeros behind */
+    {
+        /* bytes at and behind Dref[Lref]: the 0xFF the decoder plants at cblk->length (jpeg2000htdec.c:1258),
+         * then nothing */
+        auto ref_byte = [&](int i) -> unsigned {
+            if (i < Lref)
+                return Dref[i];
+            const uint32_t at = (uint32_t)d.Lcup + (uint32_t)i;
+            return at == d.length ? 0xFFu : (at < d.length ? Dref[i] : 0u);
+        };
+        const uint32_t rbits = unstuff<US_MAGREF>(Dref + Lref - 1, Lref, mr, lane, ref_byte(Lref));
+        bwd_tail_fill(mr, rl.rw, bwd_tail_make(rbits, Lref, ref_byte(0), ref_byte(1)), lane);
+    }
     uint32_t *out = scratch + scr_off[bi] + rl.sp;
     for (int i = lane; i < 2 * rl.rw; i += 32)
         out[i] = sp[i];
@@ -902,7 +819,7 @@ ht_refine_apply_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__res
     const int p = 30 - S_blk - 1;
     const uint32_t *base = scratch + scr_off[bi];
     const uint32_t *mr = base + rl.mr;
-    const uint32_t mr_limit = (uint32_t)(rl.rw - 2) * 32;
+    const BwdTail mr_tail = bwd_tail_unpack(mr[rl.rw - 1]);
     const uint8_t *sigb = reinterpret_cast<const uint8_t *>(base + rl.sig);
     const uint8_t *nsgb = reinterpret_cast<const uint8_t *>(base + rl.nsg);
     const uint8_t *sgnb = reinterpret_cast<const uint8_t *>(base + rl.sgn);
@@ -919,16 +836,11 @@ ht_refine_apply_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__res
         const unsigned vm = ((x < w ? 0x0Fu : 0) | (x + 1 < w ? 0xF0u : 0)) & (rm | (rm << 4));
         const unsigned sv = z_blk > 2 ? sb & vm : 0;
         const int cnt = __popc(sv);
-        int incl = cnt;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o)
-                incl += t;
-        }
-        const uint32_t pos = min(mr_pos + (uint32_t)(incl - cnt), mr_limit);
+        const int incl = warp_scan_add(cnt);
+        const uint32_t pos = mr_pos + (uint32_t)(incl - cnt);
         mr_pos += (uint32_t)__shfl_sync(FULL, incl, 31);
-        const uint32_t win = cnt ? __funnelshift_r(mr[pos >> 5], mr[(pos >> 5) + 1], pos & 31) : 0;
+        const uint32_t win = cnt ? __funnelshift_r(bwd_word(mr, rl.rw, mr_tail, (int)(pos >> 5)),
+                                                   bwd_word(mr, rl.rw, mr_tail, (int)(pos >> 5) + 1), pos & 31) : 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             if (i >= gh)

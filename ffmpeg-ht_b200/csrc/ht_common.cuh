@@ -78,27 +78,6 @@ __device__ __forceinline__ int mel_symbol(Mel &m)
     return 1;
 }
 
-/* ---- H2: VLC.  The backward byte stream (jpeg2000htdec.c:145-201, :283-295: bytes from Dcup[Lcup-2]
- * down to Dcup[Pcup]; a byte whose low 7 bits are ones gives 7 bits when the byte read before it is
- * > 0x8F) is un-stuffed once, in parallel, into a forward LSB-first bit array in shared memory.  The
- * serial decoder fetches 64 bits at the current bit position once per quad pair (a pair consumes at most
- * 7 + 7 + 24 bits); everything after that is 32-bit shifts.  Past the end the stream reads as zeros. */
-struct VlcWin {
-    uint32_t lo, hi;
-};
-
-__device__ __forceinline__ VlcWin vlc_fetch(const uint32_t *vl, uint32_t pos, uint32_t limit)
-{
-    pos = min(pos, limit);
-    const uint32_t *p = vl + (pos >> 5);
-    const uint32_t s = pos & 31;
-    const uint32_t a = p[0], b = p[1], c = p[2];
-    VlcWin w;
-    w.lo = __funnelshift_r(a, b, s);
-    w.hi = __funnelshift_r(b, c, s);
-    return w;
-}
-
 /* ---- H5: U-VLC (jpeg2000htdec.c:338-388) on a 32-bit window ------------------------------------------ */
 __device__ __forceinline__ int uvlc_prefix(uint32_t &win, int &used)
 {
@@ -150,6 +129,318 @@ __device__ __forceinline__ uint16_t uvlc_pair_entry(int idx)
     return (uint16_t)(used | (p0 << 3) | (p1 << 6) | (s0 << 9) | (s1 << 12));
 }
 
+/* read nb (1..31) bits at bit position pos of the un-stuffed MagSgn array */
+__device__ __forceinline__ uint32_t ms_read(const uint32_t *ms, uint32_t pos, int nb)
+{
+    uint32_t w = pos >> 5, s = pos & 31;
+    uint32_t lo = ms[w], hi = ms[w + 1];
+    uint32_t v = __funnelshift_r(lo, hi, s);
+    return v & ((1u << nb) - 1);
+}
+
+/* D1-D3: sign-magnitude sample -> plane value (as raw 32 bits) */
+__device__ __forceinline__ uint32_t dequant(uint32_t sm, int mode, int M_b, int roi_shift, const BandDesc &bd)
+{
+    /* ROI up-shift, then "val | sign" (jpeg2000htdec.c:1318-1331) */
+    uint32_t t = sm & 0x7FFFFFFFu;
+    if (roi_shift) {
+        const uint32_t mask = 0xFFFFFFFFu >> (M_b + 1);
+        if ((t & ~mask) == 0)
+            t <<= roi_shift;
+    }
+    const uint32_t c = t | (sm & 0x80000000u);
+    const bool neg = (c >> 31) != 0;
+    const uint32_t mag = c & 0x7FFFFFFFu;
+    if (mode == 3)                                   /* stage-level entry point: t1->data as is */
+        return c;
+    if (mode == J2K_DWT53) {
+        int32_t v = (int32_t)(mag >> (31 - M_b));
+        if (neg)
+            v = -v;
+        if (bd.i_stepsize != 32768)
+            v = (int32_t)(((int64_t)v * bd.i_stepsize) / 65536);
+        return (uint32_t)v;
+    } else if (mode == J2K_DWT97) {
+        int32_t v = neg ? -(int32_t)mag : (int32_t)mag;
+        return __float_as_uint(__fmul_rn((float)v, bd.fscale));
+    } else {
+        int32_t v = neg ? -(int32_t)mag : (int32_t)mag;
+        v = (v + 32) >> 6;
+        int64_t m = (int64_t)v * bd.iscale;
+        m = m > 0 ? (m + 32768) >> 16 : (m + 32767) >> 16;   /* RSHIFT(m, 16) */
+        return (uint32_t)(int32_t)m;
+    }
+}
+
+/* sample state bits in the refinement path (jpeg2000htdec.c:62-65) */
+constexpr unsigned ST_SIGMA = 1, ST_NEWSIG = 8, ST_SCANNED = 16;
+
+/* SigProp bit reader (jpeg2000htdec.c:442-460), global memory, lane 0 only */
+struct SpBits {
+    const uint8_t *d;
+    int len, pos, left;
+    unsigned cur, last;
+};
+__device__ __forceinline__ int sp_bit(SpBits &s)
+{
+    if (s.left == 0) {
+        s.left = s.last == 0xFF ? 7 : 8;
+        s.cur = s.pos < s.len ? s.d[s.pos++] : 0;
+        s.last = s.cur;
+    }
+    int b = s.cur & 1;
+    s.cur >>= 1;
+    s.left--;
+    return b;
+}
+
+/* four bytes p[0..3] (p[0] in the low byte) fetched as two aligned words; the caller guarantees that the
+ * aligned words around p are readable (the byte buffer has 64 bytes of slack and a 256-byte aligned base) */
+__device__ __forceinline__ uint32_t load4(const uint8_t *p)
+{
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (int)(a & 3) * 8);
+}
+
+/*
+ * Parallel removal of byte stuffing.  The five bit streams of an HT code-block differ only in direction,
+ * in the stuffing rule and in how a byte's bits are consumed; all become contiguous LSB-first bit arrays
+ * (first bit consumed = bit 0 of word 0):
+ *   US_MAGSGN  Dcup[0..Pcup) forward; 7 bits after 0xFF, bit 7 of such a byte is OR-ed into the next
+ *              byte's bit 0 as the reference's accumulator does (jpeg2000htdec.c:207-221)
+ *   US_MEL     Dcup[Pcup..Lcup) forward, MSB first, 7 bits after 0xFF, modDcup on the last two bytes
+ *              (:429-440, :1277-1278)
+ *   US_VLC     Dcup[Lcup-2] down to Dcup[Pcup]; 7 bits when (b & 0x7F) == 0x7F and the byte read before is
+ *              > 0x8F; first byte |= 0x0F, the byte "read before" it is 0xFF (:145-201, :283-295)
+ *   US_SIGPROP Dref[0..Lref) forward, LSB first, 7 bits after 0xFF (:442-460)
+ *   US_MAGREF  Dref[Lref-1] down to Dref[0], VLC stuffing rule, first "read before" is 0xFF (:123-131)
+ * first: address of the first byte in read order; n: bytes.  Four bytes per lane and chunk, fetched as two
+ * aligned words one chunk ahead; a warp prefix sum over the 7/8-bit lengths places them.  out[] must be
+ * zeroed.  Returns the number of bits written (warp-uniform).
+ */
+enum { US_MAGSGN, US_MEL, US_VLC, US_SIGPROP, US_MAGREF };
+
+/* inclusive warp prefix sum; shfl.up's validity predicate guards the add (no lane compare per step) */
+__device__ __forceinline__ int warp_scan_add(int v)
+{
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+        asm volatile("{ .reg .pred p; .reg .s32 t;\n"
+                     "  shfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n"
+                     "  @p add.s32 %0, %0, t; }"
+                     : "+r"(v)
+                     : "r"(o));
+    return v;
+}
+
+/* 0x01 in every byte of x that equals the corresponding byte of y */
+__device__ __forceinline__ uint64_t bytes_eq(uint64_t x, uint64_t y)
+{
+    uint64_t d = x ^ y;                                  /* zero byte <=> equal */
+    d |= d >> 4;
+    d |= d >> 2;
+    d |= d >> 1;
+    return ~d & 0x0101010101010101ull;
+}
+
+/* 0x01 in every byte of x that is > 0x8F */
+__device__ __forceinline__ uint64_t bytes_gt8f(uint64_t x)
+{
+    /* b > 0x8F  <=>  bit 7 set and (b & 0x70) != 0 */
+    const uint64_t hi = x >> 7, any = (x >> 6) | (x >> 5) | (x >> 4);
+    return hi & any & 0x0101010101010101ull;
+}
+
+template <int KIND>
+__device__ __forceinline__ uint32_t unstuff(const uint8_t *first, int n, uint32_t *out, int lane, unsigned before0 = 0xFF)
+{
+    constexpr bool BACKWARD = KIND == US_VLC || KIND == US_MAGREF;
+    constexpr bool RULE_A = BACKWARD;           /* 7 bits when (b & 0x7F) == 0x7F && before > 0x8F; else: before == 0xFF */
+    constexpr int BPL = 8;                      /* bytes per lane and chunk */
+    uint32_t bits = 0;
+    unsigned carry = RULE_A ? before0 : 0;       /* the byte "read before" the first one */
+    /* eight bytes in read order, first byte read = low byte */
+    auto fetch = [&](int idx) -> uint64_t {
+        if (idx >= n)
+            return 0;
+        const uint8_t *p = BACKWARD ? first - 7 - idx : first + idx;
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+        const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const int sh = (int)(a & 3) * 8;
+        const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+        const uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        return BACKWARD ? ((uint64_t)__byte_perm(lo, 0, 0x0123) << 32) | __byte_perm(hi, 0, 0x0123)
+                        : ((uint64_t)hi << 32) | lo;
+    };
+    uint64_t nxt = fetch(lane * BPL);
+    for (int chunk = 0; chunk < n; chunk += 32 * BPL) {
+        const int idx = chunk + lane * BPL;
+        uint64_t x = nxt;
+        nxt = fetch(idx + 32 * BPL);
+        const int nvalid = min(max(n - idx, 0), BPL);
+        const uint64_t vmask = nvalid >= 8 ? ~0ull : ((1ull << (8 * nvalid)) - 1);
+        x &= vmask;
+        if (KIND == US_VLC && idx == 0)
+            x |= 0x0F;                                   /* modDcup: low nibble of the first byte read */
+        if (KIND == US_MEL) {                            /* modDcup: last two bytes of the segment */
+            const int k2 = n - 2 - idx, k1 = n - 1 - idx;
+            if (k2 >= 0 && k2 < 8)
+                x |= 0x0Full << (8 * k2);
+            if (k1 >= 0 && k1 < 8)
+                x |= 0xFFull << (8 * k1);
+        }
+        /* the byte read before each byte */
+        unsigned before = __shfl_up_sync(FULL, (unsigned)(x >> 56), 1);
+        if (lane == 0)
+            before = carry;
+        const uint64_t prev = (x << 8) | before;
+        /* 0x01 per byte that carries only 7 bits */
+        uint64_t st;
+        if (RULE_A)
+            st = bytes_eq(x | 0x8080808080808080ull, ~0ull) & bytes_gt8f(prev);
+        else
+            st = bytes_eq(prev, ~0ull);
+        st &= vmask;
+        const int tot = 8 * nvalid - __popcll(st);
+        uint64_t v = x;
+        if (KIND == US_MEL) {                            /* consumed MSB first: reverse the bits of every byte */
+            const uint32_t lo = __byte_perm(__brev((uint32_t)x), 0, 0x0123), hi = __byte_perm(__brev((uint32_t)(x >> 32)), 0, 0x0123);
+            v = ((uint64_t)hi << 32) | lo;
+        }
+        /* squeeze out the unused bit of every 7-bit byte, highest byte first so that lower positions stay valid */
+        while (st) {
+            const int k8 = 63 - __clzll((long long)st);  /* bit 8k */
+            st ^= 1ull << k8;
+            const int pos = KIND == US_MEL ? k8 : k8 + 7;
+            const uint64_t low = (1ull << pos) - 1;
+            const uint64_t keep = KIND == US_MAGSGN ? v & (1ull << pos) : 0;    /* OR-ed into the next byte's bit 0 */
+            v = (v & low) | ((v >> 1) & ~low) | keep;
+        }
+        const int incl = warp_scan_add(tot);
+        const uint32_t off = bits + (uint32_t)(incl - tot);
+        if (tot) {
+            const uint32_t wd = off >> 5, sft = off & 31;
+            const uint64_t lo = v << sft;
+            const uint32_t hi = sft ? (uint32_t)(v >> (64 - sft)) : 0;
+            if ((uint32_t)lo)
+                atomicOr(&out[wd], (uint32_t)lo);
+            if ((uint32_t)(lo >> 32))
+                atomicOr(&out[wd + 1], (uint32_t)(lo >> 32));
+            if (hi)
+                atomicOr(&out[wd + 2], hi);
+        }
+        bits += (uint32_t)__shfl_sync(FULL, incl, 31);
+        carry = __shfl_sync(FULL, (unsigned)(x >> 56), 31);
+    }
+    __syncwarp();
+    return bits;
+}
+
+/* fill everything behind `bits` with ones (streams that read 0xFF past their end) */
+__device__ __forceinline__ void ones_behind(uint32_t *out, uint32_t bits, int words, int lane)
+{
+    const int first = (int)(bits >> 5);
+    if (lane == 0)
+        out[first] |= 0xFFFFFFFFu << (bits & 31);
+    for (int i = first + 1 + lane; i < words; i += 32)
+        out[i] = 0xFFFFFFFFu;
+    __syncwarp();
+}
+
+/*
+ * What the reference's backward reader (jpeg2000_bitbuf_refill_backwards, jpeg2000htdec.c:145-201: VLC and
+ * MagRef) yields once its R bytes base[R-1] .. base[0] are used up.  It pulls groups of four bytes; the last,
+ * partial group is zero-filled and the position is parked at 0, so every later group is base[0] followed by
+ * three zero bytes, base[0] giving 7 bits when (base[0] & 0x7F) == 0x7F and base[1] > 0x8F.  Only damaged
+ * segments ever read that far, but then the decoded garbage has to match the reference's garbage (quirk Q1
+ * keeps such blocks when no exponent bound trips).
+ *   Bv   bits of the R un-stuffed bytes plus the zero bytes that complete the partial group (a whole group
+ *        of zeros when R is a multiple of four)
+ *   pat  the 7 or 8 bits of base[0], P = their number + 24: the period of everything behind Bv
+ */
+struct BwdTail {
+    uint32_t Bv, pat;
+    int P;
+};
+
+__device__ __forceinline__ BwdTail bwd_tail_make(uint32_t data_bits, int R, unsigned b0, unsigned b1)
+{
+    BwdTail t;
+    t.Bv = data_bits + 8u * (uint32_t)(4 - (R & 3));
+    const int nb0 = ((b0 & 0x7F) == 0x7F && b1 > 0x8F) ? 7 : 8;
+    t.pat = b0 & ((1u << nb0) - 1);
+    t.P = nb0 + 24;
+    return t;
+}
+
+/* 32 bits of the periodic tail starting `t` bits behind Bv */
+__device__ __forceinline__ uint32_t bwd_tail_word(const BwdTail &tl, uint32_t t)
+{
+    const uint32_t phase = t % (uint32_t)tl.P;
+    const uint64_t pp = (uint64_t)tl.pat | ((uint64_t)tl.pat << tl.P);      /* two periods: phase + 32 <= 2 P */
+    return (uint32_t)(pp >> phase);
+}
+
+/* one word describing the tail, kept in the last word of an un-stuffed backward array */
+__device__ __forceinline__ uint32_t bwd_tail_pack(const BwdTail &t) { return t.Bv | (t.pat << 20) | ((uint32_t)(t.P == 31) << 28); }
+__device__ __forceinline__ BwdTail bwd_tail_unpack(uint32_t w)
+{
+    BwdTail t;
+    t.Bv = w & 0xFFFFF;                          /* < 2^20: segments are shorter than 65536 bytes */
+    t.pat = (w >> 20) & 0xFF;
+    t.P = (w >> 28) & 1 ? 31 : 32;
+    return t;
+}
+
+/* out[0 .. words-1): the zeroed array already holding the un-stuffed bytes; completes it with the tail
+ * pattern and stores the descriptor in out[words-1] */
+__device__ __forceinline__ void bwd_tail_fill(uint32_t *out, int words, const BwdTail &tl, int lane)
+{
+    const int first = (int)(tl.Bv >> 5);
+    for (int i = first + lane; i < words - 1; i += 32) {
+        const int t0 = 32 * i - (int)tl.Bv;
+        if (t0 < 0)
+            out[i] |= bwd_tail_word(tl, 0) << (tl.Bv & 31);
+        else
+            out[i] = bwd_tail_word(tl, (uint32_t)t0);
+    }
+    if (lane == 0)
+        out[words - 1] = bwd_tail_pack(tl);
+    __syncwarp();
+}
+
+/* word i of a backward array of `words` words (the last one is the descriptor) */
+__device__ __forceinline__ uint32_t bwd_word(const uint32_t *arr, int words, const BwdTail &tl, int i)
+{
+    return i < words - 1 ? arr[i] : bwd_tail_word(tl, (uint32_t)(32 * i) - tl.Bv);
+}
+
+/* ---- H2: VLC window of the warp-per-block kernel.  The backward byte stream is un-stuffed once, in
+ * parallel, into a forward LSB-first bit array in shared memory (unstuff<US_VLC>), completed with the
+ * reference's tail (BwdTail).  The serial decoder fetches 64 bits at the current bit position once per quad
+ * pair (a pair consumes at most 7 + 7 + 24 bits); everything after that is 32-bit shifts. */
+struct VlcWin {
+    uint32_t lo, hi;
+};
+struct VlcArr {
+    const uint32_t *vl;
+    int words;
+    BwdTail tail;
+};
+
+__device__ __forceinline__ VlcWin vlc_fetch(const VlcArr &va, uint32_t pos)
+{
+    const int i = (int)(pos >> 5);
+    const uint32_t s = pos & 31;
+    const uint32_t a = bwd_word(va.vl, va.words, va.tail, i), b = bwd_word(va.vl, va.words, va.tail, i + 1),
+                   c = bwd_word(va.vl, va.words, va.tail, i + 2);
+    VlcWin w;
+    w.lo = __funnelshift_r(a, b, s);
+    w.hi = __funnelshift_r(b, c, s);
+    return w;
+}
+
 /*
  * The serial, warp-uniform part for one segment of up to 32 quads of one quad row: MEL + CxtVLC + U-VLC
  * (jpeg2000htdec.c:632-768 first row, :784-973 other rows).  Every lane executes it on identical data and
@@ -159,11 +450,11 @@ __device__ __forceinline__ uint16_t uvlc_pair_entry(int idx)
  * mA / mC: other rows -> per-quad bits (sigma_N[1] | sigma_NW[3]) and (sigma_N[3] | sigma_NE[1]).
  */
 template <bool FIRST, bool PAIR>
-__device__ __forceinline__ void decode_pair(Mel &mel, const uint32_t *vl, uint32_t &vpos, uint32_t vlimit,
+__device__ __forceinline__ void decode_pair(Mel &mel, const VlcArr &vl, uint32_t &vpos,
                                             const uint16_t *table, const uint16_t *uvtab, unsigned mA, unsigned mC,
                                             int &carry, uint32_t *qout)
 {
-    const VlcWin vw = vlc_fetch(vl, vpos, vlimit);
+    const VlcWin vw = vlc_fetch(vl, vpos);
     uint32_t win = vw.lo;
     int used;
     unsigned q0, q1 = 0;
@@ -256,83 +547,18 @@ __device__ __forceinline__ void decode_pair(Mel &mel, const uint32_t *vl, uint32
 }
 
 template <bool FIRST>
-__device__ __forceinline__ void decode_segment(Mel &mel, const uint32_t *vl, uint32_t &vpos, uint32_t vlimit,
+__device__ __forceinline__ void decode_segment(Mel &mel, const VlcArr &vl, uint32_t &vpos,
                                                const uint16_t *table, const uint16_t *uvtab, int nq, unsigned mA,
                                                unsigned mC, int &carry, uint32_t *qinfo)
 {
     const int npairs = nq >> 1;
     for (int j = 0; j < npairs; j++) {
-        decode_pair<FIRST, true>(mel, vl, vpos, vlimit, table, uvtab, mA, mC, carry, qinfo + 2 * j);
+        decode_pair<FIRST, true>(mel, vl, vpos, table, uvtab, mA, mC, carry, qinfo + 2 * j);
         mA >>= 2;
         mC >>= 2;
     }
     if (nq & 1)
-        decode_pair<FIRST, false>(mel, vl, vpos, vlimit, table, uvtab, mA, mC, carry, qinfo + 2 * npairs);
-}
-
-/* read nb (1..31) bits at bit position pos of the un-stuffed MagSgn array */
-__device__ __forceinline__ uint32_t ms_read(const uint32_t *ms, uint32_t pos, int nb)
-{
-    uint32_t w = pos >> 5, s = pos & 31;
-    uint32_t lo = ms[w], hi = ms[w + 1];
-    uint32_t v = __funnelshift_r(lo, hi, s);
-    return v & ((1u << nb) - 1);
-}
-
-/* D1-D3: sign-magnitude sample -> plane value (as raw 32 bits) */
-__device__ __forceinline__ uint32_t dequant(uint32_t sm, int mode, int M_b, int roi_shift, const BandDesc &bd)
-{
-    /* ROI up-shift, then "val | sign" (jpeg2000htdec.c:1318-1331) */
-    uint32_t t = sm & 0x7FFFFFFFu;
-    if (roi_shift) {
-        const uint32_t mask = 0xFFFFFFFFu >> (M_b + 1);
-        if ((t & ~mask) == 0)
-            t <<= roi_shift;
-    }
-    const uint32_t c = t | (sm & 0x80000000u);
-    const bool neg = (c >> 31) != 0;
-    const uint32_t mag = c & 0x7FFFFFFFu;
-    if (mode == 3)                                   /* stage-level entry point: t1->data as is */
-        return c;
-    if (mode == J2K_DWT53) {
-        int32_t v = (int32_t)(mag >> (31 - M_b));
-        if (neg)
-            v = -v;
-        if (bd.i_stepsize != 32768)
-            v = (int32_t)(((int64_t)v * bd.i_stepsize) / 65536);
-        return (uint32_t)v;
-    } else if (mode == J2K_DWT97) {
-        int32_t v = neg ? -(int32_t)mag : (int32_t)mag;
-        return __float_as_uint(__fmul_rn((float)v, bd.fscale));
-    } else {
-        int32_t v = neg ? -(int32_t)mag : (int32_t)mag;
-        v = (v + 32) >> 6;
-        int64_t m = (int64_t)v * bd.iscale;
-        m = m > 0 ? (m + 32768) >> 16 : (m + 32767) >> 16;   /* RSHIFT(m, 16) */
-        return (uint32_t)(int32_t)m;
-    }
-}
-
-/* sample state bits in the refinement path (jpeg2000htdec.c:62-65) */
-constexpr unsigned ST_SIGMA = 1, ST_NEWSIG = 8, ST_SCANNED = 16;
-
-/* SigProp bit reader (jpeg2000htdec.c:442-460), global memory, lane 0 only */
-struct SpBits {
-    const uint8_t *d;
-    int len, pos, left;
-    unsigned cur, last;
-};
-__device__ __forceinline__ int sp_bit(SpBits &s)
-{
-    if (s.left == 0) {
-        s.left = s.last == 0xFF ? 7 : 8;
-        s.cur = s.pos < s.len ? s.d[s.pos++] : 0;
-        s.last = s.cur;
-    }
-    int b = s.cur & 1;
-    s.cur >>= 1;
-    s.left--;
-    return b;
+        decode_pair<FIRST, false>(mel, vl, vpos, table, uvtab, mA, mC, carry, qinfo + 2 * npairs);
 }
 
 }  // namespace

@@ -119,6 +119,50 @@ def test_damaged_blocks_zeroed_like_reference():
         assert np.array_equal(got[i], want), i
 
 
+@pytest.mark.parametrize("npasses", [1, 3])
+def test_fuzzed_blocks_match_oracle(npasses):
+    """Random byte damage anywhere in the segment (MagSgn, MEL, VLC, SigProp, MagRef bytes, the Scup field):
+    the kernels must agree with the oracle -- which restates the reference's behaviour on damaged data,
+    reads past the end of every bit stream included -- on the status and on every coefficient."""
+    rng = np.random.default_rng(900 + npasses)
+    blocks = []
+    while len(blocks) < 400:
+        w, h = int(rng.integers(1, 65)), int(rng.integers(1, 65))
+        if rng.random() < 0.4:
+            w, h = [(64, 64), (32, 32), (64, 32), (128, 16)][int(rng.integers(0, 4))]
+        bits = int(rng.integers(2, 13))
+        coef = (rng.standard_normal((h, w)) * rng.uniform(0.5, 2 ** bits)).astype(np.int32)
+        if rng.random() < 0.4:
+            coef[rng.random((h, w)) < rng.uniform(0.5, 0.97)] = 0
+        refine = npasses > 1
+        if not np.any(np.abs(coef) >> refine):
+            continue
+        M_b = bits + 7
+        zbp = M_b - 1 - refine
+        vsc = int(rng.integers(0, 2))
+        data, Lcup, Lref = j2kgen.encode_block(coef, npasses, bool(vsc), zbp + 1)
+        d = bytearray(data)
+        for _ in range(int(rng.integers(1, 6))):
+            kind = rng.random()
+            if kind < 0.5:
+                d[int(rng.integers(0, len(d)))] ^= 1 << int(rng.integers(0, 8))
+            elif kind < 0.8:
+                pos = int(rng.integers(0, len(d)))
+                d[pos] = int(rng.choice([0x00, 0xFF, 0x7F, 0x8F, 0x90]))
+            else:
+                pos = int(rng.integers(0, max(1, len(d) - 4)))
+                d[pos:pos + 4] = rng.integers(0, 256, len(d[pos:pos + 4]), dtype=np.uint8).tobytes()
+        if rng.random() < 0.15:
+            zbp = max(0, zbp - int(rng.integers(1, 4)))          # exponent bound violations
+        blocks.append(dict(data=bytes(d), npasses=npasses, Lcup=Lcup, Lref=Lref, zbp=zbp, w=w, h=h, M_b=M_b, roi=0, vsc=vsc))
+    got, status = fb.ht_blocks(blocks)
+    for i, b in enumerate(blocks):
+        r, want = ht_block(oracle().oracle_ht_block, b["data"], b["npasses"], b["Lcup"], b["Lref"], b["zbp"], b["w"],
+                           b["h"], b["M_b"], 0, b["vsc"])
+        assert (r > 0) == (status[i] > 0), (i, r, status[i], b["w"], b["h"])
+        assert np.array_equal(got[i], want), (i, b["w"], b["h"], b["npasses"], b["Lcup"], b["Lref"])
+
+
 # ---- W1-W4 --------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dwt_type", [0, 1, 2])
 def test_idwt_vs_oracle_and_golden(dwt_type):
@@ -182,6 +226,38 @@ def test_frames_vs_oracle(cfg, dec, dec_bitexact):
             psnr = 99.0 if mse == 0 else 10 * np.log10(((1 << bd) - 1) ** 2 / mse)
             print(f"9/7 float vs reference: max {err / lsb:.0f} LSB, PSNR {psnr:.1f} dB, identical={err == 0}")
             assert np.array_equal(got, want), "float path is expected to be bit-identical as well"
+
+
+# geometries the register-streaming IDWT path accepts (even origins, 16-byte aligned band rows, packed 16-bit
+# output) next to ones where only some levels do: strips with border lanes, short segments, tiles
+STREAM_GEOMS = [
+    dict(w=512, h=77, nc=3, bd=12, levels=3),
+    dict(w=1000, h=64, nc=1, bd=16, levels=2),
+    dict(w=488, h=130, nc=3, bd=10, levels=1, reversible=False, base_step=1.0),
+    dict(w=960, h=540, nc=3, bd=12, levels=5, tile=(480, 272)),
+    dict(w=264, h=50, nc=1, bd=12, levels=2, reversible=False, base_step=0.5),
+    dict(w=2048, h=40, nc=3, bd=12, levels=2),
+    dict(w=736, h=301, nc=3, bd=12, levels=4, reversible=False, base_step=2.0),
+    dict(w=1920, h=18, nc=1, bd=16, levels=1),
+]
+
+
+@pytest.mark.parametrize("cfg", STREAM_GEOMS, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
+def test_streaming_idwt_geometries(cfg, dec, dec_bitexact):
+    cfg = dict(cfg)
+    w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=23)
+    p = j2kgen.EncParams(**cfg)
+    cs = j2kgen.encode(planes, bd, p)
+    for bitexact in ((0,) if p.reversible else (0, 1)):
+        r, oinfo, want = oracle_decode(cs, bitexact)
+        assert r == 0
+        info, got = (dec_bitexact if bitexact else dec).decode(cs)
+        assert (info.width, info.height, info.pix_fmt) == (oinfo[0], oinfo[1], oinfo[2])
+        assert np.array_equal(got, want), "every transform path is expected to be bit-identical"
+    if p.reversible:
+        img = got.view(np.uint16).reshape(h, w, nc)
+        assert np.array_equal(img >> (16 - bd), np.stack(planes, -1))
 
 
 def test_pipelined_submit_wait(dec):
