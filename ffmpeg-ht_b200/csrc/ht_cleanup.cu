@@ -6,7 +6,7 @@
  * decoder (:462-495), CxtVLC (:300-331, :510-531) and U-VLC (:338-388), plus the dequantisation of
  * jpeg2000dec.c:2098-2181 fused into the coefficient write-back.  SURVEY.md section 8(a) rows H1-H6, D1-D3.
  *
- * Why three kernels.  ncu on the warp-per-block kernel (ht_block.cu, profiles/r1_ncu_full_v1_summary.md)
+ * Why three kernels.  ncu on the warp-per-block kernel (ht_block.cu, profiles/r1_ncu_full_v1_summary_warp_per_block_baseline.md)
  * shows it ISSUE-bound (70 % of issue slots) with 32 lanes executing the context-adaptive MEL / CxtVLC /
  * U-VLC chain redundantly: that chain is inherently serial inside a block but independent between blocks.
  * So the work is split by its shape:

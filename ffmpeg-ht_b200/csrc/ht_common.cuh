@@ -374,13 +374,15 @@ __device__ __forceinline__ BwdTail bwd_tail_make(uint32_t data_bits, int R, unsi
     return t;
 }
 
-/* 32 bits of the periodic tail starting `t` bits behind Bv */
-__device__ __forceinline__ uint32_t bwd_tail_word(const BwdTail &tl, uint32_t t)
+/* 32 bits of the periodic tail starting `t` bits behind Bv.  Out of line on purpose: only damaged segments
+ * get here, and inlined it would be if-converted into the hot refill path of the serial decoders. */
+__device__ __noinline__ uint32_t bwd_tail_word(uint32_t pat, int P, uint32_t t)
 {
-    const uint32_t phase = t % (uint32_t)tl.P;
-    const uint64_t pp = (uint64_t)tl.pat | ((uint64_t)tl.pat << tl.P);      /* two periods: phase + 32 <= 2 P */
+    const uint32_t phase = t % (uint32_t)P;
+    const uint64_t pp = (uint64_t)pat | ((uint64_t)pat << P);               /* two periods: phase + 32 <= 2 P */
     return (uint32_t)(pp >> phase);
 }
+__device__ __forceinline__ uint32_t bwd_tail_word(const BwdTail &tl, uint32_t t) { return bwd_tail_word(tl.pat, tl.P, t); }
 
 /* one word describing the tail, kept in the last word of an un-stuffed backward array */
 __device__ __forceinline__ uint32_t bwd_tail_pack(const BwdTail &t) { return t.Bv | (t.pat << 20) | ((uint32_t)(t.P == 31) << 28); }

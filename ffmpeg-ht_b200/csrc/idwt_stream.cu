@@ -4,7 +4,7 @@
  * (libavcodec/jpeg2000dec.c:2183-2209, jpeg2000dsp.c:43-91) and write_frame_16 (jpeg2000dec.c:2301-2366).
  * SURVEY.md section 8(a) rows W1-W4, M1-M3, P1.
  *
- * ncu on the shared-memory tiled kernel (idwt.cu; profiles/r1_ncu_full_v1_summary.md) showed it bound by
+ * ncu on the shared-memory tiled kernel (idwt.cu; profiles/r1_ncu_full_v1_summary_warp_per_block_baseline.md) showed it bound by
  * instruction issue (60 % of issue slots, ~52 instructions per sample), not by HBM.  This kernel removes
  * the shared-memory round trips and most of the per-sample addressing:
  *   - a warp owns a strip of 32 x 2NP columns and walks down SEG output rows;

@@ -228,6 +228,39 @@ def test_frames_vs_oracle(cfg, dec, dec_bitexact):
             assert np.array_equal(got, want), "float path is expected to be bit-identical as well"
 
 
+@pytest.mark.parametrize("npasses", [1, 3])
+def test_fuzzed_codestreams_match_oracle(npasses, dec):
+    """Damage anywhere behind the SIZ marker (truncation, bit flips, random bytes): either both sides reject
+    the packet with the same error, or both deliver the same picture -- host parser and kernels together."""
+    planes = j2kgen.synth_image(96, 80, 3, 12, seed=3)
+    cs = j2kgen.encode(planes, 12, j2kgen.EncParams(levels=3, cblk=(32, 32), npasses=npasses))
+    rng = np.random.default_rng(50 + npasses)
+    same_pixels = rejected = 0
+    for _ in range(80):
+        bad = bytearray(cs)
+        mode = rng.integers(0, 3)
+        if mode == 0:
+            bad = bad[: int(rng.integers(60, len(bad)))]
+        elif mode == 1:
+            for _ in range(int(rng.integers(1, 5))):
+                bad[int(rng.integers(110, len(bad)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            pos = int(rng.integers(110, len(bad) - 8))
+            bad[pos:pos + 8] = rng.integers(0, 256, 8, dtype=np.uint8).tobytes()
+        r, oinfo, want = oracle_decode(bytes(bad))
+        try:
+            info, got = dec.decode(bytes(bad))
+        except fb.DecodeError as e:
+            assert r < 0 and e.code == r, (r, e.code)
+            rejected += 1
+            continue
+        assert r == 0, r
+        assert (info.width, info.height, info.pix_fmt) == (oinfo[0], oinfo[1], oinfo[2])
+        assert np.array_equal(got, want)
+        same_pixels += 1
+    assert same_pixels > 10 and rejected > 0
+
+
 # geometries the register-streaming IDWT path accepts (even origins, 16-byte aligned band rows, packed 16-bit
 # output) next to ones where only some levels do: strips with border lanes, short segments, tiles
 STREAM_GEOMS = [
