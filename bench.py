@@ -109,7 +109,7 @@ def run_reference(args):
         "e2e": {"value": mpix, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -384,13 +384,36 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": n * pix / sec / 1e6, "unit": "Mpixel/s", "fps": n / sec, "cores": cores,
                                     "kind": kind, "sample": f"{n} frames of the same workload on {cores} threads "
                                                             f"({sec:.1f} s wall)"}
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL writes its version banner to
+    stdout when NCCL_DEBUG is set, torchrun children inherit it), so fd 1 is pointed at stderr for the whole
+    run and the result line is written to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -502,29 +502,30 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
         unsigned E1 = 0, E3 = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            uint32_t v = 0, val = 0;
+            /* straight-line on purpose (no divergent regions in the row loop): a sample without MagSgn bits
+             * reads a zero-length field */
             const int m = mlen[i];
-            if (m > 0) {
-                uint32_t p = min(pos, ms_bits);          /* past the end: ones */
-                v = ms_read(ms, p, m) + (((e1 >> i) & 1u) << m);
-                pos += m;
+            const int mm = max(m, 0);
+            const uint32_t p = min(pos, ms_bits);        /* past the end: ones */
+            uint32_t v = ms_read(ms, p, mm);
+            v += m > 0 ? ((e1 >> i) & 1u) << mm : 0u;
+            pos += mm;
+            const unsigned E = 32 - __clz(v | 1);        /* :419-425 */
+            if (i == 1) E1 = m != 0 ? E : 0;
+            if (i == 3) E3 = m != 0 ? E : 0;
+            uint32_t val;
+            if (DQ == DQ_INT53 && !REFINE) {
+                /* mu >> (31 - M_b) with mu = ((v >> 1) + 1) << pLSB | 1 << (pLSB - 1), then the sign: the
+                 * shifts are per-block constants (dequantization_int, jpeg2000dec.c:2120-2151) */
+                const uint32_t mag = (uint32_t)(((int32_t)v >> 1) + 1);
+                const int32_t r = (int32_t)(((mag << dq_up) >> dq_dn) | dq_half);
+                val = (uint32_t)((v & 1u) ? -r : r);
+            } else {
+                val = (uint32_t)(((int32_t)v >> 1) + 1) << pLSB;
+                val |= 1u << (pLSB - 1);
+                val |= (v & 1u) << 31;
             }
-            if (m != 0) {                                /* :419-425 */
-                unsigned E = 32 - __clz(v | 1);
-                if (i == 1) E1 = E;
-                if (i == 3) E3 = E;
-                if (DQ == DQ_INT53 && !REFINE) {
-                    /* mu >> (31 - M_b) with mu = ((v >> 1) + 1) << pLSB | 1 << (pLSB - 1), then the sign: the
-                     * shifts are per-block constants (dequantization_int, jpeg2000dec.c:2120-2151) */
-                    const uint32_t mag = (uint32_t)(((int32_t)v >> 1) + 1);
-                    const int32_t r = (int32_t)(((mag << dq_up) >> dq_dn) | dq_half);
-                    val = (uint32_t)((v & 1u) ? -r : r);
-                } else {
-                    val = (uint32_t)(((int32_t)v >> 1) + 1) << pLSB;
-                    val |= 1u << (pLSB - 1);
-                    val |= (v & 1u) << 31;
-                }
-            }
+            val = m != 0 ? val : 0u;
             mu[i] = val;
         }
         pE1 = E1;
