@@ -244,7 +244,6 @@ def run_ours(args):
     for _ in range(reps):
         stage_ms += np.array(dec.run_staged_timed(0))
     stage_ms /= reps
-    clocks = sampler.stop()
     dec.close()
 
     # ---------------- PCIe reference point for the end-to-end number ----------------
@@ -305,6 +304,7 @@ def run_ours(args):
     e2e_run(K)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()                       # sampled across both timed regions (kernel-only and end to end)
     barrier()
     e2e_s = max_over_ranks(e2e_s)
     # correctness of what was just timed: the last picture of thread 0 must be the lossless source
@@ -419,7 +419,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=16)
+    ap.add_argument("--frames-per-step", type=int, default=64)
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic frames that are cycled")
     ap.add_argument("--slots", type=int, default=8, help="frames in flight in the kernel-only leg")
     ap.add_argument("--host-threads", type=int, default=4, help="decoder contexts (host threads) in the e2e leg")

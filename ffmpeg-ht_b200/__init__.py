@@ -138,6 +138,11 @@ def _buf(b):
     return a.ctypes.data, a.size, a
 
 
+def flag_lowres(n: int) -> int:
+    """B200J2K_FLAG_LOWRES(n): AVCodecContext.lowres, drop the n highest resolution levels."""
+    return (int(n) & 15) << 8
+
+
 def probe(pkt, flags: int = 0) -> FrameInfo:
     """Header-only pass: frame geometry and pixel format (no device needed)."""
     addr, n, keep = _buf(pkt)
@@ -218,9 +223,9 @@ def frame_to_arrays(info: FrameInfo, planes):
 class Jpeg2000Decoder:
     """One decoder context (= one AVCodecContext of the reference) on one CUDA device."""
 
-    def __init__(self, device: int = 0, slots: int = 1, bitexact: bool = False):
+    def __init__(self, device: int = 0, slots: int = 1, bitexact: bool = False, lowres: int = 0):
         self._h = ctypes.c_void_p()
-        self.flags = FLAG_BITEXACT if bitexact else 0
+        self.flags = (FLAG_BITEXACT if bitexact else 0) | flag_lowres(lowres)
         _check(lib().b200j2k_create(ctypes.byref(self._h), device, slots, self.flags), "create")
         self.device = device
         self.slots = slots

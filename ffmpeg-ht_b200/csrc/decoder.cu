@@ -105,6 +105,8 @@ struct HtPlan {
 
     static int klass(const CblkDesc &d)
     {
+        if (d.flags & J2K_CBLK_SKIP)
+            return 5;                               /* dropped by lowres: no kernel touches it */
         const bool refine = d.npasses && (d.npasses % 3) != 1;
         if (d.w > 64)
             return refine ? 4 : 3;
@@ -129,12 +131,12 @@ struct HtPlan {
         scr_off.resize(n);
         maxL_fast = maxLref = maxL_wide = maxL_rwide = 0;
         scratch_words = 0;
-        size_t cnt[5] = { 0, 0, 0, 0, 0 };
+        size_t cnt[6] = { 0, 0, 0, 0, 0, 0 };
         for (size_t i = 0; i < n; i++)
             cnt[klass(cblk[i])]++;
-        size_t at[5];
+        size_t at[6];
         at[0] = 0;
-        for (int k = 1; k < 5; k++)
+        for (int k = 1; k < 6; k++)
             at[k] = at[k - 1] + cnt[k - 1];
         for (size_t k = 0; k < n; k++) {
             const uint32_t i = by_shape[k];

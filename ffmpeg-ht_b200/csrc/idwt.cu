@@ -357,9 +357,11 @@ idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__
                 a[c] = b[c] = 0;
             }
         }
-        if (TYPE == J2K_DWT97_INT) {
+        if (TYPE == J2K_DWT97_INT && nl > 0) {
             /* undo I_PRESHIFT: the last thing dwt_decode97_int does, i.e. before the component transform
-             * (jpeg2000dwt.c:534-536) */
+             * (jpeg2000dwt.c:534-536).  ff_dwt_decode returns before it when there is no level to undo
+             * (jpeg2000dwt.c:603-604): a plane without decomposition keeps its 2^8 pre-scale, as in the
+             * reference (reachable with lowres == levels under AV_CODEC_FLAG_BITEXACT) */
 #pragma unroll
             for (int c = 0; c < J2K_MAX_COMP; c++) {
                 a[c] = (uint32_t)((int32_t)((int64_t)(int32_t)a[c] + 128) >> 8);

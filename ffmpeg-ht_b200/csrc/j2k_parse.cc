@@ -8,7 +8,7 @@
  *   step sizes jpeg2000.c:214-272   packet headers jpeg2000dec.c:1136-1542 (HT paths)
  *   progression orders :1544-1833
  * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 MQ blocks, MIXED/HTDECLARED sets, POC,
- * PPM/PPT, JP2 wrapper, lowres -- SURVEY.md section 8(f) "next".
+ * PPM/PPT, JP2 wrapper -- SURVEY.md section 8(f) "next".
  */
 #include "j2k_parse.h"
 
@@ -37,6 +37,9 @@ int parse_cox(const uint8_t *p, const uint8_t *end, CodSty *c, int flags)
     c->nres = p[0] + 1;
     if (c->nres > J2K_MAX_LEVELS)
         return B200J2K_ERR_INVALIDDATA;
+    /* lowres (jpeg2000dec.c:509-520): more levels dropped than the stream has is an error */
+    if (c->nres <= B200J2K_FLAG_GET_LOWRES(flags))
+        return B200J2K_ERR_EINVAL;
     c->l2cw = (p[1] & 15) + 2;
     c->l2ch = (p[2] & 15) + 2;
     if (c->l2cw > 10 || c->l2ch > 10 || c->l2cw + c->l2ch > 12)
@@ -131,7 +134,7 @@ int choose_pix(const Header &h)
 }
 
 /* band step size, float path, same operation order as jpeg2000.c:214-272 */
-float band_stepsize(const CodSty &c, const QntSty &q, int bandno, int gbandno, int r, int cbps)
+float band_stepsize(const CodSty &c, const QntSty &q, int bandno, int gbandno, int r, int cbps, int red)
 {
     float f;
     if (q.style == 0) {
@@ -153,7 +156,7 @@ float band_stepsize(const CodSty &c, const QntSty &q, int bandno, int gbandno, i
             f *= 0.812893066115961f * 0.812893066115961f * 4;
             break;
         }
-        f *= pow(1.230174104914001f, 2 * (c.nres - r) + lband - 2);
+        f *= pow(1.230174104914001f, 2 * (c.nres - red - r) + lband - 2);   /* nreslevels2decode (jpeg2000.c:263) */
     }
     if (f > (INT32_MAX >> 15))
         f = 0;
@@ -272,7 +275,11 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             if ((int64_t)h.ntx * h.nty * 14 > size)
                 return B200J2K_ERR_EINVAL;
             parts_.assign((size_t)h.ntx * h.nty, {});
-            int ow = h.W - h.X0, oh = h.H - h.Y0;
+            const int red = B200J2K_FLAG_GET_LOWRES(flags);
+            if (red && (h.X0 || h.Y0))
+                return B200J2K_ERR_PATCHWELCOME;          /* jpeg2000dec.c:256-259 */
+            /* image size with the reduction factor (jpeg2000dec.c:314-320) */
+            int ow = ceildivpow2(h.W - h.X0, red), oh = ceildivpow2(h.H - h.Y0, red);
             h.out_w = ceildiv(ow, h.cdx[0]);
             h.out_h = ceildiv(oh, h.cdy[0]);
             for (int i = 1; i < nc; i++) {
@@ -465,6 +472,7 @@ int Parser::build_geometry(int flags)
     max_w = max_h = 0;
     max_area = max_state = 0;
     const int ntiles = h.ntx * h.nty;
+    const int red = B200J2K_FLAG_GET_LOWRES(flags);
     tiles_.resize(ntiles);
     const bool planar = h.pix == B200J2K_PIX_PLANAR8 || h.pix == B200J2K_PIX_PLANAR16;
     const bool wide = h.precision > 8;
@@ -488,11 +496,19 @@ int Parser::build_geometry(int flags)
                 return B200J2K_ERR_INVALIDDATA;
             if (!(cs.cblk_style & 0x40) || (cs.cblk_style & 0x80))
                 return B200J2K_ERR_PATCHWELCOME;          /* Part-1 MQ or MIXED code-blocks */
-            Rect cc;
+            /* cc = comp->coord_o: every resolution, band, precinct and code-block is laid out from it;
+             * cr = comp->coord = cc reduced by lowres: the plane, the DWT and the output use it
+             * (jpeg2000dec.c:1047-1050, jpeg2000.c:483-530) */
+            Rect cc, cr;
             cc.x0 = ceildiv(t.c.x0, h.cdx[c]); cc.x1 = ceildiv(t.c.x1, h.cdx[c]);
             cc.y0 = ceildiv(t.c.y0, h.cdy[c]); cc.y1 = ceildiv(t.c.y1, h.cdy[c]);
             t.comp[c] = cc;
-            const int cw = cc.x1 - cc.x0, ch = cc.y1 - cc.y0;
+            cr.x0 = ceildivpow2(cc.x0, red); cr.x1 = ceildivpow2(cc.x1, red);
+            cr.y0 = ceildivpow2(cc.y0, red); cr.y1 = ceildivpow2(cc.y1, red);
+            const int nres2decode = cs.nres - red;
+            if (nres2decode <= 0)
+                return B200J2K_ERR_EINVAL;
+            const int cw = cr.x1 - cr.x0, ch = cr.y1 - cr.y0;
             if (cw > 32768 || ch > 32768)
                 return B200J2K_ERR_PATCHWELCOME;
 
@@ -500,15 +516,15 @@ int Parser::build_geometry(int flags)
             memset(&tc, 0, sizeof(tc));
             tc.coef_off = (uint32_t)coef_elems;
             tc.width = cw; tc.height = ch;
-            tc.x0 = cc.x0; tc.y0 = cc.y0;
-            tc.nlevels = cs.nres - 1;
+            tc.x0 = cr.x0; tc.y0 = cr.y0;
+            tc.nlevels = nres2decode - 1;
             tc.transform = cs.transform;
             tc.comp = c;
-            tc.out_x = cc.x0 - ceildiv(h.X0, h.cdx[c]);
-            tc.out_y = cc.y0 - ceildiv(h.Y0, h.cdy[c]);
+            tc.out_x = cr.x0 - ceildiv(h.X0, h.cdx[c]);
+            tc.out_y = cr.y0 - ceildiv(h.Y0, h.cdy[c]);
             tc.cbps = h.cbps[c];
             {
-                int b[4] = { cc.x0, cc.x1, cc.y0, cc.y1 };
+                int b[4] = { cr.x0, cr.x1, cr.y0, cr.y1 };
                 for (int k = tc.nlevels; k >= 0; k--) {
                     tc.lev[k] = LevelDesc{ b[0], b[1], b[2], b[3] };
                     for (int i = 0; i < 4; i++)
@@ -555,7 +571,7 @@ int Parser::build_geometry(int flags)
                     BandDesc bdesc;
                     memset(&bdesc, 0, sizeof(bdesc));
                     {
-                        float fstep = band_stepsize(cs, qs, b, gband, r, h.cbps[c]);
+                        float fstep = band_stepsize(cs, qs, b, gband, r, h.cbps[c], red);
                         bdesc.i_stepsize = (int32_t)floorf(fstep * (1 << 15));
                         const int downshift = 31 - imax(M_b, 0);
                         float fscale = fstep;
@@ -606,6 +622,12 @@ int Parser::build_geometry(int flags)
                                 d.dst_off = tc.coef_off + (uint32_t)(y0 - bd.c.y0 + offy) * (uint32_t)cw + (uint32_t)(x0 - bd.c.x0 + offx);
                                 d.M_b = (uint8_t)M_b;
                                 d.flags = (uint8_t)(((cs.cblk_style & 8) ? 1 : 0) | (cs.transform << 1));
+                                if (r >= nres2decode) {
+                                    /* dropped by lowres: the packets are still parsed, the block is never decoded
+                                     * (tile_codeblocks walks nreslevels2decode levels, jpeg2000dec.c:2230) */
+                                    d.flags |= J2K_CBLK_SKIP;
+                                    d.dst_off = tc.coef_off;
+                                }
                                 d.roi_shift = (uint8_t)h.roi[c];
                                 d.band = (uint16_t)bd.band_index;
                                 if (bands.size() > 65535)
@@ -667,7 +689,6 @@ int Parser::build_geometry(int flags)
         }
     }
     ll_elems = coef_elems;   /* same offsets are used in the ping-pong buffers; they only hold <= 1/4 of each plane */
-    (void)flags;
     return 0;
 }
 

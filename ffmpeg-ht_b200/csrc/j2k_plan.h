@@ -22,6 +22,8 @@
 
 enum { J2K_DWT97 = 0, J2K_DWT53 = 1, J2K_DWT97_INT = 2 };   /* enum DWTType, jpeg2000dwt.h:37-41 */
 
+#define J2K_CBLK_SKIP 0x80
+
 /* one HT code-block: a row of the table H9 (Jpeg2000Cblk, jpeg2000.h:183-205) */
 typedef struct CblkDesc {
     uint32_t data_off;      /* offset of Dcup in bytes[]; Dref follows at data_off + Lcup */
@@ -32,7 +34,8 @@ typedef struct CblkDesc {
     uint8_t  npasses;
     uint8_t  zbp;
     uint8_t  M_b;           /* expn + guard bits - 1 (jpeg2000dec.c:2238) */
-    uint8_t  flags;         /* bit0: stripe-causal (JPEG2000_CBLK_VSC)  bits 1-2: dequant mode (DWT type) */
+    uint8_t  flags;         /* bit0: stripe-causal (JPEG2000_CBLK_VSC)  bits 1-2: dequant mode (DWT type)
+                             * bit7: J2K_CBLK_SKIP, resolution dropped by lowres: parsed, never decoded */
     uint8_t  roi_shift;
     uint8_t  pad;
     uint16_t band;          /* index into BandDesc[] */

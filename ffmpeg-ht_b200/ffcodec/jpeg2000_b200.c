@@ -17,7 +17,7 @@
  *   worker, libavcodec/pthread_frame.c:248-295) maps to one CUDA stream + staging buffers per worker.
  * Added: .close (device buffers must be released) and FF_CODEC_CAP_INIT_CLEANUP.
  * What it refuses (AVERROR_PATCHWELCOME, as the library reports): Part-1 MQ code-blocks, JP2 wrapper, POC,
- * PPM/PPT, lowres > 0 -- a build that wants those keeps the native decoder registered as fallback
+ * PPM/PPT -- a build that wants those keeps the native decoder registered as fallback
  * under a different name.
  */
 #include "libavutil/imgutils.h"
@@ -34,7 +34,8 @@ typedef struct B200J2KContext {
     const AVClass *class;
     b200j2k_decoder *dec;
     int device;             /* CUDA device index; -1 = round-robin over frame-thread workers */
-    int reduction_factor;   /* "lowres", accepted for option compatibility; only 0 is supported */
+    int reduction_factor;   /* the "lowres" private option; AVCodecContext.lowres feeds it (jpeg2000dec.c:2811-2818) */
+    int flags;              /* B200J2K_FLAG_* this context decodes with */
 } B200J2KContext;
 
 static av_cold int b200j2k_ff_init(AVCodecContext *avctx)
@@ -44,10 +45,17 @@ static av_cold int b200j2k_ff_init(AVCodecContext *avctx)
     int flags = (avctx->flags & AV_CODEC_FLAG_BITEXACT) ? B200J2K_FLAG_BITEXACT : 0;
     int device = s->device;
 
-    if (avctx->lowres || s->reduction_factor) {
-        avpriv_request_sample(avctx, "lowres with the B200 HTJ2K path");
-        return AVERROR_PATCHWELCOME;
-    }
+    /* jpeg2000_decode_init (jpeg2000dec.c:2807-2823) */
+    if (avctx->lowres)
+        av_log(avctx, AV_LOG_WARNING, "lowres is overriden by reduction_factor but set anyway\n");
+    if (!s->reduction_factor && avctx->lowres < 33)
+        s->reduction_factor = avctx->lowres;
+    if (avctx->lowres != s->reduction_factor && avctx->lowres)
+        return AVERROR(EINVAL);
+    if (s->reduction_factor > 15)
+        return AVERROR(EINVAL);
+    flags |= B200J2K_FLAG_LOWRES(s->reduction_factor);
+    s->flags = flags;
     if (ndev <= 0) {
         av_log(avctx, AV_LOG_ERROR, "no CUDA device: the B200 HTJ2K path has no CPU fallback\n");
         return AVERROR(ENODEV);
@@ -75,12 +83,13 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
     int linesize[4] = { 0 };
     enum AVPixelFormat fmt;
     int64_t consumed;
-    int ret, flags = (avctx->flags & AV_CODEC_FLAG_BITEXACT) ? B200J2K_FLAG_BITEXACT : 0;
+    int ret, flags = s->flags;
 
     /* header pass: everything jpeg2000_read_main_headers() publishes before the picture exists */
     if ((ret = b200j2k_probe(avpkt->data, avpkt->size, flags, &info)) < 0)
         return ret;
-    if ((ret = ff_set_dimensions(avctx, info.width, info.height)) < 0)
+    /* the generic layer shifts the dimensions back down by lowres (jpeg2000dec.c:326, utils.c:94-107) */
+    if ((ret = ff_set_dimensions(avctx, info.width << avctx->lowres, info.height << avctx->lowres)) < 0)
         return ret;
     if (info.pix_fmt == B200J2K_PIX_PLANAR8 || info.pix_fmt == B200J2K_PIX_PLANAR16) {
         /* planar YUV: the caller's pix_fmt, if it matches, else the first match of the native list
@@ -120,7 +129,7 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
 #define OFFSET(x) offsetof(B200J2KContext, x)
 #define VD AV_OPT_FLAG_VIDEO_PARAM | AV_OPT_FLAG_DECODING_PARAM
 static const AVOption b200j2k_options[] = {
-    { "lowres", "Lower the decoding resolution by a power of two (only 0 on this path)",
+    { "lowres", "Lower the decoding resolution by a power of two",
         OFFSET(reduction_factor), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 32, VD },
     { "device", "CUDA device index (-1: spread decoder contexts over all devices)",
         OFFSET(device), AV_OPT_TYPE_INT, { .i64 = -1 }, -1, 64, VD },

@@ -36,6 +36,10 @@ extern "C" {
 
 /* b200j2k_create flags */
 #define B200J2K_FLAG_BITEXACT 1   /* AV_CODEC_FLAG_BITEXACT: 9/7 runs the fixed-point path (jpeg2000dec.c:543-544) */
+/* AVCodecContext.lowres / the decoder's "lowres" option (jpeg2000dec.c:2807-2823, :2913-2924): drop the n
+ * highest resolution levels; picture dimensions shrink by 2^n.  n = 0..15 in bits 8-11 of the flags. */
+#define B200J2K_FLAG_LOWRES(n) (((n) & 15) << 8)
+#define B200J2K_FLAG_GET_LOWRES(flags) (((flags) >> 8) & 15)
 
 /* Output pixel formats.  b200j2k_pix_fmt_name() gives the libavutil name ("rgb48le", ...); the FFCodec
  * shim maps it to AVPixelFormat with av_get_pix_fmt().  Selection follows jpeg2000dec.c:134-193,:335-363. */

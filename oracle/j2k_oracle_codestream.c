@@ -70,7 +70,8 @@ typedef struct QntSty {
 } QntSty;
 
 typedef struct Comp {
-    Rect c;
+    Rect c;                                         /* comp->coord_o: full-resolution bounds */
+    Rect cr;                                        /* comp->coord: reduced by lowres (jpeg2000dec.c:1047-1050) */
     Res *res;
     void *data;
     int roi_shift;
@@ -88,6 +89,7 @@ typedef struct Tile {
 typedef struct Dec {
     const uint8_t *cs, *end;
     int bitexact;
+    int red;                                        /* reduction_factor = AVCodecContext.lowres (jpeg2000dec.c:2807-2823) */
     int W, H, X0, Y0, TW, TH, TX0, TY0, ncomp, precision;
     int cbps[MAXC], cdx[MAXC], cdy[MAXC], roi[MAXC];
     int isHT, cap_b05, cap_b14;
@@ -194,6 +196,8 @@ static int parse_cox(Dec *d, const uint8_t *p, const uint8_t *end, CodSty *c)
     c->nres = p[0] + 1;
     if (c->nres >= MAXRES)
         return ORACLE_ERR_INVALID;
+    if (c->nres <= d->red)                          /* "reduction_factor too large for this bitstream" (:509-517) */
+        return ORACLE_ERR_EINVAL;
     c->l2cw = (p[1] & 15) + 2;
     c->l2ch = (p[2] & 15) + 2;
     if (c->l2cw > 10 || c->l2ch > 10 || c->l2cw + c->l2ch > 12)
@@ -362,7 +366,9 @@ static int parse_headers(Dec *d)
             if ((int64_t)d->ntx * d->nty * 14 > d->end - d->cs)
                 return ORACLE_ERR_EINVAL;
             d->tile = calloc((size_t)d->ntx * d->nty, sizeof(Tile));
-            int ow = d->W - d->X0, oh = d->H - d->Y0;
+            if (d->red && (d->X0 || d->Y0))
+                return ORACLE_ERR_PATCH;                  /* :256-259 */
+            int ow = ceildivpow2(d->W - d->X0, d->red), oh = ceildivpow2(d->H - d->Y0, d->red);   /* :314-320 */
             d->out_w = ceildiv(ow, d->cdx[0]);
             d->out_h = ceildiv(oh, d->cdy[0]);
             for (int i = 1; i < nc; i++) {
@@ -519,7 +525,7 @@ static int parse_headers(Dec *d)
 /* ---- geometry -------------------------------------------------------------------------------------- */
 
 /* jpeg2000.c:214-272 -- same operations in the same types so that the float result is identical */
-static void band_stepsize(Band *b, const CodSty *c, const QntSty *q, int bandno, int gbandno, int r, int cbps)
+static void band_stepsize(Band *b, const CodSty *c, const QntSty *q, int bandno, int gbandno, int r, int cbps, int red)
 {
     float f;
     if (q->style == 0) {
@@ -541,7 +547,7 @@ static void band_stepsize(Band *b, const CodSty *c, const QntSty *q, int bandno,
             f *= 0.812893066115961f * 0.812893066115961f * 4;
             break;
         }
-        f *= pow(1.230174104914001f, 2 * (c->nres - r) + lband - 2);
+        f *= pow(1.230174104914001f, 2 * (c->nres - red - r) + lband - 2);   /* nreslevels2decode (jpeg2000.c:263) */
     }
     if (f > (INT32_MAX >> 15))
         f = 0;
@@ -576,7 +582,13 @@ static int init_tile(Dec *d, int tileno)
         comp->c.y1 = ceildiv(t->c.y1, d->cdy[c]);
         if (!comp->roi_shift)
             comp->roi_shift = d->roi[c];
-        const int cw = comp->c.x1 - comp->c.x0, ch = comp->c.y1 - comp->c.y0;
+        comp->cr.x0 = ceildivpow2(comp->c.x0, d->red);
+        comp->cr.x1 = ceildivpow2(comp->c.x1, d->red);
+        comp->cr.y0 = ceildivpow2(comp->c.y0, d->red);
+        comp->cr.y1 = ceildivpow2(comp->c.y1, d->red);
+        if (cs->nres - d->red <= 0)
+            return ORACLE_ERR_EINVAL;
+        const int cw = comp->cr.x1 - comp->cr.x0, ch = comp->cr.y1 - comp->cr.y0;
         if (cw > 32768 || ch > 32768)
             return ORACLE_ERR_PATCH;
         comp->data = calloc((size_t)cw * ch + 16, 4);
@@ -596,7 +608,7 @@ static int init_tile(Dec *d, int tileno)
             rl->npy = rl->c.y1 == rl->c.y0 ? 0 : ceildivpow2(rl->c.y1, rl->ppy) - (rl->c.y0 >> rl->ppy);
             for (int b = 0; b < rl->nbands; b++, gband++) {
                 Band *bd = &rl->band[b];
-                band_stepsize(bd, cs, qs, b, gband, r, d->cbps[c]);
+                band_stepsize(bd, cs, qs, b, gband, r, d->cbps[c], d->red);
                 int bppx, bppy;
                 if (r == 0) {
                     bd->c = rl->c;
@@ -1093,9 +1105,9 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
         Comp *comp = &t->comp[c];
         const CodSty *cs = &d->cod[c];
         const QntSty *qs = &d->qnt[c];
-        const int W = comp->c.x1 - comp->c.x0;
+        const int W = comp->cr.x1 - comp->cr.x0;
         int coded = 0, subband = 0;
-        for (int r = 0; r < cs->nres; r++) {
+        for (int r = 0; r < cs->nres - d->red; r++) {      /* nreslevels2decode (:2230) */
             Res *rl = &comp->res[r];
             for (int b = 0; b < rl->nbands; b++, subband++) {
                 Band *bd = &rl->band[b];
@@ -1130,8 +1142,8 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
             }
         }
         if (coded) {
-            int border[4] = { comp->c.x0, comp->c.x1, comp->c.y0, comp->c.y1 };
-            oracle_idwt(cs->transform, border, cs->nres - 1, comp->data);
+            int border[4] = { comp->cr.x0, comp->cr.x1, comp->cr.y0, comp->cr.y1 };
+            oracle_idwt(cs->transform, border, cs->nres - d->red - 1, comp->data);
         }
     }
     free(t1);
@@ -1139,10 +1151,10 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
     if (d->cod[0].mct) {                                  /* mct_decode (jpeg2000dec.c:2183-2209) */
         int ok = 1;
         for (int i = 1; i < 3; i++)
-            ok &= d->cod[0].transform == d->cod[i].transform && !memcmp(&t->comp[0].c, &t->comp[i].c, sizeof(Rect));
+            ok &= d->cod[0].transform == d->cod[i].transform && !memcmp(&t->comp[0].cr, &t->comp[i].cr, sizeof(Rect));
         if (ok)
             oracle_mct(d->cod[0].transform, t->comp[0].data, t->comp[1].data, t->comp[2].data,
-                       (t->comp[0].c.x1 - t->comp[0].c.x0) * (t->comp[0].c.y1 - t->comp[0].c.y0));
+                       (t->comp[0].cr.x1 - t->comp[0].cr.x0) * (t->comp[0].cr.y1 - t->comp[0].cr.y0));
     }
 
     /* write_frame_8/16 (jpeg2000dec.c:2301-2366) */
@@ -1155,14 +1167,14 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
         Comp *comp = &t->comp[c];
         const int cbps = d->cbps[c];
         const int plane = planar ? c : 0;
-        const int w = comp->c.x1 - ceildiv(d->X0, d->cdx[c]);
-        const int h = comp->c.y1 - ceildiv(d->Y0, d->cdy[c]);
+        const int w = comp->cr.x1 - ceildiv(d->X0, d->cdx[c]);
+        const int h = comp->cr.y1 - ceildiv(d->Y0, d->cdy[c]);
         const float *fp = comp->data;
         const int32_t *ip = comp->data;
         size_t k = 0;
-        for (int y = comp->c.y0 - ceildiv(d->Y0, d->cdy[c]); y < h; y++) {
+        for (int y = comp->cr.y0 - ceildiv(d->Y0, d->cdy[c]); y < h; y++) {
             uint8_t *line = planes[plane] + (size_t)y * strides[plane];
-            for (int x = comp->c.x0 - ceildiv(d->X0, d->cdx[c]); x < w; x++, k++) {
+            for (int x = comp->cr.x0 - ceildiv(d->X0, d->cdx[c]); x < w; x++, k++) {
                 int val = d->cod[c].transform == ORACLE_DWT97 ? (int)lrintf(fp[k]) : ip[k];
                 val += 1 << (cbps - 1);
                 val = clip(val, 0, (1 << cbps) - 1);
@@ -1193,7 +1205,8 @@ int oracle_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, u
     memset(&d, 0, sizeof(d));
     d.cs = cs;
     d.end = cs + len;
-    d.bitexact = bitexact;
+    d.bitexact = bitexact & 1;                      /* the argument carries flags: bit 0 BITEXACT, bits 8-11 lowres */
+    d.red = (bitexact >> 8) & 15;
     int ret = parse_headers(&d);
     if (ret < 0)
         goto end;

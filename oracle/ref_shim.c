@@ -61,8 +61,8 @@ int ff_set_dimensions(AVCodecContext *s, int width, int height)
         width = height = 0;
     s->coded_width  = width;
     s->coded_height = height;
-    s->width        = width;
-    s->height       = height;
+    s->width        = AV_CEIL_RSHIFT(width,  s->lowres);     /* as libavcodec/utils.c:94-107 */
+    s->height       = AV_CEIL_RSHIFT(height, s->lowres);
     return ret;
 }
 
@@ -108,7 +108,8 @@ static AVCodecContext *ctx_open(int bitexact)
     avctx->pix_fmt    = AV_PIX_FMT_NONE;
     avctx->max_pixels = INT32_MAX;
     avctx->execute2   = serial_execute2;
-    avctx->flags      = bitexact ? AV_CODEC_FLAG_BITEXACT : 0;
+    avctx->flags      = (bitexact & 1) ? AV_CODEC_FLAG_BITEXACT : 0;   /* argument = flags: bit 0 BITEXACT, bits 8-11 lowres */
+    avctx->lowres     = (bitexact >> 8) & 15;
     avctx->priv_data  = av_mallocz(REF_CODEC.priv_data_size);
     if (!avctx->priv_data) {
         av_free(avctx);

@@ -37,12 +37,14 @@ def test_ffcodec_shim_equals_reference(kw):
     p = j2kgen.EncParams(**kw)
     cs = j2kgen.encode(planes, bd, p)
     for bitexact in ((0,) if p.reversible else (0, 1)):
-        r1, i1, o1, _ = ref_decode(cs, bitexact)
-        r2, i2, o2 = shim_decode(cs, bitexact)
-        assert r1 == 0 and r2 == 0
-        assert i1[:3] == i2[:3]            # width, height, AVPixelFormat
-        assert i1[4] == i2[4]              # bytes consumed (decode() return value)
-        assert np.array_equal(o1, o2)
+        for lowres in (0, 1, 2):           # AVCodecContext.lowres, passed in bits 8-11 of the harness flags
+            flags = bitexact | (lowres << 8)
+            r1, i1, o1, _ = ref_decode(cs, flags)
+            r2, i2, o2 = shim_decode(cs, flags)
+            assert r1 == 0 and r2 == 0
+            assert i1[:3] == i2[:3]            # width, height, AVPixelFormat
+            assert i1[4] == i2[4]              # bytes consumed (decode() return value)
+            assert np.array_equal(o1, o2)
 
 
 def test_ffcodec_shim_error_codes():

@@ -293,6 +293,35 @@ def test_streaming_idwt_geometries(cfg, dec, dec_bitexact):
         assert np.array_equal(img >> (16 - bd), np.stack(planes, -1))
 
 
+@pytest.mark.parametrize("lowres", [1, 2, 3])
+def test_lowres_frames_vs_oracle(lowres):
+    """AVCodecContext.lowres through the C ABI: dimensions and pixels equal the oracle's."""
+    cases = [
+        (dict(w=512, h=300, nc=3, bd=12, levels=5), 0),
+        (dict(w=250, h=131, nc=3, bd=12, levels=5, tile=(128, 64)), 0),
+        (dict(w=256, h=256, nc=3, bd=10, levels=3, reversible=False, base_step=1.0), 0),
+        (dict(w=256, h=256, nc=3, bd=10, levels=3, reversible=False, base_step=1.0), 1),
+        (dict(w=255, h=253, nc=3, bd=12, levels=3, cblk=(32, 32), npasses=3, vsc=True), 0),
+        (dict(w=1024, h=512, nc=1, bd=16, levels=4), 0),
+    ]
+    for cfg, bitexact in cases:
+        cfg = dict(cfg)
+        w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+        planes = j2kgen.synth_image(w, h, nc, bd, seed=14)
+        cs = j2kgen.encode(planes, bd, j2kgen.EncParams(**cfg))
+        r, oinfo, want = oracle_decode(cs, bitexact | (lowres << 8))
+        assert r == 0
+        with fb.Jpeg2000Decoder(device=0, slots=1, bitexact=bool(bitexact), lowres=lowres) as d:
+            info, got = d.decode(cs)
+        assert (info.width, info.height, info.pix_fmt) == (oinfo[0], oinfo[1], oinfo[2])
+        assert np.array_equal(got, want), (cfg, lowres)
+    # more levels dropped than the stream has: the reference's EINVAL
+    with fb.Jpeg2000Decoder(device=0, slots=1, lowres=7) as d:
+        with pytest.raises(fb.DecodeError) as e:
+            d.decode(cs)
+        assert e.value.code == -22
+
+
 def test_pipelined_submit_wait(dec):
     """Several frames in flight on one context, pinned output planes, results in order."""
     frames = []

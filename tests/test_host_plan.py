@@ -21,6 +21,8 @@ def picture_from_plan(cs: bytes, flags: int):
     allbytes = np.concatenate([data, P["extra"], np.zeros(64, np.uint8)])
     coef = np.zeros(int(P["coef_elems"]) + 64, np.uint32)
     for d in P["cblk"]:
+        if int(d["flags"]) & 0x80:                  # J2K_CBLK_SKIP: resolution dropped by lowres
+            continue
         w, h, M_b = int(d["w"]), int(d["h"]), int(d["M_b"])
         seg = allbytes[int(d["data_off"]): int(d["data_off"]) + int(d["length"])].tobytes()
         ret, sm = ht_block(oracle().oracle_ht_block, seg, int(d["npasses"]), int(d["Lcup"]), int(d["Lref"]),
@@ -85,6 +87,40 @@ def picture_from_plan(cs: bytes, flags: int):
                 r = row.view(np.uint16) if wide else row
                 r[int(tc["out_x"]) * ps + so: (int(tc["out_x"]) + W) * ps + so: ps] = val[y]
     return info, pic
+
+
+LOWRES_STREAMS = [
+    dict(w=256, h=200, nc=3, bd=12, levels=5),
+    dict(w=250, h=131, nc=3, bd=12, levels=5, tile=(128, 64)),
+    dict(w=256, h=256, nc=3, bd=10, levels=3, reversible=False, base_step=1.0),
+    dict(w=255, h=253, nc=3, bd=12, levels=3, cblk=(32, 32), npasses=3, vsc=True),
+    dict(w=300, h=200, nc=1, bd=16, levels=5, cblk=(128, 32)),
+    dict(w=256, h=256, nc=3, bd=12, levels=3, cblk=(32, 32), precincts=[(6, 6), (7, 7)], prog=3),
+]
+
+
+@pytest.mark.parametrize("cfg", LOWRES_STREAMS, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
+def test_plan_with_lowres_reproduces_oracle_picture(cfg):
+    """AVCodecContext.lowres: the dropped resolutions are parsed but flagged, planes / DWT levels / output
+    shrink as the reference's do (jpeg2000dec.c:314-320, :509-520, :1047-1050)."""
+    cfg = dict(cfg)
+    w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=12)
+    p = j2kgen.EncParams(**cfg)
+    cs = j2kgen.encode(planes, bd, p)
+    for lowres in range(1, p.levels + 2):
+        for bitexact in ((0,) if p.reversible else (0, 1)):
+            flags = (fb.FLAG_BITEXACT if bitexact else 0) | fb.flag_lowres(lowres)
+            r, oinfo, opic = oracle_decode(cs, bitexact | (lowres << 8))
+            if r < 0:
+                assert lowres > p.levels and r == -22
+                with pytest.raises(fb.DecodeError) as e:
+                    fb.plan(cs, flags)
+                assert e.value.code == r
+                continue
+            info, pic = picture_from_plan(cs, flags)
+            assert (info.width, info.height, info.pix_fmt) == (oinfo[0], oinfo[1], oinfo[2])
+            assert np.array_equal(pic, opic), (lowres, bitexact)
 
 
 @pytest.mark.parametrize("cfg", STREAMS, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])

@@ -148,6 +148,28 @@ def test_frame_decode_bit_exact(cfg):
         assert np.array_equal(img >> shift, np.stack(planes, -1))
 
 
+@pytest.mark.parametrize("cfg", [STREAMS[2], STREAMS[3], STREAMS[6], STREAMS[12], STREAMS[14], STREAMS[16]],
+                         ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
+def test_lowres_decode_bit_exact(cfg):
+    """AVCodecContext.lowres = 1 .. levels + 1 (the last one is the reference's "reduction_factor too large"
+    EINVAL; streams with an image offset are AVERROR_PATCHWELCOME): oracle == reference, dimensions,
+    pixels and error codes."""
+    cfg = dict(cfg)
+    w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=11)
+    p = j2kgen.EncParams(**cfg)
+    cs = j2kgen.encode(planes, bd, p)
+    for lowres in range(1, p.levels + 2):
+        for bitexact in ((0,) if p.reversible else (0, 1)):
+            flags = bitexact | (lowres << 8)
+            r1, info1, out1, name = ref_decode(cs, flags)
+            r2, info2, out2 = oracle_decode(cs, flags)
+            assert r1 == r2, (lowres, r1, r2)
+            if r1 == 0:
+                assert info1[:2] == info2[:2] and ORACLE_PIX[info2[2]] == name
+                assert np.array_equal(out1, out2), lowres
+
+
 def test_error_codes_match():
     """Truncated / damaged codestreams: both fail, or both succeed with identical pixels."""
     planes = j2kgen.synth_image(96, 80, 3, 12, seed=3)
