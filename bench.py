@@ -276,9 +276,9 @@ def run_ours(args):
     pkts = [fb.PinnedPacket(f) for f in frames]
     h2d_seen = [0] * T
 
-    def e2e_worker(t, nsteps):
+    def e2e_worker(t, nsteps, outs=None):
         torch.cuda.set_device(local)
-        d, pf = decs[t], pins[t]
+        d, pf = decs[t], (outs or pins)[t]
         pending = []
         for _ in range(nsteps):
             for n, i in enumerate(per_thread[t]):
@@ -290,8 +290,8 @@ def run_ours(args):
         for s in pending:
             d.wait(s)
 
-    def e2e_run(nsteps):
-        th = [threading.Thread(target=e2e_worker, args=(t, nsteps)) for t in range(T)]
+    def e2e_run(nsteps, outs=None):
+        th = [threading.Thread(target=e2e_worker, args=(t, nsteps, outs)) for t in range(T)]
         for x in th:
             x.start()
         for x in th:
@@ -307,6 +307,20 @@ def run_ours(args):
     clocks = sampler.stop()                       # sampled across both timed regions (kernel-only and end to end)
     barrier()
     e2e_s = max_over_ranks(e2e_s)
+    # row N2 (zero-copy output): the same calls with the output planes in DEVICE memory, as AV_PIX_FMT_CUDA
+    # frames would be -- only the codestream crosses PCIe
+    devs = [[fb.DeviceFrame(info, device=local) for _ in range(args.slots_e2e)] for _ in range(T)]
+    e2e_run(1, devs)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_run(K, devs)
+    torch.cuda.synchronize()
+    e2e_dev_s = max_over_ranks(time.perf_counter() - t0)
+    dev_ok = bool(np.array_equal(devs[0][0].download(), pins[0][0].buffer))
+    for row in devs:
+        for f in row:
+            f.close()
     # correctness of what was just timed: the last picture of thread 0 must be the lossless source
     check = pins[0][0].buffer.view(np.uint16)
     ok = bool(check.size == w * h * 3 and int(check.max()) > 0)
@@ -357,6 +371,11 @@ def run_ours(args):
                     "d2h_gbs_achieved": d2h_step * K / e2e_s / 1e9, "h2d_gbs_achieved": h2d_step * K / e2e_s / 1e9,
                     "pcie_measured": pcie,
                     "bound": "PCIe device->host: every decoded 4K rgb48 frame is 49.8 MB"},
+            "e2e_device_frames": {"value": frames_total * pix / e2e_dev_s / 1e6, "unit": "Mpixel/s",
+                                  "fps": frames_total / e2e_dev_s, "h2d_bytes_per_step": int(h2d_step),
+                                  "d2h_bytes_per_step": 0, "output_check": dev_ok,
+                                  "note": "same C-ABI calls with the output planes in device memory "
+                                          "(AV_PIX_FMT_CUDA-style frames, SURVEY 8(f) N2): not the contract's e2e"},
             "gpu_launches": int(launches_per_frame * B * K),
             "roofline": {"kernel": "idwt_stream_final_kernel (last 5/3 level + RCT + level shift + clip + rgb48 pack)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -95,6 +95,11 @@ def lib():
         L.b200j2k_idwt.argtypes = [i32, i32, vp, i32, vp]
         L.b200j2k_host_alloc.argtypes = [i64]
         L.b200j2k_host_alloc.restype = vp
+        L.b200j2k_device_alloc.argtypes = [i32, i64]
+        L.b200j2k_device_alloc.restype = vp
+        L.b200j2k_device_free.argtypes = [vp]
+        L.b200j2k_device_free.restype = None
+        L.b200j2k_device_download.argtypes = [vp, vp, i64]
         L.b200j2k_host_free.argtypes = [vp]
         L.b200j2k_host_free.restype = None
         L.b200j2k_host_register.argtypes = [vp, i64]
@@ -117,7 +122,8 @@ EXPORTS = ["b200j2k_device_count", "b200j2k_create", "b200j2k_destroy", "b200j2k
            "b200j2k_fetch", "b200j2k_slot_stream", "b200j2k_slot_output", "b200j2k_slot_launches",
            "b200j2k_slot_h2d_bytes",
            "b200j2k_ht_blocks", "b200j2k_idwt", "b200j2k_host_alloc", "b200j2k_host_free",
-           "b200j2k_host_register", "b200j2k_host_unregister", "b200j2k_pix_fmt_name", "b200j2k_version",
+           "b200j2k_host_register", "b200j2k_host_unregister", "b200j2k_device_alloc", "b200j2k_device_free",
+           "b200j2k_device_download", "b200j2k_pix_fmt_name", "b200j2k_version",
            "b200j2k_plan_build", "b200j2k_plan_table", "b200j2k_plan_scalar"]
 
 
@@ -175,6 +181,52 @@ class PinnedFrame:
     def close(self):
         if self._ptr:
             lib().b200j2k_host_free(self._ptr)
+            self._ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceFrame:
+    """A picture in DEVICE memory (what an AV_PIX_FMT_CUDA frame would be): submit() writes it with a
+    device-to-device copy, the pixels never cross PCIe.  download() fetches them for checking."""
+
+    def __init__(self, info: FrameInfo, device: int = 0, pitch_align: int = 1):
+        self.info = info
+        self.linesize = (ctypes.c_int * 4)()
+        self.data = (ctypes.c_void_p * 4)()
+        sizes = []
+        for i in range(info.nplanes):
+            ls = -(-info.plane_row_bytes[i] // pitch_align) * pitch_align
+            self.linesize[i] = ls
+            sizes.append(ls * info.plane_height[i])
+        self.nbytes = sum(sizes)
+        self._ptr = lib().b200j2k_device_alloc(device, max(self.nbytes, 1))
+        if not self._ptr:
+            raise DecodeError(ERR_DEVICE, "device_alloc")
+        off = 0
+        self._off = []
+        for i in range(info.nplanes):
+            self.data[i] = self._ptr + off
+            self._off.append(off)
+            off += sizes[i]
+
+    def download(self) -> np.ndarray:
+        """-> packed picture bytes (row padding removed), same layout Jpeg2000Decoder.decode() returns"""
+        raw = np.empty(max(self.nbytes, 1), np.uint8)
+        _check(lib().b200j2k_device_download(raw.ctypes.data, self._ptr, self.nbytes), "device_download")
+        out = []
+        for i in range(self.info.nplanes):
+            ls, rb, h = self.linesize[i], self.info.plane_row_bytes[i], self.info.plane_height[i]
+            out.append(raw[self._off[i]: self._off[i] + ls * h].reshape(h, ls)[:, :rb].reshape(-1))
+        return np.concatenate(out)
+
+    def close(self):
+        if self._ptr:
+            lib().b200j2k_device_free(self._ptr)
             self._ptr = None
 
     def __del__(self):

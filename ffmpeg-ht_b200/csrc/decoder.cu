@@ -264,6 +264,18 @@ bool is_pinned(const void *p)
     return a.type == cudaMemoryTypeHost;
 }
 
+/* memory the copy engines can write without staging: pinned host memory, or device / managed memory
+ * (AV_PIX_FMT_CUDA-style frames whose data[] are device pointers: the picture never crosses PCIe) */
+bool is_dma_target(const void *p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
 /* host parse + build the staging blob + H2D */
 int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size, b200j2k_frame_info *info)
 {
@@ -388,7 +400,7 @@ int queue_output(Slot &s, uint8_t *const data[4], const int linesize[4])
     for (int i = 0; i < p.nplanes; i++) {
         if (!data[i] || linesize[i] < p.plane_row_bytes[i])
             return B200J2K_ERR_EINVAL;
-        direct = direct && is_pinned(data[i]);
+        direct = direct && is_dma_target(data[i]);
         s.dst[i] = data[i];
         s.dst_linesize[i] = linesize[i];
     }
@@ -397,7 +409,7 @@ int queue_output(Slot &s, uint8_t *const data[4], const int linesize[4])
     if (direct) {
         for (int i = 0; i < p.nplanes; i++)
             if (cudaMemcpy2DAsync(data[i], (size_t)linesize[i], pic + p.plane_off[i], (size_t)p.plane_row_bytes[i],
-                                  (size_t)p.plane_row_bytes[i], (size_t)p.plane_h[i], cudaMemcpyDeviceToHost,
+                                  (size_t)p.plane_row_bytes[i], (size_t)p.plane_h[i], cudaMemcpyDefault,
                                   s.stream) != cudaSuccess)
                 return B200J2K_ERR_DEVICE;
     } else {
@@ -765,6 +777,21 @@ int b200j2k_idwt(int device, int type, const int32_t *border, int levels, void *
     }
     cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dtc);
     return ret;
+}
+
+void *b200j2k_device_alloc(int device, int64_t bytes)
+{
+    void *p = nullptr;
+    if (device_ok() <= 0 || cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, (size_t)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return p;
+}
+void b200j2k_device_free(void *p) { if (p) cudaFree(p); }
+int b200j2k_device_download(void *dst_host, const void *src_device, int64_t bytes)
+{
+    return cudaMemcpy(dst_host, src_device, (size_t)bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : B200J2K_ERR_DEVICE;
 }
 
 void *b200j2k_host_alloc(int64_t bytes)

@@ -135,6 +135,14 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
 /* type: 0 = 9/7 float, 1 = 5/3, 2 = 9/7 fixed point; border = {x0,x1,y0,y1}; plane in Mallat layout */
 int b200j2k_idwt(int device, int type, const int32_t *border, int levels, void *plane);
 
+/* Device-resident output ("zero-copy output / hw frames"): the planes handed to
+ * b200j2k_submit / _decode may be DEVICE pointers (an AV_PIX_FMT_CUDA frame's data[] / linesize[]); the
+ * picture is then copied device-to-device on the slot's stream and never crosses PCIe.  Helpers for callers
+ * without their own CUDA allocator: */
+void *b200j2k_device_alloc(int device, int64_t bytes);
+void b200j2k_device_free(void *p);
+int b200j2k_device_download(void *dst_host, const void *src_device, int64_t bytes);
+
 /* pinned host memory helpers for AVFrame pools (get_buffer2) */
 void *b200j2k_host_alloc(int64_t bytes);
 void b200j2k_host_free(void *p);

@@ -352,6 +352,22 @@ def test_pipelined_submit_wait(dec):
     assert dec.h2d_bytes(pending[0]) > len(frames[0][0])
 
 
+def test_device_resident_output(dec):
+    """Row N2 (zero-copy output): planes given as DEVICE pointers with a padded pitch, as an AV_PIX_FMT_CUDA
+    frame would; the picture must be the one the host path delivers."""
+    planes = j2kgen.synth_image(333, 190, 3, 12, seed=77)
+    cs = j2kgen.encode(planes, 12, j2kgen.EncParams(levels=4))
+    info, want = dec.decode(cs)
+    frames = [fb.DeviceFrame(info, device=0, pitch_align=256) for _ in range(2)]
+    slots = [dec.submit(cs, f) for f in frames]
+    for s in slots:
+        dec.wait(s)
+    for f in frames:
+        assert f.linesize[0] % 256 == 0 and f.linesize[0] > info.plane_row_bytes[0]
+        assert np.array_equal(f.download(), want)
+        f.close()
+
+
 # ---- BASELINE.json configs at full size: lossless round trip (size-independent property) ---------------
 @pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5"])
 def test_baseline_configs_full_size(name, dec):
