@@ -38,7 +38,13 @@ class FrameInfo(ctypes.Structure):
                 ("profile", ctypes.c_int32), ("nplanes", ctypes.c_int32),
                 ("plane_width", ctypes.c_int32 * 4), ("plane_height", ctypes.c_int32 * 4),
                 ("plane_row_bytes", ctypes.c_int32 * 4), ("ntiles", ctypes.c_int32),
-                ("ncodeblocks", ctypes.c_int32), ("bytes_consumed", ctypes.c_int64)]
+                ("ncodeblocks", ctypes.c_int32), ("bytes_consumed", ctypes.c_int64),
+                ("av_pix_fmt_name", ctypes.c_char * 16)]
+
+    @property
+    def pix_name(self) -> str:
+        """libavutil name of the AVPixelFormat the reference would choose ("rgb48le", "yuv420p10le", ...)"""
+        return self.av_pix_fmt_name.decode()
 
 
 class DecodeError(RuntimeError):
@@ -421,7 +427,8 @@ TC_DTYPE = np.dtype([("coef_off", "<u4"), ("width", "<i4"), ("height", "<i4"), (
                      ("nlevels", "<i4"), ("transform", "<i4"), ("comp", "<i4"), ("out_x", "<i4"), ("out_y", "<i4"),
                      ("cbps", "<i4"), ("group", "<i4"), ("lev", LEVEL_DTYPE, (33,))])
 GROUP_DTYPE = np.dtype([("ncomp", "<i4"), ("tc", "<i4", (4,)), ("mct", "<i4"), ("plane", "<i4"),
-                        ("pixel_stride", "<i4"), ("sample_off", "<i4", (4,)), ("shift", "<i4", (4,)), ("wide", "<i4")])
+                        ("pixel_stride", "<i4"), ("sample_off", "<i4", (4,)), ("shift", "<i4", (4,)), ("wide", "<i4"),
+                        ("comp_plane", "<i4", (4,))])
 
 
 def plan(pkt, flags: int = 0):

@@ -252,6 +252,7 @@ void fill_info(const Parser &p, b200j2k_frame_info *info)
     info->ntiles = p.hdr.ntx * p.hdr.nty;
     info->ncodeblocks = (int32_t)p.cblk.size();
     info->bytes_consumed = p.consumed;
+    strncpy(info->av_pix_fmt_name, p.hdr.pix_name, sizeof(info->av_pix_fmt_name) - 1);
 }
 
 bool is_pinned(const void *p)

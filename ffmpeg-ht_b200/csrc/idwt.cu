@@ -393,13 +393,18 @@ idwt_final_pack_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__
 #pragma unroll
             for (int c = 0; c < J2K_MAX_COMP; c++) {
                 if (c < ncomp) {
+                    /* planar groups may send every component to its own plane (comp_plane) */
+                    const int pl = g.comp_plane[c];
+                    const uint64_t pof = pl == 0 ? po0 : pl == 1 ? po1 : pl == 2 ? po2 : po3;
+                    const int prb = pl == 0 ? rb0 : pl == 1 ? rb1 : pl == 2 ? rb2 : rb3;
+                    uint8_t *rowc = picture + pof + (size_t)(t0.out_y + Y - o.v0) * prb;
                     if (wide) {
-                        uint16_t *r16 = reinterpret_cast<uint16_t *>(row);
+                        uint16_t *r16 = reinterpret_cast<uint16_t *>(rowc);
                         if (okA) r16[px + soff[c]] = (uint16_t)pa[c];
                         if (okB) r16[px + pstride + soff[c]] = (uint16_t)pb[c];
                     } else {
-                        if (okA) row[px + soff[c]] = (uint8_t)pa[c];
-                        if (okB) row[px + pstride + soff[c]] = (uint8_t)pb[c];
+                        if (okA) rowc[px + soff[c]] = (uint8_t)pa[c];
+                        if (okB) rowc[px + pstride + soff[c]] = (uint8_t)pb[c];
                     }
                 }
             }

@@ -8,7 +8,7 @@
  *   step sizes jpeg2000.c:214-272   packet headers jpeg2000dec.c:1136-1542 (HT paths)
  *   progression orders :1544-1833
  * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 MQ blocks, MIXED/HTDECLARED sets, POC,
- * PPM/PPT, JP2 wrapper -- SURVEY.md section 8(f) "next".
+ * PPM/PPT -- SURVEY.md section 8(f) "next".
  */
 #include "j2k_parse.h"
 
@@ -104,33 +104,215 @@ int parse_qcx(const uint8_t *p, int n, QntSty *q)
     return 0;
 }
 
-/* raw codestream => all_pix_fmts order: first format with enough depth and matching subsampling */
-int choose_pix(const Header &h)
+/* ---- pixel format selection (get_siz, jpeg2000dec.c:134-193, :328-412) --------------------------------
+ * The reference walks a list of AVPixelFormats chosen by the JP2 colour specification (16 sRGB, 17 grey,
+ * 18 sYCC, anything else: all lists) and takes the first one pix_fmt_match() accepts.  The descriptors
+ * below are the fields of libavutil's AVPixFmtDescriptor that pix_fmt_match() reads. */
+struct PixDesc {
+    const char *name;       /* libavutil name */
+    uint8_t klass;          /* enum b200j2k_pix_fmt: the memory layout the pack kernels write */
+    uint8_t ncomp, depth, lw, lh, pal;
+};
+#define P8 B200J2K_PIX_PLANAR8
+#define P16 B200J2K_PIX_PLANAR16
+const PixDesc RGB_FMTS[] = {
+    { "pal8", B200J2K_PIX_NONE, 1, 8, 0, 0, 1 },    /* palettised output is not served: AVERROR_PATCHWELCOME */
+    { "rgb24", B200J2K_PIX_RGB24, 3, 8, 0, 0, 0 }, { "rgba", B200J2K_PIX_RGBA, 4, 8, 0, 0, 0 },
+    { "rgb48le", B200J2K_PIX_RGB48, 3, 16, 0, 0, 0 }, { "rgba64le", B200J2K_PIX_RGBA64, 4, 16, 0, 0, 0 },
+};
+const PixDesc GRAY_FMTS[] = {
+    { "gray", B200J2K_PIX_GRAY8, 1, 8, 0, 0, 0 }, { "ya8", B200J2K_PIX_YA8, 2, 8, 0, 0, 0 },
+    { "gray16le", B200J2K_PIX_GRAY16, 1, 16, 0, 0, 0 }, { "ya16le", B200J2K_PIX_YA16, 2, 16, 0, 0, 0 },
+};
+const PixDesc YUV_FMTS[] = {
+    { "yuv410p", P8, 3, 8, 2, 2, 0 }, { "yuv411p", P8, 3, 8, 2, 0, 0 }, { "yuva420p", P8, 4, 8, 1, 1, 0 },
+    { "yuv420p", P8, 3, 8, 1, 1, 0 }, { "yuv422p", P8, 3, 8, 1, 0, 0 }, { "yuva422p", P8, 4, 8, 1, 0, 0 },
+    { "yuv440p", P8, 3, 8, 0, 1, 0 }, { "yuv444p", P8, 3, 8, 0, 0, 0 }, { "yuva444p", P8, 4, 8, 0, 0, 0 },
+    { "yuv420p9le", P16, 3, 9, 1, 1, 0 }, { "yuv422p9le", P16, 3, 9, 1, 0, 0 }, { "yuv444p9le", P16, 3, 9, 0, 0, 0 },
+    { "yuva420p9le", P16, 4, 9, 1, 1, 0 }, { "yuva422p9le", P16, 4, 9, 1, 0, 0 }, { "yuva444p9le", P16, 4, 9, 0, 0, 0 },
+    { "yuv420p10le", P16, 3, 10, 1, 1, 0 }, { "yuv422p10le", P16, 3, 10, 1, 0, 0 }, { "yuv444p10le", P16, 3, 10, 0, 0, 0 },
+    { "yuva420p10le", P16, 4, 10, 1, 1, 0 }, { "yuva422p10le", P16, 4, 10, 1, 0, 0 }, { "yuva444p10le", P16, 4, 10, 0, 0, 0 },
+    { "yuv420p12le", P16, 3, 12, 1, 1, 0 }, { "yuv422p12le", P16, 3, 12, 1, 0, 0 }, { "yuv444p12le", P16, 3, 12, 0, 0, 0 },
+    { "yuv420p14le", P16, 3, 14, 1, 1, 0 }, { "yuv422p14le", P16, 3, 14, 1, 0, 0 }, { "yuv444p14le", P16, 3, 14, 0, 0, 0 },
+    { "yuv420p16le", P16, 3, 16, 1, 1, 0 }, { "yuv422p16le", P16, 3, 16, 1, 0, 0 }, { "yuv444p16le", P16, 3, 16, 0, 0, 0 },
+    { "yuva420p16le", P16, 4, 16, 1, 1, 0 }, { "yuva422p16le", P16, 4, 16, 1, 0, 0 }, { "yuva444p16le", P16, 4, 16, 0, 0, 0 },
+};
+const PixDesc XYZ_FMTS[] = { { "xyz12le", B200J2K_PIX_RGB48, 3, 12, 0, 0, 0 } };
+#undef P8
+#undef P16
+
+int ilog2c(int v) { return v >= 4 ? 2 : v >= 2 ? 1 : 0; }     /* cdx, cdy are 1, 2 or 4 */
+
+/* pix_fmt_match (jpeg2000dec.c:134-166) */
+bool pix_match(const PixDesc &d, const Header &h)
 {
-    bool sub = false;
-    for (int i = 0; i < h.ncomp; i++)
-        sub |= h.cdx[i] != 1 || h.cdy[i] != 1;
-    bool wide = h.precision > 8;
+    if (d.ncomp != h.ncomp || d.depth < h.precision)
+        return false;
+    bool ok = true;
+    switch (h.ncomp) {
+    case 4:
+        ok = ok && h.cdx[3] == 1 && h.cdy[3] == 1;
+        /* fall through */
+    case 3:
+        ok = ok && ilog2c(h.cdx[2]) == d.lw && ilog2c(h.cdy[2]) == d.lh;
+        /* fall through */
+    case 2:
+        ok = ok && ilog2c(h.cdx[1]) == d.lw && ilog2c(h.cdy[1]) == d.lh;
+        /* fall through */
+    case 1:
+        ok = ok && h.cdx[0] == 1 && h.cdy[0] == 1 && d.pal == (h.pal8 ? 1 : 0);
+    }
+    return ok;
+}
+
+template <size_t N> const PixDesc *first_match(const PixDesc (&list)[N], const Header &h)
+{
+    for (const PixDesc &d : list)
+        if (pix_match(d, h))
+            return &d;
+    return nullptr;
+}
+
+/* -> layout class (0 = no format: AVERROR_PATCHWELCOME); *name = the libavutil pixel format name */
+int choose_pix(Header &h, const char **name)
+{
+    const PixDesc *d = nullptr;
+    static const PixDesc YUVA420P_FALLBACK = { "yuva420p", B200J2K_PIX_PLANAR8, 4, 8, 1, 1, 0 };
     if (h.precision > 16)
         return B200J2K_PIX_NONE;
-    if (!sub) {
-        switch (h.ncomp) {
-        case 1: return wide ? B200J2K_PIX_GRAY16 : B200J2K_PIX_GRAY8;
-        case 2: return wide ? B200J2K_PIX_YA16 : B200J2K_PIX_YA8;
-        case 3: return wide ? B200J2K_PIX_RGB48 : B200J2K_PIX_RGB24;
-        case 4: return wide ? B200J2K_PIX_RGBA64 : B200J2K_PIX_RGBA;
+    switch (h.colour_space) {
+    case 16: d = first_match(RGB_FMTS, h); break;
+    case 17: d = first_match(GRAY_FMTS, h); break;
+    case 18: d = first_match(YUV_FMTS, h); break;
+    default:
+        d = first_match(RGB_FMTS, h);
+        if (!d) d = first_match(GRAY_FMTS, h);
+        if (!d) d = first_match(YUV_FMTS, h);
+        if (!d) d = first_match(XYZ_FMTS, h);
+        break;
+    }
+    if (!d) {
+        /* the reference's last resort (jpeg2000dec.c:364-398) */
+        const bool same01 = h.ncomp >= 2 && h.cdx[0] == h.cdx[1] && h.cdy[0] == h.cdy[1];
+        if (h.ncomp == 4 && h.cdx[0] == 1 && h.cdy[0] == 1 && h.cdx[1] == 1 && h.cdy[1] == 1 &&
+            h.cdx[2] == h.cdx[3] && h.cdy[2] == h.cdy[3]) {
+            if (h.precision == 8 && h.cdx[2] == 2 && h.cdy[2] == 2 && !h.pal8) {
+                d = &YUVA420P_FALLBACK;
+                for (int i = 0; i < 4; i++)
+                    h.cdef[i] = i;
+            }
+        } else if (h.ncomp == 3 && h.precision == 8 && same01 && h.cdx[0] == h.cdx[2] && h.cdy[0] == h.cdy[2]) {
+            d = &RGB_FMTS[1];
+        } else if (h.ncomp == 2 && h.precision == 8 && same01) {
+            d = &GRAY_FMTS[1];
+        } else if (h.ncomp == 2 && h.precision == 16 && same01) {
+            d = &GRAY_FMTS[3];
+        } else if (h.ncomp == 1 && h.precision == 8) {
+            d = &GRAY_FMTS[0];
+        } else if (h.ncomp == 1 && h.precision == 12) {
+            d = &GRAY_FMTS[2];
         }
+    }
+    if (!d || d->klass == B200J2K_PIX_NONE)
         return B200J2K_PIX_NONE;
+    *name = d->name;
+    h.chroma_lw = d->lw;
+    h.chroma_lh = d->lh;
+    return d->klass;
+}
+
+/* ---- JP2 wrapper: jp2_find_codestream (jpeg2000dec.c:2658-2804) --------------------------------------
+ * Walks the boxes up to the contiguous codestream box; from the JP2 header box it takes the enumerated
+ * colour space ('colr' method 1), the presence of a valid palette ('pclr'; the reference never delivers
+ * PAL8 for a one-component stream, the flag only steers the format choice) and the channel definitions
+ * ('cdef': component -> plane for planar output).  'res ' (sample aspect ratio) is not published.
+ * Returns 1 with *pos at the codestream, 0 when there is none, < 0 on a malformed box. */
+struct Cursor {
+    const uint8_t *b;
+    int64_t pos, size;
+    int64_t left() const { return size - pos; }
+    uint32_t be32()                               /* the reference reads unchecked into the zero padding */
+    {
+        uint32_t v = 0;
+        for (int i = 0; i < 4; i++, pos++)
+            v = v << 8 | (pos < size ? b[pos] : 0);
+        return v;
     }
-    if (h.ncomp == 3 && h.cdx[0] == 1 && h.cdy[0] == 1 && h.cdx[1] == h.cdx[2] && h.cdy[1] == h.cdy[2]) {
-        int cx = h.cdx[1], cy = h.cdy[1];
-        bool ok = (cx == 2 && cy == 2) || (cx == 2 && cy == 1) || (cx == 1 && cy == 2);
-        if (!wide)
-            ok |= (cx == 4 && cy == 1) || (cx == 4 && cy == 4);
-        if (ok)
-            return wide ? B200J2K_PIX_PLANAR16 : B200J2K_PIX_PLANAR8;
+    uint32_t be16() { uint32_t v = 0; for (int i = 0; i < 2; i++, pos++) v = v << 8 | (pos < size ? b[pos] : 0); return v; }
+    uint32_t u8() { uint32_t v = pos < size ? b[pos] : 0; pos++; return v; }
+    void seek(int64_t p) { pos = p < 0 ? 0 : p > size ? size : p; }
+};
+
+int jp2_find_codestream(Cursor &g, Header &h)
+{
+    int search_range = 10;
+    while (search_range && g.left() >= 8) {
+        uint32_t atom_size = g.be32();
+        const uint32_t atom = g.be32();
+        uint32_t atom_end;
+        if (atom_size == 1) {
+            if (g.be32())
+                return 0;                                  /* "Huge atom" */
+            atom_size = g.be32();
+            if (atom_size < 16 || g.pos + atom_size - 16 > INT32_MAX)
+                return B200J2K_ERR_INVALIDDATA;
+            atom_end = (uint32_t)(g.pos + atom_size - 16);
+        } else {
+            if (atom_size < 8 || g.pos + atom_size - 8 > INT32_MAX)
+                return B200J2K_ERR_INVALIDDATA;
+            atom_end = (uint32_t)(g.pos + atom_size - 8);
+        }
+        if (atom == 0x6A703263u)                           /* 'jp2c' */
+            return 1;
+        if (g.left() < (int64_t)atom_size || atom_end < atom_size)
+            return 0;
+        if (atom == 0x6A703268u && atom_size >= 16) {      /* 'jp2h' */
+            uint32_t atom2_end;
+            do {
+                if (g.left() < 8)
+                    break;
+                uint32_t atom2_size = g.be32();
+                const uint32_t atom2 = g.be32();
+                atom2_end = (uint32_t)(g.pos + atom2_size - 8);
+                if (atom2_size < 8 || atom2_end > atom_end || atom2_end < atom2_size)
+                    break;
+                atom2_size -= 8;
+                if (atom2 == 0x6A703263u) {
+                    return 1;
+                } else if (atom2 == 0x636F6C72u && atom2_size >= 7) {          /* 'colr' */
+                    const int method = (int)g.u8();
+                    g.pos += 2;
+                    if (method == 1)
+                        h.colour_space = (int)g.be32();
+                } else if (atom2 == 0x70636C72u && atom2_size >= 6) {          /* 'pclr' */
+                    const int count = (int)g.be16(), channels = (int)g.u8();
+                    int depth[3], bytes = 0;
+                    for (int i = 0; i < 3; i++) {
+                        depth[i] = (int)(g.u8() & 0x7F) + 1;
+                        bytes += ((depth[i] + 7) >> 3) * count;
+                    }
+                    if (!(count > 256 || channels != 3 || depth[0] > 16 || depth[1] > 16 || depth[2] > 16 ||
+                          (int64_t)atom2_size < bytes))
+                        h.pal8 = 1;
+                } else if (atom2 == 0x63646566u && atom2_size >= 2) {          /* 'cdef' */
+                    for (int n = (int)g.be16(); n > 0; n--) {
+                        const int cn = (int)g.be16();
+                        g.be16();
+                        const int asoc = (int)g.be16();
+                        if (cn < 4 && asoc < 4)
+                            h.cdef[cn] = asoc;
+                        if (g.pos >= g.size + 6)           /* the checked reads return 0 forever: stop early */
+                            break;
+                    }
+                }
+                g.seek(atom2_end);
+            } while (atom_end - atom2_end >= 8);
+        } else {
+            search_range--;
+        }
+        g.seek(atom_end);
     }
-    return B200J2K_PIX_NONE;
+    return 0;
 }
 
 /* band step size, float path, same operation order as jpeg2000.c:214-272 */
@@ -201,8 +383,16 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
     h = Header();
     parts_.clear();
     *main_header_len = 0;
-    if (size >= 12 && rd32(p) == 12 && rd32(p + 4) == 0x6A502020u)
-        return B200J2K_ERR_PATCHWELCOME;                  /* JP2 wrapper: next row N3 */
+    if (size >= 12 && rd32(p) == 12 && rd32(p + 4) == 0x6A502020u && rd32(p + 8) == 0x0D0A870Au) {
+        /* JP2 / JPH file (jpeg2000dec.c:2842-2854) */
+        Cursor g = { pkt, 12, size };
+        const int r = jp2_find_codestream(g, h);
+        if (r < 0)
+            return r;
+        if (!r)
+            return B200J2K_ERR_INVALIDDATA;               /* "Could not find Jpeg2000 codestream atom." */
+        p = pkt + g.pos;
+    }
     while (end - p >= 3 && rd16(p) != 0xFF4F)
         p++;
     if (end - p < 2 || rd16(p) != 0xFF4F)
@@ -286,7 +476,7 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 h.out_w = imax(h.out_w, ceildiv(ow, h.cdx[i]));
                 h.out_h = imax(h.out_h, ceildiv(oh, h.cdy[i]));
             }
-            h.pix = choose_pix(h);
+            h.pix = choose_pix(h, &h.pix_name);
             if (!h.pix)
                 return B200J2K_ERR_PATCHWELCOME;
             seg += 36 + 3 * nc;
@@ -435,6 +625,16 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
         if (h.cod[c].transform == J2K_DWT53)
             h.lossless = 1;
     }
+    /* channel definitions default to the identity, the last of an even number of components being alpha
+     * (jpeg2000dec.c:2883-2892) */
+    for (int x = 0; x < h.ncomp; x++)
+        if (h.cdef[x] < 0) {
+            for (x = 0; x < h.ncomp; x++)
+                h.cdef[x] = x + 1;
+            if ((h.ncomp & 1) == 0)
+                h.cdef[h.ncomp - 1] = 0;
+            break;
+        }
     /* output planes */
     const int bps = h.precision > 8 ? 2 : 1;
     const bool planar = h.pix == B200J2K_PIX_PLANAR8 || h.pix == B200J2K_PIX_PLANAR16;
@@ -447,10 +647,12 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
         plane_off[0] = 0;
         picture_bytes = (uint64_t)plane_row_bytes[0] * h.out_h;
     } else {
+        /* planes of the chosen AVPixelFormat: chroma planes 1 and 2 shrink by its log2_chroma_w/h */
         nplanes = h.ncomp;
         for (int c = 0; c < h.ncomp; c++) {
-            plane_w[c] = c ? ceildiv(h.out_w, h.cdx[c]) : h.out_w;
-            plane_h[c] = c ? ceildiv(h.out_h, h.cdy[c]) : h.out_h;
+            const bool chroma = c == 1 || c == 2;
+            plane_w[c] = chroma ? (h.out_w + (1 << h.chroma_lw) - 1) >> h.chroma_lw : h.out_w;
+            plane_h[c] = chroma ? (h.out_h + (1 << h.chroma_lh) - 1) >> h.chroma_lh : h.out_h;
             plane_row_bytes[c] = plane_w[c] * bps;
             plane_off[c] = picture_bytes;
             picture_bytes += (uint64_t)plane_row_bytes[c] * plane_h[c];
@@ -674,12 +876,36 @@ int Parser::build_geometry(int flags)
             g.mct = ok;
             groups.push_back(g);
         } else {
-            for (int c = 0; c < h.ncomp; c++) {
+            /* planar: component c goes to plane cdef[c] - 1, an unassociated one to the last plane
+             * (write_frame, jpeg2000dec.c:2325-2326).  The component transform does not care about the
+             * output format (mct_decode, :2183-2209): a 4:4:4 stream with the MCT bit set keeps comps 0-2 in
+             * one group so that RCT / ICT runs before the samples part ways. */
+            bool mct_ok = h.cod[0].mct != 0 && h.ncomp >= 3;
+            for (int i = 1; i < 3 && mct_ok; i++)
+                mct_ok = h.cod[0].transform == h.cod[i].transform && !memcmp(&t.comp[0], &t.comp[i], sizeof(Rect));
+            int c = 0;
+            if (mct_ok) {
+                PackGroup g;
+                memset(&g, 0, sizeof(g));
+                g.ncomp = 3;
+                g.mct = 1;
+                g.pixel_stride = 1;
+                g.wide = wide;
+                for (; c < 3; c++) {
+                    g.tc[c] = first_tc + c;
+                    g.comp_plane[c] = h.cdef[c] ? h.cdef[c] - 1 : h.ncomp - 1;
+                    g.shift[c] = out_precision - h.cbps[c];
+                    tcs[first_tc + c].group = (int)groups.size();
+                }
+                g.plane = g.comp_plane[0];
+                groups.push_back(g);
+            }
+            for (; c < h.ncomp; c++) {
                 PackGroup g;
                 memset(&g, 0, sizeof(g));
                 g.ncomp = 1;
                 g.tc[0] = first_tc + c;
-                g.plane = c;
+                g.plane = g.comp_plane[0] = h.cdef[c] ? h.cdef[c] - 1 : h.ncomp - 1;
                 g.pixel_stride = 1;
                 g.shift[0] = out_precision - h.cbps[c];
                 g.wide = wide;

@@ -83,6 +83,11 @@ struct Header {
     int ntx = 0, nty = 0;
     int pix = 0, out_w = 0, out_h = 0;
     int lossless = 0;
+    /* JP2 wrapper (jp2_find_codestream, jpeg2000dec.c:2658-2804) and the pixel format it steers */
+    int colour_space = 0, pal8 = 0;
+    int cdef[J2K_MAX_COMP] = { -1, -1, -1, -1 };
+    const char *pix_name = "none";      /* libavutil name of the chosen AVPixelFormat */
+    int chroma_lw = 0, chroma_lh = 0;   /* its log2_chroma_w / log2_chroma_h */
 };
 
 struct TilePart { const uint8_t *p, *end, *start; };

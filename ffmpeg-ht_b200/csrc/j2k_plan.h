@@ -79,6 +79,7 @@ typedef struct PackGroup {
     int32_t sample_off[J2K_MAX_COMP]; /* sample offset of each component inside a pixel */
     int32_t shift[J2K_MAX_COMP];      /* precision - cbps */
     int32_t wide;           /* 16-bit samples */
+    int32_t comp_plane[J2K_MAX_COMP]; /* output plane of each component (planar formats; packed: all = plane) */
 } PackGroup;
 
 #endif

@@ -16,7 +16,7 @@
  *   never AVERROR(EAGAIN); one decoder context per AVCodecContext, so frame threading (one context per
  *   worker, libavcodec/pthread_frame.c:248-295) maps to one CUDA stream + staging buffers per worker.
  * Added: .close (device buffers must be released) and FF_CODEC_CAP_INIT_CLEANUP.
- * What it refuses (AVERROR_PATCHWELCOME, as the library reports): Part-1 MQ code-blocks, JP2 wrapper, POC,
+ * What it refuses (AVERROR_PATCHWELCOME, as the library reports): Part-1 MQ code-blocks, POC,
  * PPM/PPT -- a build that wants those keeps the native decoder registered as fallback
  * under a different name.
  */
@@ -91,15 +91,8 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
     /* the generic layer shifts the dimensions back down by lowres (jpeg2000dec.c:326, utils.c:94-107) */
     if ((ret = ff_set_dimensions(avctx, info.width << avctx->lowres, info.height << avctx->lowres)) < 0)
         return ret;
-    if (info.pix_fmt == B200J2K_PIX_PLANAR8 || info.pix_fmt == B200J2K_PIX_PLANAR16) {
-        /* planar YUV: the caller's pix_fmt, if it matches, else the first match of the native list
-         * (jpeg2000dec.c:354-363) -- geometry is what decides the plane layout */
-        fmt = avctx->pix_fmt != AV_PIX_FMT_NONE ? avctx->pix_fmt : AV_PIX_FMT_NONE;
-        if (fmt == AV_PIX_FMT_NONE)
-            return AVERROR_PATCHWELCOME;
-    } else {
-        fmt = av_get_pix_fmt(b200j2k_pix_fmt_name(info.pix_fmt));
-    }
+    /* the library names the format get_siz() would pick (jpeg2000dec.c:328-412) */
+    fmt = av_get_pix_fmt(info.av_pix_fmt_name);
     if (fmt == AV_PIX_FMT_NONE)
         return AVERROR_PATCHWELCOME;
     avctx->pix_fmt             = fmt;

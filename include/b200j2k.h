@@ -41,8 +41,9 @@ extern "C" {
 #define B200J2K_FLAG_LOWRES(n) (((n) & 15) << 8)
 #define B200J2K_FLAG_GET_LOWRES(flags) (((flags) >> 8) & 15)
 
-/* Output pixel formats.  b200j2k_pix_fmt_name() gives the libavutil name ("rgb48le", ...); the FFCodec
- * shim maps it to AVPixelFormat with av_get_pix_fmt().  Selection follows jpeg2000dec.c:134-193,:335-363. */
+/* Output memory layouts.  b200j2k_frame_info.av_pix_fmt_name gives the exact libavutil format name; the FFCodec
+ * shim maps it to AVPixelFormat with av_get_pix_fmt().  Selection follows jpeg2000dec.c:134-193,:328-412,
+ * including the JP2 colour specification (sRGB / greyscale / sYCC lists) and channel definitions. */
 enum b200j2k_pix_fmt {
     B200J2K_PIX_NONE = 0,
     B200J2K_PIX_GRAY8, B200J2K_PIX_GRAY16, B200J2K_PIX_YA8, B200J2K_PIX_YA16,
@@ -66,6 +67,9 @@ typedef struct b200j2k_frame_info {
     int32_t ntiles;
     int32_t ncodeblocks;            /* code-blocks handed to the device */
     int64_t bytes_consumed;         /* decode() return value of the reference: bytestream2_tell() */
+    char    av_pix_fmt_name[16];    /* libavutil name of the AVPixelFormat the reference would choose for this
+                                     * stream ("rgb48le", "yuv422p10le", ...; jpeg2000dec.c:328-412): pix_fmt
+                                     * above is only its memory-layout class */
 } b200j2k_frame_info;
 
 typedef struct b200j2k_decoder b200j2k_decoder;

@@ -27,7 +27,7 @@ enum { ORACLE_DWT97 = 0, ORACLE_DWT53 = 1, ORACLE_DWT97_INT = 2 };
 enum {
     ORACLE_PIX_GRAY8 = 1, ORACLE_PIX_GRAY16, ORACLE_PIX_YA8, ORACLE_PIX_YA16,
     ORACLE_PIX_RGB24, ORACLE_PIX_RGB48, ORACLE_PIX_RGBA, ORACLE_PIX_RGBA64,
-    ORACLE_PIX_PLANAR8, ORACLE_PIX_PLANAR16   /* planar YUV(A), any subsampling */
+    ORACLE_PIX_PLANAR8, ORACLE_PIX_PLANAR16   /* planar YUV(A), any subsampling: see oracle_last_pix_fmt_name() */
 };
 
 /* H1-H8: one HT code-block.  data = Dcup||Dref.  out[h*w] = sign-magnitude int32 as left in
@@ -47,6 +47,8 @@ int oracle_mct(int type, void *p0, void *p1, void *p2, int n);
  * info[4]=number of code-blocks decoded info[5]=ncomponents info[6]=precision.
  * Returns 0 or a negative error. */
 int oracle_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint8_t *out, int64_t cap);
+/* libavutil name of the AVPixelFormat the last oracle_decode() of this thread chose ("rgb48le", "yuv420p10le") */
+const char *oracle_last_pix_fmt_name(void);
 
 /* CPU baseline ("port"): decode every codestream `reps` times on `threads` threads; seconds or <0 */
 double oracle_decode_bench(const uint8_t *const *cs, const int64_t *len, int nframes, int threads,

@@ -99,6 +99,8 @@ typedef struct Dec {
     int ntx, nty;
     Tile *tile;
     int pix, out_w, out_h;
+    int colour_space, pal8, cdef[4];                /* JP2 wrapper state (jp2_find_codestream) */
+    int chroma_lw, chroma_lh;                       /* log2_chroma_w/h of the chosen AVPixelFormat */
     /* packet header bit reader */
     const uint8_t *bp, *bend;
     int bit_index;
@@ -261,37 +263,220 @@ static int parse_qcx(const uint8_t *p, int n, QntSty *q)
 }
 
 /* pixel format choice for a raw codestream (jpeg2000dec.c:134-193, :335-363) */
+/* ---- pixel format selection (get_siz, jpeg2000dec.c:134-193, :328-412) -----------------------------------
+ * The fields of libavutil's AVPixFmtDescriptor that pix_fmt_match() reads, for the formats of the reference's
+ * rgb / gray / yuv / xyz lists, in list order. */
+typedef struct PixDesc {
+    const char *name;
+    int klass, ncomp, depth, lw, lh, pal;
+} PixDesc;
+#define P8 ORACLE_PIX_PLANAR8
+#define P16 ORACLE_PIX_PLANAR16
+static const PixDesc RGB_FMTS[] = {
+    { "pal8", 0, 1, 8, 0, 0, 1 },                   /* palettised output: outside the path (PATCHWELCOME) */
+    { "rgb24", ORACLE_PIX_RGB24, 3, 8, 0, 0, 0 }, { "rgba", ORACLE_PIX_RGBA, 4, 8, 0, 0, 0 },
+    { "rgb48le", ORACLE_PIX_RGB48, 3, 16, 0, 0, 0 }, { "rgba64le", ORACLE_PIX_RGBA64, 4, 16, 0, 0, 0 },
+};
+static const PixDesc GRAY_FMTS[] = {
+    { "gray", ORACLE_PIX_GRAY8, 1, 8, 0, 0, 0 }, { "ya8", ORACLE_PIX_YA8, 2, 8, 0, 0, 0 },
+    { "gray16le", ORACLE_PIX_GRAY16, 1, 16, 0, 0, 0 }, { "ya16le", ORACLE_PIX_YA16, 2, 16, 0, 0, 0 },
+};
+static const PixDesc YUV_FMTS[] = {
+    { "yuv410p", P8, 3, 8, 2, 2, 0 }, { "yuv411p", P8, 3, 8, 2, 0, 0 }, { "yuva420p", P8, 4, 8, 1, 1, 0 },
+    { "yuv420p", P8, 3, 8, 1, 1, 0 }, { "yuv422p", P8, 3, 8, 1, 0, 0 }, { "yuva422p", P8, 4, 8, 1, 0, 0 },
+    { "yuv440p", P8, 3, 8, 0, 1, 0 }, { "yuv444p", P8, 3, 8, 0, 0, 0 }, { "yuva444p", P8, 4, 8, 0, 0, 0 },
+    { "yuv420p9le", P16, 3, 9, 1, 1, 0 }, { "yuv422p9le", P16, 3, 9, 1, 0, 0 }, { "yuv444p9le", P16, 3, 9, 0, 0, 0 },
+    { "yuva420p9le", P16, 4, 9, 1, 1, 0 }, { "yuva422p9le", P16, 4, 9, 1, 0, 0 }, { "yuva444p9le", P16, 4, 9, 0, 0, 0 },
+    { "yuv420p10le", P16, 3, 10, 1, 1, 0 }, { "yuv422p10le", P16, 3, 10, 1, 0, 0 }, { "yuv444p10le", P16, 3, 10, 0, 0, 0 },
+    { "yuva420p10le", P16, 4, 10, 1, 1, 0 }, { "yuva422p10le", P16, 4, 10, 1, 0, 0 }, { "yuva444p10le", P16, 4, 10, 0, 0, 0 },
+    { "yuv420p12le", P16, 3, 12, 1, 1, 0 }, { "yuv422p12le", P16, 3, 12, 1, 0, 0 }, { "yuv444p12le", P16, 3, 12, 0, 0, 0 },
+    { "yuv420p14le", P16, 3, 14, 1, 1, 0 }, { "yuv422p14le", P16, 3, 14, 1, 0, 0 }, { "yuv444p14le", P16, 3, 14, 0, 0, 0 },
+    { "yuv420p16le", P16, 3, 16, 1, 1, 0 }, { "yuv422p16le", P16, 3, 16, 1, 0, 0 }, { "yuv444p16le", P16, 3, 16, 0, 0, 0 },
+    { "yuva420p16le", P16, 4, 16, 1, 1, 0 }, { "yuva422p16le", P16, 4, 16, 1, 0, 0 }, { "yuva444p16le", P16, 4, 16, 0, 0, 0 },
+};
+static const PixDesc XYZ_FMTS[] = { { "xyz12le", ORACLE_PIX_RGB48, 3, 12, 0, 0, 0 } };
+#undef P8
+#undef P16
+#define NELEM(a) ((int)(sizeof(a) / sizeof((a)[0])))
+
+static int log2c(int v) { return v >= 4 ? 2 : v >= 2 ? 1 : 0; }
+
+/* pix_fmt_match (:134-166) */
+static int pix_match(const PixDesc *f, const Dec *d)
+{
+    if (f->ncomp != d->ncomp || f->depth < d->precision)
+        return 0;
+    int ok = 1;
+    switch (d->ncomp) {
+    case 4: ok = ok && d->cdx[3] == 1 && d->cdy[3] == 1;                                /* fall through */
+    case 3: ok = ok && log2c(d->cdx[2]) == f->lw && log2c(d->cdy[2]) == f->lh;         /* fall through */
+    case 2: ok = ok && log2c(d->cdx[1]) == f->lw && log2c(d->cdy[1]) == f->lh;         /* fall through */
+    case 1: ok = ok && d->cdx[0] == 1 && d->cdy[0] == 1 && f->pal == (d->pal8 ? 1 : 0);
+    }
+    return ok;
+}
+
+static const PixDesc *first_match(const PixDesc *list, int n, const Dec *d)
+{
+    for (int i = 0; i < n; i++)
+        if (pix_match(&list[i], d))
+            return &list[i];
+    return NULL;
+}
+
+static _Thread_local const char *g_pix_name = "none";
+const char *oracle_last_pix_fmt_name(void) { return g_pix_name; }
+
 static int choose_pix(Dec *d)
 {
-    int sub = 0;
-    for (int i = 0; i < d->ncomp; i++)
-        sub |= d->cdx[i] != 1 || d->cdy[i] != 1;
-    int wide = d->precision > 8;
+    static const PixDesc YUVA420P_FALLBACK = { "yuva420p", ORACLE_PIX_PLANAR8, 4, 8, 1, 1, 0 };
+    const PixDesc *f = NULL;
     if (d->precision > 16)
         return 0;
-    if (!sub) {
-        switch (d->ncomp) {
-        case 1: return wide ? ORACLE_PIX_GRAY16 : ORACLE_PIX_GRAY8;
-        case 2: return wide ? ORACLE_PIX_YA16 : ORACLE_PIX_YA8;
-        case 3: return wide ? ORACLE_PIX_RGB48 : ORACLE_PIX_RGB24;
-        case 4: return wide ? ORACLE_PIX_RGBA64 : ORACLE_PIX_RGBA;
+    switch (d->colour_space) {                      /* :335-352 */
+    case 16: f = first_match(RGB_FMTS, NELEM(RGB_FMTS), d); break;
+    case 17: f = first_match(GRAY_FMTS, NELEM(GRAY_FMTS), d); break;
+    case 18: f = first_match(YUV_FMTS, NELEM(YUV_FMTS), d); break;
+    default:
+        f = first_match(RGB_FMTS, NELEM(RGB_FMTS), d);
+        if (!f) f = first_match(GRAY_FMTS, NELEM(GRAY_FMTS), d);
+        if (!f) f = first_match(YUV_FMTS, NELEM(YUV_FMTS), d);
+        if (!f) f = first_match(XYZ_FMTS, NELEM(XYZ_FMTS), d);
+    }
+    if (!f) {                                       /* the last resort, :364-398 */
+        const int same01 = d->ncomp >= 2 && d->cdx[0] == d->cdx[1] && d->cdy[0] == d->cdy[1];
+        if (d->ncomp == 4 && d->cdx[0] == 1 && d->cdy[0] == 1 && d->cdx[1] == 1 && d->cdy[1] == 1 &&
+            d->cdx[2] == d->cdx[3] && d->cdy[2] == d->cdy[3]) {
+            if (d->precision == 8 && d->cdx[2] == 2 && d->cdy[2] == 2 && !d->pal8) {
+                f = &YUVA420P_FALLBACK;
+                for (int i = 0; i < 4; i++)
+                    d->cdef[i] = i;
+            }
+        } else if (d->ncomp == 3 && d->precision == 8 && same01 && d->cdx[0] == d->cdx[2] && d->cdy[0] == d->cdy[2]) {
+            f = &RGB_FMTS[1];
+        } else if (d->ncomp == 2 && d->precision == 8 && same01) {
+            f = &GRAY_FMTS[1];
+        } else if (d->ncomp == 2 && d->precision == 16 && same01) {
+            f = &GRAY_FMTS[3];
+        } else if (d->ncomp == 1 && d->precision == 8) {
+            f = &GRAY_FMTS[0];
+        } else if (d->ncomp == 1 && d->precision == 12) {
+            f = &GRAY_FMTS[2];
         }
+    }
+    if (!f || !f->klass)
         return 0;
+    g_pix_name = f->name;
+    d->chroma_lw = f->lw;
+    d->chroma_lh = f->lh;
+    return f->klass;
+}
+
+/* ---- JP2 wrapper: jp2_find_codestream (:2658-2804).  Returns 1 with *ppos at the codestream box payload,
+ * 0 when no codestream box was found, < 0 for a malformed box.  'res ' is read by the reference for the
+ * sample aspect ratio only and is skipped here. */
+static uint32_t jp2_be(const Dec *d, int64_t *pos, int n)
+{
+    uint32_t v = 0;
+    const int64_t size = d->end - d->cs;
+    for (int i = 0; i < n; i++, (*pos)++)
+        v = v << 8 | (*pos < size ? d->cs[*pos] : 0);   /* unchecked reads land in the zero padding */
+    return v;
+}
+
+static int jp2_find_codestream(Dec *d, int64_t *ppos)
+{
+    const int64_t size = d->end - d->cs;
+    int64_t pos = *ppos;
+    int search_range = 10;
+#define SEEK(p) (pos = (p) < 0 ? 0 : (p) > size ? size : (p))
+    while (search_range && size - pos >= 8) {
+        uint32_t atom_size = jp2_be(d, &pos, 4);
+        const uint32_t atom = jp2_be(d, &pos, 4);
+        uint32_t atom_end;
+        if (atom_size == 1) {
+            if (jp2_be(d, &pos, 4))
+                return 0;
+            atom_size = jp2_be(d, &pos, 4);
+            if (atom_size < 16 || pos + atom_size - 16 > INT32_MAX)
+                return ORACLE_ERR_INVALID;
+            atom_end = (uint32_t)(pos + atom_size - 16);
+        } else {
+            if (atom_size < 8 || pos + atom_size - 8 > INT32_MAX)
+                return ORACLE_ERR_INVALID;
+            atom_end = (uint32_t)(pos + atom_size - 8);
+        }
+        if (atom == 0x6A703263u) {                  /* jp2c */
+            *ppos = pos;
+            return 1;
+        }
+        if (size - pos < (int64_t)atom_size || atom_end < atom_size)
+            return 0;
+        if (atom == 0x6A703268u && atom_size >= 16) {   /* jp2h */
+            uint32_t atom2_end;
+            do {
+                if (size - pos < 8)
+                    break;
+                uint32_t atom2_size = jp2_be(d, &pos, 4);
+                const uint32_t atom2 = jp2_be(d, &pos, 4);
+                atom2_end = (uint32_t)(pos + atom2_size - 8);
+                if (atom2_size < 8 || atom2_end > atom_end || atom2_end < atom2_size)
+                    break;
+                atom2_size -= 8;
+                if (atom2 == 0x6A703263u) {
+                    *ppos = pos;
+                    return 1;
+                } else if (atom2 == 0x636F6C72u && atom2_size >= 7) {          /* colr */
+                    const int method = (int)jp2_be(d, &pos, 1);
+                    pos += 2;
+                    if (method == 1)
+                        d->colour_space = (int)jp2_be(d, &pos, 4);
+                } else if (atom2 == 0x70636C72u && atom2_size >= 6) {          /* pclr */
+                    const int count = (int)jp2_be(d, &pos, 2), channels = (int)jp2_be(d, &pos, 1);
+                    int depth[3], bytes = 0;
+                    for (int i = 0; i < 3; i++) {
+                        depth[i] = (int)(jp2_be(d, &pos, 1) & 0x7F) + 1;
+                        bytes += ((depth[i] + 7) >> 3) * count;
+                    }
+                    if (!(count > 256 || channels != 3 || depth[0] > 16 || depth[1] > 16 || depth[2] > 16 ||
+                          (int64_t)atom2_size < bytes))
+                        d->pal8 = 1;
+                } else if (atom2 == 0x63646566u && atom2_size >= 2) {          /* cdef */
+                    for (int n = (int)jp2_be(d, &pos, 2); n > 0; n--) {
+                        const int cn = (int)jp2_be(d, &pos, 2);
+                        jp2_be(d, &pos, 2);
+                        const int asoc = (int)jp2_be(d, &pos, 2);
+                        if (cn < 4 && asoc < 4)
+                            d->cdef[cn] = asoc;
+                        if (pos >= size + 6)
+                            break;
+                    }
+                }
+                SEEK(atom2_end);
+            } while (atom_end - atom2_end >= 8);
+        } else {
+            search_range--;
+        }
+        SEEK(atom_end);
     }
-    if (d->ncomp == 3 && d->cdx[0] == 1 && d->cdy[0] == 1 && d->cdx[1] == d->cdx[2] && d->cdy[1] == d->cdy[2]) {
-        int cx = d->cdx[1], cy = d->cdy[1];
-        int ok = (cx == 2 && cy == 2) || (cx == 2 && cy == 1) || (cx == 1 && cy == 2);
-        if (!wide)
-            ok |= (cx == 4 && cy == 1) || (cx == 4 && cy == 4);
-        if (ok)
-            return wide ? ORACLE_PIX_PLANAR16 : ORACLE_PIX_PLANAR8;
-    }
+#undef SEEK
     return 0;
 }
 
 static int parse_headers(Dec *d)
 {
     const uint8_t *p = d->cs;
+    for (int i = 0; i < 4; i++)
+        d->cdef[i] = -1;                            /* jpeg2000dec.c:2834 */
+    if (d->end - p >= 12 && rd32(p) == 12 && rd32(p + 4) == 0x6A502020u && rd32(p + 8) == 0x0D0A870Au) {
+        int64_t pos = 12;                           /* JP2 / JPH file (:2842-2854) */
+        const int r = jp2_find_codestream(d, &pos);
+        if (r < 0)
+            return r;
+        if (!r)
+            return ORACLE_ERR_INVALID;
+        p = d->cs + pos;
+    }
     while (d->end - p >= 3 && rd16(p) != 0xFF4F)
         p++;
     if (d->end - p < 2 || rd16(p) != 0xFF4F)
@@ -1166,7 +1351,7 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
     for (int c = 0; c < d->ncomp; c++) {
         Comp *comp = &t->comp[c];
         const int cbps = d->cbps[c];
-        const int plane = planar ? c : 0;
+        const int plane = planar ? (d->cdef[c] ? d->cdef[c] - 1 : d->ncomp - 1) : 0;    /* :2325-2326 */
         const int w = comp->cr.x1 - ceildiv(d->X0, d->cdx[c]);
         const int h = comp->cr.y1 - ceildiv(d->Y0, d->cdy[c]);
         const float *fp = comp->data;
@@ -1227,7 +1412,9 @@ int oracle_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, u
             pos = (int64_t)strides[0] * d.out_h;
         } else {
             for (int c = 0; c < d.ncomp; c++) {
-                int pw = c ? ceildiv(d.out_w, d.cdx[c]) : d.out_w, ph = c ? ceildiv(d.out_h, d.cdy[c]) : d.out_h;
+                const int chroma = c == 1 || c == 2;    /* planes of the AVPixelFormat, not of the components */
+                int pw = chroma ? (d.out_w + (1 << d.chroma_lw) - 1) >> d.chroma_lw : d.out_w;
+                int ph = chroma ? (d.out_h + (1 << d.chroma_lh) - 1) >> d.chroma_lh : d.out_h;
                 strides[c] = pw * bps;
                 planes[c] = out + pos;
                 pos += (int64_t)strides[c] * ph;
@@ -1238,6 +1425,14 @@ int oracle_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, u
             goto end;
         }
         memset(out, 0, (size_t)pos);
+        for (int x = 0; x < d.ncomp; x++)           /* default channel definitions (:2883-2892) */
+            if (d.cdef[x] < 0) {
+                for (x = 0; x < d.ncomp; x++)
+                    d.cdef[x] = x + 1;
+                if ((d.ncomp & 1) == 0)
+                    d.cdef[d.ncomp - 1] = 0;
+                break;
+            }
         for (int i = 0; i < d.ntx * d.nty; i++) {
             if ((ret = init_tile(&d, i)) < 0)
                 goto end;

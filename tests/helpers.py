@@ -33,6 +33,7 @@ def oracle():
         lib.oracle_decode.argtypes = _DEC_SIG
         lib.oracle_idwt.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         lib.oracle_mct.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        lib.oracle_last_pix_fmt_name.restype = ctypes.c_char_p
         lib.oracle_decode_bench.restype = ctypes.c_double
         lib.oracle_decode_bench.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_int]
@@ -77,6 +78,11 @@ def decode_with(lib_fn, cs: bytes, bitexact=0, cap=None):
 
 def oracle_decode(cs: bytes, bitexact=0, cap=None):
     return decode_with(oracle().oracle_decode, cs, bitexact, cap)
+
+
+def oracle_pix_name() -> str:
+    """libavutil name of the AVPixelFormat the last oracle_decode() chose"""
+    return oracle().oracle_last_pix_fmt_name().decode()
 
 
 def ref_decode(cs: bytes, bitexact=0, cap=None):

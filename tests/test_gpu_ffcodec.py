@@ -47,6 +47,31 @@ def test_ffcodec_shim_equals_reference(kw):
             assert np.array_equal(o1, o2)
 
 
+def test_ffcodec_shim_jp2_and_subsampled():
+    """JP2 / JPH files and chroma-subsampled streams through the FFCodec shim: same AVPixelFormat (planar YUV
+    included), same AVFrame bytes as the reference decoder."""
+    from test_oracle_vs_ref import SUBSAMPLED, subsampled_stream
+    cases = []
+    for name, subs, bd in SUBSAMPLED[:6]:
+        cs, planes, p = subsampled_stream(subs, bd, 131, 77, dict(levels=3, tile=(64, 48)))
+        cases += [cs, j2kgen.wrap_jp2(cs, 131, 77, len(subs), bd, colour_space=18, cdef=[(0, 0, 1), (1, 0, 3), (2, 0, 2)])]
+    for nc, bd in [(3, 8), (3, 12), (1, 16), (4, 8)]:
+        planes = j2kgen.synth_image(160, 90, nc, bd, seed=8)
+        cs = j2kgen.encode(planes, bd, j2kgen.EncParams(levels=3, mct=nc >= 3))
+        cases += [j2kgen.wrap_jp2(cs, 160, 90, nc, bd, colour_space=csp) for csp in (16, 17, 18)]
+    n = 0
+    for data in cases:
+        r1, i1, o1, _ = ref_decode(data)
+        r2, i2, o2 = shim_decode(data)
+        if r1 < 0:
+            assert r2 == r1
+            continue
+        assert r2 == 0 and i1[:3] == i2[:3] and i1[4] == i2[4]
+        assert np.array_equal(o1, o2)
+        n += 1
+    assert n >= 20
+
+
 def test_ffcodec_shim_error_codes():
     planes = j2kgen.synth_image(64, 64, 1, 8, seed=2)
     cs = j2kgen.encode(planes, 8, j2kgen.EncParams(levels=2))

@@ -12,7 +12,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import STREAMS
+from test_oracle_vs_ref import STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, subsampled_stream
 
 pytestmark = pytest.mark.gpu
 
@@ -291,6 +291,44 @@ def test_streaming_idwt_geometries(cfg, dec, dec_bitexact):
     if p.reversible:
         img = got.view(np.uint16).reshape(h, w, nc)
         assert np.array_equal(img >> (16 - bd), np.stack(planes, -1))
+
+
+@pytest.mark.parametrize("name,subs,bd", SUBSAMPLED, ids=[s[0] for s in SUBSAMPLED])
+def test_subsampled_and_jp2_frames_vs_oracle(name, subs, bd, dec, dec_bitexact):
+    """Planar YUV(A) output (chroma-subsampled components; sYCC JP2 files with and without a cdef box that
+    swaps planes): plane layout, format name and every sample equal the oracle's."""
+    from helpers import oracle_pix_name
+    for w, h, kw in SUBSAMPLED_GEOMS:
+        cs, planes, p = subsampled_stream(subs, bd, w, h, kw)
+        nc = len(subs)
+        variants = [cs, j2kgen.wrap_jp2(cs, w, h, nc, bd, colour_space=18),
+                    j2kgen.wrap_jp2(cs, w, h, nc, bd, colour_space=18, cdef=[(0, 0, 1), (1, 0, 3), (2, 0, 2), (3, 1, 0)][:nc])]
+        for data in variants:
+            for bitexact in ((0,) if p.reversible else (0, 1)):
+                r, oinfo, want = oracle_decode(data, bitexact)
+                assert r == 0
+                info, got = (dec_bitexact if bitexact else dec).decode(data)
+                assert (info.width, info.height, info.pix_name) == (oinfo[0], oinfo[1], oracle_pix_name())
+                assert np.array_equal(got, want), (name, w, h, bitexact)
+
+
+def test_jp2_colour_spaces_vs_oracle(dec):
+    """4:4:4 streams in a JP2 wrapper: sRGB / grey keep the packed formats, sYCC switches to planar YUV444."""
+    from helpers import oracle_pix_name
+    for nc, bd in [(3, 8), (3, 12), (1, 16), (4, 8), (3, 10), (4, 16)]:
+        planes = j2kgen.synth_image(160, 90, nc, bd, seed=8)
+        cs = j2kgen.encode(planes, bd, j2kgen.EncParams(levels=3, mct=nc >= 3))
+        for csp in (None, 16, 17, 18):
+            data = j2kgen.wrap_jp2(cs, 160, 90, nc, bd, colour_space=csp)
+            r, oinfo, want = oracle_decode(data, 0)
+            if r < 0:
+                with pytest.raises(fb.DecodeError) as e:
+                    dec.decode(data)
+                assert e.value.code == r
+                continue
+            info, got = dec.decode(data)
+            assert (info.width, info.height, info.pix_name) == (oinfo[0], oinfo[1], oracle_pix_name())
+            assert np.array_equal(got, want), (nc, bd, csp)
 
 
 @pytest.mark.parametrize("lowres", [1, 2, 3])

@@ -11,7 +11,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import STREAMS
+from test_oracle_vs_ref import STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, subsampled_stream
 
 
 def picture_from_plan(cs: bytes, flags: int):
@@ -70,8 +70,9 @@ def picture_from_plan(cs: bytes, flags: int):
         if int(g["mct"]):
             oracle().oracle_mct(t, pls[0].ctypes.data, pls[1].ctypes.data, pls[2].ctypes.data, pls[0].size)
         wide = int(g["wide"])
-        view = pic[P["plane_off"][int(g["plane"])]:]
         for c, (tc, pl) in enumerate(zip(tcs, pls)):
+            plane = int(g["comp_plane"][c])
+            view = pic[P["plane_off"][plane]:]
             W, H = int(tc["width"]), int(tc["height"])
             if t == 0:
                 val = np.rint(pl.view(np.float32)).astype(np.int64)
@@ -80,7 +81,7 @@ def picture_from_plan(cs: bytes, flags: int):
             cb = int(tc["cbps"])
             val = np.clip(val + (1 << (cb - 1)), 0, (1 << cb) - 1) << int(g["shift"][c])
             val = val.reshape(H, W)
-            rb = rowb[int(g["plane"])]
+            rb = rowb[plane]
             ps, so = int(g["pixel_stride"]), int(g["sample_off"][c])
             for y in range(H):
                 row = view[(int(tc["out_y"]) + y) * rb: (int(tc["out_y"]) + y + 1) * rb]
@@ -214,3 +215,64 @@ def test_bytes_consumed_matches_reference():
         r, info, _, _ = ref_decode(cs, 0)
         assert r == 0
         assert fb.plan(cs, 0)["info"].bytes_consumed == info[4]
+
+
+@pytest.mark.parametrize("name,subs,bd", SUBSAMPLED, ids=[s[0] for s in SUBSAMPLED])
+def test_plan_of_subsampled_and_jp2_streams(name, subs, bd):
+    """Planar output through the plan: component -> plane by the channel definitions, plane sizes of the
+    chosen AVPixelFormat; the same stream wrapped as JP2 with a cdef box that swaps the chroma planes."""
+    for w, h, kw in SUBSAMPLED_GEOMS[:2]:
+        cs, planes, p = subsampled_stream(subs, bd, w, h, kw)
+        nc = len(subs)
+        swapped = j2kgen.wrap_jp2(cs, w, h, nc, bd, colour_space=18,
+                                  cdef=[(0, 0, 1), (1, 0, 3), (2, 0, 2), (3, 1, 0)][:nc])
+        for data in (cs, swapped):
+            r, oinfo, opic = oracle_decode(data, 0)
+            assert r == 0
+            info, pic = picture_from_plan(data, 0)
+            assert (info.width, info.height) == (oinfo[0], oinfo[1])
+            assert np.array_equal(pic, opic)
+    # 4:4:4 with the component transform, delivered planar because the JP2 header says sYCC
+    nc = min(len(subs), 4)
+    full = j2kgen.synth_image(120, 70, nc, bd, seed=2)
+    cs = j2kgen.encode(full, bd, j2kgen.EncParams(levels=3, mct=True))
+    data = j2kgen.wrap_jp2(cs, 120, 70, nc, bd, colour_space=18)
+    r, oinfo, opic = oracle_decode(data, 0)
+    assert r == 0
+    info, pic = picture_from_plan(data, 0)
+    assert info.pix_fmt in (fb.lib() and 9, 10) and np.array_equal(pic, opic)
+
+
+def test_jp2_wrapper_headers_match_reference():
+    """JP2 / JPH files (jp2_find_codestream, jpeg2000dec.c:2658-2804): the codestream is found behind the
+    boxes, the enumerated colour space picks the pixel-format list (sRGB / grey / sYCC), a palette steers
+    the choice, the search gives up after ten foreign boxes -- dimensions, AVPixelFormat name and error code
+    equal the reference's for every combination."""
+    from helpers import have_ref, ref_decode
+    if not have_ref():
+        pytest.skip("oracle/_ref not built")
+    n = 0
+    for nc, bd in [(3, 8), (3, 12), (1, 8), (1, 16), (2, 8), (4, 8), (3, 10), (4, 16), (2, 16), (1, 12)]:
+        planes = j2kgen.synth_image(64, 48, nc, bd, seed=3)
+        cs = j2kgen.encode(planes, bd, j2kgen.EncParams(levels=2, mct=nc >= 3))
+        variants = [cs]
+        for csp in (None, 16, 17, 18, 99):
+            variants.append(j2kgen.wrap_jp2(cs, 64, 48, nc, bd, colour_space=csp))
+        variants.append(j2kgen.wrap_jp2(cs, 64, 48, nc, bd, colour_space=16, palette=(16, 8)))
+        variants.append(j2kgen.wrap_jp2(cs, 64, 48, nc, bd, colour_space=18, cdef=[(0, 0, 2), (1, 0, 1), (2, 0, 3)][:nc]))
+        variants.append(j2kgen.wrap_jp2(cs, 64, 48, nc, bd, extra_before=11))
+        variants.append(j2kgen.wrap_jp2(cs, 64, 48, nc, bd, extra_before=8))
+        variants.append(j2kgen.wrap_jp2(cs, 64, 48, nc, bd)[:40])
+        for data in variants:
+            r, info, out, name = ref_decode(data)
+            try:
+                i = fb.probe(data)
+                mine = (0, i.width, i.height, i.pix_name)
+            except fb.DecodeError as e:
+                mine = (e.code,)
+            if r == 0 and name == "pal8":
+                assert mine == (-1163346256,)         # palettised output: refused, never a wrong picture
+            else:
+                assert mine == ((r, info[0], info[1], name) if r == 0 else (r,)), (nc, bd, len(data))
+            n += 1
+    assert n == 110

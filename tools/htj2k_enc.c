@@ -45,6 +45,8 @@ typedef struct J2kGenParams {
     int32_t stats_blocks;        /* out: number of non-empty code-blocks */
     int32_t stats_max_lcup;      /* out */
     int32_t error;               /* out: 0 ok, 1 exponent bound exceeded (raise guard_bits), 2 segment too long */
+    int32_t sub_x[4], sub_y[4];  /* XRsiz / YRsiz per component (0 = 1).  With subsampling: no offset, no component
+                                  * transform, LRCP / RLCP only; plane c holds ceil(W/sub_x) x ceil(H/sub_y) samples */
 } J2kGenParams;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -926,7 +928,12 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
     buf_put32(&out, X1); buf_put32(&out, Y1); buf_put32(&out, X0); buf_put32(&out, Y0);
     buf_put32(&out, TW); buf_put32(&out, TH); buf_put32(&out, X0); buf_put32(&out, Y0);
     buf_put16(&out, C);
-    for (int c = 0; c < C; c++) { buf_put(&out, P->bitdepth - 1); buf_put(&out, 1); buf_put(&out, 1); }
+    int any_sub = 0;
+    for (int c = 0; c < C && c < 4; c++) any_sub |= P->sub_x[c] > 1 || P->sub_y[c] > 1;
+    if (any_sub && (X0 || Y0 || (P->mct && C >= 3) || P->prog > 1)) { P->error = 3; return -3; }
+#define SUBX(c) ((c) < 4 && P->sub_x[c] > 1 ? P->sub_x[c] : 1)
+#define SUBY(c) ((c) < 4 && P->sub_y[c] > 1 ? P->sub_y[c] : 1)
+    for (int c = 0; c < C; c++) { buf_put(&out, P->bitdepth - 1); buf_put(&out, SUBX(c)); buf_put(&out, SUBY(c)); }
     /* CAP: Pcap bit 15 (Part 15), Ccap15: HTONLY, bit 5 = irreversible */
     {
         int magb_bits = 0;   /* the reference only range-checks MAGB (jpeg2000dec.c:473-486) */
@@ -971,9 +978,24 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
             const int W = tx1 - tx0, H = ty1 - ty0;
             /* component planes of the tile, level shifted and colour transformed */
             void **tp = calloc(C, sizeof(void *));
-            for (int c = 0; c < C; c++) tp[c] = malloc(sizeof(int32_t) * (size_t)W * H + 64);
             const int shift = 1 << (P->bitdepth - 1);
             const int use_mct = P->mct && C >= 3;
+            if (any_sub) {
+                /* every component on its own grid: tile-component = ceil(tile / (XRsiz, YRsiz)) */
+                for (int c = 0; c < C; c++) {
+                    const int dx = SUBX(c), dy = SUBY(c);
+                    const int cx0 = ceildiv(tx0, dx), cx1 = ceildiv(tx1, dx), cy0 = ceildiv(ty0, dy), cy1 = ceildiv(ty1, dy);
+                    const int cw = cx1 - cx0, ch = cy1 - cy0, pw = ceildiv(P->width, dx);
+                    tp[c] = malloc(sizeof(int32_t) * (size_t)imax(cw * ch, 1) + 64);
+                    for (int y = 0; y < ch; y++)
+                        for (int x = 0; x < cw; x++) {
+                            const int32_t v = planes[c][(size_t)(cy0 + y) * pw + (cx0 + x)] - shift;
+                            if (P->reversible) ((int32_t *)tp[c])[(size_t)y * cw + x] = v;
+                            else ((float *)tp[c])[(size_t)y * cw + x] = (float)v;
+                        }
+                }
+            } else {
+            for (int c = 0; c < C; c++) tp[c] = malloc(sizeof(int32_t) * (size_t)W * H + 64);
             for (int y = 0; y < H; y++)
                 for (int x = 0; x < W; x++) {
                     size_t src = (size_t)(ty0 - Y0 + y) * P->width + (tx0 - X0 + x), dst = (size_t)y * W + x;
@@ -997,9 +1019,15 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
                         for (int c = 0; c < C && c < 4; c++) ((float *)tp[c])[dst] = v[c];
                     }
                 }
+            }
             /* per component: DWT, geometry, block coding */
             ResLevel **res = calloc(C, sizeof(ResLevel *));
+            const int tile_x0 = tx0, tile_x1 = tx1, tile_y0 = ty0, tile_y1 = ty1;
             for (int c = 0; c < C; c++) {
+                /* the component's own rectangle shadows the tile's from here to the end of this loop body */
+                const int tx0 = ceildiv(tile_x0, SUBX(c)), tx1 = ceildiv(tile_x1, SUBX(c));
+                const int ty0 = ceildiv(tile_y0, SUBY(c)), ty1 = ceildiv(tile_y1, SUBY(c));
+                const int W = tx1 - tx0;
                 fdwt_plane(tp[c], !P->reversible, tx0, tx1, ty0, ty1, L);
                 res[c] = calloc(L + 1, sizeof(ResLevel));
                 for (int r = 0; r <= L; r++) {

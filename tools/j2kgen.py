@@ -29,6 +29,7 @@ class _Params(ctypes.Structure):
         ("eph", ctypes.c_int32), ("vsc", ctypes.c_int32), ("base_step", ctypes.c_float),
         ("x_off", ctypes.c_int32), ("y_off", ctypes.c_int32), ("stats_blocks", ctypes.c_int32),
         ("stats_max_lcup", ctypes.c_int32), ("error", ctypes.c_int32),
+        ("sub_x", ctypes.c_int32 * 4), ("sub_y", ctypes.c_int32 * 4),
     ]
 
 
@@ -70,6 +71,7 @@ class EncParams:
     base_step: float = 1.0
     tile: tuple = (0, 0)
     offset: tuple = (0, 0)
+    subsampling: list | None = None   # [(XRsiz, YRsiz)] per component; plane c is ceil(W/XRsiz) x ceil(H/YRsiz)
     stats: dict = field(default_factory=dict)
 
 
@@ -78,6 +80,9 @@ def encode(planes, bitdepth: int, p: EncParams) -> bytes:
     L = lib()
     planes = [np.ascontiguousarray(a, dtype=np.int32) for a in planes]
     h, w = planes[0].shape
+    if p.subsampling:
+        for a, (sx, sy) in zip(planes, p.subsampling):
+            assert a.shape == (-(-h // sy), -(-w // sx)), "plane shape does not match its subsampling"
     guard = p.guard_bits
     while True:
         P = _Params()
@@ -94,6 +99,9 @@ def encode(planes, bitdepth: int, p: EncParams) -> bytes:
         P.guard_bits, P.npasses, P.sop, P.eph, P.vsc = guard, p.npasses, int(p.sop), int(p.eph), int(p.vsc)
         P.base_step = p.base_step
         P.x_off, P.y_off = p.offset
+        if p.subsampling:
+            for c, (sx, sy) in enumerate(p.subsampling):
+                P.sub_x[c], P.sub_y[c] = sx, sy
         cap = int(w * h * len(planes) * 4 + (1 << 20))
         out = np.empty(cap, np.uint8)
         ptrs = (ctypes.c_void_p * len(planes))(*[a.ctypes.data for a in planes])
@@ -168,3 +176,46 @@ def make_config(name: str, scale: int = 1, phase: float = 0.0, seed_offset: int 
         enc["tile"] = (enc["tile"][0] // scale, enc["tile"][1] // scale)
     p = EncParams(**enc)
     return encode(planes, c["bitdepth"], p), planes, p
+
+
+def _box(kind: bytes, payload: bytes) -> bytes:
+    return (8 + len(payload)).to_bytes(4, "big") + kind + payload
+
+
+def wrap_jp2(cs: bytes, w: int, h: int, ncomp: int, bitdepth: int, colour_space: int | None = 16,
+             cdef: list | None = None, palette: tuple | None = None, res: tuple | None = None,
+             brand: bytes = b"jph ", extra_before: int = 0) -> bytes:
+    """Wrap a codestream into a JP2 / JPH file (ISO/IEC 15444-1 Annex I boxes), as much of it as the
+    reference's jp2_find_codestream reads: signature, ftyp, jp2h{ihdr, colr, [pclr], [cdef], [res ]}, jp2c.
+    colour_space: enumerated colour space of the colr box (16 sRGB, 17 greyscale, 18 sYCC; None = no colr box).
+    cdef: [(channel, type, association)].  palette: (entries, depth) -> a 3-channel pclr box.
+    extra_before: number of unknown boxes placed before jp2h (the reference gives up after 10)."""
+    out = _box(b"jP  ", bytes([0x0D, 0x0A, 0x87, 0x0A]))
+    out += _box(b"ftyp", brand + (0).to_bytes(4, "big") + brand + b"jp2 ")
+    for _ in range(extra_before):
+        out += _box(b"free", b"\0" * 5)
+    ihdr = h.to_bytes(4, "big") + w.to_bytes(4, "big") + ncomp.to_bytes(2, "big") + bytes([bitdepth - 1, 7, 0, 0])
+    hdr = _box(b"ihdr", ihdr)
+    if colour_space is not None:
+        hdr += _box(b"colr", bytes([1, 0, 0]) + colour_space.to_bytes(4, "big"))
+    if palette is not None:
+        entries, depth = palette
+        nbytes = (depth + 7) // 8
+        body = entries.to_bytes(2, "big") + bytes([3, depth - 1, depth - 1, depth - 1])
+        for i in range(entries):
+            for c in range(3):
+                body += ((i * (c + 1)) % (1 << depth)).to_bytes(nbytes, "big")
+        hdr += _box(b"pclr", body)
+    if cdef is not None:
+        body = len(cdef).to_bytes(2, "big")
+        for cn, typ, asoc in cdef:
+            body += cn.to_bytes(2, "big") + typ.to_bytes(2, "big") + asoc.to_bytes(2, "big")
+        hdr += _box(b"cdef", body)
+    if res is not None:
+        vnum, vden, hnum, hden, vexp, hexp = res
+        resc = vnum.to_bytes(2, "big") + vden.to_bytes(2, "big") + hnum.to_bytes(2, "big") + hden.to_bytes(2, "big") + \
+            bytes([vexp, hexp])
+        hdr += _box(b"res ", _box(b"resc", resc))
+    out += _box(b"jp2h", hdr)
+    out += _box(b"jp2c", cs)
+    return out
