@@ -74,6 +74,37 @@ def main():
         pack[k + "|out"] = out
     np.savez_compressed(OUT / "frames.npz", **pack)
 
+    # ---- the widened surface: lowres, JP2 / JPH wrapper, chroma subsampling (planar output) ----------------
+    # key = name|flags with flags = bitexact | lowres << 8 (what ref_decode / oracle_decode take)
+    from test_oracle_vs_ref import SUBSAMPLED, subsampled_stream
+    wide = {}
+    planes = j2kgen.synth_image(200, 120, 3, 12, seed=31)
+    cs = j2kgen.encode(planes, 12, j2kgen.EncParams(levels=4, tile=(128, 64)))
+    cs97 = j2kgen.encode(j2kgen.synth_image(200, 120, 3, 10, seed=32), 10,
+                         j2kgen.EncParams(levels=3, reversible=False, base_step=1.0))
+    for lowres in (1, 2, 4):
+        wide[f"lowres{lowres}_rgb12_tiles|{lowres << 8}"] = cs
+    for lowres in (1, 3):
+        for be in (0, 1):
+            wide[f"lowres{lowres}_rgb10_97|{be | lowres << 8}"] = cs97
+    for name, subs, bd in SUBSAMPLED:
+        c, _, _ = subsampled_stream(subs, bd, 131, 77, dict(levels=3, tile=(64, 48)))
+        wide[f"sub_{name}|0"] = c
+        wide[f"sub_{name}_jp2_cdef|0"] = j2kgen.wrap_jp2(c, 131, 77, len(subs), bd, colour_space=18,
+                                                         cdef=[(0, 0, 1), (1, 0, 3), (2, 0, 2), (3, 1, 0)][:len(subs)])
+    for nc, bd in [(3, 8), (3, 12), (1, 16), (4, 8)]:
+        c = j2kgen.encode(j2kgen.synth_image(160, 90, nc, bd, seed=8), bd, j2kgen.EncParams(levels=3, mct=nc >= 3))
+        for csp in (16, 17, 18):
+            wide[f"jp2_nc{nc}_bd{bd}_colr{csp}|0"] = j2kgen.wrap_jp2(c, 160, 90, nc, bd, colour_space=csp)
+    pack = {}
+    for k, data in wide.items():
+        r, info, out, pix = ref_decode(data, int(k.split("|")[1]))
+        pack[k + "|cs"] = np.frombuffer(data, np.uint8)
+        pack[k + "|meta"] = np.array([info[0], info[1], r], np.int64)
+        pack[k + "|pix"] = np.frombuffer((pix or "none").encode(), np.uint8)
+        pack[k + "|out"] = out if r == 0 else np.zeros(0, np.uint8)
+    np.savez_compressed(OUT / "frames_wide.npz", **pack)
+
     # ---- HT code-blocks ----------------------------------------------------------------------------
     rng = np.random.default_rng(2024)
     blocks = {}
@@ -118,7 +149,7 @@ def main():
             dwt[f"{t}|{j}|par"] = np.array([x0, x0 + w, y0, y0 + h, levels], np.int32)
             dwt[f"{t}|{j}|out"] = b
     np.savez_compressed(OUT / "idwt.npz", **dwt)
-    for f in ("frames.npz", "blocks.npz", "idwt.npz"):
+    for f in ("frames.npz", "frames_wide.npz", "blocks.npz", "idwt.npz"):
         b = (OUT / f).read_bytes()
         print(f, len(b), hashlib.md5(b).hexdigest())
 

@@ -3,7 +3,7 @@ CPU only; the GPU counterparts live in tests/test_gpu_parity.py."""
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, ORACLE_PIX, ht_block, oracle, oracle_decode
+from helpers import GOLDEN, ORACLE_PIX, ht_block, oracle, oracle_decode, oracle_pix_name
 
 
 def _groups(npz, fields):
@@ -24,6 +24,22 @@ def test_golden_frames():
         assert np.array_equal(got, out), key
         n += 1
     assert n >= 20
+
+
+def test_golden_frames_wide():
+    """lowres, JP2 / JPH files, chroma-subsampled streams: reference outputs and error codes"""
+    z = np.load(GOLDEN / "frames_wide.npz")
+    n = 0
+    for key, (cs, meta, pix, out) in _groups(z, ["cs", "meta", "pix", "out"]):
+        flags = int(key.split("|")[1])
+        r, info, got = oracle_decode(cs.tobytes(), flags)
+        assert r == meta[2], key
+        if r == 0:
+            assert info[0] == meta[0] and info[1] == meta[1], key
+            assert oracle_pix_name() == pix.tobytes().decode(), key
+            assert np.array_equal(got, out), key
+        n += 1
+    assert n >= 35
 
 
 def test_golden_kat_values():

@@ -202,6 +202,25 @@ def test_golden_frames(dec, dec_bitexact):
     assert n >= 20
 
 
+def test_golden_frames_wide():
+    """Reference-generated vectors for lowres, JP2 / JPH files and chroma-subsampled streams."""
+    z = np.load(GOLDEN / "frames_wide.npz")
+    n = 0
+    for key, (cs, meta, pix, out) in _groups(z, ["cs", "meta", "pix", "out"]):
+        flags = int(key.split("|")[1])
+        with fb.Jpeg2000Decoder(device=0, slots=1, bitexact=bool(flags & 1), lowres=flags >> 8) as d:
+            if meta[2] < 0:
+                with pytest.raises(fb.DecodeError) as e:
+                    d.decode(cs.tobytes())
+                assert e.value.code == meta[2], key
+            else:
+                info, got = d.decode(cs.tobytes())
+                assert (info.width, info.height, info.pix_name) == (meta[0], meta[1], pix.tobytes().decode()), key
+                assert np.array_equal(got, out), key
+        n += 1
+    assert n >= 35
+
+
 @pytest.mark.parametrize("cfg", STREAMS, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
 def test_frames_vs_oracle(cfg, dec, dec_bitexact):
     cfg = dict(cfg)
