@@ -500,9 +500,9 @@ template <int TYPE> struct StreamCfg {
 };
 /* rows per warp: enough warps to fill the GPU (148 SMs x 8 resident warps), but not so few rows that the
  * HALO warm-up rows dominate */
-int pick_seg(int strips, int units_z, int rows)
+int pick_seg(int strips, int units_z, int rows, int per_sm = STREAM_WANT)
 {
-    const long want = 148L * STREAM_WANT;
+    const long want = 148L * per_sm;
     long seg = ((long)rows * strips * units_z + want - 1) / want;
     seg = (seg + 1) & ~1L;
     if (seg < 8) seg = 8;
