@@ -173,6 +173,21 @@ def run_ours(args):
     if fb.lib().b200j2k_device_count() < 1:
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
+    # keep this rank's host threads and pinned buffers on the CPUs next to its GPU (matters for the end-to-end
+    # leg on multi-socket boxes: every frame crosses PCIe twice)
+    affinity = None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            affinity = len(cpus)
+    except Exception:
+        pass
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -364,6 +379,7 @@ def run_ours(args):
                        "l2": "inputs larger than L2: %d MB of coefficient planes + %d MB codestream per frame, "
                              "%d frames cycled" % (int(samples * 4 / 1e6), int(len(frames[0]) / 1e6), S),
                        "e2e_host_threads": T, "e2e_slots_per_thread": args.slots_e2e,
+                       "e2e_cpu_affinity": affinity,
                        "e2e_buffers": "codestreams and output pictures in pinned host memory",
                        "e2e_timer": "wall clock bracketed by device synchronisation (includes host parsing)"},
             "e2e": {"value": e2e, "unit": "Mpixel/s", "fps": frames_total / e2e_s,
