@@ -96,6 +96,13 @@ def main():
         c = j2kgen.encode(j2kgen.synth_image(160, 90, nc, bd, seed=8), bd, j2kgen.EncParams(levels=3, mct=nc >= 3))
         for csp in (16, 17, 18):
             wide[f"jp2_nc{nc}_bd{bd}_colr{csp}|0"] = j2kgen.wrap_jp2(c, 160, 90, nc, bd, colour_space=csp)
+    from test_oracle_vs_ref import LAYERED
+    for i in (1, 3, 7):                                   # two quality layers: split HT sets, placeholders, late inclusion
+        cfg = dict(LAYERED[i])
+        w_, h_, nc_, bd_ = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+        c = j2kgen.encode(j2kgen.synth_image(w_, h_, nc_, bd_, seed=4), bd_, j2kgen.EncParams(layers=2, **cfg))
+        for be in ((0,) if cfg.get("reversible", True) else (0, 1)):
+            wide[f"layers2_{i}|{be}"] = c
     pack = {}
     for k, data in wide.items():
         r, info, out, pix = ref_decode(data, int(k.split("|")[1]))

@@ -12,7 +12,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, subsampled_stream
+from test_oracle_vs_ref import LAYERED, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, subsampled_stream
 
 pytestmark = pytest.mark.gpu
 
@@ -310,6 +310,24 @@ def test_streaming_idwt_geometries(cfg, dec, dec_bitexact):
     if p.reversible:
         img = got.view(np.uint16).reshape(h, w, nc)
         assert np.array_equal(img >> (16 - bd), np.stack(planes, -1))
+
+
+@pytest.mark.parametrize("cfg", LAYERED, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
+def test_two_layer_frames_vs_oracle(cfg, dec, dec_bitexact):
+    """Two quality layers (split HT sets, late inclusion, placeholder passes => p0 > 0 in the kernels)."""
+    cfg = dict(cfg)
+    w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=4)
+    cs = j2kgen.encode(planes, bd, j2kgen.EncParams(layers=2, **cfg))
+    for bitexact in ((0,) if cfg.get("reversible", True) else (0, 1)):
+        r, oinfo, want = oracle_decode(cs, bitexact)
+        assert r == 0
+        info, got = (dec_bitexact if bitexact else dec).decode(cs)
+        assert (info.width, info.height) == (oinfo[0], oinfo[1])
+        assert np.array_equal(got, want)
+    if cfg.get("reversible", True) and cfg.get("npasses", 1) == 1:
+        img = got.view(np.uint16 if bd > 8 else np.uint8).reshape(h, w, nc)
+        assert np.array_equal(img >> ((16 - bd) if bd > 8 else 0), np.stack(planes, -1))
 
 
 @pytest.mark.parametrize("name,subs,bd", SUBSAMPLED, ids=[s[0] for s in SUBSAMPLED])

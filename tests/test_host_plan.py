@@ -11,7 +11,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, subsampled_stream
+from test_oracle_vs_ref import LAYERED, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, subsampled_stream
 
 
 def picture_from_plan(cs: bytes, flags: int):
@@ -215,6 +215,26 @@ def test_bytes_consumed_matches_reference():
         r, info, _, _ = ref_decode(cs, 0)
         assert r == 0
         assert fb.plan(cs, 0)["info"].bytes_consumed == info[4]
+
+
+@pytest.mark.parametrize("cfg", LAYERED, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
+def test_plan_of_two_layer_streams(cfg):
+    """Two quality layers: pass counts with placeholder triples, Lcup / Lref accumulated over the packets,
+    segments of one block gathered behind the codestream when its contributions are not adjacent."""
+    cfg = dict(cfg)
+    w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=4)
+    cs = j2kgen.encode(planes, bd, j2kgen.EncParams(layers=2, **cfg))
+    P = fb.plan(cs, 0)
+    npass = P["cblk"]["npasses"]
+    assert (npass > 3).any()                                  # placeholder triples do occur
+    if cfg.get("npasses", 1) > 1:
+        assert len(P["extra"]) > 0                            # and so do HT sets split over two packets
+    for bitexact in ((0,) if cfg.get("reversible", True) else (0, 1)):
+        r, oinfo, opic = oracle_decode(cs, bitexact)
+        assert r == 0
+        info, pic = picture_from_plan(cs, fb.FLAG_BITEXACT if bitexact else 0)
+        assert np.array_equal(pic, opic)
 
 
 @pytest.mark.parametrize("name,subs,bd", SUBSAMPLED, ids=[s[0] for s in SUBSAMPLED])

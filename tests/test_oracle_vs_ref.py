@@ -170,6 +170,40 @@ def test_lowres_decode_bit_exact(cfg):
                 assert np.array_equal(out1, out2), lowres
 
 
+# two quality layers: HT sets split over the layers, blocks first included in the second layer, triples of empty
+# placeholder passes in front of the HT set in the same or in an earlier packet (jpeg2000dec.c:1256-1362)
+LAYERED = [
+    dict(w=128, h=96, nc=3, bd=12, levels=3, cblk=(32, 32)),
+    dict(w=128, h=96, nc=3, bd=12, levels=3, cblk=(32, 32), npasses=3),
+    dict(w=128, h=96, nc=1, bd=8, levels=2, cblk=(16, 16), npasses=2, vsc=True),
+    dict(w=200, h=120, nc=3, bd=10, levels=4, npasses=3, prog=2, precincts=[(6, 6), (7, 7)], cblk=(32, 32)),
+    dict(w=200, h=120, nc=3, bd=10, levels=4, npasses=3, prog=3, precincts=[(6, 6), (7, 7)], cblk=(32, 32)),
+    dict(w=200, h=120, nc=3, bd=10, levels=4, npasses=3, prog=4, precincts=[(6, 6), (7, 7)], cblk=(32, 32), sop=True, eph=True),
+    dict(w=200, h=120, nc=3, bd=10, levels=4, npasses=1, prog=1, tile=(128, 64)),
+    dict(w=160, h=100, nc=3, bd=10, levels=3, reversible=False, base_step=1.0, npasses=3),
+    dict(w=300, h=200, nc=1, bd=16, levels=5, cblk=(128, 32), npasses=3),
+]
+
+
+@pytest.mark.parametrize("cfg", LAYERED, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
+def test_two_layer_streams_bit_exact(cfg):
+    """The same picture coded in one and in two quality layers: the reference decodes both to identical
+    pixels (this validates the generator), and the oracle equals the reference on the two-layer stream."""
+    cfg = dict(cfg)
+    w, h, nc, bd = cfg.pop("w"), cfg.pop("h"), cfg.pop("nc"), cfg.pop("bd")
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=4)
+    one = j2kgen.encode(planes, bd, j2kgen.EncParams(**cfg))
+    two = j2kgen.encode(planes, bd, j2kgen.EncParams(layers=2, **cfg))
+    assert len(two) != len(one)
+    for bitexact in ((0,) if cfg.get("reversible", True) else (0, 1)):
+        r0, _, out0, _ = ref_decode(one, bitexact)
+        r1, info1, out1, name = ref_decode(two, bitexact)
+        r2, info2, out2 = oracle_decode(two, bitexact)
+        assert r0 == 0 and r1 == 0 and r2 == 0
+        assert np.array_equal(out0, out1)
+        assert info1[:2] == info2[:2] and oracle_pix_name() == name and np.array_equal(out1, out2)
+
+
 # chroma-subsampled streams (XRsiz / YRsiz > 1): (name, [(XRsiz, YRsiz)], bit depth) -> the planar YUV(A) formats
 SUBSAMPLED = [("420", [(1, 1), (2, 2), (2, 2)], 8), ("422", [(1, 1), (2, 1), (2, 1)], 10), ("440", [(1, 1), (1, 2), (1, 2)], 8),
               ("411", [(1, 1), (4, 1), (4, 1)], 8), ("410", [(1, 1), (4, 4), (4, 4)], 8),

@@ -45,6 +45,12 @@ typedef struct J2kGenParams {
     int32_t stats_blocks;        /* out: number of non-empty code-blocks */
     int32_t stats_max_lcup;      /* out */
     int32_t error;               /* out: 0 ok, 1 exponent bound exceeded (raise guard_bits), 2 segment too long */
+    int32_t layers;              /* 0/1: one quality layer.  2: every block is spread over two layers in one of
+                                  * four ways chosen by a hash of its position -- all passes in layer 0; cleanup in
+                                  * layer 0 and refinement in layer 1; first included in layer 1; a triple of empty
+                                  * placeholder passes in layer 0 and the HT set in layer 1 -- and half of the blocks
+                                  * with spare zero bit-planes carry an extra placeholder triple in front of the HT set
+                                  * (jpeg2000dec.c:1256-1362) */
     int32_t sub_x[4], sub_y[4];  /* XRsiz / YRsiz per component (0 = 1).  With subsampling: no offset, no component
                                   * transform, LRCP / RLCP only; plane c holds ceil(W/sub_x) x ceil(H/sub_y) samples */
 } J2kGenParams;
@@ -776,9 +782,16 @@ typedef struct CodedBlock {
     int Lcup, Lref, len;
     int zbp;
     int included;
+    /* quality-layer plan and tier-2 state (layers == 2) */
+    int mode;                   /* 0 all in layer 0, 1 refinement in layer 1, 2 first included in layer 1, 3 placeholders first */
+    int p0_same;                /* placeholder triples signalled together with the HT set */
+    int zbp_sig;                /* zero bit-planes as signalled: zbp minus all placeholder triples */
+    int lblock, sent;           /* Lblock state; 1 once the block has appeared in a packet header */
 } CodedBlock;
 
 typedef struct Precinct {
+    TagTree incl, zbpt;         /* tag trees live as long as the precinct: their state spans the layers */
+    int tt_ready;
     int ncbw, ncbh;             /* code-block grid */
     int cx0, cy0;               /* index of first code-block column/row in the band grid */
     CodedBlock *cb;
@@ -816,7 +829,32 @@ static float decoder_stepsize(int cbps, int expn, int mant, int bandpos, int nre
     return f;
 }
 
-static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precno, int *sop_counter)
+static void put_npasses(BitW *w, int n)
+{
+    /* jpeg2000dec.c:1073-1086 */
+    if (n == 1) bw_put(w, 0, 1);
+    else if (n == 2) bw_put(w, 2, 2);
+    else if (n <= 5) bw_put(w, 0xC | (n - 3), 4);
+    else { bw_put(w, 0xF, 4); bw_put(w, n - 6, 5); }
+}
+
+static int floor_log2(int v) { int n = 0; while (v > 1) { v >>= 1; n++; } return n; }
+
+/* what a block contributes to the packet of `layer`: 0 nothing, 1 placeholder triple, 2 HT set (cleanup and,
+ * unless they follow in the next layer, the refinement passes), 3 refinement passes only */
+static int contribution(const J2kGenParams *P, const CodedBlock *cb, int layer)
+{
+    if (!cb->included)
+        return 0;
+    switch (cb->mode) {
+    case 0: return layer == 0 ? 2 : 0;
+    case 1: return layer == 0 ? 2 : (P->npasses > 1 ? 3 : 0);
+    case 2: return layer == 1 ? 2 : 0;
+    default: return layer == 0 ? 1 : 2;
+    }
+}
+
+static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precno, int layer, int *sop_counter)
 {
     if (P->sop) {
         buf_put16(out, 0xFF91); buf_put16(out, 4); buf_put16(out, (*sop_counter)++ & 0xFFFF);
@@ -827,7 +865,7 @@ static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precn
         if (bd->x0 == bd->x1 || bd->y0 == bd->y1) continue;
         Precinct *pr = &bd->prec[precno];
         for (int i = 0; i < pr->ncbw * pr->ncbh; i++)
-            any |= pr->cb[i].included;
+            any |= contribution(P, &pr->cb[i], layer) != 0;
     }
     BitW w;
     bw_init(&w, out);
@@ -844,35 +882,66 @@ static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precn
         Precinct *pr = &bd->prec[precno];
         int n = pr->ncbw * pr->ncbh;
         if (!n) continue;
-        TagTree incl, zbp;
-        tt_init(&incl, pr->ncbw, pr->ncbh);
-        tt_init(&zbp, pr->ncbw, pr->ncbh);
-        for (int i = 0; i < n; i++) {
-            tt_set(&incl, i, pr->cb[i].included ? 0 : 1);
-            if (pr->cb[i].included)
-                tt_set(&zbp, i, pr->cb[i].zbp);
+        if (!pr->tt_ready) {
+            tt_init(&pr->incl, pr->ncbw, pr->ncbh);
+            tt_init(&pr->zbpt, pr->ncbw, pr->ncbh);
+            for (int i = 0; i < n; i++) {
+                CodedBlock *cb = &pr->cb[i];
+                /* leaf of the inclusion tree = first layer with a contribution; blocks without data never appear */
+                tt_set(&pr->incl, i, cb->included ? (cb->mode == 2 ? 1 : 0) : 1 << 20);
+                if (cb->included)
+                    tt_set(&pr->zbpt, i, cb->zbp_sig);
+            }
+            pr->tt_ready = 1;
         }
         for (int i = 0; i < n; i++) {
             CodedBlock *cb = &pr->cb[i];
-            tt_encode(&incl, &w, i, 1);
-            if (!cb->included)
-                continue;
-            tt_encode(&zbp, &w, i, cb->zbp + 1);   /* emits up to and including the terminating 1 */
-            /* number of passes (libavcodec/jpeg2000dec.c:1073-1086) */
-            int np = P->npasses;
-            if (np == 1) bw_put(&w, 0, 1);
-            else if (np == 2) bw_put(&w, 2, 2);
-            else bw_put(&w, 0xC | (np - 3), 4);
-            /* lblock: cleanup length in lblock bits, refinement in lblock + log2(passes) bits */
-            int lblock = 3, need = imax(bitlen(cb->Lcup), np > 1 ? bitlen(cb->Lref) - (np == 3) : 0);
-            while (lblock < need) { bw_put(&w, 1, 1); lblock++; }
-            bw_put(&w, 0, 1);
-            bw_put(&w, cb->Lcup, lblock);
-            if (np > 1)
-                bw_put(&w, cb->Lref, lblock + (np == 3));
+            const int what = contribution(P, cb, layer);
+            if (!cb->sent) {
+                /* the decoder asks the tree twice from the second layer on (jpeg2000dec.c:1163-1170) */
+                if (layer > 0)
+                    tt_encode(&pr->incl, &w, i, 1);
+                tt_encode(&pr->incl, &w, i, layer + 1);
+                if (!what)
+                    continue;
+                tt_encode(&pr->zbpt, &w, i, cb->zbp_sig + 1);   /* emits up to and including the terminating 1 */
+                cb->sent = 1;
+                cb->lblock = 3;
+            } else {
+                bw_put(&w, what != 0, 1);
+                if (!what)
+                    continue;
+            }
+            const int np = P->npasses;
+            if (what == 1) {
+                /* three empty placeholder passes: a zero length in Lblock bits, then the one more bit the decoder
+                 * reads while it widens the field for three passes (jpeg2000dec.c:1301-1321) */
+                put_npasses(&w, 3);
+                bw_put(&w, 0, 1);
+                bw_put(&w, 0, cb->lblock);
+                bw_put(&w, 0, 1);
+            } else if (what == 2) {
+                const int npc = (cb->mode == 1 && np > 1) ? 1 : np;          /* passes of the HT set sent now */
+                const int newpasses = 3 * cb->p0_same + npc;
+                const int wide = floor_log2(3 * cb->p0_same + 1);            /* extra bits of the cleanup length field */
+                put_npasses(&w, newpasses);
+                int need = bitlen(cb->Lcup) - wide;
+                if (npc > 1)
+                    need = imax(need, bitlen(cb->Lref) - (npc == 3));
+                while (cb->lblock < need) { bw_put(&w, 1, 1); cb->lblock++; }
+                bw_put(&w, 0, 1);
+                bw_put(&w, cb->Lcup, cb->lblock + wide);
+                if (npc > 1)
+                    bw_put(&w, cb->Lref, cb->lblock + (npc == 3));
+            } else {
+                const int newpasses = np - 1;                                /* SigProp [+ MagRef] */
+                put_npasses(&w, newpasses);
+                const int need = bitlen(cb->Lref) - (newpasses == 2);
+                while (cb->lblock < need) { bw_put(&w, 1, 1); cb->lblock++; }
+                bw_put(&w, 0, 1);
+                bw_put(&w, cb->Lref, cb->lblock + (newpasses == 2));
+            }
         }
-        free(incl.n);
-        free(zbp.n);
     }
     bw_flush(&w);
     if (P->eph) buf_put16(out, 0xFF92);
@@ -880,9 +949,16 @@ static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precn
         Band *bd = &rl->band[b];
         if (bd->x0 == bd->x1 || bd->y0 == bd->y1) continue;
         Precinct *pr = &bd->prec[precno];
-        for (int i = 0; i < pr->ncbw * pr->ncbh; i++)
-            if (pr->cb[i].included)
-                buf_append(out, pr->cb[i].data, pr->cb[i].len);
+        for (int i = 0; i < pr->ncbw * pr->ncbh; i++) {
+            CodedBlock *cb = &pr->cb[i];
+            const int what = contribution(P, cb, layer);
+            if (what == 2) {
+                const int all = !(cb->mode == 1 && P->npasses > 1);
+                buf_append(out, cb->data, all ? cb->len : cb->Lcup);
+            } else if (what == 3) {
+                buf_append(out, cb->data + cb->Lcup, cb->Lref);
+            }
+        }
     }
     return 0;
 }
@@ -943,7 +1019,8 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
     buf_put16(&out, 0xFF52);
     buf_put16(&out, 12 + (P->use_precincts ? L + 1 : 0));
     buf_put(&out, (P->use_precincts ? 1 : 0) | (P->sop ? 2 : 0) | (P->eph ? 4 : 0));
-    buf_put(&out, P->prog); buf_put16(&out, 1); buf_put(&out, (P->mct && C >= 3) ? 1 : 0);
+    const int NLAY = P->layers == 2 ? 2 : 1;
+    buf_put(&out, P->prog); buf_put16(&out, NLAY); buf_put(&out, (P->mct && C >= 3) ? 1 : 0);
     buf_put(&out, L); buf_put(&out, P->cbw_log2 - 2); buf_put(&out, P->cbh_log2 - 2);
     buf_put(&out, 0x40 | (P->vsc ? 0x08 : 0));
     buf_put(&out, P->reversible ? 1 : 0);
@@ -1108,6 +1185,17 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
                                     if (o.error) P->error = o.error;
                                     cb->data = o.data.p; cb->len = (int)o.data.n;
                                     cb->Lcup = o.Lcup; cb->Lref = o.Lref; cb->zbp = zbp; cb->included = 1;
+                                    cb->zbp_sig = zbp;
+                                    if (P->layers == 2) {
+                                        uint32_t hsh = (uint32_t)(((((tileno * 131 + c) * 31 + r) * 17 + b) * 7 + pno) * 3 + k);
+                                        hsh = hsh * 2654435761u;
+                                        hsh ^= hsh >> 15;
+                                        cb->mode = (int)(hsh & 3);
+                                        cb->p0_same = (int)((hsh >> 2) & 1);
+                                        int p0 = cb->p0_same + (cb->mode == 3);
+                                        if (zbp < p0) { cb->mode = 0; cb->p0_same = 0; p0 = 0; }
+                                        cb->zbp_sig = zbp - p0;
+                                    }
                                     P->stats_blocks++;
                                     if (o.Lcup > P->stats_max_lcup) P->stats_max_lcup = o.Lcup;
                                 }
@@ -1127,17 +1215,25 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
             for (int c = 0; c < C; c++) for (int r = 0; r <= L; r++) maxnp = imax(maxnp, res[c][r].npx * res[c][r].npy);
             switch (P->prog) {
             case 0: /* LRCP */
-            case 1: /* RLCP (one layer: same as LRCP) */
+                for (int l = 0; l < NLAY; l++)
+                    for (int r = 0; r <= L; r++)
+                        for (int c = 0; c < C; c++)
+                            for (int p = 0; p < res[c][r].npx * res[c][r].npy; p++)
+                                write_packet(&out, P, &res[c][r], p, l, &sopc);
+                break;
+            case 1: /* RLCP */
                 for (int r = 0; r <= L; r++)
-                    for (int c = 0; c < C; c++)
-                        for (int p = 0; p < res[c][r].npx * res[c][r].npy; p++)
-                            write_packet(&out, P, &res[c][r], p, &sopc);
+                    for (int l = 0; l < NLAY; l++)
+                        for (int c = 0; c < C; c++)
+                            for (int p = 0; p < res[c][r].npx * res[c][r].npy; p++)
+                                write_packet(&out, P, &res[c][r], p, l, &sopc);
                 break;
             case 2: /* RPCL */
                 for (int r = 0; r <= L; r++)
                     for (int p = 0; p < res[0][r].npx * res[0][r].npy; p++)
                         for (int c = 0; c < C; c++)
-                            write_packet(&out, P, &res[c][r], p, &sopc);
+                            for (int l = 0; l < NLAY; l++)
+                                write_packet(&out, P, &res[c][r], p, l, &sopc);
                 break;
             case 3: /* PCRL: positions ordered by their top-left corner on the reference grid */
             case 4: /* CPRL */ {
@@ -1162,7 +1258,8 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
                                     int pxi = (ceildivpow2(x, nl) >> rl->ppx) - (rl->x0 >> rl->ppx);
                                     int pyi = (ceildivpow2(y, nl) >> rl->ppy) - (rl->y0 >> rl->ppy);
                                     if (pxi < 0 || pyi < 0 || pxi >= rl->npx || pyi >= rl->npy) continue;
-                                    write_packet(&out, P, rl, pxi + pyi * rl->npx, &sopc);
+                                    for (int l = 0; l < NLAY; l++)
+                                        write_packet(&out, P, rl, pxi + pyi * rl->npx, l, &sopc);
                                 }
                 }
                 break;
@@ -1181,6 +1278,7 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
                             Precinct *pr = &bd->prec[p];
                             for (int k = 0; k < pr->ncbw * pr->ncbh; k++) free(pr->cb[k].data);
                             free(pr->cb);
+                            if (pr->tt_ready) { free(pr->incl.n); free(pr->zbpt.n); }
                         }
                         free(bd->prec);
                     }

@@ -29,7 +29,7 @@ class _Params(ctypes.Structure):
         ("eph", ctypes.c_int32), ("vsc", ctypes.c_int32), ("base_step", ctypes.c_float),
         ("x_off", ctypes.c_int32), ("y_off", ctypes.c_int32), ("stats_blocks", ctypes.c_int32),
         ("stats_max_lcup", ctypes.c_int32), ("error", ctypes.c_int32),
-        ("sub_x", ctypes.c_int32 * 4), ("sub_y", ctypes.c_int32 * 4),
+        ("layers", ctypes.c_int32), ("sub_x", ctypes.c_int32 * 4), ("sub_y", ctypes.c_int32 * 4),
     ]
 
 
@@ -71,6 +71,7 @@ class EncParams:
     base_step: float = 1.0
     tile: tuple = (0, 0)
     offset: tuple = (0, 0)
+    layers: int = 1               # 2: blocks spread over two quality layers (split HT sets, late inclusion, placeholders)
     subsampling: list | None = None   # [(XRsiz, YRsiz)] per component; plane c is ceil(W/XRsiz) x ceil(H/YRsiz)
     stats: dict = field(default_factory=dict)
 
@@ -99,6 +100,7 @@ def encode(planes, bitdepth: int, p: EncParams) -> bytes:
         P.guard_bits, P.npasses, P.sop, P.eph, P.vsc = guard, p.npasses, int(p.sop), int(p.eph), int(p.vsc)
         P.base_step = p.base_step
         P.x_off, P.y_off = p.offset
+        P.layers = p.layers
         if p.subsampling:
             for c, (sx, sy) in enumerate(p.subsampling):
                 P.sub_x[c], P.sub_y[c] = sx, sy
