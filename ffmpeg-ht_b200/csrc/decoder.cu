@@ -408,11 +408,17 @@ int queue_output(Slot &s, uint8_t *const data[4], const int linesize[4])
     s.direct = direct;
     const uint8_t *pic = (const uint8_t *)s.d_picture.p;
     if (direct) {
-        for (int i = 0; i < p.nplanes; i++)
-            if (cudaMemcpy2DAsync(data[i], (size_t)linesize[i], pic + p.plane_off[i], (size_t)p.plane_row_bytes[i],
-                                  (size_t)p.plane_row_bytes[i], (size_t)p.plane_h[i], cudaMemcpyDefault,
-                                  s.stream) != cudaSuccess)
+        for (int i = 0; i < p.nplanes; i++) {
+            cudaError_t e;
+            if (linesize[i] == p.plane_row_bytes[i])     /* no row padding: one linear copy */
+                e = cudaMemcpyAsync(data[i], pic + p.plane_off[i], (size_t)p.plane_row_bytes[i] * p.plane_h[i],
+                                    cudaMemcpyDefault, s.stream);
+            else
+                e = cudaMemcpy2DAsync(data[i], (size_t)linesize[i], pic + p.plane_off[i], (size_t)p.plane_row_bytes[i],
+                                      (size_t)p.plane_row_bytes[i], (size_t)p.plane_h[i], cudaMemcpyDefault, s.stream);
+            if (e != cudaSuccess)
                 return B200J2K_ERR_DEVICE;
+        }
     } else {
         int ret = s.out_stage.ensure(p.picture_bytes);
         if (ret < 0)
