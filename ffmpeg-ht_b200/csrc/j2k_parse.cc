@@ -504,6 +504,7 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 if ((ccap15 >> 13) & 1)
                     return B200J2K_ERR_PATCHWELCOME;
                 h.cap_b05 = (ccap15 >> 5) & 1;
+                h.cap_b11 = (ccap15 >> 11) & 1;
                 int P = ccap15 & 31, B = !P ? 8 : P < 20 ? P + 8 : P < 31 ? 4 * (P - 19) + 27 : 74;
                 if (B > 31)
                     return B200J2K_ERR_PATCHWELCOME;
@@ -604,7 +605,35 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             seg += 8;
             break;
         }
-        case 0xFF5F: case 0xFF60: case 0xFF61:            /* POC, PPM, PPT */
+        case 0xFF5F: {                                    /* POC (get_poc, jpeg2000dec.c:760-818) */
+            if (cur_tile >= 0)                            /* per-tile progression changes: refused by the reference
+                                                           * for HOMOGENEOUS HT streams (:2558), not served otherwise */
+                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
+            if (end - seg < 5 || len < 2 + 7)
+                return B200J2K_ERR_INVALIDDATA;
+            const int n = (len - 2) / 7;
+            if (n > 32)
+                return B200J2K_ERR_PATCHWELCOME;
+            Header::Poc tmp[32];
+            for (int i = 0; i < n; i++) {
+                Header::Poc &e = tmp[i];
+                const uint8_t *q = seg + 7 * i;
+                e.RS = q[0]; e.CS = q[1]; e.LYE = (int)rd16(q + 2); e.RE = q[4]; e.CE = q[5]; e.P = q[6];
+                if (!e.CE)
+                    e.CE = 256;
+                if (e.CE > h.ncomp)
+                    e.CE = h.ncomp;
+                if (e.RS >= e.RE || e.RE > 33 || e.CS >= e.CE || e.CE > h.ncomp || !e.LYE)
+                    return B200J2K_ERR_INVALIDDATA;
+            }
+            if (h.npoc + n > 32)
+                return B200J2K_ERR_INVALIDDATA;
+            for (int i = 0; i < n; i++)                   /* a second POC segment extends the list */
+                h.poc[h.npoc++] = tmp[i];
+            seg += 7 * n;
+            break;
+        }
+        case 0xFF60: case 0xFF61:                         /* PPM, PPT */
             return B200J2K_ERR_PATCHWELCOME;
         default:
             seg = segend;
@@ -1218,7 +1247,7 @@ int Parser::precinct_at(int tileno, int c, int r, int x, int y, bool cprl_rule) 
     px -= (unsigned)(ceildivpow2(cc.x0, red) >> rl.ppx);
     py -= (unsigned)(ceildivpow2(cc.y0, red) >> rl.ppy);
     if (px >= (unsigned)rl.npx || py >= (unsigned)rl.npy)
-        return -1;
+        return -2;                                        /* position accepted, precinct outside the grid */
     return (int)(px + rl.npx * py);
 }
 
@@ -1229,37 +1258,50 @@ int Parser::precinct_at(int tileno, int c, int r, int x, int y, bool cprl_rule) 
             return e_;                                                            \
     } while (0)
 
-int Parser::decode_packets(int tileno)
+/* jpeg2000_decode_packets_po_iteration (jpeg2000dec.c:1544-1828): one progression over the resolution range
+ * [RS, RE), the component range [CS, CE) and the layers [0, LYE).  Packets a previous iteration already
+ * delivered are skipped inside decode_packet (decoded_layers). */
+int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, int P, int *tpp)
 {
     const Header &h = hdr;
     const TileGeom &t = tiles_[tileno];
-    const int nlayers = h.cod[0].nlayers, C = h.ncomp;
-    int tp = 0, maxres = 0;
-    for (int c = 0; c < C; c++)
-        maxres = imax(maxres, h.cod[c].nres);
-    bit_index_ = 8;
+    int &tp = *tpp;
     auto R = [&](int c, int r) -> const ResGeom & { return res_[t.res_base[c] + r]; };
-    switch (h.cod[0].prog) {
+    switch (P) {
     case 0:
-        for (int l = 0; l < nlayers; l++)
-            for (int r = 0; r < maxres; r++)
-                for (int c = 0; c < C; c++)
-                    if (r < h.cod[c].nres)
+        for (int l = 0; l < LYE; l++) {
+            bool ok = true;
+            for (int r = RS; ok && r < RE; r++) {
+                ok = false;
+                for (int c = CS; c < CE; c++)
+                    if (r < h.cod[c].nres) {
+                        ok = true;
                         for (int pn = 0; pn < R(c, r).npx * R(c, r).npy; pn++)
                             PACKET(c, r, pn, l);
+                    }
+            }
+        }
         break;
-    case 1:
-        for (int r = 0; r < maxres; r++)
-            for (int l = 0; l < nlayers; l++)
-                for (int c = 0; c < C; c++)
-                    if (r < h.cod[c].nres)
+    case 1: {
+        bool ok = true;
+        for (int r = RS; ok && r < RE; r++) {
+            ok = false;
+            for (int l = 0; l < LYE; l++)
+                for (int c = CS; c < CE; c++)
+                    if (r < h.cod[c].nres) {
+                        ok = true;
                         for (int pn = 0; pn < R(c, r).npx * R(c, r).npy; pn++)
                             PACKET(c, r, pn, l);
+                    }
+        }
         break;
-    case 2:
-        for (int r = 0; r < maxres; r++) {
+    }
+    case 2: {
+        bool ok = true;
+        for (int r = RS; ok && r < RE; r++) {
+            ok = false;
             int sx = 30, sy = 30;
-            for (int c = 0; c < C; c++)
+            for (int c = CS; c < CE; c++)
                 if (r < h.cod[c].nres) {
                     int red = h.cod[c].nres - 1 - r;
                     sx = imin(sx, R(c, r).ppx + red);
@@ -1268,21 +1310,25 @@ int Parser::decode_packets(int tileno)
             sx = 1 << sx; sy = 1 << sy;
             for (int y = t.c.y0; y < t.c.y1; y = (y / sy + 1) * sy)
                 for (int x = t.c.x0; x < t.c.x1; x = (x / sx + 1) * sx)
-                    for (int c = 0; c < C; c++) {
+                    for (int c = CS; c < CE; c++) {
                         if (r >= h.cod[c].nres)
                             continue;
                         int pn = precinct_at(tileno, c, r, x, y, false);
+                        if (pn == -1)
+                            continue;
+                        ok = true;                        /* set before the "precinct exists" test (:1730) */
                         if (pn < 0)
                             continue;
-                        for (int l = 0; l < nlayers; l++)
+                        for (int l = 0; l < LYE; l++)
                             PACKET(c, r, pn, l);
                     }
         }
         break;
+    }
     case 3: {
         int sx = 32, sy = 32;
-        for (int c = 0; c < C; c++)
-            for (int r = 0; r < h.cod[c].nres; r++) {
+        for (int c = CS; c < CE; c++)
+            for (int r = RS; r < imin(h.cod[c].nres, RE); r++) {
                 int red = h.cod[c].nres - 1 - r;
                 sx = imin(sx, R(c, r).ppx + red);
                 sy = imin(sy, R(c, r).ppy + red);
@@ -1292,20 +1338,22 @@ int Parser::decode_packets(int tileno)
         sx = 1 << sx; sy = 1 << sy;
         for (int y = t.c.y0; y < t.c.y1; y = (y / sy + 1) * sy)
             for (int x = t.c.x0; x < t.c.x1; x = (x / sx + 1) * sx)
-                for (int c = 0; c < C; c++)
-                    for (int r = 0; r < h.cod[c].nres; r++) {
+                for (int c = CS; c < CE; c++)
+                    for (int r = RS; r < imin(h.cod[c].nres, RE); r++) {
                         int pn = precinct_at(tileno, c, r, x, y, false);
                         if (pn < 0)
                             continue;
-                        for (int l = 0; l < nlayers; l++)
+                        for (int l = 0; l < LYE; l++)
                             PACKET(c, r, pn, l);
                     }
         break;
     }
     case 4:
-        for (int c = 0; c < C; c++) {
+        for (int c = CS; c < CE; c++) {
             int sx = 32, sy = 32;
-            for (int r = 0; r < h.cod[c].nres; r++) {
+            if (RS >= imin(h.cod[c].nres, RE))
+                continue;
+            for (int r = RS; r < imin(h.cod[c].nres, RE); r++) {
                 int red = h.cod[c].nres - 1 - r;
                 sx = imin(sx, R(c, r).ppx + red);
                 sy = imin(sy, R(c, r).ppy + red);
@@ -1315,11 +1363,11 @@ int Parser::decode_packets(int tileno)
             sx = 1 << sx; sy = 1 << sy;
             for (int y = t.c.y0; y < t.c.y1; y = (y / sy + 1) * sy)
                 for (int x = t.c.x0; x < t.c.x1; x = (x / sx + 1) * sx)
-                    for (int r = 0; r < h.cod[c].nres; r++) {
+                    for (int r = RS; r < imin(h.cod[c].nres, RE); r++) {
                         int pn = precinct_at(tileno, c, r, x, y, true);
                         if (pn < 0)
                             continue;
-                        for (int l = 0; l < nlayers; l++)
+                        for (int l = 0; l < LYE; l++)
                             PACKET(c, r, pn, l);
                     }
         }
@@ -1328,6 +1376,24 @@ int Parser::decode_packets(int tileno)
         break;
     }
     return 0;
+}
+
+/* jpeg2000_decode_packets (jpeg2000dec.c:1830-1869) */
+int Parser::decode_packets(int tileno)
+{
+    const Header &h = hdr;
+    const int nlayers = h.cod[0].nlayers;
+    int tp = 0, ret = 0;
+    bit_index_ = 8;
+    if (h.npoc) {
+        for (int i = 0; i < h.npoc && ret >= 0; i++) {
+            const Header::Poc &e = h.poc[i];
+            ret = po_iteration(tileno, e.RS, e.CS, imin(e.LYE, nlayers), e.RE, imin(e.CE, h.ncomp), e.P, &tp);
+        }
+    } else {
+        ret = po_iteration(tileno, 0, 0, nlayers, 33, h.ncomp, h.cod[0].prog, &tp);
+    }
+    return ret;
 }
 #undef PACKET
 

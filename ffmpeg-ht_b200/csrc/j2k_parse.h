@@ -76,13 +76,17 @@ struct TagNodeState {
 struct Header {
     int W = 0, H = 0, X0 = 0, Y0 = 0, TW = 0, TH = 0, TX0 = 0, TY0 = 0, ncomp = 0, precision = 0, rsiz = 0;
     int cbps[J2K_MAX_COMP] = {0}, cdx[J2K_MAX_COMP] = {0}, cdy[J2K_MAX_COMP] = {0}, roi[J2K_MAX_COMP] = {0};
-    int isHT = 0, cap_b05 = 0, cap_b14 = 0;
+    int isHT = 0, cap_b05 = 0, cap_b11 = 0, cap_b14 = 0;
     CodSty cod[J2K_MAX_COMP];
     QntSty qnt[J2K_MAX_COMP];
     int had_coc[J2K_MAX_COMP] = {0}, had_qcc[J2K_MAX_COMP] = {0};
     int ntx = 0, nty = 0;
     int pix = 0, out_w = 0, out_h = 0;
     int lossless = 0;
+    /* POC marker segments of the main header (get_poc, jpeg2000dec.c:760-818): progression order changes */
+    struct Poc { int RS, CS, LYE, RE, CE, P; };
+    int npoc = 0;
+    Poc poc[32];
     /* JP2 wrapper (jp2_find_codestream, jpeg2000dec.c:2658-2804) and the pixel format it steers */
     int colour_space = 0, pal8 = 0;
     int cdef[J2K_MAX_COMP] = { -1, -1, -1, -1 };
@@ -143,6 +147,7 @@ private:
     int parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *main_header_len);
     int build_geometry(int flags);
     int decode_packets(int tileno);
+    int po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, int P, int *tp);
     const uint8_t *cur_part_start_ = nullptr;
     int decode_packet(int tileno, int comp, int r, int precno, int layno, int *tp);
     int precinct_at(int tileno, int c, int r, int x, int y, bool cprl_rule) const;

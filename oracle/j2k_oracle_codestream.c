@@ -14,8 +14,8 @@
  *   tile_codeblocks      jpeg2000dec.c:2212-2299
  *   write_frame          jpeg2000dec.c:2301-2366
  *
- * Not handled (returns ORACLE_ERR_PATCH): Part-1 MQ code-blocks, MIXED/HTDECLARED sets, POC, PPM/PPT,
- * JP2 wrapper, lowres, tile-part COD/QCD.  Those are outside SURVEY.md section 8's first bar.
+ * Not handled (returns ORACLE_ERR_PATCH): Part-1 MQ code-blocks, MIXED/HTDECLARED sets, tile-part POC, PPM/PPT,
+ * tile-part COD/QCD.  Those are outside SURVEY.md section 8's first bar.
  */
 #include <math.h>
 #include <pthread.h>
@@ -92,7 +92,7 @@ typedef struct Dec {
     int red;                                        /* reduction_factor = AVCodecContext.lowres (jpeg2000dec.c:2807-2823) */
     int W, H, X0, Y0, TW, TH, TX0, TY0, ncomp, precision;
     int cbps[MAXC], cdx[MAXC], cdy[MAXC], roi[MAXC];
-    int isHT, cap_b05, cap_b14;
+    int isHT, cap_b05, cap_b11, cap_b14;
     CodSty cod[MAXC];
     QntSty qnt[MAXC];
     int had_coc[MAXC], had_qcc[MAXC];
@@ -100,6 +100,8 @@ typedef struct Dec {
     Tile *tile;
     int pix, out_w, out_h;
     int colour_space, pal8, cdef[4];                /* JP2 wrapper state (jp2_find_codestream) */
+    int npoc;                                       /* main-header POC entries (get_poc) */
+    struct { int RS, CS, LYE, RE, CE, P; } poc[32];
     int chroma_lw, chroma_lh;                       /* log2_chroma_w/h of the chosen AVPixelFormat */
     /* packet header bit reader */
     const uint8_t *bp, *bend;
@@ -588,6 +590,7 @@ static int parse_headers(Dec *d)
                 if ((ccap15 >> 13) & 1)
                     return ORACLE_ERR_PATCH;
                 d->cap_b05 = (ccap15 >> 5) & 1;
+                d->cap_b11 = (ccap15 >> 11) & 1;
                 int P = ccap15 & 31, B = !P ? 8 : P < 20 ? P + 8 : P < 31 ? 4 * (P - 19) + 27 : 74;
                 if (B > 31)
                     return ORACLE_ERR_PATCH;
@@ -694,7 +697,31 @@ static int parse_headers(Dec *d)
             seg += 8;
             break;
         }
-        case 0xFF5F: case 0xFF60: case 0xFF61:            /* POC, PPM, PPT */
+        case 0xFF5F: {                                    /* POC: get_poc (jpeg2000dec.c:760-818) */
+            if (cur_tile >= 0)                            /* :2558 refuses it for HOMOGENEOUS HT streams */
+                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
+            if (d->end - seg < 5 || len < 2 + 7)
+                return ORACLE_ERR_INVALID;
+            int n = (len - 2) / 7;
+            if (n > 32)
+                return ORACLE_ERR_PATCH;
+            if (d->npoc + n > 32)
+                return ORACLE_ERR_INVALID;
+            for (int i = 0; i < n; i++, seg += 7) {
+                int RS = seg[0], CS = seg[1], LYE = (int)rd16(seg + 2), RE = seg[4], CE = seg[5], P = seg[6];
+                if (!CE)
+                    CE = 256;
+                if (CE > d->ncomp)
+                    CE = d->ncomp;
+                if (RS >= RE || RE > 33 || CS >= CE || !LYE)
+                    return ORACLE_ERR_INVALID;
+                d->poc[d->npoc + i].RS = RS; d->poc[d->npoc + i].CS = CS; d->poc[d->npoc + i].LYE = LYE;
+                d->poc[d->npoc + i].RE = RE; d->poc[d->npoc + i].CE = CE; d->poc[d->npoc + i].P = P;
+            }
+            d->npoc += n;                                 /* a further POC segment appends (:805-812) */
+            break;
+        }
+        case 0xFF60: case 0xFF61:                         /* PPM, PPT */
             return ORACLE_ERR_PATCH;
         default:                                          /* COM, TLM, PLT, PLM, CRG, CPF, unknown: skipped */
             seg = segend;
@@ -1099,7 +1126,7 @@ static int precinct_at(Dec *d, Tile *t, int c, int r, int x, int y, int cprl_rul
         unsigned px = (unsigned)(ceildivpow2(xc, red) >> rl->ppx) - (unsigned)(ceildivpow2(t->comp[c].c.x0, red) >> rl->ppx);
         unsigned py = (unsigned)(ceildivpow2(yc, red) >> rl->ppy) - (unsigned)(ceildivpow2(t->comp[c].c.y0, red) >> rl->ppy);
         if (px >= (unsigned)rl->npx || py >= (unsigned)rl->npy)
-            return -1;
+            return -2;
         return (int)(px + rl->npx * py);
     }
     int64_t trx0 = ((int64_t)t->c.x0 + ((int64_t)d->cdx[c] << red) - 1) / ((int64_t)d->cdx[c] << red);
@@ -1115,7 +1142,7 @@ static int precinct_at(Dec *d, Tile *t, int c, int r, int x, int y, int cprl_rul
     px -= (unsigned)(ceildivpow2(t->comp[c].c.x0, red) >> rl->ppx);
     py -= (unsigned)(ceildivpow2(t->comp[c].c.y0, red) >> rl->ppy);
     if (px >= (unsigned)rl->npx || py >= (unsigned)rl->npy)
-        return -1;
+        return -2;                                        /* a precinct position, but none exists there */
     return (int)(px + rl->npx * py);
 }
 
@@ -1128,36 +1155,49 @@ static int precinct_at(Dec *d, Tile *t, int c, int r, int x, int y, int cprl_rul
             return e_;                                                                                \
     } while (0)
 
-/* jpeg2000_decode_packets_po_iteration with the default (no POC) bounds (jpeg2000dec.c:1544-1869) */
-static int decode_packets(Dec *d, Tile *t)
+/* jpeg2000_decode_packets_po_iteration (jpeg2000dec.c:1544-1828): resolutions [RS, RE), components [CS, CE),
+ * layers [0, LYE) in progression P.  The resolution loops of LRCP/RLCP/RPCL stop at the first level that no
+ * component of the range owns ("ok_reslevel"). */
+static int po_iteration(Dec *d, Tile *t, PktState *pps, int RS, int CS, int LYE, int RE, int CE, int P)
 {
-    PktState ps = { t, 0 };
-    const int nlayers = d->cod[0].nlayers, C = d->ncomp;
-    int maxres = 0;
-    for (int c = 0; c < C; c++)
-        maxres = imax(maxres, d->cod[c].nres);
-    d->bit_index = 8;
-    switch (d->cod[0].prog) {
+#define ps (*pps)
+    int ok;
+    switch (P) {
     case 0: /* LRCP */
-        for (int l = 0; l < nlayers; l++)
-            for (int r = 0; r < maxres; r++)
-                for (int c = 0; c < C; c++)
-                    if (r < d->cod[c].nres)
-                        for (int pn = 0; pn < t->comp[c].res[r].npx * t->comp[c].res[r].npy; pn++)
-                            PACKET(c, r, pn, l);
+        for (int l = 0; l < LYE; l++) {
+            ok = 1;
+            for (int r = RS; ok && r < RE; r++) {
+                ok = 0;
+                for (int c = CS; c < CE; c++) {
+                    if (r >= d->cod[c].nres)
+                        continue;
+                    ok = 1;
+                    for (int pn = 0; pn < t->comp[c].res[r].npx * t->comp[c].res[r].npy; pn++)
+                        PACKET(c, r, pn, l);
+                }
+            }
+        }
         break;
     case 1: /* RLCP */
-        for (int r = 0; r < maxres; r++)
-            for (int l = 0; l < nlayers; l++)
-                for (int c = 0; c < C; c++)
-                    if (r < d->cod[c].nres)
-                        for (int pn = 0; pn < t->comp[c].res[r].npx * t->comp[c].res[r].npy; pn++)
-                            PACKET(c, r, pn, l);
+        ok = 1;
+        for (int r = RS; ok && r < RE; r++) {
+            ok = 0;
+            for (int l = 0; l < LYE; l++)
+                for (int c = CS; c < CE; c++) {
+                    if (r >= d->cod[c].nres)
+                        continue;
+                    ok = 1;
+                    for (int pn = 0; pn < t->comp[c].res[r].npx * t->comp[c].res[r].npy; pn++)
+                        PACKET(c, r, pn, l);
+                }
+        }
         break;
     case 2: /* RPCL */
-        for (int r = 0; r < maxres; r++) {
+        ok = 1;
+        for (int r = RS; ok && r < RE; r++) {
             int sx = 30, sy = 30;
-            for (int c = 0; c < C; c++)
+            ok = 0;
+            for (int c = CS; c < CE; c++)
                 if (r < d->cod[c].nres) {
                     int red = d->cod[c].nres - 1 - r;
                     sx = imin(sx, t->comp[c].res[r].ppx + red);
@@ -1167,21 +1207,24 @@ static int decode_packets(Dec *d, Tile *t)
             sy = 1 << sy;
             for (int y = t->c.y0; y < t->c.y1; y = (y / sy + 1) * sy)
                 for (int x = t->c.x0; x < t->c.x1; x = (x / sx + 1) * sx)
-                    for (int c = 0; c < C; c++) {
+                    for (int c = CS; c < CE; c++) {
                         if (r >= d->cod[c].nres)
                             continue;
                         int pn = precinct_at(d, t, c, r, x, y, 0);
+                        if (pn == -1)
+                            continue;
+                        ok = 1;                           /* :1730, ahead of the range test */
                         if (pn < 0)
                             continue;
-                        for (int l = 0; l < nlayers; l++)
+                        for (int l = 0; l < LYE; l++)
                             PACKET(c, r, pn, l);
                     }
         }
         break;
     case 3: { /* PCRL */
         int sx = 32, sy = 32;
-        for (int c = 0; c < C; c++)
-            for (int r = 0; r < d->cod[c].nres; r++) {
+        for (int c = CS; c < CE; c++)
+            for (int r = RS; r < imin(d->cod[c].nres, RE); r++) {
                 int red = d->cod[c].nres - 1 - r;
                 sx = imin(sx, t->comp[c].res[r].ppx + red);
                 sy = imin(sy, t->comp[c].res[r].ppy + red);
@@ -1192,20 +1235,23 @@ static int decode_packets(Dec *d, Tile *t)
         sy = 1 << sy;
         for (int y = t->c.y0; y < t->c.y1; y = (y / sy + 1) * sy)
             for (int x = t->c.x0; x < t->c.x1; x = (x / sx + 1) * sx)
-                for (int c = 0; c < C; c++)
-                    for (int r = 0; r < d->cod[c].nres; r++) {
+                for (int c = CS; c < CE; c++)
+                    for (int r = RS; r < imin(d->cod[c].nres, RE); r++) {
                         int pn = precinct_at(d, t, c, r, x, y, 0);
                         if (pn < 0)
                             continue;
-                        for (int l = 0; l < nlayers; l++)
+                        for (int l = 0; l < LYE; l++)
                             PACKET(c, r, pn, l);
                     }
         break;
     }
     case 4: /* CPRL */
-        for (int c = 0; c < C; c++) {
+        for (int c = CS; c < CE; c++) {
             int sx = 32, sy = 32;
-            for (int r = 0; r < d->cod[c].nres; r++) {
+            const int rend = imin(d->cod[c].nres, RE);
+            if (RS >= rend)
+                continue;
+            for (int r = RS; r < rend; r++) {
                 int red = d->cod[c].nres - 1 - r;
                 sx = imin(sx, t->comp[c].res[r].ppx + red);
                 sy = imin(sy, t->comp[c].res[r].ppy + red);
@@ -1216,17 +1262,35 @@ static int decode_packets(Dec *d, Tile *t)
             sy = 1 << sy;
             for (int y = t->c.y0; y < t->c.y1; y = (y / sy + 1) * sy)
                 for (int x = t->c.x0; x < t->c.x1; x = (x / sx + 1) * sx)
-                    for (int r = 0; r < d->cod[c].nres; r++) {
+                    for (int r = RS; r < rend; r++) {
                         int pn = precinct_at(d, t, c, r, x, y, 1);
                         if (pn < 0)
                             continue;
-                        for (int l = 0; l < nlayers; l++)
+                        for (int l = 0; l < LYE; l++)
                             PACKET(c, r, pn, l);
                     }
         }
         break;
     default:
         break;
+    }
+    return 0;
+#undef ps
+}
+
+/* jpeg2000_decode_packets (jpeg2000dec.c:1835-1869): one iteration per POC entry, else the COD progression */
+static int decode_packets(Dec *d, Tile *t)
+{
+    PktState ps = { t, 0 };
+    const int nlayers = d->cod[0].nlayers;
+    d->bit_index = 8;
+    if (!d->npoc)
+        return po_iteration(d, t, &ps, 0, 0, nlayers, 33, d->ncomp, d->cod[0].prog);
+    for (int i = 0; i < d->npoc; i++) {
+        int ret = po_iteration(d, t, &ps, d->poc[i].RS, d->poc[i].CS, imin(d->poc[i].LYE, nlayers), d->poc[i].RE,
+                               imin(d->poc[i].CE, d->ncomp), d->poc[i].P);
+        if (ret < 0)
+            return ret;
     }
     return 0;
 }

@@ -12,7 +12,8 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import LAYERED, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, subsampled_stream
+from test_oracle_vs_ref import (LAYERED, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, poc_stream,
+                                subsampled_stream)
 
 pytestmark = pytest.mark.gpu
 
@@ -328,6 +329,20 @@ def test_two_layer_frames_vs_oracle(cfg, dec, dec_bitexact):
     if cfg.get("reversible", True) and cfg.get("npasses", 1) == 1:
         img = got.view(np.uint16 if bd > 8 else np.uint8).reshape(h, w, nc)
         assert np.array_equal(img >> ((16 - bd) if bd > 8 else 0), np.stack(planes, -1))
+
+
+@pytest.mark.parametrize("t", POC_STREAMS, ids=lambda t: "-".join("".join(map(str, e)) for e in t["poc"]))
+def test_poc_frames_vs_oracle(t, dec, dec_bitexact):
+    """Progression order changes (POC marker): packets re-sequenced per entry, pixels unchanged."""
+    cs, base = poc_stream(t)
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r, oinfo, want = oracle_decode(cs, bitexact)
+        assert r == 0
+        d = dec_bitexact if bitexact else dec
+        info, got = d.decode(cs)
+        assert (info.width, info.height) == (oinfo[0], oinfo[1])
+        assert np.array_equal(got, want)
+        assert np.array_equal(d.decode(base)[1], want)
 
 
 @pytest.mark.parametrize("name,subs,bd", SUBSAMPLED, ids=[s[0] for s in SUBSAMPLED])

@@ -11,7 +11,9 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import LAYERED, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, subsampled_stream
+from test_oracle_vs_ref import (LAYERED, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, poc_marker_cases,
+                                poc_stream,
+                                subsampled_stream)
 
 
 def picture_from_plan(cs: bytes, flags: int):
@@ -235,6 +237,27 @@ def test_plan_of_two_layer_streams(cfg):
         assert r == 0
         info, pic = picture_from_plan(cs, fb.FLAG_BITEXACT if bitexact else 0)
         assert np.array_equal(pic, opic)
+
+
+@pytest.mark.parametrize("t", POC_STREAMS, ids=lambda t: "-".join("".join(map(str, e)) for e in t["poc"]))
+def test_plan_of_poc_streams(t):
+    """POC marker: the host parser walks the entries like jpeg2000_decode_packets (jpeg2000dec.c:1835-1869)."""
+    cs, _ = poc_stream(t)
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r, oinfo, opic = oracle_decode(cs, bitexact)
+        assert r == 0
+        info, pic = picture_from_plan(cs, fb.FLAG_BITEXACT if bitexact else 0)
+        assert np.array_equal(pic, opic)
+
+
+def test_poc_marker_validation_matches_oracle():
+    for bad in poc_marker_cases():
+        r, _, opic = oracle_decode(bad)
+        try:
+            _, pic = picture_from_plan(bad, 0)
+            assert r == 0 and np.array_equal(pic, opic)
+        except fb.DecodeError as e:
+            assert r < 0 and e.code < 0
 
 
 @pytest.mark.parametrize("name,subs,bd", SUBSAMPLED, ids=[s[0] for s in SUBSAMPLED])

@@ -204,6 +204,78 @@ def test_two_layer_streams_bit_exact(cfg):
         assert info1[:2] == info2[:2] and oracle_pix_name() == name and np.array_equal(out1, out2)
 
 
+# progression order changes (POC marker in the main header, get_poc jpeg2000dec.c:760-818): every entry is
+# (RSpoc, CSpoc, LYEpoc, REpoc, CEpoc, Ppoc); entries overlap, leave CEpoc 0 (= all) and REpoc 33, and span two segments
+POC_STREAMS = [
+    dict(cfg=dict(levels=3), poc=[(2, 0, 1, 4, 3, 0), (0, 0, 1, 2, 3, 1)]),
+    dict(cfg=dict(levels=3, layers=2, npasses=3), poc=[(0, 0, 1, 4, 3, 1), (0, 0, 2, 4, 3, 4)]),
+    dict(cfg=dict(levels=4, precincts=[(6, 6), (7, 7)], cblk=(32, 32)),
+         poc=[(0, 0, 1, 3, 3, 2), (0, 0, 1, 5, 1, 4), (3, 1, 1, 5, 3, 3)]),
+    dict(cfg=dict(levels=4, precincts=[(6, 6), (7, 7)], cblk=(32, 32), layers=2, npasses=3),
+         poc=[(0, 0, 1, 5, 3, 4), (0, 0, 2, 2, 3, 2), (2, 0, 2, 33, 0, 3)], split=1),
+    dict(cfg=dict(levels=3, tile=(128, 64), sop=True, eph=True), poc=[(1, 0, 1, 4, 3, 1), (0, 0, 1, 1, 3, 0)]),
+    dict(cfg=dict(levels=2, reversible=False, base_step=1.0), poc=[(0, 1, 1, 3, 3, 1), (0, 0, 1, 3, 1, 0)]),
+]
+
+
+def poc_stream(t, w=200, h=120, nc=3, bd=10, seed=4):
+    """-> (the stream with the POC marker, the same picture in the COD progression)"""
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=seed)
+    base = j2kgen.encode(planes, bd, j2kgen.EncParams(**t["cfg"]))
+    cs = j2kgen.encode(planes, bd, j2kgen.EncParams(poc=t["poc"], poc_split=t.get("split", 0), **t["cfg"]))
+    return cs, base
+
+
+@pytest.mark.parametrize("t", POC_STREAMS, ids=lambda t: "-".join("".join(map(str, e)) for e in t["poc"]))
+def test_poc_streams_bit_exact(t):
+    """The reference decodes the re-sequenced stream to the pixels of the plain one (this validates the
+    generator's packet order), and the oracle follows the same entries."""
+    cs, base = poc_stream(t)
+    assert len(cs) > len(base) and cs[cs.index(b"\xff\x93"):] != base[base.index(b"\xff\x93"):]     # re-sequenced
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r0, _, out0, _ = ref_decode(base, bitexact)
+        r1, info1, out1, name = ref_decode(cs, bitexact)
+        r2, info2, out2 = oracle_decode(cs, bitexact)
+        assert r0 == 0 and r1 == 0 and r2 == 0
+        assert np.array_equal(out0, out1)
+        assert info1[:2] == info2[:2] and oracle_pix_name() == name and np.array_equal(out1, out2)
+
+
+def poc_marker_cases():
+    """Bad entries (RSpoc >= REpoc, REpoc > 33, CSpoc >= CEpoc, LYEpoc == 0), a segment length that is not
+    2 + 7n, and more than 32 entries over several segments."""
+    planes = j2kgen.synth_image(64, 48, 3, 8, seed=2)
+    cs = j2kgen.encode(planes, 8, j2kgen.EncParams(levels=2, poc=[(0, 0, 1, 3, 3, 1)]))
+    at = cs.index(b"\xff\x5f")
+    assert cs[at + 2:at + 4] == b"\x00\x09"
+    ent = at + 4
+    cases = []
+    for off, val in ((0, 3), (4, 34), (1, 3), (2, 0), (5, 1), (5, 4), (6, 7), (4, 1), (0, 2)):
+        bad = bytearray(cs)
+        bad[ent + off] = val
+        if off == 2:
+            bad[ent + 3] = 0
+        cases.append(bytes(bad))
+    cases.append(cs[:at + 3] + b"\x0a" + cs[at + 4:at + 11] + b"\x00" + cs[at + 11:])        # one stray byte
+    seg = cs[at:at + 11]
+    cases.append(cs[:at] + seg * 33 + cs[at + 11:])                                          # 33 entries
+    cases.append(cs[:at] + seg * 32 + cs[at + 11:])                                          # exactly 32
+    return cases
+
+
+def test_poc_marker_validation_matches_reference():
+    """get_poc's checks (jpeg2000dec.c:760-818): same verdict as the reference, same pixels where it decodes."""
+    cases = poc_marker_cases()
+    assert len(cases) == 12
+    for bad in cases:
+        r1, _, out1, _ = ref_decode(bad, 0)
+        r2, _, out2 = oracle_decode(bad, 0)
+        assert (r1 == 0) == (r2 == 0), (r1, r2)
+        if r1 == 0:
+            assert np.array_equal(out1, out2)
+    assert sum(ref_decode(bad, 0)[0] == 0 for bad in cases) >= 3
+
+
 # chroma-subsampled streams (XRsiz / YRsiz > 1): (name, [(XRsiz, YRsiz)], bit depth) -> the planar YUV(A) formats
 SUBSAMPLED = [("420", [(1, 1), (2, 2), (2, 2)], 8), ("422", [(1, 1), (2, 1), (2, 1)], 10), ("440", [(1, 1), (1, 2), (1, 2)], 8),
               ("411", [(1, 1), (4, 1), (4, 1)], 8), ("410", [(1, 1), (4, 4), (4, 4)], 8),

@@ -53,6 +53,11 @@ typedef struct J2kGenParams {
                                   * (jpeg2000dec.c:1256-1362) */
     int32_t sub_x[4], sub_y[4];  /* XRsiz / YRsiz per component (0 = 1).  With subsampling: no offset, no component
                                   * transform, LRCP / RLCP only; plane c holds ceil(W/sub_x) x ceil(H/sub_y) samples */
+    int32_t npoc;                /* > 0: a POC marker segment in the main header with these entries; the packets
+                                  * follow them in order, each packet once (the first entry that reaches it).
+                                  * poc_split > 0 puts the first poc_split entries into a POC segment of their own */
+    int32_t poc[8][6];           /* RSpoc, CSpoc, LYEpoc, REpoc, CEpoc, Ppoc */
+    int32_t poc_split;
 } J2kGenParams;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -811,7 +816,78 @@ typedef struct ResLevel {
     int ppx, ppy, npx, npy;
     int nbands;
     Band band[3];
+    int *written;               /* per precinct: layers already sequenced (POC entries may overlap) */
 } ResLevel;
+
+/* one progression over resolutions [RS, RE), components [CS, CE) and layers [0, LYE): the packet order of
+ * T.800 B.12 for that sub-volume.  A packet that an earlier progression already carried is not repeated. */
+static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precno, int layer, int *sop_counter);
+static void sequence_one(Buf *out, const J2kGenParams *P, ResLevel *rl, int precno, int layer, int *sopc)
+{
+    if (!rl->written)
+        rl->written = calloc((size_t)imax(rl->npx * rl->npy, 1), sizeof(int));
+    if (layer < rl->written[precno])
+        return;
+    rl->written[precno] = layer + 1;
+    write_packet(out, P, rl, precno, layer, sopc);
+}
+
+static void sequence_packets(Buf *out, const J2kGenParams *P, ResLevel **res, int C, int L, int tx0, int ty0,
+                             int tx1, int ty1, int RS, int CS, int LYE, int RE, int CE, int prog, int *sopc)
+{
+    RE = imin(RE, L + 1);
+    switch (prog) {
+    case 0: /* LRCP */
+        for (int l = 0; l < LYE; l++)
+            for (int r = RS; r < RE; r++)
+                for (int c = CS; c < CE; c++)
+                    for (int p = 0; p < res[c][r].npx * res[c][r].npy; p++)
+                        sequence_one(out, P, &res[c][r], p, l, sopc);
+        break;
+    case 1: /* RLCP */
+        for (int r = RS; r < RE; r++)
+            for (int l = 0; l < LYE; l++)
+                for (int c = CS; c < CE; c++)
+                    for (int p = 0; p < res[c][r].npx * res[c][r].npy; p++)
+                        sequence_one(out, P, &res[c][r], p, l, sopc);
+        break;
+    case 2: /* RPCL (components share one sampling grid here) */
+        for (int r = RS; r < RE; r++)
+            for (int p = 0; p < res[0][r].npx * res[0][r].npy; p++)
+                for (int c = CS; c < CE; c++)
+                    for (int l = 0; l < LYE; l++)
+                        sequence_one(out, P, &res[c][r], p, l, sopc);
+        break;
+    case 3: /* PCRL: positions ordered by their top-left corner on the reference grid */
+    case 4: /* CPRL */
+        for (int cc = (prog == 4 ? CS : 0); cc < (prog == 4 ? CE : 1); cc++) {
+            /* walk reference-grid positions at the finest precinct granularity */
+            int minx = 30, miny = 30;
+            for (int r = 0; r <= L; r++) {
+                minx = imin(minx, res[0][r].ppx + L - r);
+                miny = imin(miny, res[0][r].ppy + L - r);
+            }
+            int sx = 1 << imin(minx, 30), sy = 1 << imin(miny, 30);
+            for (int y = ty0; y < ty1; y = (y / sy + 1) * sy)
+                for (int x = tx0; x < tx1; x = (x / sx + 1) * sx)
+                    for (int c = (prog == 4 ? cc : CS); c < (prog == 4 ? cc + 1 : CE); c++)
+                        for (int r = RS; r < RE; r++) {
+                            ResLevel *rl = &res[c][r];
+                            int nl = L - r;
+                            if (!rl->npx || !rl->npy) continue;
+                            int okx = (x % (1 << (rl->ppx + nl)) == 0) || (x == tx0 && ((rl->x0 << nl) % (1 << (rl->ppx + nl))));
+                            int oky = (y % (1 << (rl->ppy + nl)) == 0) || (y == ty0 && ((rl->y0 << nl) % (1 << (rl->ppy + nl))));
+                            if (!okx || !oky) continue;
+                            int pxi = (ceildivpow2(x, nl) >> rl->ppx) - (rl->x0 >> rl->ppx);
+                            int pyi = (ceildivpow2(y, nl) >> rl->ppy) - (rl->y0 >> rl->ppy);
+                            if (pxi < 0 || pyi < 0 || pxi >= rl->npx || pyi >= rl->npy) continue;
+                            for (int l = 0; l < LYE; l++)
+                                sequence_one(out, P, rl, pxi + pyi * rl->npx, l, sopc);
+                        }
+        }
+        break;
+    }
+}
 
 /* the decoder's step size for a band: libavcodec/jpeg2000.c:214-272 (float path), same op order */
 static float decoder_stepsize(int cbps, int expn, int mant, int bandpos, int nres, int reslevelno)
@@ -1045,6 +1121,19 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
             }
         }
     }
+    if (P->npoc > 0) {
+        if (P->npoc > 8) { P->error = 4; return -4; }
+        int first = P->poc_split > 0 && P->poc_split < P->npoc ? P->poc_split : P->npoc;
+        for (int a = 0; a < P->npoc; ) {
+            int n = a == 0 ? first : P->npoc - a;
+            buf_put16(&out, 0xFF5F); buf_put16(&out, 2 + 7 * n);
+            for (int i = a; i < a + n; i++) {
+                buf_put(&out, P->poc[i][0]); buf_put(&out, P->poc[i][1]); buf_put16(&out, P->poc[i][2]);
+                buf_put(&out, P->poc[i][3]); buf_put(&out, P->poc[i][4]); buf_put(&out, P->poc[i][5]);
+            }
+            a += n;
+        }
+    }
 
     /* ---- tiles ---- */
     for (int ty = 0; ty < nty; ty++)
@@ -1213,57 +1302,13 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
             int sopc = 0;
             int maxnp = 0;
             for (int c = 0; c < C; c++) for (int r = 0; r <= L; r++) maxnp = imax(maxnp, res[c][r].npx * res[c][r].npy);
-            switch (P->prog) {
-            case 0: /* LRCP */
-                for (int l = 0; l < NLAY; l++)
-                    for (int r = 0; r <= L; r++)
-                        for (int c = 0; c < C; c++)
-                            for (int p = 0; p < res[c][r].npx * res[c][r].npy; p++)
-                                write_packet(&out, P, &res[c][r], p, l, &sopc);
-                break;
-            case 1: /* RLCP */
-                for (int r = 0; r <= L; r++)
-                    for (int l = 0; l < NLAY; l++)
-                        for (int c = 0; c < C; c++)
-                            for (int p = 0; p < res[c][r].npx * res[c][r].npy; p++)
-                                write_packet(&out, P, &res[c][r], p, l, &sopc);
-                break;
-            case 2: /* RPCL */
-                for (int r = 0; r <= L; r++)
-                    for (int p = 0; p < res[0][r].npx * res[0][r].npy; p++)
-                        for (int c = 0; c < C; c++)
-                            for (int l = 0; l < NLAY; l++)
-                                write_packet(&out, P, &res[c][r], p, l, &sopc);
-                break;
-            case 3: /* PCRL: positions ordered by their top-left corner on the reference grid */
-            case 4: /* CPRL */ {
-                for (int cc = 0; cc < (P->prog == 4 ? C : 1); cc++) {
-                    /* walk reference-grid positions at the finest precinct granularity */
-                    int minx = 30, miny = 30;
-                    for (int r = 0; r <= L; r++) {
-                        minx = imin(minx, res[0][r].ppx + L - r);
-                        miny = imin(miny, res[0][r].ppy + L - r);
-                    }
-                    int sx = 1 << imin(minx, 30), sy = 1 << imin(miny, 30);
-                    for (int y = ty0; y < ty1; y = (y / sy + 1) * sy)
-                        for (int x = tx0; x < tx1; x = (x / sx + 1) * sx)
-                            for (int c = (P->prog == 4 ? cc : 0); c < (P->prog == 4 ? cc + 1 : C); c++)
-                                for (int r = 0; r <= L; r++) {
-                                    ResLevel *rl = &res[c][r];
-                                    int nl = L - r;
-                                    if (!rl->npx || !rl->npy) continue;
-                                    int okx = (x % (1 << (rl->ppx + nl)) == 0) || (x == tx0 && ((rl->x0 << nl) % (1 << (rl->ppx + nl))));
-                                    int oky = (y % (1 << (rl->ppy + nl)) == 0) || (y == ty0 && ((rl->y0 << nl) % (1 << (rl->ppy + nl))));
-                                    if (!okx || !oky) continue;
-                                    int pxi = (ceildivpow2(x, nl) >> rl->ppx) - (rl->x0 >> rl->ppx);
-                                    int pyi = (ceildivpow2(y, nl) >> rl->ppy) - (rl->y0 >> rl->ppy);
-                                    if (pxi < 0 || pyi < 0 || pxi >= rl->npx || pyi >= rl->npy) continue;
-                                    for (int l = 0; l < NLAY; l++)
-                                        write_packet(&out, P, rl, pxi + pyi * rl->npx, l, &sopc);
-                                }
-                }
-                break;
-            }
+            if (P->npoc > 0) {
+                for (int i = 0; i < P->npoc; i++)
+                    sequence_packets(&out, P, res, C, L, tx0, ty0, tx1, ty1, P->poc[i][0], P->poc[i][1],
+                                     imin(P->poc[i][2], NLAY), P->poc[i][3], P->poc[i][4] ? imin(P->poc[i][4], C) : C,
+                                     P->poc[i][5], &sopc);
+            } else {
+                sequence_packets(&out, P, res, C, L, tx0, ty0, tx1, ty1, 0, 0, NLAY, L + 1, C, P->prog, &sopc);
             }
             uint32_t psot = (uint32_t)(out.n - sot_pos);
             out.p[sot_pos + 6] = psot >> 24; out.p[sot_pos + 7] = psot >> 16;
@@ -1282,6 +1327,7 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
                         }
                         free(bd->prec);
                     }
+                for (int r = 0; r <= L; r++) free(res[c][r].written);
                 free(res[c]);
                 free(tp[c]);
             }

@@ -30,6 +30,7 @@ class _Params(ctypes.Structure):
         ("x_off", ctypes.c_int32), ("y_off", ctypes.c_int32), ("stats_blocks", ctypes.c_int32),
         ("stats_max_lcup", ctypes.c_int32), ("error", ctypes.c_int32),
         ("layers", ctypes.c_int32), ("sub_x", ctypes.c_int32 * 4), ("sub_y", ctypes.c_int32 * 4),
+        ("npoc", ctypes.c_int32), ("poc", (ctypes.c_int32 * 6) * 8), ("poc_split", ctypes.c_int32),
     ]
 
 
@@ -73,6 +74,8 @@ class EncParams:
     offset: tuple = (0, 0)
     layers: int = 1               # 2: blocks spread over two quality layers (split HT sets, late inclusion, placeholders)
     subsampling: list | None = None   # [(XRsiz, YRsiz)] per component; plane c is ceil(W/XRsiz) x ceil(H/YRsiz)
+    poc: list | None = None       # [(RSpoc, CSpoc, LYEpoc, REpoc, CEpoc, Ppoc)]: POC marker; packets follow the entries
+    poc_split: int = 0            # > 0: the first poc_split entries go into a POC segment of their own
     stats: dict = field(default_factory=dict)
 
 
@@ -104,6 +107,12 @@ def encode(planes, bitdepth: int, p: EncParams) -> bytes:
         if p.subsampling:
             for c, (sx, sy) in enumerate(p.subsampling):
                 P.sub_x[c], P.sub_y[c] = sx, sy
+        if p.poc:
+            P.npoc = len(p.poc)
+            P.poc_split = p.poc_split
+            for i, e in enumerate(p.poc):
+                for k in range(6):
+                    P.poc[i][k] = e[k]
         cap = int(w * h * len(planes) * 4 + (1 << 20))
         out = np.empty(cap, np.uint8)
         ptrs = (ctypes.c_void_p * len(planes))(*[a.ctypes.data for a in planes])
