@@ -19,6 +19,8 @@
  * 9/7 arithmetic exactly as idwt.cu.  Geometry the fast path does not cover (odd origins, unaligned
  * strides, one-sample lines, 8-bit or planar output) stays on idwt.cu; launch_idwt_frame picks per launch.
  */
+#include <cstdlib>
+
 #include "idwt_common.cuh"
 
 namespace b200j2k {
@@ -49,6 +51,9 @@ template <> struct VecIO<2> {
 #ifndef STREAM_MINB
 #define STREAM_MINB 5
 #endif
+#ifndef STREAM_EXP
+#define STREAM_EXP 0
+#endif
 #ifndef STREAM_WANT
 #define STREAM_WANT 20
 #endif
@@ -70,8 +75,42 @@ template <> __device__ __forceinline__ void lds_vec<2>(uint32_t addr, uint32_t (
 {
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr) : "memory");
 }
-/* bytes of staging shared memory per warp */
-template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_warp() { return STAGES * 4 * NC * 32 * NP * 4; }
+/* Bulk-copy staging (interior strips).  ncu + tools/membench.cu: per-lane loads of this row pattern -- LDG or
+ * cp.async alike -- are bounded by the L1 miss path (the kernel slows from 44 to 59 us when the shared-memory
+ * carve-out leaves L1 small; 113 MB arrive in ~35 us), while the same rows fetched by the TMA engine with
+ * cp.async.bulk arrive in ~22 us whatever the carve-out.  So lane 0 of a warp fetches the warp's 32 x NP
+ * columns of each of the 4 NC row streams with ONE bulk copy per stream into the warp's private slots and
+ * an mbarrier per stage counts the bytes in.  Bulk copies need 16-byte aligned addresses: with NP = 2 the
+ * warp's first column sits at 8 mod 16 bytes, so the copy starts PADE = 2 elements early. */
+template <int NP> struct Bulk {
+    static constexpr int PADE = (4 - NP % 4) % 4;                         /* elements in front of lane 0's */
+    static constexpr uint32_t SLOT = 32 * NP * 4 + (PADE ? 16 : 0);       /* bytes per stream and stage */
+};
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+/* bytes of staging shared memory per warp (the bulk layout is the larger one; border strips use per-lane
+ * cp.async slots inside the same region), and of the CTA: SWARPS regions + two mbarriers per warp */
+template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_warp() { return STAGES * 4 * NC * (int)Bulk<NP>::SLOT; }
+template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_cta() { return SWARPS * stage_bytes_per_warp<NP, NC>() + SWARPS * STAGES * 8; }
 
 /* horizontal synthesis of NP (low, high) pairs per lane; x[2k] = even sample, x[2k+1] = odd sample */
 template <int TYPE, int NP>
@@ -209,18 +248,27 @@ __device__ __forceinline__ int row_ky(const StripGeo &g, int Y)
 }
 
 /* The streaming core: walks row pairs (even row = vertical low-pass, odd row = vertical high-pass), keeps the
- * vertical lifting state in registers and calls emit(Y, rows[NC][2NP]) for every finished output row.  The
- * loop is unrolled by two with the state ping-ponging between two register sets, so the sliding window never
- * costs a register move. */
-template <int TYPE, int NP, int NC, class Emit>
-__device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *(&A)[NC], const uint32_t *(&LL)[NC],
-                                            const LaneCols<NP> &lc, int Ya, int Yb, uint32_t stage_base, Emit &&emit)
+ * vertical lifting state in registers and calls emit(allin, Y, rows[NC][2NP]) for every finished output row.
+ * The loop is unrolled by two with the state ping-ponging between two register sets, so the sliding window
+ * never costs a register move, and the staging slot of a step is a compile-time constant (STAGES == 2).
+ * ALLIN: every lane of the warp lies inside the line (no column needs reflection) -- the common case, kept
+ * free of per-lane branches; the other instantiation serves the first and last strip of a line.
+ * Addressing (ncu: the first version spent ~190 of its ~700 instructions per row pair re-deriving twelve
+ * 64-bit addresses): the lane keeps one pointer per component into the LL source and one into the plane
+ * (at its column of the HL band); a row pair contributes four element offsets shared by all components. */
+template <int TYPE, int NP, int NC, bool ALLIN, class Emit>
+__device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *__restrict__ baseA,
+                                            const uint32_t *__restrict__ baseL, const uint32_t (&offA)[NC],
+                                            const uint32_t (&offL)[NC], const LaneCols<NP> &lc, int Ya, int Yb,
+                                            uint32_t warp_base, uint32_t bar_base, Emit &&emit)
 {
     using L = Lift<TYPE>;
     constexpr int HP = L::HALO / 2;
     constexpr int C2 = 2 * NP;
     constexpr int NV = 4 * NC;
-    constexpr uint32_t VSTRIDE = 32 * NP * 4, SSTRIDE = NV * VSTRIDE;
+    constexpr uint32_t VSTRIDE = ALLIN ? Bulk<NP>::SLOT : 32 * NP * 4, SSTRIDE = NV * VSTRIDE;
+    constexpr int PADE = Bulk<NP>::PADE;
+    const int lane = threadIdx.x & 31;
     VState<TYPE, NC, C2> S0, S1;
 #pragma unroll
     for (int c = 0; c < NC; c++)
@@ -232,44 +280,74 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *(
         }
     const int n0 = (Ya >> 1) - HP, n1 = (Yb >> 1) + HP;     /* iterations [n0, n1) */
     const int Ylo = max(Ya, g.v0), Yhi = min(Yb, g.v1);     /* rows this warp emits */
-    /* the four quadrant streams of every component, already offset to this lane's first column */
-    const uint32_t *pLL[NC], *pHL[NC], *pLH[NC], *pHH[NC];
+    const bool fast = ALLIN || lc.inside;
+    /* element offsets (from the kernel-uniform bases) of the lane's first column in the LL source and in the
+     * HL band of the plane; 32-bit on purpose: twelve 64-bit lane pointers do not fit the register budget */
+    uint32_t eL[NC], eA[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        pLL[c] = LL[c] + lc.vcolL;
-        pHL[c] = A[c] + g.nLh + lc.vcolH;
-        pLH[c] = A[c] + (size_t)g.nLv * g.W + lc.vcolL;
-        pHH[c] = A[c] + (size_t)g.nLv * g.W + g.nLh + lc.vcolH;
+        eL[c] = offL[c] + (uint32_t)lc.vcolL;
+        eA[c] = offA[c] + (uint32_t)(g.nLh + lc.vcolH);
     }
-    /* Asynchronous staging: every lane owns NV vector slots per stage in shared memory and fills them with
-     * cp.async STAGES-1 iterations ahead, so the bytes in flight do not cost registers.  A lane only ever
-     * reads back its own slots: no barrier, no bank conflicts.  Border lanes (columns that need reflection)
-     * load synchronously when the row pair is consumed. */
-    auto issue = [&](int n) {
-        if (n < n1 && lc.inside) {
+    const uint32_t dLH = (uint32_t)(lc.vcolL - lc.vcolH - g.nLh);   /* LH column relative to the HH column */
+    /* where copies land (stage_base) and where the lane reads its NP elements of a stream back (lane_base) */
+    const uint32_t stage_base = ALLIN ? warp_base : warp_base + (uint32_t)lane * (NP * 4);
+    const uint32_t lane_base = warp_base + (uint32_t)lane * (NP * 4) + (ALLIN ? PADE * 4 : 0);
+    /* Asynchronous staging, one row pair ahead, so the bytes in flight do not cost registers.  Interior
+     * strips: bulk copies by lane 0 (see Bulk<>), completion through the stage's mbarrier.  Border strips:
+     * every inside lane fills its own NV vector slots with cp.async; lanes whose columns need reflection
+     * load synchronously when the row pair is consumed.  A lane only ever reads back its own bytes. */
+    auto issue = [&](int n, uint32_t st, uint32_t bar) {
+        if (n < n1 && fast) {
             /* band_index() of rows 2n / 2n+1 is n - ceil(v0/2) / n - floor(v0/2) unless a row needs reflection */
             int kyE = n - g.eoffv, kyO = n - g.ooffv;
-            if (2 * n < g.v0 || 2 * n >= g.v1)
+            if (2 * n < g.v0 || 2 * n + 1 >= g.v1) {
                 kyE = row_ky(g, 2 * n);
-            if (2 * n + 1 < g.v0 || 2 * n + 1 >= g.v1)
                 kyO = row_ky(g, 2 * n + 1);
-            const uint32_t st = stage_base + (uint32_t)((n - n0) % STAGES) * SSTRIDE;
+            }
+            const uint32_t oLL = (uint32_t)(kyE * g.LLstride), oHL = (uint32_t)(kyE * g.W);
+            const uint32_t oHH = (uint32_t)((g.nLv + kyO) * g.W), oLH = oHH + dLH;
+            if (ALLIN) {
+                __syncwarp();                    /* every lane is done with the slots this refills */
+                if (lane == 0) {
+                    mbar_expect_tx(bar, NV * VSTRIDE);
 #pragma unroll
-            for (int c = 0; c < NC; c++) {
-                cp_async_vec<NP>(st + (4 * c + 0) * VSTRIDE, pLL[c] + kyE * g.LLstride);
-                cp_async_vec<NP>(st + (4 * c + 1) * VSTRIDE, pHL[c] + kyE * g.W);
-                cp_async_vec<NP>(st + (4 * c + 2) * VSTRIDE, pLH[c] + kyO * g.W);
-                cp_async_vec<NP>(st + (4 * c + 3) * VSTRIDE, pHH[c] + kyO * g.W);
+                    for (int c = 0; c < NC; c++) {
+                        bulk_g2s(st + (4 * c + 0) * VSTRIDE, baseL + (eL[c] + oLL - PADE), VSTRIDE, bar);
+                        bulk_g2s(st + (4 * c + 1) * VSTRIDE, baseA + (eA[c] + oHL - PADE), VSTRIDE, bar);
+                        bulk_g2s(st + (4 * c + 2) * VSTRIDE, baseA + (eA[c] + oLH - PADE), VSTRIDE, bar);
+                        bulk_g2s(st + (4 * c + 3) * VSTRIDE, baseA + (eA[c] + oHH - PADE), VSTRIDE, bar);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < NC; c++) {
+                    cp_async_vec<NP>(st + (4 * c + 0) * VSTRIDE, baseL + (eL[c] + oLL));
+                    cp_async_vec<NP>(st + (4 * c + 1) * VSTRIDE, baseA + (eA[c] + oHL));
+                    cp_async_vec<NP>(st + (4 * c + 2) * VSTRIDE, baseA + (eA[c] + oLH));
+                    cp_async_vec<NP>(st + (4 * c + 3) * VSTRIDE, baseA + (eA[c] + oHH));
+                }
             }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (!ALLIN)
+            asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    int slot = 0;                                /* staging slot of the row pair consumed next, and the parity */
+    uint32_t phase = 0;                          /* of its mbarrier: flips every time the ring wraps */
     auto step = [&](int n, const VState<TYPE, NC, C2> &in, VState<TYPE, NC, C2> &out) {
-        issue(n + STAGES - 1);
-        asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        const uint32_t st = lane_base + (uint32_t)slot * SSTRIDE;
+        const int prev = slot == 0 ? STAGES - 1 : slot - 1;             /* consumed by the previous step */
+        issue(n + STAGES - 1, stage_base + (uint32_t)prev * SSTRIDE, bar_base + (uint32_t)prev * 8);
+        if (ALLIN)
+            mbar_wait(bar_base + (uint32_t)slot * 8, phase);
+        else
+            asm volatile("cp.async.wait_group %0;" ::"n"(STAGES - 1) : "memory");
+        if (++slot == STAGES) {
+            slot = 0;
+            phase ^= 1;
+        }
         uint32_t cLe[NC][NP], cHe[NC][NP], cLo[NC][NP], cHo[NC][NP];
-        if (lc.inside) {
-            const uint32_t st = stage_base + (uint32_t)((n - n0) % STAGES) * SSTRIDE;
+        if (fast) {
 #pragma unroll
             for (int c = 0; c < NC; c++) {
                 lds_vec<NP>(st + (4 * c + 0) * VSTRIDE, cLe[c]);
@@ -282,12 +360,26 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *(
             row_offsets(g, 2 * n, oL, oH);
 #pragma unroll
             for (int c = 0; c < NC; c++)
-                load_row<NP>(oL >= 0 ? LL[c] + oL : A[c] + ~oL, A[c] + oH, lc, cLe[c], cHe[c]);
+                load_row<NP>(oL >= 0 ? baseL + offL[c] + oL : baseA + offA[c] + ~oL, baseA + offA[c] + oH, lc, cLe[c], cHe[c]);
             row_offsets(g, 2 * n + 1, oL, oH);
 #pragma unroll
             for (int c = 0; c < NC; c++)
-                load_row<NP>(oL >= 0 ? LL[c] + oL : A[c] + ~oL, A[c] + oH, lc, cLo[c], cHo[c]);
+                load_row<NP>(oL >= 0 ? baseL + offL[c] + oL : baseA + offA[c] + ~oL, baseA + offA[c] + oH, lc, cLo[c], cHo[c]);
         }
+#if STREAM_EXP == 1                              /* tuning experiment: loads only */
+        {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int k = 0; k < NP; k++)
+                    acc ^= cLe[c][k] + cHe[c][k] + cLo[c][k] + cHo[c][k];
+            out.vh[0][0] = in.vh[0][0] ^ acc;
+            if (n == n1 - 1 && out.vh[0][0] == 0x12345678u)
+                emit(ALLIN, Ylo, out.e1);
+            return;
+        }
+#endif
         uint32_t rowA[NC][C2];                   /* finished odd row 2n-(2HP-1); the even row 2n-(2HP-2) is out.e1 / out.e2 */
 #pragma unroll
         for (int c = 0; c < NC; c++) {
@@ -307,19 +399,32 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *(
                 }
             }
         }
+#if STREAM_EXP == 2                              /* tuning experiment: loads + arithmetic, no stores */
+        {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < NC; c++)
+#pragma unroll
+                for (int k = 0; k < C2; k++)
+                    acc ^= rowA[c][k];
+            if (acc == 0x12345678u && n == n1 - 1)
+                emit(ALLIN, Ylo, rowA);
+            return;
+        }
+#endif
         const int YA = 2 * n - (2 * HP - 1), YB = YA + 1;
         if (YA >= Ylo && YA < Yhi)
-            emit(YA, rowA);
+            emit(ALLIN, YA, rowA);
         if (YB >= Ylo && YB < Yhi) {
             if constexpr (TYPE == J2K_DWT53)
-                emit(YB, out.e1);
+                emit(ALLIN, YB, out.e1);
             else
-                emit(YB, out.e2);
+                emit(ALLIN, YB, out.e2);
         }
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++)
-        issue(n0 + s);
+        issue(n0 + s, stage_base + (uint32_t)s * SSTRIDE, bar_base + (uint32_t)s * 8);
     int n = n0;
     for (; n + 1 < n1; n += 2) {
         step(n, S0, S1);
@@ -350,18 +455,18 @@ idwt_stream_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint
         return;
     const int p0 = (XA >> 1) + lane * NP;
     const LaneCols<NP> lc = make_cols<NP>(g, p0);
-    const uint32_t *A[1] = { coefA + tc.coef_off };
-    const uint32_t *LL[1] = { j == 0 ? A[0] : coefIn + tc.coef_off };
+    const uint32_t offA[1] = { (uint32_t)tc.coef_off }, offL[1] = { (uint32_t)tc.coef_off };
+    const uint32_t *baseL = j == 0 ? coefA : coefIn;
     uint32_t *out = coefOut + tc.coef_off;
     const int lh = g.u1 - g.u0;
     const int X0 = 2 * p0;
     const bool lane_ok = lane >= 1 && lane <= 30;
     uint32_t *out_base = out + (X0 - g.u0) - (long)g.v0 * lh;
-    auto emit = [&](int Y, const uint32_t (&row)[1][C2]) {
+    auto emit = [&](bool allin, int Y, const uint32_t (&row)[1][C2]) {
         if (!lane_ok)
             return;
         uint32_t *o = out_base + (long)Y * lh;
-        if (lc.inside) {
+        if (allin || lc.inside) {
             if (NP == 4) {
                 reinterpret_cast<uint4 *>(o)[0] = make_uint4(row[0][0], row[0][1], row[0][2], row[0][3]);
                 reinterpret_cast<uint4 *>(o)[1] = make_uint4(row[0][4], row[0][5], row[0][6], row[0][7]);
@@ -375,9 +480,21 @@ idwt_stream_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint
                     o[k] = row[0][k];
         }
     };
-    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage_smem) + warp * stage_bytes_per_warp<NP, 1>() +
-                                lane * (NP * 4);
-    stream_rows<TYPE, NP, 1>(g, A, LL, lc, Ya, Yb, stage_base, emit);
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(stage_smem);
+    const uint32_t bar_base = smem0 + warp * (STAGES * 8);
+    const uint32_t warp_base = smem0 + SWARPS * STAGES * 8 + warp * stage_bytes_per_warp<NP, 1>();
+    const bool allin = __all_sync(FULLMASK, lc.inside);
+    if (allin && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; i++)
+            mbar_init(bar_base + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (allin)
+        stream_rows<TYPE, NP, 1, true>(g, coefA, baseL, offA, offL, lc, Ya, Yb, warp_base, bar_base, emit);
+    else
+        stream_rows<TYPE, NP, 1, false>(g, coefA, baseL, offA, offL, lc, Ya, Yb, warp_base, bar_base, emit);
 }
 
 /* ---- last level fused with MCT + level shift + clip + pack (packed 16-bit output) ---------------------- */
@@ -406,14 +523,13 @@ idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *
         return;
     const int p0 = (XA >> 1) + lane * NP;
     const LaneCols<NP> lc = make_cols<NP>(g, p0);
-    const uint32_t *in = ((nl - 1) & 1) ? coefIn0 : coefIn1;
-    const uint32_t *A[NC], *LL[NC];
+    const uint32_t *baseL = nl == 1 ? coefA : ((nl - 1) & 1) ? coefIn0 : coefIn1;
+    uint32_t offA[NC], offL[NC];
     int cbps[NC], shift[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         const TileCompDesc &tc = tcs[gr.tc[c]];
-        A[c] = coefA + tc.coef_off;
-        LL[c] = nl == 1 ? A[c] : in + tc.coef_off;
+        offA[c] = offL[c] = (uint32_t)tc.coef_off;
         cbps[c] = tc.cbps;
         shift[c] = gr.shift[c];
     }
@@ -425,16 +541,14 @@ idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *
     const bool lane_ok = lane >= 1 && lane <= 30;
     const long px = (long)(t0.out_x + X0 - g.u0) * NC;       /* sample index of the lane's first pixel */
     int half[NC], vmax[NC];
-    bool same_shift = true;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
         half[c] = 1 << (cbps[c] - 1);
         vmax[c] = (1 << cbps[c]) - 1;
-        same_shift = same_shift && shift[c] == shift[0];
     }
     /* byte address of this lane's first sample in output row Y = out_base + Y * rb */
     uint8_t *out_base = plane + ((long)t0.out_y - g.v0) * rb + 2 * px;
-    auto emit = [&](int Y, const uint32_t (&row)[NC][C2]) {
+    auto emit = [&](bool allin, int Y, const uint32_t (&row)[NC][C2]) {
         if (!lane_ok)
             return;
         uint32_t pix[NC][C2];                    /* level-shifted and clipped, not yet left-aligned */
@@ -456,16 +570,14 @@ idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *
             }
         }
         uint16_t *r16 = reinterpret_cast<uint16_t *>(out_base + (long)Y * rb);
-        if (lc.inside) {
+        if (allin || lc.inside) {
             /* 2NP pixels x NC samples x 16 bit: 16-byte (NP = 4) or 8-byte (NP = 2) aligned by construction */
             uint32_t w[NC * NP];
 #pragma unroll
             for (int i = 0; i < NC * NP; i++) {
                 const int s0 = 2 * i, s1 = 2 * i + 1;            /* sample indices inside the lane's run */
-                if (same_shift)
-                    w[i] = __byte_perm(pix[s0 % NC][s0 / NC], pix[s1 % NC][s1 / NC], 0x5410) << shift[0];
-                else
-                    w[i] = (pix[s0 % NC][s0 / NC] << shift[s0 % NC]) | (pix[s1 % NC][s1 / NC] << (16 + shift[s1 % NC]));
+                /* all components share one shift on this path (idwt_stream_final_ok) */
+                w[i] = __byte_perm(pix[s0 % NC][s0 / NC], pix[s1 % NC][s1 / NC], 0x5410) << shift[0];
             }
             if (NP == 4) {
                 uint4 *o = reinterpret_cast<uint4 *>(r16);
@@ -487,9 +599,21 @@ idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *
                         r16[k * NC + c] = (uint16_t)(pix[c][k] << shift[c]);
         }
     };
-    const uint32_t stage_base = (uint32_t)__cvta_generic_to_shared(stage_smem) + warp * stage_bytes_per_warp<NP, NC>() +
-                                lane * (NP * 4);
-    stream_rows<TYPE, NP, NC>(g, A, LL, lc, Ya, Yb, stage_base, emit);
+    const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(stage_smem);
+    const uint32_t bar_base = smem0 + warp * (STAGES * 8);
+    const uint32_t warp_base = smem0 + SWARPS * STAGES * 8 + warp * stage_bytes_per_warp<NP, NC>();
+    const bool allin = __all_sync(FULLMASK, lc.inside);
+    if (allin && lane == 0) {
+#pragma unroll
+        for (int i = 0; i < STAGES; i++)
+            mbar_init(bar_base + 8 * i, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    if (allin)
+        stream_rows<TYPE, NP, NC, true>(g, coefA, baseL, offA, offL, lc, Ya, Yb, warp_base, bar_base, emit);
+    else
+        stream_rows<TYPE, NP, NC, false>(g, coefA, baseL, offA, offL, lc, Ya, Yb, warp_base, bar_base, emit);
 }
 
 template <int TYPE> struct StreamCfg {
@@ -563,6 +687,8 @@ bool idwt_stream_final_ok(const IdwtFrame &f, int type, int *ncomp)
             const TileCompDesc &tc = f.h_tcs[g.tc[c]];
             if (g.sample_off[c] != c || tc.nlevels != t0.nlevels || !level_streamable(tc, tc.nlevels - 1))
                 return false;
+            if (g.shift[c] != g.shift[0] || tc.width != t0.width)
+                return false;
             const LevelDesc &a = tc.lev[tc.nlevels], &b = t0.lev[t0.nlevels];
             if (a.u0 != b.u0 || a.u1 != b.u1 || a.v0 != b.v0 || a.v1 != b.v1)
                 return false;
@@ -583,7 +709,7 @@ int launch_idwt_stream_level(cudaStream_t stream, int type, const IdwtFrame &f, 
         const int strips = (max_w + 1 + VALID - 1) / VALID;                                                    \
         const int seg = pick_seg(strips, f.ntcs, max_h), segs = (max_h + 1 + seg - 1) / seg;                   \
         dim3 grid((strips * segs + SWARPS - 1) / SWARPS, f.ntcs);                                              \
-        constexpr int sm = SWARPS * stage_bytes_per_warp<NP, 1>();                                             \
+        constexpr int sm = stage_bytes_per_cta<NP, 1>();                                                    \
         static bool attr = false;                                                                              \
         if (!attr) {                                                                                           \
             cudaFuncSetAttribute(idwt_stream_level_kernel<T, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
@@ -607,8 +733,10 @@ int launch_idwt_stream_final(cudaStream_t stream, int type, int ncomp, const Idw
         const int strips = (max_w + 1 + VALID - 1) / VALID;                                                    \
         const int seg = pick_seg(strips, f.ngroups, max_h), segs = (max_h + 1 + seg - 1) / seg;                \
         dim3 grid((strips * segs + SWARPS - 1) / SWARPS, f.ngroups);                                           \
-        constexpr int sm = SWARPS * stage_bytes_per_warp<NP, NC>();                                            \
+        constexpr int sm = stage_bytes_per_cta<NP, NC>();                                                   \
         cudaFuncSetAttribute(idwt_stream_final_kernel<T, NP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
+        if (getenv("B200J2K_CARVEOUT"))                                                                        \
+            cudaFuncSetAttribute(idwt_stream_final_kernel<T, NP, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("B200J2K_CARVEOUT"))); \
         idwt_stream_final_kernel<T, NP, NC><<<grid, SWARPS * 32, sm, stream>>>(                                \
             f.d_tcs, f.d_groups, (const uint32_t *)f.coefA, (const uint32_t *)f.coefB, (const uint32_t *)f.coefC, \
             f.picture, f.plane_off[0], f.plane_off[1], f.plane_off[2], f.plane_off[3], f.plane_row_bytes[0],   \
