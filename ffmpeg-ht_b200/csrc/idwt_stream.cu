@@ -19,8 +19,6 @@
  * 9/7 arithmetic exactly as idwt.cu.  Geometry the fast path does not cover (odd origins, unaligned
  * strides, one-sample lines, 8-bit or planar output) stays on idwt.cu; launch_idwt_frame picks per launch.
  */
-#include <cstdlib>
-
 #include "idwt_common.cuh"
 
 namespace b200j2k {
@@ -54,8 +52,8 @@ template <> struct VecIO<2> {
 #ifndef STREAM_EXP
 #define STREAM_EXP 0
 #endif
-#ifndef STREAM_WANT
-#define STREAM_WANT 20
+#ifndef STREAM_FILL
+#define STREAM_FILL 100                   /* percent of the one-wave capacity the grid may use */
 #endif
 constexpr int STAGES = STREAM_STAGES;     /* row pairs in flight per warp (cp.async groups) */
 
@@ -102,10 +100,44 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+#ifndef STREAM_HINT
+#define STREAM_HINT 1
+#endif
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
+#if STREAM_HINT
+    /* the coefficients are read exactly once: let them leave L2 first, the picture written here is read next */
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+#else
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+#endif
+}
+/* the four row streams of one component in one statement: one elected-thread wrapper and one set of uniform
+ * operands for the destination base, the size and the barrier instead of four */
+template <uint32_t STRIDE>
+__device__ __forceinline__ void bulk_g2s_x4(uint32_t dst, const void *s0, const void *s1, const void *s2, const void *s3, uint32_t bar)
+{
+#if STREAM_HINT
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %5, [%6], %7;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0+%5], [%2], %5, [%6], %7;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0+%8], [%3], %5, [%6], %7;\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0+%9], [%4], %5, [%6], %7;"
+        ::"r"(dst), "l"(s0), "l"(s1), "l"(s2), "l"(s3), "n"(STRIDE), "r"(bar), "l"(pol), "n"(2 * STRIDE), "n"(3 * STRIDE) : "memory");
+#else
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %5, [%6];\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0+%5], [%2], %5, [%6];\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0+%7], [%3], %5, [%6];\n"
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0+%8], [%4], %5, [%6];"
+        ::"r"(dst), "l"(s0), "l"(s1), "l"(s2), "l"(s3), "n"(STRIDE), "r"(bar), "n"(2 * STRIDE), "n"(3 * STRIDE) : "memory");
+#endif
 }
 /* bytes of staging shared memory per warp (the bulk layout is the larger one; border strips use per-lane
  * cp.async slots inside the same region), and of the CTA: SWARPS regions + two mbarriers per warp */
@@ -312,12 +344,9 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *_
                 if (lane == 0) {
                     mbar_expect_tx(bar, NV * VSTRIDE);
 #pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        bulk_g2s(st + (4 * c + 0) * VSTRIDE, baseL + (eL[c] + oLL - PADE), VSTRIDE, bar);
-                        bulk_g2s(st + (4 * c + 1) * VSTRIDE, baseA + (eA[c] + oHL - PADE), VSTRIDE, bar);
-                        bulk_g2s(st + (4 * c + 2) * VSTRIDE, baseA + (eA[c] + oLH - PADE), VSTRIDE, bar);
-                        bulk_g2s(st + (4 * c + 3) * VSTRIDE, baseA + (eA[c] + oHH - PADE), VSTRIDE, bar);
-                    }
+                    for (int c = 0; c < NC; c++)
+                        bulk_g2s_x4<VSTRIDE>(st + 4 * c * VSTRIDE, baseL + (eL[c] + oLL - PADE), baseA + (eA[c] + oHL - PADE),
+                                             baseA + (eA[c] + oLH - PADE), baseA + (eA[c] + oHH - PADE), bar);
                 }
             } else {
 #pragma unroll
@@ -622,16 +651,28 @@ template <int TYPE> struct StreamCfg {
 #endif
     static constexpr int NP = TYPE == J2K_DWT53 ? STREAM_NP53 : 2;
 };
-/* rows per warp: enough warps to fill the GPU (148 SMs x 8 resident warps), but not so few rows that the
- * HALO warm-up rows dominate */
-int pick_seg(int strips, int units_z, int rows, int per_sm = STREAM_WANT)
+/* Rows per warp.  These kernels run for tens of microseconds: a second, nearly empty wave of CTAs costs as much
+ * as the first, so the segment height is the smallest one (least serial work per warp) whose grid still fits
+ * the GPU in ONE wave -- `capacity` = SMs x resident CTAs per SM of the kernel as the occupancy calculator
+ * reports it -- and never so small that the HALO warm-up rows dominate. */
+int pick_seg(int strips, int rows, int capacity)
 {
-    const long want = 148L * per_sm;
-    long seg = ((long)rows * strips * units_z + want - 1) / want;
+    const long fill = (long)capacity * SWARPS * STREAM_FILL / 100;      /* warps */
+    long max_segs = fill / (strips > 0 ? strips : 1);
+    if (max_segs < 1)
+        max_segs = 1;
+    long seg = (rows + max_segs - 1) / max_segs;
     seg = (seg + 1) & ~1L;
     if (seg < 8) seg = 8;
-    if (seg > 64) seg = 64;
     return (int)seg;
+}
+template <class K> int resident_ctas(K kernel, int smem)
+{
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SWARPS * 32, smem);
+    return sms * (per_sm > 0 ? per_sm : 1);
 }
 
 /* can the fast path reconstruct level j of this tile-component?  (even origin, lines longer than one
@@ -706,15 +747,15 @@ int launch_idwt_stream_level(cudaStream_t stream, int type, const IdwtFrame &f, 
 #define LAUNCH(T)                                                                                              \
     do {                                                                                                       \
         constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;                                                  \
-        const int strips = (max_w + 1 + VALID - 1) / VALID;                                                    \
-        const int seg = pick_seg(strips, f.ntcs, max_h), segs = (max_h + 1 + seg - 1) / seg;                   \
-        dim3 grid((strips * segs + SWARPS - 1) / SWARPS, f.ntcs);                                              \
-        constexpr int sm = stage_bytes_per_cta<NP, 1>();                                                    \
-        static bool attr = false;                                                                              \
-        if (!attr) {                                                                                           \
+        constexpr int sm = stage_bytes_per_cta<NP, 1>();                                                       \
+        static int capacity = 0;                                                                               \
+        if (!capacity) {                                                                                       \
             cudaFuncSetAttribute(idwt_stream_level_kernel<T, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
-            attr = true;                                                                                       \
+            capacity = resident_ctas(idwt_stream_level_kernel<T, NP>, sm);                                     \
         }                                                                                                      \
+        const int strips = (max_w + 1 + VALID - 1) / VALID;                                                    \
+        const int seg = pick_seg(strips * f.ntcs, max_h, capacity), segs = (max_h + 1 + seg - 1) / seg;        \
+        dim3 grid((strips * segs + SWARPS - 1) / SWARPS, f.ntcs);                                              \
         idwt_stream_level_kernel<T, NP><<<grid, SWARPS * 32, sm, stream>>>(                                    \
             f.d_tcs, j, (const uint32_t *)f.coefA, (const uint32_t *)in, (uint32_t *)out, strips, seg);        \
     } while (0)
@@ -730,13 +771,15 @@ int launch_idwt_stream_final(cudaStream_t stream, int type, int ncomp, const Idw
 #define LAUNCH(T, NC)                                                                                          \
     do {                                                                                                       \
         constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;                                                  \
+        constexpr int sm = stage_bytes_per_cta<NP, NC>();                                                      \
+        static int capacity = 0;                                                                               \
+        if (!capacity) {                                                                                       \
+            cudaFuncSetAttribute(idwt_stream_final_kernel<T, NP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
+            capacity = resident_ctas(idwt_stream_final_kernel<T, NP, NC>, sm);                                 \
+        }                                                                                                      \
         const int strips = (max_w + 1 + VALID - 1) / VALID;                                                    \
-        const int seg = pick_seg(strips, f.ngroups, max_h), segs = (max_h + 1 + seg - 1) / seg;                \
+        const int seg = pick_seg(strips * f.ngroups, max_h, capacity), segs = (max_h + 1 + seg - 1) / seg;     \
         dim3 grid((strips * segs + SWARPS - 1) / SWARPS, f.ngroups);                                           \
-        constexpr int sm = stage_bytes_per_cta<NP, NC>();                                                   \
-        cudaFuncSetAttribute(idwt_stream_final_kernel<T, NP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
-        if (getenv("B200J2K_CARVEOUT"))                                                                        \
-            cudaFuncSetAttribute(idwt_stream_final_kernel<T, NP, NC>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("B200J2K_CARVEOUT"))); \
         idwt_stream_final_kernel<T, NP, NC><<<grid, SWARPS * 32, sm, stream>>>(                                \
             f.d_tcs, f.d_groups, (const uint32_t *)f.coefA, (const uint32_t *)f.coefB, (const uint32_t *)f.coefC, \
             f.picture, f.plane_off[0], f.plane_off[1], f.plane_off[2], f.plane_off[3], f.plane_row_bytes[0],   \
