@@ -162,6 +162,81 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+
+# ---- further BASELINE workloads (reported next to the contract's workload, N=1 only) -------------------
+def extra_workload(fb, torch, local, cfgname, label, B, K, T, slots_e2e, S=8):
+    """Kernel-only and end-to-end frames/s of one more BASELINE.json configuration (one distinct frame, cycled),
+    measured exactly like the main workload: CUDA events on the launching streams with the inputs resident in
+    HBM, and wall clock around b200j2k_submit/wait with pinned host buffers."""
+    import j2kgen
+    cs, planes, _ = j2kgen.make_config(cfgname)
+    h, w = planes[0].shape
+    dec = fb.Jpeg2000Decoder(device=local, slots=S)
+    info = [dec.stage(s, cs) for s in range(S)][0]
+    streams = [torch.cuda.ExternalStream(dec.stream(s), device=local) for s in range(S)]
+    for i in range(B):
+        dec.run_staged(i % S)
+    torch.cuda.synchronize()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in streams]
+    for e, st in zip(ev0, streams):
+        e.record(st)
+    for _ in range(K):
+        for i in range(B):
+            dec.run_staged(i % S)
+    for e, st in zip(ev1, streams):
+        e.record(st)
+    torch.cuda.synchronize()
+    kern_ms = max(a.elapsed_time(b) for a in ev0 for b in ev1)
+    stage = np.zeros(6)
+    dec.run_staged_timed(0)
+    for _ in range(3):
+        stage += np.array(dec.run_staged_timed(0))
+    stage /= 3
+    dec.close()
+    decs = [fb.Jpeg2000Decoder(device=local, slots=slots_e2e) for _ in range(T)]
+    pins = [[fb.PinnedFrame(info) for _ in range(slots_e2e)] for _ in range(T)]
+    pkt = fb.PinnedPacket(cs)
+
+    def worker(t, n):
+        torch.cuda.set_device(local)
+        d, pf, pending = decs[t], pins[t], []
+        for j in range(n):
+            if len(pending) == len(pf):
+                d.wait(pending.pop(0))
+            pending.append(d.submit(pkt, pf[j % len(pf)]))
+        for s_ in pending:
+            d.wait(s_)
+
+    def run(n):
+        th = [threading.Thread(target=worker, args=(t, n)) for t in range(T)]
+        for x in th:
+            x.start()
+        for x in th:
+            x.join()
+
+    per = max(1, B // T)
+    run(per)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(per * K)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    for d in decs:
+        d.close()
+    n_k, n_e = B * K, per * K * T
+    return {"workload": label, "codeblocks_per_frame": info.ncodeblocks, "compressed_bytes_per_frame": len(cs),
+            "fps": n_k / (kern_ms * 1e-3), "mpixel_s": n_k * w * h / (kern_ms * 1e-3) / 1e6,
+            "e2e_fps": n_e / e2e_s, "e2e_mpixel_s": n_e * w * h / e2e_s / 1e6,
+            "stage_ms_per_frame": [round(float(x), 4) for x in stage]}
+
+
+EXTRA = [
+    ("target8k", "7680x4320 1-component 16-bit lossless HTJ2K, one tile (north_star target: >= 60 fps on one B200)"),
+    ("cfg3", "7680x4320 1-component 16-bit lossless HTJ2K, 2x2 tiles (BASELINE configs[2])"),
+    ("cfg2", "3840x2160 4:4:4 10-bit irreversible 9/7 + ICT HTJ2K (BASELINE configs[1])"),
+]
+
 # ---- this repo's arm --------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -411,6 +486,9 @@ def run_ours(args):
                                    "idwt_levels": float(stage_ms[4]), "idwt_final_mct_pack": float(stage_ms[5])},
             "clocks": clocks,
         }
+        if world == 1 and not args.no_extra and args.scale == 1:
+            line["other_workloads"] = [extra_workload(fb, torch, local, c, lbl, 16, max(2, min(K, 4)), T, args.slots_e2e)
+                                       for c, lbl in EXTRA]
         if world == 1 and not args.no_cpu_baseline:
             fn, kind = cpu_decoder()
             cores = os.cpu_count() or 1
@@ -461,6 +539,7 @@ def main():
     ap.add_argument("--slots-e2e", type=int, default=2)
     ap.add_argument("--scale", type=int, default=1, help="shrink the frame by this factor (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE workloads (8K, 9/7) at N=1")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
