@@ -118,6 +118,11 @@ def lib():
         L.b200j2k_plan_table.restype = vp
         L.b200j2k_plan_scalar.argtypes = [i32]
         L.b200j2k_plan_scalar.restype = i64
+        L.b200j2k_splitter_create.argtypes = [ctypes.POINTER(vp), i32]
+        L.b200j2k_splitter_destroy.argtypes = [vp]
+        L.b200j2k_splitter_destroy.restype = None
+        L.b200j2k_splitter_find_frame_end.argtypes = [vp, vp, i32]
+        L.b200j2k_splitter_parse.argtypes = [vp, ctypes.POINTER(vp), _PI, vp, i32]
         _lib = L
     return _lib
 
@@ -130,7 +135,9 @@ EXPORTS = ["b200j2k_device_count", "b200j2k_create", "b200j2k_destroy", "b200j2k
            "b200j2k_ht_blocks", "b200j2k_idwt", "b200j2k_host_alloc", "b200j2k_host_free",
            "b200j2k_host_register", "b200j2k_host_unregister", "b200j2k_device_alloc", "b200j2k_device_free",
            "b200j2k_device_download", "b200j2k_pix_fmt_name", "b200j2k_version",
-           "b200j2k_plan_build", "b200j2k_plan_table", "b200j2k_plan_scalar"]
+           "b200j2k_plan_build", "b200j2k_plan_table", "b200j2k_plan_scalar",
+           "b200j2k_splitter_create", "b200j2k_splitter_destroy", "b200j2k_splitter_find_frame_end",
+           "b200j2k_splitter_parse"]
 
 
 def _check(ret: int, what: str = "") -> int:
@@ -381,6 +388,54 @@ class Jpeg2000Decoder:
 
 
 # -- stage-level entry points (parity tests) ---------------------------------------------------------
+class FrameSplitter:
+    """Mirror of the reference's AVCodecParser "jpeg2000" (libavcodec/jpeg2000_parser.c): feed a byte stream in
+    arbitrary pieces, get the codestreams / JP2 files back one by one."""
+
+    def __init__(self, complete_frames: bool = False):
+        self._h = ctypes.c_void_p()
+        _check(lib().b200j2k_splitter_create(ctypes.byref(self._h), int(complete_frames)), "splitter_create")
+
+    def close(self):
+        if self._h:
+            lib().b200j2k_splitter_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def parse(self, data):
+        """One parser_parse call on `data` (bytes-like).  -> (return value, frame bytes or None)."""
+        a = np.frombuffer(data, np.uint8) if len(data) else np.zeros(0, np.uint8)
+        out, n = ctypes.c_void_p(), ctypes.c_int(0)
+        r = lib().b200j2k_splitter_parse(self._h, ctypes.byref(out), ctypes.byref(n), a.ctypes.data if a.size else None,
+                                         int(a.size))
+        frame = ctypes.string_at(out.value, n.value) if out.value and n.value > 0 else None
+        return int(r), frame
+
+    def feed(self, data, flush: bool = False):
+        """av_parser_parse2's calling loop: consume all of `data` (and, with flush, the end-of-input call);
+        returns the list of completed frames."""
+        frames = []
+        mv = memoryview(bytes(data))
+        pos = 0
+        while pos < len(mv):
+            r, f = self.parse(mv[pos:])
+            if f is not None:
+                frames.append(f)
+            pos += max(r, 0)
+            if r <= 0 and f is None:
+                break
+        if flush:
+            r, f = self.parse(b"")
+            if f is not None:
+                frames.append(f)
+        return frames
+
+
 def ht_blocks(blocks, device: int = 0):
     """blocks: list of dicts(data, npasses, Lcup, Lref, zbp, w, h, M_b, roi, vsc) ->
     (list of int32 arrays h x w in the reference's sign-magnitude form, status array)."""

@@ -161,6 +161,25 @@ int b200j2k_plan_build(const uint8_t *pkt, int64_t pkt_size, int flags, b200j2k_
 const void *b200j2k_plan_table(int which, int64_t *count, int32_t *elem_size);
 int64_t b200j2k_plan_scalar(int which);
 
+/* ---- frame splitter: the AVCodecParser "jpeg2000" (libavcodec/jpeg2000_parser.c:36-215) ------------------
+ * Cuts a byte stream of concatenated codestreams / JP2 files, fed in arbitrary pieces, into the packets
+ * b200j2k_submit takes.  Host-only (a length-skipping serial scan).
+ *   create(complete_frames)   complete_frames != 0 = PARSER_FLAG_COMPLETE_FRAMES: every input is one frame
+ *   find_frame_end            jpeg2000_parser.c:91-175 alone, for a binding that keeps libavcodec's own
+ *                             ff_combine_frame: offset of the next frame's first byte in buf (may be < 0:
+ *                             the frame ended before this piece), or B200J2K_SPLIT_END_NOT_FOUND
+ *   parse                     jpeg2000_parse (:177-208) incl. ff_combine_frame (parser.c:203-288): returns
+ *                             the number of input bytes consumed (may be < 0, callers clamp to 0 as
+ *                             av_parser_parse2 does); *out / *out_size = one complete frame or NULL / 0.
+ *                             *out points into buf or into the splitter's own storage (valid until the next
+ *                             call).  A call with size == 0 flushes the last frame at end of input. */
+#define B200J2K_SPLIT_END_NOT_FOUND (-100)
+typedef struct b200j2k_splitter b200j2k_splitter;
+int b200j2k_splitter_create(b200j2k_splitter **out, int complete_frames);
+void b200j2k_splitter_destroy(b200j2k_splitter *sp);
+int b200j2k_splitter_find_frame_end(b200j2k_splitter *sp, const uint8_t *buf, int size);
+int b200j2k_splitter_parse(b200j2k_splitter *sp, const uint8_t **out, int *out_size, const uint8_t *buf, int size);
+
 const char *b200j2k_pix_fmt_name(int pix_fmt);
 const char *b200j2k_version(void);
 

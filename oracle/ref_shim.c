@@ -13,6 +13,8 @@
  *                       ff_jpeg2000_decode_htj2k (libavcodec/jpeg2000htdec.c:1188-1336)
  *   ref_idwt()          ff_jpeg2000_dwt_init + ff_dwt_decode (libavcodec/jpeg2000dwt.c:539-620)
  *   ref_mct()           Jpeg2000DSPContext.mct_decode[] (libavcodec/jpeg2000dsp.c:43-104)
+ *   ref_parser_*()      ff_jpeg2000_parser.parser_parse (libavcodec/jpeg2000_parser.c:177-215) on a hand-made
+ *                       AVCodecParserContext: splits a byte stream into codestreams / JP2 files
  *   ref_decode_bench()  the CPU baseline: N codestreams decoded by T threads, one decoder
  *                       context per thread (what `ffmpeg -threads T` frame threading does,
  *                       libavcodec/pthread_frame.c:248-295), wall-clock seconds returned.
@@ -264,6 +266,50 @@ int ref_mct(int type, void *p0, void *p1, void *p2, int n)
 }
 
 #endif /* REF_STAGE_API */
+
+/* ---- the frame splitter (AVCodecParser "jpeg2000") --------------------------------------- */
+#include "libavcodec/parser.h"
+#ifndef REF_PARSER
+#define REF_PARSER ff_jpeg2000_parser
+#endif
+extern const AVCodecParser REF_PARSER;
+const AVCodecParser *av_parser_iterate(void **opaque) { (void)opaque; return NULL; }   /* parser.c's only loose end */
+
+void *REF_NAME(parser_new)(int complete_frames)
+{
+    AVCodecParserContext *s = av_mallocz(sizeof(*s));
+    s->priv_data = av_mallocz(REF_PARSER.priv_data_size);
+    s->parser = &REF_PARSER;
+    s->flags = complete_frames ? PARSER_FLAG_COMPLETE_FRAMES : 0;
+    return s;
+}
+
+/* one parser_parse call: returns its return value; *out / *out_size as the parser set them (the pointer is
+ * reported as an offset into `buf` when it points there, else -1 = the parser's own buffer, copied to `copy`) */
+int REF_NAME(parser_parse)(void *p, const uint8_t *buf, int size, int64_t *out_off, int *out_size, uint8_t *copy, int64_t cap)
+{
+    AVCodecParserContext *s = p;
+    const uint8_t *o = NULL;
+    int osz = 0;
+    int r = REF_PARSER.parser_parse(s, NULL, &o, &osz, buf, size);
+    *out_size = osz;
+    if (o && o >= buf && o <= buf + size)
+        *out_off = o - buf;
+    else
+        *out_off = -1;
+    if (o && osz > 0 && osz <= cap)
+        memcpy(copy, o, osz);
+    return r;
+}
+
+void REF_NAME(parser_free)(void *p)
+{
+    AVCodecParserContext *s = p;
+    REF_PARSER.parser_close(s);
+    av_free(s->priv_data);
+    av_free(s);
+}
+
 
 /* ---- CPU baseline ---------------------------------------------------------------------- */
 

@@ -15,6 +15,6 @@ for f in csrc/*.cu; do
     objs="$objs build/$b.o"
   fi
 done
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/lib_$name.so $objs build/j2k_parse.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o variants/lib_$name.so $objs build/j2k_parse.o build/j2k_splitter.o
 rm -f variants/*_$name.o
 echo variants/lib_$name.so
