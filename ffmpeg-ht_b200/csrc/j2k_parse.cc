@@ -7,8 +7,8 @@
  *   init_tile :1016-1070   component/band/precinct/code-block geometry jpeg2000.c:274-577
  *   step sizes jpeg2000.c:214-272   packet headers jpeg2000dec.c:1136-1542 (HT paths)
  *   progression orders :1544-1833
- * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 MQ blocks, MIXED/HTDECLARED sets, POC,
- * PPM/PPT -- SURVEY.md section 8(f) "next".
+ * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 MQ blocks, MIXED/HTDECLARED sets, coding /
+ * quantisation / progression changes in tile-part headers, tile-specific ROI, PAL8 -- SURVEY.md section 8(f) "next".
  */
 #include "j2k_parse.h"
 
@@ -382,6 +382,13 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
     Header &h = hdr;
     h = Header();
     parts_.clear();
+    ppm_.clear();
+    has_ppm_ = false;
+    ppt_.clear();
+    tile_first_.clear();
+    has_ppt_.clear();
+    ppt_pos_.clear();
+    size_t ppm_pos = 0;                                    /* s->packed_headers_stream */
     *main_header_len = 0;
     if (size >= 12 && rd32(p) == 12 && rd32(p + 4) == 0x6A502020u && rd32(p + 8) == 0x0D0A870Au) {
         /* JP2 / JPH file (jpeg2000dec.c:2842-2854) */
@@ -413,8 +420,23 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 return B200J2K_ERR_INVALIDDATA;
             auto &pv = parts_[cur_tile];
             if ((int)pv.size() <= cur_tp)
-                pv.resize(cur_tp + 1, TilePart{ nullptr, nullptr, nullptr });
-            pv[cur_tp] = TilePart{ p, tp_end, p };
+                pv.resize(cur_tp + 1, TilePart{ nullptr, nullptr, nullptr, nullptr, nullptr });
+            const uint8_t *hp = nullptr, *hend = nullptr;
+            if (has_ppm_) {                               /* this tile-part's run: Nppm, then the headers (:2467-2472) */
+                uint32_t n = 0;
+                if (ppm_.size() - ppm_pos >= 4) {
+                    n = rd32(ppm_.data() + ppm_pos);
+                    ppm_pos += 4;
+                }
+                if (ppm_.size() - ppm_pos < n)
+                    return B200J2K_ERR_INVALIDDATA;
+                hp = ppm_.data() + ppm_pos;
+                hend = hp + n;
+                ppm_pos += n;
+            }
+            if (has_ppt_[cur_tile] && cur_tp == 0)
+                ppt_pos_[cur_tile] = 0;
+            pv[cur_tp] = TilePart{ p, tp_end, p, hp, hend };
             p = tp_end;
             continue;
         }
@@ -465,6 +487,10 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             if ((int64_t)h.ntx * h.nty * 14 > size)
                 return B200J2K_ERR_EINVAL;
             parts_.assign((size_t)h.ntx * h.nty, {});
+            tile_first_.assign((size_t)h.ntx * h.nty, 0);
+            ppt_.assign((size_t)h.ntx * h.nty, {});
+            has_ppt_.assign((size_t)h.ntx * h.nty, 0);
+            ppt_pos_.assign((size_t)h.ntx * h.nty, 0);
             const int red = B200J2K_FLAG_GET_LOWRES(flags);
             if (red && (h.X0 || h.Y0))
                 return B200J2K_ERR_PATCHWELCOME;          /* jpeg2000dec.c:256-259 */
@@ -512,7 +538,11 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             break;
         }
         case 0xFF52: {
-            if (cur_tile >= 0 || segend - seg < 5)
+            /* coding / quantisation styles of a single tile: INVALIDDATA for the HOMOGENEOUS set as in the
+             * reference (jpeg2000dec.c:2514-2556), not served otherwise */
+            if (cur_tile >= 0)
+                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
+            if (segend - seg < 5)
                 return B200J2K_ERR_INVALIDDATA;
             CodSty tmp;
             tmp.csty = seg[0];
@@ -531,7 +561,9 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             break;
         }
         case 0xFF53: {
-            if (cur_tile >= 0 || segend - seg < 2)
+            if (cur_tile >= 0)
+                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
+            if (segend - seg < 2)
                 return B200J2K_ERR_INVALIDDATA;
             int c = seg[0];
             if (c >= h.ncomp)
@@ -548,7 +580,7 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
         }
         case 0xFF5C: {
             if (cur_tile >= 0)
-                return B200J2K_ERR_INVALIDDATA;
+                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
             QntSty tmp;
             memset(&tmp, 0, sizeof(tmp));
             if ((ret = parse_qcx(seg, len - 2, &tmp)) < 0)
@@ -560,7 +592,9 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             break;
         }
         case 0xFF5D: {
-            if (cur_tile >= 0 || segend - seg < 1)
+            if (cur_tile >= 0)
+                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
+            if (segend - seg < 1)
                 return B200J2K_ERR_INVALIDDATA;
             int c = seg[0];
             if (c >= h.ncomp)
@@ -576,8 +610,8 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 return B200J2K_ERR_INVALIDDATA;
             if (seg[2] > 30)
                 return B200J2K_ERR_PATCHWELCOME;
-            if (cur_tile >= 0)
-                return B200J2K_ERR_PATCHWELCOME;          /* tile-specific ROI: not in the first bar */
+            if (cur_tile >= 0)                            /* tile-specific ROI (:2530-2534) */
+                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
             h.roi[seg[0]] = seg[2];
             seg += 3;
             break;
@@ -601,6 +635,8 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 return B200J2K_ERR_PATCHWELCOME;
             cur_tile = isot;
             cur_tp = tpsot;
+            if (!tpsot)
+                tile_first_[isot] = 1;                    /* get_sot copies the coding styles to the tile (:862-869) */
             tp_end = seg + 8 + psot - len - 2;
             seg += 8;
             break;
@@ -633,8 +669,20 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             seg += 7 * n;
             break;
         }
-        case 0xFF60: case 0xFF61:                         /* PPM, PPT */
-            return B200J2K_ERR_PATCHWELCOME;
+        case 0xFF60:                                      /* PPM (get_ppm, jpeg2000dec.c:958-980, :2597-2604) */
+            if (cur_tile >= 0 || len < 3)
+                return B200J2K_ERR_INVALIDDATA;
+            has_ppm_ = true;
+            ppm_.insert(ppm_.end(), seg + 1, segend);     /* Zppm is not used */
+            seg = segend;
+            break;
+        case 0xFF61:                                      /* PPT (get_ppt, :982-1014, :2605-2617) */
+            if (has_ppm_ || (h.isHT && !h.cap_b11) || len < 3 || cur_tile < 0 || cur_tp != 0)
+                return B200J2K_ERR_INVALIDDATA;
+            has_ppt_[cur_tile] = 1;
+            ppt_[cur_tile].insert(ppt_[cur_tile].end(), seg + 1, segend);
+            seg = segend;
+            break;
         default:
             seg = segend;
             break;
@@ -1012,10 +1060,33 @@ int Parser::tagtree_decode(uint32_t base, int ncw, int nch, int leaf, int thresh
     return cur;
 }
 
+/* select_header (jpeg2000dec.c:1099-1108): the tile-part's run of PPM packet headers; when it is used up the
+ * reference moves on to the NEXT tile-part and reads the header from that one's data */
+void Parser::select_header(int tileno, int *tp)
+{
+    auto &pv = parts_[tileno];
+    const uint8_t *none = pkt_ + pkt_size_;
+    if (*tp < (int)pv.size() && pv[*tp].hp) {
+        bp_ = pv[*tp].hp;
+        bend_ = pv[*tp].hend;
+    } else {
+        bp_ = bend_ = none;
+    }
+    if (bp_ >= bend_ && bit_index_ == 8 && *tp < 31) {
+        ++*tp;
+        if (*tp < (int)pv.size() && pv[*tp].p) {
+            bp_ = pv[*tp].p;
+            bend_ = pv[*tp].end;
+        } else {
+            bp_ = bend_ = none;
+        }
+    }
+}
+
 void Parser::select_part(int tileno, int *tp, int csty)
 {
     auto &pv = parts_[tileno];
-    if (pv.empty()) {
+    if (pv.empty() || *tp >= (int)pv.size()) {            /* no such tile-part: an empty stream */
         bp_ = bend_ = pkt_ + pkt_size_;
         return;
     }
@@ -1048,7 +1119,15 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
     if (layno < dl)
         return 0;
     dl = (uint8_t)(layno + 1);
-    select_part(tileno, tp, cs.csty);
+    /* where the packet header is read from (jpeg2000dec.c:1147-1153) */
+    const bool ppm = has_ppm_, ppt = !ppm && !has_ppt_.empty() && has_ppt_[tileno];
+    if (ppm)
+        select_header(tileno, tp);
+    else if (ppt) {
+        bp_ = ppt_[tileno].data() + ppt_pos_[tileno];
+        bend_ = ppt_[tileno].data() + ppt_[tileno].size();
+    } else
+        select_part(tileno, tp, cs.csty);
 
     struct Inc { uint32_t cb; int nseg; uint32_t seg[6]; };
     static thread_local std::vector<Inc> incs;
@@ -1183,6 +1262,17 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
     if (cs.csty & 4)
         if (bend_ - bp_ >= 2 && rd16(bp_) == 0xFF92)
             bp_ += 2;
+    /* packed headers: remember where the header stream stands, continue in the tile-part's data (:1474-1480) */
+    if (ppm) {
+        if (*tp < (int)parts_[tileno].size()) {
+            parts_[tileno][*tp].hp = bp_;
+            parts_[tileno][*tp].hend = bend_;
+        }
+        select_part(tileno, tp, cs.csty);
+    } else if (ppt) {
+        ppt_pos_[tileno] = (size_t)(bp_ - ppt_[tileno].data());
+        select_part(tileno, tp, cs.csty);
+    }
     /* packet body: code-block bytes are referenced in place; a block that already has bytes elsewhere
      * is gathered into `extra` so that Dcup||Dref stays contiguous for the kernel */
     for (const Inc &in : incs) {
@@ -1210,7 +1300,7 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
             }
         }
     }
-    if (!parts_[tileno].empty())
+    if (*tp < (int)parts_[tileno].size())
         parts_[tileno][*tp].p = bp_;
     return 0;
 }
@@ -1426,9 +1516,14 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
     decoded_layers_.assign(precs_.size(), 0);
     extra.clear();
     cur_part_start_ = nullptr;
-    for (int tileno = 0; tileno < hdr.ntx * hdr.nty; tileno++)
+    for (int tileno = 0; tileno < hdr.ntx * hdr.nty; tileno++) {
+        /* a tile whose first tile-part (TPsot = 0) never showed up has no coding style in the reference:
+         * init_tile fails on !codsty->init (jpeg2000dec.c:1054-1055) and the frame with it */
+        if (!tile_first_[tileno])
+            return B200J2K_ERR_INVALIDDATA;
         if ((ret = decode_packets(tileno)) < 0)
             return ret;
+    }
     /* the reference returns bytestream2_tell() of the LAST tile-part sub-stream it read, after skipping
      * the 2 EOC bytes if they are inside that sub-stream (jpeg2000dec.c:1865-1866, :2903) */
     if (cur_part_start_ && bp_ && bp_ >= cur_part_start_) {

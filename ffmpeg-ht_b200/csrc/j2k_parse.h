@@ -94,7 +94,7 @@ struct Header {
     int chroma_lw = 0, chroma_lh = 0;   /* its log2_chroma_w / log2_chroma_h */
 };
 
-struct TilePart { const uint8_t *p, *end, *start; };
+struct TilePart { const uint8_t *p, *end, *start; const uint8_t *hp, *hend; };   /* hp/hend: its run of PPM packet headers */
 
 class Parser {
 public:
@@ -137,6 +137,13 @@ private:
     std::vector<TagNodeState> tags_;
     std::vector<uint8_t> decoded_layers_;   /* per precinct of band 0 */
     std::vector<std::vector<TilePart>> parts_;
+    /* packed packet headers: PPM (main header, jpeg2000dec.c:958-980) and PPT (tile-part header, :982-1014) */
+    std::vector<uint8_t> ppm_;
+    bool has_ppm_ = false;
+    std::vector<std::vector<uint8_t>> ppt_;   /* per tile */
+    std::vector<uint8_t> has_ppt_;
+    std::vector<uint8_t> tile_first_;          /* per tile: a tile-part with TPsot == 0 was seen */
+    std::vector<size_t> ppt_pos_;             /* tile->packed_headers_stream as an offset into ppt_[tile] */
 
     /* packet-header bit reader */
     const uint8_t *bp_ = nullptr, *bend_ = nullptr;
@@ -152,6 +159,7 @@ private:
     int decode_packet(int tileno, int comp, int r, int precno, int layno, int *tp);
     int precinct_at(int tileno, int c, int r, int x, int y, bool cprl_rule) const;
     void select_part(int tileno, int *tp, int csty);
+    void select_header(int tileno, int *tp);
     inline int bits(int n);
     inline void flush();
     int tagtree_decode(uint32_t base, int ncw, int nch, int leaf, int threshold);

@@ -77,13 +77,21 @@ typedef struct Comp {
     int roi_shift;
 } Comp;
 
-typedef struct TilePart { const uint8_t *p, *end; } TilePart;
+typedef struct TilePart {
+    const uint8_t *p, *end;                         /* tpg: packets of this tile-part */
+    const uint8_t *hp, *hend;                       /* header_tpg: its run of PPM packet headers */
+} TilePart;
 
 typedef struct Tile {
     Rect c;
     Comp comp[MAXC];
     TilePart part[32];
     int nparts;
+    /* PPT: packed packet headers of this tile (get_ppt, jpeg2000dec.c:982-1014) */
+    int first_seen;                                 /* a tile-part with TPsot == 0 set this tile's coding styles (get_sot, :862-869) */
+    int has_ppt;
+    uint8_t *ppt;
+    size_t ppt_size, ppt_pos;                       /* ppt_pos = tile->packed_headers_stream */
 } Tile;
 
 typedef struct Dec {
@@ -103,6 +111,10 @@ typedef struct Dec {
     int npoc;                                       /* main-header POC entries (get_poc) */
     struct { int RS, CS, LYE, RE, CE, P; } poc[32];
     int chroma_lw, chroma_lh;                       /* log2_chroma_w/h of the chosen AVPixelFormat */
+    /* PPM: packed packet headers of the whole codestream (get_ppm, jpeg2000dec.c:958-980) */
+    int has_ppm;
+    uint8_t *ppm;
+    size_t ppm_size, ppm_pos;                       /* ppm_pos = s->packed_headers_stream */
     /* packet header bit reader */
     const uint8_t *bp, *bend;
     int bit_index;
@@ -497,6 +509,20 @@ static int parse_headers(Dec *d)
             if (!d->tile || cur_tile < 0 || tp_end < p)
                 return ORACLE_ERR_INVALID;
             Tile *t = &d->tile[cur_tile];
+            if (d->has_ppm) {                             /* Nppm, then that many bytes of headers (:2467-2472) */
+                uint32_t n = 0;
+                if (d->ppm_size - d->ppm_pos >= 4) {
+                    n = rd32(d->ppm + d->ppm_pos);
+                    d->ppm_pos += 4;
+                }
+                if (d->ppm_size - d->ppm_pos < n)
+                    return ORACLE_ERR_INVALID;
+                t->part[cur_tp].hp = d->ppm + d->ppm_pos;
+                t->part[cur_tp].hend = t->part[cur_tp].hp + n;
+                d->ppm_pos += n;
+            }
+            if (t->has_ppt && cur_tp == 0)                /* :2474-2476 */
+                t->ppt_pos = 0;
             t->part[cur_tp].p = p;
             t->part[cur_tp].end = tp_end;
             if (cur_tp + 1 > t->nparts)
@@ -598,8 +624,8 @@ static int parse_headers(Dec *d)
             break;
         }
         case 0xFF52: {                                    /* COD */
-            if (cur_tile >= 0)
-                return ORACLE_ERR_INVALID;                /* HOMOGENEOUS set: no tile-part COD (:2514-2520) */
+            if (cur_tile >= 0)                            /* HOMOGENEOUS set: no tile-part COD (:2514-2520); else: not restated */
+                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
             if (segend - seg < 5)
                 return ORACLE_ERR_INVALID;
             CodSty tmp;
@@ -621,7 +647,7 @@ static int parse_headers(Dec *d)
         }
         case 0xFF53: {                                    /* COC */
             if (cur_tile >= 0)
-                return ORACLE_ERR_INVALID;
+                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
             if (segend - seg < 2)
                 return ORACLE_ERR_INVALID;
             int c = seg[0];
@@ -639,7 +665,7 @@ static int parse_headers(Dec *d)
         }
         case 0xFF5C: {                                    /* QCD */
             if (cur_tile >= 0)
-                return ORACLE_ERR_INVALID;
+                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
             QntSty tmp;
             memset(&tmp, 0, sizeof(tmp));
             if ((ret = parse_qcx(seg, len - 2, &tmp)) < 0)
@@ -652,7 +678,7 @@ static int parse_headers(Dec *d)
         }
         case 0xFF5D: {                                    /* QCC */
             if (cur_tile >= 0)
-                return ORACLE_ERR_INVALID;
+                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
             if (segend - seg < 1)
                 return ORACLE_ERR_INVALID;
             int c = seg[0];
@@ -693,6 +719,8 @@ static int parse_headers(Dec *d)
                 return ORACLE_ERR_PATCH;
             cur_tile = isot;
             cur_tp = tpsot;
+            if (!tpsot)
+                d->tile[isot].first_seen = 1;
             tp_end = seg + 8 + psot - len - 2;
             seg += 8;
             break;
@@ -721,8 +749,29 @@ static int parse_headers(Dec *d)
             d->npoc += n;                                 /* a further POC segment appends (:805-812) */
             break;
         }
-        case 0xFF60: case 0xFF61:                         /* PPM, PPT */
-            return ORACLE_ERR_PATCH;
+        case 0xFF60: {                                    /* PPM: main header only (:2597-2604) */
+            if (cur_tile >= 0 || len < 3)
+                return ORACLE_ERR_INVALID;
+            const size_t n = (size_t)(segend - seg) - 1;  /* Zppm is skipped */
+            d->ppm = realloc(d->ppm, d->ppm_size + n + 1);
+            memcpy(d->ppm + d->ppm_size, seg + 1, n);
+            d->ppm_size += n;
+            d->has_ppm = 1;
+            seg = segend;
+            break;
+        }
+        case 0xFF61: {                                    /* PPT: first tile-part of a tile (:2605-2617, :982-1014) */
+            if (d->has_ppm || (d->isHT && !d->cap_b11) || len < 3 || cur_tile < 0 || cur_tp != 0)
+                return ORACLE_ERR_INVALID;
+            Tile *t = &d->tile[cur_tile];
+            const size_t n = (size_t)(segend - seg) - 1;
+            t->ppt = realloc(t->ppt, t->ppt_size + n + 1);
+            memcpy(t->ppt + t->ppt_size, seg + 1, n);
+            t->ppt_size += n;
+            t->has_ppt = 1;
+            seg = segend;
+            break;
+        }
         default:                                          /* COM, TLM, PLT, PLM, CRG, CPF, unknown: skipped */
             seg = segend;
             break;
@@ -772,6 +821,10 @@ static void band_stepsize(Band *b, const CodSty *c, const QntSty *q, int bandno,
 static int init_tile(Dec *d, int tileno)
 {
     Tile *t = &d->tile[tileno];
+    /* a tile whose first tile-part never showed up has no coding style: init_tile fails on !codsty->init
+     * (jpeg2000dec.c:1054-1055) and with it the whole frame */
+    if (!t->first_seen)
+        return ORACLE_ERR_INVALID;
     const int tx = tileno % d->ntx, ty = tileno / d->ntx;
     t->c.x0 = clip64((int64_t)tx * d->TW + d->TX0, d->X0, d->W);
     t->c.x1 = clip64((int64_t)(tx + 1) * d->TW + d->TX0, d->X0, d->W);
@@ -932,6 +985,24 @@ static void select_part(Dec *d, PktState *ps, int csty)
             d->bp += 6;
 }
 
+/* select_header (jpeg2000dec.c:1099-1108): read the packet header from the tile-part's PPM run; once that is
+ * used up the reference moves to the next tile-part and reads from its data */
+static void select_header(Dec *d, PktState *ps)
+{
+    Tile *t = ps->t;
+    d->bp = t->part[ps->tp].hp;
+    d->bend = t->part[ps->tp].hend;
+    if (!d->bp)
+        d->bp = d->bend = d->end;
+    if (d->bp >= d->bend && d->bit_index == 8 && ps->tp < 31) {
+        ps->tp++;
+        d->bp = t->part[ps->tp].p;
+        d->bend = t->part[ps->tp].end;
+        if (!d->bp)
+            d->bp = d->bend = d->end;
+    }
+}
+
 static int getnpasses(Dec *d)
 {
     if (!hb_bits(d, 1)) return 1;
@@ -950,7 +1021,14 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
     if (layno < rl->band[0].prec[precno].decoded_layers)
         return 0;
     rl->band[0].prec[precno].decoded_layers = layno + 1;
-    select_part(d, ps, cs->csty);
+    Tile *pt = ps->t;
+    if (d->has_ppm)                                       /* :1147-1153 */
+        select_header(d, ps);
+    else if (pt->has_ppt) {
+        d->bp = pt->ppt + pt->ppt_pos;
+        d->bend = pt->ppt + pt->ppt_size;
+    } else
+        select_part(d, ps, cs->csty);
 
     struct Inc { Cblk *cb; int nseg; int seg[8]; } *incs = NULL;
     int ninc = 0, capinc = 0;
@@ -1086,6 +1164,14 @@ finish:
     if (cs->csty & 4)                                     /* EPH */
         if (d->bend - d->bp >= 2 && rd16(d->bp) == 0xFF92)
             d->bp += 2;
+    if (d->has_ppm) {                                     /* save the header stream, go on in the data (:1474-1480) */
+        pt->part[ps->tp].hp = d->bp;
+        pt->part[ps->tp].hend = d->bend;
+        select_part(d, ps, cs->csty);
+    } else if (pt->has_ppt) {
+        pt->ppt_pos = (size_t)(d->bp - pt->ppt);
+        select_part(d, ps, cs->csty);
+    }
     for (int i = 0; i < ninc; i++) {
         Cblk *cb = incs[i].cb;
         for (int s = 0; s < incs[i].nseg; s++) {
@@ -1442,10 +1528,13 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
 static void free_dec(Dec *d)
 {
     if (d->tile) {
-        for (int i = 0; i < d->ntx * d->nty; i++)
+        for (int i = 0; i < d->ntx * d->nty; i++) {
             free_tile(d, &d->tile[i]);
+            free(d->tile[i].ppt);
+        }
         free(d->tile);
     }
+    free(d->ppm);
 }
 
 int oracle_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint8_t *out, int64_t cap)

@@ -98,7 +98,7 @@ static int g_loglevel_set;
 static AVCodecContext *ctx_open(int bitexact)
 {
     if (!g_loglevel_set) {
-        av_log_set_level(AV_LOG_FATAL);
+        av_log_set_level(getenv("REF_LOG") ? atoi(getenv("REF_LOG")) : AV_LOG_FATAL);   /* REF_LOG=32: the reference's own messages */
         g_loglevel_set = 1;
     }
     AVCodecContext *avctx = av_mallocz(sizeof(*avctx));

@@ -12,7 +12,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import (LAYERED, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, poc_stream,
+from test_oracle_vs_ref import (LAYERED, PACKED, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, packed_stream, poc_stream,
                                 subsampled_stream)
 
 pytestmark = pytest.mark.gpu
@@ -222,6 +222,24 @@ def test_golden_frames_wide():
     assert n >= 35
 
 
+def test_golden_frames_packed():
+    """Reference-generated vectors: packed packet headers (PPT / PPM), damaged PPT / PPM markers, missing tiles."""
+    z = np.load(GOLDEN / "frames_packed.npz")
+    n = 0
+    for key, (cs, meta, pix, out) in _groups(z, ["cs", "meta", "pix", "out"]):
+        flags = int(key.split("|")[1])
+        with fb.Jpeg2000Decoder(device=0, slots=1, bitexact=bool(flags & 1)) as d:
+            if meta[2] < 0:
+                with pytest.raises(fb.DecodeError):
+                    d.decode(cs.tobytes())
+            else:
+                info, got = d.decode(cs.tobytes())
+                assert (info.width, info.height, info.pix_name) == (meta[0], meta[1], pix.tobytes().decode()), key
+                assert np.array_equal(got, out), key
+        n += 1
+    assert n >= 25
+
+
 @pytest.mark.parametrize("cfg", STREAMS, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])
 def test_frames_vs_oracle(cfg, dec, dec_bitexact):
     cfg = dict(cfg)
@@ -329,6 +347,20 @@ def test_two_layer_frames_vs_oracle(cfg, dec, dec_bitexact):
     if cfg.get("reversible", True) and cfg.get("npasses", 1) == 1:
         img = got.view(np.uint16 if bd > 8 else np.uint8).reshape(h, w, nc)
         assert np.array_equal(img >> ((16 - bd) if bd > 8 else 0), np.stack(planes, -1))
+
+
+@pytest.mark.parametrize("t", PACKED, ids=lambda t: f"{'ppt' if t['mode'] == 1 else 'ppm'}-{t['chunk']}")
+def test_packed_header_frames_vs_oracle(t, dec, dec_bitexact):
+    """Packet headers packed into PPT / PPM marker segments: same pixels as the plain stream."""
+    cs, base = packed_stream(t)
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r, oinfo, want = oracle_decode(cs, bitexact)
+        assert r == 0
+        d = dec_bitexact if bitexact else dec
+        info, got = d.decode(cs)
+        assert (info.width, info.height) == (oinfo[0], oinfo[1])
+        assert np.array_equal(got, want)
+        assert np.array_equal(d.decode(base)[1], want)
 
 
 @pytest.mark.parametrize("t", POC_STREAMS, ids=lambda t: "-".join("".join(map(str, e)) for e in t["poc"]))

@@ -11,8 +11,8 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import (LAYERED, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, poc_marker_cases,
-                                poc_stream,
+from test_oracle_vs_ref import (LAYERED, PACKED, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS,
+                                packed_marker_cases, packed_stream, poc_marker_cases, poc_stream,
                                 subsampled_stream)
 
 
@@ -258,6 +258,46 @@ def test_poc_marker_validation_matches_oracle():
             assert r == 0 and np.array_equal(pic, opic)
         except fb.DecodeError as e:
             assert r < 0 and e.code < 0
+
+
+@pytest.mark.parametrize("t", PACKED, ids=lambda t: f"{'ppt' if t['mode'] == 1 else 'ppm'}-{t['chunk']}")
+def test_plan_of_packed_header_streams(t):
+    """PPT / PPM: packet headers are read from the marker segments, bodies stay referenced in place."""
+    cs, _ = packed_stream(t)
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r, oinfo, opic = oracle_decode(cs, bitexact)
+        assert r == 0
+        info, pic = picture_from_plan(cs, fb.FLAG_BITEXACT if bitexact else 0)
+        assert np.array_equal(pic, opic)
+
+
+def test_packed_header_marker_validation_matches_oracle():
+    n_ok = 0
+    for bad in packed_marker_cases():
+        r, _, opic = oracle_decode(bad)
+        try:
+            _, pic = picture_from_plan(bad, 0)
+            assert r == 0 and np.array_equal(pic, opic)
+            n_ok += 1
+        except fb.DecodeError as e:
+            assert r < 0 and e.code < 0
+    assert n_ok >= 2
+
+
+def test_tile_without_first_tile_part_fails_like_the_reference():
+    """A tile that never gets a tile-part with TPsot = 0 has no coding style: the reference's init_tile returns
+    AVERROR_INVALIDDATA for the frame (jpeg2000dec.c:862-869, :1054-1055)."""
+    planes = j2kgen.synth_image(96, 64, 3, 8, seed=5)
+    cs = j2kgen.encode(planes, 8, j2kgen.EncParams(levels=2, tile=(64, 64)))
+    sot = [i for i in range(len(cs) - 3) if cs[i:i + 4] == b"\xff\x90\x00\x0a"]
+    assert len(sot) == 2
+    renumbered = bytearray(cs)
+    renumbered[sot[1] + 10] = 1                                   # the second tile only has "tile-part 1"
+    for bad in (cs[:sot[1]], cs[:sot[1] + 3], bytes(renumbered)):
+        assert oracle_decode(bad)[0] == fb.ERR_INVALIDDATA
+        with pytest.raises(fb.DecodeError) as e:
+            fb.plan(bad, 0)
+        assert e.value.code == fb.ERR_INVALIDDATA
 
 
 @pytest.mark.parametrize("name,subs,bd", SUBSAMPLED, ids=[s[0] for s in SUBSAMPLED])

@@ -276,6 +276,91 @@ def test_poc_marker_validation_matches_reference():
     assert sum(ref_decode(bad, 0)[0] == 0 for bad in cases) >= 3
 
 
+# packed packet headers: PPT (tile-part header) and PPM (main header); chunk = payload bytes per marker segment
+PACKED = [
+    dict(cfg=dict(levels=3, tile=(128, 64), sop=True, eph=True), mode=1, chunk=0),
+    dict(cfg=dict(levels=3, tile=(128, 64), sop=True, eph=True), mode=2, chunk=0),
+    dict(cfg=dict(levels=4, cblk=(32, 32), layers=2, npasses=3, eph=True), mode=1, chunk=41),
+    dict(cfg=dict(levels=4, cblk=(32, 32), layers=2, npasses=3), mode=2, chunk=41),
+    dict(cfg=dict(levels=3, precincts=[(5, 5), (6, 6)], cblk=(16, 16), prog=2, tile=(96, 96)), mode=1, chunk=7),
+    dict(cfg=dict(levels=3, precincts=[(5, 5), (6, 6)], cblk=(16, 16), prog=4, tile=(96, 96)), mode=2, chunk=300),
+    dict(cfg=dict(levels=2, reversible=False, base_step=1.0, tile=(100, 60), sop=True), mode=1, chunk=0),
+    dict(cfg=dict(levels=2, reversible=False, base_step=1.0, poc=[(0, 1, 1, 3, 3, 1), (0, 0, 1, 3, 1, 0)]), mode=2, chunk=64),
+]
+
+
+def packed_stream(t, w=200, h=120, nc=3, bd=10, seed=6):
+    """-> (the stream with its packet headers in PPT / PPM marker segments, the same picture as a plain stream)"""
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=seed)
+    base = j2kgen.encode(planes, bd, j2kgen.EncParams(**t["cfg"]))
+    cs = j2kgen.encode(planes, bd, j2kgen.EncParams(packed_headers=t["mode"], ppx_chunk=t["chunk"], **t["cfg"]))
+    return cs, base
+
+
+@pytest.mark.parametrize("t", PACKED, ids=lambda t: f"{'ppt' if t['mode'] == 1 else 'ppm'}-{t['chunk']}-" + "-".join(
+    f"{k}{v}" for k, v in t["cfg"].items())[:40])
+def test_packed_header_streams_bit_exact(t):
+    """PPT / PPM (jpeg2000dec.c:958-1014, :1099-1108, :1147-1153, :1474-1480, :2467-2476): the reference decodes
+    the stream with packed headers to the pixels of the plain one, the oracle agrees."""
+    cs, base = packed_stream(t)
+    assert (b"\xff\x61" if t["mode"] == 1 else b"\xff\x60") in cs[:cs.index(b"\xff\x93")]
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r0, _, out0, _ = ref_decode(base, bitexact)
+        r1, info1, out1, name = ref_decode(cs, bitexact)
+        r2, info2, out2 = oracle_decode(cs, bitexact)
+        assert r0 == 0 and r1 == 0 and r2 == 0
+        assert np.array_equal(out0, out1)
+        assert info1[:2] == info2[:2] and oracle_pix_name() == name and np.array_equal(out1, out2)
+
+
+def packed_marker_cases():
+    """Marker-level damage: PPT in a HOMOGENEOUS stream (Ccap15 bit 11 clear), PPT next to PPM, a PPM run longer than
+    the data, a truncated PPM / PPT payload (headers run dry), PPM inside a tile-part header, too short segments."""
+    planes = j2kgen.synth_image(96, 64, 3, 8, seed=5)
+    kw = dict(levels=2, tile=(64, 64), eph=True)
+    ppt = j2kgen.encode(planes, 8, j2kgen.EncParams(packed_headers=1, **kw))
+    ppm = j2kgen.encode(planes, 8, j2kgen.EncParams(packed_headers=2, **kw))
+    cases = []
+    cap = ppt.index(b"\xff\x50")
+    b = bytearray(ppt); b[cap + 8] &= 0xF7; cases.append(bytes(b))                  # Ccap15 bit 11 cleared
+    at = ppm.index(b"\xff\x60")
+    n = int.from_bytes(ppm[at + 2:at + 4], "big")
+    seg = ppm[at:at + 2 + n]
+    sot = ppt.index(b"\xff\x90")
+    cases.append(ppt[:sot] + seg + ppt[sot:])                                        # PPM in the main header + PPT
+    b = bytearray(ppm); b[at + 5:at + 9] = (1 << 20).to_bytes(4, "big"); cases.append(bytes(b))   # Nppm too large
+    cases.append(ppm[:at + 2] + (n - 9).to_bytes(2, "big") + ppm[at + 4:at + 2 + n - 9] + ppm[at + 2 + n:])   # PPM cut short
+    pt = ppt.index(b"\xff\x61")
+    m = int.from_bytes(ppt[pt + 2:pt + 4], "big")
+    cases.append(ppt[:pt + 2] + (m - 5).to_bytes(2, "big") + ppt[pt + 4:pt + 2 + m - 5] + ppt[pt + 2 + m:])   # PPT cut short,
+    #   Psot now 5 too large: the next SOT is missed, tile 1 never gets a first tile-part (init_tile fails, :1054)
+    for cut in (2, 5, 20):                                                           # PPT cut short, Psot corrected:
+        b = bytearray(ppt[:pt + 2] + (m - cut).to_bytes(2, "big") + ppt[pt + 4:pt + 2 + m - cut] + ppt[pt + 2 + m:])
+        so = b.index(b"\xff\x90")                                                    # the last headers read as zeros
+        b[so + 6:so + 10] = (int.from_bytes(b[so + 6:so + 10], "big") - cut).to_bytes(4, "big")
+        cases.append(bytes(b))
+    sod = ppm.index(b"\xff\x93")
+    cases.append(ppm[:sod] + seg + ppm[sod:])                                        # PPM in a tile-part header
+    cases.append(ppm[:at] + b"\xff\x60\x00\x02" + ppm[at:])                         # Lppm = 2
+    cases.append(ppt[:pt] + b"\xff\x61\x00\x02" + ppt[pt:])                         # Lppt = 2
+    cases.append(ppm[:at] + b"\xff\x60\x00\x03\x07" + ppm[at:])                     # empty PPM segment in front
+    b = bytearray(ppm); b[at + 5:at + 9] = (0).to_bytes(4, "big"); cases.append(bytes(b))         # Nppm = 0
+    return cases
+
+
+def test_packed_header_marker_validation_matches_reference():
+    cases = packed_marker_cases()
+    verdicts = []
+    for bad in cases:
+        r1, _, out1, _ = ref_decode(bad, 0)
+        r2, _, out2 = oracle_decode(bad, 0)
+        verdicts.append(r1)
+        assert (r1 == 0) == (r2 == 0), (len(verdicts), r1, r2)
+        if r1 == 0:
+            assert np.array_equal(out1, out2), len(verdicts)
+    assert sum(v != 0 for v in verdicts) >= 4 and sum(v == 0 for v in verdicts) >= 2, verdicts
+
+
 # chroma-subsampled streams (XRsiz / YRsiz > 1): (name, [(XRsiz, YRsiz)], bit depth) -> the planar YUV(A) formats
 SUBSAMPLED = [("420", [(1, 1), (2, 2), (2, 2)], 8), ("422", [(1, 1), (2, 1), (2, 1)], 10), ("440", [(1, 1), (1, 2), (1, 2)], 8),
               ("411", [(1, 1), (4, 1), (4, 1)], 8), ("410", [(1, 1), (4, 4), (4, 4)], 8),

@@ -58,6 +58,11 @@ typedef struct J2kGenParams {
                                   * poc_split > 0 puts the first poc_split entries into a POC segment of their own */
     int32_t poc[8][6];           /* RSpoc, CSpoc, LYEpoc, REpoc, CEpoc, Ppoc */
     int32_t poc_split;
+    int32_t packed_headers;      /* 0: packet headers in front of their bodies.  1: PPT -- the packet headers of a tile
+                                  * (EPH markers included) move into PPT marker segments of its tile-part header and
+                                  * Ccap15 bit 11 is set (jpeg2000dec.c:2605-2617).  2: PPM -- into PPM marker segments
+                                  * of the main header, one Nppm-prefixed run per tile-part (:958-980, :2467-2472) */
+    int32_t ppx_chunk;           /* payload bytes per PPT / PPM marker segment (0 = as many as fit: 65532) */
 } J2kGenParams;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -930,8 +935,12 @@ static int contribution(const J2kGenParams *P, const CodedBlock *cb, int layer)
     }
 }
 
+/* where write_packet puts packet headers when they are packed (PPT / PPM); NULL = in front of the body */
+static __thread Buf *packed_hdr_target;
+
 static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precno, int layer, int *sop_counter)
 {
+    Buf *hb = packed_hdr_target ? packed_hdr_target : out;
     if (P->sop) {
         buf_put16(out, 0xFF91); buf_put16(out, 4); buf_put16(out, (*sop_counter)++ & 0xFFFF);
     }
@@ -944,11 +953,11 @@ static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precn
             any |= contribution(P, &pr->cb[i], layer) != 0;
     }
     BitW w;
-    bw_init(&w, out);
+    bw_init(&w, hb);
     if (!any) {
         bw_put(&w, 0, 1);
         bw_flush(&w);
-        if (P->eph) buf_put16(out, 0xFF92);
+        if (P->eph) buf_put16(hb, 0xFF92);
         return 0;
     }
     bw_put(&w, 1, 1);
@@ -1020,7 +1029,7 @@ static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precn
         }
     }
     bw_flush(&w);
-    if (P->eph) buf_put16(out, 0xFF92);
+    if (P->eph) buf_put16(hb, 0xFF92);
     for (int b = 0; b < rl->nbands; b++) {
         Band *bd = &rl->band[b];
         if (bd->x0 == bd->x1 || bd->y0 == bd->y1) continue;
@@ -1090,7 +1099,7 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
     {
         int magb_bits = 0;   /* the reference only range-checks MAGB (jpeg2000dec.c:473-486) */
         buf_put16(&out, 0xFF50); buf_put16(&out, 8); buf_put32(&out, 0x00020000);
-        buf_put16(&out, (P->reversible ? 0 : 0x0020) | magb_bits);
+        buf_put16(&out, (P->reversible ? 0 : 0x0020) | (P->packed_headers == 1 ? 0x0800 : 0) | magb_bits);
     }
     buf_put16(&out, 0xFF52);
     buf_put16(&out, 12 + (P->use_precincts ? L + 1 : 0));
@@ -1134,6 +1143,9 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
             a += n;
         }
     }
+
+    const size_t main_end = out.n;       /* PPM marker segments are inserted here once the tiles are written */
+    Buf ppm = { 0 };
 
     /* ---- tiles ---- */
     for (int ty = 0; ty < nty; ty++)
@@ -1294,22 +1306,39 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
                     }
                 }
             }
-            /* tile-part: SOT, SOD, packets */
-            size_t sot_pos = out.n;
-            buf_put16(&out, 0xFF90); buf_put16(&out, 10); buf_put16(&out, tileno); buf_put32(&out, 0);
-            buf_put(&out, 0); buf_put(&out, 1);
-            buf_put16(&out, 0xFF93);
+            /* tile-part: SOT, [PPT], SOD, packets */
+            Buf body = { 0 }, phdr = { 0 };
+            packed_hdr_target = P->packed_headers ? &phdr : NULL;
             int sopc = 0;
             int maxnp = 0;
             for (int c = 0; c < C; c++) for (int r = 0; r <= L; r++) maxnp = imax(maxnp, res[c][r].npx * res[c][r].npy);
             if (P->npoc > 0) {
                 for (int i = 0; i < P->npoc; i++)
-                    sequence_packets(&out, P, res, C, L, tx0, ty0, tx1, ty1, P->poc[i][0], P->poc[i][1],
+                    sequence_packets(&body, P, res, C, L, tx0, ty0, tx1, ty1, P->poc[i][0], P->poc[i][1],
                                      imin(P->poc[i][2], NLAY), P->poc[i][3], P->poc[i][4] ? imin(P->poc[i][4], C) : C,
                                      P->poc[i][5], &sopc);
             } else {
-                sequence_packets(&out, P, res, C, L, tx0, ty0, tx1, ty1, 0, 0, NLAY, L + 1, C, P->prog, &sopc);
+                sequence_packets(&body, P, res, C, L, tx0, ty0, tx1, ty1, 0, 0, NLAY, L + 1, C, P->prog, &sopc);
             }
+            packed_hdr_target = NULL;
+            size_t sot_pos = out.n;
+            buf_put16(&out, 0xFF90); buf_put16(&out, 10); buf_put16(&out, tileno); buf_put32(&out, 0);
+            buf_put(&out, 0); buf_put(&out, 1);
+            if (P->packed_headers == 1) {
+                const size_t chunk = P->ppx_chunk > 0 ? (size_t)imin(P->ppx_chunk, 65532) : 65532;
+                int z = 0;
+                for (size_t at = 0; at < phdr.n || z == 0; at += chunk, z++) {
+                    const size_t n = phdr.n - at < chunk ? phdr.n - at : chunk;
+                    buf_put16(&out, 0xFF61); buf_put16(&out, (unsigned)(3 + n)); buf_put(&out, z & 255);
+                    buf_append(&out, phdr.p + at, n);
+                }
+            } else if (P->packed_headers == 2) {
+                buf_put32(&ppm, (uint32_t)phdr.n);
+                buf_append(&ppm, phdr.p, phdr.n);
+            }
+            buf_put16(&out, 0xFF93);
+            buf_append(&out, body.p, body.n);
+            free(body.p); free(phdr.p);
             uint32_t psot = (uint32_t)(out.n - sot_pos);
             out.p[sot_pos + 6] = psot >> 24; out.p[sot_pos + 7] = psot >> 16;
             out.p[sot_pos + 8] = psot >> 8;  out.p[sot_pos + 9] = psot;
@@ -1335,6 +1364,23 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
             free(tp);
         }
     buf_put16(&out, 0xFFD9);
+    if (P->packed_headers == 2) {
+        /* PPM marker segments go to the end of the main header: Zppm, then the Nppm-prefixed runs cut into chunks */
+        Buf seg = { 0 };
+        const size_t chunk = P->ppx_chunk > 0 ? (size_t)imin(P->ppx_chunk, 65532) : 65532;
+        int z = 0;
+        for (size_t at = 0; at < ppm.n; at += chunk, z++) {
+            const size_t n = ppm.n - at < chunk ? ppm.n - at : chunk;
+            buf_put16(&seg, 0xFF60); buf_put16(&seg, (unsigned)(3 + n)); buf_put(&seg, z & 255);
+            buf_append(&seg, ppm.p + at, n);
+        }
+        buf_reserve(&out, seg.n);
+        memmove(out.p + main_end + seg.n, out.p + main_end, out.n - main_end);
+        memcpy(out.p + main_end, seg.p, seg.n);
+        out.n += seg.n;
+        free(seg.p);
+    }
+    free(ppm.p);
     int64_t n = (int64_t)out.n;
     if (n <= cap)
         memcpy(outbuf, out.p, out.n);

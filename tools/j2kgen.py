@@ -31,6 +31,7 @@ class _Params(ctypes.Structure):
         ("stats_max_lcup", ctypes.c_int32), ("error", ctypes.c_int32),
         ("layers", ctypes.c_int32), ("sub_x", ctypes.c_int32 * 4), ("sub_y", ctypes.c_int32 * 4),
         ("npoc", ctypes.c_int32), ("poc", (ctypes.c_int32 * 6) * 8), ("poc_split", ctypes.c_int32),
+        ("packed_headers", ctypes.c_int32), ("ppx_chunk", ctypes.c_int32),
     ]
 
 
@@ -76,6 +77,8 @@ class EncParams:
     subsampling: list | None = None   # [(XRsiz, YRsiz)] per component; plane c is ceil(W/XRsiz) x ceil(H/YRsiz)
     poc: list | None = None       # [(RSpoc, CSpoc, LYEpoc, REpoc, CEpoc, Ppoc)]: POC marker; packets follow the entries
     poc_split: int = 0            # > 0: the first poc_split entries go into a POC segment of their own
+    packed_headers: int = 0       # 1: packet headers in PPT marker segments (tile-part header), 2: in PPM (main header)
+    ppx_chunk: int = 0            # payload bytes per PPT / PPM marker segment (0 = 65532)
     stats: dict = field(default_factory=dict)
 
 
@@ -113,6 +116,7 @@ def encode(planes, bitdepth: int, p: EncParams) -> bytes:
             for i, e in enumerate(p.poc):
                 for k in range(6):
                     P.poc[i][k] = e[k]
+        P.packed_headers, P.ppx_chunk = p.packed_headers, p.ppx_chunk
         cap = int(w * h * len(planes) * 4 + (1 << 20))
         out = np.empty(cap, np.uint8)
         ptrs = (ctypes.c_void_p * len(planes))(*[a.ctypes.data for a in planes])
