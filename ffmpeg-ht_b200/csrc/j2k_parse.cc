@@ -854,7 +854,7 @@ int Parser::build_geometry(int flags)
                         bdesc.i_stepsize = (int32_t)floorf(fstep * (1 << 15));
                         const int downshift = 31 - imax(M_b, 0);
                         float fscale = fstep;
-                        fscale /= (float)(1 << imin(downshift, 30));
+                        fscale /= (float)(1 << imax(0, imin(downshift, 30)));   /* an empty band may carry any M_b: its constants are never used */
                         bdesc.fscale = fscale;
                         float s = fscale;
                         s *= (float)(1 << 6);
