@@ -37,6 +37,13 @@ int oracle_ht_block(const uint8_t *data, int length, int npasses, int Lcup, int 
                     int w, int h, int M_b, int roi_shift, int vsc, int32_t *out);
 
 /* W1-W4: inverse DWT of one Mallat-layout plane, border = {x0,x1,y0,y1} (jpeg2000dwt.c:539-620) */
+/* Part-1 (EBCOT / MQ) code-block of style 0 -> the same sign-magnitude words (decode_cblk, jpeg2000dec.c:1993-2089).
+ * nonzerobits = expn + guard bits - 1 - (zero bit-planes - ROI shift of component 0); bandpos 0 LL, 1 HL, 2 LH, 3 HH;
+ * out: w * h words, row stride w.  0 = no data, 1 = decoded, ORACLE_ERR_INVALID = the bit-plane counter left its
+ * range ("bpno became invalid"): out holds what was decoded until then, which the reference dequantises as it is. */
+int oracle_mq_block(const uint8_t *data, int length, int npasses, int nonzerobits, int w, int h, int bandpos,
+                    int M_b, int roi_shift, int32_t *out);
+
 int oracle_idwt(int type, const int *border, int levels, void *data);
 
 /* M1-M3: inverse component transform in place (jpeg2000dsp.c:43-91) */

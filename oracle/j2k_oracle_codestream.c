@@ -1090,6 +1090,18 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
 
             int segment_passes, next_segment_passes = 0, bits;
             unsigned segment_bytes = 0;
+            if (!(cs->cblk_style & 0x40)) {
+                /* Part-1 block: with neither restart nor bypass there is one codeword segment and one length
+                 * of lblock + floor(log2(passes)) bits per packet (:1364-1368); the others are not restated */
+                if (cs->cblk_style & (0x01 | 0x04)) {
+                    ret = ORACLE_ERR_PATCH;
+                    goto fail;
+                }
+                segment_bytes = (unsigned)hb_bits(d, cb->lblock + ilog2(newpasses));
+                cb->npasses += newpasses;
+                in->seg[in->nseg++] = (int)segment_bytes;
+                continue;
+            }
             if (cb->plhd) {                               /* :1256-1340, non-MIXED */
                 int href = (cb->npasses + newpasses - 1) % 3;
                 segment_passes = newpasses - href;
@@ -1458,11 +1470,22 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
                     for (int k = 0; k < pr->ncw * pr->nch; k++) {
                         Cblk *cb = &pr->cb[k];
                         const int bw = cb->x1 - cb->x0, bh = cb->y1 - cb->y0;
-                        if (!(cs->cblk_style & 0x40)) {
-                            free(t1);
-                            return ORACLE_ERR_PATCH;      /* Part-1 MQ block: outside this path */
-                        }
                         static const uint8_t none[8];
+                        if (!(cs->cblk_style & 0x40)) {   /* Part-1 block (decode_cblk, :2270-2275) */
+                            if (cs->cblk_style) {         /* reset / causal / segmentation symbols: not restated */
+                                free(t1);
+                                return ORACLE_ERR_PATCH;
+                            }
+                            const int nonzerobits = M_b - (cb->zbp - t->comp[0].roi_shift);
+                            if (oracle_mq_block(cb->data ? cb->data : none, cb->length, cb->npasses, nonzerobits, bw, bh,
+                                                b + (r > 0), M_b, comp->roi_shift, t1)) {
+                                coded = 1;
+                                d->nblocks++;
+                                dequantise(t1, bw, bh, comp->data, W, cb->x0 - bd->c.x0, cb->y0 - bd->c.y0,
+                                           cs->transform, bd, M_b);
+                            }
+                            continue;
+                        }
                         int ret = oracle_ht_block(cb->data ? cb->data : none, cb->length, cb->npasses, cb->Lcup,
                                                   cb->Lref, cb->zbp, bw, bh, M_b, comp->roi_shift,
                                                   cs->cblk_style & 8, t1);

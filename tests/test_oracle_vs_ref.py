@@ -361,6 +361,85 @@ def test_packed_header_marker_validation_matches_reference():
     assert sum(v != 0 for v in verdicts) >= 4 and sum(v == 0 for v in verdicts) >= 2, verdicts
 
 
+# ---- Part-1 (EBCOT / MQ) code-blocks: SURVEY 8(f) row N4 ----------------------------------------------------
+# The reference has no HT encoder and this repo's test encoder writes HT only, so Part-1 streams come from an
+# independent encoder: OpenJPEG through Pillow (code-block style 0: no bypass / restart / reset / causal / segsym).
+PART1 = [
+    dict(mode="RGB", w=100, h=80, kw=dict(irreversible=False)),
+    dict(mode="RGB", w=100, h=80, kw=dict(irreversible=True, quality_mode="rates", quality_layers=[8])),
+    dict(mode="RGB", w=131, h=77, kw=dict(irreversible=False, num_resolutions=3, codeblock_size=(32, 32), progression="RPCL",
+                                          precinct_size=(64, 64))),
+    dict(mode="RGB", w=200, h=120, kw=dict(irreversible=False, quality_mode="rates", quality_layers=[20, 8, 1],
+                                           tile_size=(64, 64))),
+    dict(mode="RGB", w=200, h=120, kw=dict(irreversible=True, quality_mode="rates", quality_layers=[40, 10], progression="CPRL",
+                                           tile_size=(128, 96), codeblock_size=(16, 64))),
+    dict(mode="L", w=97, h=61, kw=dict(irreversible=False, num_resolutions=1)),
+    dict(mode="L", w=160, h=90, kw=dict(irreversible=True, quality_mode="dB", quality_layers=[38], progression="PCRL")),
+    dict(mode="I;16", w=150, h=100, kw=dict(irreversible=False, codeblock_size=(64, 64))),
+    dict(mode="I;16", w=150, h=100, kw=dict(irreversible=True, quality_mode="rates", quality_layers=[6], progression="RLCP")),
+    dict(mode="RGBA", w=120, h=70, kw=dict(irreversible=False, mct=1, codeblock_size=(4, 4), num_resolutions=2)),
+    dict(mode="RGB", w=180, h=100, kw=dict(irreversible=False, offset=(13, 7), tile_offset=(5, 3), tile_size=(80, 60))),
+    dict(mode="LA", w=64, h=64, kw=dict(irreversible=False)),
+    dict(mode="RGB", w=256, h=200, kw=dict(irreversible=False, codeblock_size=(1024, 4), num_resolutions=2)),
+]
+
+
+def part1_stream(t, jp2=False, seed=9):
+    """A Part-1 codestream (or JP2 file) of synthetic content from OpenJPEG via Pillow."""
+    import io
+
+    from PIL import Image
+    nc = {"L": 1, "I;16": 1, "LA": 2, "RGB": 3, "RGBA": 4}[t["mode"]]
+    bd = 16 if t["mode"] == "I;16" else 8
+    planes = j2kgen.synth_image(t["w"], t["h"], nc, bd, seed=seed)
+    if t["mode"] == "I;16":
+        im = Image.fromarray(planes[0].astype(np.uint16))
+    else:
+        a = np.stack(planes, -1).astype(np.uint8)
+        im = Image.fromarray(a[..., 0] if nc == 1 else a, t["mode"])
+    b = io.BytesIO()
+    im.save(b, "JPEG2000", no_jp2=not jp2, **t["kw"])
+    return b.getvalue()
+
+
+@pytest.mark.parametrize("t", PART1, ids=lambda t: f"{t['mode']}-{t['w']}x{t['h']}-" + "-".join(
+    f"{k[:4]}{v}" for k, v in t["kw"].items())[:50])
+def test_part1_streams_bit_exact(t):
+    """MQ decoder, context formation, the three coding passes, T2 lengths of non-HT blocks
+    (jpeg2000dec.c:1364-1368, :1872-2089; mqcdec.c): reference == oracle, float and fixed-point 9/7."""
+    for jp2 in (False, True):
+        cs = part1_stream(t, jp2)
+        for bitexact in ((0,) if not t["kw"].get("irreversible") else (0, 1)):
+            r1, info1, out1, name = ref_decode(cs, bitexact)
+            r2, info2, out2 = oracle_decode(cs, bitexact)
+            assert r1 == 0 and r2 == 0, (r1, r2)
+            assert info1[:2] == info2[:2] and oracle_pix_name() == name and np.array_equal(out1, out2)
+
+
+def test_part1_damaged_streams_match_reference():
+    """Byte damage inside the packets: the MQ decoder runs into the 0xFF 0xFF sentinel, lengths go wrong, the
+    bit-plane counter may leave its range -- same verdict and same pixels as the reference."""
+    rng = np.random.default_rng(77)
+    n_ok = 0
+    for t in (PART1[0], PART1[3], PART1[7], PART1[4]):
+        cs = part1_stream(t)
+        sod = cs.index(b"\xff\x93")
+        for k in range(12):
+            bad = bytearray(cs)
+            for _ in range(int(rng.integers(1, 6))):
+                bad[int(rng.integers(sod + 2, len(bad) - 2))] = int(rng.integers(0, 256))
+            if k % 4 == 3:
+                bad = bad[:int(rng.integers(sod + 10, len(bad)))]
+            bad = bytes(bad)
+            r1, info1, out1, _ = ref_decode(bad, 0)
+            r2, info2, out2 = oracle_decode(bad, 0)
+            assert (r1 == 0) == (r2 == 0), (t["mode"], k, r1, r2)
+            if r1 == 0:
+                assert np.array_equal(out1, out2), (t["mode"], k)
+                n_ok += 1
+    assert n_ok >= 20
+
+
 # chroma-subsampled streams (XRsiz / YRsiz > 1): (name, [(XRsiz, YRsiz)], bit depth) -> the planar YUV(A) formats
 SUBSAMPLED = [("420", [(1, 1), (2, 2), (2, 2)], 8), ("422", [(1, 1), (2, 1), (2, 1)], 10), ("440", [(1, 1), (1, 2), (1, 2)], 8),
               ("411", [(1, 1), (4, 1), (4, 1)], 8), ("410", [(1, 1), (4, 4), (4, 4)], 8),
