@@ -96,7 +96,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
  * run in step. */
 struct HtPlan {
     std::vector<uint32_t> order, scr_off;
-    int n_refine = 0, n_coded = 0, n_zero = 0, n_wide = 0, n_rwide = 0;
+    int n_refine = 0, n_coded = 0, n_zero = 0, n_wide = 0, n_rwide = 0, n_mq = 0;
     int maxL_fast = 0, maxLref = 0, maxL_wide = 0, maxL_rwide = 0;
     size_t scratch_words = 0;
     /* descriptor indices sorted by quad-grid shape; depends on the geometry only */
@@ -106,7 +106,9 @@ struct HtPlan {
     static int klass(const CblkDesc &d)
     {
         if (d.flags & J2K_CBLK_SKIP)
-            return 5;                               /* dropped by lowres: no kernel touches it */
+            return 6;                               /* dropped by lowres: no kernel touches it */
+        if (d.flags & J2K_CBLK_MQ)                  /* Part-1 block: own kernel; without data it only needs zeros */
+            return d.npasses && d.length ? 5 : 2;
         const bool refine = d.npasses && (d.npasses % 3) != 1;
         if (d.w > 64)
             return refine ? 4 : 3;
@@ -131,12 +133,12 @@ struct HtPlan {
         scr_off.resize(n);
         maxL_fast = maxLref = maxL_wide = maxL_rwide = 0;
         scratch_words = 0;
-        size_t cnt[6] = { 0, 0, 0, 0, 0, 0 };
+        size_t cnt[7] = { 0, 0, 0, 0, 0, 0, 0 };
         for (size_t i = 0; i < n; i++)
             cnt[klass(cblk[i])]++;
-        size_t at[6];
+        size_t at[7];
         at[0] = 0;
-        for (int k = 1; k < 6; k++)
+        for (int k = 1; k < 7; k++)
             at[k] = at[k - 1] + cnt[k - 1];
         for (size_t k = 0; k < n; k++) {
             const uint32_t i = by_shape[k];
@@ -160,6 +162,7 @@ struct HtPlan {
         n_zero = (int)cnt[2];
         n_wide = (int)cnt[3];
         n_rwide = (int)cnt[4];
+        n_mq = (int)cnt[5];
     }
 };
 
@@ -177,6 +180,9 @@ int run_ht(cudaStream_t st, const HtPlan &hp, const CblkDesc *d_cblk, const uint
     const uint32_t *o_wide = d_order + hp.n_refine + hp.n_coded + hp.n_zero;
     r = launch_ht_decode(st, false, d_cblk, o_wide, hp.n_wide, d_bytes, d_bands, coef, status, hp.maxL_wide, max_w, max_area,
                          max_state);
+    if (r < 0) return r;
+    launches += r;
+    r = launch_mq_blocks(st, d_cblk, o_wide + hp.n_wide + hp.n_rwide, hp.n_mq, d_bytes, d_bands, coef, status);
     if (r < 0) return r;
     launches += r;
     if (ev) cudaEventRecord(ev[3], st);

@@ -43,6 +43,11 @@ int launch_ht_refine(cudaStream_t stream, const CblkDesc *descs, const uint32_t 
                      int n_refine, const uint8_t *bytes, const BandDesc *bands, void *scratch, void *coef,
                      int32_t *status, int max_Lcup);
 
+/* Part-1 (EBCOT / MQ) code-blocks of style 0 (mq_block.cu): order[0..nblocks) lists descriptors flagged
+ * J2K_CBLK_MQ that carry data; one warp per block, dequantisation fused into the write-back. */
+int launch_mq_blocks(cudaStream_t stream, const CblkDesc *descs, const uint32_t *order, int nblocks, const uint8_t *bytes,
+                     const BandDesc *bands, void *coef, int32_t *status);
+
 /* Inverse DWT levels + final MCT / level shift / clip / pack.
  * tcs/groups: device copies of the plan tables.  coefA: HT output (Mallat layout), coefB/coefC: LL
  * ping-pong, picture: packed output.  Returns the number of kernels queued or < 0. */

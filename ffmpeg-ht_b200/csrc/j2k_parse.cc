@@ -773,8 +773,11 @@ int Parser::build_geometry(int flags)
                 return B200J2K_ERR_INVALIDDATA;
             if (h.isHT && h.cap_b14 != (cs.cblk_style >> 6) && h.cap_b14 != 0)
                 return B200J2K_ERR_INVALIDDATA;
-            if (!(cs.cblk_style & 0x40) || (cs.cblk_style & 0x80))
-                return B200J2K_ERR_PATCHWELCOME;          /* Part-1 MQ or MIXED code-blocks */
+            if (cs.cblk_style & 0x80)
+                return B200J2K_ERR_PATCHWELCOME;          /* MIXED code-blocks */
+            if (!(cs.cblk_style & 0x40) && cs.cblk_style)
+                return B200J2K_ERR_PATCHWELCOME;          /* Part-1 blocks with bypass / restart / reset / causal /
+                                                           * segmentation symbols: only style 0 is served */
             /* cc = comp->coord_o: every resolution, band, precinct and code-block is laid out from it;
              * cr = comp->coord = cc reduced by lowres: the plane, the DWT and the output use it
              * (jpeg2000dec.c:1047-1050, jpeg2000.c:483-530) */
@@ -901,6 +904,10 @@ int Parser::build_geometry(int flags)
                                 d.dst_off = tc.coef_off + (uint32_t)(y0 - bd.c.y0 + offy) * (uint32_t)cw + (uint32_t)(x0 - bd.c.x0 + offx);
                                 d.M_b = (uint8_t)M_b;
                                 d.flags = (uint8_t)(((cs.cblk_style & 8) ? 1 : 0) | (cs.transform << 1));
+                                if (!(cs.cblk_style & 0x40)) {
+                                    d.flags |= J2K_CBLK_MQ;
+                                    d.Lref = (uint16_t)(b + (r > 0));        /* bandpos (jpeg2000dec.c:2240) */
+                                }
                                 if (r >= nres2decode) {
                                     /* dropped by lowres: the packets are still parsed, the block is never decoded
                                      * (tile_codeblocks walks nreslevels2decode levels, jpeg2000dec.c:2230) */
@@ -1188,6 +1195,14 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
 
                 int segment_passes, next_segment_passes = 0, nb;
                 unsigned segment_bytes = 0;
+                if (!(cs.cblk_style & 0x40)) {
+                    /* Part-1 block, style 0: one codeword segment, one length of lblock + floor(log2(passes))
+                     * bits per packet (jpeg2000dec.c:1364-1368) */
+                    segment_bytes = (unsigned)bits(cb.lblock + ilog2((unsigned)newpasses));
+                    cb.npasses = (uint8_t)(cb.npasses + newpasses);
+                    in.seg[in.nseg++] = segment_bytes & 0xFFFF;
+                    continue;
+                }
                 if (cb.plhd) {
                     int href = (cb.npasses + newpasses - 1) % 3;
                     segment_passes = newpasses - href;
@@ -1538,11 +1553,17 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
         const CblkState &s = state_[i];
         CblkDesc &d = cblk[i];
         d.data_off = s.data_off;
-        d.Lcup = (uint16_t)s.Lcup;
-        d.Lref = (uint16_t)s.Lref;
         d.npasses = s.npasses;
         d.zbp = s.zbp;
         d.length = s.length;
+        if (d.flags & J2K_CBLK_MQ) {
+            /* cblk->nonzerobits = expn + guard bits - 1 - (zero bit-planes - ROI shift of component 0)
+             * (jpeg2000dec.c:1186-1194); Lref keeps the band orientation set with the geometry */
+            d.Lcup = (uint16_t)(d.M_b - ((int)s.zbp - hdr.roi[0]));
+            continue;
+        }
+        d.Lcup = (uint16_t)s.Lcup;
+        d.Lref = (uint16_t)s.Lref;
         if (s.npasses) {
             /* the decoder reads Dcup[0..Lcup) and Dref[0..Lref): keep both inside the gathered bytes */
             if ((uint32_t)d.Lcup + d.Lref > s.length) {

@@ -23,6 +23,9 @@
 enum { J2K_DWT97 = 0, J2K_DWT53 = 1, J2K_DWT97_INT = 2 };   /* enum DWTType, jpeg2000dwt.h:37-41 */
 
 #define J2K_CBLK_SKIP 0x80
+#define J2K_CBLK_MQ   0x08  /* Part-1 (EBCOT / MQ) code-block, style 0: decoded by mq_block_kernel (decode_cblk,
+                             * jpeg2000dec.c:1993-2089).  Its descriptor carries nonzerobits in Lcup and the band
+                             * orientation (0 LL, 1 HL, 2 LH, 3 HH) in Lref; data = the single codeword segment */
 
 /* one HT code-block: a row of the table H9 (Jpeg2000Cblk, jpeg2000.h:183-205) */
 typedef struct CblkDesc {

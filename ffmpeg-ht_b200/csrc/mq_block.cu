@@ -1,0 +1,344 @@
+/*
+ * mq_block.cu -- Part-1 (EBCOT / MQ) code-block decode for sm_100a, code-block style 0, with the
+ * dequantisation fused into the coefficient write-back.
+ *
+ * Replaces, for code-blocks that are not HT:
+ *   decode_cblk + decode_sigpass / decode_refpass / decode_clnpass  libavcodec/jpeg2000dec.c:1872-2089
+ *   the MQ decoder                                                     libavcodec/mqcdec.c:30-140, mqc.c:28-90
+ *   context labels                                                     libavcodec/jpeg2000.c:90-170
+ *   dequantization_{int,float,int_97}                                  libavcodec/jpeg2000dec.c:2098-2181
+ *
+ * First correct version, parity before speed: the arithmetic decoder is one serial chain per code-block (every
+ * decision feeds the interval of the next and, through the significance state, its context), so one warp owns a
+ * block, lane 0 walks the coding passes with the sample values and the significance state of the block in
+ * shared memory, and all 32 lanes share the clearing, the ROI shift, the dequantisation and the coalesced
+ * write-back.  ~10 blocks are resident per SM; blocks of a frame run side by side.  (Round 2: split the state
+ * scan from the decoder so that context formation runs ahead on the idle lanes.)
+ *
+ * Error behaviour of the reference kept: no data => the block stays zero; a bit-plane counter outside 0..29
+ * ("bpno became invalid") stops the passes and what was decoded so far is dequantised WITHOUT the ROI step
+ * (decode_cblk returns before it, tile_codeblocks dequantises on any non-zero return, :2264-2287).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ht_common.cuh"
+#include "j2k_kernels.h"
+#include "j2k_plan.h"
+
+namespace b200j2k {
+
+namespace {
+
+/* ITU-T T.800 Table C.2 (normative): Qe, next state after an MPS / LPS, MPS switch */
+__device__ __constant__ uint16_t c_mq_qe[47] = {
+    0x5601, 0x3401, 0x1801, 0x0AC1, 0x0521, 0x0221, 0x5601, 0x5401, 0x4801, 0x3801, 0x3001, 0x2401,
+    0x1C01, 0x1601, 0x5601, 0x5401, 0x5101, 0x4801, 0x3801, 0x3401, 0x3001, 0x2801, 0x2401, 0x2201,
+    0x1C01, 0x1801, 0x1601, 0x1401, 0x1201, 0x1101, 0x0AC1, 0x09C1, 0x08A1, 0x0521, 0x0441, 0x02A1,
+    0x0221, 0x0141, 0x0111, 0x0085, 0x0049, 0x0025, 0x0015, 0x0009, 0x0005, 0x0001, 0x5601 };
+__device__ __constant__ uint8_t c_mq_nmps[47] = {
+    1, 2, 3, 4, 5, 38, 7, 8, 9, 10, 11, 12, 13, 29, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24,
+    25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 44, 45, 45, 46 };
+__device__ __constant__ uint8_t c_mq_nlps[47] = {
+    1, 6, 9, 12, 29, 33, 6, 14, 14, 14, 17, 18, 20, 21, 14, 14, 15, 16, 17, 18, 19, 19, 20, 21,
+    22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 40, 41, 42, 43, 46 };
+__device__ __constant__ uint8_t c_mq_switch[47] = {
+    1, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+    0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+
+enum { CX_SIG = 0, CX_SGN = 9, CX_REF = 14, CX_UNI = 17, CX_RL = 18, CX_COUNT = 19 };
+enum : uint8_t { S_SIG = 1, S_NEG = 2, S_VIS = 4, S_REF = 8 };
+
+constexpr int MQ_VAL_WORDS = 4096;            /* w * h <= 4096 (jpeg2000dec.c:2002) */
+constexpr int MQ_STATE_BYTES = 6176;          /* (w + 2) * (h + 2) <= 1026 * 6, rounded up to 16 */
+
+struct Mq {
+    const uint8_t *data;
+    int len, pos;
+    uint32_t a, c;
+    uint8_t cx[CX_COUNT];                     /* 2 * state + MPS */
+};
+
+/* the reference plants 0xFF 0xFF behind the segment (:2014-2015): a marker the decoder never steps over */
+__device__ __forceinline__ unsigned mq_byte(const Mq &m, int i) { return i < m.len ? __ldg(m.data + i) : 0xFFu; }
+
+__device__ __forceinline__ void mq_bytein(Mq &m)
+{
+    if (mq_byte(m, m.pos) == 0xFF) {
+        if (mq_byte(m, m.pos + 1) > 0x8F)
+            m.c++;
+        else {
+            m.pos++;
+            m.c += 2 + 0xFE00 - (mq_byte(m, m.pos) << 9);
+        }
+    } else {
+        m.pos++;
+        m.c += 1 + 0xFF00 - (mq_byte(m, m.pos) << 8);
+    }
+}
+
+__device__ void mq_init(Mq &m, const uint8_t *data, int len)
+{
+    for (int i = 0; i < CX_COUNT; i++)
+        m.cx[i] = 0;
+    m.cx[CX_UNI] = 2 * 46;
+    m.cx[CX_RL] = 2 * 3;
+    m.cx[0] = 2 * 4;
+    m.data = data;
+    m.len = len;
+    m.pos = 0;
+    m.c = (mq_byte(m, 0) ^ 0xFFu) << 16;
+    mq_bytein(m);
+    m.c <<= 7;
+    m.a = 0x8000;
+}
+
+__device__ __noinline__ int mq_decode(Mq &m, int ctx)
+{
+    const unsigned s = m.cx[ctx], idx = s >> 1, mps = s & 1, qe = c_mq_qe[idx];
+    int d;
+    m.a -= qe;
+    if ((m.c >> 16) < m.a) {
+        if (m.a & 0x8000)
+            return (int)mps;
+        if (m.a < qe) {                        /* conditional exchange on the MPS path */
+            d = 1 - (int)mps;
+            m.cx[ctx] = (uint8_t)(2 * c_mq_nlps[idx] + (mps ^ c_mq_switch[idx]));
+        } else {
+            d = (int)mps;
+            m.cx[ctx] = (uint8_t)(2 * c_mq_nmps[idx] + mps);
+        }
+    } else {
+        m.c -= m.a << 16;
+        if (m.a < qe) {                        /* conditional exchange on the LPS path */
+            d = (int)mps;
+            m.cx[ctx] = (uint8_t)(2 * c_mq_nmps[idx] + mps);
+        } else {
+            d = 1 - (int)mps;
+            m.cx[ctx] = (uint8_t)(2 * c_mq_nlps[idx] + (mps ^ c_mq_switch[idx]));
+        }
+        m.a = qe;
+    }
+    do {                                       /* RENORMD */
+        if (!(m.c & 0xFF)) {
+            m.c -= 0x100;
+            mq_bytein(m);
+        }
+        m.a += m.a;
+        m.c += m.c;
+    } while (!(m.a & 0x8000));
+    return d;
+}
+
+struct Blk {
+    int w, h, stride;                          /* stride = w + 2 */
+    uint8_t *st;                               /* (h + 2) rows of stride bytes; sample (x, y) at (y + 1) * stride + x + 1 */
+    uint32_t *val;                             /* w * h, row stride w */
+    int bandpos;
+};
+
+__device__ __forceinline__ uint8_t &state_at(const Blk &b, int x, int y) { return b.st[(y + 1) * b.stride + x + 1]; }
+
+/* significant neighbours: horizontal, vertical, diagonal */
+__device__ __forceinline__ void counts(const Blk &b, int x, int y, int &h, int &v, int &d)
+{
+    const uint8_t *r0 = b.st + y * b.stride + x, *r1 = r0 + b.stride, *r2 = r1 + b.stride;
+    h = (r1[0] & S_SIG) + (r1[2] & S_SIG);
+    v = (r0[1] & S_SIG) + (r2[1] & S_SIG);
+    d = (r0[0] & S_SIG) + (r0[2] & S_SIG) + (r2[0] & S_SIG) + (r2[2] & S_SIG);
+}
+
+/* T.800 Table D.1; bandpos 0 LL, 1 HL, 2 LH, 3 HH */
+__device__ __forceinline__ int sig_context(const Blk &b, int h, int v, int d)
+{
+    if (b.bandpos == 3) {
+        const int hv = h + v;
+        if (d >= 3) return 8;
+        if (d == 2) return hv >= 1 ? 7 : 6;
+        if (d == 1) return hv >= 2 ? 5 : hv == 1 ? 4 : 3;
+        return hv >= 2 ? 2 : hv;
+    }
+    if (b.bandpos == 1) { const int t = h; h = v; v = t; }
+    if (h == 2) return 8;
+    if (h == 1) return v >= 1 ? 7 : d >= 1 ? 6 : 5;
+    if (v == 2) return 4;
+    if (v == 1) return 3;
+    return d >= 2 ? 2 : d;
+}
+
+/* Tables D.2 / D.3 */
+__device__ __forceinline__ int sign_context(const Blk &b, int x, int y, int &xorbit)
+{
+    const uint8_t *r1 = b.st + (y + 1) * b.stride + x;
+    auto contrib = [](uint8_t s) { return (s & S_SIG) ? ((s & S_NEG) ? -1 : 1) : 0; };
+    int hc = contrib(r1[0]) + contrib(r1[2]);
+    int vc = contrib(r1[1 - b.stride]) + contrib(r1[1 + b.stride]);
+    hc = max(-1, min(1, hc));
+    vc = max(-1, min(1, vc));
+    xorbit = 0;
+    if (hc < 0 || (hc == 0 && vc < 0)) {
+        xorbit = 1;
+        hc = -hc;
+        vc = -vc;
+    }
+    return hc == 1 ? CX_SGN + 3 + vc : CX_SGN + vc;
+}
+
+__device__ __forceinline__ void become_significant(const Blk &b, Mq &m, int x, int y, uint32_t mask)
+{
+    int xorbit;
+    const int ctx = sign_context(b, x, y, xorbit);
+    const unsigned neg = (unsigned)(mq_decode(m, ctx) ^ xorbit);
+    b.val[y * b.w + x] |= (neg << 31) | mask;
+    state_at(b, x, y) |= (uint8_t)(S_SIG | (neg ? S_NEG : 0));
+}
+
+/* decode_sigpass (:1872-1904) */
+__device__ void pass_sigprop(const Blk &b, Mq &m, int bp)
+{
+    const uint32_t mask = 3u << (bp - 1);
+    for (int y0 = 0; y0 < b.h; y0 += 4)
+        for (int x = 0; x < b.w; x++)
+            for (int y = y0; y < b.h && y < y0 + 4; y++) {
+                uint8_t &s = state_at(b, x, y);
+                if (s & (S_SIG | S_VIS))
+                    continue;
+                int h, v, d;
+                counts(b, x, y, h, v, d);
+                if (!(h + v + d))
+                    continue;
+                if (mq_decode(m, CX_SIG + sig_context(b, h, v, d)))
+                    become_significant(b, m, x, y, mask);
+                s |= S_VIS;
+            }
+}
+
+/* decode_refpass (:1906-1931) */
+__device__ void pass_magref(const Blk &b, Mq &m, int bp)
+{
+    const uint32_t phalf = 1u << (bp - 1);
+    for (int y0 = 0; y0 < b.h; y0 += 4)
+        for (int x = 0; x < b.w; x++)
+            for (int y = y0; y < b.h && y < y0 + 4; y++) {
+                uint8_t &s = state_at(b, x, y);
+                if ((s & (S_SIG | S_VIS)) != S_SIG)
+                    continue;
+                int ctx = CX_REF + 2;
+                if (!(s & S_REF)) {
+                    int h, v, d;
+                    counts(b, x, y, h, v, d);
+                    ctx = CX_REF + (h + v + d ? 1 : 0);
+                }
+                uint32_t &p = b.val[y * b.w + x];
+                p |= phalf;
+                if (mq_decode(m, ctx))
+                    p |= phalf << 1;
+                else
+                    p &= ~(phalf << 1);
+                s |= S_REF;
+            }
+}
+
+/* decode_clnpass (:1933-1990), no segmentation symbols */
+__device__ void pass_cleanup(const Blk &b, Mq &m, int bp)
+{
+    const uint32_t mask = 3u << (bp - 1);
+    for (int y0 = 0; y0 < b.h; y0 += 4)
+        for (int x = 0; x < b.w; x++) {
+            int runlen = 0, dec = 0;
+            if (y0 + 3 < b.h) {
+                bool quiet = true;             /* a full column: nothing significant, visited or next to significance */
+                for (int y = y0; y < y0 + 4 && quiet; y++) {
+                    int h, v, d;
+                    counts(b, x, y, h, v, d);
+                    quiet = !(state_at(b, x, y) & (S_SIG | S_VIS)) && !(h + v + d);
+                }
+                if (quiet) {
+                    if (!mq_decode(m, CX_RL))
+                        continue;
+                    runlen = mq_decode(m, CX_UNI);
+                    runlen = (runlen << 1) | mq_decode(m, CX_UNI);
+                    dec = 1;
+                }
+            }
+            for (int y = y0 + runlen; y < y0 + 4 && y < b.h; y++) {
+                uint8_t &s = state_at(b, x, y);
+                if (!dec && !(s & (S_SIG | S_VIS))) {
+                    int h, v, d;
+                    counts(b, x, y, h, v, d);
+                    dec = mq_decode(m, CX_SIG + sig_context(b, h, v, d));
+                }
+                if (dec)
+                    become_significant(b, m, x, y, mask);
+                dec = 0;
+                s &= (uint8_t)~S_VIS;
+            }
+        }
+}
+
+__global__ void __launch_bounds__(32)
+mq_block_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order, int nblocks,
+                const uint8_t *__restrict__ bytes, const BandDesc *__restrict__ bands,
+                uint32_t *__restrict__ coef, int32_t *__restrict__ status)
+{
+    extern __shared__ __align__(16) uint32_t smem[];
+    if ((int)blockIdx.x >= nblocks)
+        return;
+    const int lane = threadIdx.x;
+    const uint32_t bi = order ? order[blockIdx.x] : blockIdx.x;
+    const CblkDesc d = descs[bi];
+    const int w = d.w, h = d.h, stride = w + 2;
+    uint32_t *val = smem;
+    uint8_t *st = reinterpret_cast<uint8_t *>(smem + MQ_VAL_WORDS);
+    for (int i = lane; i < w * h; i += 32)
+        val[i] = 0;
+    for (int i = lane; i < (stride * (h + 2) + 3) / 4; i += 32)
+        reinterpret_cast<uint32_t *>(st)[i] = 0;
+    __syncwarp();
+    int ret = 1;
+    if (lane == 0) {
+        Blk b = { w, h, stride, st, val, (int)d.Lref };
+        Mq m;
+        mq_init(m, bytes + d.data_off, (int)d.length);
+        int npasses = d.npasses, pass_t = 2;
+        int bpno = (int)d.Lcup - 1 + 31 - d.M_b - 1 - d.roi_shift;      /* Lcup carries nonzerobits */
+        while (npasses--) {
+            if (bpno < 0 || bpno > 29) {
+                ret = B200J2K_KERR_INVALID;
+                break;
+            }
+            if (pass_t == 0) pass_sigprop(b, m, bpno + 1);
+            else if (pass_t == 1) pass_magref(b, m, bpno + 1);
+            else pass_cleanup(b, m, bpno + 1);
+            if (++pass_t == 3) {
+                bpno--;
+                pass_t = 0;
+            }
+        }
+        if (status)
+            status[bi] = ret;
+    }
+    ret = __shfl_sync(0xFFFFFFFFu, ret, 0);
+    __syncwarp();
+    const BandDesc bd = bands[d.band];
+    const int mode = (d.flags >> 1) & 3;
+    const int roi = ret == 1 ? d.roi_shift : 0;
+    uint32_t *dst = coef + d.dst_off;
+    for (int y = 0; y < h; y++)
+        for (int x = lane; x < w; x += 32)
+            dst[(size_t)y * d.dst_stride + x] = dequant(val[y * w + x], mode, d.M_b, roi, bd);
+}
+
+}  // namespace
+
+int launch_mq_blocks(cudaStream_t stream, const CblkDesc *descs, const uint32_t *order, int nblocks, const uint8_t *bytes,
+                     const BandDesc *bands, void *coef, int32_t *status)
+{
+    if (nblocks <= 0)
+        return 0;
+    constexpr int smem = MQ_VAL_WORDS * 4 + MQ_STATE_BYTES;
+    mq_block_kernel<<<nblocks, 32, smem, stream>>>(descs, order, nblocks, bytes, bands, (uint32_t *)coef, status);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+}  // namespace b200j2k

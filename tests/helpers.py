@@ -68,6 +68,16 @@ def ht_block(lib_fn, data: bytes, npasses, Lcup, Lref, zbp, w, h, M_b, roi=0, vs
     return ret, out.reshape(h, w)
 
 
+def mq_block(data: bytes, npasses, nonzerobits, w, h, bandpos, M_b, roi=0):
+    """oracle_mq_block: a Part-1 code-block of style 0 -> (ret, sign-magnitude words)"""
+    fn = oracle().oracle_mq_block
+    fn.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+    out = np.zeros(w * h, np.int32)
+    ret = fn(data, len(data), npasses, nonzerobits, w, h, bandpos, M_b, roi, out.ctypes.data)
+    return ret, out.reshape(h, w)
+
+
 def decode_with(lib_fn, cs: bytes, bitexact=0, cap=None):
     """-> (ret, info list, packed bytes or None)"""
     info = (ctypes.c_int64 * 8)()

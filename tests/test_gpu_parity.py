@@ -12,7 +12,8 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import (LAYERED, PACKED, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, packed_stream, poc_stream,
+from test_oracle_vs_ref import (LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, packed_stream,
+                                part1_stream, poc_stream,
                                 subsampled_stream)
 
 pytestmark = pytest.mark.gpu
@@ -347,6 +348,47 @@ def test_two_layer_frames_vs_oracle(cfg, dec, dec_bitexact):
     if cfg.get("reversible", True) and cfg.get("npasses", 1) == 1:
         img = got.view(np.uint16 if bd > 8 else np.uint8).reshape(h, w, nc)
         assert np.array_equal(img >> ((16 - bd) if bd > 8 else 0), np.stack(planes, -1))
+
+
+@pytest.mark.parametrize("t", PART1, ids=lambda t: f"{t['mode']}-{t['w']}x{t['h']}")
+def test_part1_frames_vs_oracle(t, dec, dec_bitexact):
+    """Part-1 (EBCOT / MQ) code-blocks through mq_block_kernel: codestream and JP2 file, float and fixed-point 9/7."""
+    from helpers import oracle_pix_name
+    for jp2 in (False, True):
+        cs = part1_stream(t, jp2)
+        for bitexact in ((0,) if not t["kw"].get("irreversible") else (0, 1)):
+            r, oinfo, want = oracle_decode(cs, bitexact)
+            assert r == 0
+            d = dec_bitexact if bitexact else dec
+            info, got = d.decode(cs)
+            assert (info.width, info.height, info.pix_name) == (oinfo[0], oinfo[1], oracle_pix_name())
+            assert np.array_equal(got, want)
+
+
+def test_part1_damaged_frames_match_oracle(dec):
+    """Random byte damage inside the packets of Part-1 streams: same verdict, same pixels as the oracle (which
+    is pinned to the reference on the same kind of damage)."""
+    rng = np.random.default_rng(78)
+    n_ok = 0
+    for t in (PART1[0], PART1[3], PART1[7], PART1[4], PART1[9]):
+        cs = part1_stream(t)
+        sod = cs.index(b"\xff\x93")
+        for k in range(12):
+            bad = bytearray(cs)
+            for _ in range(int(rng.integers(1, 6))):
+                bad[int(rng.integers(sod + 2, len(bad) - 2))] = int(rng.integers(0, 256))
+            if k % 4 == 3:
+                bad = bad[:int(rng.integers(sod + 10, len(bad)))]
+            bad = bytes(bad)
+            r, oinfo, want = oracle_decode(bad, 0)
+            if r == 0:
+                info, got = dec.decode(bad)
+                assert np.array_equal(got, want), (t["mode"], k)
+                n_ok += 1
+            else:
+                with pytest.raises(fb.DecodeError):
+                    dec.decode(bad)
+    assert n_ok >= 25
 
 
 @pytest.mark.parametrize("t", PACKED, ids=lambda t: f"{'ppt' if t['mode'] == 1 else 'ppm'}-{t['chunk']}")

@@ -10,8 +10,8 @@ import pytest
 
 import ffmpeg_ht_b200 as fb
 import j2kgen
-from helpers import ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import (LAYERED, PACKED, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS,
+from helpers import ht_block, mq_block, oracle, oracle_decode
+from test_oracle_vs_ref import (LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, part1_stream,
                                 packed_marker_cases, packed_stream, poc_marker_cases, poc_stream,
                                 subsampled_stream)
 
@@ -27,14 +27,17 @@ def picture_from_plan(cs: bytes, flags: int):
             continue
         w, h, M_b = int(d["w"]), int(d["h"]), int(d["M_b"])
         seg = allbytes[int(d["data_off"]): int(d["data_off"]) + int(d["length"])].tobytes()
-        ret, sm = ht_block(oracle().oracle_ht_block, seg, int(d["npasses"]), int(d["Lcup"]), int(d["Lref"]),
-                           int(d["zbp"]), w, h, M_b, int(d["roi_shift"]), int(d["flags"]) & 1)
+        if int(d["flags"]) & 0x08:                  # J2K_CBLK_MQ: Lcup = nonzerobits, Lref = band orientation
+            ret, sm = mq_block(seg, int(d["npasses"]), int(d["Lcup"]), w, h, int(d["Lref"]), M_b, int(d["roi_shift"]))
+        else:
+            ret, sm = ht_block(oracle().oracle_ht_block, seg, int(d["npasses"]), int(d["Lcup"]), int(d["Lref"]),
+                               int(d["zbp"]), w, h, M_b, int(d["roi_shift"]), int(d["flags"]) & 1)
         band = P["bands"][int(d["band"])]
         mode = (int(d["flags"]) >> 1) & 3
         sm = sm.astype(np.int64)
         mag = sm & 0x7FFFFFFF
         neg = sm < 0
-        if ret == 0 or ret < 0:
+        if ret == 0 or (ret < 0 and not int(d["flags"]) & 0x08):   # a failed MQ block keeps what it decoded
             vals = np.zeros((h, w), np.uint32)
         elif mode == 1:
             v = mag >> (31 - M_b)
@@ -282,6 +285,19 @@ def test_packed_header_marker_validation_matches_oracle():
         except fb.DecodeError as e:
             assert r < 0 and e.code < 0
     assert n_ok >= 2
+
+
+@pytest.mark.parametrize("t", PART1, ids=lambda t: f"{t['mode']}-{t['w']}x{t['h']}")
+def test_plan_of_part1_streams(t):
+    """Part-1 (MQ) code-blocks: T2 lengths, nonzerobits, band orientation and placement in the flat plan."""
+    for jp2 in (False, True):
+        cs = part1_stream(t, jp2)
+        for bitexact in ((0,) if not t["kw"].get("irreversible") else (0, 1)):
+            r, oinfo, opic = oracle_decode(cs, bitexact)
+            assert r == 0
+            info, pic = picture_from_plan(cs, fb.FLAG_BITEXACT if bitexact else 0)
+            assert (info.width, info.height) == (oinfo[0], oinfo[1])
+            assert np.array_equal(pic, opic)
 
 
 def test_tile_without_first_tile_part_fails_like_the_reference():
