@@ -169,7 +169,19 @@ def extra_workload(fb, torch, local, cfgname, label, B, K, T, slots_e2e, S=8):
     measured exactly like the main workload: CUDA events on the launching streams with the inputs resident in
     HBM, and wall clock around b200j2k_submit/wait with pinned host buffers."""
     import j2kgen
-    cs, planes, _ = j2kgen.make_config(cfgname)
+    if cfgname == "part1_4k":
+        # Part-1 (EBCOT / MQ) code-blocks: the reference ships no HT encoder and this repo's generator writes HT
+        # only, so this stream comes from OpenJPEG (through Pillow), 8-bit RGB because that is what Pillow offers
+        import io
+
+        from PIL import Image
+        planes = j2kgen.synth_image(W, H, 3, 8, seed=11)
+        b = io.BytesIO()
+        Image.fromarray(np.stack(planes, -1).astype(np.uint8), "RGB").save(b, "JPEG2000", no_jp2=True, irreversible=False,
+                                                                         codeblock_size=(64, 64))
+        cs = b.getvalue()
+    else:
+        cs, planes, _ = j2kgen.make_config(cfgname)
     h, w = planes[0].shape
     dec = fb.Jpeg2000Decoder(device=local, slots=S)
     info = [dec.stage(s, cs) for s in range(S)][0]
@@ -225,7 +237,13 @@ def extra_workload(fb, torch, local, cfgname, label, B, K, T, slots_e2e, S=8):
     for d in decs:
         d.close()
     n_k, n_e = B * K, per * K * T
-    return {"workload": label, "codeblocks_per_frame": info.ncodeblocks, "compressed_bytes_per_frame": len(cs),
+    extra = {}
+    if cfgname == "part1_4k":                  # the reference's MQ path on the same stream, all host threads
+        fn, kind = cpu_decoder()
+        cores = os.cpu_count() or 1
+        sec = cpu_decode_seconds(fn, [cs], cores, cores)
+        extra = {"cpu_fps": cores / sec, "cpu_kind": kind, "cpu_cores": cores}
+    return {"workload": label, **extra, "codeblocks_per_frame": info.ncodeblocks, "compressed_bytes_per_frame": len(cs),
             "fps": n_k / (kern_ms * 1e-3), "mpixel_s": n_k * w * h / (kern_ms * 1e-3) / 1e6,
             "e2e_fps": n_e / e2e_s, "e2e_mpixel_s": n_e * w * h / e2e_s / 1e6,
             "stage_ms_per_frame": [round(float(x), 4) for x in stage]}
@@ -235,6 +253,8 @@ EXTRA = [
     ("target8k", "7680x4320 1-component 16-bit lossless HTJ2K, one tile (north_star target: >= 60 fps on one B200)"),
     ("cfg3", "7680x4320 1-component 16-bit lossless HTJ2K, 2x2 tiles (BASELINE configs[2])"),
     ("cfg2", "3840x2160 4:4:4 10-bit irreversible 9/7 + ICT HTJ2K (BASELINE configs[1])"),
+    ("part1_4k", "3840x2160 RGB 8-bit lossless Part-1 (EBCOT / MQ code-blocks, OpenJPEG-encoded): SURVEY 8(f) N4, "
+                 "first correct version of mq_block_kernel"),
 ]
 
 # ---- this repo's arm --------------------------------------------------------------------------------
@@ -487,7 +507,8 @@ def run_ours(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_extra and args.scale == 1:
-            line["other_workloads"] = [extra_workload(fb, torch, local, c, lbl, 16, max(2, min(K, 4)), T, args.slots_e2e)
+            line["other_workloads"] = [extra_workload(fb, torch, local, c, lbl, 16 if c != "part1_4k" else 8,
+                                                      max(2, min(K, 4)) if c != "part1_4k" else 2, T, args.slots_e2e)
                                        for c, lbl in EXTRA]
         if world == 1 and not args.no_cpu_baseline:
             fn, kind = cpu_decoder()

@@ -86,12 +86,13 @@ struct HostBuf {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 /* How the code-blocks of one frame are spread over the HT kernels.  order[] lists descriptor indices as
- * [refine | coded | zero | wide | rwide]:
+ * [refine | coded | zero | wide | rwide | mq]:
  *   refine  blocks with SigProp / MagRef passes, <= 64 samples wide -> split pipeline + refinement kernels
  *   coded   cleanup-only blocks with data, <= 64 samples wide      -> split pipeline (ht_cleanup.cu)
  *   zero    blocks without data                                    -> zero-filled by the MagSgn kernel
  *   wide    cleanup-only blocks wider than 64 samples              -> general warp-per-block kernel
  *   rwide   refinement blocks wider than 64 samples                -> general kernel, refinement variant
+ *   mq      Part-1 (EBCOT / MQ) blocks with data                   -> mq_block.cu (those without data: zero)
  * refine and coded are sorted by shape so that the 32 blocks sharing a warp of the lane-per-block kernels
  * run in step. */
 struct HtPlan {

@@ -10,10 +10,11 @@
  *
  * First correct version, parity before speed: the arithmetic decoder is one serial chain per code-block (every
  * decision feeds the interval of the next and, through the significance state, its context), so one warp owns a
- * block, lane 0 walks the coding passes with the sample values and the significance state of the block in
- * shared memory, and all 32 lanes share the clearing, the ROI shift, the dequantisation and the coalesced
- * write-back.  ~10 blocks are resident per SM; blocks of a frame run side by side.  (Round 2: split the state
- * scan from the decoder so that context formation runs ahead on the idle lanes.)
+ * block and lane 0 walks the coding passes.  The significance state of the block (one byte per sample, 6 KB)
+ * lives in shared memory; the sample values are built up in place in the block's own rectangle of the
+ * coefficient plane (read-modify-write by lane 0, the load issued ahead of the decision it waits for), which
+ * keeps shared memory small enough for 32 blocks per SM instead of 10.  All 32 lanes share the clearing and the
+ * final in-place ROI shift + dequantisation.  (Round 2: let the idle lanes form contexts ahead of the decoder.)
  *
  * Error behaviour of the reference kept: no data => the block stays zero; a bit-plane counter outside 0..29
  * ("bpno became invalid") stops the passes and what was decoded so far is dequantised WITHOUT the ROI step
@@ -49,14 +50,13 @@ __device__ __constant__ uint8_t c_mq_switch[47] = {
 enum { CX_SIG = 0, CX_SGN = 9, CX_REF = 14, CX_UNI = 17, CX_RL = 18, CX_COUNT = 19 };
 enum : uint8_t { S_SIG = 1, S_NEG = 2, S_VIS = 4, S_REF = 8 };
 
-constexpr int MQ_VAL_WORDS = 4096;            /* w * h <= 4096 (jpeg2000dec.c:2002) */
-constexpr int MQ_STATE_BYTES = 6176;          /* (w + 2) * (h + 2) <= 1026 * 6, rounded up to 16 */
+constexpr int MQ_STATE_BYTES = 6176;          /* (w + 2) * (h + 2) <= 1026 * 6 for w * h <= 4096 (:2002), rounded up to 16 */
 
 struct Mq {
     const uint8_t *data;
     int len, pos;
     uint32_t a, c;
-    uint8_t cx[CX_COUNT];                     /* 2 * state + MPS */
+    uint8_t *cx;                              /* CX_COUNT context states in shared memory: 2 * state + MPS */
 };
 
 /* the reference plants 0xFF 0xFF behind the segment (:2014-2015): a marker the decoder never steps over */
@@ -77,8 +77,9 @@ __device__ __forceinline__ void mq_bytein(Mq &m)
     }
 }
 
-__device__ void mq_init(Mq &m, const uint8_t *data, int len)
+__device__ void mq_init(Mq &m, uint8_t *cx, const uint8_t *data, int len)
 {
+    m.cx = cx;
     for (int i = 0; i < CX_COUNT; i++)
         m.cx[i] = 0;
     m.cx[CX_UNI] = 2 * 46;
@@ -93,7 +94,7 @@ __device__ void mq_init(Mq &m, const uint8_t *data, int len)
     m.a = 0x8000;
 }
 
-__device__ __noinline__ int mq_decode(Mq &m, int ctx)
+__device__ __forceinline__ int mq_decode(Mq &m, int ctx)
 {
     const unsigned s = m.cx[ctx], idx = s >> 1, mps = s & 1, qe = c_mq_qe[idx];
     int d;
@@ -133,7 +134,8 @@ __device__ __noinline__ int mq_decode(Mq &m, int ctx)
 struct Blk {
     int w, h, stride;                          /* stride = w + 2 */
     uint8_t *st;                               /* (h + 2) rows of stride bytes; sample (x, y) at (y + 1) * stride + x + 1 */
-    uint32_t *val;                             /* w * h, row stride w */
+    uint32_t *val;                             /* the block's rectangle in the coefficient plane ... */
+    uint32_t vstride;                          /* ... and its row stride */
     int bandpos;
 };
 
@@ -189,7 +191,7 @@ __device__ __forceinline__ void become_significant(const Blk &b, Mq &m, int x, i
     int xorbit;
     const int ctx = sign_context(b, x, y, xorbit);
     const unsigned neg = (unsigned)(mq_decode(m, ctx) ^ xorbit);
-    b.val[y * b.w + x] |= (neg << 31) | mask;
+    b.val[(size_t)y * b.vstride + x] |= (neg << 31) | mask;
     state_at(b, x, y) |= (uint8_t)(S_SIG | (neg ? S_NEG : 0));
 }
 
@@ -229,7 +231,7 @@ __device__ void pass_magref(const Blk &b, Mq &m, int bp)
                     counts(b, x, y, h, v, d);
                     ctx = CX_REF + (h + v + d ? 1 : 0);
                 }
-                uint32_t &p = b.val[y * b.w + x];
+                uint32_t &p = b.val[(size_t)y * b.vstride + x];
                 p |= phalf;
                 if (mq_decode(m, ctx))
                     p |= phalf << 1;
@@ -288,18 +290,19 @@ mq_block_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__
     const uint32_t bi = order ? order[blockIdx.x] : blockIdx.x;
     const CblkDesc d = descs[bi];
     const int w = d.w, h = d.h, stride = w + 2;
-    uint32_t *val = smem;
-    uint8_t *st = reinterpret_cast<uint8_t *>(smem + MQ_VAL_WORDS);
-    for (int i = lane; i < w * h; i += 32)
-        val[i] = 0;
+    uint8_t *st = reinterpret_cast<uint8_t *>(smem);
+    uint32_t *dst = coef + d.dst_off;
+    for (int y = 0; y < h; y++)
+        for (int x = lane; x < w; x += 32)
+            dst[(size_t)y * d.dst_stride + x] = 0;
     for (int i = lane; i < (stride * (h + 2) + 3) / 4; i += 32)
-        reinterpret_cast<uint32_t *>(st)[i] = 0;
+        smem[i] = 0;
     __syncwarp();
     int ret = 1;
     if (lane == 0) {
-        Blk b = { w, h, stride, st, val, (int)d.Lref };
+        Blk b = { w, h, stride, st, dst, d.dst_stride, (int)d.Lref };
         Mq m;
-        mq_init(m, bytes + d.data_off, (int)d.length);
+        mq_init(m, st + MQ_STATE_BYTES, bytes + d.data_off, (int)d.length);
         int npasses = d.npasses, pass_t = 2;
         int bpno = (int)d.Lcup - 1 + 31 - d.M_b - 1 - d.roi_shift;      /* Lcup carries nonzerobits */
         while (npasses--) {
@@ -323,10 +326,11 @@ mq_block_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__
     const BandDesc bd = bands[d.band];
     const int mode = (d.flags >> 1) & 3;
     const int roi = ret == 1 ? d.roi_shift : 0;
-    uint32_t *dst = coef + d.dst_off;
     for (int y = 0; y < h; y++)
-        for (int x = lane; x < w; x += 32)
-            dst[(size_t)y * d.dst_stride + x] = dequant(val[y * w + x], mode, d.M_b, roi, bd);
+        for (int x = lane; x < w; x += 32) {
+            uint32_t *p = dst + (size_t)y * d.dst_stride + x;
+            *p = dequant(*p, mode, d.M_b, roi, bd);
+        }
 }
 
 }  // namespace
@@ -336,7 +340,7 @@ int launch_mq_blocks(cudaStream_t stream, const CblkDesc *descs, const uint32_t 
 {
     if (nblocks <= 0)
         return 0;
-    constexpr int smem = MQ_VAL_WORDS * 4 + MQ_STATE_BYTES;
+    constexpr int smem = MQ_STATE_BYTES + 32;   /* + the 19 context states */
     mq_block_kernel<<<nblocks, 32, smem, stream>>>(descs, order, nblocks, bytes, bands, (uint32_t *)coef, status);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }

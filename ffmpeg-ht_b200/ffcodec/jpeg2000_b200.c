@@ -16,8 +16,9 @@
  *   never AVERROR(EAGAIN); one decoder context per AVCodecContext, so frame threading (one context per
  *   worker, libavcodec/pthread_frame.c:248-295) maps to one CUDA stream + staging buffers per worker.
  * Added: .close (device buffers must be released) and FF_CODEC_CAP_INIT_CLEANUP.
- * What it refuses (AVERROR_PATCHWELCOME, as the library reports): Part-1 MQ code-blocks, coding-style /
- * progression changes in tile-part headers, PAL8 -- a build that wants those keeps the native decoder registered as fallback
+ * What it refuses (AVERROR_PATCHWELCOME, as the library reports): Part-1 code-blocks with mode switches (bypass,
+ * restart, ...), MIXED HT sets, coding-style / progression changes in tile-part headers, PAL8 -- a build that wants
+ * those keeps the native decoder registered as fallback
  * under a different name.
  */
 #include "libavutil/imgutils.h"

@@ -57,6 +57,21 @@ def test_golden_frames_packed():
     assert n >= 25
 
 
+def test_golden_frames_part1():
+    """Part-1 (EBCOT / MQ) streams from OpenJPEG, plain and damaged: reference verdicts + pixels"""
+    z = np.load(GOLDEN / "frames_part1.npz")
+    n = 0
+    for key, (cs, meta, pix, out) in _groups(z, ["cs", "meta", "pix", "out"]):
+        r, info, got = oracle_decode(cs.tobytes(), int(key.split("|")[1]))
+        assert (r == 0) == (meta[2] == 0), key
+        if r == 0:
+            assert info[0] == meta[0] and info[1] == meta[1], key
+            assert oracle_pix_name() == pix.tobytes().decode(), key
+            assert np.array_equal(got, out), key
+        n += 1
+    assert n >= 25
+
+
 def test_golden_kat_values():
     """The survey's hand-checked numbers on top of the byte comparison."""
     z = np.load(GOLDEN / "frames.npz")

@@ -47,6 +47,23 @@ def test_ffcodec_shim_equals_reference(kw):
             assert np.array_equal(o1, o2)
 
 
+def test_ffcodec_shim_part1_streams():
+    """Part-1 (MQ) streams from OpenJPEG through both FFCodecs: same frame bytes, format, bytes consumed; lowres too."""
+    from test_oracle_vs_ref import PART1, part1_stream
+    for t in (PART1[0], PART1[1], PART1[3], PART1[7], PART1[9], PART1[10]):
+        for jp2 in (False, True):
+            cs = part1_stream(t, jp2)
+            for bitexact in ((0,) if not t["kw"].get("irreversible") else (0, 1)):
+                for lowres in (0, 1):
+                    flags = bitexact | (lowres << 8)
+                    r1, i1, o1, _ = ref_decode(cs, flags)
+                    r2, i2, o2 = shim_decode(cs, flags)
+                    assert r1 == r2, (t["mode"], jp2, flags, r1, r2)
+                    if r1 == 0:
+                        assert i1[:3] == i2[:3] and i1[4] == i2[4]
+                        assert np.array_equal(o1, o2)
+
+
 def test_ffcodec_shim_jp2_and_subsampled():
     """JP2 / JPH files and chroma-subsampled streams through the FFCodec shim: same AVPixelFormat (planar YUV
     included), same AVFrame bytes as the reference decoder."""

@@ -223,9 +223,11 @@ def test_golden_frames_wide():
     assert n >= 35
 
 
-def test_golden_frames_packed():
-    """Reference-generated vectors: packed packet headers (PPT / PPM), damaged PPT / PPM markers, missing tiles."""
-    z = np.load(GOLDEN / "frames_packed.npz")
+@pytest.mark.parametrize("name", ["frames_packed.npz", "frames_part1.npz"])
+def test_golden_frames_packed_and_part1(name):
+    """Reference-generated vectors: packed packet headers (PPT / PPM), damaged PPT / PPM markers, missing tiles;
+    Part-1 (EBCOT / MQ) streams from OpenJPEG, plain and damaged."""
+    z = np.load(GOLDEN / name)
     n = 0
     for key, (cs, meta, pix, out) in _groups(z, ["cs", "meta", "pix", "out"]):
         flags = int(key.split("|")[1])
