@@ -98,7 +98,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 struct HtPlan {
     std::vector<uint32_t> order, scr_off;
     int n_refine = 0, n_coded = 0, n_zero = 0, n_wide = 0, n_rwide = 0, n_mq = 0;
-    int maxL_fast = 0, maxLref = 0, maxL_wide = 0, maxL_rwide = 0;
+    int maxL_fast = 0, maxLref = 0, maxL_wide = 0, maxL_rwide = 0, mq_state_words = 0;
     size_t scratch_words = 0;
     /* descriptor indices sorted by quad-grid shape; depends on the geometry only */
     std::vector<uint32_t> by_shape;
@@ -132,7 +132,7 @@ struct HtPlan {
         }
         order.resize(n);
         scr_off.resize(n);
-        maxL_fast = maxLref = maxL_wide = maxL_rwide = 0;
+        maxL_fast = maxLref = maxL_wide = maxL_rwide = mq_state_words = 0;
         scratch_words = 0;
         size_t cnt[7] = { 0, 0, 0, 0, 0, 0, 0 };
         for (size_t i = 0; i < n; i++)
@@ -156,6 +156,9 @@ struct HtPlan {
                 if (d.Lcup > maxL_wide) maxL_wide = d.Lcup;
             } else if (c == 4) {
                 if (d.Lcup > maxL_rwide) maxL_rwide = d.Lcup;
+            } else if (c == 5) {
+                const int words = mq_state_words_of(d.w, d.h);
+                if (words > mq_state_words) mq_state_words = words;
             }
         }
         n_refine = (int)cnt[0];
@@ -164,6 +167,12 @@ struct HtPlan {
         n_wide = (int)cnt[3];
         n_rwide = (int)cnt[4];
         n_mq = (int)cnt[5];
+        if (n_mq > 1) {
+            /* a Part-1 block costs about what its segment is long: start the long ones first, so that the last
+             * wave of warps is made of short blocks (longest-processing-time-first) */
+            uint32_t *mq = order.data() + (n - cnt[6] - cnt[5]);
+            std::stable_sort(mq, mq + n_mq, [&](uint32_t a, uint32_t b) { return cblk[a].length > cblk[b].length; });
+        }
     }
 };
 
@@ -183,7 +192,8 @@ int run_ht(cudaStream_t st, const HtPlan &hp, const CblkDesc *d_cblk, const uint
                          max_state);
     if (r < 0) return r;
     launches += r;
-    r = launch_mq_blocks(st, d_cblk, o_wide + hp.n_wide + hp.n_rwide, hp.n_mq, d_bytes, d_bands, coef, status);
+    r = launch_mq_blocks(st, d_cblk, o_wide + hp.n_wide + hp.n_rwide, hp.n_mq, d_bytes, d_bands, coef, status,
+                         hp.mq_state_words);
     if (r < 0) return r;
     launches += r;
     if (ev) cudaEventRecord(ev[3], st);

@@ -44,9 +44,12 @@ int launch_ht_refine(cudaStream_t stream, const CblkDesc *descs, const uint32_t 
                      int32_t *status, int max_Lcup);
 
 /* Part-1 (EBCOT / MQ) code-blocks of style 0 (mq_block.cu): order[0..nblocks) lists descriptors flagged
- * J2K_CBLK_MQ that carry data; one warp per block, dequantisation fused into the write-back. */
+ * J2K_CBLK_MQ that carry data; one warp per block, dequantisation fused into the write-back.  state_words: the
+ * largest mq_state_words_of() over those blocks. */
 int launch_mq_blocks(cudaStream_t stream, const CblkDesc *descs, const uint32_t *order, int nblocks, const uint8_t *bytes,
-                     const BandDesc *bands, void *coef, int32_t *status);
+                     const BandDesc *bands, void *coef, int32_t *status, int state_words);
+/* words of shared-memory state a w x h block needs there: two arrays of one word per 4-row stripe and column, framed */
+static inline __host__ __device__ int mq_state_words_of(int w, int h) { return 2 * (((h + 7) >> 2) + 1) * (w + 2); }
 
 /* Inverse DWT levels + final MCT / level shift / clip / pack.
  * tcs/groups: device copies of the plan tables.  coefA: HT output (Mallat layout), coefB/coefC: LL

@@ -10,10 +10,12 @@
  *
  * First correct version, parity before speed: the arithmetic decoder is one serial chain per code-block (every
  * decision feeds the interval of the next and, through the significance state, its context), so one warp owns a
- * block and lane 0 walks the coding passes.  The significance state of the block (one byte per sample, 6 KB)
- * lives in shared memory; the sample values are built up in place in the block's own rectangle of the
- * coefficient plane (read-modify-write by lane 0, the load issued ahead of the decision it waits for), which
- * keeps shared memory small enough for 32 blocks per SM instead of 10.  All 32 lanes share the clearing and the
+ * block and lane 0 walks the coding passes.  The state of the block lives in shared memory in scan order (a
+ * word per stripe column: own state and significant-neighbour mask of its four samples, see Blk), so a column
+ * with nothing to do costs one load and a context label comes from one byte instead of eight neighbour reads;
+ * the sample values are built up in place in the block's own rectangle of the coefficient plane with plain
+ * stores and fire-and-forget reductions (never read back by the decoder), which keeps shared memory at 9.5 KB for
+ * 64x64 blocks (23 blocks resident per SM).  All 32 lanes share the clearing and the
  * final in-place ROI shift + dequantisation.  (Round 2: let the idle lanes form contexts ahead of the decoder.)
  *
  * Error behaviour of the reference kept: no data => the block stays zero; a bit-plane counter outside 0..29
@@ -50,11 +52,12 @@ __device__ __constant__ uint8_t c_mq_switch[47] = {
 enum { CX_SIG = 0, CX_SGN = 9, CX_REF = 14, CX_UNI = 17, CX_RL = 18, CX_COUNT = 19 };
 enum : uint8_t { S_SIG = 1, S_NEG = 2, S_VIS = 4, S_REF = 8 };
 
-constexpr int MQ_STATE_BYTES = 6176;          /* (w + 2) * (h + 2) <= 1026 * 6 for w * h <= 4096 (:2002), rounded up to 16 */
 
 struct Mq {
     const uint8_t *data;
-    int len, pos;
+    int len, pos;                             /* pos = index of the byte last folded into C */
+    unsigned cur, nxt;                        /* bytes at pos and pos + 1: the next one is fetched a byte ahead, so the
+                                               * load is long done when the renormalisation needs it */
     uint32_t a, c;
     uint8_t *cx;                              /* CX_COUNT context states in shared memory: 2 * state + MPS */
 };
@@ -64,17 +67,18 @@ __device__ __forceinline__ unsigned mq_byte(const Mq &m, int i) { return i < m.l
 
 __device__ __forceinline__ void mq_bytein(Mq &m)
 {
-    if (mq_byte(m, m.pos) == 0xFF) {
-        if (mq_byte(m, m.pos + 1) > 0x8F)
-            m.c++;
-        else {
-            m.pos++;
-            m.c += 2 + 0xFE00 - (mq_byte(m, m.pos) << 9);
+    if (m.cur == 0xFF) {
+        if (m.nxt > 0x8F) {
+            m.c++;                             /* marker: feed ones, stay */
+            return;
         }
+        m.c += 2 + 0xFE00 - (m.nxt << 9);      /* stuffed byte: 7 bits */
     } else {
-        m.pos++;
-        m.c += 1 + 0xFF00 - (mq_byte(m, m.pos) << 8);
+        m.c += 1 + 0xFF00 - (m.nxt << 8);
     }
+    m.pos++;
+    m.cur = m.nxt;
+    m.nxt = mq_byte(m, m.pos + 1);
 }
 
 __device__ void mq_init(Mq &m, uint8_t *cx, const uint8_t *data, int len)
@@ -88,7 +92,9 @@ __device__ void mq_init(Mq &m, uint8_t *cx, const uint8_t *data, int len)
     m.data = data;
     m.len = len;
     m.pos = 0;
-    m.c = (mq_byte(m, 0) ^ 0xFFu) << 16;
+    m.cur = mq_byte(m, 0);
+    m.nxt = mq_byte(m, 1);
+    m.c = (m.cur ^ 0xFFu) << 16;
     mq_bytein(m);
     m.c <<= 7;
     m.a = 0x8000;
@@ -131,28 +137,32 @@ __device__ __forceinline__ int mq_decode(Mq &m, int ctx)
     return d;
 }
 
+/* Sample state of the block in shared memory, laid out for the scan: per 4-row stripe and column one 32-bit word
+ * whose byte r belongs to row 4 * stripe + r, so that one load answers "anything to do in this column?" for the
+ * four samples a coding pass visits next.  Two such arrays:
+ *   st4  S_SIG | S_NEG | S_VIS | S_REF of the sample itself
+ *   nb4  which of its eight neighbours are significant (kept up to date when a sample becomes significant, as
+ *        the reference keeps JPEG2000_T1_SIG_* in its flags, jpeg2000.c:172-200)
+ * A frame of one column left / right and one stripe above / below the block stands in for the neighbours
+ * outside. */
+enum : uint8_t { NB_N = 1, NB_S = 2, NB_W = 4, NB_E = 8, NB_NW = 16, NB_NE = 32, NB_SW = 64, NB_SE = 128 };
+
 struct Blk {
-    int w, h, stride;                          /* stride = w + 2 */
-    uint8_t *st;                               /* (h + 2) rows of stride bytes; sample (x, y) at (y + 1) * stride + x + 1 */
+    int w, h, W2;                              /* W2 = w + 2 words per stripe */
+    uint32_t *st4, *nb4;
     uint32_t *val;                             /* the block's rectangle in the coefficient plane ... */
     uint32_t vstride;                          /* ... and its row stride */
     int bandpos;
 };
 
-__device__ __forceinline__ uint8_t &state_at(const Blk &b, int x, int y) { return b.st[(y + 1) * b.stride + x + 1]; }
+/* byte address of sample (x, y), -1 <= x <= w, -4 <= y < h + 4 */
+__device__ __forceinline__ int byte_at(const Blk &b, int x, int y) { return ((((y + 4) >> 2) * b.W2 + x + 1) << 2) + ((y + 4) & 3); }
 
-/* significant neighbours: horizontal, vertical, diagonal */
-__device__ __forceinline__ void counts(const Blk &b, int x, int y, int &h, int &v, int &d)
+/* T.800 Table D.1 from the neighbour byte; bandpos 0 LL, 1 HL, 2 LH, 3 HH */
+__device__ __forceinline__ int sig_context(const Blk &b, unsigned n)
 {
-    const uint8_t *r0 = b.st + y * b.stride + x, *r1 = r0 + b.stride, *r2 = r1 + b.stride;
-    h = (r1[0] & S_SIG) + (r1[2] & S_SIG);
-    v = (r0[1] & S_SIG) + (r2[1] & S_SIG);
-    d = (r0[0] & S_SIG) + (r0[2] & S_SIG) + (r2[0] & S_SIG) + (r2[2] & S_SIG);
-}
-
-/* T.800 Table D.1; bandpos 0 LL, 1 HL, 2 LH, 3 HH */
-__device__ __forceinline__ int sig_context(const Blk &b, int h, int v, int d)
-{
+    int h = ((n >> 2) & 1) + ((n >> 3) & 1), v = (n & 1) + ((n >> 1) & 1);
+    const int d = __popc(n >> 4);
     if (b.bandpos == 3) {
         const int hv = h + v;
         if (d >= 3) return 8;
@@ -168,13 +178,13 @@ __device__ __forceinline__ int sig_context(const Blk &b, int h, int v, int d)
     return d >= 2 ? 2 : d;
 }
 
-/* Tables D.2 / D.3 */
+/* Tables D.2 / D.3 from the states of the four direct neighbours */
 __device__ __forceinline__ int sign_context(const Blk &b, int x, int y, int &xorbit)
 {
-    const uint8_t *r1 = b.st + (y + 1) * b.stride + x;
+    const uint8_t *st = reinterpret_cast<const uint8_t *>(b.st4);
     auto contrib = [](uint8_t s) { return (s & S_SIG) ? ((s & S_NEG) ? -1 : 1) : 0; };
-    int hc = contrib(r1[0]) + contrib(r1[2]);
-    int vc = contrib(r1[1 - b.stride]) + contrib(r1[1 + b.stride]);
+    int hc = contrib(st[byte_at(b, x - 1, y)]) + contrib(st[byte_at(b, x + 1, y)]);
+    int vc = contrib(st[byte_at(b, x, y - 1)]) + contrib(st[byte_at(b, x, y + 1)]);
     hc = max(-1, min(1, hc));
     vc = max(-1, min(1, vc));
     xorbit = 0;
@@ -191,118 +201,146 @@ __device__ __forceinline__ void become_significant(const Blk &b, Mq &m, int x, i
     int xorbit;
     const int ctx = sign_context(b, x, y, xorbit);
     const unsigned neg = (unsigned)(mq_decode(m, ctx) ^ xorbit);
-    b.val[(size_t)y * b.vstride + x] |= (neg << 31) | mask;
-    state_at(b, x, y) |= (uint8_t)(S_SIG | (neg ? S_NEG : 0));
+    /* an insignificant sample is still zero: a plain store, no read of the plane on the decoder's critical path */
+    b.val[(size_t)y * b.vstride + x] = (neg << 31) | mask;
+    uint8_t *st = reinterpret_cast<uint8_t *>(b.st4), *nb = reinterpret_cast<uint8_t *>(b.nb4);
+    st[byte_at(b, x, y)] |= (uint8_t)(S_SIG | (neg ? S_NEG : 0));
+    /* tell the eight neighbours: seen from the sample above, this one lies to its south, and so on */
+    nb[byte_at(b, x, y - 1)] |= NB_S;
+    nb[byte_at(b, x, y + 1)] |= NB_N;
+    nb[byte_at(b, x - 1, y)] |= NB_E;
+    nb[byte_at(b, x + 1, y)] |= NB_W;
+    nb[byte_at(b, x - 1, y - 1)] |= NB_SE;
+    nb[byte_at(b, x + 1, y - 1)] |= NB_SW;
+    nb[byte_at(b, x - 1, y + 1)] |= NB_NE;
+    nb[byte_at(b, x + 1, y + 1)] |= NB_NW;
+}
+
+/* 0x80 in every byte of v that is not zero */
+__device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v)
+{
+    return (((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v) & 0x80808080u;
 }
 
 /* decode_sigpass (:1872-1904) */
 __device__ void pass_sigprop(const Blk &b, Mq &m, int bp)
 {
     const uint32_t mask = 3u << (bp - 1);
-    for (int y0 = 0; y0 < b.h; y0 += 4)
-        for (int x = 0; x < b.w; x++)
-            for (int y = y0; y < b.h && y < y0 + 4; y++) {
-                uint8_t &s = state_at(b, x, y);
-                if (s & (S_SIG | S_VIS))
+    uint8_t *st = reinterpret_cast<uint8_t *>(b.st4);
+    const uint8_t *nb = reinterpret_cast<const uint8_t *>(b.nb4);
+    for (int y0 = 0; y0 < b.h; y0 += 4) {
+        const int rows = min(4, b.h - y0), base = ((y0 + 4) >> 2) * b.W2 + 1;
+        for (int x = 0; x < b.w; x++) {
+            /* candidates: a significant neighbour, not significant, not visited -- most columns have none */
+            const uint32_t n4 = b.nb4[base + x];
+            if (!n4 || !(nonzero_bytes(n4) & ~nonzero_bytes(b.st4[base + x] & 0x05050505u)))
+                continue;
+            const int at = (base + x) << 2;
+            for (int r = 0; r < rows; r++) {
+                const uint8_t s = st[at + r], n = nb[at + r];
+                if ((s & (S_SIG | S_VIS)) || !n)
                     continue;
-                int h, v, d;
-                counts(b, x, y, h, v, d);
-                if (!(h + v + d))
-                    continue;
-                if (mq_decode(m, CX_SIG + sig_context(b, h, v, d)))
-                    become_significant(b, m, x, y, mask);
-                s |= S_VIS;
+                if (mq_decode(m, CX_SIG + sig_context(b, n)))
+                    become_significant(b, m, x, y0 + r, mask);
+                st[at + r] |= S_VIS;
             }
+        }
+    }
 }
 
 /* decode_refpass (:1906-1931) */
 __device__ void pass_magref(const Blk &b, Mq &m, int bp)
 {
     const uint32_t phalf = 1u << (bp - 1);
-    for (int y0 = 0; y0 < b.h; y0 += 4)
-        for (int x = 0; x < b.w; x++)
-            for (int y = y0; y < b.h && y < y0 + 4; y++) {
-                uint8_t &s = state_at(b, x, y);
+    uint8_t *st = reinterpret_cast<uint8_t *>(b.st4);
+    const uint8_t *nb = reinterpret_cast<const uint8_t *>(b.nb4);
+    for (int y0 = 0; y0 < b.h; y0 += 4) {
+        const int rows = min(4, b.h - y0), base = ((y0 + 4) >> 2) * b.W2 + 1;
+        for (int x = 0; x < b.w; x++) {
+            const uint32_t s4 = b.st4[base + x];
+            if (!(s4 & ~(s4 >> 2) & 0x01010101u))  /* nothing significant that was not just visited */
+                continue;
+            const int at = (base + x) << 2;
+            for (int r = 0; r < rows; r++) {
+                const uint8_t s = st[at + r];
                 if ((s & (S_SIG | S_VIS)) != S_SIG)
                     continue;
-                int ctx = CX_REF + 2;
-                if (!(s & S_REF)) {
-                    int h, v, d;
-                    counts(b, x, y, h, v, d);
-                    ctx = CX_REF + (h + v + d ? 1 : 0);
-                }
-                uint32_t &p = b.val[(size_t)y * b.vstride + x];
-                p |= phalf;
+                const int ctx = (s & S_REF) ? CX_REF + 2 : CX_REF + (nb[at + r] ? 1 : 0);
+                /* The reference does  v |= phalf;  v = bit ? v | 2 phalf : v & ~(2 phalf).  Bit 2 phalf is the
+                 * half-LSB the previous coding step of this sample left set and the bits below it are clear, so
+                 * that is "OR phalf" for a one and "XOR 3 phalf" for a zero: fire-and-forget reductions, no load
+                 * of the plane (an L2 round trip per symbol when the value is read back). */
+                uint32_t *p = b.val + (size_t)(y0 + r) * b.vstride + x;
                 if (mq_decode(m, ctx))
-                    p |= phalf << 1;
+                    atomicOr(p, phalf);
                 else
-                    p &= ~(phalf << 1);
-                s |= S_REF;
+                    atomicXor(p, 3u * phalf);
+                st[at + r] = s | S_REF;
             }
+        }
+    }
 }
 
 /* decode_clnpass (:1933-1990), no segmentation symbols */
 __device__ void pass_cleanup(const Blk &b, Mq &m, int bp)
 {
     const uint32_t mask = 3u << (bp - 1);
-    for (int y0 = 0; y0 < b.h; y0 += 4)
+    uint8_t *st = reinterpret_cast<uint8_t *>(b.st4);
+    const uint8_t *nb = reinterpret_cast<const uint8_t *>(b.nb4);
+    for (int y0 = 0; y0 < b.h; y0 += 4) {
+        const int rows = min(4, b.h - y0), base = ((y0 + 4) >> 2) * b.W2 + 1;
         for (int x = 0; x < b.w; x++) {
             int runlen = 0, dec = 0;
-            if (y0 + 3 < b.h) {
-                bool quiet = true;             /* a full column: nothing significant, visited or next to significance */
-                for (int y = y0; y < y0 + 4 && quiet; y++) {
-                    int h, v, d;
-                    counts(b, x, y, h, v, d);
-                    quiet = !(state_at(b, x, y) & (S_SIG | S_VIS)) && !(h + v + d);
-                }
-                if (quiet) {
-                    if (!mq_decode(m, CX_RL))
-                        continue;
-                    runlen = mq_decode(m, CX_UNI);
-                    runlen = (runlen << 1) | mq_decode(m, CX_UNI);
-                    dec = 1;
-                }
+            const uint32_t s4 = b.st4[base + x];
+            if (rows == 4 && nonzero_bytes(s4 & 0x05050505u) == 0x80808080u) {
+                b.st4[base + x] = s4 & ~0x04040404u;       /* every sample significant or visited: only un-visit */
+                continue;
             }
-            for (int y = y0 + runlen; y < y0 + 4 && y < b.h; y++) {
-                uint8_t &s = state_at(b, x, y);
-                if (!dec && !(s & (S_SIG | S_VIS))) {
-                    int h, v, d;
-                    counts(b, x, y, h, v, d);
-                    dec = mq_decode(m, CX_SIG + sig_context(b, h, v, d));
-                }
+            /* a full column with nothing significant, visited or next to significance: run-length mode */
+            if (rows == 4 && !(s4 & 0x05050505u) && !b.nb4[base + x]) {
+                if (!mq_decode(m, CX_RL))
+                    continue;
+                runlen = mq_decode(m, CX_UNI);
+                runlen = (runlen << 1) | mq_decode(m, CX_UNI);
+                dec = 1;
+            }
+            const int at = (base + x) << 2;
+            for (int r = runlen; r < rows; r++) {
+                if (!dec && !(st[at + r] & (S_SIG | S_VIS)))
+                    dec = mq_decode(m, CX_SIG + sig_context(b, nb[at + r]));
                 if (dec)
-                    become_significant(b, m, x, y, mask);
+                    become_significant(b, m, x, y0 + r, mask);
                 dec = 0;
-                s &= (uint8_t)~S_VIS;
+                st[at + r] &= (uint8_t)~S_VIS;
             }
         }
+    }
 }
 
 __global__ void __launch_bounds__(32)
 mq_block_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order, int nblocks,
                 const uint8_t *__restrict__ bytes, const BandDesc *__restrict__ bands,
-                uint32_t *__restrict__ coef, int32_t *__restrict__ status)
+                uint32_t *__restrict__ coef, int32_t *__restrict__ status, int state_words)
 {
-    extern __shared__ __align__(16) uint32_t smem[];
+    extern __shared__ __align__(16) uint32_t smem[];     /* st4 | nb4 (state_words in all) | 19 context states */
     if ((int)blockIdx.x >= nblocks)
         return;
     const int lane = threadIdx.x;
     const uint32_t bi = order ? order[blockIdx.x] : blockIdx.x;
     const CblkDesc d = descs[bi];
-    const int w = d.w, h = d.h, stride = w + 2;
-    uint8_t *st = reinterpret_cast<uint8_t *>(smem);
+    const int w = d.w, h = d.h, W2 = w + 2, words = mq_state_words_of(w, h) / 2;
     uint32_t *dst = coef + d.dst_off;
     for (int y = 0; y < h; y++)
         for (int x = lane; x < w; x += 32)
             dst[(size_t)y * d.dst_stride + x] = 0;
-    for (int i = lane; i < (stride * (h + 2) + 3) / 4; i += 32)
+    for (int i = lane; i < 2 * words; i += 32)
         smem[i] = 0;
     __syncwarp();
     int ret = 1;
     if (lane == 0) {
-        Blk b = { w, h, stride, st, dst, d.dst_stride, (int)d.Lref };
+        Blk b = { w, h, W2, smem, smem + words, dst, d.dst_stride, (int)d.Lref };
         Mq m;
-        mq_init(m, st + MQ_STATE_BYTES, bytes + d.data_off, (int)d.length);
+        mq_init(m, reinterpret_cast<uint8_t *>(smem + state_words), bytes + d.data_off, (int)d.length);
         int npasses = d.npasses, pass_t = 2;
         int bpno = (int)d.Lcup - 1 + 31 - d.M_b - 1 - d.roi_shift;      /* Lcup carries nonzerobits */
         while (npasses--) {
@@ -336,12 +374,14 @@ mq_block_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__
 }  // namespace
 
 int launch_mq_blocks(cudaStream_t stream, const CblkDesc *descs, const uint32_t *order, int nblocks, const uint8_t *bytes,
-                     const BandDesc *bands, void *coef, int32_t *status)
+                     const BandDesc *bands, void *coef, int32_t *status, int state_words)
 {
     if (nblocks <= 0)
         return 0;
-    constexpr int smem = MQ_STATE_BYTES + 32;   /* + the 19 context states */
-    mq_block_kernel<<<nblocks, 32, smem, stream>>>(descs, order, nblocks, bytes, bands, (uint32_t *)coef, status);
+    /* the two state arrays of the largest block of the frame: w * h <= 4096, so at most 2 x 12.3 KB (1024 x 4) */
+    const int smem = state_words * 4 + 32;
+    mq_block_kernel<<<nblocks, 32, smem, stream>>>(descs, order, nblocks, bytes, bands, (uint32_t *)coef, status,
+                                                   state_words);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
