@@ -12,8 +12,8 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import (LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, packed_stream,
-                                part1_stream, poc_stream,
+from test_oracle_vs_ref import (LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+                                packed_stream, part1_stream, poc_stream, tile_part_stream,
                                 subsampled_stream)
 
 pytestmark = pytest.mark.gpu
@@ -391,6 +391,21 @@ def test_part1_damaged_frames_match_oracle(dec):
                 with pytest.raises(fb.DecodeError):
                     dec.decode(bad)
     assert n_ok >= 25
+
+
+@pytest.mark.parametrize("t", TILE_PARTS, ids=lambda t: f"mode{t['mode']}-tp{t['tp']}-il{int(t['il'])}")
+def test_tile_part_frames_vs_oracle(t, dec):
+    """Several (interleaved) tile-parts per tile, with PPT / PPM."""
+    cs, base = tile_part_stream(t)
+    r, oinfo, want = oracle_decode(cs, 0)
+    if r == 0:
+        info, got = dec.decode(cs)
+        assert np.array_equal(got, want)
+        if t["mode"] != 2:
+            assert np.array_equal(dec.decode(base)[1], want)
+    else:
+        with pytest.raises(fb.DecodeError):
+            dec.decode(cs)
 
 
 @pytest.mark.parametrize("t", PACKED, ids=lambda t: f"{'ppt' if t['mode'] == 1 else 'ppm'}-{t['chunk']}")

@@ -11,7 +11,8 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import ht_block, mq_block, oracle, oracle_decode
-from test_oracle_vs_ref import (LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, part1_stream,
+from test_oracle_vs_ref import (LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+                                part1_stream, tile_part_stream,
                                 packed_marker_cases, packed_stream, poc_marker_cases, poc_stream,
                                 subsampled_stream)
 
@@ -272,6 +273,19 @@ def test_plan_of_packed_header_streams(t):
         assert r == 0
         info, pic = picture_from_plan(cs, fb.FLAG_BITEXACT if bitexact else 0)
         assert np.array_equal(pic, opic)
+
+
+@pytest.mark.parametrize("t", TILE_PARTS, ids=lambda t: f"mode{t['mode']}-tp{t['tp']}-il{int(t['il'])}")
+def test_plan_of_tile_part_streams(t):
+    """Several (interleaved) tile-parts per tile, with PPT / PPM: same verdict and picture as the oracle, the
+    select_header quirk of PPM streams included."""
+    cs, _ = tile_part_stream(t)
+    r, oinfo, opic = oracle_decode(cs, 0)
+    try:
+        info, pic = picture_from_plan(cs, 0)
+        assert r == 0 and np.array_equal(pic, opic)
+    except fb.DecodeError as e:
+        assert r < 0 and e.code < 0
 
 
 def test_packed_header_marker_validation_matches_oracle():

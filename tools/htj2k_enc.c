@@ -63,6 +63,10 @@ typedef struct J2kGenParams {
                                   * Ccap15 bit 11 is set (jpeg2000dec.c:2605-2617).  2: PPM -- into PPM marker segments
                                   * of the main header, one Nppm-prefixed run per tile-part (:958-980, :2467-2472) */
     int32_t ppx_chunk;           /* payload bytes per PPT / PPM marker segment (0 = as many as fit: 65532) */
+    int32_t tp_packets;          /* > 0: a new tile-part after every tp_packets packets (at most 32 parts per tile, the
+                                  * reference's limit); PPT headers all go to the first part (jpeg2000dec.c:995), PPM
+                                  * gets one Nppm-prefixed run per tile-part */
+    int32_t tp_interleave;       /* with tp_packets: write part 0 of every tile, then part 1 of every tile, ... */
 } J2kGenParams;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -826,6 +830,12 @@ typedef struct ResLevel {
 
 /* one progression over resolutions [RS, RE), components [CS, CE) and layers [0, LYE): the packet order of
  * T.800 B.12 for that sub-volume.  A packet that an earlier progression already carried is not repeated. */
+/* where write_packet puts packet headers when they are packed (PPT / PPM); NULL = in front of the body */
+static __thread Buf *packed_hdr_target;
+/* tile-part cuts: body / packed-header sizes after every packet (filled by sequence_one when cut_pos != NULL) */
+static __thread size_t *cut_pos;
+static __thread int cut_n, cut_cap;
+
 static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precno, int layer, int *sop_counter);
 static void sequence_one(Buf *out, const J2kGenParams *P, ResLevel *rl, int precno, int layer, int *sopc)
 {
@@ -835,6 +845,11 @@ static void sequence_one(Buf *out, const J2kGenParams *P, ResLevel *rl, int prec
         return;
     rl->written[precno] = layer + 1;
     write_packet(out, P, rl, precno, layer, sopc);
+    if (cut_pos && cut_n < cut_cap) {
+        cut_pos[2 * cut_n] = out->n;
+        cut_pos[2 * cut_n + 1] = packed_hdr_target ? packed_hdr_target->n : 0;
+        cut_n++;
+    }
 }
 
 static void sequence_packets(Buf *out, const J2kGenParams *P, ResLevel **res, int C, int L, int tx0, int ty0,
@@ -935,8 +950,6 @@ static int contribution(const J2kGenParams *P, const CodedBlock *cb, int layer)
     }
 }
 
-/* where write_packet puts packet headers when they are packed (PPT / PPM); NULL = in front of the body */
-static __thread Buf *packed_hdr_target;
 
 static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precno, int layer, int *sop_counter)
 {
@@ -1146,6 +1159,10 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
 
     const size_t main_end = out.n;       /* PPM marker segments are inserted here once the tiles are written */
     Buf ppm = { 0 };
+    /* every tile-part is assembled on its own, so that the parts of different tiles can be interleaved */
+    const int ntiles = ntx * nty;
+    Buf *tparts = calloc((size_t)ntiles * 32, sizeof(Buf)), *tphdr = calloc((size_t)ntiles * 32, sizeof(Buf));
+    int *tnparts = calloc((size_t)ntiles, sizeof(int));
 
     /* ---- tiles ---- */
     for (int ty = 0; ty < nty; ty++)
@@ -1306,12 +1323,18 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
                     }
                 }
             }
-            /* tile-part: SOT, [PPT], SOD, packets */
+            /* tile-part(s): SOT, [PPT], SOD, packets */
             Buf body = { 0 }, phdr = { 0 };
             packed_hdr_target = P->packed_headers ? &phdr : NULL;
             int sopc = 0;
-            int maxnp = 0;
-            for (int c = 0; c < C; c++) for (int r = 0; r <= L; r++) maxnp = imax(maxnp, res[c][r].npx * res[c][r].npy);
+            int maxnp = 0, total_packets = 0;
+            for (int c = 0; c < C; c++) for (int r = 0; r <= L; r++) {
+                maxnp = imax(maxnp, res[c][r].npx * res[c][r].npy);
+                total_packets += res[c][r].npx * res[c][r].npy * NLAY;
+            }
+            cut_cap = total_packets + 1;
+            cut_pos = P->tp_packets > 0 ? calloc((size_t)cut_cap * 2, sizeof(size_t)) : NULL;
+            cut_n = 0;
             if (P->npoc > 0) {
                 for (int i = 0; i < P->npoc; i++)
                     sequence_packets(&body, P, res, C, L, tx0, ty0, tx1, ty1, P->poc[i][0], P->poc[i][1],
@@ -1321,27 +1344,40 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
                 sequence_packets(&body, P, res, C, L, tx0, ty0, tx1, ty1, 0, 0, NLAY, L + 1, C, P->prog, &sopc);
             }
             packed_hdr_target = NULL;
-            size_t sot_pos = out.n;
-            buf_put16(&out, 0xFF90); buf_put16(&out, 10); buf_put16(&out, tileno); buf_put32(&out, 0);
-            buf_put(&out, 0); buf_put(&out, 1);
-            if (P->packed_headers == 1) {
-                const size_t chunk = P->ppx_chunk > 0 ? (size_t)imin(P->ppx_chunk, 65532) : 65532;
-                int z = 0;
-                for (size_t at = 0; at < phdr.n || z == 0; at += chunk, z++) {
-                    const size_t n = phdr.n - at < chunk ? phdr.n - at : chunk;
-                    buf_put16(&out, 0xFF61); buf_put16(&out, (unsigned)(3 + n)); buf_put(&out, z & 255);
-                    buf_append(&out, phdr.p + at, n);
-                }
-            } else if (P->packed_headers == 2) {
-                buf_put32(&ppm, (uint32_t)phdr.n);
-                buf_append(&ppm, phdr.p, phdr.n);
+            /* part k holds packets [k * per, (k + 1) * per); the last one takes the rest */
+            int nparts = 1, per = cut_n;
+            if (cut_pos && cut_n > 0) {
+                per = imax(P->tp_packets, (cut_n + 31) / 32);
+                nparts = (cut_n + per - 1) / per;
             }
-            buf_put16(&out, 0xFF93);
-            buf_append(&out, body.p, body.n);
+            for (int k = 0; k < nparts; k++) {
+                size_t b0 = 0, b1 = body.n, h0 = 0, h1 = phdr.n;
+                if (nparts > 1) {
+                    if (k > 0) { b0 = cut_pos[2 * (k * per - 1)]; h0 = cut_pos[2 * (k * per - 1) + 1]; }
+                    if (k + 1 < nparts) { b1 = cut_pos[2 * ((k + 1) * per - 1)]; h1 = cut_pos[2 * ((k + 1) * per - 1) + 1]; }
+                }
+                Buf *tp_out = &tparts[tileno * 32 + k];
+                buf_put16(tp_out, 0xFF90); buf_put16(tp_out, 10); buf_put16(tp_out, tileno); buf_put32(tp_out, 0);
+                buf_put(tp_out, k); buf_put(tp_out, nparts);
+                if (P->packed_headers == 1 && k == 0) {
+                    const size_t chunk = P->ppx_chunk > 0 ? (size_t)imin(P->ppx_chunk, 65532) : 65532;
+                    int z = 0;
+                    for (size_t at = 0; at < phdr.n || z == 0; at += chunk, z++) {
+                        const size_t n = phdr.n - at < chunk ? phdr.n - at : chunk;
+                        buf_put16(tp_out, 0xFF61); buf_put16(tp_out, (unsigned)(3 + n)); buf_put(tp_out, z & 255);
+                        buf_append(tp_out, phdr.p + at, n);
+                    }
+                } else if (P->packed_headers == 2) {
+                    buf_append(&tphdr[tileno * 32 + k], phdr.p + h0, h1 - h0);
+                }
+                buf_put16(tp_out, 0xFF93);
+                buf_append(tp_out, body.p + b0, b1 - b0);
+                const uint32_t psot = (uint32_t)tp_out->n;
+                tp_out->p[6] = psot >> 24; tp_out->p[7] = psot >> 16; tp_out->p[8] = psot >> 8; tp_out->p[9] = psot;
+            }
+            tnparts[tileno] = nparts;
+            free(cut_pos); cut_pos = NULL;
             free(body.p); free(phdr.p);
-            uint32_t psot = (uint32_t)(out.n - sot_pos);
-            out.p[sot_pos + 6] = psot >> 24; out.p[sot_pos + 7] = psot >> 16;
-            out.p[sot_pos + 8] = psot >> 8;  out.p[sot_pos + 9] = psot;
             /* free */
             for (int c = 0; c < C; c++) {
                 for (int r = 0; r <= L; r++)
@@ -1363,6 +1399,18 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
             free(res);
             free(tp);
         }
+    /* emit the tile-parts: tile after tile, or part k of every tile before part k + 1 of any */
+    for (int pass = 0; pass < (P->tp_interleave ? 32 : 1); pass++)
+        for (int t = 0; t < ntiles; t++)
+            for (int k = P->tp_interleave ? pass : 0; k < (P->tp_interleave ? imin(pass + 1, tnparts[t]) : tnparts[t]); k++) {
+                buf_append(&out, tparts[t * 32 + k].p, tparts[t * 32 + k].n);
+                if (P->packed_headers == 2) {            /* PPM runs follow the order of the tile-parts in the stream */
+                    buf_put32(&ppm, (uint32_t)tphdr[t * 32 + k].n);
+                    buf_append(&ppm, tphdr[t * 32 + k].p, tphdr[t * 32 + k].n);
+                }
+            }
+    for (int i = 0; i < ntiles * 32; i++) { free(tparts[i].p); free(tphdr[i].p); }
+    free(tparts); free(tphdr); free(tnparts);
     buf_put16(&out, 0xFFD9);
     if (P->packed_headers == 2) {
         /* PPM marker segments go to the end of the main header: Zppm, then the Nppm-prefixed runs cut into chunks */

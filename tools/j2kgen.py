@@ -32,6 +32,7 @@ class _Params(ctypes.Structure):
         ("layers", ctypes.c_int32), ("sub_x", ctypes.c_int32 * 4), ("sub_y", ctypes.c_int32 * 4),
         ("npoc", ctypes.c_int32), ("poc", (ctypes.c_int32 * 6) * 8), ("poc_split", ctypes.c_int32),
         ("packed_headers", ctypes.c_int32), ("ppx_chunk", ctypes.c_int32),
+        ("tp_packets", ctypes.c_int32), ("tp_interleave", ctypes.c_int32),
     ]
 
 
@@ -79,6 +80,8 @@ class EncParams:
     poc_split: int = 0            # > 0: the first poc_split entries go into a POC segment of their own
     packed_headers: int = 0       # 1: packet headers in PPT marker segments (tile-part header), 2: in PPM (main header)
     ppx_chunk: int = 0            # payload bytes per PPT / PPM marker segment (0 = 65532)
+    tp_packets: int = 0           # > 0: a new tile-part after this many packets (at most 32 parts per tile)
+    tp_interleave: bool = False   # write part k of every tile before part k + 1 of any
     stats: dict = field(default_factory=dict)
 
 
@@ -117,6 +120,7 @@ def encode(planes, bitdepth: int, p: EncParams) -> bytes:
                 for k in range(6):
                     P.poc[i][k] = e[k]
         P.packed_headers, P.ppx_chunk = p.packed_headers, p.ppx_chunk
+        P.tp_packets, P.tp_interleave = p.tp_packets, int(p.tp_interleave)
         cap = int(w * h * len(planes) * 4 + (1 << 20))
         out = np.empty(cap, np.uint8)
         ptrs = (ctypes.c_void_p * len(planes))(*[a.ctypes.data for a in planes])
