@@ -178,42 +178,41 @@ __device__ __forceinline__ int sig_context(const Blk &b, unsigned n)
     return d >= 2 ? 2 : d;
 }
 
-/* Tables D.2 / D.3 from the states of the four direct neighbours */
-__device__ __forceinline__ int sign_context(const Blk &b, int x, int y, int &xorbit)
+/* Sample (x, y) becomes significant: decode its sign (Tables D.2 / D.3 from the states of the four direct
+ * neighbours), store the value, mark it and tell the eight neighbours.  The byte addresses of the rows above and
+ * below follow from the sample's own: one byte back / forth inside the stripe word, or over to the neighbouring
+ * stripe's word. */
+__device__ __forceinline__ void become_significant(const Blk &b, Mq &m, int x, int y, uint32_t mask)
 {
-    const uint8_t *st = reinterpret_cast<const uint8_t *>(b.st4);
+    uint8_t *st = reinterpret_cast<uint8_t *>(b.st4), *nb = reinterpret_cast<uint8_t *>(b.nb4);
+    const int r = y & 3;                                   /* y + 4 has the same low bits */
+    const int at = ((((y + 4) >> 2) * b.W2 + x + 1) << 2) + r;
+    const int up = r ? at - 1 : at - (b.W2 << 2) + 3, dn = r != 3 ? at + 1 : at + (b.W2 << 2) - 3;
     auto contrib = [](uint8_t s) { return (s & S_SIG) ? ((s & S_NEG) ? -1 : 1) : 0; };
-    int hc = contrib(st[byte_at(b, x - 1, y)]) + contrib(st[byte_at(b, x + 1, y)]);
-    int vc = contrib(st[byte_at(b, x, y - 1)]) + contrib(st[byte_at(b, x, y + 1)]);
+    int hc = contrib(st[at - 4]) + contrib(st[at + 4]);
+    int vc = contrib(st[up]) + contrib(st[dn]);
     hc = max(-1, min(1, hc));
     vc = max(-1, min(1, vc));
-    xorbit = 0;
+    int xorbit = 0;
     if (hc < 0 || (hc == 0 && vc < 0)) {
         xorbit = 1;
         hc = -hc;
         vc = -vc;
     }
-    return hc == 1 ? CX_SGN + 3 + vc : CX_SGN + vc;
-}
-
-__device__ __forceinline__ void become_significant(const Blk &b, Mq &m, int x, int y, uint32_t mask)
-{
-    int xorbit;
-    const int ctx = sign_context(b, x, y, xorbit);
+    const int ctx = hc == 1 ? CX_SGN + 3 + vc : CX_SGN + vc;
     const unsigned neg = (unsigned)(mq_decode(m, ctx) ^ xorbit);
     /* an insignificant sample is still zero: a plain store, no read of the plane on the decoder's critical path */
     b.val[(size_t)y * b.vstride + x] = (neg << 31) | mask;
-    uint8_t *st = reinterpret_cast<uint8_t *>(b.st4), *nb = reinterpret_cast<uint8_t *>(b.nb4);
-    st[byte_at(b, x, y)] |= (uint8_t)(S_SIG | (neg ? S_NEG : 0));
-    /* tell the eight neighbours: seen from the sample above, this one lies to its south, and so on */
-    nb[byte_at(b, x, y - 1)] |= NB_S;
-    nb[byte_at(b, x, y + 1)] |= NB_N;
-    nb[byte_at(b, x - 1, y)] |= NB_E;
-    nb[byte_at(b, x + 1, y)] |= NB_W;
-    nb[byte_at(b, x - 1, y - 1)] |= NB_SE;
-    nb[byte_at(b, x + 1, y - 1)] |= NB_SW;
-    nb[byte_at(b, x - 1, y + 1)] |= NB_NE;
-    nb[byte_at(b, x + 1, y + 1)] |= NB_NW;
+    st[at] |= (uint8_t)(S_SIG | (neg ? S_NEG : 0));
+    /* seen from the sample above, this one lies to its south, and so on */
+    nb[up] |= NB_S;
+    nb[dn] |= NB_N;
+    nb[at - 4] |= NB_E;
+    nb[at + 4] |= NB_W;
+    nb[up - 4] |= NB_SE;
+    nb[up + 4] |= NB_SW;
+    nb[dn - 4] |= NB_NE;
+    nb[dn + 4] |= NB_NW;
 }
 
 /* 0x80 in every byte of v that is not zero */

@@ -8,7 +8,7 @@ import pytest
 
 import j2kgen
 from helpers import ROOT
-from test_oracle_vs_ref import PACKED, POC_STREAMS, packed_stream, poc_stream
+from test_oracle_vs_ref import PACKED, PART1, POC_STREAMS, TILE_PARTS, packed_stream, part1_stream, poc_stream, tile_part_stream
 
 
 def test_host_parser_and_splitter_under_sanitizers(tmp_path):
@@ -28,13 +28,15 @@ def test_host_parser_and_splitter_under_sanitizers(tmp_path):
     seeds.append(j2kgen.wrap_jp2(seeds[0], 96, 64, 3, 8, colour_space=16, cdef=[(0, 0, 1), (1, 0, 2), (2, 0, 3)]))
     seeds += [packed_stream(t, w=90, h=70)[0] for t in (PACKED[0], PACKED[3], PACKED[5])]
     seeds.append(poc_stream(POC_STREAMS[2], w=90, h=70)[0])
+    seeds += [part1_stream(PART1[0]), part1_stream(PART1[3], jp2=True), part1_stream(PART1[9])]
+    seeds += [tile_part_stream(t, w=90, h=70)[0] for t in (TILE_PARTS[1], TILE_PARTS[7])]
     files = []
     for i, s in enumerate(seeds):
         f = tmp_path / f"seed{i}.j2k"
         f.write_bytes(s)
         files.append(str(f))
     env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0", UBSAN_OPTIONS="print_stacktrace=1")
-    r = subprocess.run([str(exe), "7", "1500"] + files, capture_output=True, text=True, env=env, timeout=600)
+    r = subprocess.run([str(exe), "7", "2500"] + files, capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0 and "runtime error" not in r.stderr and "ERROR" not in r.stderr, r.stderr[-2000:]
     ok = int(r.stdout.split()[1])
     assert ok > 50, r.stdout            # the mutations must not all be rejected outright
