@@ -385,10 +385,18 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
     ppm_.clear();
     has_ppm_ = false;
     ppt_.clear();
+    tsty_.clear();
+    geom_extra_.clear();
     tile_first_.clear();
     has_ppt_.clear();
     ppt_pos_.clear();
     size_t ppm_pos = 0;                                    /* s->packed_headers_stream */
+    /* tile-part header segments that change what build_geometry lays out: part of the geometry cache key */
+    auto note_tile_segment = [&](int tile, const uint8_t *from, const uint8_t *to) {
+        const uint8_t t[4] = { (uint8_t)(tile >> 24), (uint8_t)(tile >> 16), (uint8_t)(tile >> 8), (uint8_t)tile };
+        geom_extra_.insert(geom_extra_.end(), t, t + 4);
+        geom_extra_.insert(geom_extra_.end(), from, to);
+    };
     *main_header_len = 0;
     if (size >= 12 && rd32(p) == 12 && rd32(p + 4) == 0x6A502020u && rd32(p + 8) == 0x0D0A870Au) {
         /* JP2 / JPH file (jpeg2000dec.c:2842-2854) */
@@ -488,6 +496,7 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 return B200J2K_ERR_EINVAL;
             parts_.assign((size_t)h.ntx * h.nty, {});
             tile_first_.assign((size_t)h.ntx * h.nty, 0);
+            tsty_.assign((size_t)h.ntx * h.nty, TileSty());
             ppt_.assign((size_t)h.ntx * h.nty, {});
             has_ppt_.assign((size_t)h.ntx * h.nty, 0);
             ppt_pos_.assign((size_t)h.ntx * h.nty, 0);
@@ -531,6 +540,7 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                     return B200J2K_ERR_PATCHWELCOME;
                 h.cap_b05 = (ccap15 >> 5) & 1;
                 h.cap_b11 = (ccap15 >> 11) & 1;
+                h.cap_b12 = (ccap15 >> 12) & 1;
                 int P = ccap15 & 31, B = !P ? 8 : P < 20 ? P + 8 : P < 31 ? 4 * (P - 19) + 27 : 74;
                 if (B > 31)
                     return B200J2K_ERR_PATCHWELCOME;
@@ -538,12 +548,13 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             break;
         }
         case 0xFF52: {
-            /* coding / quantisation styles of a single tile: INVALIDDATA for the HOMOGENEOUS set as in the
-             * reference (jpeg2000dec.c:2514-2556), not served otherwise */
-            if (cur_tile >= 0)
-                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
+            /* in a tile-part header: the styles of that tile; INVALIDDATA for the HOMOGENEOUS HT set
+             * (jpeg2000dec.c:2514-2556) */
+            if (cur_tile >= 0 && h.isHT && !h.cap_b11)
+                return B200J2K_ERR_INVALIDDATA;
             if (segend - seg < 5)
                 return B200J2K_ERR_INVALIDDATA;
+            CodSty *codp = cur_tile >= 0 ? tsty_[cur_tile].cod : h.cod;
             CodSty tmp;
             tmp.csty = seg[0];
             tmp.prog = seg[1];
@@ -555,64 +566,88 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 return ret;
             tmp.init = 1;
             for (int c = 0; c < h.ncomp; c++)
-                if (!h.had_coc[c])
-                    h.cod[c] = tmp;
+                if (!(cur_tile >= 0 ? tsty_[cur_tile].had_coc[c] : h.had_coc[c]))
+                    codp[c] = tmp;
+            if (cur_tile >= 0)
+                note_tile_segment(cur_tile, marker_pos, segend);
             seg += 10 + ((tmp.csty & 1) ? tmp.nres : 0);
             break;
         }
         case 0xFF53: {
-            if (cur_tile >= 0)
-                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
+            if (cur_tile >= 0 && h.isHT && !h.cap_b11)
+                return B200J2K_ERR_INVALIDDATA;
             if (segend - seg < 2)
                 return B200J2K_ERR_INVALIDDATA;
             int c = seg[0];
             if (c >= h.ncomp)
                 return B200J2K_ERR_INVALIDDATA;
-            CodSty *cs = &h.cod[c];
+            CodSty *cs = cur_tile >= 0 ? &tsty_[cur_tile].cod[c] : &h.cod[c];
             int keep = cs->csty & 6;
             cs->csty = seg[1] | keep;
             if ((ret = parse_cox(seg + 2, segend, cs, flags)) < 0)
                 return ret;
-            h.had_coc[c] = 1;
+            if (cur_tile >= 0) {
+                tsty_[cur_tile].had_coc[c] = 1;
+                note_tile_segment(cur_tile, marker_pos, segend);
+            } else
+                h.had_coc[c] = 1;
             cs->init = 1;
             seg += 7 + ((cs->csty & 1) ? cs->nres : 0);
             break;
         }
         case 0xFF5C: {
-            if (cur_tile >= 0)
-                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
+            if (cur_tile >= 0 && h.isHT && !h.cap_b11)
+                return B200J2K_ERR_INVALIDDATA;
             QntSty tmp;
             memset(&tmp, 0, sizeof(tmp));
             if ((ret = parse_qcx(seg, len - 2, &tmp)) < 0)
                 return ret;
-            for (int c = 0; c < h.ncomp; c++)
-                if (!h.had_qcc[c])
+            for (int c = 0; c < h.ncomp; c++) {
+                if (cur_tile >= 0) {
+                    if (!tsty_[cur_tile].had_qcc[c])
+                        tsty_[cur_tile].qnt[c] = tmp;
+                } else if (!h.had_qcc[c])
                     h.qnt[c] = tmp;
+            }
+            if (cur_tile >= 0)
+                note_tile_segment(cur_tile, marker_pos, segend);
             seg = segend;
             break;
         }
         case 0xFF5D: {
-            if (cur_tile >= 0)
-                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
+            if (cur_tile >= 0 && h.isHT && !h.cap_b11)
+                return B200J2K_ERR_INVALIDDATA;
             if (segend - seg < 1)
                 return B200J2K_ERR_INVALIDDATA;
             int c = seg[0];
             if (c >= h.ncomp)
                 return B200J2K_ERR_INVALIDDATA;
-            h.had_qcc[c] = 1;
-            if ((ret = parse_qcx(seg + 1, len - 3, &h.qnt[c])) < 0)
+            if (cur_tile >= 0) {
+                tsty_[cur_tile].had_qcc[c] = 1;
+                note_tile_segment(cur_tile, marker_pos, segend);
+            } else
+                h.had_qcc[c] = 1;
+            if ((ret = parse_qcx(seg + 1, len - 3, cur_tile >= 0 ? &tsty_[cur_tile].qnt[c] : &h.qnt[c])) < 0)
                 return ret;
             seg = segend;
             break;
         }
-        case 0xFF5E: {
+        case 0xFF5E: {                                    /* RGN (get_rgn, jpeg2000dec.c:641-672; :2530-2534) */
+            if (cur_tile >= 0 && h.isHT && !h.cap_b11)
+                return B200J2K_ERR_INVALIDDATA;
+            if (h.isHT && !h.cap_b12)                     /* "belongs to the RGNFREE set" (:2536-2540) */
+                return B200J2K_ERR_INVALIDDATA;
             if (segend - seg < 3 || seg[1] != 0 || seg[0] >= h.ncomp)
+                return B200J2K_ERR_INVALIDDATA;
+            if (cur_tile >= 0 && cur_tp != 0)             /* only in the first tile-part of a tile */
                 return B200J2K_ERR_INVALIDDATA;
             if (seg[2] > 30)
                 return B200J2K_ERR_PATCHWELCOME;
-            if (cur_tile >= 0)                            /* tile-specific ROI (:2530-2534) */
-                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
-            h.roi[seg[0]] = seg[2];
+            if (cur_tile >= 0) {
+                tsty_[cur_tile].roi[seg[0]] = seg[2];
+                note_tile_segment(cur_tile, marker_pos, segend);
+            } else
+                h.roi[seg[0]] = seg[2];
             seg += 3;
             break;
         }
@@ -635,16 +670,25 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 return B200J2K_ERR_PATCHWELCOME;
             cur_tile = isot;
             cur_tp = tpsot;
-            if (!tpsot)
-                tile_first_[isot] = 1;                    /* get_sot copies the coding styles to the tile (:862-869) */
+            if (!tpsot) {                                 /* get_sot copies the styles to the tile (:862-869) */
+                tile_first_[isot] = 1;
+                TileSty &T = tsty_[isot];
+                for (int c = 0; c < J2K_MAX_COMP; c++) {
+                    T.cod[c] = h.cod[c];
+                    T.qnt[c] = h.qnt[c];
+                }
+                T.npoc = h.npoc;
+                for (int i = 0; i < h.npoc; i++)
+                    T.poc[i] = h.poc[i];
+                T.poc_default = true;
+            }
             tp_end = seg + 8 + psot - len - 2;
             seg += 8;
             break;
         }
         case 0xFF5F: {                                    /* POC (get_poc, jpeg2000dec.c:760-818) */
-            if (cur_tile >= 0)                            /* per-tile progression changes: refused by the reference
-                                                           * for HOMOGENEOUS HT streams (:2558), not served otherwise */
-                return h.isHT && !h.cap_b11 ? B200J2K_ERR_INVALIDDATA : B200J2K_ERR_PATCHWELCOME;
+            if (cur_tile >= 0 && h.isHT && !h.cap_b11)    /* HOMOGENEOUS HT set: no progression change per tile (:2558) */
+                return B200J2K_ERR_INVALIDDATA;
             if (end - seg < 5 || len < 2 + 7)
                 return B200J2K_ERR_INVALIDDATA;
             const int n = (len - 2) / 7;
@@ -662,10 +706,23 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 if (e.RS >= e.RE || e.RE > 33 || e.CS >= e.CE || e.CE > h.ncomp || !e.LYE)
                     return B200J2K_ERR_INVALIDDATA;
             }
-            if (h.npoc + n > 32)
-                return B200J2K_ERR_INVALIDDATA;
-            for (int i = 0; i < n; i++)                   /* a second POC segment extends the list */
-                h.poc[h.npoc++] = tmp[i];
+            if (cur_tile >= 0) {
+                /* the tile's list starts as a copy of the main header's ("default"): the first POC segment of
+                 * the tile replaces it, further ones extend it (:806-816) */
+                TileSty &T = tsty_[cur_tile];
+                if (!T.npoc || T.poc_default)
+                    T.npoc = 0;
+                else if (T.npoc + n > 32)
+                    return B200J2K_ERR_INVALIDDATA;
+                for (int i = 0; i < n; i++)
+                    T.poc[T.npoc++] = tmp[i];
+                T.poc_default = false;
+            } else {
+                if (h.npoc + n > 32)
+                    return B200J2K_ERR_INVALIDDATA;
+                for (int i = 0; i < n; i++)               /* a second POC segment extends the list */
+                    h.poc[h.npoc++] = tmp[i];
+            }
             seg += 7 * n;
             break;
         }
@@ -767,8 +824,10 @@ int Parser::build_geometry(int flags)
         t.c.y1 = clip64((int64_t)(ty + 1) * h.TH + h.TY0, h.Y0, h.H);
         const int first_tc = (int)tcs.size();
         for (int c = 0; c < h.ncomp; c++) {
-            const CodSty &cs = h.cod[c];
-            const QntSty &qs = h.qnt[c];
+            const CodSty &cs = tsty_[tileno].cod[c];
+            const QntSty &qs = tsty_[tileno].qnt[c];
+            if (!cs.init)
+                return B200J2K_ERR_INVALIDDATA;
             if (h.isHT && !h.cap_b05 && !cs.transform)
                 return B200J2K_ERR_INVALIDDATA;
             if (h.isHT && h.cap_b14 != (cs.cblk_style >> 6) && h.cap_b14 != 0)
@@ -914,7 +973,7 @@ int Parser::build_geometry(int flags)
                                     d.flags |= J2K_CBLK_SKIP;
                                     d.dst_off = tc.coef_off;
                                 }
-                                d.roi_shift = (uint8_t)h.roi[c];
+                                d.roi_shift = (uint8_t)roi_of(tileno, c);
                                 d.band = (uint16_t)bd.band_index;
                                 if (bands.size() > 65535)
                                     return B200J2K_ERR_PATCHWELCOME;
@@ -954,9 +1013,10 @@ int Parser::build_geometry(int flags)
                 g.shift[c] = out_precision - h.cbps[c];
                 tcs[first_tc + c].group = (int)groups.size();
             }
-            bool ok = h.cod[0].mct != 0 && h.ncomp >= 3;
+            const CodSty *tcod = tsty_[tileno].cod;
+            bool ok = tcod[0].mct != 0 && h.ncomp >= 3;
             for (int i = 1; i < 3 && ok; i++)
-                ok = h.cod[0].transform == h.cod[i].transform && !memcmp(&t.comp[0], &t.comp[i], sizeof(Rect));
+                ok = tcod[0].transform == tcod[i].transform && !memcmp(&t.comp[0], &t.comp[i], sizeof(Rect));
             g.mct = ok;
             groups.push_back(g);
         } else {
@@ -964,9 +1024,10 @@ int Parser::build_geometry(int flags)
              * (write_frame, jpeg2000dec.c:2325-2326).  The component transform does not care about the
              * output format (mct_decode, :2183-2209): a 4:4:4 stream with the MCT bit set keeps comps 0-2 in
              * one group so that RCT / ICT runs before the samples part ways. */
-            bool mct_ok = h.cod[0].mct != 0 && h.ncomp >= 3;
+            const CodSty *tcod = tsty_[tileno].cod;
+            bool mct_ok = tcod[0].mct != 0 && h.ncomp >= 3;
             for (int i = 1; i < 3 && mct_ok; i++)
-                mct_ok = h.cod[0].transform == h.cod[i].transform && !memcmp(&t.comp[0], &t.comp[i], sizeof(Rect));
+                mct_ok = tcod[0].transform == tcod[i].transform && !memcmp(&t.comp[0], &t.comp[i], sizeof(Rect));
             int c = 0;
             if (mct_ok) {
                 PackGroup g;
@@ -1115,12 +1176,12 @@ void Parser::select_part(int tileno, int *tp, int csty)
 /* jpeg2000_decode_packet, HT-only paths */
 int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *tp)
 {
-    const CodSty &cs = hdr.cod[c];
-    const QntSty &qs = hdr.qnt[c];
+    const CodSty &cs = tsty_[tileno].cod[c];
+    const QntSty &qs = tsty_[tileno].qnt[c];
     const TileGeom &t = tiles_[tileno];
     const ResGeom &rl = res_[t.res_base[c] + r];
     const uint8_t *expn = qs.expn + (r ? 3 * (r - 1) + 1 : 0);
-    const int roi0 = hdr.roi[0];                         /* quirk Q6: component 0's shift for every component */
+    const int roi0 = roi_of(tileno, 0);                  /* quirk Q6: component 0's shift for every component */
 
     uint8_t &dl = decoded_layers_[rl.band[0].prec_base + precno];
     if (layno < dl)
@@ -1164,6 +1225,7 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                             return B200J2K_ERR_INVALIDDATA;
                         cb.incl = 1;
                         cb.zbp = (uint8_t)zbp;
+                        cb.nzb = (uint8_t)v;
                         cb.lblock = 3;
                     }
                 } else {
@@ -1325,7 +1387,7 @@ int Parser::precinct_at(int tileno, int c, int r, int x, int y, bool cprl_rule) 
     const Header &h = hdr;
     const TileGeom &t = tiles_[tileno];
     const ResGeom &rl = res_[t.res_base[c] + r];
-    const int red = h.cod[c].nres - 1 - r;
+    const int red = tsty_[tileno].cod[c].nres - 1 - r;
     const Rect &cc = t.comp[c];
     if (cprl_rule) {
         int xc = x / h.cdx[c], yc = y / h.cdy[c];
@@ -1369,6 +1431,7 @@ int Parser::precinct_at(int tileno, int c, int r, int x, int y, bool cprl_rule) 
 int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, int P, int *tpp)
 {
     const Header &h = hdr;
+    const CodSty *tcod = tsty_[tileno].cod;          /* this tile's coding styles */
     const TileGeom &t = tiles_[tileno];
     int &tp = *tpp;
     auto R = [&](int c, int r) -> const ResGeom & { return res_[t.res_base[c] + r]; };
@@ -1379,7 +1442,7 @@ int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, in
             for (int r = RS; ok && r < RE; r++) {
                 ok = false;
                 for (int c = CS; c < CE; c++)
-                    if (r < h.cod[c].nres) {
+                    if (r < tcod[c].nres) {
                         ok = true;
                         for (int pn = 0; pn < R(c, r).npx * R(c, r).npy; pn++)
                             PACKET(c, r, pn, l);
@@ -1393,7 +1456,7 @@ int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, in
             ok = false;
             for (int l = 0; l < LYE; l++)
                 for (int c = CS; c < CE; c++)
-                    if (r < h.cod[c].nres) {
+                    if (r < tcod[c].nres) {
                         ok = true;
                         for (int pn = 0; pn < R(c, r).npx * R(c, r).npy; pn++)
                             PACKET(c, r, pn, l);
@@ -1407,8 +1470,8 @@ int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, in
             ok = false;
             int sx = 30, sy = 30;
             for (int c = CS; c < CE; c++)
-                if (r < h.cod[c].nres) {
-                    int red = h.cod[c].nres - 1 - r;
+                if (r < tcod[c].nres) {
+                    int red = tcod[c].nres - 1 - r;
                     sx = imin(sx, R(c, r).ppx + red);
                     sy = imin(sy, R(c, r).ppy + red);
                 }
@@ -1416,7 +1479,7 @@ int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, in
             for (int y = t.c.y0; y < t.c.y1; y = (y / sy + 1) * sy)
                 for (int x = t.c.x0; x < t.c.x1; x = (x / sx + 1) * sx)
                     for (int c = CS; c < CE; c++) {
-                        if (r >= h.cod[c].nres)
+                        if (r >= tcod[c].nres)
                             continue;
                         int pn = precinct_at(tileno, c, r, x, y, false);
                         if (pn == -1)
@@ -1433,8 +1496,8 @@ int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, in
     case 3: {
         int sx = 32, sy = 32;
         for (int c = CS; c < CE; c++)
-            for (int r = RS; r < imin(h.cod[c].nres, RE); r++) {
-                int red = h.cod[c].nres - 1 - r;
+            for (int r = RS; r < imin(tcod[c].nres, RE); r++) {
+                int red = tcod[c].nres - 1 - r;
                 sx = imin(sx, R(c, r).ppx + red);
                 sy = imin(sy, R(c, r).ppy + red);
             }
@@ -1444,7 +1507,7 @@ int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, in
         for (int y = t.c.y0; y < t.c.y1; y = (y / sy + 1) * sy)
             for (int x = t.c.x0; x < t.c.x1; x = (x / sx + 1) * sx)
                 for (int c = CS; c < CE; c++)
-                    for (int r = RS; r < imin(h.cod[c].nres, RE); r++) {
+                    for (int r = RS; r < imin(tcod[c].nres, RE); r++) {
                         int pn = precinct_at(tileno, c, r, x, y, false);
                         if (pn < 0)
                             continue;
@@ -1456,10 +1519,10 @@ int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, in
     case 4:
         for (int c = CS; c < CE; c++) {
             int sx = 32, sy = 32;
-            if (RS >= imin(h.cod[c].nres, RE))
+            if (RS >= imin(tcod[c].nres, RE))
                 continue;
-            for (int r = RS; r < imin(h.cod[c].nres, RE); r++) {
-                int red = h.cod[c].nres - 1 - r;
+            for (int r = RS; r < imin(tcod[c].nres, RE); r++) {
+                int red = tcod[c].nres - 1 - r;
                 sx = imin(sx, R(c, r).ppx + red);
                 sy = imin(sy, R(c, r).ppy + red);
             }
@@ -1468,7 +1531,7 @@ int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, in
             sx = 1 << sx; sy = 1 << sy;
             for (int y = t.c.y0; y < t.c.y1; y = (y / sy + 1) * sy)
                 for (int x = t.c.x0; x < t.c.x1; x = (x / sx + 1) * sx)
-                    for (int r = RS; r < imin(h.cod[c].nres, RE); r++) {
+                    for (int r = RS; r < imin(tcod[c].nres, RE); r++) {
                         int pn = precinct_at(tileno, c, r, x, y, true);
                         if (pn < 0)
                             continue;
@@ -1487,16 +1550,17 @@ int Parser::po_iteration(int tileno, int RS, int CS, int LYE, int RE, int CE, in
 int Parser::decode_packets(int tileno)
 {
     const Header &h = hdr;
-    const int nlayers = h.cod[0].nlayers;
+    const TileSty &T = tsty_[tileno];
+    const int nlayers = T.cod[0].nlayers;
     int tp = 0, ret = 0;
     bit_index_ = 8;
-    if (h.npoc) {
-        for (int i = 0; i < h.npoc && ret >= 0; i++) {
-            const Header::Poc &e = h.poc[i];
+    if (T.npoc) {
+        for (int i = 0; i < T.npoc && ret >= 0; i++) {
+            const Header::Poc &e = T.poc[i];
             ret = po_iteration(tileno, e.RS, e.CS, imin(e.LYE, nlayers), e.RE, imin(e.CE, h.ncomp), e.P, &tp);
         }
     } else {
-        ret = po_iteration(tileno, 0, 0, nlayers, 33, h.ncomp, h.cod[0].prog, &tp);
+        ret = po_iteration(tileno, 0, 0, nlayers, 33, h.ncomp, T.cod[0].prog, &tp);
     }
     return ret;
 }
@@ -1517,11 +1581,13 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
     if (headers_only)
         return 0;
     /* geometry only depends on the main header: reuse it across a sequence */
-    if (geom_flags_ != flags || geom_key_.size() != mh || memcmp(geom_key_.data(), pkt, mh)) {
+    if (geom_flags_ != flags || geom_key_.size() != mh || memcmp(geom_key_.data(), pkt, mh) ||
+        geom_extra_key_ != geom_extra_) {
         geom_flags_ = -1;
         if ((ret = build_geometry(flags)) < 0)
             return ret;
         geom_key_.assign(pkt, pkt + mh);
+        geom_extra_key_ = geom_extra_;
         geom_flags_ = flags;
         geom_serial++;
     }
@@ -1559,7 +1625,7 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
         if (d.flags & J2K_CBLK_MQ) {
             /* cblk->nonzerobits = expn + guard bits - 1 - (zero bit-planes - ROI shift of component 0)
              * (jpeg2000dec.c:1186-1194); Lref keeps the band orientation set with the geometry */
-            d.Lcup = (uint16_t)(d.M_b - ((int)s.zbp - hdr.roi[0]));
+            d.Lcup = s.nzb;
             continue;
         }
         d.Lcup = (uint16_t)s.Lcup;

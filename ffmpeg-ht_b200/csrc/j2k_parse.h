@@ -64,6 +64,7 @@ struct CblkState {
     uint8_t incl, lblock, plhd, npasses;
     uint8_t zbp;
     uint8_t ncontrib;
+    uint8_t nzb;             /* cblk->nonzerobits as computed at first inclusion (jpeg2000dec.c:1186-1194) */
     uint32_t Lcup, Lref, length;
     uint32_t data_off;
 };
@@ -76,7 +77,7 @@ struct TagNodeState {
 struct Header {
     int W = 0, H = 0, X0 = 0, Y0 = 0, TW = 0, TH = 0, TX0 = 0, TY0 = 0, ncomp = 0, precision = 0, rsiz = 0;
     int cbps[J2K_MAX_COMP] = {0}, cdx[J2K_MAX_COMP] = {0}, cdy[J2K_MAX_COMP] = {0}, roi[J2K_MAX_COMP] = {0};
-    int isHT = 0, cap_b05 = 0, cap_b11 = 0, cap_b14 = 0;
+    int isHT = 0, cap_b05 = 0, cap_b11 = 0, cap_b12 = 0, cap_b14 = 0;
     CodSty cod[J2K_MAX_COMP];
     QntSty qnt[J2K_MAX_COMP];
     int had_coc[J2K_MAX_COMP] = {0}, had_qcc[J2K_MAX_COMP] = {0};
@@ -92,6 +93,18 @@ struct Header {
     int cdef[J2K_MAX_COMP] = { -1, -1, -1, -1 };
     const char *pix_name = "none";      /* libavutil name of the chosen AVPixelFormat */
     int chroma_lw = 0, chroma_lh = 0;   /* its log2_chroma_w / log2_chroma_h */
+};
+
+/* coding / quantisation / progression styles of one tile: the main header's at its first tile-part (get_sot,
+ * jpeg2000dec.c:862-869), then whatever COD / COC / QCD / QCC / POC / RGN its tile-part headers carry */
+struct TileSty {
+    CodSty cod[J2K_MAX_COMP];
+    QntSty qnt[J2K_MAX_COMP];
+    int roi[J2K_MAX_COMP] = {0};            /* tile RGN; 0 = the main header's value (init_tile, :1052-1053) */
+    uint8_t had_coc[J2K_MAX_COMP] = {0}, had_qcc[J2K_MAX_COMP] = {0};   /* tile->properties */
+    int npoc = 0;
+    bool poc_default = true;
+    Header::Poc poc[32];
 };
 
 struct TilePart { const uint8_t *p, *end, *start; const uint8_t *hp, *hend; };   /* hp/hend: its run of PPM packet headers */
@@ -142,6 +155,9 @@ private:
     bool has_ppm_ = false;
     std::vector<std::vector<uint8_t>> ppt_;   /* per tile */
     std::vector<uint8_t> has_ppt_;
+    std::vector<TileSty> tsty_;
+    std::vector<uint8_t> geom_extra_, geom_extra_key_;   /* tile-header segments the geometry depends on */
+    int roi_of(int tileno, int c) const { return tsty_[tileno].roi[c] ? tsty_[tileno].roi[c] : hdr.roi[c]; }
     std::vector<uint8_t> tile_first_;          /* per tile: a tile-part with TPsot == 0 was seen */
     std::vector<size_t> ppt_pos_;             /* tile->packed_headers_stream as an offset into ppt_[tile] */
 

@@ -89,6 +89,13 @@ typedef struct Tile {
     int nparts;
     /* PPT: packed packet headers of this tile (get_ppt, jpeg2000dec.c:982-1014) */
     int first_seen;                                 /* a tile-part with TPsot == 0 set this tile's coding styles (get_sot, :862-869) */
+    /* the tile's own styles: the main header's at that point, then what COD / COC / QCD / QCC / POC segments of its
+     * tile-part headers change (tile->codsty / qntsty / poc / properties) */
+    CodSty cod[MAXC];
+    QntSty qnt[MAXC];
+    int had_coc[MAXC], had_qcc[MAXC];
+    int npoc, poc_default;
+    struct { int RS, CS, LYE, RE, CE, P; } poc[32];
     int has_ppt;
     uint8_t *ppt;
     size_t ppt_size, ppt_pos;                       /* ppt_pos = tile->packed_headers_stream */
@@ -100,7 +107,7 @@ typedef struct Dec {
     int red;                                        /* reduction_factor = AVCodecContext.lowres (jpeg2000dec.c:2807-2823) */
     int W, H, X0, Y0, TW, TH, TX0, TY0, ncomp, precision;
     int cbps[MAXC], cdx[MAXC], cdy[MAXC], roi[MAXC];
-    int isHT, cap_b05, cap_b11, cap_b14;
+    int isHT, cap_b05, cap_b11, cap_b12, cap_b14;
     CodSty cod[MAXC];
     QntSty qnt[MAXC];
     int had_coc[MAXC], had_qcc[MAXC];
@@ -617,6 +624,7 @@ static int parse_headers(Dec *d)
                     return ORACLE_ERR_PATCH;
                 d->cap_b05 = (ccap15 >> 5) & 1;
                 d->cap_b11 = (ccap15 >> 11) & 1;
+                d->cap_b12 = (ccap15 >> 12) & 1;
                 int P = ccap15 & 31, B = !P ? 8 : P < 20 ? P + 8 : P < 31 ? 4 * (P - 19) + 27 : 74;
                 if (B > 31)
                     return ORACLE_ERR_PATCH;
@@ -624,8 +632,8 @@ static int parse_headers(Dec *d)
             break;
         }
         case 0xFF52: {                                    /* COD */
-            if (cur_tile >= 0)                            /* HOMOGENEOUS set: no tile-part COD (:2514-2520); else: not restated */
-                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
+            if (cur_tile >= 0 && d->isHT && !d->cap_b11)  /* HOMOGENEOUS set: no tile-part COD (:2514-2520) */
+                return ORACLE_ERR_INVALID;
             if (segend - seg < 5)
                 return ORACLE_ERR_INVALID;
             CodSty tmp;
@@ -639,59 +647,79 @@ static int parse_headers(Dec *d)
             if ((ret = parse_cox(d, seg + 5, segend, &tmp)) < 0)
                 return ret;
             tmp.init = 1;
-            for (int c = 0; c < d->ncomp; c++)
-                if (!d->had_coc[c])
+            for (int c = 0; c < d->ncomp; c++) {
+                if (cur_tile >= 0) {
+                    if (!d->tile[cur_tile].had_coc[c])
+                        d->tile[cur_tile].cod[c] = tmp;
+                } else if (!d->had_coc[c])
                     d->cod[c] = tmp;
+            }
             seg += 10 + ((tmp.csty & 1) ? tmp.nres : 0);
             break;
         }
         case 0xFF53: {                                    /* COC */
-            if (cur_tile >= 0)
-                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
+            if (cur_tile >= 0 && d->isHT && !d->cap_b11)
+                return ORACLE_ERR_INVALID;
             if (segend - seg < 2)
                 return ORACLE_ERR_INVALID;
             int c = seg[0];
             if (c >= d->ncomp)
                 return ORACLE_ERR_INVALID;
-            CodSty *cs = &d->cod[c];
+            CodSty *cs = cur_tile >= 0 ? &d->tile[cur_tile].cod[c] : &d->cod[c];
             int keep = cs->csty & 6;
             cs->csty = seg[1] | keep;
             if ((ret = parse_cox(d, seg + 2, segend, cs)) < 0)
                 return ret;
-            d->had_coc[c] = 1;
+            if (cur_tile >= 0)
+                d->tile[cur_tile].had_coc[c] = 1;
+            else
+                d->had_coc[c] = 1;
             cs->init = 1;
             seg += 7 + ((cs->csty & 1) ? cs->nres : 0);
             break;
         }
         case 0xFF5C: {                                    /* QCD */
-            if (cur_tile >= 0)
-                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
+            if (cur_tile >= 0 && d->isHT && !d->cap_b11)
+                return ORACLE_ERR_INVALID;
             QntSty tmp;
             memset(&tmp, 0, sizeof(tmp));
             if ((ret = parse_qcx(seg, len - 2, &tmp)) < 0)
                 return ret;
-            for (int c = 0; c < d->ncomp; c++)
-                if (!d->had_qcc[c])
+            for (int c = 0; c < d->ncomp; c++) {
+                if (cur_tile >= 0) {
+                    if (!d->tile[cur_tile].had_qcc[c])
+                        d->tile[cur_tile].qnt[c] = tmp;
+                } else if (!d->had_qcc[c])
                     d->qnt[c] = tmp;
+            }
             seg = segend;
             break;
         }
         case 0xFF5D: {                                    /* QCC */
-            if (cur_tile >= 0)
-                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
+            if (cur_tile >= 0 && d->isHT && !d->cap_b11)
+                return ORACLE_ERR_INVALID;
             if (segend - seg < 1)
                 return ORACLE_ERR_INVALID;
             int c = seg[0];
             if (c >= d->ncomp)
                 return ORACLE_ERR_INVALID;
-            d->had_qcc[c] = 1;
-            if ((ret = parse_qcx(seg + 1, len - 3, &d->qnt[c])) < 0)
+            if (cur_tile >= 0)
+                d->tile[cur_tile].had_qcc[c] = 1;
+            else
+                d->had_qcc[c] = 1;
+            if ((ret = parse_qcx(seg + 1, len - 3, cur_tile >= 0 ? &d->tile[cur_tile].qnt[c] : &d->qnt[c])) < 0)
                 return ret;
             seg = segend;
             break;
         }
-        case 0xFF5E: {                                    /* RGN */
+        case 0xFF5E: {                                    /* RGN (get_rgn, :641-672) */
+            if (cur_tile >= 0 && d->isHT && !d->cap_b11)
+                return ORACLE_ERR_INVALID;
+            if (d->isHT && !d->cap_b12)                   /* "belongs to the RGNFREE set" (:2536-2540) */
+                return ORACLE_ERR_INVALID;
             if (segend - seg < 3 || seg[1] != 0 || seg[0] >= d->ncomp)
+                return ORACLE_ERR_INVALID;
+            if (cur_tile >= 0 && cur_tp != 0)             /* only in the first tile-part of a tile */
                 return ORACLE_ERR_INVALID;
             if (seg[2] > 30)
                 return ORACLE_ERR_PATCH;
@@ -719,22 +747,28 @@ static int parse_headers(Dec *d)
                 return ORACLE_ERR_PATCH;
             cur_tile = isot;
             cur_tp = tpsot;
-            if (!tpsot)
-                d->tile[isot].first_seen = 1;
+            if (!tpsot) {
+                Tile *t = &d->tile[isot];
+                t->first_seen = 1;
+                memcpy(t->cod, d->cod, sizeof(t->cod));
+                memcpy(t->qnt, d->qnt, sizeof(t->qnt));
+                memcpy(t->poc, d->poc, sizeof(t->poc));
+                t->npoc = d->npoc;
+                t->poc_default = 1;
+            }
             tp_end = seg + 8 + psot - len - 2;
             seg += 8;
             break;
         }
         case 0xFF5F: {                                    /* POC: get_poc (jpeg2000dec.c:760-818) */
-            if (cur_tile >= 0)                            /* :2558 refuses it for HOMOGENEOUS HT streams */
-                return d->isHT && !d->cap_b11 ? ORACLE_ERR_INVALID : ORACLE_ERR_PATCH;
+            if (cur_tile >= 0 && d->isHT && !d->cap_b11)  /* :2558 refuses it for HOMOGENEOUS HT streams */
+                return ORACLE_ERR_INVALID;
             if (d->end - seg < 5 || len < 2 + 7)
                 return ORACLE_ERR_INVALID;
             int n = (len - 2) / 7;
             if (n > 32)
                 return ORACLE_ERR_PATCH;
-            if (d->npoc + n > 32)
-                return ORACLE_ERR_INVALID;
+            struct { int RS, CS, LYE, RE, CE, P; } tmp[32];
             for (int i = 0; i < n; i++, seg += 7) {
                 int RS = seg[0], CS = seg[1], LYE = (int)rd16(seg + 2), RE = seg[4], CE = seg[5], P = seg[6];
                 if (!CE)
@@ -743,10 +777,25 @@ static int parse_headers(Dec *d)
                     CE = d->ncomp;
                 if (RS >= RE || RE > 33 || CS >= CE || !LYE)
                     return ORACLE_ERR_INVALID;
-                d->poc[d->npoc + i].RS = RS; d->poc[d->npoc + i].CS = CS; d->poc[d->npoc + i].LYE = LYE;
-                d->poc[d->npoc + i].RE = RE; d->poc[d->npoc + i].CE = CE; d->poc[d->npoc + i].P = P;
+                tmp[i].RS = RS; tmp[i].CS = CS; tmp[i].LYE = LYE; tmp[i].RE = RE; tmp[i].CE = CE; tmp[i].P = P;
             }
-            d->npoc += n;                                 /* a further POC segment appends (:805-812) */
+            if (cur_tile >= 0) {
+                /* the tile's list is a copy of the main header's until its first own segment, which replaces it;
+                 * further ones append (:806-816) */
+                Tile *t = &d->tile[cur_tile];
+                if (!t->npoc || t->poc_default)
+                    t->npoc = 0;
+                else if (t->npoc + n > 32)
+                    return ORACLE_ERR_INVALID;
+                memcpy(&t->poc[t->npoc], tmp, sizeof(tmp[0]) * (size_t)n);
+                t->npoc += n;
+                t->poc_default = 0;
+            } else {
+                if (d->npoc + n > 32)
+                    return ORACLE_ERR_INVALID;
+                memcpy(&d->poc[d->npoc], tmp, sizeof(tmp[0]) * (size_t)n);
+                d->npoc += n;                             /* a further POC segment appends (:805-812) */
+            }
             break;
         }
         case 0xFF60: {                                    /* PPM: main header only (:2597-2604) */
@@ -833,8 +882,8 @@ static int init_tile(Dec *d, int tileno)
 
     for (int c = 0; c < d->ncomp; c++) {
         Comp *comp = &t->comp[c];
-        const CodSty *cs = &d->cod[c];
-        const QntSty *qs = &d->qnt[c];
+        const CodSty *cs = &t->cod[c];
+        const QntSty *qs = &t->qnt[c];
         if (!cs->init)
             return ORACLE_ERR_INVALID;
         if (d->isHT && !d->cap_b05 && !cs->transform)
@@ -938,7 +987,7 @@ static void free_tile(Dec *d, Tile *t)
     for (int c = 0; c < d->ncomp; c++) {
         Comp *comp = &t->comp[c];
         if (comp->res) {
-            for (int r = 0; r < d->cod[c].nres; r++)
+            for (int r = 0; r < t->cod[c].nres; r++)
                 for (int b = 0; b < comp->res[r].nbands; b++) {
                     Band *bd = &comp->res[r].band[b];
                     if (!bd->prec)
@@ -1212,7 +1261,7 @@ fail:
 /* does (x, y) on the reference grid start a precinct of this resolution?  (jpeg2000dec.c:1700-1722) */
 static int precinct_at(Dec *d, Tile *t, int c, int r, int x, int y, int cprl_rule)
 {
-    const CodSty *cs = &d->cod[c];
+    const CodSty *cs = &t->cod[c];
     Res *rl = &t->comp[c].res[r];
     const int red = cs->nres - 1 - r;
     if (cprl_rule) {                                      /* the CPRL loop uses a weaker test (:1642-1648) */
@@ -1246,8 +1295,8 @@ static int precinct_at(Dec *d, Tile *t, int c, int r, int x, int y, int cprl_rul
 
 #define PACKET(c, r, pn, l)                                                                           \
     do {                                                                                              \
-        int e_ = decode_packet(d, &ps, &d->cod[c], &t->comp[c].res[r], pn, l,                         \
-                               d->qnt[c].expn + ((r) ? 3 * ((r) - 1) + 1 : 0), d->qnt[c].nguard,      \
+        int e_ = decode_packet(d, &ps, &t->cod[c], &t->comp[c].res[r], pn, l,                         \
+                               t->qnt[c].expn + ((r) ? 3 * ((r) - 1) + 1 : 0), t->qnt[c].nguard,      \
                                t->comp[0].roi_shift);                                                 \
         if (e_ < 0)                                                                                   \
             return e_;                                                                                \
@@ -1267,7 +1316,7 @@ static int po_iteration(Dec *d, Tile *t, PktState *pps, int RS, int CS, int LYE,
             for (int r = RS; ok && r < RE; r++) {
                 ok = 0;
                 for (int c = CS; c < CE; c++) {
-                    if (r >= d->cod[c].nres)
+                    if (r >= t->cod[c].nres)
                         continue;
                     ok = 1;
                     for (int pn = 0; pn < t->comp[c].res[r].npx * t->comp[c].res[r].npy; pn++)
@@ -1282,7 +1331,7 @@ static int po_iteration(Dec *d, Tile *t, PktState *pps, int RS, int CS, int LYE,
             ok = 0;
             for (int l = 0; l < LYE; l++)
                 for (int c = CS; c < CE; c++) {
-                    if (r >= d->cod[c].nres)
+                    if (r >= t->cod[c].nres)
                         continue;
                     ok = 1;
                     for (int pn = 0; pn < t->comp[c].res[r].npx * t->comp[c].res[r].npy; pn++)
@@ -1296,8 +1345,8 @@ static int po_iteration(Dec *d, Tile *t, PktState *pps, int RS, int CS, int LYE,
             int sx = 30, sy = 30;
             ok = 0;
             for (int c = CS; c < CE; c++)
-                if (r < d->cod[c].nres) {
-                    int red = d->cod[c].nres - 1 - r;
+                if (r < t->cod[c].nres) {
+                    int red = t->cod[c].nres - 1 - r;
                     sx = imin(sx, t->comp[c].res[r].ppx + red);
                     sy = imin(sy, t->comp[c].res[r].ppy + red);
                 }
@@ -1306,7 +1355,7 @@ static int po_iteration(Dec *d, Tile *t, PktState *pps, int RS, int CS, int LYE,
             for (int y = t->c.y0; y < t->c.y1; y = (y / sy + 1) * sy)
                 for (int x = t->c.x0; x < t->c.x1; x = (x / sx + 1) * sx)
                     for (int c = CS; c < CE; c++) {
-                        if (r >= d->cod[c].nres)
+                        if (r >= t->cod[c].nres)
                             continue;
                         int pn = precinct_at(d, t, c, r, x, y, 0);
                         if (pn == -1)
@@ -1322,8 +1371,8 @@ static int po_iteration(Dec *d, Tile *t, PktState *pps, int RS, int CS, int LYE,
     case 3: { /* PCRL */
         int sx = 32, sy = 32;
         for (int c = CS; c < CE; c++)
-            for (int r = RS; r < imin(d->cod[c].nres, RE); r++) {
-                int red = d->cod[c].nres - 1 - r;
+            for (int r = RS; r < imin(t->cod[c].nres, RE); r++) {
+                int red = t->cod[c].nres - 1 - r;
                 sx = imin(sx, t->comp[c].res[r].ppx + red);
                 sy = imin(sy, t->comp[c].res[r].ppy + red);
             }
@@ -1334,7 +1383,7 @@ static int po_iteration(Dec *d, Tile *t, PktState *pps, int RS, int CS, int LYE,
         for (int y = t->c.y0; y < t->c.y1; y = (y / sy + 1) * sy)
             for (int x = t->c.x0; x < t->c.x1; x = (x / sx + 1) * sx)
                 for (int c = CS; c < CE; c++)
-                    for (int r = RS; r < imin(d->cod[c].nres, RE); r++) {
+                    for (int r = RS; r < imin(t->cod[c].nres, RE); r++) {
                         int pn = precinct_at(d, t, c, r, x, y, 0);
                         if (pn < 0)
                             continue;
@@ -1346,11 +1395,11 @@ static int po_iteration(Dec *d, Tile *t, PktState *pps, int RS, int CS, int LYE,
     case 4: /* CPRL */
         for (int c = CS; c < CE; c++) {
             int sx = 32, sy = 32;
-            const int rend = imin(d->cod[c].nres, RE);
+            const int rend = imin(t->cod[c].nres, RE);
             if (RS >= rend)
                 continue;
             for (int r = RS; r < rend; r++) {
-                int red = d->cod[c].nres - 1 - r;
+                int red = t->cod[c].nres - 1 - r;
                 sx = imin(sx, t->comp[c].res[r].ppx + red);
                 sy = imin(sy, t->comp[c].res[r].ppy + red);
             }
@@ -1380,13 +1429,13 @@ static int po_iteration(Dec *d, Tile *t, PktState *pps, int RS, int CS, int LYE,
 static int decode_packets(Dec *d, Tile *t)
 {
     PktState ps = { t, 0 };
-    const int nlayers = d->cod[0].nlayers;
+    const int nlayers = t->cod[0].nlayers;
     d->bit_index = 8;
-    if (!d->npoc)
-        return po_iteration(d, t, &ps, 0, 0, nlayers, 33, d->ncomp, d->cod[0].prog);
-    for (int i = 0; i < d->npoc; i++) {
-        int ret = po_iteration(d, t, &ps, d->poc[i].RS, d->poc[i].CS, imin(d->poc[i].LYE, nlayers), d->poc[i].RE,
-                               imin(d->poc[i].CE, d->ncomp), d->poc[i].P);
+    if (!t->npoc)
+        return po_iteration(d, t, &ps, 0, 0, nlayers, 33, d->ncomp, t->cod[0].prog);
+    for (int i = 0; i < t->npoc; i++) {
+        int ret = po_iteration(d, t, &ps, t->poc[i].RS, t->poc[i].CS, imin(t->poc[i].LYE, nlayers), t->poc[i].RE,
+                               imin(t->poc[i].CE, d->ncomp), t->poc[i].P);
         if (ret < 0)
             return ret;
     }
@@ -1450,8 +1499,8 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
     int32_t *t1 = malloc(sizeof(int32_t) * 4096);
     for (int c = 0; c < d->ncomp; c++) {
         Comp *comp = &t->comp[c];
-        const CodSty *cs = &d->cod[c];
-        const QntSty *qs = &d->qnt[c];
+        const CodSty *cs = &t->cod[c];
+        const QntSty *qs = &t->qnt[c];
         const int W = comp->cr.x1 - comp->cr.x0;
         int coded = 0, subband = 0;
         for (int r = 0; r < cs->nres - d->red; r++) {      /* nreslevels2decode (:2230) */
@@ -1506,12 +1555,12 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
     }
     free(t1);
 
-    if (d->cod[0].mct) {                                  /* mct_decode (jpeg2000dec.c:2183-2209) */
+    if (t->cod[0].mct) {                                  /* mct_decode (jpeg2000dec.c:2183-2209) */
         int ok = 1;
         for (int i = 1; i < 3; i++)
-            ok &= d->cod[0].transform == d->cod[i].transform && !memcmp(&t->comp[0].cr, &t->comp[i].cr, sizeof(Rect));
+            ok &= t->cod[0].transform == t->cod[i].transform && !memcmp(&t->comp[0].cr, &t->comp[i].cr, sizeof(Rect));
         if (ok)
-            oracle_mct(d->cod[0].transform, t->comp[0].data, t->comp[1].data, t->comp[2].data,
+            oracle_mct(t->cod[0].transform, t->comp[0].data, t->comp[1].data, t->comp[2].data,
                        (t->comp[0].cr.x1 - t->comp[0].cr.x0) * (t->comp[0].cr.y1 - t->comp[0].cr.y0));
     }
 
@@ -1533,7 +1582,7 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
         for (int y = comp->cr.y0 - ceildiv(d->Y0, d->cdy[c]); y < h; y++) {
             uint8_t *line = planes[plane] + (size_t)y * strides[plane];
             for (int x = comp->cr.x0 - ceildiv(d->X0, d->cdx[c]); x < w; x++, k++) {
-                int val = d->cod[c].transform == ORACLE_DWT97 ? (int)lrintf(fp[k]) : ip[k];
+                int val = t->cod[c].transform == ORACLE_DWT97 ? (int)lrintf(fp[k]) : ip[k];
                 val += 1 << (cbps - 1);
                 val = clip(val, 0, (1 << cbps) - 1);
                 val <<= precision - cbps;

@@ -12,7 +12,7 @@ import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import ht_block, mq_block, oracle, oracle_decode
 from test_oracle_vs_ref import (LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
-                                part1_stream, tile_part_stream,
+                                TILE_STYLES, part1_stream, tile_part_stream, tile_style_marker_cases, tile_style_stream,
                                 packed_marker_cases, packed_stream, poc_marker_cases, poc_stream,
                                 subsampled_stream)
 
@@ -286,6 +286,43 @@ def test_plan_of_tile_part_streams(t):
         assert r == 0 and np.array_equal(pic, opic)
     except fb.DecodeError as e:
         assert r < 0 and e.code < 0
+
+
+@pytest.mark.parametrize("t", TILE_STYLES, ids=lambda t: f"var{t['var']}-" + "-".join(f"{k}{v}" for k, v in t["cfg"].items())[:30])
+def test_plan_of_tile_style_streams(t):
+    """COD / QCD / POC in tile-part headers: geometry, step sizes and packet order per tile."""
+    cs, _ = tile_style_stream(t)
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r, oinfo, opic = oracle_decode(cs, bitexact)
+        assert r == 0
+        info, pic = picture_from_plan(cs, fb.FLAG_BITEXACT if bitexact else 0)
+        assert np.array_equal(pic, opic)
+
+
+def test_tile_style_marker_validation_matches_oracle():
+    n_ok = 0
+    for bad in tile_style_marker_cases():
+        r, _, opic = oracle_decode(bad)
+        try:
+            _, pic = picture_from_plan(bad, 0)
+            assert r == 0 and np.array_equal(pic, opic)
+            n_ok += 1
+        except fb.DecodeError as e:
+            assert r < 0 and e.code == r
+    assert n_ok >= 4
+
+
+def test_geometry_cache_sees_tile_header_changes():
+    """Two frames with the same main header but different tile-part COD segments must not share cached geometry."""
+    import ctypes
+    planes = j2kgen.synth_image(128, 96, 3, 8, seed=4)
+    kw = dict(levels=2, cblk=(32, 32), tile=(64, 48))
+    a = j2kgen.encode(planes, 8, j2kgen.EncParams(tile_var=4, **kw))       # odd tiles: narrower code-blocks
+    b = j2kgen.encode(planes, 8, j2kgen.EncParams(tile_var=2, **kw))       # odd tiles: one level less
+    for cs in (a, b, a, b):
+        r, _, opic = oracle_decode(cs)
+        _, pic = picture_from_plan(cs, 0)
+        assert r == 0 and np.array_equal(pic, opic)
 
 
 def test_packed_header_marker_validation_matches_oracle():

@@ -402,6 +402,94 @@ def test_tile_part_streams_match_reference(t):
             assert info1[:2] == info2[:2] and np.array_equal(out1, out2)
 
 
+# coding / quantisation / progression styles of single tiles: COD / QCD / POC segments in the first tile-part header
+# of every odd tile (Ccap15 bit 11 set: not the HOMOGENEOUS set).  var: 1 progression, 2 one level less, 4 narrower
+# code-blocks, 8 guard bit / step, 16 tile POC
+TILE_STYLES = [
+    dict(cfg=dict(levels=3, cblk=(32, 32), tile=(64, 48)), var=1),
+    dict(cfg=dict(levels=3, cblk=(32, 32), tile=(64, 48)), var=2),
+    dict(cfg=dict(levels=3, cblk=(32, 32), tile=(64, 48)), var=4),
+    dict(cfg=dict(levels=3, cblk=(32, 32), tile=(64, 48)), var=8),
+    dict(cfg=dict(levels=3, cblk=(32, 32), tile=(64, 48)), var=16),
+    dict(cfg=dict(levels=3, cblk=(32, 32), tile=(64, 48), packed_headers=1, ppx_chunk=61), var=31),
+    dict(cfg=dict(levels=3, cblk=(32, 32), tile=(64, 48), reversible=False, base_step=1.0), var=12),
+    dict(cfg=dict(levels=3, cblk=(32, 32), tile=(64, 48), reversible=False, base_step=1.0, tp_packets=3, tp_interleave=True), var=31),
+    dict(cfg=dict(levels=4, cblk=(16, 16), tile=(100, 60), precincts=[(5, 5), (6, 6)], prog=1, layers=2, npasses=3, eph=True), var=19),
+    dict(cfg=dict(levels=4, cblk=(16, 16), tile=(100, 60), precincts=[(5, 5), (6, 6)], prog=3, sop=True), var=7),
+]
+
+
+def tile_style_stream(t, w=200, h=120, nc=3, bd=10, seed=3):
+    planes = j2kgen.synth_image(w, h, nc, bd, seed=seed)
+    return j2kgen.encode(planes, bd, j2kgen.EncParams(tile_var=t["var"], **t["cfg"])), planes
+
+
+@pytest.mark.parametrize("t", TILE_STYLES, ids=lambda t: f"var{t['var']}-" + "-".join(f"{k}{v}" for k, v in t["cfg"].items())[:40])
+def test_tile_style_streams_bit_exact(t):
+    """COD / QCD / POC in tile-part headers (get_sot's copy of the main styles, then get_cod / get_qcd / get_poc on the
+    tile's copies, jpeg2000dec.c:862-869, :571-759, :760-818): reference == oracle; lossless ones give back the source."""
+    cs, planes = tile_style_stream(t)
+    assert cs.count(b"\xff\x52") + cs.count(b"\xff\x5c") + cs.count(b"\xff\x5f") > 2
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r1, info1, out1, name = ref_decode(cs, bitexact)
+        r2, info2, out2 = oracle_decode(cs, bitexact)
+        assert r1 == 0 and r2 == 0
+        assert info1[:2] == info2[:2] and oracle_pix_name() == name and np.array_equal(out1, out2)
+        if t["cfg"].get("reversible", True) and t["cfg"].get("npasses", 1) == 1:
+            assert np.array_equal(out1.view(np.uint16).reshape(120, 200, 3) >> 6, np.stack(planes, -1))
+
+
+def tile_style_marker_cases():
+    """Tile-part COD in a HOMOGENEOUS stream (Ccap15 bit 11 clear), a tile RGN (first and later tile-part), a tile QCC
+    and COC, a second tile POC segment, a damaged tile COD."""
+    planes = j2kgen.synth_image(128, 96, 3, 8, seed=4)
+    kw = dict(levels=2, cblk=(32, 32), tile=(64, 48))
+    cs = j2kgen.encode(planes, 8, j2kgen.EncParams(tile_var=17, **kw))
+
+    def insert_in_tile_header(data, tile_sot_index, segment):
+        sots = [i for i in range(len(data) - 3) if data[i:i + 4] == b"\xff\x90\x00\x0a"]
+        at = sots[tile_sot_index]
+        psot = int.from_bytes(data[at + 6:at + 10], "big") + len(segment)
+        return data[:at + 6] + psot.to_bytes(4, "big") + data[at + 10:at + 12] + segment + data[at + 12:]
+
+    cases = []
+    cap = cs.index(b"\xff\x50")
+    b = bytearray(cs); b[cap + 8] &= 0xF7; cases.append(bytes(b))                           # bit 11 cleared: INVALIDDATA
+    cases.append(insert_in_tile_header(cs, 1, b"\xff\x5e\x00\x05\x01\x00\x03"))            # RGN in the RGNFREE set (bit 12 clear)
+    b = bytearray(cs); b[cap + 8] |= 0x10; cs = bytes(b)                                    # from here on: bit 12 set
+    cases.append(insert_in_tile_header(cs, 1, b"\xff\x5e\x00\x05\x01\x00\x03"))            # RGN, component 1, shift 3
+    cases.append(insert_in_tile_header(cs, 2, b"\xff\x5e\x00\x05\x00\x00\x02"))            # RGN, component 0 (quirk Q6)
+    cases.append(insert_in_tile_header(cs, 0, b"\xff\x5e\x00\x05\x00\x00\x1f"))            # shift 31: PATCHWELCOME
+    qcd = cs.index(b"\xff\x5c")
+    n = int.from_bytes(cs[qcd + 2:qcd + 4], "big")
+    qcc = b"\xff\x5d" + (n + 1).to_bytes(2, "big") + b"\x02" + cs[qcd + 4:qcd + 2 + n]
+    cases.append(insert_in_tile_header(cs, 3, qcc))                                         # tile QCC for component 2
+    cod = cs.index(b"\xff\x52")
+    coc = b"\xff\x53\x00\x09\x01" + cs[cod + 4:cod + 5] + cs[cod + 9:cod + 14]
+    cases.append(insert_in_tile_header(cs, 2, coc))                                         # tile COC for component 1
+    poc = b"\xff\x5f\x00\x09\x00\x00\x00\x01\x03\x03\x02"
+    cases.append(insert_in_tile_header(cs, 1, poc))                                         # tile POC in front of the tile's own
+    tile_cod = cs.index(b"\xff\x52", cs.index(b"\xff\x90"))
+    b = bytearray(cs); b[tile_cod + 9] = 9; cases.append(bytes(b))                          # tile COD: code-block width 2^11
+    multi = bytearray(j2kgen.encode(planes, 8, j2kgen.EncParams(tile_var=1, tp_packets=4, **kw)))
+    multi[multi.index(b"\xff\x50") + 8] |= 0x10
+    multi = bytes(multi)
+    cases.append(insert_in_tile_header(multi, 1, b"\xff\x5e\x00\x05\x00\x00\x02"))         # RGN in a later tile-part
+    return cases
+
+
+def test_tile_style_marker_validation_matches_reference():
+    verdicts = []
+    for bad in tile_style_marker_cases():
+        r1, _, out1, _ = ref_decode(bad, 0)
+        r2, _, out2 = oracle_decode(bad, 0)
+        verdicts.append(r1)
+        assert (r1 == 0) == (r2 == 0), (len(verdicts), r1, r2)
+        if r1 == 0:
+            assert np.array_equal(out1, out2), len(verdicts)
+    assert sum(v != 0 for v in verdicts) >= 3 and sum(v == 0 for v in verdicts) >= 4, verdicts
+
+
 # ---- Part-1 (EBCOT / MQ) code-blocks: SURVEY 8(f) row N4 ----------------------------------------------------
 # The reference has no HT encoder and this repo's test encoder writes HT only, so Part-1 streams come from an
 # independent encoder: OpenJPEG through Pillow (code-block style 0: no bypass / restart / reset / causal / segsym).

@@ -67,6 +67,11 @@ typedef struct J2kGenParams {
                                   * reference's limit); PPT headers all go to the first part (jpeg2000dec.c:995), PPM
                                   * gets one Nppm-prefixed run per tile-part */
     int32_t tp_interleave;       /* with tp_packets: write part 0 of every tile, then part 1 of every tile, ... */
+    int32_t tile_var;            /* != 0: every odd tile is coded differently and says so in its first tile-part header
+                                  * (Ccap15 bit 11 set: not the HOMOGENEOUS set, jpeg2000dec.c:2514-2563).  Bits:
+                                  * 1 another progression order (COD), 2 one decomposition level less (COD + QCD),
+                                  * 4 narrower code-blocks (COD), 8 one more guard bit / a coarser step (QCD),
+                                  * 16 a POC marker segment with two entries (only without a main-header POC) */
 } J2kGenParams;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -1061,6 +1066,44 @@ static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precn
     return 0;
 }
 
+static void quant_exps(const J2kGenParams *P, int compno, int r, int bandpos, int *expn, int *mant);
+
+/* COD and QCD marker segments from the parameters: main header, or a tile-part header when a tile differs */
+static void put_cod(Buf *out, const J2kGenParams *P, int C)
+{
+    const int L = P->levels;
+    buf_put16(out, 0xFF52);
+    buf_put16(out, 12 + (P->use_precincts ? L + 1 : 0));
+    buf_put(out, (P->use_precincts ? 1 : 0) | (P->sop ? 2 : 0) | (P->eph ? 4 : 0));
+    buf_put(out, P->prog); buf_put16(out, P->layers == 2 ? 2 : 1); buf_put(out, (P->mct && C >= 3) ? 1 : 0);
+    buf_put(out, L); buf_put(out, P->cbw_log2 - 2); buf_put(out, P->cbh_log2 - 2);
+    buf_put(out, 0x40 | (P->vsc ? 0x08 : 0));
+    buf_put(out, P->reversible ? 1 : 0);
+    if (P->use_precincts)
+        for (int r = 0; r <= L; r++) buf_put(out, P->prec_exps[r]);
+}
+
+static void put_qcd(Buf *out, const J2kGenParams *P)
+{
+    const int nb = 3 * P->levels + 1;
+    buf_put16(out, 0xFF5C);
+    if (P->reversible) {
+        buf_put16(out, 3 + nb); buf_put(out, (P->guard_bits << 5) | 0);
+        for (int b = 0; b < nb; b++) {
+            int r = b == 0 ? 0 : (b - 1) / 3 + 1, bp = b == 0 ? 0 : (b - 1) % 3 + 1, e, m;
+            quant_exps(P, 0, r, bp, &e, &m);
+            buf_put(out, e << 3);
+        }
+    } else {
+        buf_put16(out, 3 + 2 * nb); buf_put(out, (P->guard_bits << 5) | 2);
+        for (int b = 0; b < nb; b++) {
+            int r = b == 0 ? 0 : (b - 1) / 3 + 1, bp = b == 0 ? 0 : (b - 1) % 3 + 1, e, m;
+            quant_exps(P, 0, r, bp, &e, &m);
+            buf_put16(out, (e << 11) | m);
+        }
+    }
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 
 static void quant_exps(const J2kGenParams *P, int compno, int r, int bandpos, int *expn, int *mant)
@@ -1112,37 +1155,11 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
     {
         int magb_bits = 0;   /* the reference only range-checks MAGB (jpeg2000dec.c:473-486) */
         buf_put16(&out, 0xFF50); buf_put16(&out, 8); buf_put32(&out, 0x00020000);
-        buf_put16(&out, (P->reversible ? 0 : 0x0020) | (P->packed_headers == 1 ? 0x0800 : 0) | magb_bits);
+        buf_put16(&out, (P->reversible ? 0 : 0x0020) | ((P->packed_headers == 1 || P->tile_var) ? 0x0800 : 0) | magb_bits);
     }
-    buf_put16(&out, 0xFF52);
-    buf_put16(&out, 12 + (P->use_precincts ? L + 1 : 0));
-    buf_put(&out, (P->use_precincts ? 1 : 0) | (P->sop ? 2 : 0) | (P->eph ? 4 : 0));
     const int NLAY = P->layers == 2 ? 2 : 1;
-    buf_put(&out, P->prog); buf_put16(&out, NLAY); buf_put(&out, (P->mct && C >= 3) ? 1 : 0);
-    buf_put(&out, L); buf_put(&out, P->cbw_log2 - 2); buf_put(&out, P->cbh_log2 - 2);
-    buf_put(&out, 0x40 | (P->vsc ? 0x08 : 0));
-    buf_put(&out, P->reversible ? 1 : 0);
-    if (P->use_precincts)
-        for (int r = 0; r <= L; r++) buf_put(&out, P->prec_exps[r]);
-    {
-        int nb = 3 * L + 1;
-        buf_put16(&out, 0xFF5C);
-        if (P->reversible) {
-            buf_put16(&out, 3 + nb); buf_put(&out, (P->guard_bits << 5) | 0);
-            for (int b = 0; b < nb; b++) {
-                int r = b == 0 ? 0 : (b - 1) / 3 + 1, bp = b == 0 ? 0 : (b - 1) % 3 + 1, e, m;
-                quant_exps(P, 0, r, bp, &e, &m);
-                buf_put(&out, e << 3);
-            }
-        } else {
-            buf_put16(&out, 3 + 2 * nb); buf_put(&out, (P->guard_bits << 5) | 2);
-            for (int b = 0; b < nb; b++) {
-                int r = b == 0 ? 0 : (b - 1) / 3 + 1, bp = b == 0 ? 0 : (b - 1) % 3 + 1, e, m;
-                quant_exps(P, 0, r, bp, &e, &m);
-                buf_put16(&out, (e << 11) | m);
-            }
-        }
-    }
+    put_cod(&out, P, C);
+    put_qcd(&out, P);
     if (P->npoc > 0) {
         if (P->npoc > 8) { P->error = 4; return -4; }
         int first = P->poc_split > 0 && P->poc_split < P->npoc ? P->poc_split : P->npoc;
@@ -1168,6 +1185,30 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
     for (int ty = 0; ty < nty; ty++)
         for (int tx = 0; tx < ntx; tx++) {
             const int tileno = ty * ntx + tx;
+            /* the parameters this tile is coded with: the main header's, or a variation announced in its header */
+            J2kGenParams *const Pmain = P;
+            J2kGenParams Pt = *Pmain;
+            const int tile_differs = Pmain->tile_var && (tileno & 1);
+            if (tile_differs) {
+                if (Pmain->tile_var & 1) Pt.prog = (Pmain->prog + 2) % 5;
+                if (Pmain->tile_var & 2) Pt.levels = imax(1, Pmain->levels - 1);
+                if (Pmain->tile_var & 4) Pt.cbw_log2 = imax(2, Pmain->cbw_log2 - 1);
+                if (Pmain->tile_var & 8) {
+                    if (Pmain->reversible) Pt.guard_bits = imin(7, Pmain->guard_bits + 1);
+                    else Pt.base_step = Pmain->base_step * 2.0f;
+                }
+                if ((Pmain->tile_var & 16) && !Pmain->npoc) {
+                    const int nl = Pmain->layers == 2 ? 2 : 1;
+                    Pt.npoc = 2;
+                    Pt.poc[0][0] = 0; Pt.poc[0][1] = 0; Pt.poc[0][2] = nl; Pt.poc[0][3] = imax(1, (Pt.levels + 1) / 2);
+                    Pt.poc[0][4] = C; Pt.poc[0][5] = 1;
+                    Pt.poc[1][0] = 0; Pt.poc[1][1] = 0; Pt.poc[1][2] = nl; Pt.poc[1][3] = Pt.levels + 1;
+                    Pt.poc[1][4] = C; Pt.poc[1][5] = 0;
+                }
+            }
+            {
+            J2kGenParams *P = &Pt;
+            const int L = Pt.levels;
             const int tx0 = imax(X0 + tx * TW, X0), tx1 = imin(X0 + (tx + 1) * TW, X1);
             const int ty0 = imax(Y0 + ty * TH, Y0), ty1 = imin(Y0 + (ty + 1) * TH, Y1);
             const int W = tx1 - tx0, H = ty1 - ty0;
@@ -1359,6 +1400,17 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
                 Buf *tp_out = &tparts[tileno * 32 + k];
                 buf_put16(tp_out, 0xFF90); buf_put16(tp_out, 10); buf_put16(tp_out, tileno); buf_put32(tp_out, 0);
                 buf_put(tp_out, k); buf_put(tp_out, nparts);
+                if (tile_differs && k == 0) {             /* this tile's own coding / quantisation / progression */
+                    if (Pmain->tile_var & 7) put_cod(tp_out, P, C);
+                    if (Pmain->tile_var & (2 | 8)) put_qcd(tp_out, P);
+                    if ((Pmain->tile_var & 16) && !Pmain->npoc) {
+                        buf_put16(tp_out, 0xFF5F); buf_put16(tp_out, 2 + 7 * P->npoc);
+                        for (int i = 0; i < P->npoc; i++) {
+                            buf_put(tp_out, P->poc[i][0]); buf_put(tp_out, P->poc[i][1]); buf_put16(tp_out, P->poc[i][2]);
+                            buf_put(tp_out, P->poc[i][3]); buf_put(tp_out, P->poc[i][4]); buf_put(tp_out, P->poc[i][5]);
+                        }
+                    }
+                }
                 if (P->packed_headers == 1 && k == 0) {
                     const size_t chunk = P->ppx_chunk > 0 ? (size_t)imin(P->ppx_chunk, 65532) : 65532;
                     int z = 0;
@@ -1398,6 +1450,10 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
             }
             free(res);
             free(tp);
+            }
+            Pmain->stats_blocks = Pt.stats_blocks;
+            Pmain->stats_max_lcup = Pt.stats_max_lcup;
+            if (Pt.error) Pmain->error = Pt.error;
         }
     /* emit the tile-parts: tile after tile, or part k of every tile before part k + 1 of any */
     for (int pass = 0; pass < (P->tp_interleave ? 32 : 1); pass++)

@@ -32,7 +32,7 @@ class _Params(ctypes.Structure):
         ("layers", ctypes.c_int32), ("sub_x", ctypes.c_int32 * 4), ("sub_y", ctypes.c_int32 * 4),
         ("npoc", ctypes.c_int32), ("poc", (ctypes.c_int32 * 6) * 8), ("poc_split", ctypes.c_int32),
         ("packed_headers", ctypes.c_int32), ("ppx_chunk", ctypes.c_int32),
-        ("tp_packets", ctypes.c_int32), ("tp_interleave", ctypes.c_int32),
+        ("tp_packets", ctypes.c_int32), ("tp_interleave", ctypes.c_int32), ("tile_var", ctypes.c_int32),
     ]
 
 
@@ -82,6 +82,8 @@ class EncParams:
     ppx_chunk: int = 0            # payload bytes per PPT / PPM marker segment (0 = 65532)
     tp_packets: int = 0           # > 0: a new tile-part after this many packets (at most 32 parts per tile)
     tp_interleave: bool = False   # write part k of every tile before part k + 1 of any
+    tile_var: int = 0             # odd tiles coded differently (COD / QCD / POC in their tile-part header): bit 1 progression,
+    #                               2 one level less, 4 narrower code-blocks, 8 guard bit / step, 16 tile POC
     stats: dict = field(default_factory=dict)
 
 
@@ -121,6 +123,7 @@ def encode(planes, bitdepth: int, p: EncParams) -> bytes:
                     P.poc[i][k] = e[k]
         P.packed_headers, P.ppx_chunk = p.packed_headers, p.ppx_chunk
         P.tp_packets, P.tp_interleave = p.tp_packets, int(p.tp_interleave)
+        P.tile_var = p.tile_var
         cap = int(w * h * len(planes) * 4 + (1 << 20))
         out = np.empty(cap, np.uint8)
         ptrs = (ctypes.c_void_p * len(planes))(*[a.ctypes.data for a in planes])
