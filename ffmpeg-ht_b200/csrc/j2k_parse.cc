@@ -7,8 +7,8 @@
  *   init_tile :1016-1070   component/band/precinct/code-block geometry jpeg2000.c:274-577
  *   step sizes jpeg2000.c:214-272   packet headers jpeg2000dec.c:1136-1542 (HT paths)
  *   progression orders :1544-1833
- * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 MQ blocks, MIXED/HTDECLARED sets, coding /
- * quantisation / progression changes in tile-part headers, tile-specific ROI, PAL8 -- SURVEY.md section 8(f) "next".
+ * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 blocks with mode switches, MIXED/HTDECLARED sets,
+ * PAL8 -- SURVEY.md section 8(f) "next".
  */
 #include "j2k_parse.h"
 
