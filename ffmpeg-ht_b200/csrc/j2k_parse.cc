@@ -7,8 +7,7 @@
  *   init_tile :1016-1070   component/band/precinct/code-block geometry jpeg2000.c:274-577
  *   step sizes jpeg2000.c:214-272   packet headers jpeg2000dec.c:1136-1542 (HT paths)
  *   progression orders :1544-1833
- * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 blocks with mode switches, MIXED/HTDECLARED sets,
- * PAL8 -- SURVEY.md section 8(f) "next".
+ * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 blocks with mode switches, PAL8 -- SURVEY.md section 8(f) "next".
  */
 #include "j2k_parse.h"
 
@@ -662,9 +661,11 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             uint32_t psot = rd32(seg + 2);
             int tpsot = seg[6];
             int64_t left = end - (seg + 8);
+            /* get_sot measures against "bytes left - 2 + n + 2" AFTER it has read the 8 bytes (:845-850): a
+             * tile-part has to end two bytes (the EOC marker) before the end of the packet */
             if (!psot)
-                psot = (uint32_t)(left + len + 2);
-            if ((int64_t)psot > left + len + 2)
+                psot = (uint32_t)(left + len);
+            if ((int64_t)psot > left + len)
                 return B200J2K_ERR_INVALIDDATA;
             if (tpsot >= 32)
                 return B200J2K_ERR_PATCHWELCOME;
@@ -832,11 +833,10 @@ int Parser::build_geometry(int flags)
                 return B200J2K_ERR_INVALIDDATA;
             if (h.isHT && h.cap_b14 != (cs.cblk_style >> 6) && h.cap_b14 != 0)
                 return B200J2K_ERR_INVALIDDATA;
-            if (cs.cblk_style & 0x80)
-                return B200J2K_ERR_PATCHWELCOME;          /* MIXED code-blocks */
-            if (!(cs.cblk_style & 0x40) && cs.cblk_style)
+            if (!(cs.cblk_style & 0xC0) && cs.cblk_style)
                 return B200J2K_ERR_PATCHWELCOME;          /* Part-1 blocks with bypass / restart / reset / causal /
-                                                           * segmentation symbols: only style 0 is served */
+                                                           * segmentation symbols: only style 0 is served (for the
+                                                           * Part-1 blocks of a MIXED stream tier 2 checks that) */
             /* cc = comp->coord_o: every resolution, band, precinct and code-block is laid out from it;
              * cr = comp->coord = cc reduced by lowres: the plane, the DWT and the output use it
              * (jpeg2000dec.c:1047-1050, jpeg2000.c:483-530) */
@@ -963,9 +963,10 @@ int Parser::build_geometry(int flags)
                                 d.dst_off = tc.coef_off + (uint32_t)(y0 - bd.c.y0 + offy) * (uint32_t)cw + (uint32_t)(x0 - bd.c.x0 + offx);
                                 d.M_b = (uint8_t)M_b;
                                 d.flags = (uint8_t)(((cs.cblk_style & 8) ? 1 : 0) | (cs.transform << 1));
-                                if (!(cs.cblk_style & 0x40)) {
-                                    d.flags |= J2K_CBLK_MQ;
-                                    d.Lref = (uint16_t)(b + (r > 0));        /* bandpos (jpeg2000dec.c:2240) */
+                                d.pad = (uint8_t)(b + (r > 0));              /* bandpos (jpeg2000dec.c:2240) */
+                                if (!(cs.cblk_style & 0xC0)) {
+                                    d.flags |= J2K_CBLK_MQ;                  /* MIXED sets: decided per block in tier 2 */
+                                    d.Lref = d.pad;
                                 }
                                 if (r >= nres2decode) {
                                     /* dropped by lowres: the packets are still parsed, the block is never decoded
@@ -1214,7 +1215,9 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                 CblkState &cb = state_[pg.cblk_base + k];
                 int incl;
                 if (!cb.incl) {
-                    cb.plhd = 1;
+                    cb.modes = (uint8_t)cs.cblk_style;    /* :1177-1179 */
+                    if (cb.modes >= 0x40)
+                        cb.plhd = 1;
                     if (layno > 0)
                         tagtree_decode(pg.tag_base, pg.ncw, pg.nch, k, 1);
                     incl = tagtree_decode(pg.tag_base, pg.ncw, pg.nch, k, layno + 1) == layno;
@@ -1257,14 +1260,15 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
 
                 int segment_passes, next_segment_passes = 0, nb;
                 unsigned segment_bytes = 0;
-                if (!(cs.cblk_style & 0x40)) {
-                    /* Part-1 block, style 0: one codeword segment, one length of lblock + floor(log2(passes))
-                     * bits per packet (jpeg2000dec.c:1364-1368) */
-                    segment_bytes = (unsigned)bits(cb.lblock + ilog2((unsigned)newpasses));
-                    cb.npasses = (uint8_t)(cb.npasses + newpasses);
-                    in.seg[in.nseg++] = segment_bytes & 0xFFFF;
-                    continue;
-                }
+                /* a MIXED block (SPcod bit 7) that the length rules unmask as a Part-1 block: HT bit off for good
+                 * (:1271-1274, :1303-1305, :1331-1333); only style 0 Part-1 blocks are served */
+                auto turns_part1 = [&]() -> bool {
+                    if (cs.cblk_style & 0x3F)
+                        return false;
+                    cb.plhd = 0;
+                    cb.modes &= (uint8_t)~0x40;
+                    return true;
+                };
                 if (cb.plhd) {
                     int href = (cb.npasses + newpasses - 1) % 3;
                     segment_passes = newpasses - href;
@@ -1274,16 +1278,30 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                         segment_passes = newpasses;
                         while (pass_bound <= segment_passes) { nb++; pass_bound += pass_bound; }
                         segment_bytes = (unsigned)bits(nb);
+                        if (segment_bytes && (cb.modes & 0x80) && !turns_part1())
+                            return B200J2K_ERR_PATCHWELCOME;
                     } else {
                         while (pass_bound <= segment_passes) { nb++; pass_bound += pass_bound; }
                         segment_bytes = (unsigned)bits(nb);
                         if (segment_bytes) {
-                            next_segment_passes = 2;
-                            cb.plhd = 0;
-                            cb.Lcup = segment_bytes;
+                            if (!(cb.modes & 0x80) ||
+                                (cb.lblock > 3 && segment_bytes > 1 && (segment_bytes >> (nb - 1)) == 0)) {
+                                next_segment_passes = 2;          /* the first HT cleanup pass */
+                                cb.plhd = 0;
+                                cb.Lcup = segment_bytes;
+                            } else {                              /* an original (Part-1) coding pass */
+                                if (!turns_part1())
+                                    return B200J2K_ERR_PATCHWELCOME;
+                                segment_passes = newpasses;
+                                while (pass_bound <= segment_passes) {
+                                    nb++;
+                                    pass_bound += pass_bound;
+                                    segment_bytes = (segment_bytes << 1) + (unsigned)bits(1);
+                                }
+                            }
                         } else {
                             segment_passes = newpasses;
-                            if (pass_bound <= segment_passes)
+                            if (pass_bound <= segment_passes) {
                                 for (;;) {
                                     nb++;
                                     pass_bound += pass_bound;
@@ -1291,8 +1309,16 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                                     if (pass_bound > segment_passes)
                                         break;
                                 }
+                                if (segment_bytes && (cb.modes & 0x80) && !turns_part1())
+                                    return B200J2K_ERR_PATCHWELCOME;
+                            }
                         }
                     }
+                } else if (!(cb.modes & 0x40)) {
+                    /* Part-1 block, style 0: one codeword segment, one length of lblock + floor(log2(passes))
+                     * bits per packet (jpeg2000dec.c:1364-1368) */
+                    segment_bytes = (unsigned)bits(cb.lblock + ilog2((unsigned)newpasses));
+                    segment_passes = newpasses;
                 } else {
                     segment_passes = cb.npasses % 3;
                     nb = 0;
@@ -1311,7 +1337,7 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                 cb.npasses = (uint8_t)(cb.npasses + segment_passes);
                 in.seg[in.nseg++] = segment_bytes & 0xFFFF;
                 newpasses -= segment_passes & 0xFF;
-                if (!cb.plhd) {
+                if ((cb.modes & 0x40) && !cb.plhd) {
                     while (newpasses > 0) {
                         segment_passes = newpasses > 1 ? next_segment_passes : 1;
                         next_segment_passes = 3 - next_segment_passes;
@@ -1622,7 +1648,9 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
         d.npasses = s.npasses;
         d.zbp = s.zbp;
         d.length = s.length;
-        if (d.flags & J2K_CBLK_MQ) {
+        if ((d.flags & J2K_CBLK_MQ) || (s.incl && !(s.modes & 0x40))) {
+            d.flags |= J2K_CBLK_MQ;                       /* also the Part-1 blocks of a MIXED set */
+            d.Lref = d.pad;
             /* cblk->nonzerobits = expn + guard bits - 1 - (zero bit-planes - ROI shift of component 0)
              * (jpeg2000dec.c:1186-1194); Lref keeps the band orientation set with the geometry */
             d.Lcup = s.nzb;

@@ -65,6 +65,7 @@ struct CblkState {
     uint8_t zbp;
     uint8_t ncontrib;
     uint8_t nzb;             /* cblk->nonzerobits as computed at first inclusion (jpeg2000dec.c:1186-1194) */
+    uint8_t modes;           /* cblk->modes: SPcod copy (:1177), bit 6 cleared once a MIXED block turns out to be Part-1 */
     uint32_t Lcup, Lref, length;
     uint32_t data_off;
 };

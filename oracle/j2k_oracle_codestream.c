@@ -35,6 +35,7 @@ typedef struct TagNode { int val, vis; struct TagNode *parent; } TagNode;
 typedef struct Cblk {
     int x0, x1, y0, y1;          /* plane coordinates relative to band origin, Mallat offset included */
     int npasses, zbp, incl, lblock, plhd;
+    int modes;                   /* cblk->modes: SPcod copy; bit 6 cleared once a MIXED block turns out to be a Part-1 block */
     int Lcup, Lref;
     uint8_t *data;
     int length, cap;
@@ -739,9 +740,11 @@ static int parse_headers(Dec *d)
             uint32_t psot = rd32(seg + 2);
             int tpsot = seg[6];
             int64_t left = d->end - (seg + 8);
+            /* get_sot measures against "bytes left - 2 + n + 2" AFTER it has read the 8 bytes (:845-850): a
+             * tile-part has to end two bytes (the EOC marker) before the end of the packet */
             if (!psot)
-                psot = (uint32_t)(left + len + 2);
-            if ((int64_t)psot > left + len + 2)
+                psot = (uint32_t)(left + len);
+            if ((int64_t)psot > left + len)
                 return ORACLE_ERR_INVALID;
             if (tpsot >= 32)
                 return ORACLE_ERR_PATCH;
@@ -1096,7 +1099,9 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
             Cblk *cb = &pr->cb[k];
             int incl;
             if (!cb->incl) {
-                cb->plhd = 1;
+                cb->modes = cs->cblk_style;               /* :1177-1179 */
+                if (cb->modes >= 0x40)
+                    cb->plhd = 1;
                 if (layno > 0)
                     tagtree_decode(d, pr->incl + k, 1);
                 incl = tagtree_decode(d, pr->incl + k, layno + 1) == layno;
@@ -1139,19 +1144,12 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
 
             int segment_passes, next_segment_passes = 0, bits;
             unsigned segment_bytes = 0;
-            if (!(cs->cblk_style & 0x40)) {
-                /* Part-1 block: with neither restart nor bypass there is one codeword segment and one length
-                 * of lblock + floor(log2(passes)) bits per packet (:1364-1368); the others are not restated */
-                if (cs->cblk_style & (0x01 | 0x04)) {
-                    ret = ORACLE_ERR_PATCH;
-                    goto fail;
-                }
-                segment_bytes = (unsigned)hb_bits(d, cb->lblock + ilog2(newpasses));
-                cb->npasses += newpasses;
-                in->seg[in->nseg++] = (int)segment_bytes;
-                continue;
-            }
-            if (cb->plhd) {                               /* :1256-1340, non-MIXED */
+            /* a MIXED block (SPcod bit 7) that the length rules below unmask as a Part-1 block: HT bit off for good
+             * (:1271-1274, :1303-1305, :1331-1333).  Part-1 blocks of any style but 0 are not restated. */
+#define TURNS_PART1(cb) do { \
+                if (cs->cblk_style & 0x3F) { ret = ORACLE_ERR_PATCH; goto fail; } \
+                (cb)->plhd = 0; (cb)->modes &= ~0x40; } while (0)
+            if (cb->plhd) {                               /* :1256-1340 */
                 int href = (cb->npasses + newpasses - 1) % 3;
                 segment_passes = newpasses - href;
                 int pass_bound = 2;
@@ -1160,16 +1158,29 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
                     segment_passes = newpasses;
                     while (pass_bound <= segment_passes) { bits++; pass_bound += pass_bound; }
                     segment_bytes = hb_bits(d, bits);
+                    if (segment_bytes && (cb->modes & 0x80))
+                        TURNS_PART1(cb);
                 } else {
                     while (pass_bound <= segment_passes) { bits++; pass_bound += pass_bound; }
                     segment_bytes = hb_bits(d, bits);
                     if (segment_bytes) {
-                        next_segment_passes = 2;
-                        cb->plhd = 0;
-                        cb->Lcup = segment_bytes;
+                        if (!(cb->modes & 0x80) ||
+                            (cb->lblock > 3 && segment_bytes > 1 && (segment_bytes >> (bits - 1)) == 0)) {
+                            next_segment_passes = 2;      /* the first HT cleanup pass */
+                            cb->plhd = 0;
+                            cb->Lcup = segment_bytes;
+                        } else {                          /* an original (Part-1) coding pass */
+                            TURNS_PART1(cb);
+                            segment_passes = newpasses;
+                            while (pass_bound <= segment_passes) {
+                                bits++;
+                                pass_bound += pass_bound;
+                                segment_bytes = (segment_bytes << 1) + hb_bits(d, 1);
+                            }
+                        }
                     } else {
                         segment_passes = newpasses;
-                        if (pass_bound <= segment_passes)
+                        if (pass_bound <= segment_passes) {
                             for (;;) {
                                 bits++;
                                 pass_bound += pass_bound;
@@ -1177,8 +1188,20 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
                                 if (pass_bound > segment_passes)
                                     break;
                             }
+                            if (segment_bytes && (cb->modes & 0x80))
+                                TURNS_PART1(cb);
+                        }
                     }
                 }
+            } else if (!(cb->modes & 0x40)) {
+                /* Part-1 block: with neither restart nor bypass there is one codeword segment and one length
+                 * of lblock + floor(log2(passes)) bits per packet (:1364-1368); the others are not restated */
+                if (cs->cblk_style & (0x01 | 0x04)) {
+                    ret = ORACLE_ERR_PATCH;
+                    goto fail;
+                }
+                segment_bytes = (unsigned)hb_bits(d, cb->lblock + ilog2(newpasses));
+                segment_passes = newpasses;
             } else {                                      /* :1341-1362 later contributions of an HT block */
                 segment_passes = cb->npasses % 3;
                 bits = 0;
@@ -1197,7 +1220,7 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
             cb->npasses = (cb->npasses + segment_passes) & 0xFF;
             in->seg[in->nseg++] = segment_bytes;
             newpasses -= segment_passes & 0xFF;
-            if (!cb->plhd) {                              /* :1404-1418 */
+            if ((cb->modes & 0x40) && !cb->plhd) {        /* :1404-1418 */
                 while (newpasses > 0) {
                     segment_passes = newpasses > 1 ? next_segment_passes : 1;
                     next_segment_passes = 3 - next_segment_passes;
@@ -1520,8 +1543,11 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
                         Cblk *cb = &pr->cb[k];
                         const int bw = cb->x1 - cb->x0, bh = cb->y1 - cb->y0;
                         static const uint8_t none[8];
-                        if (!(cs->cblk_style & 0x40)) {   /* Part-1 block (decode_cblk, :2270-2275) */
-                            if (cs->cblk_style) {         /* reset / causal / segmentation symbols: not restated */
+                        if (!(cb->modes & 0x40)) {        /* Part-1 block (decode_cblk, :2264-2275); cb->modes is 0 for a
+                                                           * block no packet ever reached, as in the reference */
+                            if (!cb->length)
+                                continue;
+                            if (cs->cblk_style & 0x3F) {  /* reset / causal / segmentation symbols: not restated */
                                 free(t1);
                                 return ORACLE_ERR_PATCH;
                             }

@@ -57,7 +57,7 @@ def test_golden_frames_packed():
     assert n >= 25
 
 
-@pytest.mark.parametrize("name", ["frames_part1.npz", "frames_tiles.npz"])
+@pytest.mark.parametrize("name", ["frames_part1.npz", "frames_tiles.npz", "frames_htsets.npz"])
 def test_golden_frames_part1_and_tiles(name):
     """Part-1 (EBCOT / MQ) streams from OpenJPEG, plain and damaged; several tile-parts per tile, tiles with their own
     COD / QCD / POC, damaged tile-header markers: reference verdicts + pixels"""

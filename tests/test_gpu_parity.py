@@ -12,7 +12,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import (LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+from test_oracle_vs_ref import (HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
                                 TILE_STYLES, packed_stream, part1_stream, poc_stream, tile_part_stream,
                                 tile_style_marker_cases, tile_style_stream,
                                 subsampled_stream)
@@ -224,7 +224,7 @@ def test_golden_frames_wide():
     assert n >= 35
 
 
-@pytest.mark.parametrize("name", ["frames_packed.npz", "frames_part1.npz", "frames_tiles.npz"])
+@pytest.mark.parametrize("name", ["frames_packed.npz", "frames_part1.npz", "frames_tiles.npz", "frames_htsets.npz"])
 def test_golden_frames_packed_and_part1(name):
     """Reference-generated vectors: packed packet headers (PPT / PPM), damaged PPT / PPM markers, missing tiles;
     Part-1 (EBCOT / MQ) streams from OpenJPEG, plain and damaged."""
@@ -419,6 +419,35 @@ def test_tile_style_marker_cases_match_oracle(dec):
             with pytest.raises(fb.DecodeError) as e:
                 dec.decode(bad)
             assert e.value.code == r
+
+
+@pytest.mark.parametrize("t", HT_SETS, ids=HT_SET_IDS)
+def test_ht_set_frames_vs_oracle(t, dec, dec_bitexact):
+    """HTDECLARED / MIXED streams: HT blocks on the HT kernels, Part-1 blocks of the same frame on mq_block_kernel."""
+    cs, planes = ht_set_stream(t)
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r, oinfo, want = oracle_decode(cs, bitexact)
+        d = dec_bitexact if bitexact else dec
+        if r == 0:
+            info, got = d.decode(cs)
+            assert np.array_equal(got, want)              # the float 9/7 path is bit-identical as well
+        else:
+            with pytest.raises(fb.DecodeError) as e:
+                d.decode(cs)
+            assert e.value.code == r
+
+
+def test_ht_set_damaged_frames_match_oracle(dec):
+    n_ok = 0
+    for i, bad in enumerate(ht_set_damaged_streams()):
+        r, _, want = oracle_decode(bad, 0)
+        if r == 0:
+            assert np.array_equal(dec.decode(bad)[1], want), i
+            n_ok += 1
+        else:
+            with pytest.raises(fb.DecodeError):
+                dec.decode(bad)
+    assert n_ok >= 20
 
 
 @pytest.mark.parametrize("t", TILE_PARTS, ids=lambda t: f"mode{t['mode']}-tp{t['tp']}-il{int(t['il'])}")

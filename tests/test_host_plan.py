@@ -11,7 +11,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import ht_block, mq_block, oracle, oracle_decode
-from test_oracle_vs_ref import (LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+from test_oracle_vs_ref import (psot_bound_cases, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
                                 TILE_STYLES, part1_stream, tile_part_stream, tile_style_marker_cases, tile_style_stream,
                                 packed_marker_cases, packed_stream, poc_marker_cases, poc_stream,
                                 subsampled_stream)
@@ -323,6 +323,42 @@ def test_geometry_cache_sees_tile_header_changes():
         r, _, opic = oracle_decode(cs)
         _, pic = picture_from_plan(cs, 0)
         assert r == 0 and np.array_equal(pic, opic)
+
+
+def test_psot_bound_matches_oracle():
+    for i, c in enumerate(psot_bound_cases()):
+        r, _, opic = oracle_decode(c)
+        try:
+            _, pic = picture_from_plan(c, 0)
+            assert r == 0 and np.array_equal(pic, opic), i
+        except fb.DecodeError as e:
+            assert e.code == r, i
+
+
+@pytest.mark.parametrize("t", HT_SETS, ids=HT_SET_IDS)
+def test_plan_of_ht_set_streams(t):
+    """HTDECLARED / MIXED streams: which block coder a block belongs to is decided per block in tier 2."""
+    cs, _ = ht_set_stream(t)
+    for bitexact in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
+        r, oinfo, opic = oracle_decode(cs, bitexact)
+        try:
+            info, pic = picture_from_plan(cs, fb.FLAG_BITEXACT if bitexact else 0)
+            assert r == 0 and np.array_equal(pic, opic)
+        except fb.DecodeError as e:
+            assert r < 0 and e.code == r
+
+
+def test_plan_of_damaged_ht_set_streams():
+    n_ok = 0
+    for i, bad in enumerate(ht_set_damaged_streams()):
+        r, _, opic = oracle_decode(bad)
+        try:
+            _, pic = picture_from_plan(bad, 0)
+            assert r == 0 and np.array_equal(pic, opic), i
+            n_ok += 1
+        except fb.DecodeError as e:
+            assert r < 0 and e.code < 0, i
+    assert n_ok >= 20
 
 
 def test_packed_header_marker_validation_matches_oracle():

@@ -72,6 +72,14 @@ typedef struct J2kGenParams {
                                   * 1 another progression order (COD), 2 one decomposition level less (COD + QCD),
                                   * 4 narrower code-blocks (COD), 8 one more guard bit / a coarser step (QCD),
                                   * 16 a POC marker segment with two entries (only without a main-header POC) */
+    int32_t ht_set;              /* Ccap15 bits 14-15 / SPcod bits 6-7 (jpeg2000dec.c:443-459, :1060, :1256-1340):
+                                  * 0 HTONLY, style 0x40.  1 HTDECLARED (Ccap15 0x4000), style 0x40.
+                                  * 3 MIXED (0xC000), style 0xC0, cleanup lengths written the way a MIXED stream must
+                                  *   (Lblock > 3, the top bit of the length field 0) so every block reads as HT.
+                                  * 4 MIXED, style 0xC0, lengths written as for HTONLY: the reference then takes the
+                                  *   blocks whose field has Lblock == 3 or its top bit set for Part-1 (MQ) blocks and
+                                  *   decodes their HT bytes with the MQ decoder (parity material, not a picture).
+                                  * 5 like 4 with Ccap15 saying HTONLY (the reference does not cross-check that) */
 } J2kGenParams;
 
 /* ------------------------------------------------------------------------------------------------ */
@@ -1031,6 +1039,8 @@ static int write_packet(Buf *out, const J2kGenParams *P, ResLevel *rl, int precn
                 int need = bitlen(cb->Lcup) - wide;
                 if (npc > 1)
                     need = imax(need, bitlen(cb->Lref) - (npc == 3));
+                if (P->ht_set == 3)       /* MIXED: an HT cleanup length needs Lblock > 3 and a 0 on top (:1293-1298) */
+                    need = imax(imax(need, bitlen(cb->Lcup) - wide + 1), 4);
                 while (cb->lblock < need) { bw_put(&w, 1, 1); cb->lblock++; }
                 bw_put(&w, 0, 1);
                 bw_put(&w, cb->Lcup, cb->lblock + wide);
@@ -1077,7 +1087,7 @@ static void put_cod(Buf *out, const J2kGenParams *P, int C)
     buf_put(out, (P->use_precincts ? 1 : 0) | (P->sop ? 2 : 0) | (P->eph ? 4 : 0));
     buf_put(out, P->prog); buf_put16(out, P->layers == 2 ? 2 : 1); buf_put(out, (P->mct && C >= 3) ? 1 : 0);
     buf_put(out, L); buf_put(out, P->cbw_log2 - 2); buf_put(out, P->cbh_log2 - 2);
-    buf_put(out, 0x40 | (P->vsc ? 0x08 : 0));
+    buf_put(out, (P->ht_set >= 3 ? 0xC0 : 0x40) | (P->vsc ? 0x08 : 0));
     buf_put(out, P->reversible ? 1 : 0);
     if (P->use_precincts)
         for (int r = 0; r <= L; r++) buf_put(out, P->prec_exps[r]);
@@ -1155,7 +1165,8 @@ int64_t j2kgen_encode(const int32_t *const *planes, J2kGenParams *P, uint8_t *ou
     {
         int magb_bits = 0;   /* the reference only range-checks MAGB (jpeg2000dec.c:473-486) */
         buf_put16(&out, 0xFF50); buf_put16(&out, 8); buf_put32(&out, 0x00020000);
-        buf_put16(&out, (P->reversible ? 0 : 0x0020) | ((P->packed_headers == 1 || P->tile_var) ? 0x0800 : 0) | magb_bits);
+        buf_put16(&out, (P->reversible ? 0 : 0x0020) | ((P->packed_headers == 1 || P->tile_var) ? 0x0800 : 0) | magb_bits |
+                        (P->ht_set == 1 ? 0x4000 : P->ht_set == 3 || P->ht_set == 4 ? 0xC000 : 0));
     }
     const int NLAY = P->layers == 2 ? 2 : 1;
     put_cod(&out, P, C);

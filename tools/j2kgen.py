@@ -33,6 +33,7 @@ class _Params(ctypes.Structure):
         ("npoc", ctypes.c_int32), ("poc", (ctypes.c_int32 * 6) * 8), ("poc_split", ctypes.c_int32),
         ("packed_headers", ctypes.c_int32), ("ppx_chunk", ctypes.c_int32),
         ("tp_packets", ctypes.c_int32), ("tp_interleave", ctypes.c_int32), ("tile_var", ctypes.c_int32),
+        ("ht_set", ctypes.c_int32),
     ]
 
 
@@ -84,6 +85,8 @@ class EncParams:
     tp_interleave: bool = False   # write part k of every tile before part k + 1 of any
     tile_var: int = 0             # odd tiles coded differently (COD / QCD / POC in their tile-part header): bit 1 progression,
     #                               2 one level less, 4 narrower code-blocks, 8 guard bit / step, 16 tile POC
+    ht_set: int = 0               # 0 HTONLY, 1 HTDECLARED, 3 MIXED (all blocks read as HT), 4 MIXED with HTONLY-style lengths
+    #                               (some blocks read as Part-1 blocks: parity material), 5 like 4 under an HTONLY Ccap15
     stats: dict = field(default_factory=dict)
 
 
@@ -124,6 +127,7 @@ def encode(planes, bitdepth: int, p: EncParams) -> bytes:
         P.packed_headers, P.ppx_chunk = p.packed_headers, p.ppx_chunk
         P.tp_packets, P.tp_interleave = p.tp_packets, int(p.tp_interleave)
         P.tile_var = p.tile_var
+        P.ht_set = p.ht_set
         cap = int(w * h * len(planes) * 4 + (1 << 20))
         out = np.empty(cap, np.uint8)
         ptrs = (ctypes.c_void_p * len(planes))(*[a.ctypes.data for a in planes])
