@@ -493,7 +493,7 @@ def plan(pkt, flags: int = 0):
     _check(lib().b200j2k_plan_build(addr, n, flags, ctypes.byref(info)), "plan_build")
     out = {"info": info}
     for which, name, dt in ((0, "cblk", CBLK_DTYPE), (1, "bands", BAND_DTYPE), (2, "tcs", TC_DTYPE),
-                            (3, "groups", GROUP_DTYPE), (4, "extra", np.dtype("u1"))):
+                            (3, "groups", GROUP_DTYPE), (4, "extra", np.dtype("u1")), (5, "palette", np.dtype("<u4"))):
         cnt, es = ctypes.c_int64(), ctypes.c_int32()
         p = lib().b200j2k_plan_table(which, ctypes.byref(cnt), ctypes.byref(es))
         assert es.value == dt.itemsize, (name, es.value, dt.itemsize)

@@ -316,6 +316,10 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     s.off_groups = off; off = align_up(off + p.groups.size() * sizeof(PackGroup), 256);
     s.off_order = off;  off = align_up(off + ncb * sizeof(uint32_t), 256);
     s.off_scr = off;    off = align_up(off + ncb * sizeof(uint32_t), 256);
+    const bool pal8 = p.nplanes == 2 && !strcmp(p.hdr.pix_name, "pal8");
+    const size_t off_pal = off;
+    if (pal8)                                             /* the palette travels with the tables */
+        off = align_up(off + sizeof(p.hdr.palette), 256);
     s.off_bytes = off;
     const size_t tail = p.extra.size() + 64;              /* gathered bytes + slack, placed behind the codestream */
     const size_t off_tail = s.off_bytes + (size_t)size;
@@ -332,6 +336,8 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     memcpy(h + s.off_groups, p.groups.data(), p.groups.size() * sizeof(PackGroup));
     memcpy(h + s.off_order, order.data(), ncb * sizeof(uint32_t));
     memcpy(h + s.off_scr, s.ht.scr_off.data(), ncb * sizeof(uint32_t));
+    if (pal8)
+        memcpy(h + off_pal, p.hdr.palette, sizeof(p.hdr.palette));
     uint8_t *htail = direct_in ? h + s.off_bytes : h + off_tail;
     if (!direct_in)
         memcpy(h + s.off_bytes, pkt, (size_t)size);
@@ -359,6 +365,10 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     } else {
         e = cudaMemcpyAsync(dblob, h, off_tail + tail, cudaMemcpyHostToDevice, s.stream);
     }
+    /* PAL8: plane 1 of the picture is the palette (AVFrame.data[1], jpeg2000dec.c:2900-2901); no kernel writes it */
+    if (e == cudaSuccess && pal8)
+        e = cudaMemcpyAsync((uint8_t *)s.d_picture.p + p.plane_off[1], dblob + off_pal, sizeof(p.hdr.palette),
+                            cudaMemcpyDeviceToDevice, s.stream);
     if (e != cudaSuccess)
         return B200J2K_ERR_DEVICE;
     s.h2d_bytes = off_tail + tail;
@@ -416,7 +426,8 @@ int queue_output(Slot &s, uint8_t *const data[4], const int linesize[4])
     Parser &p = s.parser;
     bool direct = true;
     for (int i = 0; i < p.nplanes; i++) {
-        if (!data[i] || linesize[i] < p.plane_row_bytes[i])
+        if (!data[i] || (linesize[i] < p.plane_row_bytes[i] && p.plane_h[i] > 1))   /* a one-row plane (palette)
+                                                                                     * has no meaningful linesize */
             return B200J2K_ERR_EINVAL;
         direct = direct && is_dma_target(data[i]);
         s.dst[i] = data[i];
@@ -427,7 +438,7 @@ int queue_output(Slot &s, uint8_t *const data[4], const int linesize[4])
     if (direct) {
         for (int i = 0; i < p.nplanes; i++) {
             cudaError_t e;
-            if (linesize[i] == p.plane_row_bytes[i])     /* no row padding: one linear copy */
+            if (linesize[i] == p.plane_row_bytes[i] || p.plane_h[i] == 1)     /* no row padding: one linear copy */
                 e = cudaMemcpyAsync(data[i], pic + p.plane_off[i], (size_t)p.plane_row_bytes[i] * p.plane_h[i],
                                     cudaMemcpyDefault, s.stream);
             else
@@ -864,6 +875,7 @@ const void *b200j2k_plan_table(int which, int64_t *count, int32_t *elem_size)
     case 2: *count = (int64_t)g_plan->tcs.size(); *elem_size = sizeof(TileCompDesc); return g_plan->tcs.data();
     case 3: *count = (int64_t)g_plan->groups.size(); *elem_size = sizeof(PackGroup); return g_plan->groups.data();
     case 4: *count = (int64_t)g_plan->extra.size(); *elem_size = 1; return g_plan->extra.data();
+    case 5: *count = 256; *elem_size = 4; return g_plan->hdr.palette;
     }
     return nullptr;
 }

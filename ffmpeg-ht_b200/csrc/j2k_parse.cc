@@ -115,7 +115,7 @@ struct PixDesc {
 #define P8 B200J2K_PIX_PLANAR8
 #define P16 B200J2K_PIX_PLANAR16
 const PixDesc RGB_FMTS[] = {
-    { "pal8", B200J2K_PIX_NONE, 1, 8, 0, 0, 1 },    /* palettised output is not served: AVERROR_PATCHWELCOME */
+    { "pal8", B200J2K_PIX_GRAY8, 1, 8, 0, 0, 1 },   /* index plane laid out like gray8 + the palette as plane 1 */
     { "rgb24", B200J2K_PIX_RGB24, 3, 8, 0, 0, 0 }, { "rgba", B200J2K_PIX_RGBA, 4, 8, 0, 0, 0 },
     { "rgb48le", B200J2K_PIX_RGB48, 3, 16, 0, 0, 0 }, { "rgba64le", B200J2K_PIX_RGBA64, 4, 16, 0, 0, 0 },
 };
@@ -222,8 +222,8 @@ int choose_pix(Header &h, const char **name)
 
 /* ---- JP2 wrapper: jp2_find_codestream (jpeg2000dec.c:2658-2804) --------------------------------------
  * Walks the boxes up to the contiguous codestream box; from the JP2 header box it takes the enumerated
- * colour space ('colr' method 1), the presence of a valid palette ('pclr'; the reference never delivers
- * PAL8 for a one-component stream, the flag only steers the format choice) and the channel definitions
+ * colour space ('colr' method 1), a valid palette ('pclr': steers the format choice and, for a one-component
+ * stream of at most 8 bits outside the greyscale list, makes the output PAL8) and the channel definitions
  * ('cdef': component -> plane for planar output).  'res ' (sample aspect ratio) is not published.
  * Returns 1 with *pos at the codestream, 0 when there is none, < 0 on a malformed box. */
 struct Cursor {
@@ -291,8 +291,21 @@ int jp2_find_codestream(Cursor &g, Header &h)
                         bytes += ((depth[i] + 7) >> 3) * count;
                     }
                     if (!(count > 256 || channels != 3 || depth[0] > 16 || depth[1] > 16 || depth[2] > 16 ||
-                          (int64_t)atom2_size < bytes))
+                          (int64_t)atom2_size < bytes)) {
                         h.pal8 = 1;
+                        for (int i = 0; i < count; i++) {                      /* :2731-2752, uint32 arithmetic */
+                            uint32_t v[3];
+                            for (int k = 0; k < 3; k++) {
+                                if (depth[k] <= 8) {
+                                    v[k] = g.u8() << (8 - depth[k]);
+                                    v[k] |= v[k] >> depth[k];
+                                } else {
+                                    v[k] = g.be16() >> (depth[k] - 8);
+                                }
+                            }
+                            h.palette[i] = 0xffu << 24 | v[0] << 16 | v[1] << 8 | v[2];
+                        }
+                    }
                 } else if (atom2 == 0x63646566u && atom2_size >= 2) {          /* 'cdef' */
                     for (int n = (int)g.be16(); n > 0; n--) {
                         const int cn = (int)g.be16();
@@ -781,6 +794,15 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
         plane_row_bytes[0] = h.out_w * h.ncomp * bps;
         plane_off[0] = 0;
         picture_bytes = (uint64_t)plane_row_bytes[0] * h.out_h;
+        if (h.pix_name && !strcmp(h.pix_name, "pal8")) {
+            /* AVFrame.data[1] of a PAL8 frame: 256 native-endian 0xAARRGGBB words (jpeg2000dec.c:2900-2901) */
+            nplanes = 2;
+            plane_w[1] = 256;
+            plane_h[1] = 1;
+            plane_row_bytes[1] = 1024;
+            plane_off[1] = picture_bytes;
+            picture_bytes = plane_off[1] + 1024;
+        }
     } else {
         /* planes of the chosen AVPixelFormat: chroma planes 1 and 2 shrink by its log2_chroma_w/h */
         nplanes = h.ncomp;

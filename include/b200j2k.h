@@ -50,6 +50,9 @@ enum b200j2k_pix_fmt {
     B200J2K_PIX_RGB24, B200J2K_PIX_RGB48, B200J2K_PIX_RGBA, B200J2K_PIX_RGBA64,
     B200J2K_PIX_PLANAR8, B200J2K_PIX_PLANAR16
 };
+/* Palettised JP2 files (one component of at most 8 bits + a 'pclr' box, jpeg2000dec.c:2711-2752): av_pix_fmt_name is
+ * "pal8", pix_fmt is B200J2K_PIX_GRAY8 (the index plane) and nplanes is 2 -- plane 1 is AVFrame.data[1] of a PAL8
+ * frame: one row of 256 native-endian 0xAARRGGBB words (plane_row_bytes[1] = 1024; its linesize is not looked at). */
 
 /* What jpeg2000_decode_frame() publishes on AVCodecContext / AVFrame before the pixels exist
  * (jpeg2000dec.c:213, :326, :354-363, :420, :546). */
@@ -155,7 +158,7 @@ int b200j2k_host_unregister(void *p);
 
 /* Introspection of the host-side plan (CPU only, no device needed): lets tests check the parser's flat
  * tables.  which: 0 CblkDesc, 1 BandDesc, 2 TileCompDesc, 3 PackGroup (ffmpeg-ht_b200/csrc/j2k_plan.h),
- * 4 gathered bytes of multi-contribution blocks.  Pointers stay valid until the next plan_build on the
+ * 4 gathered bytes of multi-contribution blocks, 5 the palette of a PAL8 frame (256 words).  Pointers stay valid until the next plan_build on the
  * calling thread. */
 int b200j2k_plan_build(const uint8_t *pkt, int64_t pkt_size, int flags, b200j2k_frame_info *info);
 const void *b200j2k_plan_table(int which, int64_t *count, int32_t *elem_size);

@@ -116,6 +116,7 @@ typedef struct Dec {
     Tile *tile;
     int pix, out_w, out_h;
     int colour_space, pal8, cdef[4];                /* JP2 wrapper state (jp2_find_codestream) */
+    uint32_t palette[256];                          /* s->palette (jpeg2000dec.h:94): 0xAARRGGBB per entry */
     int npoc;                                       /* main-header POC entries (get_poc) */
     struct { int RS, CS, LYE, RE, CE, P; } poc[32];
     int chroma_lw, chroma_lh;                       /* log2_chroma_w/h of the chosen AVPixelFormat */
@@ -295,7 +296,7 @@ typedef struct PixDesc {
 #define P8 ORACLE_PIX_PLANAR8
 #define P16 ORACLE_PIX_PLANAR16
 static const PixDesc RGB_FMTS[] = {
-    { "pal8", 0, 1, 8, 0, 0, 1 },                   /* palettised output: outside the path (PATCHWELCOME) */
+    { "pal8", ORACLE_PIX_GRAY8, 1, 8, 0, 0, 1 },    /* index plane written like gray8 (write_frame_8), then the palette */
     { "rgb24", ORACLE_PIX_RGB24, 3, 8, 0, 0, 0 }, { "rgba", ORACLE_PIX_RGBA, 4, 8, 0, 0, 0 },
     { "rgb48le", ORACLE_PIX_RGB48, 3, 16, 0, 0, 0 }, { "rgba64le", ORACLE_PIX_RGBA64, 4, 16, 0, 0, 0 },
 };
@@ -461,8 +462,21 @@ static int jp2_find_codestream(Dec *d, int64_t *ppos)
                         bytes += ((depth[i] + 7) >> 3) * count;
                     }
                     if (!(count > 256 || channels != 3 || depth[0] > 16 || depth[1] > 16 || depth[2] > 16 ||
-                          (int64_t)atom2_size < bytes))
+                          (int64_t)atom2_size < bytes)) {
                         d->pal8 = 1;
+                        for (int i = 0; i < count; i++) {                      /* :2731-2752, uint32 arithmetic */
+                            uint32_t v[3];
+                            for (int k = 0; k < 3; k++) {
+                                if (depth[k] <= 8) {
+                                    v[k] = jp2_be(d, &pos, 1) << (8 - depth[k]);
+                                    v[k] |= v[k] >> depth[k];
+                                } else {
+                                    v[k] = jp2_be(d, &pos, 2) >> (depth[k] - 8);
+                                }
+                            }
+                            d->palette[i] = 0xffu << 24 | v[0] << 16 | v[1] << 8 | v[2];
+                        }
+                    }
                 } else if (atom2 == 0x63646566u && atom2_size >= 2) {          /* cdef */
                     for (int n = (int)jp2_be(d, &pos, 2); n > 0; n--) {
                         const int cn = (int)jp2_be(d, &pos, 2);
@@ -1671,11 +1685,16 @@ int oracle_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, u
                 pos += (int64_t)strides[c] * ph;
             }
         }
+        const int64_t pal_at = pos;
+        if (!strcmp(g_pix_name, "pal8"))            /* data[1] of a PAL8 frame: 256 native-endian words (:2900-2901) */
+            pos += 1024;
         if (pos > cap) {
             ret = ORACLE_ERR_NOMEM;
             goto end;
         }
         memset(out, 0, (size_t)pos);
+        if (pos > pal_at)
+            memcpy(out + pal_at, d.palette, 1024);
         for (int x = 0; x < d.ncomp; x++)           /* default channel definitions (:2883-2892) */
             if (d.cdef[x] < 0) {
                 for (x = 0; x < d.ncomp; x++)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Generates tests/golden/frames_htsets.npz with the REFERENCE (oracle/_ref/libj2kref.so built from /root/reference):
 HTDECLARED and MIXED streams (blocks of one frame on both block coders), MIXED streams with random byte damage, and
-the Psot bound cases -- reference verdict and a SHA-1 digest of its picture.  Same layout as frames_tiles.npz
+the Psot bound cases, palettised JP2 files (PAL8: index plane + palette) -- reference verdict and a SHA-1 digest of its picture.  Same layout as frames_tiles.npz
 (key = name|flags).  Run where the reference is mounted:  python tests/golden/make_htsets_golden.py"""
 import hashlib
 import sys
@@ -12,7 +12,8 @@ import numpy as np
 ROOT = Path(__file__).resolve().parents[2]
 sys.path[:0] = [str(ROOT), str(ROOT / "tools"), str(ROOT / "tests")]
 from helpers import ref_decode  # noqa: E402
-from test_oracle_vs_ref import HT_SETS, ht_set_damaged_streams, ht_set_stream, psot_bound_cases  # noqa: E402
+from test_oracle_vs_ref import (HT_SETS, PAL8_CASES, ht_set_damaged_streams, ht_set_stream, pal8_file,  # noqa: E402
+                                psot_bound_cases)
 
 items = {}
 for i, t in enumerate(HT_SETS):
@@ -26,6 +27,8 @@ for i, bad in enumerate(ht_set_damaged_streams()):
     items[f"ht_set_damaged{i:02d}|0"] = bad
 for i, c in enumerate(psot_bound_cases()):
     items[f"psot{i}|0"] = c
+for i, (bd, csp, pal) in enumerate(PAL8_CASES):
+    items[f"pal8_{i}|0"] = pal8_file(bd, csp, pal, tile=(64, 32))[0]
 pack = {}
 for k, data in items.items():
     r, info, out, pix = ref_decode(data, int(k.split("|")[1]))

@@ -12,7 +12,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import (HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+from test_oracle_vs_ref import (PAL8_CASES, pal8_file, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
                                 TILE_STYLES, packed_stream, part1_stream, poc_stream, tile_part_stream,
                                 tile_style_marker_cases, tile_style_stream,
                                 subsampled_stream)
@@ -510,6 +510,18 @@ def test_subsampled_and_jp2_frames_vs_oracle(name, subs, bd, dec, dec_bitexact):
                 info, got = (dec_bitexact if bitexact else dec).decode(data)
                 assert (info.width, info.height, info.pix_name) == (oinfo[0], oinfo[1], oracle_pix_name())
                 assert np.array_equal(got, want), (name, w, h, bitexact)
+
+
+@pytest.mark.parametrize("bd,csp,pal", PAL8_CASES)
+def test_pal8_files_vs_oracle(bd, csp, pal, dec):
+    """Palettised JP2 files: index plane from the kernels, palette (plane 1) uploaded with the tables."""
+    from helpers import oracle_pix_name
+    for kw in (dict(), dict(tile=(64, 32))):
+        data, _ = pal8_file(bd, csp, pal, **kw)
+        r, oinfo, want = oracle_decode(data, 0)
+        info, got = dec.decode(data)
+        assert r == 0 and (info.width, info.height, info.pix_name) == (oinfo[0], oinfo[1], oracle_pix_name())
+        assert np.array_equal(got, want)
 
 
 def test_jp2_colour_spaces_vs_oracle(dec):

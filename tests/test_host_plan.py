@@ -10,8 +10,8 @@ import pytest
 
 import ffmpeg_ht_b200 as fb
 import j2kgen
-from helpers import ht_block, mq_block, oracle, oracle_decode
-from test_oracle_vs_ref import (psot_bound_cases, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+from helpers import ht_block, mq_block, oracle, oracle_decode, oracle_pix_name
+from test_oracle_vs_ref import (PAL8_CASES, pal8_file, psot_bound_cases, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
                                 TILE_STYLES, part1_stream, tile_part_stream, tile_style_marker_cases, tile_style_stream,
                                 packed_marker_cases, packed_stream, poc_marker_cases, poc_stream,
                                 subsampled_stream)
@@ -68,6 +68,8 @@ def picture_from_plan(cs: bytes, flags: int):
             assert oracle().oracle_idwt(int(tc["transform"]), border.ctypes.data, int(tc["nlevels"]), pl.ctypes.data) == 0
         planes.append(pl)
     pic = np.zeros(int(P["picture_bytes"]), np.uint8)
+    if info.pix_name == "pal8":                            # plane 1 = the palette, filled in by the host
+        pic[P["plane_off"][1]:] = P["palette"].view(np.uint8)
     rowb = [info.plane_row_bytes[i] for i in range(4)]
     for g in P["groups"]:
         tcs = [P["tcs"][int(g["tc"][c])] for c in range(int(g["ncomp"]))]
@@ -325,6 +327,18 @@ def test_geometry_cache_sees_tile_header_changes():
         assert r == 0 and np.array_equal(pic, opic)
 
 
+@pytest.mark.parametrize("bd,csp,pal", PAL8_CASES)
+def test_plan_of_pal8_files(bd, csp, pal):
+    """PAL8: plane 0 = indices (gray8 layout), plane 1 = one row of 256 palette words."""
+    for kw in (dict(), dict(tile=(64, 32))):
+        data, _ = pal8_file(bd, csp, pal, **kw)
+        r, oinfo, opic = oracle_decode(data)
+        info, pic = picture_from_plan(data, 0)
+        assert r == 0 and info.pix_name == oracle_pix_name() and np.array_equal(pic, opic)
+        if info.pix_name == "pal8":
+            assert info.nplanes == 2 and info.plane_row_bytes[1] == 1024 and info.plane_height[1] == 1
+
+
 def test_psot_bound_matches_oracle():
     for i, c in enumerate(psot_bound_cases()):
         r, _, opic = oracle_decode(c)
@@ -456,9 +470,6 @@ def test_jp2_wrapper_headers_match_reference():
                 mine = (0, i.width, i.height, i.pix_name)
             except fb.DecodeError as e:
                 mine = (e.code,)
-            if r == 0 and name == "pal8":
-                assert mine == (-1163346256,)         # palettised output: refused, never a wrong picture
-            else:
-                assert mine == ((r, info[0], info[1], name) if r == 0 else (r,)), (nc, bd, len(data))
+            assert mine == ((r, info[0], info[1], name) if r == 0 else (r,)), (nc, bd, len(data))
             n += 1
     assert n == 110

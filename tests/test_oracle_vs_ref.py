@@ -696,8 +696,8 @@ def test_subsampled_decode_bit_exact(name, subs, bd):
 
 def test_jp2_wrapped_decode_bit_exact():
     """JP2 / JPH files: the codestream behind the boxes, the colour specification's pixel-format list (planar
-    YUV for sYCC), channel definitions that remap components to planes, a palette that only steers the
-    format choice, the ten-box search limit -- oracle == reference in dimensions, AVPixelFormat and pixels."""
+    YUV for sYCC), channel definitions that remap components to planes, a palette (PAL8 for one component,
+    only steering the format choice otherwise), the ten-box search limit -- oracle == reference in dimensions, AVPixelFormat and pixels."""
     n = 0
     for nc, bd, sub in [(3, 8, None), (3, 12, None), (1, 8, None), (1, 16, None), (2, 8, None), (4, 8, None), (3, 10, None),
                         (4, 16, None), (3, 8, "420"), (3, 10, "422")]:
@@ -712,15 +712,39 @@ def test_jp2_wrapped_decode_bit_exact():
         for data in variants:
             r1, info1, out1, name = ref_decode(data)
             r2, info2, out2 = oracle_decode(data)
-            if r1 == 0 and name == "pal8":
-                assert r2 == -1163346256            # palettised output is outside the path: refused
-                continue
             assert r1 == r2, (nc, bd, r1, r2)
             if r1 == 0:
                 assert info1[:2] == info2[:2] and oracle_pix_name() == name
                 assert np.array_equal(out1, out2), (nc, bd, name)
             n += 1
     assert n > 80
+
+
+# palettised JP2 files: (bit depth, colour space, (entries, palette depth))
+PAL8_CASES = [(8, 16, (200, 8)), (8, None, (256, 12)), (6, 16, (7, 4)), (8, 99, (256, 16)), (5, 16, (32, 1)), (8, 17, (16, 8)),
+              (8, 16, (257, 8)), (1, 16, (2, 8)), (8, 18, (100, 9))]
+
+
+def pal8_file(bd, csp, pal, w=96, h=64, **kw):
+    planes = j2kgen.synth_image(w, h, 1, bd, seed=3)
+    cs = j2kgen.encode(planes, bd, j2kgen.EncParams(levels=2, cblk=(32, 32), mct=False, **kw))
+    return j2kgen.wrap_jp2(cs, w, h, 1, bd, colour_space=csp, palette=pal), planes
+
+
+@pytest.mark.parametrize("bd,csp,pal", PAL8_CASES)
+def test_pal8_files_match_reference(bd, csp, pal):
+    """One component of at most 8 bits + a valid 'pclr' box outside the greyscale list: AV_PIX_FMT_PAL8 -- the index
+    plane written like gray8 and 256 palette words in data[1] (jpeg2000dec.c:2711-2752, :2900-2901)."""
+    for kw in (dict(), dict(tile=(64, 32))):
+        data, planes = pal8_file(bd, csp, pal, **kw)
+        r1, info1, out1, name = ref_decode(data)
+        r2, info2, out2 = oracle_decode(data)
+        assert r1 == 0 and r2 == 0 and info1[:2] == info2[:2] and oracle_pix_name() == name
+        assert np.array_equal(out1, out2)
+        if name == "pal8":
+            assert out1.size == 96 * 64 + 1024
+            assert np.array_equal(out1[:96 * 64].reshape(64, 96) >> (8 - bd), planes[0])
+    assert (name == "pal8") == (csp not in (17, 18) and pal[0] <= 256)      # grey and sYCC lists hold no PAL8
 
 
 def test_error_codes_match():
