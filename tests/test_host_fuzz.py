@@ -8,7 +8,8 @@ import pytest
 
 import j2kgen
 from helpers import ROOT
-from test_oracle_vs_ref import PACKED, PART1, POC_STREAMS, TILE_PARTS, packed_stream, part1_stream, poc_stream, tile_part_stream
+from test_oracle_vs_ref import (HT_SETS, PACKED, PAL8_CASES, PART1, POC_STREAMS, TILE_PARTS, TILE_STYLES, ht_set_stream,
+                                packed_stream, pal8_file, part1_stream, poc_stream, tile_part_stream, tile_style_stream)
 
 
 def test_host_parser_and_splitter_under_sanitizers(tmp_path):
@@ -30,6 +31,9 @@ def test_host_parser_and_splitter_under_sanitizers(tmp_path):
     seeds.append(poc_stream(POC_STREAMS[2], w=90, h=70)[0])
     seeds += [part1_stream(PART1[0]), part1_stream(PART1[3], jp2=True), part1_stream(PART1[9])]
     seeds += [tile_part_stream(t, w=90, h=70)[0] for t in (TILE_PARTS[1], TILE_PARTS[7])]
+    seeds += [tile_style_stream(t, w=90, h=70)[0] for t in (TILE_STYLES[5], TILE_STYLES[8])]
+    seeds += [ht_set_stream(t, w=90, h=70)[0] for t in (HT_SETS[7], HT_SETS[10], HT_SETS[12], HT_SETS[18])]
+    seeds.append(pal8_file(*PAL8_CASES[1], tile=(64, 32))[0])
     files = []
     for i, s in enumerate(seeds):
         f = tmp_path / f"seed{i}.j2k"
