@@ -7,7 +7,7 @@
  *   init_tile :1016-1070   component/band/precinct/code-block geometry jpeg2000.c:274-577
  *   step sizes jpeg2000.c:214-272   packet headers jpeg2000dec.c:1136-1542 (HT paths)
  *   progression orders :1544-1833
- * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 blocks with mode switches, PAL8 -- SURVEY.md section 8(f) "next".
+ * Unsupported on purpose (B200J2K_ERR_PATCHWELCOME): Part-1 blocks with bypass / termination on each pass -- SURVEY.md section 8(f) "next".
  */
 #include "j2k_parse.h"
 
@@ -855,10 +855,11 @@ int Parser::build_geometry(int flags)
                 return B200J2K_ERR_INVALIDDATA;
             if (h.isHT && h.cap_b14 != (cs.cblk_style >> 6) && h.cap_b14 != 0)
                 return B200J2K_ERR_INVALIDDATA;
-            if (!(cs.cblk_style & 0xC0) && cs.cblk_style)
-                return B200J2K_ERR_PATCHWELCOME;          /* Part-1 blocks with bypass / restart / reset / causal /
-                                                           * segmentation symbols: only style 0 is served (for the
-                                                           * Part-1 blocks of a MIXED stream tier 2 checks that) */
+            if (!(cs.cblk_style & 0xC0) && (cs.cblk_style & 0x05))
+                return B200J2K_ERR_PATCHWELCOME;          /* Part-1 blocks with arithmetic-coding bypass or termination
+                                                           * on each pass (several codeword segments per block) are not
+                                                           * served; for the Part-1 blocks of a MIXED stream tier 2
+                                                           * checks that */
             /* cc = comp->coord_o: every resolution, band, precinct and code-block is laid out from it;
              * cr = comp->coord = cc reduced by lowres: the plane, the DWT and the output use it
              * (jpeg2000dec.c:1047-1050, jpeg2000.c:483-530) */
@@ -984,7 +985,10 @@ int Parser::build_geometry(int flags)
                                 d.dst_stride = (uint32_t)cw;
                                 d.dst_off = tc.coef_off + (uint32_t)(y0 - bd.c.y0 + offy) * (uint32_t)cw + (uint32_t)(x0 - bd.c.x0 + offx);
                                 d.M_b = (uint8_t)M_b;
-                                d.flags = (uint8_t)(((cs.cblk_style & 8) ? 1 : 0) | (cs.transform << 1));
+                                /* bits 4-5 only mean something to mq_block_kernel: context reset, segmentation symbols */
+                                d.flags = (uint8_t)(((cs.cblk_style & 8) ? 1 : 0) | (cs.transform << 1) |
+                                                    ((cs.cblk_style & 0x02) ? J2K_CBLK_MQ_RESET : 0) |
+                                                    ((cs.cblk_style & 0x20) ? J2K_CBLK_MQ_SEGSYM : 0));
                                 d.pad = (uint8_t)(b + (r > 0));              /* bandpos (jpeg2000dec.c:2240) */
                                 if (!(cs.cblk_style & 0xC0)) {
                                     d.flags |= J2K_CBLK_MQ;                  /* MIXED sets: decided per block in tier 2 */
@@ -1283,9 +1287,9 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                 int segment_passes, next_segment_passes = 0, nb;
                 unsigned segment_bytes = 0;
                 /* a MIXED block (SPcod bit 7) that the length rules unmask as a Part-1 block: HT bit off for good
-                 * (:1271-1274, :1303-1305, :1331-1333); only style 0 Part-1 blocks are served */
+                 * (:1271-1274, :1303-1305, :1331-1333); no bypass / termination on each pass */
                 auto turns_part1 = [&]() -> bool {
-                    if (cs.cblk_style & 0x3F)
+                    if (cs.cblk_style & 0x05)
                         return false;
                     cb.plhd = 0;
                     cb.modes &= (uint8_t)~0x40;

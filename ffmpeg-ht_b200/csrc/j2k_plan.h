@@ -27,6 +27,10 @@ enum { J2K_DWT97 = 0, J2K_DWT53 = 1, J2K_DWT97_INT = 2 };   /* enum DWTType, jpe
                              * jpeg2000dec.c:1993-2089).  Its descriptor carries nonzerobits in Lcup and the band
                              * orientation (0 LL, 1 HL, 2 LH, 3 HH) in Lref; data = the single codeword segment */
 
+#define J2K_CBLK_MQ_RESET  0x10  /* Part-1 block: JPEG2000_CBLK_RESET, context states re-initialised after every pass */
+#define J2K_CBLK_MQ_SEGSYM 0x20  /* Part-1 block: JPEG2000_CBLK_SEGSYM, a segmentation symbol behind every clean-up pass
+                                  * (flags bit 0, stripe-causal, means vertically causal contexts for a Part-1 block) */
+
 /* one HT code-block: a row of the table H9 (Jpeg2000Cblk, jpeg2000.h:183-205) */
 typedef struct CblkDesc {
     uint32_t data_off;      /* offset of Dcup in bytes[]; Dref follows at data_off + Lcup */

@@ -1,6 +1,7 @@
 /*
- * mq_block.cu -- Part-1 (EBCOT / MQ) code-block decode for sm_100a, code-block style 0, with the
- * dequantisation fused into the coefficient write-back.
+ * mq_block.cu -- Part-1 (EBCOT / MQ) code-block decode for sm_100a with the dequantisation fused into the
+ * coefficient write-back.  Code-block styles with one codeword segment: 0, context
+ * reset (0x02), vertically causal contexts (0x08), predictable termination (0x10), segmentation symbols (0x20).
  *
  * Replaces, for code-blocks that are not HT:
  *   decode_cblk + decode_sigpass / decode_refpass / decode_clnpass  libavcodec/jpeg2000dec.c:1872-2089
@@ -81,14 +82,19 @@ __device__ __forceinline__ void mq_bytein(Mq &m)
     m.nxt = mq_byte(m, m.pos + 1);
 }
 
-__device__ void mq_init(Mq &m, uint8_t *cx, const uint8_t *data, int len)
+__device__ void mq_reset_contexts(Mq &m)      /* ff_mqc_init_contexts */
 {
-    m.cx = cx;
     for (int i = 0; i < CX_COUNT; i++)
         m.cx[i] = 0;
     m.cx[CX_UNI] = 2 * 46;
     m.cx[CX_RL] = 2 * 3;
     m.cx[0] = 2 * 4;
+}
+
+__device__ void mq_init(Mq &m, uint8_t *cx, const uint8_t *data, int len)
+{
+    m.cx = cx;
+    mq_reset_contexts(m);
     m.data = data;
     m.len = len;
     m.pos = 0;
@@ -144,7 +150,13 @@ __device__ __forceinline__ int mq_decode(Mq &m, int ctx)
  *   nb4  which of its eight neighbours are significant (kept up to date when a sample becomes significant, as
  *        the reference keeps JPEG2000_T1_SIG_* in its flags, jpeg2000.c:172-200)
  * A frame of one column left / right and one stripe above / below the block stands in for the neighbours
- * outside. */
+ * outside.
+ * Vertically causal contexts (JPEG2000_CBLK_VSC; the passes are instantiated for it, VSC): the fourth row of a
+ * stripe reads its S / SW / SE neighbours as insignificant and the sign of S as absent (flags_mask,
+ * jpeg2000dec.c:1882-1883, :1916-1917, :1966-1968) -- a mask on byte 3 of the nb4 word when it is READ. */
+constexpr uint32_t VSC_BYTE3 = 0xFFu & ~(2u | 64u | 128u);          /* ~(NB_S | NB_SW | NB_SE) */
+template <bool VSC> __device__ __forceinline__ uint32_t nb_word(uint32_t n4) { return VSC ? n4 & (0x00FFFFFFu | (VSC_BYTE3 << 24)) : n4; }
+template <bool VSC> __device__ __forceinline__ unsigned nb_byte(unsigned n, int r) { return VSC && r == 3 ? n & VSC_BYTE3 : n; }
 enum : uint8_t { NB_N = 1, NB_S = 2, NB_W = 4, NB_E = 8, NB_NW = 16, NB_NE = 32, NB_SW = 64, NB_SE = 128 };
 
 struct Blk {
@@ -182,6 +194,7 @@ __device__ __forceinline__ int sig_context(const Blk &b, unsigned n)
  * neighbours), store the value, mark it and tell the eight neighbours.  The byte addresses of the rows above and
  * below follow from the sample's own: one byte back / forth inside the stripe word, or over to the neighbouring
  * stripe's word. */
+template <bool VSC>
 __device__ __forceinline__ void become_significant(const Blk &b, Mq &m, int x, int y, uint32_t mask)
 {
     uint8_t *st = reinterpret_cast<uint8_t *>(b.st4), *nb = reinterpret_cast<uint8_t *>(b.nb4);
@@ -190,7 +203,7 @@ __device__ __forceinline__ void become_significant(const Blk &b, Mq &m, int x, i
     const int up = r ? at - 1 : at - (b.W2 << 2) + 3, dn = r != 3 ? at + 1 : at + (b.W2 << 2) - 3;
     auto contrib = [](uint8_t s) { return (s & S_SIG) ? ((s & S_NEG) ? -1 : 1) : 0; };
     int hc = contrib(st[at - 4]) + contrib(st[at + 4]);
-    int vc = contrib(st[up]) + contrib(st[dn]);
+    int vc = contrib(st[up]) + (VSC && r == 3 ? 0 : contrib(st[dn]));
     hc = max(-1, min(1, hc));
     vc = max(-1, min(1, vc));
     int xorbit = 0;
@@ -222,6 +235,7 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t v)
 }
 
 /* decode_sigpass (:1872-1904) */
+template <bool VSC>
 __device__ void pass_sigprop(const Blk &b, Mq &m, int bp)
 {
     const uint32_t mask = 3u << (bp - 1);
@@ -231,16 +245,17 @@ __device__ void pass_sigprop(const Blk &b, Mq &m, int bp)
         const int rows = min(4, b.h - y0), base = ((y0 + 4) >> 2) * b.W2 + 1;
         for (int x = 0; x < b.w; x++) {
             /* candidates: a significant neighbour, not significant, not visited -- most columns have none */
-            const uint32_t n4 = b.nb4[base + x];
+            const uint32_t n4 = nb_word<VSC>(b.nb4[base + x]);
             if (!n4 || !(nonzero_bytes(n4) & ~nonzero_bytes(b.st4[base + x] & 0x05050505u)))
                 continue;
             const int at = (base + x) << 2;
             for (int r = 0; r < rows; r++) {
-                const uint8_t s = st[at + r], n = nb[at + r];
+                const uint8_t s = st[at + r];
+                const unsigned n = nb_byte<VSC>(nb[at + r], r);
                 if ((s & (S_SIG | S_VIS)) || !n)
                     continue;
                 if (mq_decode(m, CX_SIG + sig_context(b, n)))
-                    become_significant(b, m, x, y0 + r, mask);
+                    become_significant<VSC>(b, m, x, y0 + r, mask);
                 st[at + r] |= S_VIS;
             }
         }
@@ -248,6 +263,7 @@ __device__ void pass_sigprop(const Blk &b, Mq &m, int bp)
 }
 
 /* decode_refpass (:1906-1931) */
+template <bool VSC>
 __device__ void pass_magref(const Blk &b, Mq &m, int bp)
 {
     const uint32_t phalf = 1u << (bp - 1);
@@ -264,7 +280,7 @@ __device__ void pass_magref(const Blk &b, Mq &m, int bp)
                 const uint8_t s = st[at + r];
                 if ((s & (S_SIG | S_VIS)) != S_SIG)
                     continue;
-                const int ctx = (s & S_REF) ? CX_REF + 2 : CX_REF + (nb[at + r] ? 1 : 0);
+                const int ctx = (s & S_REF) ? CX_REF + 2 : CX_REF + (nb_byte<VSC>(nb[at + r], r) ? 1 : 0);
                 /* The reference does  v |= phalf;  v = bit ? v | 2 phalf : v & ~(2 phalf).  Bit 2 phalf is the
                  * half-LSB the previous coding step of this sample left set and the bits below it are clear, so
                  * that is "OR phalf" for a one and "XOR 3 phalf" for a zero: fire-and-forget reductions, no load
@@ -280,7 +296,8 @@ __device__ void pass_magref(const Blk &b, Mq &m, int bp)
     }
 }
 
-/* decode_clnpass (:1933-1990), no segmentation symbols */
+/* decode_clnpass (:1933-1990); the segmentation symbol is read by the caller */
+template <bool VSC>
 __device__ void pass_cleanup(const Blk &b, Mq &m, int bp)
 {
     const uint32_t mask = 3u << (bp - 1);
@@ -296,7 +313,7 @@ __device__ void pass_cleanup(const Blk &b, Mq &m, int bp)
                 continue;
             }
             /* a full column with nothing significant, visited or next to significance: run-length mode */
-            if (rows == 4 && !(s4 & 0x05050505u) && !b.nb4[base + x]) {
+            if (rows == 4 && !(s4 & 0x05050505u) && !nb_word<VSC>(b.nb4[base + x])) {
                 if (!mq_decode(m, CX_RL))
                     continue;
                 runlen = mq_decode(m, CX_UNI);
@@ -306,14 +323,41 @@ __device__ void pass_cleanup(const Blk &b, Mq &m, int bp)
             const int at = (base + x) << 2;
             for (int r = runlen; r < rows; r++) {
                 if (!dec && !(st[at + r] & (S_SIG | S_VIS)))
-                    dec = mq_decode(m, CX_SIG + sig_context(b, nb[at + r]));
+                    dec = mq_decode(m, CX_SIG + sig_context(b, nb_byte<VSC>(nb[at + r], r)));
                 if (dec)
-                    become_significant(b, m, x, y0 + r, mask);
+                    become_significant<VSC>(b, m, x, y0 + r, mask);
                 dec = 0;
                 st[at + r] &= (uint8_t)~S_VIS;
             }
         }
     }
+}
+
+/* the pass loop of decode_cblk (:2017-2059): clean-up first, then SigProp / MagRef / clean-up per bit-plane */
+template <bool VSC>
+__device__ int run_passes(const Blk &b, Mq &m, int npasses, int bpno, int sty)
+{
+    int pass_t = 2;
+    while (npasses--) {
+        if (bpno < 0 || bpno > 29)
+            return B200J2K_KERR_INVALID;
+        if (pass_t == 0) pass_sigprop<VSC>(b, m, bpno + 1);
+        else if (pass_t == 1) pass_magref<VSC>(b, m, bpno + 1);
+        else {
+            pass_cleanup<VSC>(b, m, bpno + 1);
+            if (sty & J2K_CBLK_MQ_SEGSYM)                   /* four UNIFORM decisions, 1010 expected; the reference
+                                                            * only logs a mismatch (:1981-1989) */
+                for (int i = 0; i < 4; i++)
+                    mq_decode(m, CX_UNI);
+        }
+        if (sty & J2K_CBLK_MQ_RESET)                        /* JPEG2000_CBLK_RESET (:2038-2039) */
+            mq_reset_contexts(m);
+        if (++pass_t == 3) {
+            bpno--;
+            pass_t = 0;
+        }
+    }
+    return 1;
 }
 
 __global__ void __launch_bounds__(32)
@@ -340,21 +384,9 @@ mq_block_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__
         Blk b = { w, h, W2, smem, smem + words, dst, d.dst_stride, (int)d.Lref };
         Mq m;
         mq_init(m, reinterpret_cast<uint8_t *>(smem + state_words), bytes + d.data_off, (int)d.length);
-        int npasses = d.npasses, pass_t = 2;
-        int bpno = (int)d.Lcup - 1 + 31 - d.M_b - 1 - d.roi_shift;      /* Lcup carries nonzerobits */
-        while (npasses--) {
-            if (bpno < 0 || bpno > 29) {
-                ret = B200J2K_KERR_INVALID;
-                break;
-            }
-            if (pass_t == 0) pass_sigprop(b, m, bpno + 1);
-            else if (pass_t == 1) pass_magref(b, m, bpno + 1);
-            else pass_cleanup(b, m, bpno + 1);
-            if (++pass_t == 3) {
-                bpno--;
-                pass_t = 0;
-            }
-        }
+        const int bpno0 = (int)d.Lcup - 1 + 31 - d.M_b - 1 - d.roi_shift;      /* Lcup carries nonzerobits */
+        const int sty = d.flags & (J2K_CBLK_MQ_RESET | J2K_CBLK_MQ_SEGSYM);
+        ret = (d.flags & 1) ? run_passes<true>(b, m, d.npasses, bpno0, sty) : run_passes<false>(b, m, d.npasses, bpno0, sty);
         if (status)
             status[bi] = ret;
     }

@@ -44,6 +44,11 @@ int oracle_ht_block(const uint8_t *data, int length, int npasses, int Lcup, int 
 int oracle_mq_block(const uint8_t *data, int length, int npasses, int nonzerobits, int w, int h, int bandpos,
                     int M_b, int roi_shift, int32_t *out);
 
+/* the same under a code-block style with one codeword segment: 0x02 context reset after each pass, 0x08 vertically
+ * causal contexts, 0x20 segmentation symbols (jpeg2000dec.c:1999, :2034-2039) */
+int oracle_mq_block_style(const uint8_t *data, int length, int npasses, int nonzerobits, int w, int h, int bandpos,
+                          int M_b, int roi_shift, int style, int32_t *out);
+
 int oracle_idwt(int type, const int *border, int levels, void *data);
 
 /* M1-M3: inverse component transform in place (jpeg2000dsp.c:43-91) */

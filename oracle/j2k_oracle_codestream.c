@@ -1159,9 +1159,9 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
             int segment_passes, next_segment_passes = 0, bits;
             unsigned segment_bytes = 0;
             /* a MIXED block (SPcod bit 7) that the length rules below unmask as a Part-1 block: HT bit off for good
-             * (:1271-1274, :1303-1305, :1331-1333).  Part-1 blocks of any style but 0 are not restated. */
+             * (:1271-1274, :1303-1305, :1331-1333).  Part-1 blocks with bypass / termination on each pass are not restated. */
 #define TURNS_PART1(cb) do { \
-                if (cs->cblk_style & 0x3F) { ret = ORACLE_ERR_PATCH; goto fail; } \
+                if (cs->cblk_style & 0x05) { ret = ORACLE_ERR_PATCH; goto fail; } \
                 (cb)->plhd = 0; (cb)->modes &= ~0x40; } while (0)
             if (cb->plhd) {                               /* :1256-1340 */
                 int href = (cb->npasses + newpasses - 1) % 3;
@@ -1561,13 +1561,13 @@ static int decode_tile(Dec *d, Tile *t, uint8_t *const planes[4], const int stri
                                                            * block no packet ever reached, as in the reference */
                             if (!cb->length)
                                 continue;
-                            if (cs->cblk_style & 0x3F) {  /* reset / causal / segmentation symbols: not restated */
+                            if (cs->cblk_style & 0x05) {  /* bypass / termination on each pass: not restated */
                                 free(t1);
                                 return ORACLE_ERR_PATCH;
                             }
                             const int nonzerobits = M_b - (cb->zbp - t->comp[0].roi_shift);
-                            if (oracle_mq_block(cb->data ? cb->data : none, cb->length, cb->npasses, nonzerobits, bw, bh,
-                                                b + (r > 0), M_b, comp->roi_shift, t1)) {
+                            if (oracle_mq_block_style(cb->data ? cb->data : none, cb->length, cb->npasses, nonzerobits, bw,
+                                                      bh, b + (r > 0), M_b, comp->roi_shift, cs->cblk_style, t1)) {
                                 coded = 1;
                                 d->nblocks++;
                                 dequantise(t1, bw, bh, comp->data, W, cb->x0 - bd->c.x0, cb->y0 - bd->c.y0,

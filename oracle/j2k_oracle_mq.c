@@ -10,8 +10,9 @@
  *   libavcodec/jpeg2000.c:90-170    context labels: significance (Table D.1), sign (D.2/D.3), refinement (D.4)
  *   libavcodec/jpeg2000dec.c:1872-1990  significance propagation, magnitude refinement and clean-up passes
  *   libavcodec/jpeg2000dec.c:1993-2089  decode_cblk: pass loop, bit-plane bookkeeping, ROI, sign-magnitude output
- * Only code-block style 0 (one codeword segment, no bypass / restart / reset / causal / segmentation symbols)
- * is restated: the T2 side refuses the others.
+ * Restated: the styles with one codeword segment -- 0, context reset (0x02), vertically causal contexts (0x08),
+ * predictable termination (0x10, nothing to do in a decoder) and segmentation symbols (0x20); the T2 side
+ * refuses arithmetic-coding bypass (0x01) and termination on each pass (0x04).
  *
  * Output as the reference leaves it in t1->data: bit 31 sign, magnitude left-aligned with the binary point at
  * bit 31 - M_b and the reconstruction half-bit set -- the same format the HT decoder produces, so the same
@@ -66,12 +67,17 @@ static void mq_bytein(Mq *m)
     }
 }
 
-static void mq_init(Mq *m, const uint8_t *data, int len)
+static void mq_reset_contexts(Mq *m)                       /* ff_mqc_init_contexts (mqcdec.c) */
 {
     memset(m->cx, 0, sizeof(m->cx));
     m->cx[CX_UNI] = 2 * 46;
     m->cx[CX_RL] = 2 * 3;
     m->cx[0] = 2 * 4;
+}
+
+static void mq_init(Mq *m, const uint8_t *data, int len)
+{
+    mq_reset_contexts(m);
     m->data = data;
     m->len = len;
     m->pos = 0;
@@ -129,18 +135,24 @@ typedef struct Blk {
     uint8_t *st;               /* (h + 2) rows */
     int32_t *val;              /* w * h, row stride w */
     int bandpos;
+    int vsc;                   /* JPEG2000_CBLK_VSC: the last row of a stripe does not see the stripe below */
 } Blk;
 
 #define ST(b, x, y) ((b)->st[((y) + 1) * (b)->stride + (x) + 1])
 
 static inline int sig(const Blk *b, int x, int y) { return ST(b, x, y) & ST_SIG; }
 
+/* flags_mask of the coding passes (jpeg2000dec.c:1882-1883, :1916-1917, :1966-1968): with vertically causal
+ * contexts the fourth row of a stripe reads its S, SW, SE neighbours as insignificant (and their sign as absent) */
+static inline int blind_south(const Blk *b, int y) { return b->vsc && (y & 3) == 3; }
+
 /* neighbourhood sums: horizontal, vertical, diagonal significant neighbours */
 static void counts(const Blk *b, int x, int y, int *h, int *v, int *d)
 {
+    const int south = !blind_south(b, y);
     *h = !!sig(b, x - 1, y) + !!sig(b, x + 1, y);
-    *v = !!sig(b, x, y - 1) + !!sig(b, x, y + 1);
-    *d = !!sig(b, x - 1, y - 1) + !!sig(b, x + 1, y - 1) + !!sig(b, x - 1, y + 1) + !!sig(b, x + 1, y + 1);
+    *v = !!sig(b, x, y - 1) + (south && sig(b, x, y + 1));
+    *d = !!sig(b, x - 1, y - 1) + !!sig(b, x + 1, y - 1) + (south && sig(b, x - 1, y + 1)) + (south && sig(b, x + 1, y + 1));
 }
 
 /* Table D.1; bandpos 0 LL, 1 HL, 2 LH, 3 HH */
@@ -168,7 +180,7 @@ static int sign_context(const Blk *b, int x, int y, int *xorbit)
 {
     static const int8_t contrib[4] = { 0, 1, 0, -1 };     /* index = SIG | NEG: insignificant 0, positive +1, negative -1 */
     int hc = contrib[ST(b, x - 1, y) & 3] + contrib[ST(b, x + 1, y) & 3];
-    int vc = contrib[ST(b, x, y - 1) & 3] + contrib[ST(b, x, y + 1) & 3];
+    int vc = contrib[ST(b, x, y - 1) & 3] + (blind_south(b, y) ? 0 : contrib[ST(b, x, y + 1) & 3]);
     hc = hc > 1 ? 1 : hc < -1 ? -1 : hc;
     vc = vc > 1 ? 1 : vc < -1 ? -1 : vc;
     if (hc < 0 || (hc == 0 && vc < 0)) {
@@ -243,8 +255,8 @@ static void pass_magref(Blk *b, Mq *m, int bp)
             }
 }
 
-/* decode_clnpass (:1933-1990), without segmentation symbols */
-static void pass_cleanup(Blk *b, Mq *m, int bp)
+/* decode_clnpass (:1933-1990); the segmentation symbol behind it is read and, like in the reference, only logged */
+static void pass_cleanup(Blk *b, Mq *m, int bp, int segsym)
 {
     const int32_t mask = 3 << (bp - 1);
     for (int y0 = 0; y0 < b->h; y0 += 4)
@@ -271,6 +283,9 @@ static void pass_cleanup(Blk *b, Mq *m, int bp)
                 ST(b, x, y) &= ~ST_VIS;
             }
         }
+    if (segsym)
+        for (int i = 0; i < 4; i++)
+            mq_decode(m, CX_UNI);
 }
 
 /* decode_cblk (:1993-2089).  nonzerobits = expn + guard bits - 1 - (zero bit-planes - roi shift of component 0).
@@ -279,10 +294,17 @@ static void pass_cleanup(Blk *b, Mq *m, int bp)
 int oracle_mq_block(const uint8_t *data, int length, int npasses, int nonzerobits, int w, int h, int bandpos,
                     int M_b, int roi_shift, int32_t *out)
 {
+    return oracle_mq_block_style(data, length, npasses, nonzerobits, w, h, bandpos, M_b, roi_shift, 0, out);
+}
+
+/* style = SPcod code-block style: 0x02 reset, 0x08 causal, 0x20 segmentation symbols (0x10 changes nothing) */
+int oracle_mq_block_style(const uint8_t *data, int length, int npasses, int nonzerobits, int w, int h, int bandpos,
+                          int M_b, int roi_shift, int style, int32_t *out)
+{
     memset(out, 0, sizeof(int32_t) * (size_t)w * h);
     if (!length)
         return 0;
-    Blk b = { w, h, w + 2, calloc((size_t)(w + 2) * (h + 2), 1), out, bandpos };
+    Blk b = { w, h, w + 2, calloc((size_t)(w + 2) * (h + 3), 1), out, bandpos, style & 0x08 };
     Mq m;
     mq_init(&m, data, length);
     int bpno = nonzerobits - 1 + 31 - M_b - 1 - roi_shift, pass_t = 2, ret = 1;
@@ -293,7 +315,9 @@ int oracle_mq_block(const uint8_t *data, int length, int npasses, int nonzerobit
         }
         if (pass_t == 0) pass_sigprop(&b, &m, bpno + 1);
         else if (pass_t == 1) pass_magref(&b, &m, bpno + 1);
-        else pass_cleanup(&b, &m, bpno + 1);
+        else pass_cleanup(&b, &m, bpno + 1, style & 0x20);
+        if (style & 0x02)                                   /* JPEG2000_CBLK_RESET (:2038-2039) */
+            mq_reset_contexts(&m);
         if (++pass_t == 3) {
             bpno--;
             pass_t = 0;

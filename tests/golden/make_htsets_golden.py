@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
 """Generates tests/golden/frames_htsets.npz with the REFERENCE (oracle/_ref/libj2kref.so built from /root/reference):
 HTDECLARED and MIXED streams (blocks of one frame on both block coders), MIXED streams with random byte damage, and
-the Psot bound cases, palettised JP2 files (PAL8: index plane + palette) -- reference verdict and a SHA-1 digest of its picture.  Same layout as frames_tiles.npz
+the Psot bound cases, palettised JP2 files (PAL8: index plane + palette), Part-1 streams re-labelled with
+other code-block styles (context reset, causal contexts, segmentation symbols) -- reference verdict and a SHA-1 digest of its picture.  Same layout as frames_tiles.npz
 (key = name|flags).  Run where the reference is mounted:  python tests/golden/make_htsets_golden.py"""
 import hashlib
 import sys
@@ -13,12 +14,10 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path[:0] = [str(ROOT), str(ROOT / "tools"), str(ROOT / "tests")]
 from helpers import ref_decode  # noqa: E402
 from test_oracle_vs_ref import (HT_SETS, PAL8_CASES, ht_set_damaged_streams, ht_set_stream, pal8_file,  # noqa: E402
-                                psot_bound_cases)
+                                part1_styled_streams, psot_bound_cases)
 
 items = {}
 for i, t in enumerate(HT_SETS):
-    if t["ht_set"] >= 4 and t["cfg"].get("vsc"):
-        continue            # Part-1 blocks with a stripe-causal style: served by the reference only
     for be in ((0,) if t["cfg"].get("reversible", True) else (0, 1)):
         items[f"ht_set{i:02d}|{be}"] = ht_set_stream(t)[0]
 for i, bad in enumerate(ht_set_damaged_streams()):
@@ -27,6 +26,9 @@ for i, bad in enumerate(ht_set_damaged_streams()):
     items[f"ht_set_damaged{i:02d}|0"] = bad
 for i, c in enumerate(psot_bound_cases()):
     items[f"psot{i}|0"] = c
+for i, (name, c) in enumerate(part1_styled_streams()):
+    if i % 8 < 6 and (i // 8) in (0, 3, 5):          # three layouts x six served styles
+        items[f"part1_styled{i:02d}|0"] = c
 for i, (bd, csp, pal) in enumerate(PAL8_CASES):
     items[f"pal8_{i}|0"] = pal8_file(bd, csp, pal, tile=(64, 32))[0]
 pack = {}

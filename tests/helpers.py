@@ -68,13 +68,14 @@ def ht_block(lib_fn, data: bytes, npasses, Lcup, Lref, zbp, w, h, M_b, roi=0, vs
     return ret, out.reshape(h, w)
 
 
-def mq_block(data: bytes, npasses, nonzerobits, w, h, bandpos, M_b, roi=0):
-    """oracle_mq_block: a Part-1 code-block of style 0 -> (ret, sign-magnitude words)"""
-    fn = oracle().oracle_mq_block
+def mq_block(data: bytes, npasses, nonzerobits, w, h, bandpos, M_b, roi=0, style=0):
+    """oracle_mq_block_style: a Part-1 code-block (style bits 0x02 reset, 0x08 causal, 0x20 segmentation symbols) ->
+    (ret, sign-magnitude words)"""
+    fn = oracle().oracle_mq_block_style
     fn.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                   ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+                   ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
     out = np.zeros(w * h, np.int32)
-    ret = fn(data, len(data), npasses, nonzerobits, w, h, bandpos, M_b, roi, out.ctypes.data)
+    ret = fn(data, len(data), npasses, nonzerobits, w, h, bandpos, M_b, roi, style, out.ctypes.data)
     return ret, out.reshape(h, w)
 
 

@@ -12,7 +12,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import (PAL8_CASES, pal8_file, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+from test_oracle_vs_ref import (part1_styled_streams, PAL8_CASES, pal8_file, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
                                 TILE_STYLES, packed_stream, part1_stream, poc_stream, tile_part_stream,
                                 tile_style_marker_cases, tile_style_stream,
                                 subsampled_stream)
@@ -510,6 +510,21 @@ def test_subsampled_and_jp2_frames_vs_oracle(name, subs, bd, dec, dec_bitexact):
                 info, got = (dec_bitexact if bitexact else dec).decode(data)
                 assert (info.width, info.height, info.pix_name) == (oinfo[0], oinfo[1], oracle_pix_name())
                 assert np.array_equal(got, want), (name, w, h, bitexact)
+
+
+def test_part1_styled_frames_vs_oracle(dec):
+    """mq_block_kernel under context reset, vertically causal contexts and segmentation symbols (and combinations)."""
+    n = 0
+    for name, cs in part1_styled_streams():
+        r, _, want = oracle_decode(cs, 0)
+        if r == 0:
+            assert np.array_equal(dec.decode(cs)[1], want), name
+            n += 1
+        else:
+            with pytest.raises(fb.DecodeError) as e:
+                dec.decode(cs)
+            assert e.value.code == r, name
+    assert n == 42
 
 
 @pytest.mark.parametrize("bd,csp,pal", PAL8_CASES)

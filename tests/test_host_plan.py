@@ -11,7 +11,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import ht_block, mq_block, oracle, oracle_decode, oracle_pix_name
-from test_oracle_vs_ref import (PAL8_CASES, pal8_file, psot_bound_cases, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+from test_oracle_vs_ref import (part1_styled_streams, PAL8_CASES, pal8_file, psot_bound_cases, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
                                 TILE_STYLES, part1_stream, tile_part_stream, tile_style_marker_cases, tile_style_stream,
                                 packed_marker_cases, packed_stream, poc_marker_cases, poc_stream,
                                 subsampled_stream)
@@ -29,7 +29,9 @@ def picture_from_plan(cs: bytes, flags: int):
         w, h, M_b = int(d["w"]), int(d["h"]), int(d["M_b"])
         seg = allbytes[int(d["data_off"]): int(d["data_off"]) + int(d["length"])].tobytes()
         if int(d["flags"]) & 0x08:                  # J2K_CBLK_MQ: Lcup = nonzerobits, Lref = band orientation
-            ret, sm = mq_block(seg, int(d["npasses"]), int(d["Lcup"]), w, h, int(d["Lref"]), M_b, int(d["roi_shift"]))
+            f = int(d["flags"])                            # descriptor flags -> SPcod style bits of a Part-1 block
+            style = (0x08 if f & 1 else 0) | (0x02 if f & 0x10 else 0) | (0x20 if f & 0x20 else 0)
+            ret, sm = mq_block(seg, int(d["npasses"]), int(d["Lcup"]), w, h, int(d["Lref"]), M_b, int(d["roi_shift"]), style)
         else:
             ret, sm = ht_block(oracle().oracle_ht_block, seg, int(d["npasses"]), int(d["Lcup"]), int(d["Lref"]),
                                int(d["zbp"]), w, h, M_b, int(d["roi_shift"]), int(d["flags"]) & 1)
@@ -325,6 +327,20 @@ def test_geometry_cache_sees_tile_header_changes():
         r, _, opic = oracle_decode(cs)
         _, pic = picture_from_plan(cs, 0)
         assert r == 0 and np.array_equal(pic, opic)
+
+
+def test_plan_of_part1_styled_streams():
+    """Part-1 blocks under context reset / causal contexts / segmentation symbols: descriptor flags carry the style."""
+    n = 0
+    for name, cs in part1_styled_streams():
+        r, _, opic = oracle_decode(cs)
+        try:
+            _, pic = picture_from_plan(cs, 0)
+            assert r == 0 and np.array_equal(pic, opic), name
+            n += 1
+        except fb.DecodeError as e:
+            assert e.code == r, name
+    assert n >= 20
 
 
 @pytest.mark.parametrize("bd,csp,pal", PAL8_CASES)
