@@ -39,7 +39,7 @@ class FrameInfo(ctypes.Structure):
                 ("plane_width", ctypes.c_int32 * 4), ("plane_height", ctypes.c_int32 * 4),
                 ("plane_row_bytes", ctypes.c_int32 * 4), ("ntiles", ctypes.c_int32),
                 ("ncodeblocks", ctypes.c_int32), ("bytes_consumed", ctypes.c_int64),
-                ("av_pix_fmt_name", ctypes.c_char * 16)]
+                ("av_pix_fmt_name", ctypes.c_char * 16), ("sar_num", ctypes.c_int32), ("sar_den", ctypes.c_int32)]
 
     @property
     def pix_name(self) -> str:

@@ -270,6 +270,8 @@ void fill_info(const Parser &p, b200j2k_frame_info *info)
     info->ncodeblocks = (int32_t)p.cblk.size();
     info->bytes_consumed = p.consumed;
     strncpy(info->av_pix_fmt_name, p.hdr.pix_name, sizeof(info->av_pix_fmt_name) - 1);
+    info->sar_num = p.hdr.sar_num && p.hdr.sar_den ? p.hdr.sar_num : 0;      /* published only when both are set (:2867) */
+    info->sar_den = p.hdr.sar_num && p.hdr.sar_den ? p.hdr.sar_den : 0;
 }
 
 bool is_pinned(const void *p)

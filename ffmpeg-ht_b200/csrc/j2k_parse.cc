@@ -224,7 +224,7 @@ int choose_pix(Header &h, const char **name)
  * Walks the boxes up to the contiguous codestream box; from the JP2 header box it takes the enumerated
  * colour space ('colr' method 1), a valid palette ('pclr': steers the format choice and, for a one-component
  * stream of at most 8 bits outside the greyscale list, makes the output PAL8) and the channel definitions
- * ('cdef': component -> plane for planar output).  'res ' (sample aspect ratio) is not published.
+ * ('cdef': component -> plane for planar output) and the sample aspect ratio ('res ').
  * Returns 1 with *pos at the codestream, 0 when there is none, < 0 on a malformed box. */
 struct Cursor {
     const uint8_t *b;
@@ -241,6 +241,39 @@ struct Cursor {
     uint32_t u8() { uint32_t v = pos < size ? b[pos] : 0; pos++; return v; }
     void seek(int64_t p) { pos = p < 0 ? 0 : p > size ? size : p; }
 };
+
+/* av_reduce() of libavutil (rational.c:35-78) for non-negative arguments: lowest terms when both fit under max,
+ * else the closest fraction with both terms <= max (last fitting convergent of the continued fraction, or the
+ * last semi-convergent when that is closer). */
+void reduce_fraction(int *out_num, int *out_den, int64_t num, int64_t den, int64_t max)
+{
+    int64_t g = num, t = den;
+    while (t) { const int64_t r = g % t; g = t; t = r; }
+    if (g) { num /= g; den /= g; }
+    int64_t pn = 0, pd = 1, cn = 1, cd = 0;                 /* previous / current convergent */
+    if (num <= max && den <= max) {
+        cn = num; cd = den; den = 0;
+    }
+    while (den) {
+        const uint64_t x = (uint64_t)(num / den);
+        const int64_t next_den = num - den * (int64_t)x;
+        const int64_t nn = (int64_t)x * cn + pn, nd = (int64_t)x * cd + pd;
+        if (nn > max || nd > max) {
+            uint64_t k = x;
+            if (cn) k = (uint64_t)((max - pn) / cn);
+            if (cd && (uint64_t)((max - pd) / cd) < k) k = (uint64_t)((max - pd) / cd);
+            if (den * (2 * (int64_t)k * cd + pd) > num * cd) {
+                const int64_t a = (int64_t)k * cn + pn, b = (int64_t)k * cd + pd;
+                cn = a; cd = b;
+            }
+            break;
+        }
+        pn = cn; pd = cd; cn = nn; cd = nd;
+        num = den; den = next_den;
+    }
+    *out_num = (int)cn;
+    *out_den = (int)cd;
+}
 
 int jp2_find_codestream(Cursor &g, Header &h)
 {
@@ -315,6 +348,20 @@ int jp2_find_codestream(Cursor &g, Header &h)
                             h.cdef[cn] = asoc;
                         if (g.pos >= g.size + 6)           /* the checked reads return 0 forever: stop early */
                             break;
+                    }
+                } else if (atom2 == 0x72657320u && atom2_size >= 18) {         /* 'res ': capture / display resolution */
+                    g.pos += 4;
+                    const uint32_t resx = g.be32();
+                    if (resx == 0x72657363u || resx == 0x72657364u) {          /* 'resc' / 'resd' */
+                        int64_t vnum = g.be16(), vden = g.be16(), hnum = g.be16(), hden = g.be16();
+                        int64_t vexp = g.u8(), hexp = g.u8();
+                        if (vnum && vden && hnum && hden) {
+                            if (vexp > hexp) { vexp -= hexp; hexp = 0; } else { hexp -= vexp; vexp = 0; }
+                            /* same double arithmetic as the reference (:2788-2794) */
+                            if (INT64_MAX / (hnum * vden) > pow(10, hexp) && INT64_MAX / (vnum * hden) > pow(10, vexp))
+                                reduce_fraction(&h.sar_den, &h.sar_num, (int64_t)(hnum * vden * pow(10, hexp)),
+                                                (int64_t)(vnum * hden * pow(10, vexp)), INT32_MAX);
+                        }
                     }
                 }
                 g.seek(atom2_end);

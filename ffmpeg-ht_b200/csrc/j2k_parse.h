@@ -91,6 +91,7 @@ struct Header {
     Poc poc[32];
     /* JP2 wrapper (jp2_find_codestream, jpeg2000dec.c:2658-2804) and the pixel format it steers */
     int colour_space = 0, pal8 = 0;
+    int sar_num = 0, sar_den = 0;     /* s->sar from the 'res ' box (jpeg2000dec.c:2762-2796) */
     uint32_t palette[256] = {0};      /* s->palette (jpeg2000dec.h:94), 0xAARRGGBB per entry; delivered as plane 1 of pal8 */
     int cdef[J2K_MAX_COMP] = { -1, -1, -1, -1 };
     const char *pix_name = "none";      /* libavutil name of the chosen AVPixelFormat */

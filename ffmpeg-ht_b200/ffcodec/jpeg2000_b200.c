@@ -101,6 +101,8 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
     avctx->bits_per_raw_sample = info.precision;
     if (info.lossless)
         avctx->properties |= FF_CODEC_PROPERTY_LOSSLESS;
+    if (info.sar_num && info.sar_den)                      /* jpeg2000dec.c:2867-2868 */
+        avctx->sample_aspect_ratio = (AVRational){ info.sar_num, info.sar_den };
 
     if (avctx->skip_frame >= AVDISCARD_ALL)
         return avpkt->size;

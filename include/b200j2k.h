@@ -73,6 +73,8 @@ typedef struct b200j2k_frame_info {
     char    av_pix_fmt_name[16];    /* libavutil name of the AVPixelFormat the reference would choose for this
                                      * stream ("rgb48le", "yuv422p10le", ...; jpeg2000dec.c:328-412): pix_fmt
                                      * above is only its memory-layout class */
+    int32_t sar_num, sar_den;       /* AVCodecContext.sample_aspect_ratio from the capture / display resolution box
+                                     * of a JP2 file ('res ', jpeg2000dec.c:2762-2796, :2867-2868); 0 / 0 = leave it */
 } b200j2k_frame_info;
 
 typedef struct b200j2k_decoder b200j2k_decoder;

@@ -56,7 +56,8 @@ int oracle_mct(int type, void *p0, void *p1, void *p2, int n);
 
 /* whole codestream -> tightly packed pixels.
  * info[0]=width info[1]=height info[2]=ORACLE_PIX_* info[3]=bytes written
- * info[4]=number of code-blocks decoded info[5]=ncomponents info[6]=precision.
+ * info[4]=number of code-blocks decoded info[5]=ncomponents info[6]=precision
+ * info[7]=sample aspect ratio from a JP2 'res ' box, num << 32 | den, 0 = none (jpeg2000dec.c:2762-2796, :2867).
  * Returns 0 or a negative error. */
 int oracle_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint8_t *out, int64_t cap);
 /* libavutil name of the AVPixelFormat the last oracle_decode() of this thread chose ("rgb48le", "yuv420p10le") */

@@ -117,6 +117,7 @@ typedef struct Dec {
     int pix, out_w, out_h;
     int colour_space, pal8, cdef[4];                /* JP2 wrapper state (jp2_find_codestream) */
     uint32_t palette[256];                          /* s->palette (jpeg2000dec.h:94): 0xAARRGGBB per entry */
+    int sar_num, sar_den;                           /* s->sar from the 'res ' box (:2762-2796), 0/0 = none */
     int npoc;                                       /* main-header POC entries (get_poc) */
     struct { int RS, CS, LYE, RE, CE, P; } poc[32];
     int chroma_lw, chroma_lh;                       /* log2_chroma_w/h of the chosen AVPixelFormat */
@@ -395,9 +396,41 @@ static int choose_pix(Dec *d)
     return f->klass;
 }
 
+/* av_reduce(dst_num, dst_den, num, den, max) of libavutil (rational.c:35-78) for non-negative arguments: the
+ * fraction in lowest terms when it fits, else the best approximation with both terms <= max -- the last convergent
+ * of the continued fraction that fits, or the last semi-convergent when that one is closer. */
+static void reduce_fraction(int *out_num, int *out_den, int64_t num, int64_t den, int64_t max)
+{
+    int64_t a = num, b = den;
+    while (b) { int64_t t = a % b; a = b; b = t; }           /* gcd */
+    if (a) { num /= a; den /= a; }
+    int64_t p0 = 0, q0 = 1, p1 = 1, q1 = 0;                   /* convergents p/q: previous and current */
+    if (num <= max && den <= max) {
+        p1 = num; q1 = den; den = 0;
+    }
+    while (den) {
+        const uint64_t x = (uint64_t)(num / den);
+        const int64_t rest = num - den * (int64_t)x;
+        const int64_t p2 = (int64_t)x * p1 + p0, q2 = (int64_t)x * q1 + q0;
+        if (p2 > max || q2 > max) {
+            uint64_t k = x;
+            if (p1) k = (uint64_t)((max - p0) / p1);
+            if (q1) { const uint64_t kq = (uint64_t)((max - q0) / q1); if (kq < k) k = kq; }
+            if (den * (2 * (int64_t)k * q1 + q0) > num * q1) {
+                const int64_t np = (int64_t)k * p1 + p0, nq = (int64_t)k * q1 + q0;
+                p1 = np; q1 = nq;
+            }
+            break;
+        }
+        p0 = p1; q0 = q1; p1 = p2; q1 = q2;
+        num = den; den = rest;
+    }
+    *out_num = (int)p1;
+    *out_den = (int)q1;
+}
+
 /* ---- JP2 wrapper: jp2_find_codestream (:2658-2804).  Returns 1 with *ppos at the codestream box payload,
- * 0 when no codestream box was found, < 0 for a malformed box.  'res ' is read by the reference for the
- * sample aspect ratio only and is skipped here. */
+ * 0 when no codestream box was found, < 0 for a malformed box. */
 static uint32_t jp2_be(const Dec *d, int64_t *pos, int n)
 {
     uint32_t v = 0;
@@ -486,6 +519,20 @@ static int jp2_find_codestream(Dec *d, int64_t *ppos)
                             d->cdef[cn] = asoc;
                         if (pos >= size + 6)
                             break;
+                    }
+                } else if (atom2 == 0x72657320u && atom2_size >= 18) {         /* 'res ' -> sample aspect ratio */
+                    pos += 4;
+                    const uint32_t resx = jp2_be(d, &pos, 4);
+                    if (resx == 0x72657363u || resx == 0x72657364u) {          /* resc / resd */
+                        int64_t vnum = jp2_be(d, &pos, 2), vden = jp2_be(d, &pos, 2);
+                        int64_t hnum = jp2_be(d, &pos, 2), hden = jp2_be(d, &pos, 2);
+                        int64_t vexp = jp2_be(d, &pos, 1), hexp = jp2_be(d, &pos, 1);
+                        if (vnum && vden && hnum && hden) {
+                            if (vexp > hexp) { vexp -= hexp; hexp = 0; } else { hexp -= vexp; vexp = 0; }
+                            if (INT64_MAX / (hnum * vden) > pow(10, hexp) && INT64_MAX / (vnum * hden) > pow(10, vexp))
+                                reduce_fraction(&d->sar_den, &d->sar_num, (int64_t)(hnum * vden * pow(10, hexp)),
+                                                (int64_t)(vnum * hden * pow(10, vexp)), INT32_MAX);
+                        }
                     }
                 }
                 SEEK(atom2_end);
@@ -1719,6 +1766,7 @@ int oracle_decode(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, u
         info[4] = d.nblocks;
         info[5] = d.ncomp;
         info[6] = d.precision;
+        info[7] = d.sar_num && d.sar_den ? ((int64_t)d.sar_num << 32) | (uint32_t)d.sar_den : 0;   /* :2867-2868 */
         ret = 0;
     }
 end:

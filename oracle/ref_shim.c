@@ -167,6 +167,7 @@ static int64_t pack_frame(const AVCodecContext *avctx, const AVFrame *f, uint8_t
 
 /*
  * info[0]=width info[1]=height info[2]=AVPixelFormat info[3]=bytes written info[4]=decode return
+ * info[5]/info[6]=AVCodecContext.sample_aspect_ratio num/den
  * returns 0 on success, the negative AVERROR otherwise.
  */
 int REF_NAME(decode)(const uint8_t *cs, int64_t len, int bitexact, int64_t *info, uint8_t *out, int64_t cap)
@@ -189,6 +190,8 @@ int REF_NAME(decode)(const uint8_t *cs, int64_t len, int bitexact, int64_t *info
         info[1] = frame->height;
         info[2] = avctx->pix_fmt;
         info[3] = pack_frame(avctx, frame, out, cap);
+        info[5] = avctx->sample_aspect_ratio.num;
+        info[6] = avctx->sample_aspect_ratio.den;
         ret = info[3] < 0 ? -1 : 0;
     } else if (ret >= 0) {
         ret = -1;

@@ -91,6 +91,17 @@ def test_ffcodec_shim_jp2_and_subsampled():
     assert n >= 20
 
 
+def test_ffcodec_shim_sample_aspect_ratio():
+    """AVCodecContext.sample_aspect_ratio from the 'res ' box of a JP2 file, like the reference decoder sets it."""
+    from test_oracle_vs_ref import RES_BOXES, res_box_file
+    for res in RES_BOXES:
+        data = res_box_file(res)
+        r1, i1, o1, _ = ref_decode(data)
+        r2, i2, o2 = shim_decode(data)
+        assert r1 == 0 and r2 == 0 and np.array_equal(o1, o2)
+        assert (i1[5], i1[6]) == (i2[5], i2[6]), res
+
+
 def test_ffcodec_shim_error_codes():
     planes = j2kgen.synth_image(64, 64, 1, 8, seed=2)
     cs = j2kgen.encode(planes, 8, j2kgen.EncParams(levels=2))

@@ -747,6 +747,30 @@ def test_jp2_wrapped_decode_bit_exact():
     assert n > 80
 
 
+# capture / display resolution boxes: (vnum, vden, hnum, hden, vexp, hexp) -> AVCodecContext.sample_aspect_ratio
+RES_BOXES = [(300, 1, 300, 1, 0, 0), (300, 1, 150, 1, 0, 0), (72, 1, 96, 1, 2, 1), (65535, 3, 7, 65535, 9, 0), (1, 1, 1, 1, 0, 18),
+             (1, 1, 1, 1, 0, 19), (5, 0, 5, 1, 0, 0), (65535, 1, 65535, 1, 200, 3), (1000, 7, 999, 13, 3, 5),
+             (65535, 65534, 65533, 65532, 0, 12), (1, 65535, 65535, 1, 0, 0), (59, 7, 61, 11, 4, 4)]
+
+
+def res_box_file(res):
+    planes = j2kgen.synth_image(64, 48, 3, 8, seed=3)
+    return j2kgen.wrap_jp2(j2kgen.encode(planes, 8, j2kgen.EncParams(levels=2)), 64, 48, 3, 8, res=res)
+
+
+def test_sample_aspect_ratio_matches_reference():
+    """'res ' box -> s->sar through av_reduce with the reference's double arithmetic and overflow guards
+    (jpeg2000dec.c:2762-2796); published only when both terms are non-zero (:2867-2868)."""
+    seen = set()
+    for res in RES_BOXES:
+        r1, info1, out1, _ = ref_decode(res_box_file(res))
+        r2, info2, out2 = oracle_decode(res_box_file(res))
+        assert r1 == 0 and r2 == 0 and np.array_equal(out1, out2)
+        assert (info2[7] >> 32, info2[7] & 0xFFFFFFFF) == (info1[5], info1[6]), res
+        seen.add((info1[5], info1[6]))
+    assert (0, 0) in seen and (2, 1) in seen and (1, 2147483647) in seen and len(seen) >= 7
+
+
 # palettised JP2 files: (bit depth, colour space, (entries, palette depth))
 PAL8_CASES = [(8, 16, (200, 8)), (8, None, (256, 12)), (6, 16, (7, 4)), (8, 99, (256, 16)), (5, 16, (32, 1)), (8, 17, (16, 8)),
               (8, 16, (257, 8)), (1, 16, (2, 8)), (8, 18, (100, 9))]
