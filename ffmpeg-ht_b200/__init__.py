@@ -203,6 +203,27 @@ class PinnedFrame:
             pass
 
 
+class PageableFrame:
+    """A picture in ordinary (pageable) host memory -- what an AVFrame from libavcodec's default get_buffer2 is.
+    The library copies device -> pinned staging -> this memory (b200j2k_submit's note on unregistered planes)."""
+
+    def __init__(self, info: FrameInfo):
+        self.info = info
+        sizes = [info.plane_row_bytes[i] * info.plane_height[i] for i in range(info.nplanes)]
+        self.nbytes = sum(sizes)
+        self.buffer = np.zeros(max(self.nbytes, 1), np.uint8)
+        self.data = (ctypes.c_void_p * 4)()
+        self.linesize = (ctypes.c_int * 4)()
+        off = 0
+        for i in range(info.nplanes):
+            self.data[i] = self.buffer.ctypes.data + off
+            self.linesize[i] = info.plane_row_bytes[i]
+            off += sizes[i]
+
+    def close(self):
+        pass
+
+
 class DeviceFrame:
     """A picture in DEVICE memory (what an AV_PIX_FMT_CUDA frame would be): submit() writes it with a
     device-to-device copy, the pixels never cross PCIe.  download() fetches them for checking."""

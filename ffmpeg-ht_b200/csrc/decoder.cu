@@ -473,6 +473,10 @@ int finish_slot(Slot &s)
         Parser &p = s.parser;
         for (int i = 0; i < p.nplanes; i++) {
             const uint8_t *src = s.out_stage.p + p.plane_off[i];
+            if (s.dst_linesize[i] == p.plane_row_bytes[i] || p.plane_h[i] == 1) {
+                memcpy(s.dst[i], src, (size_t)p.plane_row_bytes[i] * p.plane_h[i]);
+                continue;
+            }
             for (int y = 0; y < p.plane_h[i]; y++)
                 memcpy(s.dst[i] + (size_t)y * s.dst_linesize[i], src + (size_t)y * p.plane_row_bytes[i],
                        (size_t)p.plane_row_bytes[i]);
