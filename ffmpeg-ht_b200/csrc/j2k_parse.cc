@@ -179,7 +179,17 @@ int choose_pix(Header &h, const char **name)
     static const PixDesc YUVA420P_FALLBACK = { "yuva420p", B200J2K_PIX_PLANAR8, 4, 8, 1, 1, 0 };
     if (h.precision > 16)
         return B200J2K_PIX_NONE;
-    switch (h.colour_space) {
+    const bool dcinema = h.rsiz == 3 || h.rsiz == 4;      /* AV_PROFILE_JPEG2000_DCINEMA_2K / _4K: the XYZ list, whatever
+                                                           * the colour specification says (jpeg2000dec.c:330-333) */
+    switch (dcinema ? -1 : h.colour_space) {
+    case -1:
+        /* a stream of at most 8 bits would be written with one byte per sample into the 16-bit XYZ12 frame
+         * (write_frame_8), leaving half of every row untouched: not served */
+        if (h.precision <= 8 && h.ncomp == 3)
+            return B200J2K_PIX_NONE;
+        d = first_match(XYZ_FMTS, h);
+        if (!d) d = first_match(YUV_FMTS, h);
+        break;
     case 16: d = first_match(RGB_FMTS, h); break;
     case 17: d = first_match(GRAY_FMTS, h); break;
     case 18: d = first_match(YUV_FMTS, h); break;
@@ -530,8 +540,6 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 return B200J2K_ERR_INVALIDDATA;
             if (nc > 4)
                 return B200J2K_ERR_PATCHWELCOME;
-            if (h.rsiz == 3 || h.rsiz == 4)
-                return B200J2K_ERR_PATCHWELCOME;          /* D-Cinema => XYZ12, not an HT profile */
             if (h.TX0 < 0 || h.TY0 < 0 || h.X0 < h.TX0 || h.Y0 < h.TY0 ||
                 h.TW + (int64_t)h.TX0 <= h.X0 || h.TH + (int64_t)h.TY0 <= h.Y0)
                 return B200J2K_ERR_INVALIDDATA;

@@ -116,6 +116,7 @@ typedef struct Dec {
     Tile *tile;
     int pix, out_w, out_h;
     int colour_space, pal8, cdef[4];                /* JP2 wrapper state (jp2_find_codestream) */
+    int rsiz;                                       /* avctx->profile: 3 / 4 = D-Cinema 2K / 4K */
     uint32_t palette[256];                          /* s->palette (jpeg2000dec.h:94): 0xAARRGGBB per entry */
     int sar_num, sar_den;                           /* s->sar from the 'res ' box (:2762-2796), 0/0 = none */
     int npoc;                                       /* main-header POC entries (get_poc) */
@@ -357,7 +358,15 @@ static int choose_pix(Dec *d)
     const PixDesc *f = NULL;
     if (d->precision > 16)
         return 0;
-    switch (d->colour_space) {                      /* :335-352 */
+    const int dcinema = d->rsiz == 3 || d->rsiz == 4;
+    switch (dcinema ? -1 : d->colour_space) {       /* :330-352 */
+    case -1:                                        /* D-Cinema profiles: XYZ12, then the YUV list */
+        if (d->precision <= 8 && d->ncomp == 3)     /* would be written bytewise into half of a 16-bit frame: the other
+                                                     * half is whatever the frame buffer held -- not restated */
+            return 0;
+        f = first_match(XYZ_FMTS, NELEM(XYZ_FMTS), d);
+        if (!f) f = first_match(YUV_FMTS, NELEM(YUV_FMTS), d);
+        break;
     case 16: f = first_match(RGB_FMTS, NELEM(RGB_FMTS), d); break;
     case 17: f = first_match(GRAY_FMTS, NELEM(GRAY_FMTS), d); break;
     case 18: f = first_match(YUV_FMTS, NELEM(YUV_FMTS), d); break;
@@ -624,8 +633,7 @@ static int parse_headers(Dec *d)
                 return ORACLE_ERR_INVALID;
             if (nc > 4)
                 return ORACLE_ERR_PATCH;
-            if (rsiz == 3 || rsiz == 4)
-                return ORACLE_ERR_PATCH;                  /* D-Cinema profiles -> XYZ12: outside the HT path */
+            d->rsiz = (int)rsiz;
             if (d->TX0 < 0 || d->TY0 < 0 || d->X0 < d->TX0 || d->Y0 < d->TY0 ||
                 d->TW + (int64_t)d->TX0 <= d->X0 || d->TH + (int64_t)d->TY0 <= d->Y0)
                 return ORACLE_ERR_INVALID;

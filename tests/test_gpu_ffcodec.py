@@ -76,8 +76,9 @@ def test_ffcodec_shim_jp2_and_subsampled():
         planes = j2kgen.synth_image(160, 90, nc, bd, seed=8)
         cs = j2kgen.encode(planes, bd, j2kgen.EncParams(levels=3, mct=nc >= 3))
         cases += [j2kgen.wrap_jp2(cs, 160, 90, nc, bd, colour_space=csp) for csp in (16, 17, 18)]
-    from test_oracle_vs_ref import PAL8_CASES, pal8_file
+    from test_oracle_vs_ref import PAL8_CASES, dcinema_cases, pal8_file
     cases += [pal8_file(bd, csp, pal)[0] for bd, csp, pal in PAL8_CASES]       # AV_PIX_FMT_PAL8: data[1] = palette
+    cases += [cs for name, cs in dcinema_cases() if "x8" not in name and "8-bit" not in name]     # XYZ12 and friends
     n = 0
     for data in cases:
         r1, i1, o1, _ = ref_decode(data)

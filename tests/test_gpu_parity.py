@@ -12,7 +12,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import GOLDEN, ht_block, oracle, oracle_decode
-from test_oracle_vs_ref import (part1_styled_streams, PAL8_CASES, pal8_file, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+from test_oracle_vs_ref import (dcinema_cases, part1_styled_streams, PAL8_CASES, pal8_file, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
                                 TILE_STYLES, packed_stream, part1_stream, poc_stream, tile_part_stream,
                                 tile_style_marker_cases, tile_style_stream,
                                 subsampled_stream)
@@ -510,6 +510,23 @@ def test_subsampled_and_jp2_frames_vs_oracle(name, subs, bd, dec, dec_bitexact):
                 info, got = (dec_bitexact if bitexact else dec).decode(data)
                 assert (info.width, info.height, info.pix_name) == (oinfo[0], oinfo[1], oracle_pix_name())
                 assert np.array_equal(got, want), (name, w, h, bitexact)
+
+
+def test_dcinema_profile_frames_vs_oracle(dec):
+    """Rsiz 3 / 4: XYZ12 (packed like RGB48) or the planar YUV formats of the XYZ list."""
+    from helpers import oracle_pix_name
+    n = 0
+    for name, cs in dcinema_cases():
+        r, oinfo, want = oracle_decode(cs, 0)
+        if r == 0:
+            info, got = dec.decode(cs)
+            assert info.pix_name == oracle_pix_name() and np.array_equal(got, want), name
+            n += 1
+        else:
+            with pytest.raises(fb.DecodeError) as e:
+                dec.decode(cs)
+            assert e.value.code == r, name
+    assert n >= 18
 
 
 def test_part1_styled_frames_vs_oracle(dec):

@@ -11,7 +11,7 @@ import pytest
 import ffmpeg_ht_b200 as fb
 import j2kgen
 from helpers import ht_block, mq_block, oracle, oracle_decode, oracle_pix_name
-from test_oracle_vs_ref import (RES_BOXES, res_box_file, part1_styled_streams, PAL8_CASES, pal8_file, psot_bound_cases, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
+from test_oracle_vs_ref import (dcinema_cases, RES_BOXES, res_box_file, part1_styled_streams, PAL8_CASES, pal8_file, psot_bound_cases, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
                                 TILE_STYLES, part1_stream, tile_part_stream, tile_style_marker_cases, tile_style_stream,
                                 packed_marker_cases, packed_stream, poc_marker_cases, poc_stream,
                                 subsampled_stream)
@@ -327,6 +327,19 @@ def test_geometry_cache_sees_tile_header_changes():
         r, _, opic = oracle_decode(cs)
         _, pic = picture_from_plan(cs, 0)
         assert r == 0 and np.array_equal(pic, opic)
+
+
+def test_plan_of_dcinema_profile_streams():
+    n = 0
+    for name, cs in dcinema_cases():
+        r, _, opic = oracle_decode(cs)
+        try:
+            info, pic = picture_from_plan(cs, 0)
+            assert r == 0 and info.pix_name == oracle_pix_name() and np.array_equal(pic, opic), name
+            n += 1
+        except fb.DecodeError as e:
+            assert e.code == r, name
+    assert n >= 18
 
 
 def test_sample_aspect_ratio_of_res_boxes():
