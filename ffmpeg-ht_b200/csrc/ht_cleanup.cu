@@ -324,11 +324,12 @@ __device__ __forceinline__ void vlc_pair_lane(VlcReader &v, MelLane &mel, const 
 }
 
 constexpr int VLC_LANES_PER_CTA = 32;
+constexpr int VLC_ACTIVE_LANES = 16;     /* blocks per warp (B200J2K_VLC_ACTIVE overrides, for experiments) */
 
 __global__ void __launch_bounds__(VLC_LANES_PER_CTA)
 ht_vlc_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order,
               const uint32_t *__restrict__ scr_off, int nblocks, const uint8_t *__restrict__ bytes,
-              uint32_t *__restrict__ scratch)
+              uint32_t *__restrict__ scratch, int active)
 {
     __shared__ uint16_t tab[2048 + 256];
     for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
@@ -339,8 +340,10 @@ ht_vlc_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ o
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         uvtab[i] = uvlc_pair_entry(i);
     __syncthreads();
-    const int gt = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gt >= nblocks)
+    /* `active` lanes of the warp own a block each, the others only helped with the tables: every lane walks its
+     * own control flow (MEL events, U-VLC cases), so the warp pays for the union of its lanes' paths */
+    const int gt = blockIdx.x * active + threadIdx.x;
+    if ((int)threadIdx.x >= active || gt >= nblocks)
         return;
     const uint32_t bi = order[gt];
     const CblkDesc d = descs[bi];
@@ -919,8 +922,13 @@ int launch_ht_cleanup(cudaStream_t stream, const CblkDesc *descs, const uint32_t
     if (after_unstuff)
         cudaEventRecord(after_unstuff, stream);
     if (n_vlc > 0) {
-        ht_vlc_kernel<<<(n_vlc + VLC_LANES_PER_CTA - 1) / VLC_LANES_PER_CTA, VLC_LANES_PER_CTA, 0, stream>>>(
-            descs, order, scr_off, n_vlc, bytes, scr);
+        static const int active = [] {
+            const char *e = getenv("B200J2K_VLC_ACTIVE");
+            const int a = e ? atoi(e) : VLC_ACTIVE_LANES;
+            return a >= 1 && a <= VLC_LANES_PER_CTA ? a : VLC_ACTIVE_LANES;
+        }();
+        ht_vlc_kernel<<<(n_vlc + active - 1) / active, VLC_LANES_PER_CTA, 0, stream>>>(
+            descs, order, scr_off, n_vlc, bytes, scr, active);
         launches++;
     }
     if (after_vlc)
