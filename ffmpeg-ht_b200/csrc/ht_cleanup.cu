@@ -22,6 +22,13 @@
  *                                          dequantised and stored as row segments
  * Blocks wider than 64 samples and blocks with SigProp / MagRef passes stay on the general kernel.
  */
+/* One warp per CTA for the warp-per-block kernels of this file: the hardware scheduler then hands out code-blocks
+ * one at a time (32 resident per SM either way), which shortens the tail of the un-stuff and MagSgn kernels --
+ * measured 4 -> 1 warps per CTA: MagSgn 89.7 -> 86.0 us, un-stuff 26.9 -> 25.2 us, kernel-only 4K 5845 -> 6000 fps
+ * (2 warps: 5908, 8 warps: 5684). */
+#ifndef B200J2K_WARPS_PER_CTA
+#define B200J2K_WARPS_PER_CTA 1
+#endif
 #include "ht_common.cuh"
 
 namespace b200j2k {

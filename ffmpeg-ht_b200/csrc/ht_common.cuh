@@ -18,7 +18,11 @@
 namespace b200j2k {
 namespace {
 
+#ifdef B200J2K_WARPS_PER_CTA                     /* tuning builds (tools/build_variant.sh) */
+constexpr int WARPS_PER_CTA = B200J2K_WARPS_PER_CTA;
+#else
 constexpr int WARPS_PER_CTA = 4;
+#endif
 constexpr int TABLE_WORDS = 1024 + 128;         /* 2 x 1024 x u16 CxtVLC + 256 x u16 U-VLC pair table */
 constexpr unsigned FULL = 0xFFFFFFFFu;
 

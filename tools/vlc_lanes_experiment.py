@@ -19,7 +19,7 @@ import ffmpeg_ht_b200 as fb  # noqa: E402
 
 torch.cuda.set_device(0)
 frames = bench.make_frames(4)
-S = 8
+S = int(os.environ.get("SLOTS", "8"))
 dec = fb.Jpeg2000Decoder(device=0, slots=S)
 for s in range(S):
     dec.stage(s, frames[s % len(frames)])
@@ -41,6 +41,6 @@ for _ in range(2):
     dec.run_staged_timed(0)
 for _ in range(10):
     st += np.array(dec.run_staged_timed(0))
-print("active", os.environ.get("B200J2K_VLC_ACTIVE", "default"), "pipelined fps %.0f" % (320 / dt),
+print("active", os.environ.get("B200J2K_VLC_ACTIVE", "default"), "slots", S, "pipelined fps %.0f" % (320 / dt),
       "stage ms", [round(float(x) / 10, 4) for x in st])
 dec.close()
