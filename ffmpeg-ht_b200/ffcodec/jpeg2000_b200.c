@@ -16,11 +16,17 @@
  *   never AVERROR(EAGAIN); one decoder context per AVCodecContext, so frame threading (one context per
  *   worker, libavcodec/pthread_frame.c:248-295) maps to one CUDA stream + staging buffers per worker.
  * Added: .close (device buffers must be released) and FF_CODEC_CAP_INIT_CLEANUP.
- * What it refuses (AVERROR_PATCHWELCOME, as the library reports): Part-1 code-blocks with mode switches (bypass,
- * restart, ...), MIXED HT sets, coding-style / progression changes in tile-part headers, PAL8 -- a build that wants
- * those keeps the native decoder registered as fallback
- * under a different name.
+ * Added: .close (device buffers must be released), FF_CODEC_CAP_INIT_CLEANUP, and a pinned frame pool: as long
+ * as the caller has not installed its own get_buffer2, the pictures come from an AVBufferPool of page-locked host
+ * memory owned by this decoder (the way libdav1d.c owns its picture pool), so the device->host copy lands in the
+ * AVFrame itself instead of going through the library's staging buffer and a 50 MB memcpy per 4K frame
+ * (private option "pinned_frames", default on).  With a caller-supplied get_buffer2 the picture is taken from
+ * ff_thread_get_buffer() as in the reference.
+ * What it refuses (AVERROR_PATCHWELCOME, as the library reports): Part-1 code-blocks with arithmetic-coding bypass or
+ * termination on each pass -- a build that wants those keeps the native decoder registered as fallback under a
+ * different name.
  */
+#include "libavutil/buffer.h"
 #include "libavutil/imgutils.h"
 #include "libavutil/opt.h"
 #include "libavutil/pixdesc.h"
@@ -37,7 +43,73 @@ typedef struct B200J2KContext {
     int device;             /* CUDA device index; -1 = round-robin over frame-thread workers */
     int reduction_factor;   /* the "lowres" private option; AVCodecContext.lowres feeds it (jpeg2000dec.c:2811-2818) */
     int flags;              /* B200J2K_FLAG_* this context decodes with */
+    int pinned_frames;      /* own the frame pool (page-locked memory) while the caller uses the default get_buffer2 */
+    AVBufferPool *pool;
+    size_t pool_size;
 } B200J2KContext;
+
+/* ---- pinned frame pool ------------------------------------------------------------------------------------ */
+static void b200j2k_pinned_free(void *opaque, uint8_t *data)
+{
+    b200j2k_host_free(data);
+}
+
+static AVBufferRef *b200j2k_pinned_alloc(size_t size)
+{
+    uint8_t *p = b200j2k_host_alloc((int64_t)size);
+    AVBufferRef *ref;
+    if (!p)
+        return NULL;
+    ref = av_buffer_create(p, size, b200j2k_pinned_free, NULL, 0);
+    if (!ref)
+        b200j2k_host_free(p);
+    return ref;
+}
+
+/* what ff_get_buffer() + avcodec_default_get_buffer2() do for a video frame (decode.c, get_buffer.c:86-125), with the
+ * one buffer of the picture taken from page-locked memory: 64-byte aligned rows, planes back to back */
+static int b200j2k_get_pinned_frame(AVCodecContext *avctx, B200J2KContext *s, AVFrame *f)
+{
+    int linesize[4], ret;
+    ptrdiff_t ls[4];
+    size_t sizes[4], total = 0;
+
+    f->width  = avctx->width;
+    f->height = avctx->height;
+    f->format = avctx->pix_fmt;
+    if ((ret = ff_decode_frame_props(avctx, f)) < 0)
+        return ret;
+    if ((ret = av_image_fill_linesizes(linesize, f->format, f->width)) < 0)
+        return ret;
+    for (int i = 0; i < 4; i++)
+        ls[i] = linesize[i] = FFALIGN(linesize[i], 64);
+    if ((ret = av_image_fill_plane_sizes(sizes, f->format, f->height, ls)) < 0)
+        return ret;
+    for (int i = 0; i < 4; i++) {
+        if (sizes[i] > SIZE_MAX / 8 - total)
+            return AVERROR(EINVAL);
+        total += sizes[i];
+    }
+    total += 64;
+    if (!s->pool || s->pool_size != total) {
+        av_buffer_pool_uninit(&s->pool);          /* buffers still referenced by frames stay alive until released */
+        s->pool = av_buffer_pool_init(total, b200j2k_pinned_alloc);
+        if (!s->pool)
+            return AVERROR(ENOMEM);
+        s->pool_size = total;
+    }
+    f->buf[0] = av_buffer_pool_get(s->pool);
+    if (!f->buf[0])
+        return AVERROR(ENOMEM);
+    if ((ret = av_image_fill_pointers(f->data, f->format, f->height, f->buf[0]->data, linesize)) < 0) {
+        av_buffer_unref(&f->buf[0]);
+        return ret;
+    }
+    for (int i = 0; i < 4; i++)
+        f->linesize[i] = linesize[i];
+    f->extended_data = f->data;
+    return 0;
+}
 
 static av_cold int b200j2k_ff_init(AVCodecContext *avctx)
 {
@@ -73,6 +145,7 @@ static av_cold int b200j2k_ff_close(AVCodecContext *avctx)
     B200J2KContext *s = avctx->priv_data;
     b200j2k_destroy(s->dec);
     s->dec = NULL;
+    av_buffer_pool_uninit(&s->pool);
     return 0;
 }
 
@@ -107,7 +180,11 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
     if (avctx->skip_frame >= AVDISCARD_ALL)
         return avpkt->size;
 
-    if ((ret = ff_thread_get_buffer(avctx, picture, 0)) < 0)
+    if (s->pinned_frames && (!avctx->get_buffer2 || avctx->get_buffer2 == avcodec_default_get_buffer2))
+        ret = b200j2k_get_pinned_frame(avctx, s, picture);
+    else
+        ret = ff_thread_get_buffer(avctx, picture, 0);
+    if (ret < 0)
         return ret;
     for (int i = 0; i < info.nplanes; i++) {
         data[i]     = picture->data[i];
@@ -129,6 +206,9 @@ static const AVOption b200j2k_options[] = {
         OFFSET(reduction_factor), AV_OPT_TYPE_INT, { .i64 = 0 }, 0, 32, VD },
     { "device", "CUDA device index (-1: spread decoder contexts over all devices)",
         OFFSET(device), AV_OPT_TYPE_INT, { .i64 = -1 }, -1, 64, VD },
+    { "pinned_frames", "Take the pictures from a pool of page-locked memory owned by the decoder unless the caller "
+                       "installed a get_buffer2",
+        OFFSET(pinned_frames), AV_OPT_TYPE_BOOL, { .i64 = 1 }, 0, 1, VD },
     { NULL },
 };
 

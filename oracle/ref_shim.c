@@ -28,7 +28,9 @@
 #include <time.h>
 
 #include "libavutil/imgutils.h"
+#include "libavutil/buffer.h"
 #include "libavutil/log.h"
+#include "libavutil/opt.h"
 #include "libavutil/mem.h"
 #include "libavutil/pixdesc.h"
 #include "libavcodec/avcodec.h"
@@ -79,6 +81,28 @@ int ff_thread_get_buffer(AVCodecContext *avctx, AVFrame *f, int flags)
     return ret < 0 ? ret : 0;
 }
 
+/* the FFCodec shim of the product owns a pinned frame pool while the caller uses the default allocator: the two
+ * generic-layer symbols that path touches */
+int avcodec_default_get_buffer2(AVCodecContext *s, AVFrame *frame, int flags)
+{
+    return ff_thread_get_buffer(s, frame, flags);
+}
+
+int ff_decode_frame_props(AVCodecContext *avctx, AVFrame *frame)
+{
+    (void)avctx;
+    frame->pts = AV_NOPTS_VALUE;
+    return 0;
+}
+
+static void release_frame(AVFrame *frame)
+{
+    if (frame->buf[0])
+        av_buffer_unref(&frame->buf[0]);          /* pool buffer (the product's shim) */
+    else if (frame->data[0])
+        av_freep(&frame->data[0]);                /* av_image_alloc of the ff_thread_get_buffer stand-in above */
+}
+
 static int serial_execute2(AVCodecContext *c,
                            int (*func)(AVCodecContext *c2, void *arg, int jobnr, int threadnr),
                            void *arg2, int *ret, int count)
@@ -118,6 +142,14 @@ static AVCodecContext *ctx_open(int bitexact)
         return NULL;
     }
     *(const AVClass **)avctx->priv_data = REF_CODEC.p.priv_class;
+    /* av_opt_set_defaults() for the integer / boolean private options (avcodec_open2 does this, avcodec.c:209-216);
+     * REF_OPT_<name>=<value> in the environment overrides one, like -<name> <value> on the ffmpeg command line */
+    for (const AVOption *o = REF_CODEC.p.priv_class ? REF_CODEC.p.priv_class->option : NULL; o && o->name; o++)
+        if (o->type == AV_OPT_TYPE_INT || o->type == AV_OPT_TYPE_BOOL) {
+            char key[64];
+            snprintf(key, sizeof(key), "REF_OPT_%s", o->name);
+            *(int *)((uint8_t *)avctx->priv_data + o->offset) = getenv(key) ? atoi(getenv(key)) : (int)o->default_val.i64;
+        }
     if (REF_CODEC.init(avctx) < 0) {
         av_free(avctx->priv_data);
         av_free(avctx);
@@ -196,8 +228,7 @@ int REF_NAME(decode)(const uint8_t *cs, int64_t len, int bitexact, int64_t *info
     } else if (ret >= 0) {
         ret = -1;
     }
-    if (frame->data[0])
-        av_freep(&frame->data[0]);
+    release_frame(frame);
     av_free(frame);
     av_free(padded);
     ctx_close(avctx);
@@ -329,21 +360,17 @@ static void *bench_worker(void *arg)
     AVCodecContext *avctx = ctx_open(j->bitexact);
     for (int r = 0; r < j->reps; r++) {
         for (int i = j->first; i < j->nframes; i += j->step) {
-            uint8_t *padded = av_mallocz(j->len[i] + AV_INPUT_BUFFER_PADDING_SIZE);
-            memcpy(padded, j->cs[i], j->len[i]);
             AVPacket pkt;
             memset(&pkt, 0, sizeof(pkt));
-            pkt.data = padded;
+            pkt.data = (uint8_t *)j->cs[i];               /* padded copies made by decode_bench, outside the timing */
             pkt.size = (int)j->len[i];
             AVFrame *frame = av_mallocz(sizeof(AVFrame));
             int got = 0;
             avctx->pix_fmt = AV_PIX_FMT_NONE;
             if (REF_CODEC.cb.decode(avctx, frame, &got, &pkt) < 0 || !got)
                 j->errors++;
-            if (frame->data[0])
-                av_freep(&frame->data[0]);
+            release_frame(frame);
             av_free(frame);
-            av_free(padded);
         }
     }
     ctx_close(avctx);
@@ -363,9 +390,15 @@ double REF_NAME(decode_bench)(const uint8_t *const *cs, const int64_t *len, int 
     struct timespec t0, t1;
     /* make sure one-time init (LUTs, log level) is outside the timed region */
     ctx_close(ctx_open(bitexact));
+    /* the packets as a demuxer hands them over: padded (AV_INPUT_BUFFER_PADDING_SIZE), allocated once */
+    uint8_t **padded = av_calloc(nframes, sizeof(*padded));
+    for (int i = 0; i < nframes; i++) {
+        padded[i] = av_mallocz(len[i] + AV_INPUT_BUFFER_PADDING_SIZE);
+        memcpy(padded[i], cs[i], len[i]);
+    }
     clock_gettime(CLOCK_MONOTONIC, &t0);
     for (int t = 0; t < threads; t++) {
-        jobs[t] = (BenchJob){ cs, len, nframes, t, threads, bitexact, reps, 0 };
+        jobs[t] = (BenchJob){ (const uint8_t *const *)padded, len, nframes, t, threads, bitexact, reps, 0 };
         pthread_create(&th[t], NULL, bench_worker, &jobs[t]);
     }
     int errors = 0;
@@ -374,6 +407,9 @@ double REF_NAME(decode_bench)(const uint8_t *const *cs, const int64_t *len, int 
         errors += jobs[t].errors;
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
+    for (int i = 0; i < nframes; i++)
+        av_free(padded[i]);
+    av_free(padded);
     if (errors)
         return -1.0;
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);

@@ -103,6 +103,23 @@ def test_ffcodec_shim_sample_aspect_ratio():
         assert (i1[5], i1[6]) == (i2[5], i2[6]), res
 
 
+def test_ffcodec_shim_frame_pool_on_and_off(monkeypatch):
+    """The shim's own pool of page-locked frames (private option pinned_frames, default on while the caller uses the
+    default get_buffer2) and the ff_thread_get_buffer() path give the same AVFrame bytes as the reference, for packed,
+    planar and palettised formats; a change of picture size re-creates the pool."""
+    from test_oracle_vs_ref import PAL8_CASES, SUBSAMPLED, pal8_file, subsampled_stream
+    cases = [pal8_file(*PAL8_CASES[0])[0], subsampled_stream(SUBSAMPLED[0][1], SUBSAMPLED[0][2], 131, 77, dict(levels=3))[0]]
+    for w, h, nc, bd in ((160, 90, 3, 12), (333, 111, 3, 12), (64, 64, 1, 16), (160, 90, 4, 8)):
+        planes = j2kgen.synth_image(w, h, nc, bd, seed=8)
+        cases.append(j2kgen.encode(planes, bd, j2kgen.EncParams(levels=3, mct=nc >= 3)))
+    for pinned in ("1", "0"):
+        monkeypatch.setenv("REF_OPT_pinned_frames", pinned)
+        for data in cases:
+            r1, i1, o1, _ = ref_decode(data)
+            r2, i2, o2 = shim_decode(data)
+            assert r1 == 0 and r2 == 0 and i1[:3] == i2[:3] and np.array_equal(o1, o2), pinned
+
+
 def test_ffcodec_shim_error_codes():
     planes = j2kgen.synth_image(64, 64, 1, 8, seed=2)
     cs = j2kgen.encode(planes, 8, j2kgen.EncParams(levels=2))
