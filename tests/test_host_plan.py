@@ -10,7 +10,7 @@ import pytest
 
 import ffmpeg_ht_b200 as fb
 import j2kgen
-from helpers import ht_block, mq_block, oracle, oracle_decode, oracle_pix_name
+from helpers import ROOT, ht_block, mq_block, oracle, oracle_decode, oracle_pix_name
 from test_oracle_vs_ref import (dcinema_cases, RES_BOXES, res_box_file, part1_styled_streams, PAL8_CASES, pal8_file, psot_bound_cases, HT_SETS, HT_SET_IDS, ht_set_damaged_streams, ht_set_stream, LAYERED, PACKED, PART1, POC_STREAMS, STREAMS, SUBSAMPLED, SUBSAMPLED_GEOMS, TILE_PARTS,
                                 TILE_STYLES, part1_stream, tile_part_stream, tile_style_marker_cases, tile_style_stream,
                                 packed_marker_cases, packed_stream, poc_marker_cases, poc_stream,
@@ -199,6 +199,24 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert L.b200j2k_version().startswith(b"b200j2k")
+
+
+def test_frame_info_layout_matches_the_header(tmp_path):
+    """The ctypes mirror of b200j2k_frame_info (what every Python caller reads) against the C header: size and the
+    offsets of the fields behind the arrays, taken from a C compiler."""
+    import ctypes
+    import subprocess
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stddef.h>\n#include <stdio.h>\n#include "b200j2k.h"\n'
+                   'int main(void) { printf("%zu %zu %zu %zu %zu\\n", sizeof(b200j2k_frame_info), '
+                   'offsetof(b200j2k_frame_info, plane_row_bytes), offsetof(b200j2k_frame_info, bytes_consumed), '
+                   'offsetof(b200j2k_frame_info, av_pix_fmt_name), offsetof(b200j2k_frame_info, sar_num)); return 0; }\n')
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)])
+    want = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    F = fb.FrameInfo
+    assert want == [ctypes.sizeof(F), F.plane_row_bytes.offset, F.bytes_consumed.offset, F.av_pix_fmt_name.offset,
+                    F.sar_num.offset]
 
 
 def test_no_device_fails_loudly():
