@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Frames per second of the FFCodec shim (oracle/_ref/libj2kb200shim.so: the shim compiled against the reference's
 headers and driven by the test harness the way libavcodec drives a decoder, one context per thread = frame threading)
-on the bench workload, with the shim's pinned frame pool on and off.   python tools/shim_throughput.py [threads]"""
+on the bench workload, with the shim's pinned frame pool on and off.   python tests/shim_throughput.py [threads]"""
 import ctypes
 import os
 import sys
