@@ -341,8 +341,6 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     if (pal8)
         memcpy(h + off_pal, p.hdr.palette, sizeof(p.hdr.palette));
     uint8_t *htail = direct_in ? h + s.off_bytes : h + off_tail;
-    if (!direct_in)
-        memcpy(h + s.off_bytes, pkt, (size_t)size);
     if (!p.extra.empty())
         memcpy(htail, p.extra.data(), p.extra.size());
     memset(htail + p.extra.size(), 0, 64);
@@ -365,7 +363,17 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
         if (e == cudaSuccess)
             e = cudaMemcpyAsync(dblob + off_tail, htail, tail, cudaMemcpyHostToDevice, s.stream);
     } else {
-        e = cudaMemcpyAsync(dblob, h, off_tail + tail, cudaMemcpyHostToDevice, s.stream);
+        /* pageable packet: copied into the pinned staging buffer piece by piece, each piece's DMA running while the
+         * next one is copied (the tables go first: they are ready) */
+        e = cudaMemcpyAsync(dblob, h, s.off_bytes, cudaMemcpyHostToDevice, s.stream);
+        const size_t piece = (size_t)4 << 20;
+        for (size_t at = 0; at < (size_t)size && e == cudaSuccess; at += piece) {
+            const size_t n = (size_t)size - at < piece ? (size_t)size - at : piece;
+            memcpy(h + s.off_bytes + at, pkt + at, n);
+            e = cudaMemcpyAsync(dblob + s.off_bytes + at, h + s.off_bytes + at, n, cudaMemcpyHostToDevice, s.stream);
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(dblob + off_tail, htail, tail, cudaMemcpyHostToDevice, s.stream);
     }
     /* PAL8: plane 1 of the picture is the palette (AVFrame.data[1], jpeg2000dec.c:2900-2901); no kernel writes it */
     if (e == cudaSuccess && pal8)
