@@ -214,6 +214,7 @@ struct Slot {
     HostBuf out_stage;      /* pinned: picture when the caller's planes are pageable */
     DevBuf d_blob, d_coefA, d_coefB, d_coefC, d_picture, d_status, d_scratch;
     HtPlan ht;
+    IdwtStreamCache *idwt_cache = nullptr;
     size_t off_scr = 0;
     /* offsets inside the blob */
     size_t off_cblk = 0, off_bands = 0, off_tcs = 0, off_groups = 0, off_order = 0, off_bytes = 0, blob_bytes = 0;
@@ -419,6 +420,10 @@ int run_kernels(Slot &s, cudaEvent_t *ev = nullptr)
     f.coefB = s.d_coefB.p;
     f.coefC = s.d_coefC.p;
     f.picture = (uint8_t *)s.d_picture.p;
+    if (!s.idwt_cache)
+        s.idwt_cache = idwt_stream_cache_create();
+    f.stream_cache = s.idwt_cache;
+    f.geom_serial = p.geom_serial;
     for (int i = 0; i < 4; i++) {
         f.plane_off[i] = p.plane_off[i];
         f.plane_row_bytes[i] = p.plane_row_bytes[i];
@@ -541,6 +546,8 @@ void b200j2k_destroy(b200j2k_decoder *d)
         s.out_stage.release();
         s.d_blob.release(); s.d_coefA.release(); s.d_coefB.release(); s.d_coefC.release();
         s.d_picture.release(); s.d_status.release(); s.d_scratch.release();
+        idwt_stream_cache_destroy(s.idwt_cache);
+        s.idwt_cache = nullptr;
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -650,8 +657,13 @@ int b200j2k_run_staged_timed(b200j2k_decoder *d, int slot, float *ms)
             return B200J2K_ERR_DEVICE;
     Slot &s = d->slots[slot];
     int r = run_kernels(s, ev);
-    if (r >= 0 && cudaStreamSynchronize(s.stream) != cudaSuccess)
+    if (r < 0)
+        fprintf(stderr, "b200j2k_run_staged_timed: launch failed (%d): %s\n", r, cudaGetErrorString(cudaGetLastError()));
+    cudaError_t se = cudaSuccess;
+    if (r >= 0 && (se = cudaStreamSynchronize(s.stream)) != cudaSuccess) {
+        fprintf(stderr, "b200j2k_run_staged_timed: CUDA error: %s\n", cudaGetErrorString(se));
         r = B200J2K_ERR_DEVICE;
+    }
     if (r >= 0)
         for (int i = 0; i < 6; i++)
             cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);

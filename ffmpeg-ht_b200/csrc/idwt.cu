@@ -432,8 +432,11 @@ int run_levels(cudaStream_t stream, const IdwtFrame &f, int max_levels, bool any
         if (max_w[j] <= 0)
             continue;
         if (fast) {
-            launches += launch_idwt_stream_level(stream, TYPE, f, j, max_w[j], max_h[j], (j & 1) ? f.coefB : f.coefC,
-                                                 (j & 1) ? f.coefC : f.coefB);
+            const int r = launch_idwt_stream_level(stream, TYPE, f, j, max_w[j], max_h[j], (j & 1) ? f.coefB : f.coefC,
+                                                   (j & 1) ? f.coefC : f.coefB);
+            if (r < 0)
+                return r;
+            launches += r;
             continue;
         }
         constexpr int LTX = Geo<TYPE>::TX;
@@ -453,6 +456,7 @@ int run_levels(cudaStream_t stream, const IdwtFrame &f, int max_levels, bool any
 int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f)
 {
     int launches = 0;
+    idwt_stream_cache_begin(f.stream_cache, f.geom_serial, f);
     /* pass 1: intermediate levels of every transform type present (host copies of the tables size the grids) */
     for (int type = 0; type < 3; type++) {
         int mw[J2K_MAX_LEVELS] = { 0 }, mh[J2K_MAX_LEVELS] = { 0 };
@@ -471,9 +475,13 @@ int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f)
                 if (j + 1 > maxlev) maxlev = j + 1;
             }
         }
-        if (type == J2K_DWT53) launches += run_levels<J2K_DWT53>(stream, f, maxlev, any, mw, mh, 0);
-        if (type == J2K_DWT97) launches += run_levels<J2K_DWT97>(stream, f, maxlev, any, mw, mh, 0);
-        if (type == J2K_DWT97_INT) launches += run_levels<J2K_DWT97_INT>(stream, f, maxlev, any, mw, mh, 0);
+        int r = 0;
+        if (type == J2K_DWT53) r = run_levels<J2K_DWT53>(stream, f, maxlev, any, mw, mh, 0);
+        if (type == J2K_DWT97) r = run_levels<J2K_DWT97>(stream, f, maxlev, any, mw, mh, 0);
+        if (type == J2K_DWT97_INT) r = run_levels<J2K_DWT97_INT>(stream, f, maxlev, any, mw, mh, 0);
+        if (r < 0)
+            return -1;
+        launches += r;
     }
     if (f.before_final)
         cudaEventRecord(f.before_final, stream);
@@ -494,7 +502,10 @@ int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f)
         }
         int snc = 0;
         if (anyg && gw > 0 && gh > 0 && idwt_stream_final_ok(f, type, &snc)) {
-            launches += launch_idwt_stream_final(stream, type, snc, f, gw, gh);
+            const int r = launch_idwt_stream_final(stream, type, snc, f, gw, gh);
+            if (r < 0)
+                return -1;
+            launches += r;
         } else if (anyg && gw > 0 && gh > 0) {
 #define LAUNCH_FINAL(T)                                                                                     \
     do {                                                                                                    \

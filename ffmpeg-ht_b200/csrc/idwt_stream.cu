@@ -8,17 +8,26 @@
  * instruction issue (60 % of issue slots, ~52 instructions per sample), not by HBM.  This kernel removes
  * the shared-memory round trips and most of the per-sample addressing:
  *   - a warp owns a strip of 32 x 2NP columns and walks down SEG output rows;
- *   - per row each lane loads NP low-pass and NP high-pass coefficients per component with ONE 128-bit
- *     (NP = 4) or 64-bit (NP = 2) load each -- the Mallat quadrants are read as coalesced row segments;
+ *   - the rows of the four Mallat quadrants reach the warp through TMA: one cp.async.bulk.tensor box copy per
+ *     quadrant and row pair (all components in one box), descriptor and coordinates in uniform registers,
+ *     completion counted by an mbarrier per stage; each lane reads its NP coefficients back with one LDS;
  *   - horizontal synthesis runs in registers, neighbours across lanes come from one shuffle per lifting
  *     step; the first and last lane of the warp are apron;
  *   - vertical synthesis is a sliding window over the rows: 2 (5/3) or 4 (9/7) state values per column
  *     stay in registers, so every coefficient is read once and no intermediate ever leaves the SM;
- *   - the last level applies RCT / ICT, level shift, clip and packs rgb48 / gray16 with 128-bit stores.
+ *   - the last level applies RCT / ICT, level shift, clip and packs rgb48 / gray16.
  * Rows before columns at every level (quirk Q7), uint32 wrap-around 5/3 arithmetic and un-contracted fp32
  * 9/7 arithmetic exactly as idwt.cu.  Geometry the fast path does not cover (odd origins, unaligned
  * strides, one-sample lines, 8-bit or planar output) stays on idwt.cu; launch_idwt_frame picks per launch.
  */
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
 #include "idwt_common.cuh"
 
 namespace b200j2k {
@@ -26,6 +35,35 @@ namespace b200j2k {
 namespace {
 
 constexpr int SWARPS = 4;                 /* warps (independent strips) per CTA */
+constexpr int MAXDOM = 4;                 /* DWT domains (tile-components / pack groups) per launch */
+
+/* One DWT domain of a streaming launch -- a tile-component (intermediate level) or a pack group (last level) --
+ * as the kernel sees it: two TMA tensor maps and the geometry, all in the kernel's PARAMETER space
+ * (__grid_constant__), so that descriptor addresses, box coordinates and the row walk live in uniform
+ * registers.  (Round 1 staged rows with 1-D cp.async.bulk from vector-register addresses: ptxas wrapped each
+ * of the twelve copies of a row pair in an ELECT / R2UR loop, 37 % of the loop's instructions.)
+ *   mapL  rank 3 (column, row, component) over the LL source: the compact buffer the previous level wrote,
+ *         or the top-left quadrant of the plane itself at the first level
+ *   mapA  rank 3 over the Mallat-layout coefficient planes; HL, LH and HH are boxes of the same map
+ * A box is one row of 32 x NP columns of every component: four copies per row pair instead of twelve. */
+struct alignas(64) StreamDom {
+    CUtensorMap mapL, mapA;
+    const uint32_t *ll;       /* LL source (border strips read it through pointers) */
+    int32_t u0, u1, v0, v1;   /* bounds of the resolution this level reconstructs */
+    int32_t W, LLstride;      /* row strides in elements: plane, LL source */
+    int32_t tma;              /* both maps were encoded (else every strip takes the pointer path) */
+    uint32_t off[3];          /* element offsets of the component planes (same in the ping-pong buffers) */
+    /* last level only */
+    int32_t out_x, out_y, rb, mct, shift;
+    int32_t cbps[3];
+    uint64_t plane_off;
+};
+struct StreamLaunch {
+    StreamDom dom[MAXDOM];
+    const uint32_t *coefA;
+    void *out;                /* intermediate level: compact ping-pong buffer; last level: the picture */
+    int32_t strips, SEG;
+};
 
 template <int NP> struct VecIO;
 template <> struct VecIO<4> {
@@ -43,19 +81,16 @@ template <> struct VecIO<2> {
     }
 };
 
-#ifndef STREAM_STAGES
-#define STREAM_STAGES 2
-#endif
 #ifndef STREAM_MINB
 #define STREAM_MINB 5
-#endif
-#ifndef STREAM_EXP
-#define STREAM_EXP 0
 #endif
 #ifndef STREAM_FILL
 #define STREAM_FILL 100                   /* percent of the one-wave capacity the grid may use */
 #endif
-constexpr int STAGES = STREAM_STAGES;     /* row pairs in flight per warp (cp.async groups) */
+#ifndef STREAM_STAGES
+#define STREAM_STAGES 2
+#endif
+constexpr int STAGES = STREAM_STAGES;     /* staging slots per warp: STAGES - 1 row pairs in flight */
 
 template <int NP> __device__ __forceinline__ void cp_async_vec(uint32_t dst, const uint32_t *src)
 {
@@ -73,16 +108,21 @@ template <> __device__ __forceinline__ void lds_vec<2>(uint32_t addr, uint32_t (
 {
     asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v[0]), "=r"(v[1]) : "r"(addr) : "memory");
 }
-/* Bulk-copy staging (interior strips).  ncu + tools/membench.cu: per-lane loads of this row pattern -- LDG or
- * cp.async alike -- are bounded by the L1 miss path (the kernel slows from 44 to 59 us when the shared-memory
- * carve-out leaves L1 small; 113 MB arrive in ~35 us), while the same rows fetched by the TMA engine with
- * cp.async.bulk arrive in ~22 us whatever the carve-out.  So lane 0 of a warp fetches the warp's 32 x NP
- * columns of each of the 4 NC row streams with ONE bulk copy per stream into the warp's private slots and
- * an mbarrier per stage counts the bytes in.  Bulk copies need 16-byte aligned addresses: with NP = 2 the
- * warp's first column sits at 8 mod 16 bytes, so the copy starts PADE = 2 elements early. */
-template <int NP> struct Bulk {
-    static constexpr int PADE = (4 - NP % 4) % 4;                         /* elements in front of lane 0's */
-    static constexpr uint32_t SLOT = 32 * NP * 4 + (PADE ? 16 : 0);       /* bytes per stream and stage */
+/* TMA staging (interior strips).  ncu + tools/membench.cu: per-lane loads of this row pattern -- LDG or
+ * cp.async alike -- are bounded by the L1 miss path (113 MB arrive in ~35 us), while the same rows fetched by
+ * the TMA engine arrive in ~22 us whatever the carve-out.  One elected lane fetches, per quadrant, the warp's
+ * 32 x NP columns of every component with ONE tensor box copy into the warp's private slots; an mbarrier per
+ * stage counts the bytes in.  Stage layout: [quadrant LL, HL, LH, HH][component][32 x NP columns]. */
+/* A box must start at a multiple of 16 bytes in its innermost dimension (a start 8 bytes off raises "illegal
+ * instruction" -- tools/tma_probe2.cu).  With NP = 2 the strip's first column sits at 2 mod 4 elements, so the
+ * box starts PADE = 2 columns early and is 4 columns wider. */
+template <int NP, int NC> struct Box {
+    static constexpr int PADE = (4 - NP % 4) % 4;                          /* columns in front of lane 0's */
+    static constexpr uint32_t BOXW = 32 * NP + (PADE ? 4 : 0);             /* columns of a box */
+    static constexpr uint32_t ROWB = BOXW * 4;                             /* bytes of one row of the strip in one band */
+    static constexpr uint32_t QSTRIDE = (NC * ROWB + 127) / 128 * 128;     /* one quadrant: NC rows, 128-byte aligned */
+    static constexpr uint32_t SSTRIDE = 4 * QSTRIDE;                       /* one stage */
+    static constexpr uint32_t TXBYTES = 4 * NC * ROWB;                     /* what the four copies of a stage deliver */
 };
 __device__ __forceinline__ void mbar_init(uint32_t bar, int count)
 {
@@ -100,49 +140,36 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+    return p != 0;
+}
+/* the coefficients are read exactly once: let them leave L2 first, the picture written here is read next
+ * (the constant is what createpolicy.fractional.L2::evict_first.b64 with fraction 1.0 returns) */
+constexpr uint64_t L2_EVICT_FIRST = 0x12F0000000000000ull;
 #ifndef STREAM_HINT
 #define STREAM_HINT 1
 #endif
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+#ifndef STREAM_ELECT
+#define STREAM_ELECT 1
+#endif
+__device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap *map, int x, int y, uint32_t bar)
 {
 #if STREAM_HINT
-    /* the coefficients are read exactly once: let them leave L2 first, the picture written here is read next */
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+                 " [%0], [%1, {%2, %3, %4}], [%5], %6;"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(0), "r"(bar), "l"(L2_EVICT_FIRST) : "memory");
 #else
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+                 " [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(0), "r"(bar) : "memory");
 #endif
 }
-/* the four row streams of one component in one statement: one elected-thread wrapper and one set of uniform
- * operands for the destination base, the size and the barrier instead of four */
-template <uint32_t STRIDE>
-__device__ __forceinline__ void bulk_g2s_x4(uint32_t dst, const void *s0, const void *s1, const void *s2, const void *s3, uint32_t bar)
-{
-#if STREAM_HINT
-    uint64_t pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %5, [%6], %7;\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0+%5], [%2], %5, [%6], %7;\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0+%8], [%3], %5, [%6], %7;\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0+%9], [%4], %5, [%6], %7;"
-        ::"r"(dst), "l"(s0), "l"(s1), "l"(s2), "l"(s3), "n"(STRIDE), "r"(bar), "l"(pol), "n"(2 * STRIDE), "n"(3 * STRIDE) : "memory");
-#else
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %5, [%6];\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0+%5], [%2], %5, [%6];\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0+%7], [%3], %5, [%6];\n"
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0+%8], [%4], %5, [%6];"
-        ::"r"(dst), "l"(s0), "l"(s1), "l"(s2), "l"(s3), "n"(STRIDE), "r"(bar), "n"(2 * STRIDE), "n"(3 * STRIDE) : "memory");
-#endif
-}
-/* bytes of staging shared memory per warp (the bulk layout is the larger one; border strips use per-lane
- * cp.async slots inside the same region), and of the CTA: SWARPS regions + two mbarriers per warp */
-template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_warp() { return STAGES * 4 * NC * (int)Bulk<NP>::SLOT; }
-template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_cta() { return SWARPS * stage_bytes_per_warp<NP, NC>() + SWARPS * STAGES * 8; }
+/* bytes of staging shared memory per warp and per CTA (one 128-byte line of mbarriers in front) */
+template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_warp() { return STAGES * (int)Box<NP, NC>::SSTRIDE; }
+template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_cta() { return 128 + SWARPS * stage_bytes_per_warp<NP, NC>(); }
 
 /* horizontal synthesis of NP (low, high) pairs per lane; x[2k] = even sample, x[2k+1] = odd sample */
 template <int TYPE, int NP>
@@ -192,19 +219,18 @@ struct StripGeo {
     int eoffv, ooffv;   /* ceil(v0/2), floor(v0/2) */
 };
 
-__device__ __forceinline__ StripGeo make_geo(const TileCompDesc &tc, int j)
+__device__ __forceinline__ StripGeo make_geo(const StreamDom &d)
 {
-    const LevelDesc o = tc.lev[j + 1];
     StripGeo g;
-    g.u0 = o.u0; g.u1 = o.u1; g.v0 = o.v0; g.v1 = o.v1;
-    g.nLh = ((o.u1 + 1) >> 1) - ((o.u0 + 1) >> 1);
-    g.nLv = ((o.v1 + 1) >> 1) - ((o.v0 + 1) >> 1);
-    g.W = tc.width;
-    g.LLstride = j == 0 ? tc.width : g.nLh;
-    g.eoff = (o.u0 + 1) >> 1;
-    g.ooff = o.u0 >> 1;
-    g.eoffv = (o.v0 + 1) >> 1;
-    g.ooffv = o.v0 >> 1;
+    g.u0 = d.u0; g.u1 = d.u1; g.v0 = d.v0; g.v1 = d.v1;
+    g.nLh = ((d.u1 + 1) >> 1) - ((d.u0 + 1) >> 1);
+    g.nLv = ((d.v1 + 1) >> 1) - ((d.v0 + 1) >> 1);
+    g.W = d.W;
+    g.LLstride = d.LLstride;
+    g.eoff = (d.u0 + 1) >> 1;
+    g.ooff = d.u0 >> 1;
+    g.eoffv = (d.v0 + 1) >> 1;
+    g.ooffv = d.v0 >> 1;
     return g;
 }
 
@@ -272,35 +298,38 @@ template <int TYPE, int NC, int C2> struct VState {
     uint32_t e2[TYPE == J2K_DWT53 ? 1 : NC][TYPE == J2K_DWT53 ? 1 : C2];
 };
 
-/* band_index of the (reflected) absolute row Y */
+/* band_index of the (reflected) absolute row Y.  Only the first and last row pairs of a plane come here, at most
+ * HALO + 1 rows outside [v0, v1) with v1 - v0 >= 2 (level_streamable): folding back and forth gives what
+ * reflect() computes with an integer division, in a fraction of the code */
 __device__ __forceinline__ int row_ky(const StripGeo &g, int Y)
 {
-    const int Yr = (Y >= g.v0 && Y < g.v1) ? Y : reflect(Y, g.v0, g.v1);
-    return band_index(Yr, g.v0);
+    while (Y < g.v0 || Y >= g.v1)
+        Y = Y < g.v0 ? 2 * g.v0 - Y : 2 * (g.v1 - 1) - Y;
+    return band_index(Y, g.v0);
 }
 
 /* The streaming core: walks row pairs (even row = vertical low-pass, odd row = vertical high-pass), keeps the
  * vertical lifting state in registers and calls emit(allin, Y, rows[NC][2NP]) for every finished output row.
  * The loop is unrolled by two with the state ping-ponging between two register sets, so the sliding window
  * never costs a register move, and the staging slot of a step is a compile-time constant (STAGES == 2).
- * ALLIN: every lane of the warp lies inside the line (no column needs reflection) -- the common case, kept
- * free of per-lane branches; the other instantiation serves the first and last strip of a line.
- * Addressing (ncu: the first version spent ~190 of its ~700 instructions per row pair re-deriving twelve
- * 64-bit addresses): the lane keeps one pointer per component into the LL source and one into the plane
- * (at its column of the HL band); a row pair contributes four element offsets shared by all components. */
+ * ALLIN: every lane of the warp lies inside the line (no column needs reflection) -- the common case, fed by
+ * TMA and free of per-lane branches; the other instantiation serves the first and last strip of a line with
+ * per-lane cp.async / synchronous loads through pointers.
+ * cs: the strip's first column inside the bands -- warp-uniform, like Ya / Yb and everything derived from them,
+ * so the box coordinates of the TMA copies are computed on the uniform datapath. */
 template <int TYPE, int NP, int NC, bool ALLIN, class Emit>
-__device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *__restrict__ baseA,
-                                            const uint32_t *__restrict__ baseL, const uint32_t (&offA)[NC],
-                                            const uint32_t (&offL)[NC], const LaneCols<NP> &lc, int Ya, int Yb,
-                                            uint32_t warp_base, uint32_t bar_base, Emit &&emit)
+__device__ __forceinline__ void stream_rows(const StreamDom &D, const StripGeo &g, const uint32_t *__restrict__ baseA,
+                                            const LaneCols<NP> &lc, int cs, int Ya, int Yb, uint32_t warp_base,
+                                            uint32_t bar_base, Emit &&emit)
 {
     using L = Lift<TYPE>;
     constexpr int HP = L::HALO / 2;
     constexpr int C2 = 2 * NP;
-    constexpr int NV = 4 * NC;
-    constexpr uint32_t VSTRIDE = ALLIN ? Bulk<NP>::SLOT : 32 * NP * 4, SSTRIDE = NV * VSTRIDE;
-    constexpr int PADE = Bulk<NP>::PADE;
+    using B = Box<NP, NC>;
+    constexpr uint32_t ROWB = B::ROWB, QSTRIDE = B::QSTRIDE, SSTRIDE = B::SSTRIDE;
+    constexpr int PADE = B::PADE;
     const int lane = threadIdx.x & 31;
+    const uint32_t *__restrict__ baseL = D.ll;
     VState<TYPE, NC, C2> S0, S1;
 #pragma unroll
     for (int c = 0; c < NC; c++)
@@ -313,21 +342,20 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *_
     const int n0 = (Ya >> 1) - HP, n1 = (Yb >> 1) + HP;     /* iterations [n0, n1) */
     const int Ylo = max(Ya, g.v0), Yhi = min(Yb, g.v1);     /* rows this warp emits */
     const bool fast = ALLIN || lc.inside;
-    /* element offsets (from the kernel-uniform bases) of the lane's first column in the LL source and in the
-     * HL band of the plane; 32-bit on purpose: twelve 64-bit lane pointers do not fit the register budget */
+    /* border strips: element offsets (from the kernel-uniform bases) of the lane's first column in the LL source
+     * and in the HL band of the plane */
     uint32_t eL[NC], eA[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        eL[c] = offL[c] + (uint32_t)lc.vcolL;
-        eA[c] = offA[c] + (uint32_t)(g.nLh + lc.vcolH);
+        eL[c] = D.off[c] + (uint32_t)lc.vcolL;
+        eA[c] = D.off[c] + (uint32_t)(g.nLh + lc.vcolH);
     }
     const uint32_t dLH = (uint32_t)(lc.vcolL - lc.vcolH - g.nLh);   /* LH column relative to the HH column */
-    /* where copies land (stage_base) and where the lane reads its NP elements of a stream back (lane_base) */
-    const uint32_t stage_base = ALLIN ? warp_base : warp_base + (uint32_t)lane * (NP * 4);
-    const uint32_t lane_base = warp_base + (uint32_t)lane * (NP * 4) + (ALLIN ? PADE * 4 : 0);
+    const uint32_t lane_off = (uint32_t)(PADE + lane * NP) * 4;           /* the lane's columns inside a staged row */
+    const uint32_t lane_base = warp_base + lane_off;
     /* Asynchronous staging, one row pair ahead, so the bytes in flight do not cost registers.  Interior
-     * strips: bulk copies by lane 0 (see Bulk<>), completion through the stage's mbarrier.  Border strips:
-     * every inside lane fills its own NV vector slots with cp.async; lanes whose columns need reflection
+     * strips: four TMA box copies by one elected lane, completion through the stage's mbarrier.  Border strips:
+     * every inside lane fills its own vector slots with cp.async; lanes whose columns need reflection
      * load synchronously when the row pair is consumed.  A lane only ever reads back its own bytes. */
     auto issue = [&](int n, uint32_t st, uint32_t bar) {
         if (n < n1 && fast) {
@@ -337,24 +365,25 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *_
                 kyE = row_ky(g, 2 * n);
                 kyO = row_ky(g, 2 * n + 1);
             }
-            const uint32_t oLL = (uint32_t)(kyE * g.LLstride), oHL = (uint32_t)(kyE * g.W);
-            const uint32_t oHH = (uint32_t)((g.nLv + kyO) * g.W), oLH = oHH + dLH;
             if (ALLIN) {
                 __syncwarp();                    /* every lane is done with the slots this refills */
-                if (lane == 0) {
-                    mbar_expect_tx(bar, NV * VSTRIDE);
-#pragma unroll
-                    for (int c = 0; c < NC; c++)
-                        bulk_g2s_x4<VSTRIDE>(st + 4 * c * VSTRIDE, baseL + (eL[c] + oLL - PADE), baseA + (eA[c] + oHL - PADE),
-                                             baseA + (eA[c] + oLH - PADE), baseA + (eA[c] + oHH - PADE), bar);
+                if (STREAM_ELECT ? elect_one() : lane == 0) {
+                    mbar_expect_tx(bar, B::TXBYTES);
+                    tma_box(st, &D.mapL, cs - PADE, kyE, bar);
+                    tma_box(st + QSTRIDE, &D.mapA, g.nLh + cs - PADE, kyE, bar);
+                    tma_box(st + 2 * QSTRIDE, &D.mapA, cs - PADE, g.nLv + kyO, bar);
+                    tma_box(st + 3 * QSTRIDE, &D.mapA, g.nLh + cs - PADE, g.nLv + kyO, bar);
                 }
             } else {
+                const uint32_t oLL = (uint32_t)(kyE * g.LLstride), oHL = (uint32_t)(kyE * g.W);
+                const uint32_t oHH = (uint32_t)((g.nLv + kyO) * g.W), oLH = oHH + dLH;
+                const uint32_t sl = st + lane_off;
 #pragma unroll
                 for (int c = 0; c < NC; c++) {
-                    cp_async_vec<NP>(st + (4 * c + 0) * VSTRIDE, baseL + (eL[c] + oLL));
-                    cp_async_vec<NP>(st + (4 * c + 1) * VSTRIDE, baseA + (eA[c] + oHL));
-                    cp_async_vec<NP>(st + (4 * c + 2) * VSTRIDE, baseA + (eA[c] + oLH));
-                    cp_async_vec<NP>(st + (4 * c + 3) * VSTRIDE, baseA + (eA[c] + oHH));
+                    cp_async_vec<NP>(sl + c * ROWB, baseL + (eL[c] + oLL));
+                    cp_async_vec<NP>(sl + QSTRIDE + c * ROWB, baseA + (eA[c] + oHL));
+                    cp_async_vec<NP>(sl + 2 * QSTRIDE + c * ROWB, baseA + (eA[c] + oLH));
+                    cp_async_vec<NP>(sl + 3 * QSTRIDE + c * ROWB, baseA + (eA[c] + oHH));
                 }
             }
         }
@@ -366,7 +395,7 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *_
     auto step = [&](int n, const VState<TYPE, NC, C2> &in, VState<TYPE, NC, C2> &out) {
         const uint32_t st = lane_base + (uint32_t)slot * SSTRIDE;
         const int prev = slot == 0 ? STAGES - 1 : slot - 1;             /* consumed by the previous step */
-        issue(n + STAGES - 1, stage_base + (uint32_t)prev * SSTRIDE, bar_base + (uint32_t)prev * 8);
+        issue(n + STAGES - 1, warp_base + (uint32_t)prev * SSTRIDE, bar_base + (uint32_t)prev * 8);
         if (ALLIN)
             mbar_wait(bar_base + (uint32_t)slot * 8, phase);
         else
@@ -379,36 +408,22 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *_
         if (fast) {
 #pragma unroll
             for (int c = 0; c < NC; c++) {
-                lds_vec<NP>(st + (4 * c + 0) * VSTRIDE, cLe[c]);
-                lds_vec<NP>(st + (4 * c + 1) * VSTRIDE, cHe[c]);
-                lds_vec<NP>(st + (4 * c + 2) * VSTRIDE, cLo[c]);
-                lds_vec<NP>(st + (4 * c + 3) * VSTRIDE, cHo[c]);
+                lds_vec<NP>(st + c * ROWB, cLe[c]);
+                lds_vec<NP>(st + QSTRIDE + c * ROWB, cHe[c]);
+                lds_vec<NP>(st + 2 * QSTRIDE + c * ROWB, cLo[c]);
+                lds_vec<NP>(st + 3 * QSTRIDE + c * ROWB, cHo[c]);
             }
         } else {
             int oL, oH;
             row_offsets(g, 2 * n, oL, oH);
 #pragma unroll
             for (int c = 0; c < NC; c++)
-                load_row<NP>(oL >= 0 ? baseL + offL[c] + oL : baseA + offA[c] + ~oL, baseA + offA[c] + oH, lc, cLe[c], cHe[c]);
+                load_row<NP>(oL >= 0 ? baseL + D.off[c] + oL : baseA + D.off[c] + ~oL, baseA + D.off[c] + oH, lc, cLe[c], cHe[c]);
             row_offsets(g, 2 * n + 1, oL, oH);
 #pragma unroll
             for (int c = 0; c < NC; c++)
-                load_row<NP>(oL >= 0 ? baseL + offL[c] + oL : baseA + offA[c] + ~oL, baseA + offA[c] + oH, lc, cLo[c], cHo[c]);
+                load_row<NP>(oL >= 0 ? baseL + D.off[c] + oL : baseA + D.off[c] + ~oL, baseA + D.off[c] + oH, lc, cLo[c], cHo[c]);
         }
-#if STREAM_EXP == 1                              /* tuning experiment: loads only */
-        {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-#pragma unroll
-                for (int k = 0; k < NP; k++)
-                    acc ^= cLe[c][k] + cHe[c][k] + cLo[c][k] + cHo[c][k];
-            out.vh[0][0] = in.vh[0][0] ^ acc;
-            if (n == n1 - 1 && out.vh[0][0] == 0x12345678u)
-                emit(ALLIN, Ylo, out.e1);
-            return;
-        }
-#endif
         uint32_t rowA[NC][C2];                   /* finished odd row 2n-(2HP-1); the even row 2n-(2HP-2) is out.e1 / out.e2 */
 #pragma unroll
         for (int c = 0; c < NC; c++) {
@@ -428,19 +443,6 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *_
                 }
             }
         }
-#if STREAM_EXP == 2                              /* tuning experiment: loads + arithmetic, no stores */
-        {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-#pragma unroll
-                for (int k = 0; k < C2; k++)
-                    acc ^= rowA[c][k];
-            if (acc == 0x12345678u && n == n1 - 1)
-                emit(ALLIN, Ylo, rowA);
-            return;
-        }
-#endif
         const int YA = 2 * n - (2 * HP - 1), YB = YA + 1;
         if (YA >= Ylo && YA < Yhi)
             emit(ALLIN, YA, rowA);
@@ -453,7 +455,7 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *_
     };
 #pragma unroll
     for (int s = 0; s < STAGES - 1; s++)
-        issue(n0 + s, stage_base + (uint32_t)s * SSTRIDE, bar_base + (uint32_t)s * 8);
+        issue(n0 + s, warp_base + (uint32_t)s * SSTRIDE, bar_base + (uint32_t)s * 8);
     int n = n0;
     for (; n + 1 < n1; n += 2) {
         step(n, S0, S1);
@@ -463,30 +465,39 @@ __device__ __forceinline__ void stream_rows(const StripGeo &g, const uint32_t *_
         step(n, S0, S1);
 }
 
+/* what a warp works on: its index inside the CTA is made provably warp-uniform with a broadcast (the compiler
+ * cannot know that threadIdx.x >> 5 is), so the strip / segment arithmetic stays in uniform registers */
+struct WarpUnit {
+    int warp, strip, seg;
+};
+__device__ __forceinline__ WarpUnit warp_unit(int strips)
+{
+    WarpUnit u;
+    u.warp = __shfl_sync(FULLMASK, (int)(threadIdx.x >> 5), 0);
+    const int unit = (int)blockIdx.x * SWARPS + u.warp;
+    u.seg = unit / strips;
+    u.strip = unit - u.seg * strips;
+    return u;
+}
+
 /* ---- intermediate level: reconstructed resolution -> compact ping-pong buffer -------------------------- */
 template <int TYPE, int NP>
 __global__ void __launch_bounds__(SWARPS * 32)
-idwt_stream_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint32_t *__restrict__ coefA,
-                         const uint32_t *__restrict__ coefIn, uint32_t *__restrict__ coefOut, int strips, int SEG)
+idwt_stream_level_kernel(const __grid_constant__ StreamLaunch P)
 {
-    extern __shared__ __align__(16) uint32_t stage_smem[];
+    extern __shared__ __align__(128) uint32_t stage_smem[];
     constexpr int C2 = 2 * NP, VALID = 30 * C2;
-    const TileCompDesc &tc = tcs[blockIdx.y];
-    if (tc.transform != TYPE || j >= tc.nlevels - 1)
-        return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int unit = blockIdx.x * SWARPS + warp;
-    const int strip = unit % strips, seg = unit / strips;
-    const StripGeo g = make_geo(tc, j);
-    const int XA = (g.u0 & ~1) + strip * VALID - C2;          /* first column of lane 0 (apron lane) */
-    const int Ya = (g.v0 & ~1) + seg * SEG, Yb = min(Ya + SEG, (g.v1 + 1) & ~1);
+    const StreamDom &D = P.dom[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const WarpUnit wu = warp_unit(P.strips);
+    const StripGeo g = make_geo(D);
+    const int XA = (g.u0 & ~1) + wu.strip * VALID - C2;       /* first column of lane 0 (apron lane) */
+    const int Ya = (g.v0 & ~1) + wu.seg * P.SEG, Yb = min(Ya + P.SEG, (g.v1 + 1) & ~1);
     if (XA + C2 >= g.u1 || Ya >= g.v1)
         return;
     const int p0 = (XA >> 1) + lane * NP;
     const LaneCols<NP> lc = make_cols<NP>(g, p0);
-    const uint32_t offA[1] = { (uint32_t)tc.coef_off }, offL[1] = { (uint32_t)tc.coef_off };
-    const uint32_t *baseL = j == 0 ? coefA : coefIn;
-    uint32_t *out = coefOut + tc.coef_off;
+    uint32_t *out = (uint32_t *)P.out + D.off[0];
     const int lh = g.u1 - g.u0;
     const int X0 = 2 * p0;
     const bool lane_ok = lane >= 1 && lane <= 30;
@@ -510,9 +521,9 @@ idwt_stream_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint
         }
     };
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(stage_smem);
-    const uint32_t bar_base = smem0 + warp * (STAGES * 8);
-    const uint32_t warp_base = smem0 + SWARPS * STAGES * 8 + warp * stage_bytes_per_warp<NP, 1>();
-    const bool allin = __all_sync(FULLMASK, lc.inside);
+    const uint32_t bar_base = smem0 + wu.warp * (STAGES * 8);
+    const uint32_t warp_base = smem0 + 128 + wu.warp * stage_bytes_per_warp<NP, 1>();
+    const bool allin = __all_sync(FULLMASK, lc.inside) && D.tma;
     if (allin && lane == 0) {
 #pragma unroll
         for (int i = 0; i < STAGES; i++)
@@ -520,63 +531,45 @@ idwt_stream_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    const int cs = (XA >> 1) - g.eoff;
     if (allin)
-        stream_rows<TYPE, NP, 1, true>(g, coefA, baseL, offA, offL, lc, Ya, Yb, warp_base, bar_base, emit);
+        stream_rows<TYPE, NP, 1, true>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
     else
-        stream_rows<TYPE, NP, 1, false>(g, coefA, baseL, offA, offL, lc, Ya, Yb, warp_base, bar_base, emit);
+        stream_rows<TYPE, NP, 1, false>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
 }
 
 /* ---- last level fused with MCT + level shift + clip + pack (packed 16-bit output) ---------------------- */
 template <int TYPE, int NP, int NC>
 __global__ void __launch_bounds__(SWARPS * 32, NP == 4 ? 2 : (TYPE == J2K_DWT53 ? STREAM_MINB : 3))
-idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *__restrict__ groups,
-                         const uint32_t *__restrict__ coefA, const uint32_t *__restrict__ coefIn0,
-                         const uint32_t *__restrict__ coefIn1, uint8_t *__restrict__ picture,
-                         uint64_t po0, uint64_t po1, uint64_t po2, uint64_t po3, int rb0, int rb1, int rb2, int rb3,
-                         int strips, int SEG)
+idwt_stream_final_kernel(const __grid_constant__ StreamLaunch P)
 {
-    extern __shared__ __align__(16) uint32_t stage_smem[];
+    extern __shared__ __align__(128) uint32_t stage_smem[];
     constexpr int C2 = 2 * NP, VALID = 30 * C2;
-    const PackGroup &gr = groups[blockIdx.y];
-    const TileCompDesc &t0 = tcs[gr.tc[0]];
-    if (t0.transform != TYPE || gr.ncomp != NC)
-        return;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int unit = blockIdx.x * SWARPS + warp;
-    const int strip = unit % strips, seg = unit / strips;
-    const int nl = t0.nlevels;
-    const StripGeo g = make_geo(t0, nl - 1);
-    const int XA = (g.u0 & ~1) + strip * VALID - C2;
-    const int Ya = (g.v0 & ~1) + seg * SEG, Yb = min(Ya + SEG, (g.v1 + 1) & ~1);
+    const StreamDom &D = P.dom[blockIdx.y];
+    const int lane = threadIdx.x & 31;
+    const WarpUnit wu = warp_unit(P.strips);
+    const StripGeo g = make_geo(D);
+    const int XA = (g.u0 & ~1) + wu.strip * VALID - C2;
+    const int Ya = (g.v0 & ~1) + wu.seg * P.SEG, Yb = min(Ya + P.SEG, (g.v1 + 1) & ~1);
     if (XA + C2 >= g.u1 || Ya >= g.v1)
         return;
     const int p0 = (XA >> 1) + lane * NP;
     const LaneCols<NP> lc = make_cols<NP>(g, p0);
-    const uint32_t *baseL = nl == 1 ? coefA : ((nl - 1) & 1) ? coefIn0 : coefIn1;
-    uint32_t offA[NC], offL[NC];
-    int cbps[NC], shift[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-        const TileCompDesc &tc = tcs[gr.tc[c]];
-        offA[c] = offL[c] = (uint32_t)tc.coef_off;
-        cbps[c] = tc.cbps;
-        shift[c] = gr.shift[c];
-    }
-    const uint64_t poff = gr.plane == 0 ? po0 : gr.plane == 1 ? po1 : gr.plane == 2 ? po2 : po3;
-    const int rb = gr.plane == 0 ? rb0 : gr.plane == 1 ? rb1 : gr.plane == 2 ? rb2 : rb3;
-    uint8_t *plane = picture + poff;
-    const int mct_on = gr.mct;
+    const int shift = D.shift;
+    const int rb = D.rb;
+    uint8_t *plane = (uint8_t *)P.out + D.plane_off;
+    const int mct_on = D.mct;
     const int X0 = 2 * p0;
     const bool lane_ok = lane >= 1 && lane <= 30;
-    const long px = (long)(t0.out_x + X0 - g.u0) * NC;       /* sample index of the lane's first pixel */
+    const long px = (long)(D.out_x + X0 - g.u0) * NC;        /* sample index of the lane's first pixel */
     int half[NC], vmax[NC];
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-        half[c] = 1 << (cbps[c] - 1);
-        vmax[c] = (1 << cbps[c]) - 1;
+        half[c] = 1 << (D.cbps[c] - 1);
+        vmax[c] = (1 << D.cbps[c]) - 1;
     }
     /* byte address of this lane's first sample in output row Y = out_base + Y * rb */
-    uint8_t *out_base = plane + ((long)t0.out_y - g.v0) * rb + 2 * px;
+    uint8_t *out_base = plane + ((long)D.out_y - g.v0) * rb + 2 * px;
     auto emit = [&](bool allin, int Y, const uint32_t (&row)[NC][C2]) {
         if (!lane_ok)
             return;
@@ -606,7 +599,7 @@ idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *
             for (int i = 0; i < NC * NP; i++) {
                 const int s0 = 2 * i, s1 = 2 * i + 1;            /* sample indices inside the lane's run */
                 /* all components share one shift on this path (idwt_stream_final_ok) */
-                w[i] = __byte_perm(pix[s0 % NC][s0 / NC], pix[s1 % NC][s1 / NC], 0x5410) << shift[0];
+                w[i] = __byte_perm(pix[s0 % NC][s0 / NC], pix[s1 % NC][s1 / NC], 0x5410) << shift;
             }
             if (NP == 4) {
                 uint4 *o = reinterpret_cast<uint4 *>(r16);
@@ -625,13 +618,13 @@ idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *
                 if (X0 + k >= g.u0 && X0 + k < g.u1)
 #pragma unroll
                     for (int c = 0; c < NC; c++)
-                        r16[k * NC + c] = (uint16_t)(pix[c][k] << shift[c]);
+                        r16[k * NC + c] = (uint16_t)(pix[c][k] << shift);
         }
     };
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(stage_smem);
-    const uint32_t bar_base = smem0 + warp * (STAGES * 8);
-    const uint32_t warp_base = smem0 + SWARPS * STAGES * 8 + warp * stage_bytes_per_warp<NP, NC>();
-    const bool allin = __all_sync(FULLMASK, lc.inside);
+    const uint32_t bar_base = smem0 + wu.warp * (STAGES * 8);
+    const uint32_t warp_base = smem0 + 128 + wu.warp * stage_bytes_per_warp<NP, NC>();
+    const bool allin = __all_sync(FULLMASK, lc.inside) && D.tma;
     if (allin && lane == 0) {
 #pragma unroll
         for (int i = 0; i < STAGES; i++)
@@ -639,10 +632,11 @@ idwt_stream_final_kernel(const TileCompDesc *__restrict__ tcs, const PackGroup *
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    const int cs = (XA >> 1) - g.eoff;
     if (allin)
-        stream_rows<TYPE, NP, NC, true>(g, coefA, baseL, offA, offL, lc, Ya, Yb, warp_base, bar_base, emit);
+        stream_rows<TYPE, NP, NC, true>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
     else
-        stream_rows<TYPE, NP, NC, false>(g, coefA, baseL, offA, offL, lc, Ya, Yb, warp_base, bar_base, emit);
+        stream_rows<TYPE, NP, NC, false>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
 }
 
 template <int TYPE> struct StreamCfg {
@@ -666,14 +660,24 @@ int pick_seg(int strips, int rows, int capacity)
     if (seg < 8) seg = 8;
     return (int)seg;
 }
-template <class K> int resident_ctas(K kernel, int smem)
-{
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SWARPS * 32, smem);
-    return sms * (per_sm > 0 ? per_sm : 1);
-}
+/* resident CTAs of a kernel on the current device (function attributes are per device, so is this cache) */
+struct PerDevice {
+    int cap[64] = { 0 };
+    template <class K> int get(K kernel, int smem)
+    {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        if (dev >= 0 && dev < 64 && cap[dev])
+            return cap[dev];
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SWARPS * 32, smem);
+        const int c = sms * (per_sm > 0 ? per_sm : 1);
+        if (dev >= 0 && dev < 64)
+            cap[dev] = c;
+        return c;
+    }
+};
 
 /* can the fast path reconstruct level j of this tile-component?  (even origin, lines longer than one
  * sample, 16-byte aligned band rows) */
@@ -692,10 +696,109 @@ bool level_streamable(const TileCompDesc &tc, int j)
     return true;
 }
 
+/* ---- host: tensor maps --------------------------------------------------------------------------------- */
+PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder()
+{
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            p = nullptr;
+        }
+        return (PFN_cuTensorMapEncodeTiled_v12000)p;
+    }();
+    return fn;
+}
+
+/* rank-3 map (column, row, component) of uint32 elements; box = one row of `boxw` columns of all components */
+bool encode_rows(CUtensorMap *m, const void *base, uint64_t cols, uint64_t rows, uint64_t nc, uint64_t row_stride_elems,
+                 uint64_t comp_stride_elems, uint32_t boxw)
+{
+    PFN_cuTensorMapEncodeTiled_v12000 enc = tensor_map_encoder();
+    if (!enc)
+        return false;
+    const cuuint64_t dims[3] = { cols, rows, nc };
+    const cuuint64_t strides[2] = { row_stride_elems * 4, (nc > 1 ? comp_stride_elems : row_stride_elems * rows) * 4 };
+    const cuuint32_t box[3] = { boxw, 1, (cuuint32_t)nc };
+    const cuuint32_t estr[3] = { 1, 1, 1 };
+    if ((strides[0] & 15) || (strides[1] & 15) || ((uintptr_t)base & 15))
+        return false;
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<void *>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+/* geometry + maps of level j of the nc tile-components tcs[0..nc) (equal geometry, equally spaced planes) */
+bool fill_dom(StreamDom &d, const TileCompDesc *const *tcs, int nc, int j, const void *coefA, const void *ll_buf, int NP)
+{
+    const TileCompDesc &t0 = *tcs[0];
+    const LevelDesc &o = t0.lev[j + 1];
+    memset(&d, 0, sizeof(d));
+    d.u0 = o.u0; d.u1 = o.u1; d.v0 = o.v0; d.v1 = o.v1;
+    d.W = t0.width;
+    const int nLh = ((o.u1 + 1) >> 1) - ((o.u0 + 1) >> 1), nLv = ((o.v1 + 1) >> 1) - ((o.v0 + 1) >> 1);
+    d.LLstride = j == 0 ? t0.width : nLh;
+    for (int c = 0; c < 3; c++)
+        d.off[c] = tcs[c < nc ? c : 0]->coef_off;
+    uint64_t cstride = 0;
+    if (nc > 1) {
+        if (tcs[1]->coef_off <= t0.coef_off)
+            return false;
+        cstride = (uint64_t)tcs[1]->coef_off - t0.coef_off;
+        for (int c = 1; c < nc; c++)
+            if ((uint64_t)tcs[c]->coef_off != t0.coef_off + (uint64_t)c * cstride)
+                return false;
+    }
+    const uint32_t *A = (const uint32_t *)coefA + t0.coef_off;
+    const uint32_t *Lb = j == 0 ? A : (const uint32_t *)ll_buf + t0.coef_off;
+    d.ll = j == 0 ? (const uint32_t *)coefA : (const uint32_t *)ll_buf;
+    const uint32_t boxw = NP == 2 ? Box<2, 1>::BOXW : Box<4, 1>::BOXW;
+    /* a line with an interior strip is at least two boxes long; shorter ones only have border strips */
+    d.tma = nLh >= (int)boxw && nLv >= 1 &&
+            encode_rows(&d.mapA, A, (uint64_t)t0.width, (uint64_t)t0.height, nc, (uint64_t)t0.width, cstride, boxw) &&
+            encode_rows(&d.mapL, Lb, (uint64_t)nLh, (uint64_t)nLv, nc, (uint64_t)d.LLstride, cstride, boxw);
+    return true;
+}
+
 }  // namespace
+
+/* What launch_idwt_frame memoises per slot: the parameter blocks (tensor maps included) of the streaming
+ * launches of one frame geometry on one set of device buffers.  Encoding a tensor map costs about a
+ * microsecond of host time and a 5-level 4K frame needs 26 of them; a sequence re-uses them frame after frame. */
+struct IdwtStreamCache {
+    struct Item {
+        StreamLaunch p;
+        dim3 grid;
+        int last;             /* last launch of the call that recorded it */
+    };
+    uint64_t serial = ~0ull;
+    const void *a = nullptr, *b = nullptr, *c = nullptr, *pic = nullptr;
+    std::vector<Item> items;
+    size_t cursor = 0;
+    bool replay = false;
+};
+IdwtStreamCache *idwt_stream_cache_create() { return new IdwtStreamCache(); }
+void idwt_stream_cache_destroy(IdwtStreamCache *c) { delete c; }
+void idwt_stream_cache_begin(IdwtStreamCache *c, uint64_t serial, const IdwtFrame &f)
+{
+    if (!c)
+        return;
+    c->replay = c->serial == serial && c->a == f.coefA && c->b == f.coefB && c->c == f.coefC && c->pic == f.picture &&
+                !c->items.empty();
+    if (!c->replay) {
+        c->items.clear();
+        c->serial = serial;
+        c->a = f.coefA; c->b = f.coefB; c->c = f.coefC; c->pic = f.picture;
+    }
+    c->cursor = 0;
+}
 
 bool idwt_stream_levels_ok(const TileCompDesc *h_tcs, int ntcs, int type)
 {
+    if (!tensor_map_encoder())
+        return false;
     for (int i = 0; i < ntcs; i++) {
         const TileCompDesc &tc = h_tcs[i];
         if (tc.transform != type)
@@ -714,6 +817,8 @@ bool idwt_stream_levels_ok(const TileCompDesc *h_tcs, int ntcs, int type)
 bool idwt_stream_final_ok(const IdwtFrame &f, int type, int *ncomp)
 {
     int nc = 0;
+    if (!tensor_map_encoder())
+        return false;
     for (int i = 0; i < f.ngroups; i++) {
         const PackGroup &g = f.h_groups[i];
         const TileCompDesc &t0 = f.h_tcs[g.tc[0]];
@@ -728,11 +833,18 @@ bool idwt_stream_final_ok(const IdwtFrame &f, int type, int *ncomp)
             const TileCompDesc &tc = f.h_tcs[g.tc[c]];
             if (g.sample_off[c] != c || tc.nlevels != t0.nlevels || !level_streamable(tc, tc.nlevels - 1))
                 return false;
-            if (g.shift[c] != g.shift[0] || tc.width != t0.width)
+            if (g.shift[c] != g.shift[0] || tc.width != t0.width || tc.height != t0.height)
                 return false;
             const LevelDesc &a = tc.lev[tc.nlevels], &b = t0.lev[t0.nlevels];
             if (a.u0 != b.u0 || a.u1 != b.u1 || a.v0 != b.v0 || a.v1 != b.v1)
                 return false;
+            /* one box covers the components: their planes must be equally spaced (they are allocated back to back) */
+            if (c > 0) {
+                const TileCompDesc &t1 = f.h_tcs[g.tc[1]];
+                if (t1.coef_off <= t0.coef_off ||
+                    (uint64_t)tc.coef_off != t0.coef_off + (uint64_t)c * ((uint64_t)t1.coef_off - t0.coef_off))
+                    return false;
+            }
         }
         if ((t0.out_x & 7) || (f.plane_row_bytes[g.plane] & 15) || (f.plane_off[g.plane] & 15))
             return false;
@@ -741,61 +853,154 @@ bool idwt_stream_final_ok(const IdwtFrame &f, int type, int *ncomp)
     return nc != 0;
 }
 
+namespace {
+
+template <class K>
+int run_items(cudaStream_t stream, K kernel, int smem, IdwtStreamCache *cache, std::vector<IdwtStreamCache::Item> &fresh)
+{
+    int launches = 0;
+    if (cache && cache->replay) {
+        /* same geometry, same buffers: the items of this call were recorded in the same order */
+        while (cache->cursor < cache->items.size()) {
+            IdwtStreamCache::Item &it = cache->items[cache->cursor++];
+            kernel<<<it.grid, SWARPS * 32, smem, stream>>>(it.p);
+            launches++;
+            if (it.last)
+                break;
+        }
+        return launches;
+    }
+    for (size_t i = 0; i < fresh.size(); i++) {
+        fresh[i].last = i + 1 == fresh.size();
+        kernel<<<fresh[i].grid, SWARPS * 32, smem, stream>>>(fresh[i].p);
+        launches++;
+        if (cache)
+            cache->items.push_back(fresh[i]);
+    }
+    return launches;
+}
+
+int cache_fail(IdwtStreamCache *cache)
+{
+    if (cache) {
+        cache->items.clear();
+        cache->serial = ~0ull;
+    }
+    return -1;
+}
+
+void finish_item(std::vector<IdwtStreamCache::Item> &fresh, IdwtStreamCache::Item &it, int nd, const IdwtFrame &f,
+                 void *out, int strips, int seg, int segs)
+{
+    it.p.coefA = (const uint32_t *)f.coefA;
+    it.p.out = out;
+    it.p.strips = strips;
+    it.p.SEG = seg;
+    it.grid = dim3((strips * segs + SWARPS - 1) / SWARPS, nd);
+    fresh.push_back(it);
+}
+
+template <int T>
+int stream_level(cudaStream_t stream, const IdwtFrame &f, int j, int max_w, int max_h, const void *in, void *out)
+{
+    constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;
+    constexpr int sm = stage_bytes_per_cta<NP, 1>();
+    static PerDevice capacity;
+    const int cap = capacity.get(idwt_stream_level_kernel<T, NP>, sm);
+    IdwtStreamCache *cache = f.stream_cache;
+    std::vector<IdwtStreamCache::Item> fresh;
+    if (!(cache && cache->replay)) {
+        const int strips = (max_w + 1 + VALID - 1) / VALID;
+        int ndom = 0;
+        for (int i = 0; i < f.ntcs; i++)
+            ndom += f.h_tcs[i].transform == T && j < f.h_tcs[i].nlevels - 1;
+        const int seg = pick_seg(strips * ndom, max_h, cap), segs = (max_h + 1 + seg - 1) / seg;
+        IdwtStreamCache::Item it;
+        memset(&it, 0, sizeof(it));
+        int nd = 0;
+        for (int i = 0; i < f.ntcs; i++) {
+            const TileCompDesc *tc = &f.h_tcs[i];
+            if (tc->transform != T || j >= tc->nlevels - 1)
+                continue;
+            if (!fill_dom(it.p.dom[nd], &tc, 1, j, f.coefA, in, NP))
+                return cache_fail(cache);
+            if (++nd == MAXDOM) {
+                finish_item(fresh, it, nd, f, out, strips, seg, segs);
+                nd = 0;
+            }
+        }
+        if (nd)
+            finish_item(fresh, it, nd, f, out, strips, seg, segs);
+    }
+    return run_items(stream, idwt_stream_level_kernel<T, NP>, sm, cache, fresh);
+}
+
+template <int T, int NC>
+int stream_final(cudaStream_t stream, const IdwtFrame &f, int max_w, int max_h)
+{
+    constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;
+    constexpr int sm = stage_bytes_per_cta<NP, NC>();
+    static PerDevice capacity;
+    const int cap = capacity.get(idwt_stream_final_kernel<T, NP, NC>, sm);
+    IdwtStreamCache *cache = f.stream_cache;
+    std::vector<IdwtStreamCache::Item> fresh;
+    if (!(cache && cache->replay)) {
+        const int strips = (max_w + 1 + VALID - 1) / VALID;
+        int ndom = 0;
+        for (int i = 0; i < f.ngroups; i++)
+            ndom += f.h_tcs[f.h_groups[i].tc[0]].transform == T;
+        const int seg = pick_seg(strips * ndom, max_h, cap), segs = (max_h + 1 + seg - 1) / seg;
+        IdwtStreamCache::Item it;
+        memset(&it, 0, sizeof(it));
+        int nd = 0;
+        for (int i = 0; i < f.ngroups; i++) {
+            const PackGroup &g = f.h_groups[i];
+            const TileCompDesc *tcs[3] = { &f.h_tcs[g.tc[0]], &f.h_tcs[g.tc[NC > 1 ? 1 : 0]], &f.h_tcs[g.tc[NC > 2 ? 2 : 0]] };
+            if (tcs[0]->transform != T)
+                continue;
+            const int nl = tcs[0]->nlevels;
+            StreamDom &d = it.p.dom[nd];
+            if (!fill_dom(d, tcs, NC, nl - 1, f.coefA, ((nl - 1) & 1) ? f.coefB : f.coefC, NP))
+                return cache_fail(cache);
+            d.out_x = tcs[0]->out_x;
+            d.out_y = tcs[0]->out_y;
+            d.rb = f.plane_row_bytes[g.plane];
+            d.plane_off = f.plane_off[g.plane];
+            d.mct = g.mct;
+            d.shift = g.shift[0];
+            for (int c = 0; c < 3; c++)
+                d.cbps[c] = tcs[c]->cbps;
+            if (++nd == MAXDOM) {
+                finish_item(fresh, it, nd, f, f.picture, strips, seg, segs);
+                nd = 0;
+            }
+        }
+        if (nd)
+            finish_item(fresh, it, nd, f, f.picture, strips, seg, segs);
+    }
+    return run_items(stream, idwt_stream_final_kernel<T, NP, NC>, sm, cache, fresh);
+}
+
+}  // namespace
+
 int launch_idwt_stream_level(cudaStream_t stream, int type, const IdwtFrame &f, int j, int max_w, int max_h,
                              const void *in, void *out)
 {
-#define LAUNCH(T)                                                                                              \
-    do {                                                                                                       \
-        constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;                                                  \
-        constexpr int sm = stage_bytes_per_cta<NP, 1>();                                                       \
-        static int capacity = 0;                                                                               \
-        if (!capacity) {                                                                                       \
-            cudaFuncSetAttribute(idwt_stream_level_kernel<T, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
-            capacity = resident_ctas(idwt_stream_level_kernel<T, NP>, sm);                                     \
-        }                                                                                                      \
-        const int strips = (max_w + 1 + VALID - 1) / VALID;                                                    \
-        const int seg = pick_seg(strips * f.ntcs, max_h, capacity), segs = (max_h + 1 + seg - 1) / seg;        \
-        dim3 grid((strips * segs + SWARPS - 1) / SWARPS, f.ntcs);                                              \
-        idwt_stream_level_kernel<T, NP><<<grid, SWARPS * 32, sm, stream>>>(                                    \
-            f.d_tcs, j, (const uint32_t *)f.coefA, (const uint32_t *)in, (uint32_t *)out, strips, seg);        \
-    } while (0)
-    if (type == J2K_DWT53) LAUNCH(J2K_DWT53);
-    else if (type == J2K_DWT97) LAUNCH(J2K_DWT97);
-    else LAUNCH(J2K_DWT97_INT);
-#undef LAUNCH
-    return 1;
+    if (type == J2K_DWT53) return stream_level<J2K_DWT53>(stream, f, j, max_w, max_h, in, out);
+    if (type == J2K_DWT97) return stream_level<J2K_DWT97>(stream, f, j, max_w, max_h, in, out);
+    return stream_level<J2K_DWT97_INT>(stream, f, j, max_w, max_h, in, out);
 }
 
 int launch_idwt_stream_final(cudaStream_t stream, int type, int ncomp, const IdwtFrame &f, int max_w, int max_h)
 {
-#define LAUNCH(T, NC)                                                                                          \
-    do {                                                                                                       \
-        constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;                                                  \
-        constexpr int sm = stage_bytes_per_cta<NP, NC>();                                                      \
-        static int capacity = 0;                                                                               \
-        if (!capacity) {                                                                                       \
-            cudaFuncSetAttribute(idwt_stream_final_kernel<T, NP, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm); \
-            capacity = resident_ctas(idwt_stream_final_kernel<T, NP, NC>, sm);                                 \
-        }                                                                                                      \
-        const int strips = (max_w + 1 + VALID - 1) / VALID;                                                    \
-        const int seg = pick_seg(strips * f.ngroups, max_h, capacity), segs = (max_h + 1 + seg - 1) / seg;     \
-        dim3 grid((strips * segs + SWARPS - 1) / SWARPS, f.ngroups);                                           \
-        idwt_stream_final_kernel<T, NP, NC><<<grid, SWARPS * 32, sm, stream>>>(                                \
-            f.d_tcs, f.d_groups, (const uint32_t *)f.coefA, (const uint32_t *)f.coefB, (const uint32_t *)f.coefC, \
-            f.picture, f.plane_off[0], f.plane_off[1], f.plane_off[2], f.plane_off[3], f.plane_row_bytes[0],   \
-            f.plane_row_bytes[1], f.plane_row_bytes[2], f.plane_row_bytes[3], strips, seg);                    \
-    } while (0)
     if (ncomp == 3) {
-        if (type == J2K_DWT53) LAUNCH(J2K_DWT53, 3);
-        else if (type == J2K_DWT97) LAUNCH(J2K_DWT97, 3);
-        else LAUNCH(J2K_DWT97_INT, 3);
-    } else {
-        if (type == J2K_DWT53) LAUNCH(J2K_DWT53, 1);
-        else if (type == J2K_DWT97) LAUNCH(J2K_DWT97, 1);
-        else LAUNCH(J2K_DWT97_INT, 1);
+        if (type == J2K_DWT53) return stream_final<J2K_DWT53, 3>(stream, f, max_w, max_h);
+        if (type == J2K_DWT97) return stream_final<J2K_DWT97, 3>(stream, f, max_w, max_h);
+        return stream_final<J2K_DWT97_INT, 3>(stream, f, max_w, max_h);
     }
-#undef LAUNCH
-    return 1;
+    if (type == J2K_DWT53) return stream_final<J2K_DWT53, 1>(stream, f, max_w, max_h);
+    if (type == J2K_DWT97) return stream_final<J2K_DWT97, 1>(stream, f, max_w, max_h);
+    return stream_final<J2K_DWT97_INT, 1>(stream, f, max_w, max_h);
 }
 
 }  // namespace b200j2k

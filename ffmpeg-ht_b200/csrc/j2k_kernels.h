@@ -54,6 +54,10 @@ static inline __host__ __device__ int mq_state_words_of(int w, int h) { return 2
 /* Inverse DWT levels + final MCT / level shift / clip / pack.
  * tcs/groups: device copies of the plan tables.  coefA: HT output (Mallat layout), coefB/coefC: LL
  * ping-pong, picture: packed output.  Returns the number of kernels queued or < 0. */
+struct IdwtStreamCache;           /* idwt_stream.cu: memoised launch parameters (tensor maps) of one geometry */
+IdwtStreamCache *idwt_stream_cache_create();
+void idwt_stream_cache_destroy(IdwtStreamCache *c);
+
 struct IdwtFrame {
     const TileCompDesc *d_tcs;    /* device */
     const PackGroup *d_groups;    /* device */
@@ -65,7 +69,10 @@ struct IdwtFrame {
     uint64_t plane_off[4];
     int plane_row_bytes[4];
     cudaEvent_t before_final;     /* optional: recorded between the level kernels and the fused last level */
+    IdwtStreamCache *stream_cache;/* optional: owned by the slot; valid while geom_serial and the buffers stay the same */
+    uint64_t geom_serial;         /* Parser::geom_serial of the tables above */
 };
+void idwt_stream_cache_begin(IdwtStreamCache *c, uint64_t serial, const IdwtFrame &f);
 int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f);
 
 /* Register-streaming fast path (idwt_stream.cu).  The *_ok functions decide on the host, per launch,
