@@ -65,22 +65,6 @@ struct StreamLaunch {
     int32_t strips, SEG;
 };
 
-template <int NP> struct VecIO;
-template <> struct VecIO<4> {
-    static __device__ __forceinline__ void load(const uint32_t *p, uint32_t (&v)[4])
-    {
-        const uint4 t = __ldg(reinterpret_cast<const uint4 *>(p));
-        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    }
-};
-template <> struct VecIO<2> {
-    static __device__ __forceinline__ void load(const uint32_t *p, uint32_t (&v)[2])
-    {
-        const uint2 t = __ldg(reinterpret_cast<const uint2 *>(p));
-        v[0] = t.x; v[1] = t.y;
-    }
-};
-
 #ifndef STREAM_MINB
 #define STREAM_MINB 5
 #endif
@@ -90,7 +74,13 @@ template <> struct VecIO<2> {
 #ifndef STREAM_STAGES
 #define STREAM_STAGES 2
 #endif
-constexpr int STAGES = STREAM_STAGES;     /* staging slots per warp: STAGES - 1 row pairs in flight */
+#ifndef STREAM_STAGES_LEVEL
+#define STREAM_STAGES_LEVEL 6
+#endif
+/* staging slots per warp (STAGES - 1 row pairs in flight).  The last level runs at full occupancy and is fastest
+ * with two; the intermediate levels are small grids whose warps walk few rows, each step a full memory latency:
+ * they keep a whole segment's rows in flight */
+constexpr int STAGES_FINAL = STREAM_STAGES, STAGES_LEVEL = STREAM_STAGES_LEVEL;
 
 template <int NP> __device__ __forceinline__ void cp_async_vec(uint32_t dst, const uint32_t *src)
 {
@@ -98,6 +88,10 @@ template <int NP> __device__ __forceinline__ void cp_async_vec(uint32_t dst, con
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
     else
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const uint32_t *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 template <int NP> __device__ __forceinline__ void lds_vec(uint32_t addr, uint32_t (&v)[NP]);
 template <> __device__ __forceinline__ void lds_vec<4>(uint32_t addr, uint32_t (&v)[4])
@@ -140,6 +134,15 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+/* Programmatic dependent launch: the kernels of a frame follow each other on one stream, each a few microseconds
+ * long.  A kernel launched with the programmatic-serialisation attribute may start while its predecessor drains;
+ * everything up to here (geometry, barrier set-up) overlaps with that tail, the first read of the predecessor's
+ * output waits for its completion.  Dependents of this kernel may be scheduled from now on. */
+__device__ __forceinline__ void pdl_prologue_done()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ bool elect_one()
 {
     uint32_t p;
@@ -168,8 +171,12 @@ __device__ __forceinline__ void tma_box(uint32_t dst, const CUtensorMap *map, in
 #endif
 }
 /* bytes of staging shared memory per warp and per CTA (one 128-byte line of mbarriers in front) */
-template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_warp() { return STAGES * (int)Box<NP, NC>::SSTRIDE; }
-template <int NP, int NC> __host__ __device__ constexpr int stage_bytes_per_cta() { return 128 + SWARPS * stage_bytes_per_warp<NP, NC>(); }
+template <int NP, int NC, int STAGES> __host__ __device__ constexpr int stage_bytes_per_warp() { return STAGES * (int)Box<NP, NC>::SSTRIDE; }
+template <int NP, int NC, int STAGES> __host__ __device__ constexpr int bar_bytes_per_cta() { return (SWARPS * STAGES * 8 + 127) / 128 * 128; }
+template <int NP, int NC, int STAGES> __host__ __device__ constexpr int stage_bytes_per_cta()
+{
+    return bar_bytes_per_cta<NP, NC, STAGES>() + SWARPS * stage_bytes_per_warp<NP, NC, STAGES>();
+}
 
 /* horizontal synthesis of NP (low, high) pairs per lane; x[2k] = even sample, x[2k+1] = odd sample */
 template <int TYPE, int NP>
@@ -234,21 +241,6 @@ __device__ __forceinline__ StripGeo make_geo(const StreamDom &d)
     return g;
 }
 
-/* element offsets of the low-pass / high-pass halves of absolute row Y: offL < 0 means ~offL into the
- * plane (LH band), else into the LL source; offH into the plane (HL or HH band) */
-__device__ __forceinline__ void row_offsets(const StripGeo &g, int Y, int &offL, int &offH)
-{
-    const int Yr = (Y >= g.v0 && Y < g.v1) ? Y : reflect(Y, g.v0, g.v1);
-    const int ky = band_index(Yr, g.v0);
-    if (Yr & 1) {
-        offL = ~((g.nLv + ky) * g.W);
-        offH = (g.nLv + ky) * g.W + g.nLh;
-    } else {
-        offL = ky * g.LLstride;
-        offH = ky * g.W + g.nLh;
-    }
-}
-
 /* per-lane column bookkeeping: fixed for all rows of the strip */
 template <int NP> struct LaneCols {
     bool inside;        /* all 2NP samples inside [u0,u1): vector loads */
@@ -273,22 +265,6 @@ __device__ __forceinline__ LaneCols<NP> make_cols(const StripGeo &g, int p0)
         lc.io[k] = (Xo >> 1) - g.ooff;
     }
     return lc;
-}
-
-template <int NP>
-__device__ __forceinline__ void load_row(const uint32_t *rowL, const uint32_t *rowH, const LaneCols<NP> &lc,
-                                         uint32_t (&Lc)[NP], uint32_t (&Hc)[NP])
-{
-    if (lc.inside) {
-        VecIO<NP>::load(rowL + lc.vcolL, Lc);
-        VecIO<NP>::load(rowH + lc.vcolH, Hc);
-    } else {
-#pragma unroll
-        for (int k = 0; k < NP; k++) {
-            Lc[k] = rowL[lc.ie[k]];
-            Hc[k] = rowH[lc.io[k]];
-        }
-    }
 }
 
 /* vertical lifting state of one lane: per component and column the values the next row pair needs */
@@ -317,7 +293,7 @@ __device__ __forceinline__ int row_ky(const StripGeo &g, int Y)
  * per-lane cp.async / synchronous loads through pointers.
  * cs: the strip's first column inside the bands -- warp-uniform, like Ya / Yb and everything derived from them,
  * so the box coordinates of the TMA copies are computed on the uniform datapath. */
-template <int TYPE, int NP, int NC, bool ALLIN, class Emit>
+template <int TYPE, int NP, int NC, int STAGES, bool ALLIN, class Emit>
 __device__ __forceinline__ void stream_rows(const StreamDom &D, const StripGeo &g, const uint32_t *__restrict__ baseA,
                                             const LaneCols<NP> &lc, int cs, int Ya, int Yb, uint32_t warp_base,
                                             uint32_t bar_base, Emit &&emit)
@@ -341,7 +317,6 @@ __device__ __forceinline__ void stream_rows(const StreamDom &D, const StripGeo &
         }
     const int n0 = (Ya >> 1) - HP, n1 = (Yb >> 1) + HP;     /* iterations [n0, n1) */
     const int Ylo = max(Ya, g.v0), Yhi = min(Yb, g.v1);     /* rows this warp emits */
-    const bool fast = ALLIN || lc.inside;
     /* border strips: element offsets (from the kernel-uniform bases) of the lane's first column in the LL source
      * and in the HL band of the plane */
     uint32_t eL[NC], eA[NC];
@@ -358,7 +333,7 @@ __device__ __forceinline__ void stream_rows(const StreamDom &D, const StripGeo &
      * every inside lane fills its own vector slots with cp.async; lanes whose columns need reflection
      * load synchronously when the row pair is consumed.  A lane only ever reads back its own bytes. */
     auto issue = [&](int n, uint32_t st, uint32_t bar) {
-        if (n < n1 && fast) {
+        if (n < n1) {
             /* band_index() of rows 2n / 2n+1 is n - ceil(v0/2) / n - floor(v0/2) unless a row needs reflection */
             int kyE = n - g.eoffv, kyO = n - g.ooffv;
             if (2 * n < g.v0 || 2 * n + 1 >= g.v1) {
@@ -378,12 +353,26 @@ __device__ __forceinline__ void stream_rows(const StreamDom &D, const StripGeo &
                 const uint32_t oLL = (uint32_t)(kyE * g.LLstride), oHL = (uint32_t)(kyE * g.W);
                 const uint32_t oHH = (uint32_t)((g.nLv + kyO) * g.W), oLH = oHH + dLH;
                 const uint32_t sl = st + lane_off;
+                if (lc.inside) {
 #pragma unroll
-                for (int c = 0; c < NC; c++) {
-                    cp_async_vec<NP>(sl + c * ROWB, baseL + (eL[c] + oLL));
-                    cp_async_vec<NP>(sl + QSTRIDE + c * ROWB, baseA + (eA[c] + oHL));
-                    cp_async_vec<NP>(sl + 2 * QSTRIDE + c * ROWB, baseA + (eA[c] + oLH));
-                    cp_async_vec<NP>(sl + 3 * QSTRIDE + c * ROWB, baseA + (eA[c] + oHH));
+                    for (int c = 0; c < NC; c++) {
+                        cp_async_vec<NP>(sl + c * ROWB, baseL + (eL[c] + oLL));
+                        cp_async_vec<NP>(sl + QSTRIDE + c * ROWB, baseA + (eA[c] + oHL));
+                        cp_async_vec<NP>(sl + 2 * QSTRIDE + c * ROWB, baseA + (eA[c] + oLH));
+                        cp_async_vec<NP>(sl + 3 * QSTRIDE + c * ROWB, baseA + (eA[c] + oHH));
+                    }
+                } else {
+                    /* columns that need reflection: element by element, still asynchronous */
+                    const uint32_t rHL = oHL + (uint32_t)g.nLh, rLH = oHH, rHH = oHH + (uint32_t)g.nLh;
+#pragma unroll
+                    for (int c = 0; c < NC; c++)
+#pragma unroll
+                        for (int k = 0; k < NP; k++) {
+                            cp_async_4(sl + c * ROWB + 4 * k, baseL + (D.off[c] + oLL + (uint32_t)lc.ie[k]));
+                            cp_async_4(sl + QSTRIDE + c * ROWB + 4 * k, baseA + (D.off[c] + rHL + (uint32_t)lc.io[k]));
+                            cp_async_4(sl + 2 * QSTRIDE + c * ROWB + 4 * k, baseA + (D.off[c] + rLH + (uint32_t)lc.ie[k]));
+                            cp_async_4(sl + 3 * QSTRIDE + c * ROWB + 4 * k, baseA + (D.off[c] + rHH + (uint32_t)lc.io[k]));
+                        }
                 }
             }
         }
@@ -405,24 +394,12 @@ __device__ __forceinline__ void stream_rows(const StreamDom &D, const StripGeo &
             phase ^= 1;
         }
         uint32_t cLe[NC][NP], cHe[NC][NP], cLo[NC][NP], cHo[NC][NP];
-        if (fast) {
 #pragma unroll
-            for (int c = 0; c < NC; c++) {
-                lds_vec<NP>(st + c * ROWB, cLe[c]);
-                lds_vec<NP>(st + QSTRIDE + c * ROWB, cHe[c]);
-                lds_vec<NP>(st + 2 * QSTRIDE + c * ROWB, cLo[c]);
-                lds_vec<NP>(st + 3 * QSTRIDE + c * ROWB, cHo[c]);
-            }
-        } else {
-            int oL, oH;
-            row_offsets(g, 2 * n, oL, oH);
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-                load_row<NP>(oL >= 0 ? baseL + D.off[c] + oL : baseA + D.off[c] + ~oL, baseA + D.off[c] + oH, lc, cLe[c], cHe[c]);
-            row_offsets(g, 2 * n + 1, oL, oH);
-#pragma unroll
-            for (int c = 0; c < NC; c++)
-                load_row<NP>(oL >= 0 ? baseL + D.off[c] + oL : baseA + D.off[c] + ~oL, baseA + D.off[c] + oH, lc, cLo[c], cHo[c]);
+        for (int c = 0; c < NC; c++) {
+            lds_vec<NP>(st + c * ROWB, cLe[c]);
+            lds_vec<NP>(st + QSTRIDE + c * ROWB, cHe[c]);
+            lds_vec<NP>(st + 2 * QSTRIDE + c * ROWB, cLo[c]);
+            lds_vec<NP>(st + 3 * QSTRIDE + c * ROWB, cHo[c]);
         }
         uint32_t rowA[NC][C2];                   /* finished odd row 2n-(2HP-1); the even row 2n-(2HP-2) is out.e1 / out.e2 */
 #pragma unroll
@@ -521,8 +498,9 @@ idwt_stream_level_kernel(const __grid_constant__ StreamLaunch P)
         }
     };
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(stage_smem);
+    constexpr int STAGES = STAGES_LEVEL;
     const uint32_t bar_base = smem0 + wu.warp * (STAGES * 8);
-    const uint32_t warp_base = smem0 + 128 + wu.warp * stage_bytes_per_warp<NP, 1>();
+    const uint32_t warp_base = smem0 + bar_bytes_per_cta<NP, 1, STAGES>() + wu.warp * stage_bytes_per_warp<NP, 1, STAGES>();
     const bool allin = __all_sync(FULLMASK, lc.inside) && D.tma;
     if (allin && lane == 0) {
 #pragma unroll
@@ -531,11 +509,12 @@ idwt_stream_level_kernel(const __grid_constant__ StreamLaunch P)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    pdl_prologue_done();
     const int cs = (XA >> 1) - g.eoff;
     if (allin)
-        stream_rows<TYPE, NP, 1, true>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
+        stream_rows<TYPE, NP, 1, STAGES, true>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
     else
-        stream_rows<TYPE, NP, 1, false>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
+        stream_rows<TYPE, NP, 1, STAGES, false>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
 }
 
 /* ---- last level fused with MCT + level shift + clip + pack (packed 16-bit output) ---------------------- */
@@ -622,8 +601,9 @@ idwt_stream_final_kernel(const __grid_constant__ StreamLaunch P)
         }
     };
     const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(stage_smem);
+    constexpr int STAGES = STAGES_FINAL;
     const uint32_t bar_base = smem0 + wu.warp * (STAGES * 8);
-    const uint32_t warp_base = smem0 + 128 + wu.warp * stage_bytes_per_warp<NP, NC>();
+    const uint32_t warp_base = smem0 + bar_bytes_per_cta<NP, NC, STAGES>() + wu.warp * stage_bytes_per_warp<NP, NC, STAGES>();
     const bool allin = __all_sync(FULLMASK, lc.inside) && D.tma;
     if (allin && lane == 0) {
 #pragma unroll
@@ -632,11 +612,12 @@ idwt_stream_final_kernel(const __grid_constant__ StreamLaunch P)
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
+    pdl_prologue_done();
     const int cs = (XA >> 1) - g.eoff;
     if (allin)
-        stream_rows<TYPE, NP, NC, true>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
+        stream_rows<TYPE, NP, NC, STAGES, true>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
     else
-        stream_rows<TYPE, NP, NC, false>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
+        stream_rows<TYPE, NP, NC, STAGES, false>(D, g, P.coefA, lc, cs, Ya, Yb, warp_base, bar_base, emit);
 }
 
 template <int TYPE> struct StreamCfg {
@@ -855,6 +836,22 @@ bool idwt_stream_final_ok(const IdwtFrame &f, int type, int *ncomp)
 
 namespace {
 
+template <class K> void launch_item(cudaStream_t stream, K kernel, int smem, const IdwtStreamCache::Item &it)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = it.grid;
+    cfg.blockDim = dim3(SWARPS * 32);
+    cfg.dynamicSmemBytes = (size_t)smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, it.p);
+}
+
 template <class K>
 int run_items(cudaStream_t stream, K kernel, int smem, IdwtStreamCache *cache, std::vector<IdwtStreamCache::Item> &fresh)
 {
@@ -863,7 +860,7 @@ int run_items(cudaStream_t stream, K kernel, int smem, IdwtStreamCache *cache, s
         /* same geometry, same buffers: the items of this call were recorded in the same order */
         while (cache->cursor < cache->items.size()) {
             IdwtStreamCache::Item &it = cache->items[cache->cursor++];
-            kernel<<<it.grid, SWARPS * 32, smem, stream>>>(it.p);
+            launch_item(stream, kernel, smem, it);
             launches++;
             if (it.last)
                 break;
@@ -872,7 +869,7 @@ int run_items(cudaStream_t stream, K kernel, int smem, IdwtStreamCache *cache, s
     }
     for (size_t i = 0; i < fresh.size(); i++) {
         fresh[i].last = i + 1 == fresh.size();
-        kernel<<<fresh[i].grid, SWARPS * 32, smem, stream>>>(fresh[i].p);
+        launch_item(stream, kernel, smem, fresh[i]);
         launches++;
         if (cache)
             cache->items.push_back(fresh[i]);
@@ -904,7 +901,7 @@ template <int T>
 int stream_level(cudaStream_t stream, const IdwtFrame &f, int j, int max_w, int max_h, const void *in, void *out)
 {
     constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;
-    constexpr int sm = stage_bytes_per_cta<NP, 1>();
+    constexpr int sm = stage_bytes_per_cta<NP, 1, STAGES_LEVEL>();
     static PerDevice capacity;
     const int cap = capacity.get(idwt_stream_level_kernel<T, NP>, sm);
     IdwtStreamCache *cache = f.stream_cache;
@@ -939,7 +936,7 @@ template <int T, int NC>
 int stream_final(cudaStream_t stream, const IdwtFrame &f, int max_w, int max_h)
 {
     constexpr int NP = StreamCfg<T>::NP, VALID = 60 * NP;
-    constexpr int sm = stage_bytes_per_cta<NP, NC>();
+    constexpr int sm = stage_bytes_per_cta<NP, NC, STAGES_FINAL>();
     static PerDevice capacity;
     const int cap = capacity.get(idwt_stream_final_kernel<T, NP, NC>, sm);
     IdwtStreamCache *cache = f.stream_cache;
