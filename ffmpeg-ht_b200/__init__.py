@@ -39,7 +39,8 @@ class FrameInfo(ctypes.Structure):
                 ("plane_width", ctypes.c_int32 * 4), ("plane_height", ctypes.c_int32 * 4),
                 ("plane_row_bytes", ctypes.c_int32 * 4), ("ntiles", ctypes.c_int32),
                 ("ncodeblocks", ctypes.c_int32), ("bytes_consumed", ctypes.c_int64),
-                ("av_pix_fmt_name", ctypes.c_char * 16), ("sar_num", ctypes.c_int32), ("sar_den", ctypes.c_int32)]
+                ("av_pix_fmt_name", ctypes.c_char * 16), ("sar_num", ctypes.c_int32), ("sar_den", ctypes.c_int32),
+                ("nblocks_failed", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
     @property
     def pix_name(self) -> str:
@@ -95,6 +96,7 @@ def lib():
         L.b200j2k_slot_output.argtypes = [vp, i32, ctypes.POINTER(i64)]
         L.b200j2k_slot_output.restype = vp
         L.b200j2k_slot_launches.argtypes = [vp, i32]
+        L.b200j2k_slot_blocks_failed.argtypes = [vp, i32]
         L.b200j2k_slot_h2d_bytes.argtypes = [vp, i32]
         L.b200j2k_slot_h2d_bytes.restype = i64
         L.b200j2k_ht_blocks.argtypes = [i32, vp, i64, vp, i32, vp, vp]
@@ -130,7 +132,7 @@ def lib():
 EXPORTS = ["b200j2k_device_count", "b200j2k_create", "b200j2k_destroy", "b200j2k_probe", "b200j2k_submit",
            "b200j2k_wait", "b200j2k_decode", "b200j2k_stage", "b200j2k_run_staged", "b200j2k_run_staged_timed",
            "b200j2k_sync",
-           "b200j2k_fetch", "b200j2k_slot_stream", "b200j2k_slot_output", "b200j2k_slot_launches",
+           "b200j2k_fetch", "b200j2k_slot_stream", "b200j2k_slot_output", "b200j2k_slot_launches", "b200j2k_slot_blocks_failed",
            "b200j2k_slot_h2d_bytes",
            "b200j2k_ht_blocks", "b200j2k_idwt", "b200j2k_host_alloc", "b200j2k_host_free",
            "b200j2k_host_register", "b200j2k_host_unregister", "b200j2k_device_alloc", "b200j2k_device_free",
@@ -406,6 +408,10 @@ class Jpeg2000Decoder:
 
     def launches(self, slot: int) -> int:
         return int(lib().b200j2k_slot_launches(self._h, slot))
+
+    def blocks_failed(self, slot: int) -> int:
+        """After wait(): code-blocks of the slot's frame the kernels zero-filled because their data was damaged."""
+        return int(lib().b200j2k_slot_blocks_failed(self._h, slot))
 
 
 # -- stage-level entry points (parity tests) ---------------------------------------------------------

@@ -219,6 +219,7 @@ struct Slot {
     /* offsets inside the blob */
     size_t off_cblk = 0, off_bands = 0, off_tcs = 0, off_groups = 0, off_order = 0, off_bytes = 0, blob_bytes = 0;
     bool busy = false, staged = false;
+    int32_t *h_failed = nullptr;   /* pinned: status[-1] of the last frame (blocks zero-filled for damaged data) */
     size_t h2d_bytes = 0;
     int launches = 0;
     /* pending output */
@@ -353,7 +354,7 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
         if ((ret = s.d_coefC.ensure(p.ll_elems * 4 + 256)) < 0) return ret;
     }
     if ((ret = s.d_picture.ensure(p.picture_bytes + 256)) < 0) return ret;
-    if ((ret = s.d_status.ensure(ncb * 4 + 256)) < 0) return ret;
+    if ((ret = s.d_status.ensure(ncb * 4 + 256 + 16)) < 0) return ret;     /* 16 bytes in front: the failure counter */
     if ((ret = s.d_scratch.ensure(s.ht.scratch_words * 4 + 256)) < 0) return ret;
     uint8_t *dblob = (uint8_t *)s.d_blob.p;
     cudaError_t e;
@@ -401,9 +402,11 @@ int run_kernels(Slot &s, cudaEvent_t *ev = nullptr)
     const uint32_t *d_order = (const uint32_t *)(blob + s.off_order);
     const uint8_t *d_bytes = blob + s.off_bytes;
     int launches = 0, r;
+    if (cudaMemsetAsync((int32_t *)s.d_status.p + 3, 0, 4, s.stream) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
     if (ev) cudaEventRecord(ev[0], s.stream);
     r = run_ht(s.stream, s.ht, d_cblk, d_order, (const uint32_t *)(blob + s.off_scr), d_bytes, d_bands, s.d_scratch.p,
-               s.d_coefA.p, (int32_t *)s.d_status.p, (int)p.max_w, (int)p.max_area, (int)p.max_state, ev);
+               s.d_coefA.p, (int32_t *)s.d_status.p + 4, (int)p.max_w, (int)p.max_area, (int)p.max_state, ev);
     if (r < 0) return B200J2K_ERR_DEVICE;
     launches += r;
     if (ev) cudaEventRecord(ev[4], s.stream);
@@ -440,6 +443,13 @@ int queue_output(Slot &s, uint8_t *const data[4], const int linesize[4])
 {
     Parser &p = s.parser;
     bool direct = true;
+    if (!s.h_failed && cudaHostAlloc((void **)&s.h_failed, 16, cudaHostAllocDefault) != cudaSuccess) {
+        cudaGetLastError();
+        s.h_failed = nullptr;
+        return B200J2K_ERR_NOMEM;
+    }
+    if (cudaMemcpyAsync(s.h_failed, (int32_t *)s.d_status.p + 3, 4, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
     for (int i = 0; i < p.nplanes; i++) {
         if (!data[i] || (linesize[i] < p.plane_row_bytes[i] && p.plane_h[i] > 1))   /* a one-row plane (palette)
                                                                                      * has no meaningful linesize */
@@ -544,6 +554,9 @@ void b200j2k_destroy(b200j2k_decoder *d)
             cudaStreamSynchronize(s.stream);
         s.stage.release();
         s.out_stage.release();
+        if (s.h_failed)
+            cudaFreeHost(s.h_failed);
+        s.h_failed = nullptr;
         s.d_blob.release(); s.d_coefA.release(); s.d_coefB.release(); s.d_coefC.release();
         s.d_picture.release(); s.d_status.release(); s.d_scratch.release();
         idwt_stream_cache_destroy(s.idwt_cache);
@@ -585,12 +598,16 @@ int b200j2k_submit(b200j2k_decoder *d, const uint8_t *pkt, int64_t pkt_size, uin
     }
     Slot &s = d->slots[pick];
     int ret = stage_frame(d, s, pkt, pkt_size, info);
-    if (ret < 0)
+    if (ret >= 0 && (ret = run_kernels(s)) >= 0)
+        ret = queue_output(s, data, linesize);
+    if (ret < 0) {
+        /* copies from the caller's packet or from the staging buffer may be in flight: nobody may touch or
+         * free either before the stream has drained */
+        if (cudaStreamSynchronize(s.stream) != cudaSuccess)
+            cudaGetLastError();
+        s.staged = false;
         return ret;
-    if ((ret = run_kernels(s)) < 0)
-        return ret;
-    if ((ret = queue_output(s, data, linesize)) < 0)
-        return ret;
+    }
     s.busy = true;
     s.seq = ++d->seq;
     return pick;
@@ -615,6 +632,7 @@ int64_t b200j2k_decode(b200j2k_decoder *d, const uint8_t *pkt, int64_t pkt_size,
     int r = b200j2k_wait(d, slot);
     if (r < 0)
         return r;
+    local.nblocks_failed = b200j2k_slot_blocks_failed(d, slot);
     if (info)
         *info = local;
     return local.bytes_consumed;
@@ -721,6 +739,14 @@ int64_t b200j2k_slot_h2d_bytes(b200j2k_decoder *d, int slot)
     return (int64_t)d->slots[slot].h2d_bytes;
 }
 
+int b200j2k_slot_blocks_failed(b200j2k_decoder *d, int slot)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size())
+        return B200J2K_ERR_EINVAL;
+    const Slot &s = d->slots[slot];
+    return s.busy || !s.h_failed ? 0 : *s.h_failed;
+}
+
 int b200j2k_slot_launches(b200j2k_decoder *d, int slot)
 {
     if (!d || slot < 0 || slot >= (int)d->slots.size())
@@ -784,7 +810,7 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
     if (cudaMalloc(&d_bytes_alloc, (size_t)data_size + 16 + 64) != cudaSuccess || cudaMalloc(&d_descs, n * sizeof(CblkDesc)) != cudaSuccess ||
         cudaMalloc(&d_order, n * 4) != cudaSuccess || cudaMalloc(&d_scr, n * 4) != cudaSuccess ||
         cudaMalloc(&d_out, total * 4 + 4) != cudaSuccess || cudaMalloc(&d_scratch, hp.scratch_words * 4 + 256) != cudaSuccess ||
-        cudaMalloc(&d_band, sizeof(BandDesc)) != cudaSuccess || cudaMalloc(&d_status, n * 4) != cudaSuccess) {
+        cudaMalloc(&d_band, sizeof(BandDesc)) != cudaSuccess || cudaMalloc(&d_status, n * 4 + 16) != cudaSuccess) {
         ret = B200J2K_ERR_NOMEM;
     } else {
         d_bytes = d_bytes_alloc + 16;
@@ -795,10 +821,11 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
         cudaMemcpyAsync(d_scr, hp.scr_off.data(), n * 4, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_band, &band, sizeof(band), cudaMemcpyHostToDevice, st);
         cudaMemsetAsync(d_out, 0x55, total * 4 + 4, st);
-        if (run_ht(st, hp, d_descs, d_order, d_scr, d_bytes, d_band, d_scratch, d_out, d_status, maxw, max_area, max_state) < 0)
+        cudaMemsetAsync(d_status, 0, 16, st);
+        if (run_ht(st, hp, d_descs, d_order, d_scr, d_bytes, d_band, d_scratch, d_out, d_status + 4, maxw, max_area, max_state) < 0)
             ret = B200J2K_ERR_DEVICE;
         cudaMemcpyAsync(out, d_out, total * 4, cudaMemcpyDeviceToHost, st);
-        if (status) cudaMemcpyAsync(status, d_status, n * 4, cudaMemcpyDeviceToHost, st);
+        if (status) cudaMemcpyAsync(status, d_status + 4, n * 4, cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) {
             fprintf(stderr, "b200j2k_ht_blocks: CUDA error: %s\n", cudaGetErrorString(e));

@@ -117,8 +117,8 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
         for (int y = 0; y < h; y++)
             for (int x = lane; x < w; x += 32)
                 dst[(size_t)y * dstride + x] = 0;
-        if (lane == 0 && status)
-            status[bi] = result;
+        if (lane == 0)
+            j2k_block_status(status, bi, result);
         return;
     }
 
@@ -285,8 +285,8 @@ ht_decode_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
         for (int y = 0; y < h; y++)
             for (int x = lane; x < w; x += 32)
                 dst[(size_t)y * dstride + x] = 0;
-        if (lane == 0 && status)
-            status[bi] = B200J2K_KERR_INVALID;
+        if (lane == 0)
+            j2k_block_status(status, bi, B200J2K_KERR_INVALID);
         return;
     }
 

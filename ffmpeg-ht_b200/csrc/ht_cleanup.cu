@@ -67,7 +67,9 @@ __host__ __device__ inline RefLayout ref_layout(const CblkDesc &d)
  * nothing to decode, -1 when the segment header is damaged (block = zeros, quirk Q1) */
 __device__ __forceinline__ int ht_block_scup(const CblkDesc &d, const uint8_t *Dcup)
 {
-    if (d.npasses == 0)
+    /* a Part-1 block only reaches these kernels when it carries no bytes (decode_cblk returns zeros for
+     * !cblk->length, jpeg2000dec.c:2005): its Lcup / Lref fields hold other things */
+    if (d.npasses == 0 || (d.flags & J2K_CBLK_MQ))
         return 0;
     const int rem = d.npasses % 3;
     const int plhd = rem ? d.npasses - rem : d.npasses - 3;
@@ -586,8 +588,8 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
         __syncwarp();
         zero_block(dst, dstride, w, h, lane);
     }
-    if (lane == 0 && status)
-        status[bi] = bad ? B200J2K_KERR_INVALID : 1;
+    if (lane == 0)
+        j2k_block_status(status, bi, bad ? B200J2K_KERR_INVALID : 1);
 }
 
 template <bool REFINE>
@@ -610,8 +612,8 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
     if (Scup <= 0) {
         /* nothing decoded or damaged header: the block is all zeros (quirk Q1) */
         zero_block(dst, d.dst_stride, d.w, d.h, lane);
-        if (lane == 0 && status)
-            status[bi] = Scup == 0 ? 0 : B200J2K_KERR_INVALID;
+        if (lane == 0)
+            j2k_block_status(status, bi, Scup == 0 ? 0 : B200J2K_KERR_INVALID);
         return;
     }
     const BandDesc bd = bands[d.band];

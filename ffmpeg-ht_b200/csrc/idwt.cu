@@ -21,8 +21,6 @@
  * (a - c*(b+d) as add, multiply, subtract), so no FMA contraction can change a bit; lrintf is
  * __float2int_rn (round to nearest even).
  */
-#include <cstdlib>
-
 #include "idwt_common.cuh"
 
 namespace b200j2k {
@@ -248,205 +246,6 @@ idwt_level_kernel(const TileCompDesc *__restrict__ tcs, int j, const uint32_t *_
     }
 }
 
-/* ---- the lowest levels fused: up to FUSE_MAX levels per launch, intermediates never leave the SM ---------- */
-/* The first levels of a 5-level 4K frame reconstruct 240 x 135, 480 x 270 and 960 x 540 samples: a launch each
- * costs more in launch latency and pipeline fill than in work (7.7 + 7.7 + 8.4 us measured, round 1).  Here a
- * CTA owns one TX x TY tile of the TOP fused level and recomputes, level by level, the part of the lower
- * resolutions that tile depends on: the tile of level j is placed so that its valid centre covers every LL sample
- * (reflected ones included) the tile of level j + 1 asks for, and is handed over in shared memory.  Same row-
- * then-column lifting, same reflection rules and the same routines as idwt_level_kernel: bit-identical. */
-constexpr int FUSE_MAX = 3;
-
-struct FuseRow {
-    int offL, offH;     /* element offsets of the row's low-pass / high-pass halves */
-    int ll;             /* the low-pass half is an LL row (else an LH row of the plane) */
-};
-
-template <int TYPE, int TY>
-__global__ void __launch_bounds__(THREADS, 1)
-idwt_fused_levels_kernel(const TileCompDesc *__restrict__ tcs, int j0, int jtop, const uint32_t *__restrict__ coefA,
-                         uint32_t *__restrict__ coefB, uint32_t *__restrict__ coefC)
-{
-    using G = Geo<TYPE>;
-    using L = Lift<TYPE>;
-    constexpr int HALO = G::HALO, HP = G::HP, TX = G::TX, SH = TY + 2 * HALO;
-    constexpr int NHALF = 2, RH = TY / NHALF, R = RH + 2 * HALO;
-    constexpr int NB = (SH + NWARPS - 1) / NWARPS;          /* tile rows per warp in the horizontal pass */
-    static_assert(TX * NHALF <= THREADS, "one thread per (column, half)");
-    extern __shared__ __align__(16) uint32_t fsm[];
-    uint32_t *tile = fsm;                       /* SH x TX: rows after the horizontal pass */
-    uint32_t *llbuf = fsm + SH * TX;            /* TY x TX: valid output of the previous level */
-    __shared__ FuseRow rowtab[FUSE_MAX][SH];
-    const TileCompDesc &tc = tcs[blockIdx.z];
-    if (tc.transform != TYPE)
-        return;
-    const int jt = min(jtop, tc.nlevels - 2);   /* the last level is the fused pack kernel's */
-    if (jt < j0)
-        return;
-    const int nlev = jt - j0 + 1;
-    /* tile origins, top down: XA[l] / YA[l] = even absolute coordinates of column / row 0 of the tile of level j0 + l */
-    int XA[FUSE_MAX], YA[FUSE_MAX];
-#pragma unroll
-    for (int l = 0; l < FUSE_MAX; l++)
-        XA[l] = YA[l] = 0;
-    {
-        const LevelDesc o = tc.lev[jt + 1];
-        const int xa = (o.u0 & ~1) + blockIdx.x * TX, ya = (o.v0 & ~1) + blockIdx.y * TY;
-        if (xa >= o.u1 || ya >= o.v1)
-            return;
-#pragma unroll
-        for (int l = 0; l < FUSE_MAX; l++)
-            if (l == nlev - 1) {
-                XA[l] = xa;
-                YA[l] = ya;
-            }
-    }
-#pragma unroll
-    for (int l = FUSE_MAX - 2; l >= 0; l--)
-        if (l < nlev - 1) {
-            /* level l + 1 reads LL columns from pair (XA' >> 1) - HP on, rows from (YA' - HALO) >> 1 on; never left
-             * of the resolution, where it reads reflected (inner) samples instead */
-            const LevelDesc o = tc.lev[j0 + l + 1];
-            XA[l] = max((XA[l + 1] >> 1) - HP, o.u0) & ~1;
-            YA[l] = max((YA[l + 1] - HALO) >> 1, o.v0) & ~1;
-        }
-    const uint32_t *A = coefA + tc.coef_off;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int W = tc.width;
-    /* row tables of every level, and this lane's (reflected) column indices */
-    int ie[FUSE_MAX][G::ITERS], io[FUSE_MAX][G::ITERS];
-#pragma unroll
-    for (int l = 0; l < FUSE_MAX; l++) {
-        if (l >= nlev)
-            continue;
-        const int j = j0 + l;
-        const LevelDesc o = tc.lev[j + 1];
-        const int u0 = o.u0, u1 = o.u1, v0 = o.v0, v1 = o.v1;
-        const int nLh = ((u1 + 1) >> 1) - ((u0 + 1) >> 1), nLv = ((v1 + 1) >> 1) - ((v0 + 1) >> 1);
-        const int eoff = (u0 + 1) >> 1, ooff = u0 >> 1, eoffv = (v0 + 1) >> 1;
-        /* LL source: the plane (first level of the frame), the ping-pong buffer an earlier launch wrote, or the
-         * previous level's tile: llbuf[(row - YA[l-1]) * TX + (col - XA[l-1])] in absolute LL coordinates */
-        for (int r = threadIdx.x; r < SH; r += THREADS) {
-            const int Y = YA[l] - HALO + r;
-            const int Yr = (Y >= v0 && Y < v1) ? Y : reflect(Y, v0, v1);
-            const int ky = band_index(Yr, v0);
-            FuseRow t;
-            t.ll = 0;
-            if (Yr & 1) {
-                t.offL = (nLv + ky) * W;
-                t.offH = (nLv + ky) * W + nLh;
-            } else {
-                t.ll = 1;
-                t.offL = l > 0 ? (ky + eoffv - YA[l > 0 ? l - 1 : 0]) * TX + (eoff - XA[l > 0 ? l - 1 : 0])
-                               : ky * (j == 0 ? W : nLh);
-                t.offH = ky * W + nLh;
-            }
-            rowtab[l][r] = t;
-        }
-#pragma unroll
-        for (int it = 0; it < G::ITERS; it++) {
-            const int pair = (XA[l] >> 1) + it * G::VP - HP + lane;
-            int Xe = 2 * pair, Xo = Xe + 1;
-            if (u1 - u0 > 1) {
-                if (Xe < u0 || Xe >= u1) Xe = reflect(Xe, u0, u1);
-                if (Xo < u0 || Xo >= u1) Xo = reflect(Xo, u0, u1);
-                ie[l][it] = (Xe >> 1) - eoff;
-                io[l][it] = (Xo >> 1) - ooff;
-            } else {
-                ie[l][it] = io[l][it] = 0;
-            }
-        }
-    }
-    __syncthreads();
-    /* every coefficient the three levels take from HBM, fetched up front: one memory round trip for the launch */
-    uint32_t Lg[FUSE_MAX][NB][G::ITERS], Hg[FUSE_MAX][NB][G::ITERS];
-    const uint32_t *LLg = j0 == 0 ? A : ((j0 & 1) ? coefB : coefC) + tc.coef_off;
-#pragma unroll
-    for (int l = 0; l < FUSE_MAX; l++) {
-        if (l >= nlev)
-            continue;
-        const LevelDesc o = tc.lev[j0 + l + 1];
-        const bool line = o.u1 - o.u0 > 1, odd0 = o.u0 & 1;
-#pragma unroll
-        for (int b = 0; b < NB; b++) {
-            const int r = warp + b * NWARPS;
-            if (r >= SH)
-                continue;
-            const FuseRow t = rowtab[l][r];
-            const bool Lglobal = !t.ll || l == 0;
-            const uint32_t *rowL = !t.ll ? A + t.offL : LLg + t.offL;
-            const uint32_t *rowH = A + t.offH;
-#pragma unroll
-            for (int it = 0; it < G::ITERS; it++) {
-                Lg[l][b][it] = Hg[l][b][it] = 0;
-                if (line || odd0)
-                    Hg[l][b][it] = rowH[io[l][it]];
-                if (Lglobal && (line || !odd0))
-                    Lg[l][b][it] = rowL[ie[l][it]];
-            }
-        }
-    }
-#pragma unroll
-    for (int l = 0; l < FUSE_MAX; l++) {
-        if (l >= nlev)
-            continue;
-        const int j = j0 + l;
-        const LevelDesc o = tc.lev[j + 1];
-        const int u0 = o.u0, u1 = o.u1, v0 = o.v0, v1 = o.v1;
-        const int lh = u1 - u0, lv = v1 - v0;
-        /* horizontal pass: lane = one (low, high) pair of the row */
-#pragma unroll
-        for (int b = 0; b < NB; b++) {
-            const int r = warp + b * NWARPS;
-            if (r >= SH)
-                continue;
-            uint32_t *trow = tile + (size_t)r * TX;
-            const FuseRow t = rowtab[l][r];
-#pragma unroll
-            for (int it = 0; it < G::ITERS; it++) {
-                uint32_t Lc = Lg[l][b][it];
-                const uint32_t Hc = Hg[l][b][it];
-                if (l > 0 && t.ll && (lh > 1 || !(u0 & 1)))
-                    Lc = llbuf[t.offL + ie[l][it]];
-                uint32_t xe, xo;
-                if (lh > 1)
-                    hlift<TYPE>(Lc, Hc, xe, xo);
-                else     /* one-sample line (jpeg2000dwt.c:313-317, :380-386, :457-463) */
-                    xe = xo = L::single((u0 & 1) ? Hc : Lc, u0 & 1);
-                if (lane >= HP && lane < 32 - HP)
-                    *reinterpret_cast<uint2 *>(trow + 2 * (it * G::VP + lane - HP)) = make_uint2(xe, xo);
-            }
-        }
-        __syncthreads();
-        /* vertical pass in registers: thread = (column, half of the tile rows) */
-        const int col = threadIdx.x % TX, half = threadIdx.x / TX;
-        if (half < NHALF) {
-            uint32_t v[R];
-#pragma unroll
-            for (int k = 0; k < R; k++)
-                v[k] = tile[(half * RH + k) * TX + col];
-            vlift<TYPE, R>(v, lv, v0);
-            if (l < nlev - 1) {
-#pragma unroll
-                for (int k = 0; k < RH; k++)
-                    llbuf[(half * RH + k) * TX + col] = v[HALO + k];
-            } else {
-                uint32_t *out = ((j & 1) ? coefC : coefB) + tc.coef_off;
-                const int X = XA[l] + col;
-                if (X >= u0 && X < u1) {
-#pragma unroll
-                    for (int k = 0; k < RH; k++) {
-                        const int Y = YA[l] + half * RH + k;
-                        if (Y >= v0 && Y < v1)
-                            out[(size_t)(Y - v0) * lh + (X - u0)] = v[HALO + k];
-                    }
-                }
-            }
-        }
-        __syncthreads();
-    }
-}
-
 /* final fixed-point rescale of the 9/7 integer path when the plane itself is the output (jpeg2000dwt.c:534-536) */
 __global__ void rescale97i_kernel(uint32_t *p, size_t n)
 {
@@ -619,7 +418,6 @@ template <int TYPE, int TY> constexpr size_t final_smem(int ncomp)
 }
 
 constexpr int LTY = 64;    /* tile rows, intermediate levels */
-constexpr long FUSE_LIMIT = 1l << 20;   /* samples per plane up to which a level counts as small (fused kernel) */
 constexpr int FTY = 32;    /* tile rows, fused last level */
 
 template <int TYPE>
@@ -630,37 +428,7 @@ int run_levels(cudaStream_t stream, const IdwtFrame &f, int max_levels, bool any
     if (!any_type)
         return 0;
     const bool fast = !to_plane && idwt_stream_levels_ok(f.h_tcs, f.ntcs, TYPE);
-    int j = 0;
-    /* the lowest levels, as long as they are small, go FUSE_MAX at a time through the fused kernel */
-    static const long fuse_limit = getenv("B200J2K_FUSE") ? atol(getenv("B200J2K_FUSE")) : FUSE_LIMIT;
-    while (!to_plane && j < max_levels) {
-        int n = 0, gw = 0, gh = 0;
-        while (n < FUSE_MAX && j + n < max_levels && (long)max_w[j + n] * max_h[j + n] <= fuse_limit) {
-            gw = max_w[j + n] > gw ? max_w[j + n] : gw;
-            gh = max_h[j + n] > gh ? max_h[j + n] : gh;
-            n++;
-        }
-        if (n == 0)
-            break;
-        if (gw > 0 && gh > 0) {
-            constexpr int FTX = Geo<TYPE>::TX;
-            constexpr int sm = (2 * LTY + 2 * Lift<TYPE>::HALO) * FTX * 4;
-            static bool raised[64] = { false };         /* function attributes are per device */
-            int dev = 0;
-            cudaGetDevice(&dev);
-            if (dev < 0 || dev >= 64 || !raised[dev]) {
-                cudaFuncSetAttribute(idwt_fused_levels_kernel<TYPE, LTY>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
-                if (dev >= 0 && dev < 64)
-                    raised[dev] = true;
-            }
-            dim3 grid((gw + 1 + FTX - 1) / FTX, (gh + 1 + LTY - 1) / LTY, f.ntcs);
-            idwt_fused_levels_kernel<TYPE, LTY><<<grid, THREADS, sm, stream>>>(
-                f.d_tcs, j, j + n - 1, (const uint32_t *)f.coefA, (uint32_t *)f.coefB, (uint32_t *)f.coefC);
-            launches++;
-        }
-        j += n;
-    }
-    for (; j < max_levels; j++) {
+    for (int j = 0; j < max_levels; j++) {
         if (max_w[j] <= 0)
             continue;
         if (fast) {

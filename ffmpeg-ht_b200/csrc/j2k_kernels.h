@@ -9,6 +9,21 @@
 
 #define B200J2K_KERR_INVALID (-1094995529)
 
+/* status[] convention of the block kernels: one word per code-block (1 decoded, 0 nothing to decode,
+ * B200J2K_KERR_INVALID zero-filled because its segment was damaged) and, IN FRONT of the array, status[-1] = how
+ * many blocks of the frame ended up INVALID -- what the reference reports block by block with av_log
+ * (jpeg2000dec.c:2275-2278).  The host zeroes the counter per frame and reads it back with the picture. */
+#ifdef __CUDACC__
+static __device__ __forceinline__ void j2k_block_status(int32_t *status, uint32_t bi, int32_t value)
+{
+    if (!status)
+        return;
+    status[bi] = value;
+    if (value < 0)
+        atomicAdd(status - 1, 1);
+}
+#endif
+
 namespace b200j2k {
 
 /* HT block decode + dequantisation.  order: optional list of descriptor indices (nullptr = 0..n-1).

@@ -1142,6 +1142,19 @@ int Parser::build_geometry(int flags)
         }
     }
     ll_elems = coef_elems;   /* same offsets are used in the ping-pong buffers; they only hold <= 1/4 of each plane */
+    /* Every component has to fit the plane it is written to.  The plane of a planar format comes from the 'cdef'
+     * box of the file: a crafted one can send a full-size component to a subsampled chroma plane.  The reference's
+     * write_frame then writes past the end of the AVFrame plane on the host; here the same write would leave
+     * the picture allocation on the device, so such a frame is refused. */
+    for (const PackGroup &g : groups)
+        for (int c = 0; c < g.ncomp; c++) {
+            const TileCompDesc &tc = tcs[g.tc[c]];
+            const LevelDesc &o = tc.lev[tc.nlevels];
+            const int pl = g.pixel_stride == g.ncomp && g.ncomp > 1 ? g.plane : (g.ncomp > 1 ? g.comp_plane[c] : g.plane);
+            if (pl < 0 || pl >= nplanes || tc.out_x < 0 || tc.out_y < 0 ||
+                (int64_t)tc.out_x + (o.u1 - o.u0) > plane_w[pl] || (int64_t)tc.out_y + (o.v1 - o.v0) > plane_h[pl])
+                return B200J2K_ERR_INVALIDDATA;
+        }
     return 0;
 }
 

@@ -394,8 +394,7 @@ mq_block_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__
         const int bpno0 = (int)d.Lcup - 1 + 31 - d.M_b - 1 - d.roi_shift;      /* Lcup carries nonzerobits */
         const int sty = d.flags & (J2K_CBLK_MQ_RESET | J2K_CBLK_MQ_SEGSYM);
         ret = (d.flags & 1) ? run_passes<true>(b, m, d.npasses, bpno0, sty) : run_passes<false>(b, m, d.npasses, bpno0, sty);
-        if (status)
-            status[bi] = ret;
+        j2k_block_status(status, bi, ret);
     }
     ret = __shfl_sync(0xFFFFFFFFu, ret, 0);
     __syncwarp();
@@ -419,13 +418,10 @@ int launch_mq_blocks(cudaStream_t stream, const CblkDesc *descs, const uint32_t 
     /* the two state arrays of the largest block of the frame: w * h <= 4096, so at most 2 x 12.3 KB (1024 x 4) */
     const int smem = (state_words * 4 + 32) * MQ_WARPS_PER_CTA;
     if (smem > 48 * 1024) {                     /* 1024 x 4 blocks: 2 x 24.6 KB */
-        static thread_local int raised = 0;     /* per host thread: cheap, and attribute calls are per device context */
-        if (raised < smem) {
-            if (cudaFuncSetAttribute((const void *)mq_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-                cudaSuccess)
-                return -1;
-            raised = smem;
-        }
+        /* function attributes belong to the device: no caching across the devices a host thread may visit */
+        if (cudaFuncSetAttribute((const void *)mq_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess)
+            return -1;
     }
     mq_block_kernel<<<(nblocks + MQ_WARPS_PER_CTA - 1) / MQ_WARPS_PER_CTA, 32 * MQ_WARPS_PER_CTA, smem, stream>>>(descs, order, nblocks, bytes, bands, (uint32_t *)coef, status,
                                                    state_words);

@@ -26,6 +26,8 @@
  * termination on each pass -- a build that wants those keeps the native decoder registered as fallback under a
  * different name.
  */
+#include <stdatomic.h>
+
 #include "libavutil/buffer.h"
 #include "libavutil/imgutils.h"
 #include "libavutil/opt.h"
@@ -33,6 +35,7 @@
 #include "avcodec.h"
 #include "codec_internal.h"
 #include "decode.h"
+#include "profiles.h"
 #include "thread.h"
 
 #include "b200j2k.h"
@@ -134,8 +137,8 @@ static av_cold int b200j2k_ff_init(AVCodecContext *avctx)
         return AVERROR(ENODEV);
     }
     if (device < 0) {
-        static int next_device;              /* frame threads open one context each: spread them */
-        device = next_device++ % ndev;
+        static atomic_uint next_device;      /* frame threads open one context each: spread them */
+        device = (int)(atomic_fetch_add(&next_device, 1) % (unsigned)ndev);
     }
     return b200j2k_create(&s->dec, device, 1, flags);
 }
@@ -195,6 +198,9 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
     consumed = b200j2k_decode(s->dec, avpkt->data, avpkt->size, data, linesize, &info);
     if (consumed < 0)
         return (int)consumed;
+    /* the reference logs every damaged HT block and carries on with zeros in its place (jpeg2000dec.c:2275-2278) */
+    if (info.nblocks_failed > 0)
+        av_log(avctx, AV_LOG_ERROR, "%d code-blocks could not be decoded (zeros in their place)\n", info.nblocks_failed);
     *got_frame = 1;
     return (int)consumed;
 }
@@ -231,5 +237,6 @@ const FFCodec ff_jpeg2000_b200_decoder = {
     FF_CODEC_DECODE_CB(b200j2k_ff_decode),
     .p.priv_class   = &b200j2k_class,
     .p.max_lowres   = 5,
+    .p.profiles     = NULL_IF_CONFIG_SMALL(ff_jpeg2000_profiles),
     .caps_internal  = FF_CODEC_CAP_SKIP_FRAME_FILL_PARAM | FF_CODEC_CAP_INIT_CLEANUP,
 };

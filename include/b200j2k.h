@@ -75,6 +75,10 @@ typedef struct b200j2k_frame_info {
                                      * above is only its memory-layout class */
     int32_t sar_num, sar_den;       /* AVCodecContext.sample_aspect_ratio from the capture / display resolution box
                                      * of a JP2 file ('res ', jpeg2000dec.c:2762-2796, :2867-2868); 0 / 0 = leave it */
+    int32_t nblocks_failed;         /* code-blocks zero-filled because their segment was damaged: what the reference
+                                     * logs block by block and carries on from (jpeg2000dec.c:2275-2278).  Known once
+                                     * the frame is done: filled by b200j2k_decode(), else b200j2k_slot_blocks_failed() */
+    int32_t reserved;
 } b200j2k_frame_info;
 
 typedef struct b200j2k_decoder b200j2k_decoder;
@@ -133,6 +137,9 @@ void *b200j2k_slot_output(b200j2k_decoder *dec, int slot, int64_t *bytes);
 int64_t b200j2k_slot_h2d_bytes(b200j2k_decoder *dec, int slot);
 /* number of kernel launches the last run of `slot` queued */
 int b200j2k_slot_launches(b200j2k_decoder *dec, int slot);
+/* After b200j2k_wait(): how many code-blocks of the slot's frame were zero-filled because their segment was damaged
+ * (the reference logs each one and carries on, jpeg2000dec.c:2275-2278); 0 while the slot is still busy. */
+int b200j2k_slot_blocks_failed(b200j2k_decoder *dec, int slot);
 
 /* Stage-level entry points (parity tests against the oracle; same argument meaning as the reference's
  * ff_jpeg2000_decode_htj2k / ff_dwt_decode): all buffers are HOST pointers, the work runs on the device.

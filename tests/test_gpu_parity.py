@@ -398,6 +398,67 @@ def test_part1_damaged_frames_match_oracle(dec):
     assert n_ok >= 25
 
 
+def test_failed_block_count_reaches_the_host(dec):
+    """The reference logs every HT block it cannot decode and carries on with zeros (jpeg2000dec.c:2275-2278).  The
+    kernels count those blocks (status[-1]) and b200j2k_decode() reports the count: nine blocks get an Scup of zero
+    (jpeg2000htdec.c:1246-1250 -> error), the picture still equals the oracle's and exactly nine failures arrive."""
+    planes = j2kgen.synth_image(256, 200, 3, 10, seed=4)
+    cs = j2kgen.encode(planes, 10, j2kgen.EncParams(levels=3, cblk=(32, 32)))
+    info, pic = dec.decode(cs)
+    assert info.nblocks_failed == 0
+    c = fb.plan(cs, 0)["cblk"]
+    coded = np.nonzero((c["npasses"] > 0) & (c["Lcup"] >= 2))[0]
+    pick = coded[::7][:9]
+    assert len(pick) == 9
+    bad = bytearray(cs)
+    for i in pick:
+        end = int(c["data_off"][i]) + int(c["Lcup"][i])
+        bad[end - 1] = 0
+        bad[end - 2] &= 0xF0
+    bad = bytes(bad)
+    r, oinfo, want = oracle_decode(bad, 0)
+    assert r == 0
+    info, got = dec.decode(bad)
+    assert np.array_equal(got, want)
+    assert info.nblocks_failed == 9
+
+
+def test_part1_blocks_with_passes_but_no_bytes(dec):
+    """Damaged packet headers can include a Part-1 block with coding passes and a length of zero.  The reference
+    returns zeros for it (decode_cblk: !cblk->length, jpeg2000dec.c:2005); such a block travels with the blocks that
+    only need zeros through ht_magsgn_kernel, whose segment checks must not look at a Part-1 descriptor (its Lcup
+    field holds the non-zero bit-planes).  Streams are picked with the host plan so that every one has such a block."""
+    rng = np.random.default_rng(5)
+    n = 0
+    for ti in (0, 3, 7, 4):
+        cs = part1_stream(PART1[ti])
+        sod = cs.index(b"\xff\x93")
+        picked = 0
+        for k in range(400):
+            bad = bytearray(cs)
+            for _ in range(int(rng.integers(1, 4))):
+                bad[int(rng.integers(sod + 2, min(len(bad) - 2, sod + 402)))] = int(rng.integers(0, 256))
+            bad = bytes(bad)
+            try:
+                P = fb.plan(bad, 0)
+            except fb.DecodeError:
+                continue
+            c = P["cblk"]
+            hit = ((c["flags"] & 0x88) == 0x08) & (c["npasses"] > 0) & (c["length"] == 0)
+            if not hit.any():
+                continue
+            r, oinfo, want = oracle_decode(bad, 0)
+            if r != 0:
+                continue
+            info, got = dec.decode(bad)
+            assert np.array_equal(got, want), (ti, k)
+            picked += 1
+            if picked == 8:
+                break
+        n += picked
+    assert n >= 20
+
+
 @pytest.mark.parametrize("t", TILE_STYLES, ids=lambda t: f"var{t['var']}-" + "-".join(f"{k}{v}" for k, v in t["cfg"].items())[:30])
 def test_tile_style_frames_vs_oracle(t, dec, dec_bitexact):
     """Tiles with their own COD / QCD / POC (levels, code-block size, progression, step sizes differ per tile)."""

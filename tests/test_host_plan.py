@@ -528,3 +528,20 @@ def test_jp2_wrapper_headers_match_reference():
             assert mine == ((r, info[0], info[1], name) if r == 0 else (r,)), (nc, bd, len(data))
             n += 1
     assert n == 110
+
+
+def test_component_must_fit_its_output_plane():
+    """A 'cdef' box names the output plane of every component of a planar picture (write_frame, jpeg2000dec.c:2325-2326).
+    A crafted one sends the full-size luma component of a 4:2:0 stream to a half-size chroma plane: the reference then
+    writes past the end of that AVFrame plane.  The plan refuses such a file (INVALIDDATA) instead of carrying the
+    out-of-bounds write over to the device; honest channel definitions of the same stream still pass."""
+    subs, bd = [(1, 1), (2, 2), (2, 2)], 8
+    for w, h, kw in SUBSAMPLED_GEOMS[:2]:
+        cs, planes, p = subsampled_stream(subs, bd, w, h, kw)
+        good = j2kgen.wrap_jp2(cs, w, h, 3, bd, colour_space=18, cdef=[(0, 0, 1), (1, 0, 3), (2, 0, 2)])
+        assert fb.plan(good, 0)["info"].width == w
+        for cdef in ([(0, 0, 2), (1, 0, 1), (2, 0, 3)], [(0, 0, 3), (1, 0, 2), (2, 0, 1)]):
+            bad = j2kgen.wrap_jp2(cs, w, h, 3, bd, colour_space=18, cdef=cdef)
+            with pytest.raises(fb.DecodeError) as e:
+                fb.plan(bad, 0)
+            assert e.value.code == fb.ERR_INVALIDDATA
