@@ -16,14 +16,18 @@ Numbers on the JSON line:
   e2e        the same metric through the public C-ABI call (b200j2k_submit/wait) with HOST buffers:
              host parsing, pinned staging, H2D of codestream + tables and D2H of the picture all inside
              the timed region (wall clock bracketed by synchronisation, max over ranks)
-  roofline   the fused last-IDWT-level + MCT + pack kernel (the HBM-bound stage) against MEASURED_PEAKS
+  roofline   the fused last-IDWT-level + MCT + pack kernel (the HBM-bound stage) against MEASURED_PEAKS,
+             and `stage`: all IDWT launches of a frame together (t_dwt_mct_pack)
   entropy    the HT block-decode kernels (bit-serial, not on a bandwidth roofline): code-blocks/s
   cpu_baseline  the reference decoder timed on this box's host cores on a bounded sample of the workload
+  checks     every picture the timed legs left behind is compared with the lossless source of its frame
+             (SHA-1), and the reference decoder's picture of frame 0 with the GPU's, in this same run
 """
 from __future__ import annotations
 
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -42,31 +46,55 @@ W, H, NCOMP, DEPTH = 3840, 2160, 3, 12
 WORKLOAD = "3840x2160 4:4:4 12-bit lossless HTJ2K (5/3+RCT, 5 levels, 64x64 code-blocks, cleanup pass only)"
 
 
-def make_frames(distinct: int, seed_offset: int = 0, scale: int = 1):
+def sha1(a) -> str:
+    return hashlib.sha1(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).hexdigest()
+
+
+def packed_source(planes, depth: int) -> np.ndarray:
+    """The picture a lossless stream of these planes decodes to: samples interleaved, left-aligned in 8 or 16 bits
+    (write_frame_8 / write_frame_16, jpeg2000dec.c:2301-2366)."""
+    if depth <= 8:
+        return (np.stack(planes, -1).astype(np.uint8) << (8 - depth)).reshape(-1)
+    return (np.stack(planes, -1).astype(np.uint16) << (16 - depth)).reshape(-1).view(np.uint8)
+
+
+def make_frames(distinct: int, seed_offset: int = 0, scale: int = 1, with_hashes: bool = False):
     import j2kgen
-    frames = []
+    frames, hashes = [], []
     for i in range(distinct):
         cs, planes, p = j2kgen.make_config("cfg4", scale=scale, phase=0.37 * i, seed_offset=seed_offset)
         frames.append(cs)
-    return frames
+        hashes.append(sha1(packed_source(planes, DEPTH)))
+    return (frames, hashes) if with_hashes else frames
 
 
 # ---- reference arm ----------------------------------------------------------------------------------
+_cpu = None
+
+
+def cpu_library():
+    """-> (ctypes library, kind, prefix).  oracle/_ref (the unmodified reference) when it was built, else the port."""
+    global _cpu
+    if _cpu is None:
+        ref = ROOT / "oracle" / "_ref" / "libj2kref.so"
+        if ref.exists():
+            lib, kind, prefix = ctypes.CDLL(str(ref)), "reference", "ref_"
+        else:
+            subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "liboracle.so"])
+            lib, kind, prefix = ctypes.CDLL(str(ROOT / "oracle" / "liboracle.so")), "port", "oracle_"
+        bench = getattr(lib, prefix + "decode_bench")
+        bench.restype = ctypes.c_double
+        bench.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        dec = getattr(lib, prefix + "decode")
+        dec.argtypes = [ctypes.c_char_p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p,
+                        ctypes.c_int64]
+        _cpu = (lib, kind, bench, dec)
+    return _cpu
+
+
 def cpu_decoder():
-    """-> (ctypes function, kind).  oracle/_ref (the unmodified reference) when it was built, else the port."""
-    ref = ROOT / "oracle" / "_ref" / "libj2kref.so"
-    if ref.exists():
-        lib = ctypes.CDLL(str(ref))
-        fn = lib.ref_decode_bench
-        kind = "reference"
-    else:
-        subprocess.check_call(["make", "-s", "-C", str(ROOT / "oracle"), "liboracle.so"])
-        lib = ctypes.CDLL(str(ROOT / "oracle" / "liboracle.so"))
-        fn = lib.oracle_decode_bench
-        kind = "port"
-    fn.restype = ctypes.c_double
-    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
-    return fn, kind
+    lib, kind, bench, dec = cpu_library()
+    return bench, kind
 
 
 def cpu_decode_seconds(fn, frames, nframes: int, threads: int) -> float:
@@ -79,13 +107,24 @@ def cpu_decode_seconds(fn, frames, nframes: int, threads: int) -> float:
     return float(sec)
 
 
+def cpu_picture_sha1(cs: bytes, nbytes: int):
+    """SHA-1 of the picture the CPU decoder (the reference where it was built) makes of one codestream."""
+    lib, kind, bench, dec = cpu_library()
+    info = (ctypes.c_int64 * 8)()
+    out = np.zeros(nbytes + 4096, np.uint8)
+    ret = dec(bytes(cs), len(cs), 0, info, out.ctypes.data, out.size)
+    if ret != 0:
+        return None
+    return sha1(out[: info[3]])
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
     fn, kind = cpu_decoder()
     cores = os.cpu_count() or 1
-    frames = make_frames(min(args.distinct, 2), scale=args.scale)
+    frames, hashes = make_frames(min(args.distinct, 2), scale=args.scale, with_hashes=True)
     w, h = W // args.scale, H // args.scale
     nframes = max(cores, 4)
     for _ in range(args.warmup if args.warmup < 2 else 1):
@@ -94,6 +133,8 @@ def run_reference(args):
     total = sum(t)
     fps = nframes * args.steps / total
     mpix = fps * w * h / 1e6
+    t1 = cpu_decode_seconds(fn, frames, 2, 1)                     # one context, one thread: the reference's default
+    pic = cpu_picture_sha1(frames[0], w * h * 3 * 2)
     line = {
         "metric": "decoded Mpixel/s", "value": mpix, "unit": "Mpixel/s", "impl": "reference",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
@@ -105,8 +146,11 @@ def run_reference(args):
                               "(frame threading), C build without x86 asm" if kind == "reference" else
                               "oracle port of the reference decoder"},
         "cpu_baseline": {"value": mpix, "unit": "Mpixel/s", "cores": cores, "kind": kind,
-                         "sample": f"{nframes} frames per step x {args.steps} steps on {cores} threads"},
+                         "sample": f"{nframes} frames per step x {args.steps} steps on {cores} threads",
+                         "fps_one_thread": 2 / t1},
         "e2e": {"value": mpix, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "checks": {"frame0_picture_sha1": pic, "frame0_source_sha1": hashes[0],
+                   "frame0_is_the_lossless_source": pic == hashes[0]},
         "gpu_launches": 0,
     }
     emit(line)
@@ -162,13 +206,14 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-
 # ---- further BASELINE workloads (reported next to the contract's workload, N=1 only) -------------------
 def extra_workload(fb, torch, local, cfgname, label, B, K, T, slots_e2e, S=8):
     """Kernel-only and end-to-end frames/s of one more BASELINE.json configuration (one distinct frame, cycled),
     measured exactly like the main workload: CUDA events on the launching streams with the inputs resident in
-    HBM, and wall clock around b200j2k_submit/wait with pinned host buffers."""
+    HBM, and wall clock around b200j2k_submit/wait with pinned host buffers.  The picture the timed end-to-end leg
+    leaves behind is checked: lossless streams against their source, irreversible ones against the CPU decoder."""
     import j2kgen
+    lossless = True
     if cfgname == "part1_4k":
         # Part-1 (EBCOT / MQ) code-blocks: the reference ships no HT encoder and this repo's generator writes HT
         # only, so this stream comes from OpenJPEG (through Pillow), 8-bit RGB because that is what Pillow offers
@@ -176,12 +221,17 @@ def extra_workload(fb, torch, local, cfgname, label, B, K, T, slots_e2e, S=8):
 
         from PIL import Image
         planes = j2kgen.synth_image(W, H, 3, 8, seed=11)
+        depth = 8
         b = io.BytesIO()
         Image.fromarray(np.stack(planes, -1).astype(np.uint8), "RGB").save(b, "JPEG2000", no_jp2=True, irreversible=False,
                                                                          codeblock_size=(64, 64))
         cs = b.getvalue()
     else:
-        cs, planes, _ = j2kgen.make_config(cfgname)
+        cs, planes, p = j2kgen.make_config(cfgname)
+        depth = j2kgen.CONFIGS[cfgname]["bitdepth"]
+        enc = j2kgen.CONFIGS[cfgname]["enc"]
+        # refinement passes reconstruct with the reference's half-step offsets: judged against the CPU decoder
+        lossless = bool(enc.get("reversible", True)) and enc.get("npasses", 1) == 1
     h, w = planes[0].shape
     dec = fb.Jpeg2000Decoder(device=local, slots=S)
     info = [dec.stage(s, cs) for s in range(S)][0]
@@ -236,26 +286,69 @@ def extra_workload(fb, torch, local, cfgname, label, B, K, T, slots_e2e, S=8):
     e2e_s = time.perf_counter() - t0
     for d in decs:
         d.close()
+    # what the timed leg left in every output buffer
+    got = {sha1(f.buffer) for row in pins for f in row}
+    fn, kind = cpu_decoder()
+    cores = os.cpu_count() or 1
+    if lossless:
+        want, against = sha1(packed_source(planes, depth)), "lossless source"
+    else:
+        want, against = cpu_picture_sha1(cs, pins[0][0].nbytes), f"CPU decoder ({kind})"
+    n_cpu = max(cores, 4)
+    sec = cpu_decode_seconds(fn, [cs], n_cpu, cores)
     n_k, n_e = B * K, per * K * T
-    extra = {}
-    if cfgname == "part1_4k":                  # the reference's MQ path on the same stream, all host threads
-        fn, kind = cpu_decoder()
-        cores = os.cpu_count() or 1
-        sec = cpu_decode_seconds(fn, [cs], cores, cores)
-        extra = {"cpu_fps": cores / sec, "cpu_kind": kind, "cpu_cores": cores}
-    return {"workload": label, **extra, "codeblocks_per_frame": info.ncodeblocks, "compressed_bytes_per_frame": len(cs),
+    return {"workload": label, "codeblocks_per_frame": info.ncodeblocks, "compressed_bytes_per_frame": len(cs),
             "fps": n_k / (kern_ms * 1e-3), "mpixel_s": n_k * w * h / (kern_ms * 1e-3) / 1e6,
             "e2e_fps": n_e / e2e_s, "e2e_mpixel_s": n_e * w * h / e2e_s / 1e6,
+            "cpu_fps": n_cpu / sec, "cpu_kind": kind, "cpu_cores": cores, "cpu_sample": f"{n_cpu} frames, {sec:.1f} s",
+            "output_check": got == {want}, "output_check_against": against,
             "stage_ms_per_frame": [round(float(x), 4) for x in stage]}
 
 
 EXTRA = [
-    ("target8k", "7680x4320 1-component 16-bit lossless HTJ2K, one tile (north_star target: >= 60 fps on one B200)"),
-    ("cfg3", "7680x4320 1-component 16-bit lossless HTJ2K, 2x2 tiles (BASELINE configs[2])"),
+    ("cfg1", "2048x1080 4:4:4 12-bit lossless HTJ2K (BASELINE configs[0], the reference's own CPU-runnable case)"),
     ("cfg2", "3840x2160 4:4:4 10-bit irreversible 9/7 + ICT HTJ2K (BASELINE configs[1])"),
-    ("part1_4k", "3840x2160 RGB 8-bit lossless Part-1 (EBCOT / MQ code-blocks, OpenJPEG-encoded): SURVEY 8(f) N4, "
-                 "first correct version of mq_block_kernel"),
+    ("cfg3", "7680x4320 1-component 16-bit lossless HTJ2K, 2x2 tiles (BASELINE configs[2])"),
+    ("cfg5", "2048x1080 4:4:4 12-bit lossless HTJ2K, 32x32 code-blocks, cleanup + SigProp + MagRef passes, RPCL "
+             "(BASELINE configs[4])"),
+    ("target8k", "7680x4320 1-component 16-bit lossless HTJ2K, one tile (north_star target: >= 60 fps on one B200)"),
+    ("part1_4k", "3840x2160 RGB 8-bit lossless Part-1 (EBCOT / MQ code-blocks, OpenJPEG-encoded): SURVEY 8(f) N4"),
 ]
+
+
+def shim_leg(frames, contexts=(1, 4, 8, 16)):
+    """The FFCodec shim (ffmpeg-ht_b200/ffcodec/jpeg2000_b200.c compiled against the reference's headers) driven the
+    way libavcodec drives a decoder -- FFCodec.init / cb.decode / close, one context per frame thread, pageable
+    packets, a new AVFrame per picture -- by the harness that also drives the reference decoder (oracle/ref_shim.c
+    built with -DREF_CODEC=ff_jpeg2000_b200_decoder).  Only where that library was built (needs /root/reference)."""
+    so = ROOT / "oracle" / "_ref" / "libj2kb200shim.so"
+    if not so.exists():
+        return None
+    lib = ctypes.CDLL(str(so))
+    fn = lib.b200shim_decode_bench
+    fn.restype = ctypes.c_double
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    n = 16
+    bufs = [np.frombuffer(frames[i % len(frames)], np.uint8) for i in range(n)]
+    ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    lens = (ctypes.c_int64 * n)(*[b.size for b in bufs])
+    out = {}
+    for label, env in (("pageable_packets", "0"), ("pinned_packets", "1")):
+        os.environ["REF_PINNED_PACKETS"] = env
+        res = {}
+        for t in contexts:
+            reps = max(3, (48 * t + n - 1) // n)           # at least 48 timed frames per context
+            s = fn(ptrs, lens, n, t, reps, 0)               # the harness decodes one frame per context before its clock starts
+            if s < 0:
+                return {"error": "shim decode failed"}
+            res[str(t)] = n * reps / s
+        out[label] = res
+    os.environ.pop("REF_PINNED_PACKETS", None)
+    return {"fps_by_contexts": out, "unit": "frames/s",
+            "note": "same workload through FFCodec.cb.decode of the shim, one decoder context per frame thread, pictures "
+                    "from the shim's page-locked frame pool; packets in ordinary av_malloc'ed memory (what libavformat "
+                    "hands over) or in page-locked memory (a caller-owned buffer pool); steady state"}
+
 
 # ---- this repo's arm --------------------------------------------------------------------------------
 def run_ours(args):
@@ -270,13 +363,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     # keep this rank's host threads and pinned buffers on the CPUs next to its GPU (matters for the end-to-end
     # leg on multi-socket boxes: every frame crosses PCIe twice)
-    affinity = None
+    affinity, numa_nodes = None, None
     try:
+        numa_nodes = (Path("/sys/devices/system/node/online").read_text().strip())
         import pynvml
         pynvml.nvmlInit()
-        h = pynvml.nvmlDeviceGetHandleByIndex(local)
-        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
-        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        words = pynvml.nvmlDeviceGetCpuAffinity(hnd, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (wd >> b) & 1}
         cpus &= os.sched_getaffinity(0)
         if cpus and len(cpus) < len(os.sched_getaffinity(0)):
             os.sched_setaffinity(0, cpus)
@@ -292,22 +386,18 @@ def run_ours(args):
         if dist is not None:
             dist.barrier()
 
-    def max_over_ranks(x: float) -> float:
+    def reduce(x: float, op: str) -> float:
         if dist is None:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op={"max": dist.ReduceOp.MAX, "min": dist.ReduceOp.MIN, "sum": dist.ReduceOp.SUM}[op])
         return float(t.item())
 
-    def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    def max_over_ranks(x: float) -> float:
+        return reduce(x, "max")
 
     w, h = W // args.scale, H // args.scale
-    frames = make_frames(args.distinct, scale=args.scale)
+    frames, hashes = make_frames(args.distinct, scale=args.scale, with_hashes=True)
     D = len(frames)
     B = args.frames_per_step
     K, Wm = args.steps, args.warmup
@@ -345,6 +435,8 @@ def run_ours(args):
     kern_ms = max(a.elapsed_time(b) for a in ev0 for b in ev1)
     kern_ms = max_over_ranks(kern_ms)
     launches_per_frame = dec.launches(0)
+    # the pictures the kernel-only leg left in HBM are the lossless sources of the frames staged in the slots
+    kernel_ok = all(sha1(dec.fetch(s, infos[s])) == hashes[s % D] for s in range(min(S, D)))
 
     # per-stage timing, one frame at a time on one stream (the roofline / entropy numbers)
     stage_ms = np.zeros(6)
@@ -357,24 +449,40 @@ def run_ours(args):
     dec.close()
 
     # ---------------- PCIe reference point for the end-to-end number ----------------
+    # bare pinned copies, ALL ranks at the same time (barrier on both sides): what the platform lets N GPUs move
+    # to and from host memory together, to hold against what the decoder delivers end to end
     pcie = {}
     try:
         nb = 256 << 20
         hbuf = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
         dbuf = torch.empty(nb, dtype=torch.uint8, device="cuda")
-        for name, (dst, src) in (("d2h_gbs", (hbuf, dbuf)), ("h2d_gbs", (dbuf, hbuf))):
-            dst.copy_(src, non_blocking=True)
+        h2 = torch.empty(nb, dtype=torch.uint8, pin_memory=True)
+        d2 = torch.empty(nb, dtype=torch.uint8, device="cuda")
+        side = torch.cuda.Stream()
+
+        def timed(copies):
             torch.cuda.synchronize()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
+            barrier()
+            t0 = time.perf_counter()
             for _ in range(4):
-                dst.copy_(src, non_blocking=True)
-            b.record()
+                for dst, src, st in copies:
+                    with torch.cuda.stream(st):
+                        dst.copy_(src, non_blocking=True)
             torch.cuda.synchronize()
-            pcie[name] = 4 * nb / (a.elapsed_time(b) * 1e-3) / 1e9
-        del hbuf, dbuf
-    except Exception:
-        pcie = {}
+            dt = time.perf_counter() - t0
+            barrier()
+            return 4 * nb / dt / 1e9
+
+        cur = torch.cuda.current_stream()
+        for name, copies in (("d2h_gbs", [(hbuf, dbuf, cur)]), ("h2d_gbs", [(dbuf, hbuf, cur)]),
+                             ("both_gbs_each_way", [(hbuf, dbuf, cur), (d2, h2, side)])):
+            timed(copies)
+            g = timed(copies)
+            pcie[name] = {"this_rank": g, "sum_over_ranks": reduce(g, "sum"), "min_rank": reduce(g, "min"),
+                          "max_rank": reduce(g, "max")} if world > 1 else g
+        del hbuf, dbuf, h2, d2
+    except Exception as ex:                               # noqa: BLE001
+        pcie = {"error": str(ex)[:100]}
 
     # ---------------- end to end: host buffers in, host picture out ----------------
     T = args.host_threads
@@ -385,69 +493,68 @@ def run_ours(args):
     # frame's codestream + tables and the D2H of its picture happen inside the timed region
     pkts = [fb.PinnedPacket(f) for f in frames]
     h2d_seen = [0] * T
+    failed = [0] * T
+    last = {}                                   # (thread, buffer) -> index of the frame decoded into it last
 
-    def e2e_worker(t, nsteps, outs=None):
+    def e2e_worker(t, nsteps, outs):
         torch.cuda.set_device(local)
-        d, pf = decs[t], (outs or pins)[t]
+        d, pf = decs[t], outs[t]
         pending = []
         for _ in range(nsteps):
             for n, i in enumerate(per_thread[t]):
                 if len(pending) == len(pf):
-                    d.wait(pending.pop(0))
+                    s0 = pending.pop(0)
+                    d.wait(s0)
+                    failed[t] += d.blocks_failed(s0)
                 slot = d.submit(pkts[i % D], pf[n % len(pf)])
+                last[(t, n % len(pf))] = i % D
                 pending.append(slot)
                 h2d_seen[t] = d.h2d_bytes(slot)
         for s in pending:
             d.wait(s)
+            failed[t] += d.blocks_failed(s)
 
-    def e2e_run(nsteps, outs=None):
+    def e2e_run(nsteps, outs):
         th = [threading.Thread(target=e2e_worker, args=(t, nsteps, outs)) for t in range(T)]
         for x in th:
             x.start()
         for x in th:
             x.join()
 
-    e2e_run(max(1, min(Wm, 3)))
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(K)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
+    def verify(outs, fetch):
+        """every output buffer of the leg holds the lossless source of the frame decoded into it last"""
+        return all(sha1(fetch(outs[t][b])) == hashes[i] for (t, b), i in last.items())
+
+    def timed_leg(outs, fetch, warm):
+        last.clear()
+        e2e_run(warm, outs)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        e2e_run(K, outs)
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        barrier()
+        return max_over_ranks(sec), verify(outs, fetch)
+
+    e2e_s, ok = timed_leg(pins, lambda f: f.buffer, max(1, min(Wm, 3)))
+    chk_idx = last.get((0, 0), 0)                 # the frame whose picture sits in thread 0's first buffer
     clocks = sampler.stop()                       # sampled across both timed regions (kernel-only and end to end)
-    barrier()
-    e2e_s = max_over_ranks(e2e_s)
     # row N2 (zero-copy output): the same calls with the output planes in DEVICE memory, as AV_PIX_FMT_CUDA
     # frames would be -- only the codestream crosses PCIe
     devs = [[fb.DeviceFrame(info, device=local) for _ in range(args.slots_e2e)] for _ in range(T)]
-    e2e_run(1, devs)
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(K, devs)
-    torch.cuda.synchronize()
-    e2e_dev_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_dev_s, dev_ok = timed_leg(devs, lambda f: f.download(), 1)
+    for row in devs:
+        for f in row:
+            f.close()
     # what a caller gets WITHOUT a pinned frame pool: packets and pictures in ordinary (pageable) memory, the library
     # stages both through its own pinned buffers (one extra host copy each way)
     pkts_pinned = pkts
     pkts = [bytes(f) for f in frames]
     pages = [[fb.PageableFrame(info) for _ in range(args.slots_e2e)] for _ in range(T)]
-    e2e_run(1, pages)
-    torch.cuda.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_run(K, pages)
-    torch.cuda.synchronize()
-    e2e_page_s = max_over_ranks(time.perf_counter() - t0)
-    page_ok = bool(np.array_equal(pages[0][0].buffer, pins[0][0].buffer))
+    e2e_page_s, page_ok = timed_leg(pages, lambda f: f.buffer, 1)
     pkts = pkts_pinned
-    dev_ok = bool(np.array_equal(devs[0][0].download(), pins[0][0].buffer))
-    for row in devs:
-        for f in row:
-            f.close()
-    # correctness of what was just timed: the last picture of thread 0 must be the lossless source
-    check = pins[0][0].buffer.view(np.uint16)
-    ok = bool(check.size == w * h * 3 and int(check.max()) > 0)
+    gpu_chk = sha1(pins[0][0].buffer)
     for d in decs:
         d.close()
 
@@ -468,6 +575,8 @@ def run_ours(args):
     alg_bytes = samples * 6.0                      # 4 B coefficient read + 2 B output write per sample
     final_ms = float(stage_ms[5])
     achieved = alg_bytes / (final_ms * 1e-3) / 1e9 if final_ms > 0 else 0.0
+    stage_total_ms = float(stage_ms[4] + stage_ms[5])
+    stage_achieved = alg_bytes / (stage_total_ms * 1e-3) / 1e9 if stage_total_ms > 0 else 0.0
     traffic = None
     try:
         traffic = json.loads((ROOT / "profiles" / "final_kernel_traffic.json").read_text()).get("bytes_per_launch")
@@ -488,13 +597,16 @@ def run_ours(args):
                        "l2": "inputs larger than L2: %d MB of coefficient planes + %d MB codestream per frame, "
                              "%d frames cycled" % (int(samples * 4 / 1e6), int(len(frames[0]) / 1e6), S),
                        "e2e_host_threads": T, "e2e_slots_per_thread": args.slots_e2e,
-                       "e2e_cpu_affinity": affinity,
+                       "e2e_cpu_affinity": affinity, "host_numa_nodes": numa_nodes, "host_cpus": os.cpu_count(),
                        "e2e_buffers": "codestreams and output pictures in pinned host memory",
-                       "e2e_timer": "wall clock bracketed by device synchronisation (includes host parsing)"},
+                       "e2e_timer": "wall clock bracketed by device synchronisation (includes host parsing)",
+                       "pcie_bare_copies_all_ranks_at_once": pcie,
+                       "e2e_device_frames_fps": frames_total / e2e_dev_s,
+                       "e2e_d2h_gbs_all_ranks": d2h_step * K * world / e2e_s / 1e9},
             "e2e": {"value": e2e, "unit": "Mpixel/s", "fps": frames_total / e2e_s,
                     "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step), "output_check": ok,
                     "d2h_gbs_achieved": d2h_step * K / e2e_s / 1e9, "h2d_gbs_achieved": h2d_step * K / e2e_s / 1e9,
-                    "pcie_measured": pcie,
+                    "pcie_measured": pcie, "blocks_failed": int(sum(failed)),
                     "bound": "PCIe device->host: every decoded 4K rgb48 frame is 49.8 MB"},
             "e2e_pageable_frames": {"value": frames_total * pix / e2e_page_s / 1e6, "unit": "Mpixel/s",
                                     "fps": frames_total / e2e_page_s, "output_check": page_ok,
@@ -506,12 +618,20 @@ def run_ours(args):
                                   "d2h_bytes_per_step": 0, "output_check": dev_ok,
                                   "note": "same C-ABI calls with the output planes in device memory "
                                           "(AV_PIX_FMT_CUDA-style frames, SURVEY 8(f) N2): not the contract's e2e"},
+            "checks": {"what": "SHA-1 of every output buffer the timed legs left behind == SHA-1 of the lossless source "
+                               "of the frame decoded into it last",
+                       "kernel_only": kernel_ok, "e2e": ok, "e2e_pageable": page_ok, "e2e_device_frames": dev_ok,
+                       "compared_frame": chk_idx, "source_sha1": hashes[chk_idx], "gpu_sha1": gpu_chk},
             "gpu_launches": int(launches_per_frame * B * K),
             "roofline": {"kernel": "idwt_stream_final_kernel (last 5/3 level + RCT + level shift + clip + rgb48 pack)",
                          "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": traffic,
                          "algorithmic_bytes_per_launch": alg_bytes, "ms_per_launch": final_ms,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s"},
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
+                         "stage": {"what": "all inverse-DWT launches of a frame (intermediate levels + fused last level): "
+                                           "SURVEY 8(d) t_dwt_mct_pack, same algorithmic bytes",
+                                   "ms": stage_total_ms, "achieved": stage_achieved,
+                                   "frac": stage_achieved / peak if peak else None}},
             "entropy": {"kernels": "ht_unstuff_kernel (warp per block) -> ht_vlc_kernel (lane per block) -> "
                                    "ht_magsgn_kernel (warp per block)",
                         "ms_per_frame_one_stream": ht_ms,
@@ -529,14 +649,23 @@ def run_ours(args):
             line["other_workloads"] = [extra_workload(fb, torch, local, c, lbl, 16 if c != "part1_4k" else 8,
                                                       max(2, min(K, 4)) if c != "part1_4k" else 2, T, args.slots_e2e)
                                        for c, lbl in EXTRA]
+            line["e2e_ffcodec_shim"] = shim_leg(frames)
         if world == 1 and not args.no_cpu_baseline:
             fn, kind = cpu_decoder()
             cores = os.cpu_count() or 1
             n = max(cores, 4)
             sec = cpu_decode_seconds(fn, frames[:2], n, cores)
+            sec1 = cpu_decode_seconds(fn, frames[:2], 2, 1)
             line["cpu_baseline"] = {"value": n * pix / sec / 1e6, "unit": "Mpixel/s", "fps": n / sec, "cores": cores,
                                     "kind": kind, "sample": f"{n} frames of the same workload on {cores} threads "
-                                                            f"({sec:.1f} s wall)"}
+                                                            f"({sec:.1f} s wall)",
+                                    "fps_one_thread": 2 / sec1}
+            # BASELINE.md section 2, "correctness in the same run": the CPU decoder's picture of one frame against
+            # the GPU's picture of it (as the timed end-to-end leg left it) and against the lossless source
+            ref_sha = cpu_picture_sha1(frames[chk_idx], int(d2h_step // B))
+            line["checks"]["cpu_sha1"] = ref_sha
+            line["checks"]["cpu_kind"] = kind
+            line["checks"]["gpu_equals_cpu_decoder"] = bool(ref_sha and ref_sha == gpu_chk == hashes[chk_idx])
         emit(line)
     if dist is not None:
         dist.destroy_process_group()

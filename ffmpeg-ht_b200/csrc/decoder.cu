@@ -111,7 +111,10 @@ struct HtPlan {
         if (d.flags & J2K_CBLK_MQ)                  /* Part-1 block: own kernel; without data it only needs zeros */
             return d.npasses && d.length ? 5 : 2;
         const bool refine = d.npasses && (d.npasses % 3) != 1;
-        if (d.w > 64)
+        /* the split pipeline sizes its shared memory by the longest segment of its class: a block whose lengths
+         * are beyond anything 4096 samples can need (damaged or crafted packet headers) must not cost every other
+         * block of the frame its occupancy, so it goes with the wide blocks */
+        if (d.w > 64 || d.Lcup > 16384 || d.Lref > 8192)
             return refine ? 4 : 3;
         if (refine)
             return 0;

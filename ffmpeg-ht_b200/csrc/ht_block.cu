@@ -20,6 +20,12 @@
  * The CxtVLC tables (2 x 1024 x u16, cxtvlc_tables.h) are staged in shared memory per CTA.
  * Integer/bit work throughout: no tensor cores (nothing here is a contraction).
  */
+/* Two warps per CTA: this kernel also takes the blocks whose segment lengths are out of any sane range (up to
+ * 65535 bytes each, straight from damaged packet headers); even those must fit 227 KB of shared memory, so that a
+ * crafted block costs its own decode and not the frame */
+#ifndef B200J2K_WARPS_PER_CTA
+#define B200J2K_WARPS_PER_CTA 2
+#endif
 #include "ht_common.cuh"
 
 namespace b200j2k {

@@ -21,6 +21,7 @@
  *
  * Nothing in the product (ffmpeg-ht_b200/) may link or load this file.
  */
+#define _GNU_SOURCE            /* pthread_barrier_t under -std=c17 */
 #include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -352,32 +353,48 @@ typedef struct BenchJob {
     const int64_t *len;
     int nframes, first, step, bitexact, reps;
     int errors;
+    pthread_barrier_t *start;
 } BenchJob;
+
+static int bench_decode_one(AVCodecContext *avctx, const uint8_t *data, int64_t len)
+{
+    AVPacket pkt;
+    memset(&pkt, 0, sizeof(pkt));
+    pkt.data = (uint8_t *)data;                           /* padded copies made by decode_bench, outside the timing */
+    pkt.size = (int)len;
+    AVFrame *frame = av_mallocz(sizeof(AVFrame));
+    int got = 0;
+    avctx->pix_fmt = AV_PIX_FMT_NONE;
+    const int bad = REF_CODEC.cb.decode(avctx, frame, &got, &pkt) < 0 || !got;
+    release_frame(frame);
+    av_free(frame);
+    return bad;
+}
 
 static void *bench_worker(void *arg)
 {
     BenchJob *j = arg;
     AVCodecContext *avctx = ctx_open(j->bitexact);
-    for (int r = 0; r < j->reps; r++) {
-        for (int i = j->first; i < j->nframes; i += j->step) {
-            AVPacket pkt;
-            memset(&pkt, 0, sizeof(pkt));
-            pkt.data = (uint8_t *)j->cs[i];               /* padded copies made by decode_bench, outside the timing */
-            pkt.size = (int)j->len[i];
-            AVFrame *frame = av_mallocz(sizeof(AVFrame));
-            int got = 0;
-            avctx->pix_fmt = AV_PIX_FMT_NONE;
-            if (REF_CODEC.cb.decode(avctx, frame, &got, &pkt) < 0 || !got)
-                j->errors++;
-            release_frame(frame);
-            av_free(frame);
-        }
-    }
+    /* steady state is what is measured: opening the context and the first frame of a sequence (tables, buffers
+     * that grow once) happen before the clock starts, for the reference and for the shim alike */
+    if (j->first < j->nframes)
+        j->errors += bench_decode_one(avctx, j->cs[j->first], j->len[j->first]);
+    pthread_barrier_wait(j->start);
+    for (int r = 0; r < j->reps; r++)
+        for (int i = j->first; i < j->nframes; i += j->step)
+            j->errors += bench_decode_one(avctx, j->cs[i], j->len[i]);
     ctx_close(avctx);
     return NULL;
 }
 
-/* decodes every codestream `reps` times using `threads` decoder contexts; returns seconds (<0 on error) */
+#ifndef REF_STAGE_API
+int b200j2k_host_register(void *p, int64_t bytes);
+int b200j2k_host_unregister(void *p);
+#endif
+
+/* decodes every codestream `reps` times using `threads` decoder contexts; returns seconds (<0 on error).
+ * REF_PINNED_PACKETS=1 (shim build only): the packets live in page-locked memory, as a caller's own AVBuffer pool
+ * could provide them; default: ordinary av_malloc'ed packets, what libavformat hands over. */
 double REF_NAME(decode_bench)(const uint8_t *const *cs, const int64_t *len, int nframes, int threads,
                         int reps, int bitexact)
 {
@@ -388,28 +405,48 @@ double REF_NAME(decode_bench)(const uint8_t *const *cs, const int64_t *len, int 
     pthread_t th[256];
     BenchJob jobs[256];
     struct timespec t0, t1;
+    pthread_barrier_t start;
     /* make sure one-time init (LUTs, log level) is outside the timed region */
     ctx_close(ctx_open(bitexact));
     /* the packets as a demuxer hands them over: padded (AV_INPUT_BUFFER_PADDING_SIZE), allocated once */
     uint8_t **padded = av_calloc(nframes, sizeof(*padded));
+    int pinned = 0;
     for (int i = 0; i < nframes; i++) {
         padded[i] = av_mallocz(len[i] + AV_INPUT_BUFFER_PADDING_SIZE);
         memcpy(padded[i], cs[i], len[i]);
     }
-    clock_gettime(CLOCK_MONOTONIC, &t0);
+#ifndef REF_STAGE_API
+    if (getenv("REF_PINNED_PACKETS") && atoi(getenv("REF_PINNED_PACKETS"))) {
+        pinned = 1;
+        for (int i = 0; i < nframes; i++)
+            if (b200j2k_host_register(padded[i], len[i] + AV_INPUT_BUFFER_PADDING_SIZE) < 0)
+                pinned = -1;
+    }
+#endif
+    pthread_barrier_init(&start, NULL, threads + 1);
     for (int t = 0; t < threads; t++) {
-        jobs[t] = (BenchJob){ (const uint8_t *const *)padded, len, nframes, t, threads, bitexact, reps, 0 };
+        jobs[t] = (BenchJob){ (const uint8_t *const *)padded, len, nframes, t, threads, bitexact, reps, 0, &start };
         pthread_create(&th[t], NULL, bench_worker, &jobs[t]);
     }
+    pthread_barrier_wait(&start);
+    clock_gettime(CLOCK_MONOTONIC, &t0);
     int errors = 0;
     for (int t = 0; t < threads; t++) {
         pthread_join(th[t], NULL);
         errors += jobs[t].errors;
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);
-    for (int i = 0; i < nframes; i++)
+    pthread_barrier_destroy(&start);
+    for (int i = 0; i < nframes; i++) {
+#ifndef REF_STAGE_API
+        if (pinned)
+            b200j2k_host_unregister(padded[i]);
+#endif
         av_free(padded[i]);
+    }
     av_free(padded);
+    if (pinned < 0)
+        return -2.0;
     if (errors)
         return -1.0;
     return (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);

@@ -88,6 +88,37 @@ def test_blocks_vs_oracle(npasses):
         assert np.array_equal(got[i], want), (i, b["w"], b["h"], b["npasses"])
 
 
+def test_blocks_with_absurd_segment_lengths():
+    """Damaged packet headers can announce cleanup / refinement segments of tens of kilobytes for a small block.
+    Such blocks run on the general kernel (their lengths would size the shared memory of the whole split pipeline):
+    a valid block padded in front to 20 000 and 60 000 bytes (the MagSgn bytes then differ, the suffix stays valid)
+    and blocks of random bytes decode exactly like the oracle, next to ordinary blocks in the same batch."""
+    rng = np.random.default_rng(311)
+    blocks = []
+    for total in (20000, 60000, 17000, 65000):
+        w, h = int(rng.integers(8, 65)), int(rng.integers(8, 65))
+        coef = (rng.standard_normal((h, w)) * 300).astype(np.int32)
+        M_b = 16
+        data, Lcup, Lref = j2kgen.encode_block(coef, 1, False, M_b)
+        pad = bytes(rng.integers(0, 255, total - Lcup, dtype=np.uint8))        # 0xFF-free: no stuffing trouble
+        blocks.append(dict(data=pad + data, npasses=1, Lcup=total, Lref=0, zbp=M_b - 1, w=w, h=h, M_b=M_b, roi=0, vsc=0))
+        junk = bytes(rng.integers(0, 256, total, dtype=np.uint8))
+        blocks.append(dict(data=junk, npasses=1, Lcup=total, Lref=0, zbp=3, w=w, h=h, M_b=M_b, roi=0, vsc=0))
+        blocks.append(dict(data=data, npasses=1, Lcup=Lcup, Lref=0, zbp=M_b - 1, w=w, h=h, M_b=M_b, roi=0, vsc=0))
+    # refinement segments of absurd length behind a valid cleanup segment
+    for lref in (9000, 50000):
+        coef = (rng.standard_normal((32, 32)) * 300).astype(np.int32)
+        data, Lcup, Lref = j2kgen.encode_block(coef, 3, False, 15)
+        tail = bytes(rng.integers(0, 256, lref - Lref, dtype=np.uint8))
+        blocks.append(dict(data=data + tail, npasses=3, Lcup=Lcup, Lref=lref, zbp=14 - 1, w=32, h=32, M_b=16, roi=0, vsc=0))
+    got, status = fb.ht_blocks(blocks)
+    for i, b in enumerate(blocks):
+        r, want = ht_block(oracle().oracle_ht_block, b["data"], b["npasses"], b["Lcup"], b["Lref"], b["zbp"], b["w"],
+                           b["h"], b["M_b"], b["roi"], b["vsc"])
+        assert (r > 0) == (status[i] > 0), (i, r, status[i])
+        assert np.array_equal(got[i], want), (i, b["Lcup"], b["Lref"])
+
+
 def test_damaged_blocks_zeroed_like_reference():
     """Quirk Q1: an error inside a block leaves a block of zeros; the damage is chosen so that it hits the
     segment header / exponent bound (cases where oracle and kernel must agree)."""
@@ -712,7 +743,7 @@ def test_device_resident_output(dec):
 
 
 # ---- BASELINE.json configs at full size: lossless round trip (size-independent property) ---------------
-@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5"])
+@pytest.mark.parametrize("name", ["cfg1", "cfg3", "cfg4", "cfg5", "target8k"])
 def test_baseline_configs_full_size(name, dec):
     cs, planes, p = j2kgen.make_config(name)
     c = j2kgen.CONFIGS[name]
