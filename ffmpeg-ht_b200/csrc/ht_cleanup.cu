@@ -470,19 +470,28 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
     const int QW = (w + 1) >> 1, QH = (h + 1) >> 1;
     const bool act = lane < QW;
     const bool vec = (((d.dst_off | dstride) & 1) == 0);      /* 8-byte aligned sample pairs */
-    uint32_t nextq = act ? q[lane] : 0;
+    /* the quad words come from HBM scratch: two rows ahead, so the load of a row is never waited for (ncu: a quarter
+     * of this kernel's stall samples sat on the one-row-ahead load) */
+    uint32_t nextq = act ? q[lane] : 0, next2 = act && QH > 1 ? q[QW + lane] : 0;
     unsigned pE1 = 0, pE3 = 0;                           /* exponents of samples 1 and 3 of the quad above */
     uint32_t ms_pos = 0;
     bool bad = false;
     const int x = 2 * lane;
     unsigned prev_sg = 0;
     uint32_t *rowp = dst + x;
+    /* The four samples of a quad are handled as four BYTES of one register where that saves instructions (ncu: this
+     * kernel is bound by the integer pipes, ~260 instructions per quad row before): bit i of rho / emb_k becomes byte
+     * i (multiplication by 0x00204081 puts bit i at bit 8i without a carry), the MagSgn bit counts are then
+     * m = rho * U - emb_k in all four bytes at once, their sum and their prefix sums one multiplication each.
+     * That needs 0 <= m <= 32 per byte: emb_k is a subset of rho and emb_1 of emb_k in every CxtVLC table entry
+     * (checked over both tables), U >= 1, and U is clamped to 32 -- a larger one exceeds maxbp <= 31 anyway, which
+     * condemns the block (quirk Q1): the lanes note that and carry on; one vote after the last row decides. */
     for (int qy = 0; qy < QH; qy++, rowp += 2 * (size_t)dstride) {
         const unsigned mine = nextq;                     /* u_off | rho<<1 | emb_k<<5 | emb_1<<9 | u<<16; 0 in idle lanes */
-        if (qy + 1 < QH)
-            nextq = act ? q[(qy + 1) * QW + lane] : 0;
+        nextq = next2;
+        if (qy + 2 < QH)
+            next2 = act ? q[(qy + 2) * QW + lane] : 0;
         const unsigned rho = (mine >> 1) & 15;
-        const unsigned ek = (mine >> 5) & 15, e1 = (mine >> 9) & 15;
         const int u = (int)(mine >> 16);
         int kappa = 1;
         if (qy > 0) {                                    /* :855-885 */
@@ -496,49 +505,41 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
             kappa = max(1, gamma * (m - 1));
         }
         const int U = kappa + u;
-        if (__any_sync(FULL, act && U > maxbp)) {        /* :715, :889 */
-            bad = true;
-            break;
-        }
-        int mlen[4];
-        int tot = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            mlen[i] = (((rho >> i) & 1) ? U : 0) - (int)((ek >> i) & 1);
-            tot += max(mlen[i], 0);
-        }
+        bad |= U > maxbp;                                /* :715, :889; idle lanes have U = 1 */
+        const uint32_t rhoB = (rho * 0x00204081u) & 0x01010101u;
+        const uint32_t ekB = (((mine >> 5) & 15) * 0x00204081u) & 0x01010101u;
+        const uint32_t e1B = (((mine >> 9) & 15) * 0x00204081u) & 0x01010101u;
+        const uint32_t mB = rhoB * (uint32_t)min(U, 32) - ekB;           /* MagSgn bits of the four samples */
+        const int tot = (int)((mB * 0x01010101u) >> 24);
         const int incl = warp_scan_add(tot);
-        uint32_t pos = ms_pos + (uint32_t)(incl - tot);
+        const uint32_t pos0 = ms_pos + (uint32_t)(incl - tot);
         ms_pos += (uint32_t)__shfl_sync(FULL, incl, 31);
+        const uint32_t preB = mB * 0x01010100u;                          /* bits in front of each sample, inside the quad */
         uint32_t mu[4];
         unsigned E1 = 0, E3 = 0;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             /* straight-line on purpose (no divergent regions in the row loop): a sample without MagSgn bits
              * reads a zero-length field */
-            const int m = mlen[i];
-            const int mm = max(m, 0);
-            const uint32_t p = min(pos, ms_bits);        /* past the end: ones */
-            uint32_t v = ms_read(ms, p, mm);
-            v += m > 0 ? ((e1 >> i) & 1u) << mm : 0u;
-            pos += mm;
+            const int mm = (int)((mB >> (8 * i)) & 0xFF);
+            const uint32_t p = min(pos0 + ((preB >> (8 * i)) & 0xFF), ms_bits);   /* past the end: ones */
+            uint32_t v = ms_read(ms, p, mm) | (((e1B >> (8 * i)) & 1u) << mm);
             const unsigned E = 32 - __clz(v | 1);        /* :419-425 */
-            if (i == 1) E1 = m != 0 ? E : 0;
-            if (i == 3) E3 = m != 0 ? E : 0;
+            if (i == 1) E1 = mm ? E : 0;
+            if (i == 3) E3 = mm ? E : 0;
             uint32_t val;
             if (DQ == DQ_INT53 && !REFINE) {
                 /* mu >> (31 - M_b) with mu = ((v >> 1) + 1) << pLSB | 1 << (pLSB - 1), then the sign: the
                  * shifts are per-block constants (dequantization_int, jpeg2000dec.c:2120-2151) */
-                const uint32_t mag = (uint32_t)(((int32_t)v >> 1) + 1);
+                const uint32_t mag = (v >> 1) + 1;
                 const int32_t r = (int32_t)(((mag << dq_up) >> dq_dn) | dq_half);
                 val = (uint32_t)((v & 1u) ? -r : r);
             } else {
-                val = (uint32_t)(((int32_t)v >> 1) + 1) << pLSB;
+                val = ((v >> 1) + 1) << pLSB;
                 val |= 1u << (pLSB - 1);
                 val |= (v & 1u) << 31;
             }
-            val = m != 0 ? val : 0u;
-            mu[i] = val;
+            mu[i] = mm ? val : 0u;
         }
         pE1 = E1;
         pE3 = E3;
@@ -582,6 +583,7 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
             }
         }
     }
+    bad = __any_sync(FULL, bad);
     if (REFINE && (QH & 1) && !bad)
         sigb[(QH >> 1) * 32 + lane] = (uint8_t)((prev_sg & 3) | (((prev_sg >> 2) & 3) << 4));
     if (bad) {
@@ -910,7 +912,8 @@ int launch_ht_cleanup(cudaStream_t stream, const CblkDesc *descs, const uint32_t
     int launches = 0, r;
     const int n_vlc = n_refine + n_coded;
     uint32_t *scr = (uint32_t *)scratch;
-    if (n_vlc > 0) {
+    static const int skip = getenv("B200J2K_SKIP") ? atoi(getenv("B200J2K_SKIP")) : 0;   /* tuning: marginal cost of a kernel */
+    if (n_vlc > 0 && !(skip & 1)) {
         const int warp_words = 2 * ht_stream_words(max_Lcup < 4079 ? max_Lcup : 4079);
         const size_t smem0 = (size_t)warp_words * 4 * WARPS_PER_CTA;
         if ((r = set_smem((const void *)ht_unstuff_kernel, smem0)) < 0)
@@ -930,7 +933,7 @@ int launch_ht_cleanup(cudaStream_t stream, const CblkDesc *descs, const uint32_t
     }
     if (after_unstuff)
         cudaEventRecord(after_unstuff, stream);
-    if (n_vlc > 0) {
+    if (n_vlc > 0 && !(skip & 2)) {
         static const int active = [] {
             const char *e = getenv("B200J2K_VLC_ACTIVE");
             const int a = e ? atoi(e) : VLC_ACTIVE_LANES;
@@ -942,7 +945,7 @@ int launch_ht_cleanup(cudaStream_t stream, const CblkDesc *descs, const uint32_t
     }
     if (after_vlc)
         cudaEventRecord(after_vlc, stream);
-    if (n_coded + n_zero > 0) {
+    if (n_coded + n_zero > 0 && !(skip & 4)) {
         const int stream_words = (max_Lcup + 3) / 4 + 4;
         const size_t smem2 = (size_t)stream_words * 4 * WARPS_PER_CTA;
         if ((r = set_smem((const void *)ht_magsgn_kernel<false>, smem2)) < 0)

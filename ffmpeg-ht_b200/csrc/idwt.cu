@@ -21,6 +21,8 @@
  * (a - c*(b+d) as add, multiply, subtract), so no FMA contraction can change a bit; lrintf is
  * __float2int_rn (round to nearest even).
  */
+#include <cstdlib>
+
 #include "idwt_common.cuh"
 
 namespace b200j2k {
@@ -456,6 +458,9 @@ int run_levels(cudaStream_t stream, const IdwtFrame &f, int max_levels, bool any
 int launch_idwt_frame(cudaStream_t stream, const IdwtFrame &f)
 {
     int launches = 0;
+    static const int skip = getenv("B200J2K_SKIP") ? atoi(getenv("B200J2K_SKIP")) : 0;   /* tuning: marginal cost of the stage */
+    if (skip & 8)
+        return 0;
     idwt_stream_cache_begin(f.stream_cache, f.geom_serial, f);
     /* pass 1: intermediate levels of every transform type present (host copies of the tables size the grids) */
     for (int type = 0; type < 3; type++) {
