@@ -885,6 +885,16 @@ int b200j2k_device_download(void *dst_host, const void *src_device, int64_t byte
     return cudaMemcpy(dst_host, src_device, (size_t)bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : B200J2K_ERR_DEVICE;
 }
 
+int b200j2k_pointer_device(const void *p)
+{
+    cudaPointerAttributes a;
+    if (device_ok() <= 0 || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged ? a.device : -1;
+}
+
 void *b200j2k_host_alloc(int64_t bytes)
 {
     void *p = nullptr;

@@ -22,6 +22,12 @@
  * AVFrame itself instead of going through the library's staging buffer and a 50 MB memcpy per 4K frame
  * (private option "pinned_frames", default on).  With a caller-supplied get_buffer2 the picture is taken from
  * ff_thread_get_buffer() as in the reference.
+ * Added: device-resident pictures.  When the caller offers a CUDA device or frames
+ * context (AVCodecContext.hw_device_ctx / hw_frames_ctx, libavutil/hwcontext_cuda.c:81-260) the decoder proposes
+ * AV_PIX_FMT_CUDA through ff_get_format() the way cuviddec.c does; if that is what get_format picks, the picture is
+ * taken from the frames context with av_hwframe_get_buffer() -- AVFrame.data[] are device pointers, sw_format is the
+ * format the reference would have produced -- and the kernels' output is copied there device to device: it never
+ * crosses PCIe.  Without such a context nothing changes.
  * What it refuses (AVERROR_PATCHWELCOME, as the library reports): Part-1 code-blocks with arithmetic-coding bypass or
  * termination on each pass -- a build that wants those keeps the native decoder registered as fallback under a
  * different name.
@@ -29,6 +35,7 @@
 #include <stdatomic.h>
 
 #include "libavutil/buffer.h"
+#include "libavutil/hwcontext.h"
 #include "libavutil/imgutils.h"
 #include "libavutil/opt.h"
 #include "libavutil/pixdesc.h"
@@ -49,6 +56,8 @@ typedef struct B200J2KContext {
     int pinned_frames;      /* own the frame pool (page-locked memory) while the caller uses the default get_buffer2 */
     AVBufferPool *pool;
     size_t pool_size;
+    AVBufferRef *hwframes;  /* frames context this decoder created from the caller's hw_device_ctx */
+    int cur_device;         /* device the library context lives on */
 } B200J2KContext;
 
 /* ---- pinned frame pool ------------------------------------------------------------------------------------ */
@@ -114,6 +123,61 @@ static int b200j2k_get_pinned_frame(AVCodecContext *avctx, B200J2KContext *s, AV
     return 0;
 }
 
+/* Device-resident picture.  Returns 1 with `f` filled from a CUDA frames context, 0 when the caller's get_format did
+ * not pick AV_PIX_FMT_CUDA (the software path goes on), < 0 on error.  Mirrors cuviddec.c: the frames context is the
+ * caller's (hw_frames_ctx), else one made here on the caller's device (hw_device_ctx) for this picture size. */
+static int b200j2k_get_cuda_frame(AVCodecContext *avctx, B200J2KContext *s, AVFrame *f, enum AVPixelFormat sw_fmt)
+{
+    const enum AVPixelFormat fmts[] = { AV_PIX_FMT_CUDA, sw_fmt, AV_PIX_FMT_NONE };
+    AVBufferRef *ref = avctx->hw_frames_ctx;
+    int ret;
+
+    avctx->pix_fmt = sw_fmt;
+    ret = ff_get_format(avctx, fmts);
+    if (ret < 0)
+        return ret;
+    if (ret != AV_PIX_FMT_CUDA) {
+        avctx->pix_fmt = sw_fmt;
+        return 0;
+    }
+    if (!ref) {
+        AVHWFramesContext *fc = s->hwframes ? (AVHWFramesContext *)s->hwframes->data : NULL;
+        if (!fc || fc->sw_format != sw_fmt || fc->width != avctx->width || fc->height != avctx->height) {
+            av_buffer_unref(&s->hwframes);
+            s->hwframes = av_hwframe_ctx_alloc(avctx->hw_device_ctx);
+            if (!s->hwframes)
+                return AVERROR(ENOMEM);
+            fc = (AVHWFramesContext *)s->hwframes->data;
+            fc->format    = AV_PIX_FMT_CUDA;
+            fc->sw_format = sw_fmt;
+            fc->width     = avctx->width;
+            fc->height    = avctx->height;
+            if ((ret = av_hwframe_ctx_init(s->hwframes)) < 0) {
+                av_buffer_unref(&s->hwframes);
+                return ret;
+            }
+        }
+        ref = s->hwframes;
+    } else {
+        const AVHWFramesContext *fc = (const AVHWFramesContext *)ref->data;
+        if (fc->format != AV_PIX_FMT_CUDA || fc->sw_format != sw_fmt || fc->width < avctx->width ||
+            fc->height < avctx->height) {
+            av_log(avctx, AV_LOG_ERROR, "hw_frames_ctx does not fit the picture (%s %dx%d wanted)\n",
+                   av_get_pix_fmt_name(sw_fmt), avctx->width, avctx->height);
+            return AVERROR(EINVAL);
+        }
+    }
+    avctx->pix_fmt    = AV_PIX_FMT_CUDA;
+    avctx->sw_pix_fmt = sw_fmt;
+    if ((ret = ff_decode_frame_props(avctx, f)) < 0)
+        return ret;
+    if ((ret = av_hwframe_get_buffer(ref, f, 0)) < 0)
+        return ret;
+    f->width  = avctx->width;
+    f->height = avctx->height;
+    return 1;
+}
+
 static av_cold int b200j2k_ff_init(AVCodecContext *avctx)
 {
     B200J2KContext *s = avctx->priv_data;
@@ -140,6 +204,7 @@ static av_cold int b200j2k_ff_init(AVCodecContext *avctx)
         static atomic_uint next_device;      /* frame threads open one context each: spread them */
         device = (int)(atomic_fetch_add(&next_device, 1) % (unsigned)ndev);
     }
+    s->cur_device = device;
     return b200j2k_create(&s->dec, device, 1, flags);
 }
 
@@ -149,6 +214,7 @@ static av_cold int b200j2k_ff_close(AVCodecContext *avctx)
     b200j2k_destroy(s->dec);
     s->dec = NULL;
     av_buffer_pool_uninit(&s->pool);
+    av_buffer_unref(&s->hwframes);
     return 0;
 }
 
@@ -183,12 +249,29 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
     if (avctx->skip_frame >= AVDISCARD_ALL)
         return avpkt->size;
 
+    if (avctx->hw_frames_ctx || avctx->hw_device_ctx) {
+        if ((ret = b200j2k_get_cuda_frame(avctx, s, picture, fmt)) < 0)
+            return ret;
+        if (ret > 0) {
+            /* decode on the GPU the caller's frames live on */
+            const int dev = b200j2k_pointer_device(picture->data[0]);
+            if (dev >= 0 && dev != s->cur_device) {
+                b200j2k_destroy(s->dec);
+                s->dec = NULL;
+                if ((ret = b200j2k_create(&s->dec, dev, 1, s->flags)) < 0)
+                    return ret;
+                s->cur_device = dev;
+            }
+            goto have_picture;
+        }
+    }
     if (s->pinned_frames && (!avctx->get_buffer2 || avctx->get_buffer2 == avcodec_default_get_buffer2))
         ret = b200j2k_get_pinned_frame(avctx, s, picture);
     else
         ret = ff_thread_get_buffer(avctx, picture, 0);
     if (ret < 0)
         return ret;
+have_picture:
     for (int i = 0; i < info.nplanes; i++) {
         data[i]     = picture->data[i];
         linesize[i] = picture->linesize[i];

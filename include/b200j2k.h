@@ -159,6 +159,10 @@ void *b200j2k_device_alloc(int device, int64_t bytes);
 void b200j2k_device_free(void *p);
 int b200j2k_device_download(void *dst_host, const void *src_device, int64_t bytes);
 
+/* Device ordinal of the GPU a pointer's memory lives on, -1 for host memory: lets the FFCodec shim put its decoder
+ * context next to the AV_PIX_FMT_CUDA frames the caller hands it (AVHWFramesContext, libavutil/hwcontext_cuda.c:204). */
+int b200j2k_pointer_device(const void *p);
+
 /* pinned host memory helpers for AVFrame pools (get_buffer2) */
 void *b200j2k_host_alloc(int64_t bytes);
 void b200j2k_host_free(void *p);

@@ -52,6 +52,7 @@
 #define REF_STAGE_API 1
 #else
 #define REF_NAME(x) b200shim_##x
+#include "b200j2k.h"
 #endif
 extern const FFCodec REF_CODEC;
 
@@ -95,6 +96,20 @@ int ff_decode_frame_props(AVCodecContext *avctx, AVFrame *frame)
     frame->pts = AV_NOPTS_VALUE;
     return 0;
 }
+
+#ifndef REF_STAGE_API
+/* decode.c's format negotiation, as much of it as a decoder proposing a hardware format needs: the caller's
+ * get_format picks from the list, the default takes the first software format (avcodec_default_get_format) */
+#include "libavutil/hwcontext.h"
+int ff_get_format(AVCodecContext *avctx, const enum AVPixelFormat *fmt)
+{
+    if (avctx->get_format)
+        return avctx->get_format(avctx, fmt);
+    while (*fmt != AV_PIX_FMT_NONE && (av_pix_fmt_desc_get(*fmt)->flags & AV_PIX_FMT_FLAG_HWACCEL))
+        fmt++;
+    return *fmt;
+}
+#endif
 
 static void release_frame(AVFrame *frame)
 {
@@ -237,6 +252,103 @@ int REF_NAME(decode)(const uint8_t *cs, int64_t len, int bitexact, int64_t *info
 }
 
 const char *REF_NAME(pix_fmt_name)(int fmt) { return av_get_pix_fmt_name(fmt); }
+
+#ifndef REF_STAGE_API
+/* ---- the shim with a CUDA device / frames context ------------------------------------------ */
+int standin_download(const AVFrame *f, enum AVPixelFormat sw_format, uint8_t *out, int64_t cap);
+
+static enum AVPixelFormat pick_cuda(AVCodecContext *c, const enum AVPixelFormat *fmt)
+{
+    (void)c;
+    for (; *fmt != AV_PIX_FMT_NONE; fmt++)
+        if (*fmt == AV_PIX_FMT_CUDA)
+            return *fmt;
+    return AV_PIX_FMT_NONE;
+}
+static enum AVPixelFormat pick_software(AVCodecContext *c, const enum AVPixelFormat *fmt)
+{
+    (void)c;
+    while (*fmt != AV_PIX_FMT_NONE && (av_pix_fmt_desc_get(*fmt)->flags & AV_PIX_FMT_FLAG_HWACCEL))
+        fmt++;
+    return *fmt;
+}
+
+/*
+ * Decodes `n` codestreams of one sequence with ONE decoder context the way an application with CUDA frames would.
+ * mode 0: the caller owns the frames context (avctx->hw_frames_ctx, sized from sw_name / width / height)
+ * mode 1: the caller only offers the device (avctx->hw_device_ctx): the decoder makes the frames context
+ * mode 2: a device is offered but get_format declines AV_PIX_FMT_CUDA: ordinary software frames
+ * info per frame: [0]=width [1]=height [2]=AVFrame.format [3]=bytes written [4]=1 when data[0] is device memory
+ *                 [5]=avctx->sw_pix_fmt; out receives the frames one after the other, tightly packed.
+ */
+int REF_NAME(decode_cuda)(const uint8_t *const *cs, const int64_t *len, int n, int mode, const char *sw_name, int width,
+                          int height, int64_t *info, uint8_t *out, int64_t cap)
+{
+    AVBufferRef *device = NULL, *frames = NULL;
+    int ret = av_hwdevice_ctx_create(&device, AV_HWDEVICE_TYPE_CUDA, "0", NULL, 0);
+    if (ret < 0)
+        return ret;
+    AVCodecContext *avctx = ctx_open(0);
+    if (!avctx) {
+        av_buffer_unref(&device);
+        return AVERROR(ENOMEM);
+    }
+    avctx->get_format = mode == 2 ? pick_software : pick_cuda;
+    if (mode == 0) {
+        frames = av_hwframe_ctx_alloc(device);
+        AVHWFramesContext *fc = (AVHWFramesContext *)frames->data;
+        fc->format    = AV_PIX_FMT_CUDA;
+        fc->sw_format = av_get_pix_fmt(sw_name);
+        fc->width     = width;
+        fc->height    = height;
+        if ((ret = av_hwframe_ctx_init(frames)) < 0)
+            goto end;
+        avctx->hw_frames_ctx = av_buffer_ref(frames);
+    } else {
+        avctx->hw_device_ctx = av_buffer_ref(device);
+    }
+    int64_t pos = 0;
+    for (int i = 0; i < n && ret >= 0; i++) {
+        AVPacket pkt;
+        memset(&pkt, 0, sizeof(pkt));
+        uint8_t *padded = av_mallocz(len[i] + AV_INPUT_BUFFER_PADDING_SIZE);
+        memcpy(padded, cs[i], len[i]);
+        pkt.data = padded;
+        pkt.size = (int)len[i];
+        AVFrame *frame = av_mallocz(sizeof(AVFrame));
+        frame->extended_data = frame->data;
+        int got = 0;
+        ret = REF_CODEC.cb.decode(avctx, frame, &got, &pkt);
+        if (ret >= 0 && got) {
+            int64_t *fi = info + 8 * i;
+            fi[0] = frame->width;
+            fi[1] = frame->height;
+            fi[2] = frame->format;
+            fi[4] = b200j2k_pointer_device(frame->data[0]) >= 0;
+            fi[5] = avctx->sw_pix_fmt;
+            int64_t w = frame->format == AV_PIX_FMT_CUDA ? standin_download(frame, avctx->sw_pix_fmt, out + pos, cap - pos)
+                                                         : pack_frame(avctx, frame, out + pos, cap - pos);
+            if (w < 0)
+                ret = AVERROR(EINVAL);
+            else {
+                fi[3] = w;
+                pos += w;
+            }
+        } else if (ret >= 0)
+            ret = AVERROR_INVALIDDATA;
+        release_frame(frame);
+        av_free(frame);
+        av_free(padded);
+    }
+end:
+    av_buffer_unref(&avctx->hw_frames_ctx);
+    av_buffer_unref(&avctx->hw_device_ctx);
+    ctx_close(avctx);
+    av_buffer_unref(&frames);
+    av_buffer_unref(&device);
+    return ret < 0 ? ret : 0;
+}
+#endif
 
 #ifdef REF_STAGE_API
 /* ---- stage-level entry points ---------------------------------------------------------- */
@@ -387,10 +499,6 @@ static void *bench_worker(void *arg)
     return NULL;
 }
 
-#ifndef REF_STAGE_API
-int b200j2k_host_register(void *p, int64_t bytes);
-int b200j2k_host_unregister(void *p);
-#endif
 
 /* decodes every codestream `reps` times using `threads` decoder contexts; returns seconds (<0 on error).
  * REF_PINNED_PACKETS=1 (shim build only): the packets live in page-locked memory, as a caller's own AVBuffer pool

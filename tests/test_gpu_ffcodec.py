@@ -126,3 +126,62 @@ def test_ffcodec_shim_error_codes():
     r1, *_ = ref_decode(cs[:40])
     r2, *_ = shim_decode(cs[:40])
     assert r1 < 0 and r2 < 0
+
+
+def shim_decode_cuda(streams, mode, sw_name, w, h):
+    lib = ctypes.CDLL(str(SHIM))
+    n = len(streams)
+    bufs = [np.frombuffer(s, np.uint8) for s in streams]
+    ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    lens = (ctypes.c_int64 * n)(*[b.size for b in bufs])
+    info = (ctypes.c_int64 * (8 * n))()
+    out = np.zeros(1 << 26, np.uint8)
+    lib.b200shim_decode_cuda.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_char_p,
+                                         ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64), ctypes.c_void_p,
+                                         ctypes.c_int64]
+    ret = lib.b200shim_decode_cuda(ptrs, lens, n, mode, sw_name.encode(), w, h, info, out.ctypes.data, out.size)
+    frames, pos = [], 0
+    for i in range(n):
+        fi = list(info[8 * i: 8 * i + 8])
+        frames.append((fi, out[pos: pos + max(fi[3], 0)].copy()))
+        pos += max(fi[3], 0)
+    return ret, frames
+
+
+@pytest.mark.parametrize("kw", [dict(nc=3, bd=12, levels=4), dict(nc=1, bd=16, levels=3, tile=(128, 128)),
+                                dict(nc=3, bd=10, levels=3, reversible=False, base_step=2.0),
+                                dict(nc=3, bd=8, levels=2, sub=[(1, 1), (2, 2), (2, 2)])])
+def test_ffcodec_shim_cuda_frames(kw):
+    """SURVEY 8(f) N2 through the reference's own hardware-frame API: an application offers a CUDA frames context
+    (mode 0) or only a CUDA device (mode 1); the shim proposes AV_PIX_FMT_CUDA through get_format, takes the picture
+    from av_hwframe_get_buffer() and leaves it in device memory (AVFrame.data[] are device pointers, sw_pix_fmt is the
+    reference's format).  Downloaded, every frame of a three-frame sequence equals the reference decoder's AVFrame;
+    when get_format declines the hardware format (mode 2) the ordinary software frames come out.  libavutil's
+    generic hwcontext.c is the reference's own; the CUDA type behind it is the stand-in of oracle/hwcuda_standin.c."""
+    kw = dict(kw)
+    nc, bd, sub = kw.pop("nc"), kw.pop("bd"), kw.pop("sub", None)
+    w, h = 272, 176
+    streams = []
+    for seed in (1, 2, 3):
+        full = j2kgen.synth_image(w, h, nc, bd, seed=seed)
+        if sub:
+            planes = [np.ascontiguousarray(a[::sy, ::sx]) for a, (sx, sy) in zip(full, sub)]
+            streams.append(j2kgen.encode(planes, bd, j2kgen.EncParams(mct=False, subsampling=sub, **kw)))
+        else:
+            streams.append(j2kgen.encode(full, bd, j2kgen.EncParams(**kw)))
+    want = [ref_decode(cs, 0) for cs in streams]
+    assert all(r[0] == 0 for r in want)
+    sw_name = want[0][3]
+    AV_PIX_FMT_CUDA = None
+    for mode in (0, 1, 2):
+        ret, frames = shim_decode_cuda(streams, mode, sw_name, w, h)
+        assert ret == 0, (mode, ret)
+        for (fi, got), (r, i1, o1, name) in zip(frames, want):
+            assert fi[0] == i1[0] and fi[1] == i1[1]
+            assert np.array_equal(got, o1), mode
+            if mode < 2:
+                assert fi[4] == 1 and fi[5] == i1[2]        # device memory; sw_pix_fmt = the reference's pix_fmt
+                AV_PIX_FMT_CUDA = AV_PIX_FMT_CUDA or fi[2]
+                assert fi[2] == AV_PIX_FMT_CUDA and fi[2] != i1[2]
+            else:
+                assert fi[4] == 0 and fi[2] == i1[2]
