@@ -560,6 +560,55 @@ def run_ours(args):
     for d in decs:
         d.close()
 
+    # ---------------- N > 1: the tiles of ONE oversized frame over the GPUs ----------------
+    # north_star: "frames, and tiles of oversized frames, are partitioned across the GPUs".  An 8K frame of 4 x 2 tiles;
+    # rank r decodes tiles r, r + N, ... of every frame (B200J2K_FLAG_TILES) end to end into its own page-locked frame:
+    # whole frames per second = frames / max-over-ranks time, no collective on the data path.
+    tile_leg = None
+    if world > 1 and args.scale == 1:
+        import j2kgen
+        from ffmpeg_ht_b200 import sharding
+        planes8 = j2kgen.synth_image(7680, 4320, 1, 16, seed=33)
+        cs8 = j2kgen.encode(planes8, 16, j2kgen.EncParams(levels=5, cblk=(64, 64), reversible=True, mct=False,
+                                                          tile=(1920, 2160)))
+        want8 = packed_source(planes8, 16)
+        d8 = fb.Jpeg2000Decoder(device=local, slots=2, flags=sharding.tile_flags(rank, world))
+        info8 = fb.probe(cs8)
+        f8 = [fb.PinnedFrame(info8) for _ in range(2)]
+        pk8 = fb.PinnedPacket(cs8)
+        for f in f8:
+            f.buffer[:] = 0
+
+        def run8(n):
+            pend = []
+            for i in range(n):
+                if len(pend) == 2:
+                    d8.wait(pend.pop(0))
+                pend.append(d8.submit(pk8, f8[i % 2]))
+            for s_ in pend:
+                d8.wait(s_)
+
+        n8 = 8 * K
+        run8(4)
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        run8(n8)
+        torch.cuda.synchronize()
+        sec8 = max_over_ranks(time.perf_counter() - t0)
+        # this rank's tiles must be the lossless source, the rest of its frame untouched (zeros)
+        got8 = f8[0].buffer
+        mine = got8 != 0
+        ok8 = bool(np.array_equal(got8[mine], want8[mine])) and (rank >= 8 or bool(mine.any()))
+        ok8 = reduce(1.0 if ok8 else 0.0, "min") > 0.5
+        covered = reduce(float(mine.sum()), "sum")
+        tile_leg = {"workload": "7680x4320 1-component 16-bit lossless HTJ2K, 4 x 2 tiles; rank r decodes tiles r, r+N, ... "
+                                "of every frame, end to end (host buffers)",
+                    "fps": n8 / sec8, "mpixel_s": n8 * 7680 * 4320 / sec8 / 1e6, "tiles": info8.ntiles,
+                    "output_check": ok8, "bytes_covered_by_all_ranks": covered, "bytes_in_frame": int(want8.size),
+                    "h2d_bytes_per_frame_this_rank": d8.h2d_bytes(0), "compressed_bytes_per_frame": len(cs8)}
+        d8.close()
+
     frames_total = B * K * world
     pix = float(w) * h
     value = frames_total * pix / (kern_ms * 1e-3) / 1e6
@@ -604,6 +653,7 @@ def run_ours(args):
                        "e2e_timer": "wall clock bracketed by device synchronisation (includes host parsing)",
                        "pcie_bare_copies_all_ranks_at_once": pcie,
                        "e2e_device_frames_fps": frames_total / e2e_dev_s,
+                       "tiles_of_one_frame_over_the_gpus": tile_leg,
                        "e2e_d2h_gbs_all_ranks": d2h_step * K * world / e2e_s / 1e9},
             "e2e": {"value": e2e, "unit": "Mpixel/s", "fps": frames_total / e2e_s,
                     "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step), "output_check": ok,

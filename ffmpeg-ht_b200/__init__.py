@@ -311,9 +311,10 @@ def frame_to_arrays(info: FrameInfo, planes):
 class Jpeg2000Decoder:
     """One decoder context (= one AVCodecContext of the reference) on one CUDA device."""
 
-    def __init__(self, device: int = 0, slots: int = 1, bitexact: bool = False, lowres: int = 0):
+    def __init__(self, device: int = 0, slots: int = 1, bitexact: bool = False, lowres: int = 0, flags: int = 0):
+        """flags: further B200J2K_FLAG_* bits, e.g. sharding.tile_flags(rank, world) for a tile subset"""
         self._h = ctypes.c_void_p()
-        self.flags = (FLAG_BITEXACT if bitexact else 0) | flag_lowres(lowres)
+        self.flags = (FLAG_BITEXACT if bitexact else 0) | flag_lowres(lowres) | flags
         _check(lib().b200j2k_create(ctypes.byref(self._h), device, slots, self.flags), "create")
         self.device = device
         self.slots = slots

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <utility>
 #include <vector>
 
 #include "../../include/b200j2k.h"
@@ -228,7 +229,7 @@ struct Slot {
     /* pending output */
     uint8_t *dst[4] = { nullptr, nullptr, nullptr, nullptr };
     int dst_linesize[4] = { 0, 0, 0, 0 };
-    bool direct = false;
+    bool direct = false, subset_out = false;
     uint64_t seq = 0;
 };
 
@@ -361,32 +362,38 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
     if ((ret = s.d_scratch.ensure(s.ht.scratch_words * 4 + 256)) < 0) return ret;
     uint8_t *dblob = (uint8_t *)s.d_blob.p;
     cudaError_t e;
-    if (direct_in) {
-        e = cudaMemcpyAsync(dblob, h, s.off_bytes, cudaMemcpyHostToDevice, s.stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(dblob + s.off_bytes, pkt, (size_t)size, cudaMemcpyHostToDevice, s.stream);
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(dblob + off_tail, htail, tail, cudaMemcpyHostToDevice, s.stream);
-    } else {
+    /* the part of the packet the kernels will read: all of it, or -- for a context that decodes a subset of the tiles
+     * (B200J2K_FLAG_TILES) -- the tile-parts of its own tiles, at unchanged offsets */
+    std::vector<std::pair<uint32_t, uint32_t>> whole(1, std::make_pair(0u, (uint32_t)size));
+    const std::vector<std::pair<uint32_t, uint32_t>> &ranges = p.tile_subset ? p.needed_ranges : whole;
+    size_t uploaded = 0;
+    e = cudaMemcpyAsync(dblob, h, s.off_bytes, cudaMemcpyHostToDevice, s.stream);       /* the tables go first: they are ready */
+    for (const auto &rg : ranges) {
+        const size_t at0 = rg.first, len = rg.second;
+        uploaded += len;
+        if (direct_in) {
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(dblob + s.off_bytes + at0, pkt + at0, len, cudaMemcpyHostToDevice, s.stream);
+            continue;
+        }
         /* pageable packet: copied into the pinned staging buffer piece by piece, each piece's DMA running while the
-         * next one is copied (the tables go first: they are ready) */
-        e = cudaMemcpyAsync(dblob, h, s.off_bytes, cudaMemcpyHostToDevice, s.stream);
+         * next one is copied */
         const size_t piece = (size_t)4 << 20;
-        for (size_t at = 0; at < (size_t)size && e == cudaSuccess; at += piece) {
-            const size_t n = (size_t)size - at < piece ? (size_t)size - at : piece;
+        for (size_t at = at0; at < at0 + len && e == cudaSuccess; at += piece) {
+            const size_t n = at0 + len - at < piece ? at0 + len - at : piece;
             memcpy(h + s.off_bytes + at, pkt + at, n);
             e = cudaMemcpyAsync(dblob + s.off_bytes + at, h + s.off_bytes + at, n, cudaMemcpyHostToDevice, s.stream);
         }
-        if (e == cudaSuccess)
-            e = cudaMemcpyAsync(dblob + off_tail, htail, tail, cudaMemcpyHostToDevice, s.stream);
     }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dblob + off_tail, htail, tail, cudaMemcpyHostToDevice, s.stream);
     /* PAL8: plane 1 of the picture is the palette (AVFrame.data[1], jpeg2000dec.c:2900-2901); no kernel writes it */
     if (e == cudaSuccess && pal8)
         e = cudaMemcpyAsync((uint8_t *)s.d_picture.p + p.plane_off[1], dblob + off_pal, sizeof(p.hdr.palette),
                             cudaMemcpyDeviceToDevice, s.stream);
     if (e != cudaSuccess)
         return B200J2K_ERR_DEVICE;
-    s.h2d_bytes = off_tail + tail;
+    s.h2d_bytes = s.off_bytes + uploaded + tail;
     s.staged = true;
     return 0;
 }
@@ -463,6 +470,35 @@ int queue_output(Slot &s, uint8_t *const data[4], const int linesize[4])
     }
     s.direct = direct;
     const uint8_t *pic = (const uint8_t *)s.d_picture.p;
+    if (p.tile_subset) {
+        /* only this context's tiles were reconstructed: only their rectangles leave the device, and only into memory
+         * the copy engines reach directly (several contexts fill one frame side by side) */
+        if (!direct)
+            return B200J2K_ERR_EINVAL;
+        s.subset_out = true;
+        for (const PackGroup &g : p.groups) {
+            for (int c = 0; c < g.ncomp; c++) {
+                const TileCompDesc &tc = p.tcs[g.tc[c]];
+                if (tc.transform < 0)
+                    break;
+                const bool packed = g.pixel_stride == g.ncomp && g.ncomp > 1;
+                if (packed && c > 0)
+                    break;                                            /* one rectangle holds all its components */
+                const int pl = packed || g.ncomp == 1 ? g.plane : g.comp_plane[c];
+                const LevelDesc &o = tc.lev[tc.nlevels];
+                const size_t bpp = (size_t)(g.wide ? 2 : 1) * (packed ? g.ncomp : 1);
+                const size_t wbytes = (size_t)(o.u1 - o.u0) * bpp, rows = (size_t)(o.v1 - o.v0);
+                if (!wbytes || !rows)
+                    continue;
+                const size_t src = p.plane_off[pl] + (size_t)tc.out_y * p.plane_row_bytes[pl] + (size_t)tc.out_x * bpp;
+                uint8_t *dst = data[pl] + (size_t)tc.out_y * linesize[pl] + (size_t)tc.out_x * bpp;
+                if (cudaMemcpy2DAsync(dst, (size_t)linesize[pl], pic + src, (size_t)p.plane_row_bytes[pl], wbytes, rows,
+                                      cudaMemcpyDefault, s.stream) != cudaSuccess)
+                    return B200J2K_ERR_DEVICE;
+            }
+        }
+        return 0;
+    }
     if (direct) {
         for (int i = 0; i < p.nplanes; i++) {
             cudaError_t e;

@@ -937,7 +937,9 @@ int Parser::build_geometry(int flags)
             tc.width = cw; tc.height = ch;
             tc.x0 = cr.x0; tc.y0 = cr.y0;
             tc.nlevels = nres2decode - 1;
-            tc.transform = cs.transform;
+            /* a tile outside this context's subset keeps its place in the tables, but no kernel reconstructs it:
+             * no transform type matches, and its code-blocks are flagged like those lowres drops */
+            tc.transform = tile_selected(flags, tileno) ? cs.transform : -1;
             tc.comp = c;
             tc.out_x = cr.x0 - ceildiv(h.X0, h.cdx[c]);
             tc.out_y = cr.y0 - ceildiv(h.Y0, h.cdy[c]);
@@ -1049,7 +1051,7 @@ int Parser::build_geometry(int flags)
                                     d.flags |= J2K_CBLK_MQ;                  /* MIXED sets: decided per block in tier 2 */
                                     d.Lref = d.pad;
                                 }
-                                if (r >= nres2decode) {
+                                if (r >= nres2decode || !tile_selected(flags, tileno)) {
                                     /* dropped by lowres: the packets are still parsed, the block is never decoded
                                      * (tile_codeblocks walks nreslevels2decode levels, jpeg2000dec.c:2230) */
                                     d.flags |= J2K_CBLK_SKIP;
@@ -1686,6 +1688,12 @@ int Parser::decode_packets(int tileno)
 }
 #undef PACKET
 
+bool Parser::tile_selected(int flags, int tileno)
+{
+    const int step = B200J2K_FLAG_GET_TILE_STEP(flags);
+    return step <= 1 || tileno % step == (int)B200J2K_FLAG_GET_TILE_FIRST(flags) % step;
+}
+
 int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only)
 {
     if (!pkt || size < 2)
@@ -1717,11 +1725,19 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
     decoded_layers_.assign(precs_.size(), 0);
     extra.clear();
     cur_part_start_ = nullptr;
+    tile_subset = B200J2K_FLAG_GET_TILE_STEP(flags) > 1;
+    needed_ranges.clear();
     for (int tileno = 0; tileno < hdr.ntx * hdr.nty; tileno++) {
         /* a tile whose first tile-part (TPsot = 0) never showed up has no coding style in the reference:
          * init_tile fails on !codsty->init (jpeg2000dec.c:1054-1055) and the frame with it */
         if (!tile_first_[tileno])
             return B200J2K_ERR_INVALIDDATA;
+        if (!tile_selected(flags, tileno))
+            continue;                                     /* another context's tile: its packets are not even read */
+        if (tile_subset)
+            for (const TilePart &tp : parts_[tileno])
+                if (tp.start && tp.end > tp.start)
+                    needed_ranges.emplace_back((uint32_t)(tp.start - pkt), (uint32_t)(tp.end - tp.start));
         if ((ret = decode_packets(tileno)) < 0)
             return ret;
     }

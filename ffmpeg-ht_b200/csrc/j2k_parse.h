@@ -12,6 +12,7 @@
 #define B200J2K_PARSE_H
 
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "j2k_plan.h"
@@ -134,6 +135,11 @@ public:
     uint32_t max_Lcup = 0, max_Lref = 0;
     int any_refine = 0;
     uint64_t geom_serial = 0;         /* bumped whenever the geometry tables were rebuilt */
+    /* tile subset (B200J2K_FLAG_TILES): byte ranges of the packet the selected tiles' code-blocks live in -- empty =
+     * the whole packet is needed */
+    std::vector<std::pair<uint32_t, uint32_t>> needed_ranges;     /* (offset, length) */
+    bool tile_subset = false;
+    static bool tile_selected(int flags, int tileno);
 
     /* flags: B200J2K_FLAG_* ; headers_only: stop after the marker segments */
     int parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only);

@@ -1,8 +1,18 @@
-"""Multi-GPU partitioning of the decode path: frames of a sequence (and tiles of one oversized frame) are
-independent units -- the reference decodes them on independent frame-thread contexts
-(libavcodec/pthread_frame.c:248-295) and independent execute2 tile jobs (libavcodec/jpeg2000dec.c:2894) --
-so ranks shard them round-robin with NO data-path collective.  torch.distributed is used only for the
-barrier around the timed region and for reducing the bookkeeping (max of elapsed time, sum of counts)."""
+"""Multi-GPU partitioning of the decode path.
+
+Frames of a sequence and tiles of one oversized frame are independent units: the reference decodes them on
+independent frame-thread contexts (libavcodec/pthread_frame.c:248-295) and independent execute2 tile jobs
+(jpeg2000_decode_tile, libavcodec/jpeg2000dec.c:2368-2395, :2894).  Here they are sharded round-robin over GPUs with
+NO data-path collective:
+
+  frames   rank r of N decodes frames r, r + N, ...            (shard_indices; bench.py's main legs)
+  tiles    context r of N decodes tiles r, r + N, ... of EVERY frame: a decoder context created with
+           B200J2K_FLAG_TILES(r, N) parses only its tiles' packets, uploads only their tile-parts, reconstructs
+           only them and writes only their rectangles of the output planes (tile_flags; TileShardedDecoder drives
+           one such context per GPU of this process into one shared frame, the way one libavcodec process would)
+
+torch.distributed is used only for the barrier around a timed region and for reducing the bookkeeping (max of the
+elapsed time, sum of the unit counts)."""
 from __future__ import annotations
 
 
@@ -15,6 +25,42 @@ def shard_indices(n_units: int, rank: int, world: int) -> list[int]:
 
 def owner(unit: int, world: int) -> int:
     return unit % world
+
+
+def tile_flags(rank: int, world: int) -> int:
+    """B200J2K_FLAG_TILES(rank, world) of include/b200j2k.h: flags of the decoder context that owns tiles
+    rank, rank + world, ... (0 = every tile when there is only one context)."""
+    if world < 1 or world > 255 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return 0 if world == 1 else ((world & 255) << 16) | ((rank & 255) << 24)
+
+
+class TileShardedDecoder:
+    """One oversized frame over several GPUs of this process: context i (on devices[i]) owns tiles i, i + n, ...
+    All contexts write their tiles' rectangles into the SAME page-locked frame; decode() returns when every one has."""
+
+    def __init__(self, devices, flags: int = 0, slots: int = 1):
+        import ffmpeg_ht_b200 as fb
+        self.devices = list(devices)
+        n = len(self.devices)
+        self.ctx = [fb.Jpeg2000Decoder(device=d, slots=slots, flags=flags | tile_flags(i, n))
+                    for i, d in enumerate(self.devices)]
+
+    def decode(self, pkt, frame):
+        """pkt: bytes or PinnedPacket; frame: PinnedFrame (or DeviceFrame) every context writes its tiles into."""
+        pending = [(c, c.submit(pkt, frame)) for c in self.ctx]
+        for c, slot in pending:
+            c.wait(slot)
+
+    def close(self):
+        for c in self.ctx:
+            c.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
 
 
 def reduce_stats(elapsed_s: float, units_done: int, dist=None, device=None):

@@ -40,6 +40,14 @@ extern "C" {
  * highest resolution levels; picture dimensions shrink by 2^n.  n = 0..15 in bits 8-11 of the flags. */
 #define B200J2K_FLAG_LOWRES(n) (((n) & 15) << 8)
 #define B200J2K_FLAG_GET_LOWRES(flags) (((flags) >> 8) & 15)
+/* Tile subset: this decoder context reconstructs only the tiles whose index t satisfies t % step == first, writes only
+ * their rectangles of the output planes and uploads only their tile-parts.  It is how the tiles of an oversized frame
+ * are spread over several GPUs (one context per GPU, `first` = its rank, `step` = the number of GPUs, all writing
+ * into the same AVFrame): the reference's per-tile jobs (jpeg2000_decode_tile through avctx->execute2,
+ * jpeg2000dec.c:2368-2395, :2894) partitioned by device instead of by slice thread.  step <= 1: every tile. */
+#define B200J2K_FLAG_TILES(first, step) ((((step) & 255) << 16) | (((first) & 255) << 24))
+#define B200J2K_FLAG_GET_TILE_STEP(flags)  (((flags) >> 16) & 255)
+#define B200J2K_FLAG_GET_TILE_FIRST(flags) (((unsigned)(flags) >> 24) & 255)
 
 /* Output memory layouts.  b200j2k_frame_info.av_pix_fmt_name gives the exact libavutil format name; the FFCodec
  * shim maps it to AVPixelFormat with av_get_pix_fmt().  Selection follows jpeg2000dec.c:134-193,:328-412,

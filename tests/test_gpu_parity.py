@@ -771,3 +771,46 @@ def test_baseline_cfg2_irreversible_full_size(dec):
     print(f"cfg2 vs oracle: max {err} LSB, PSNR {99.0 if mse == 0 else 10 * np.log10(1023 ** 2 / mse):.1f} dB; "
           f"{8 * len(cs) / (3840 * 2160):.2f} bpp")
     assert err <= 1
+
+
+# ---- tiles of one frame over several decoder contexts (multi-GPU partitioning of an oversized frame) ----
+@pytest.mark.parametrize("kw,nctx", [(dict(nc=3, bd=12, levels=3, tile=(128, 96)), 3),
+                                     (dict(nc=1, bd=16, levels=4, tile=(160, 128)), 2),
+                                     (dict(nc=3, bd=10, levels=3, tile=(128, 128), reversible=False, base_step=2.0), 4),
+                                     (dict(nc=3, bd=8, levels=2, tile=(128, 64), sub=[(1, 1), (2, 2), (2, 2)]), 2)])
+def test_tiles_sharded_over_contexts_fill_one_frame(kw, nctx):
+    """B200J2K_FLAG_TILES(first, step): context i reconstructs tiles i, i + n, ... and writes only their rectangles.
+    n contexts (here all on cuda:0; one per GPU in production, ffmpeg-ht_b200/sharding.py) fill ONE page-locked frame:
+    it equals the ordinary decode; after the first context alone the other tiles still hold the pattern the frame was
+    filled with, and that context uploaded only its own tile-parts."""
+    from ffmpeg_ht_b200 import sharding
+    kw = dict(kw)
+    nc, bd, sub = kw.pop("nc"), kw.pop("bd"), kw.pop("sub", None)
+    w, h = 400, 300
+    full = j2kgen.synth_image(w, h, nc, bd, seed=21)
+    if sub:
+        planes = [np.ascontiguousarray(a[::sy, ::sx]) for a, (sx, sy) in zip(full, sub)]
+        cs = j2kgen.encode(planes, bd, j2kgen.EncParams(mct=False, subsampling=sub, **kw))
+    else:
+        cs = j2kgen.encode(full, bd, j2kgen.EncParams(**kw))
+    with fb.Jpeg2000Decoder(device=0, slots=1) as whole:
+        info, want = whole.decode(cs)
+        full_h2d = None
+        frame = fb.PinnedFrame(info)
+        slot = whole.submit(cs, frame)
+        whole.wait(slot)
+        full_h2d = whole.h2d_bytes(slot)
+        assert np.array_equal(frame.buffer, want)
+    frame.buffer[:] = 0xA5
+    with sharding.TileShardedDecoder([0] * nctx) as sh:
+        slot = sh.ctx[0].submit(cs, frame)
+        sh.ctx[0].wait(slot)
+        assert sh.ctx[0].h2d_bytes(slot) < full_h2d                   # only its tile-parts crossed PCIe
+        part = frame.buffer.copy()
+        assert not np.array_equal(part, want)
+        touched = part != 0xA5
+        assert touched.any() and np.array_equal(part[touched], want[touched])
+        assert (~touched).sum() > want.size // (2 * nctx)             # the other contexts' tiles were left alone
+        sh.decode(cs, frame)
+        assert np.array_equal(frame.buffer, want)
+    frame.close()

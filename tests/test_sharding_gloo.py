@@ -64,6 +64,61 @@ def test_two_ranks_shard_a_sequence():
         assert blocks > 0
 
 
+def _tile_worker(rank, world, port, q):
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tools"))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import ffmpeg_ht_b200 as fb
+    from ffmpeg_ht_b200 import sharding
+    import j2kgen
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    planes = j2kgen.synth_image(300, 200, 3, 12, seed=7)
+    cs = j2kgen.encode(planes, 12, j2kgen.EncParams(levels=3, tile=(128, 96)))      # 3 x 3 tiles
+    whole = fb.plan(cs)
+    mine = fb.plan(cs, sharding.tile_flags(rank, world))
+    live = (mine["cblk"]["flags"] & 0x80) == 0                # J2K_CBLK_SKIP marks the other ranks' blocks
+    tiles = sorted({i // 3 for i, t in enumerate(mine["tcs"]) if int(t["transform"]) >= 0})
+    # no data-path collective: only the bookkeeping is reduced -- every block and every tile has exactly one owner
+    owners = torch.from_numpy(live.astype(np.int64))
+    dist.all_reduce(owners, op=dist.ReduceOp.SUM)
+    q.put((rank, tiles, int(live.sum()), len(whole["cblk"]), bool((owners == 1).all())))
+    dist.destroy_process_group()
+
+
+def test_two_ranks_shard_the_tiles_of_a_frame():
+    """Tiles of one frame over two ranks (B200J2K_FLAG_TILES): each rank's plan keeps the tables of the whole frame
+    but only its own tiles are live; together the ranks cover every code-block exactly once."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_tile_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == [0, 2, 4, 6, 8] and res[1][1] == [1, 3, 5, 7]
+    assert res[0][2] + res[1][2] == res[0][3]
+    assert all(r[4] for r in res)
+
+
+def test_tile_flags():
+    sys.path.insert(0, str(ROOT))
+    from ffmpeg_ht_b200 import sharding
+    assert sharding.tile_flags(0, 1) == 0
+    assert sharding.tile_flags(3, 8) == (8 << 16) | (3 << 24)
+    for bad in ((1, 1), (-1, 2), (0, 256)):
+        with pytest.raises(ValueError):
+            sharding.tile_flags(*bad)
+
+
 def test_shard_indices_properties():
     sys.path.insert(0, str(ROOT))
     from ffmpeg_ht_b200 import sharding
