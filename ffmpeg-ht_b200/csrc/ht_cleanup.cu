@@ -333,7 +333,10 @@ __device__ __forceinline__ void vlc_pair_lane(VlcReader &v, MelLane &mel, const 
 }
 
 constexpr int VLC_LANES_PER_CTA = 32;
-constexpr int VLC_ACTIVE_LANES = 16;     /* blocks per warp (B200J2K_VLC_ACTIVE overrides, for experiments) */
+constexpr int VLC_ACTIVE_LANES = 32;     /* blocks per warp (B200J2K_VLC_ACTIVE overrides, for experiments).  Round 2,
+                                          * kernel-only 4K frames/s with 12 frames in flight: 8 lanes 5471, 16 lanes
+                                          * 6368, 24 lanes 6582, 32 lanes 6590 (round 1 favoured 16 when the kernels
+                                          * around it were slower) */
 
 __global__ void __launch_bounds__(VLC_LANES_PER_CTA)
 ht_vlc_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ order,
