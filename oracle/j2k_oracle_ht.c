@@ -5,7 +5,7 @@
  *   H1 orchestration        libavcodec/jpeg2000htdec.c:1188-1336
  *   H2 the four bit readers :123-131, :145-221, :283-295, :429-460
  *   H3 MEL                  :462-495
- *   H4 CxtVLC               :300-331, :510-531 (tables: oracle/cxtvlc_tables.h, generated)
+ *   H4 CxtVLC               :300-331, :510-531 (tables: ffmpeg-ht_b200/csrc/cxtvlc_tables.h, generated from the reference's)
  *   H5 U-VLC                :338-388, combination rules :671-712 and :833-854
  *   H6 cleanup pass         :547-1014
  *   H7 SigProp              :1016-1131

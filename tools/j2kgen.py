@@ -41,7 +41,8 @@ def build(force: bool = False) -> Path:
     so = _HERE / "libj2kgen.so"
     src = _HERE / "htj2k_enc.c"
     if force or not so.exists() or so.stat().st_mtime < src.stat().st_mtime:
-        subprocess.check_call(["gcc", "-std=c11", "-O2", "-fPIC", "-shared", "-o", str(so), str(src), "-lm"])
+        subprocess.check_call(["gcc", "-std=c11", "-O2", "-fPIC", "-shared", f"-I{_HERE.parent / 'ffmpeg-ht_b200' / 'csrc'}",
+                               "-o", str(so), str(src), "-lm"])
     return so
 
 
