@@ -28,30 +28,67 @@ using namespace b200j2k;
 
 namespace {
 
+/* Device buffers grow on demand and are never shrunk.  With B200J2K_REDZONE=1 in the environment (debugging: the
+ * fuzz tests run that way, compute-sanitizer being unavailable on the GPU pool) every buffer gets a guard zone on
+ * either side, filled with a pattern that finish_slot() checks after each frame: a kernel writing next to its
+ * buffer fails the decode loudly instead of corrupting a neighbour. */
+constexpr size_t REDZONE = 4096;
+constexpr int REDZONE_BYTE = 0xC5;
+inline bool redzones_on()
+{
+    static const bool on = getenv("B200J2K_REDZONE") && atoi(getenv("B200J2K_REDZONE"));
+    return on;
+}
+
 struct DevBuf {
-    void *p = nullptr;
+    void *p = nullptr;      /* what the kernels see */
+    void *base = nullptr;   /* what cudaMalloc returned (p - REDZONE when guard zones are on) */
     size_t cap = 0;
     int ensure(size_t n)
     {
         if (n <= cap)
             return 0;
-        if (p)
-            cudaFree(p);
-        p = nullptr;
+        if (base)
+            cudaFree(base);
+        p = base = nullptr;
         cap = 0;
         size_t want = n + n / 8 + 4096;
-        if (cudaMalloc(&p, want) != cudaSuccess) {
+        const size_t guard = redzones_on() ? REDZONE : 0;
+        if (guard)
+            want = (want + 255) & ~(size_t)255;
+        if (cudaMalloc(&base, want + 2 * guard) != cudaSuccess) {
             cudaGetLastError();
+            base = nullptr;
             return B200J2K_ERR_NOMEM;
         }
+        p = (uint8_t *)base + guard;
         cap = want;
+        if (guard) {
+            cudaMemset(base, REDZONE_BYTE, guard);
+            cudaMemset((uint8_t *)p + cap, REDZONE_BYTE, guard);
+        }
         return 0;
+    }
+    /* number of guard bytes a kernel has overwritten (0 when guard zones are off) */
+    size_t violated(cudaStream_t st) const
+    {
+        if (!redzones_on() || !base)
+            return 0;
+        static thread_local uint8_t host[2 * REDZONE];
+        if (cudaMemcpyAsync(host, base, REDZONE, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaMemcpyAsync(host + REDZONE, (const uint8_t *)p + cap, REDZONE, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+            cudaStreamSynchronize(st) != cudaSuccess)
+            return 1;
+        size_t bad = 0;
+        for (size_t i = 0; i < 2 * REDZONE; i++)
+            bad += host[i] != REDZONE_BYTE;
+        return bad;
     }
     void release()
     {
-        if (p)
-            cudaFree(p);
-        p = nullptr;
+        if (base)
+            cudaFree(base);
+        p = base = nullptr;
         cap = 0;
     }
 };
@@ -531,6 +568,24 @@ int finish_slot(Slot &s)
         cudaGetLastError();
         return B200J2K_ERR_DEVICE;
     }
+    if (redzones_on()) {
+        const DevBuf *bufs[] = { &s.d_blob, &s.d_coefA, &s.d_coefB, &s.d_coefC, &s.d_picture, &s.d_status, &s.d_scratch };
+        const char *names[] = { "blob", "coefA", "coefB", "coefC", "picture", "status", "scratch" };
+        size_t bad = 0;
+        for (int i = 0; i < 7; i++) {
+            const size_t b = bufs[i]->violated(s.stream);
+            if (b)
+                fprintf(stderr, "b200j2k: %zu guard bytes of the %s buffer were overwritten\n", b, names[i]);
+            bad += b;
+        }
+        const int asserts = ht_cleanup_bounds_failures();
+        if (asserts) {
+            fprintf(stderr, "b200j2k: %d in-kernel bounds assertions failed\n", asserts);
+            bad += (size_t)(asserts > 0 ? asserts : 1);
+        }
+        if (bad)
+            return B200J2K_ERR_DEVICE;
+    }
     if (!s.direct && s.dst[0]) {
         Parser &p = s.parser;
         for (int i = 0; i < p.nplanes; i++) {
@@ -784,6 +839,16 @@ int b200j2k_slot_blocks_failed(b200j2k_decoder *d, int slot)
         return B200J2K_ERR_EINVAL;
     const Slot &s = d->slots[slot];
     return s.busy || !s.h_failed ? 0 : *s.h_failed;
+}
+
+/* debugging aid for the guard-zone checker (tests/test_gpu_debug_bounds.py): writes one byte right behind the slot's
+ * picture buffer, i.e. into its guard zone when B200J2K_REDZONE=1 -- refused otherwise */
+int b200j2k_debug_poke(b200j2k_decoder *d, int slot)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size() || !redzones_on() || !d->slots[slot].d_picture.p)
+        return B200J2K_ERR_EINVAL;
+    const DevBuf &b = d->slots[slot].d_picture;
+    return cudaMemset((uint8_t *)b.p + b.cap + 7, 0, 1) == cudaSuccess ? 0 : B200J2K_ERR_DEVICE;
 }
 
 int b200j2k_slot_launches(b200j2k_decoder *d, int slot)

@@ -109,6 +109,7 @@ ht_unstuff_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict
     const int vlw = ht_stream_words(Scup);
     uint32_t *vl = smem + (size_t)warp * warp_words;
     uint32_t *ml = vl + vlw;
+    J2K_BOUNDS(2 * vlw <= warp_words);
     for (int i = lane; i < 2 * vlw; i += 32)
         vl[i] = 0;
     __syncwarp();
@@ -526,6 +527,7 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
              * reads a zero-length field */
             const int mm = (int)((mB >> (8 * i)) & 0xFF);
             const uint32_t p = min(pos0 + ((preB >> (8 * i)) & 0xFF), ms_bits);   /* past the end: ones */
+            J2K_BOUNDS((int)(p >> 5) + 1 < ms_words);
             uint32_t v = ms_read(ms, p, mm) | (((e1B >> (8 * i)) & 1u) << mm);
             const unsigned E = 32 - __clz(v | 1);        /* :419-425 */
             if (i == 1) E1 = mm ? E : 0;
@@ -625,6 +627,7 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
     const int mode = (d.flags >> 1) & 3;
     const uint32_t *q = scratch + scr_off[bi] + 2 * ht_stream_words(Scup);
     uint32_t *ms = smem + (size_t)warp * stream_words;
+    J2K_BOUNDS((d.Lcup - Scup + 3) / 4 + 2 <= stream_words);
     if (REFINE) {
         const RefLayout rl = ref_layout(d);
         uint8_t *sigb = reinterpret_cast<uint8_t *>(const_cast<uint32_t *>(scratch) + scr_off[bi] + rl.sig);
@@ -655,6 +658,7 @@ ht_unstuff_ref_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__rest
     const uint8_t *Dref = bytes + d.data_off + d.Lcup;
     const int Lref = d.Lref;
     uint32_t *sp = smem + (size_t)warp * warp_words, *mr = sp + rl.rw;
+    J2K_BOUNDS(2 * rl.rw <= warp_words);
     for (int i = lane; i < 2 * rl.rw; i += 32)
         sp[i] = 0;
     __syncwarp();
@@ -887,6 +891,19 @@ ht_refine_apply_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__res
 }  // namespace
 
 /* ---- host side ----------------------------------------------------------------------------------------- */
+int ht_cleanup_bounds_failures()
+{
+#ifdef B200J2K_DEBUG_BOUNDS
+    int n = 0, zero = 0;
+    if (cudaMemcpyFromSymbol(&n, g_bounds_failures, sizeof(n)) != cudaSuccess)
+        return -1;
+    cudaMemcpyToSymbol(g_bounds_failures, &zero, sizeof(zero));
+    return n;
+#else
+    return 0;
+#endif
+}
+
 uint32_t ht_cleanup_scratch_words(const CblkDesc &d)
 {
     if (d.npasses == 0 || d.Lcup < 2)

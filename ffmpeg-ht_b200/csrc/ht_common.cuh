@@ -23,6 +23,16 @@ constexpr int WARPS_PER_CTA = B200J2K_WARPS_PER_CTA;
 #else
 constexpr int WARPS_PER_CTA = 4;
 #endif
+/* Bounds assertions of a debug build (-DB200J2K_DEBUG_BOUNDS; tools/build_variant.sh dbg ht_cleanup.cu ...): the
+ * fuzz tests run against that build with guard zones around every device buffer (B200J2K_REDZONE=1) -- the stand-in
+ * for compute-sanitizer, which is not available on the GPU pool.  A failed assertion is counted, the decode of the
+ * frame then fails on the host (decoder.cu finish_slot). */
+#ifdef B200J2K_DEBUG_BOUNDS
+__device__ int g_bounds_failures;
+#define J2K_BOUNDS(cond) do { if (!(cond)) atomicAdd(&g_bounds_failures, 1); } while (0)
+#else
+#define J2K_BOUNDS(cond) do { } while (0)
+#endif
 constexpr int TABLE_WORDS = 1024 + 128;         /* 2 x 1024 x u16 CxtVLC + 256 x u16 U-VLC pair table */
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -327,6 +337,8 @@ __device__ __forceinline__ uint32_t unstuff(const uint8_t *first, int n, uint32_
             const uint32_t wd = off >> 5, sft = off & 31;
             const uint64_t lo = v << sft;
             const uint32_t hi = sft ? (uint32_t)(v >> (64 - sft)) : 0;
+            /* n bytes give at most 8 n bits: no word at or behind bit 8 n is ever touched */
+            J2K_BOUNDS(32u * (wd + (hi ? 2u : (uint32_t)(lo >> 32) ? 1u : 0u)) < 8u * (uint32_t)n);
             if ((uint32_t)lo)
                 atomicOr(&out[wd], (uint32_t)lo);
             if ((uint32_t)(lo >> 32))

@@ -42,6 +42,9 @@ static inline __host__ __device__ int ht_stream_words(int Scup) { return (Scup +
  * one word per quad and -- with refinement passes -- the Dref bit arrays and three significance maps);
  * always even, 0 for blocks without data. */
 uint32_t ht_cleanup_scratch_words(const CblkDesc &d);
+/* bounds assertions that failed in the kernels of ht_cleanup.cu since the last call (always 0 unless the file was
+ * built with -DB200J2K_DEBUG_BOUNDS); synchronises the device */
+int ht_cleanup_bounds_failures();
 /* scr_off: device array of scratch word offsets, indexed like descs.  order[] = [refine | coded | zero]:
  *   refine  blocks with SigProp / MagRef passes (<= 64 samples wide): un-stuffed and VLC-decoded here,
  *           finished by launch_ht_refine

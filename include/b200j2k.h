@@ -145,6 +145,9 @@ void *b200j2k_slot_output(b200j2k_decoder *dec, int slot, int64_t *bytes);
 int64_t b200j2k_slot_h2d_bytes(b200j2k_decoder *dec, int slot);
 /* number of kernel launches the last run of `slot` queued */
 int b200j2k_slot_launches(b200j2k_decoder *dec, int slot);
+/* Debug builds / B200J2K_REDZONE=1 only: dirties the guard zone behind the slot's picture buffer so that the checker
+ * can be tested (tests/test_gpu_debug_bounds.py); EINVAL when guard zones are off. */
+int b200j2k_debug_poke(b200j2k_decoder *dec, int slot);
 /* After b200j2k_wait(): how many code-blocks of the slot's frame were zero-filled because their segment was damaged
  * (the reference logs each one and carries on, jpeg2000dec.c:2275-2278); 0 while the slot is still busy. */
 int b200j2k_slot_blocks_failed(b200j2k_decoder *dec, int slot);
