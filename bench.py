@@ -316,7 +316,7 @@ EXTRA = [
 ]
 
 
-def shim_leg(frames, contexts=(1, 4, 8, 16)):
+def shim_leg(frames, contexts=(1, 4, 8)):
     """The FFCodec shim (ffmpeg-ht_b200/ffcodec/jpeg2000_b200.c compiled against the reference's headers) driven the
     way libavcodec drives a decoder -- FFCodec.init / cb.decode / close, one context per frame thread, pageable
     packets, a new AVFrame per picture -- by the harness that also drives the reference decoder (oracle/ref_shim.c
@@ -333,21 +333,28 @@ def shim_leg(frames, contexts=(1, 4, 8, 16)):
     ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
     lens = (ctypes.c_int64 * n)(*[b.size for b in bufs])
     out = {}
-    for label, env in (("pageable_packets", "0"), ("pinned_packets", "1")):
+    for label, env, depth in (("pageable_packets", "0", "1"), ("pinned_packets", "1", "1"),
+                              ("pageable_packets_async_depth_2", "0", "2"), ("pinned_packets_async_depth_2", "1", "2")):
         os.environ["REF_PINNED_PACKETS"] = env
+        os.environ["REF_OPT_async_depth"] = depth
         res = {}
         for t in contexts:
-            reps = max(3, (48 * t + n - 1) // n)           # at least 48 timed frames per context
-            s = fn(ptrs, lens, n, t, reps, 0)               # the harness decodes one frame per context before its clock starts
-            if s < 0:
-                return {"error": "shim decode failed"}
-            res[str(t)] = n * reps / s
+            reps = max(4, (64 * t + n - 1) // n)           # at least 64 timed frames per context
+            best = 0.0
+            for _ in range(2):                              # host-side noise on shared boxes: best of two
+                s = fn(ptrs, lens, n, t, reps, 0)           # the harness warms every context up before its clock starts
+                if s < 0:
+                    return {"error": "shim decode failed"}
+                best = max(best, n * reps / s)
+            res[str(t)] = best
         out[label] = res
     os.environ.pop("REF_PINNED_PACKETS", None)
+    os.environ.pop("REF_OPT_async_depth", None)
     return {"fps_by_contexts": out, "unit": "frames/s",
             "note": "same workload through FFCodec.cb.decode of the shim, one decoder context per frame thread, pictures "
                     "from the shim's page-locked frame pool; packets in ordinary av_malloc'ed memory (what libavformat "
-                    "hands over) or in page-locked memory (a caller-owned buffer pool); steady state"}
+                    "hands over) or in page-locked memory (a caller-owned buffer pool); async_depth 2 = the shim's "
+                    "private option: two pictures in flight per context, one frame of delay; steady state"}
 
 
 # ---- this repo's arm --------------------------------------------------------------------------------

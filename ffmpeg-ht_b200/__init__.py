@@ -133,7 +133,7 @@ def lib():
 EXPORTS = ["b200j2k_device_count", "b200j2k_create", "b200j2k_destroy", "b200j2k_probe", "b200j2k_submit",
            "b200j2k_wait", "b200j2k_decode", "b200j2k_stage", "b200j2k_run_staged", "b200j2k_run_staged_timed",
            "b200j2k_sync",
-           "b200j2k_fetch", "b200j2k_slot_stream", "b200j2k_slot_output", "b200j2k_slot_launches", "b200j2k_slot_blocks_failed", "b200j2k_pointer_device", "b200j2k_debug_poke",
+           "b200j2k_fetch", "b200j2k_slot_stream", "b200j2k_slot_output", "b200j2k_slot_launches", "b200j2k_slot_blocks_failed", "b200j2k_pointer_device", "b200j2k_debug_poke", "b200j2k_wait_upload", "b200j2k_pointer_is_pinned",
            "b200j2k_slot_h2d_bytes",
            "b200j2k_ht_blocks", "b200j2k_idwt", "b200j2k_host_alloc", "b200j2k_host_free",
            "b200j2k_host_register", "b200j2k_host_unregister", "b200j2k_device_alloc", "b200j2k_device_free",

@@ -14,8 +14,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
 #include <mutex>
 #include <new>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -122,6 +124,72 @@ struct HostBuf {
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+/* A pageable packet has to be copied into page-locked staging before the copy engine can take it: 23 MB per 4K
+ * frame, 3.3 ms for one host thread on the GPU boxes' CPUs -- more than everything else a frame costs the host.  One
+ * helper thread per decoder context takes the second half of every piece. */
+class CopyHelper {
+public:
+    ~CopyHelper()
+    {
+        if (th_.joinable()) {
+            {
+                std::lock_guard<std::mutex> g(m_);
+                quit_ = true;
+            }
+            cv_.notify_all();
+            th_.join();
+        }
+    }
+    /* memcpy(dst, src, n) with the helper's hand */
+    void copy(uint8_t *dst, const uint8_t *src, size_t n)
+    {
+        if (n < ((size_t)256 << 10)) {
+            memcpy(dst, src, n);
+            return;
+        }
+        if (!th_.joinable())
+            th_ = std::thread([this] { run(); });
+        const size_t half = (n / 2) & ~(size_t)63;
+        {
+            std::lock_guard<std::mutex> g(m_);
+            dst_ = dst + half;
+            src_ = src + half;
+            n_ = n - half;
+            pending_ = true;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, half);
+        std::unique_lock<std::mutex> g(m_);
+        done_.wait(g, [this] { return !pending_; });
+    }
+
+private:
+    void run()
+    {
+        std::unique_lock<std::mutex> g(m_);
+        for (;;) {
+            cv_.wait(g, [this] { return pending_ || quit_; });
+            if (quit_)
+                return;
+            uint8_t *d = dst_;
+            const uint8_t *s = src_;
+            const size_t n = n_;
+            g.unlock();
+            memcpy(d, s, n);
+            g.lock();
+            pending_ = false;
+            done_.notify_all();
+        }
+    }
+    std::thread th_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    uint8_t *dst_ = nullptr;
+    const uint8_t *src_ = nullptr;
+    size_t n_ = 0;
+    bool pending_ = false, quit_ = false;
+};
 
 /* How the code-blocks of one frame are spread over the HT kernels.  order[] lists descriptor indices as
  * [refine | coded | zero | wide | rwide | mq]:
@@ -249,7 +317,7 @@ int run_ht(cudaStream_t st, const HtPlan &hp, const CblkDesc *d_cblk, const uint
 
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
+    cudaEvent_t done = nullptr;       /* recorded behind the host->device copies of a frame (b200j2k_wait_upload) */
     Parser parser;
     HostBuf stage;          /* pinned: tables + bytes */
     HostBuf out_stage;      /* pinned: picture when the caller's planes are pageable */
@@ -277,6 +345,7 @@ struct b200j2k_decoder {
     int flags = 0;
     std::vector<Slot> slots;
     uint64_t seq = 0;
+    CopyHelper copier;
 };
 
 namespace {
@@ -418,12 +487,14 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
         const size_t piece = (size_t)4 << 20;
         for (size_t at = at0; at < at0 + len && e == cudaSuccess; at += piece) {
             const size_t n = at0 + len - at < piece ? at0 + len - at : piece;
-            memcpy(h + s.off_bytes + at, pkt + at, n);
+            dec->copier.copy(h + s.off_bytes + at, pkt + at, n);
             e = cudaMemcpyAsync(dblob + s.off_bytes + at, h + s.off_bytes + at, n, cudaMemcpyHostToDevice, s.stream);
         }
     }
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(dblob + off_tail, htail, tail, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess)
+        e = cudaEventRecord(s.done, s.stream);
     /* PAL8: plane 1 of the picture is the palette (AVFrame.data[1], jpeg2000dec.c:2900-2901); no kernel writes it */
     if (e == cudaSuccess && pal8)
         e = cudaMemcpyAsync((uint8_t *)s.d_picture.p + p.plane_off[1], dblob + off_pal, sizeof(p.hdr.palette),
@@ -715,6 +786,17 @@ int b200j2k_wait(b200j2k_decoder *d, int slot)
         return B200J2K_ERR_DEVICE;
     return finish_slot(d->slots[slot]);
 }
+
+int b200j2k_wait_upload(b200j2k_decoder *d, int slot)
+{
+    if (!d || slot < 0 || slot >= (int)d->slots.size())
+        return B200J2K_ERR_EINVAL;
+    if (cudaSetDevice(d->device) != cudaSuccess)
+        return B200J2K_ERR_DEVICE;
+    return cudaEventSynchronize(d->slots[slot].done) == cudaSuccess ? 0 : B200J2K_ERR_DEVICE;
+}
+
+int b200j2k_pointer_is_pinned(const void *p) { return device_ok() > 0 && is_pinned(p); }
 
 int64_t b200j2k_decode(b200j2k_decoder *d, const uint8_t *pkt, int64_t pkt_size, uint8_t *const data[4],
                        const int linesize[4], b200j2k_frame_info *info)

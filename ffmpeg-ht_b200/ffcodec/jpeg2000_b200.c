@@ -33,6 +33,8 @@
  * different name.
  */
 #include <stdatomic.h>
+#include <string.h>
+#include <time.h>
 
 #include "libavutil/buffer.h"
 #include "libavutil/hwcontext.h"
@@ -47,6 +49,8 @@
 
 #include "b200j2k.h"
 
+#define B200J2K_MAX_ASYNC 4
+
 typedef struct B200J2KContext {
     const AVClass *class;
     b200j2k_decoder *dec;
@@ -58,7 +62,25 @@ typedef struct B200J2KContext {
     size_t pool_size;
     AVBufferRef *hwframes;  /* frames context this decoder created from the caller's hw_device_ctx */
     int cur_device;         /* device the library context lives on */
+    /* "async_depth" > 1: up to that many pictures are in flight inside this context, the frame of packet N comes out
+     * while packet N + depth - 1 goes in (a decoder with delay, like every hardware decoder of libavcodec) */
+    int async_depth;
+    struct {
+        AVFrame *frame;
+        int slot;
+    } pending[B200J2K_MAX_ASYNC];
+    int npending;
+    double t_phase[6];      /* B200SHIM_TRACE=1: seconds spent in probe / get frame / submit / upload wait / output wait */
+    int n_calls;
 } B200J2KContext;
+
+static int b200j2k_drain(AVCodecContext *avctx, B200J2KContext *s);
+static double b200j2k_now(void)
+{
+    struct timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return t.tv_sec + 1e-9 * t.tv_nsec;
+}
 
 /* ---- pinned frame pool ------------------------------------------------------------------------------------ */
 static void b200j2k_pinned_free(void *opaque, uint8_t *data)
@@ -205,17 +227,60 @@ static av_cold int b200j2k_ff_init(AVCodecContext *avctx)
         device = (int)(atomic_fetch_add(&next_device, 1) % (unsigned)ndev);
     }
     s->cur_device = device;
-    return b200j2k_create(&s->dec, device, 1, flags);
+    s->async_depth = FFMAX(1, FFMIN(s->async_depth, B200J2K_MAX_ASYNC));
+    return b200j2k_create(&s->dec, device, s->async_depth, flags);
 }
 
 static av_cold int b200j2k_ff_close(AVCodecContext *avctx)
 {
     B200J2KContext *s = avctx->priv_data;
+    if (getenv("B200SHIM_TRACE") && s->n_calls)
+        av_log(avctx, AV_LOG_ERROR, "b200 shim trace: %d calls, ms per call: probe %.3f frame %.3f submit %.3f upload-wait %.3f "
+               "output-wait %.3f\n", s->n_calls, 1e3 * s->t_phase[0] / s->n_calls, 1e3 * s->t_phase[1] / s->n_calls,
+               1e3 * s->t_phase[2] / s->n_calls, 1e3 * s->t_phase[3] / s->n_calls, 1e3 * s->t_phase[4] / s->n_calls);
+    b200j2k_drain(avctx, s);
     b200j2k_destroy(s->dec);
     s->dec = NULL;
     av_buffer_pool_uninit(&s->pool);
     av_buffer_unref(&s->hwframes);
     return 0;
+}
+
+/* waits for the oldest picture in flight and hands it out */
+static int b200j2k_output_oldest(AVCodecContext *avctx, B200J2KContext *s, AVFrame *picture, int *got_frame)
+{
+    int ret, failed;
+    if (!s->npending)
+        return 0;
+    ret = b200j2k_wait(s->dec, s->pending[0].slot);
+    failed = ret < 0 ? 0 : b200j2k_slot_blocks_failed(s->dec, s->pending[0].slot);
+    if (ret >= 0) {
+        av_frame_move_ref(picture, s->pending[0].frame);
+        *got_frame = 1;
+        if (failed > 0)
+            av_log(avctx, AV_LOG_ERROR, "%d code-blocks could not be decoded (zeros in their place)\n", failed);
+    }
+    av_frame_free(&s->pending[0].frame);
+    s->npending--;
+    memmove(&s->pending[0], &s->pending[1], s->npending * sizeof(s->pending[0]));
+    return ret;
+}
+
+/* drops everything in flight (close, seek, change of device) */
+static int b200j2k_drain(AVCodecContext *avctx, B200J2KContext *s)
+{
+    while (s->npending) {
+        b200j2k_wait(s->dec, s->pending[0].slot);
+        av_frame_free(&s->pending[0].frame);
+        s->npending--;
+        memmove(&s->pending[0], &s->pending[1], s->npending * sizeof(s->pending[0]));
+    }
+    return 0;
+}
+
+static av_cold void b200j2k_ff_flush(AVCodecContext *avctx)
+{
+    b200j2k_drain(avctx, avctx->priv_data);
 }
 
 static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_frame, AVPacket *avpkt)
@@ -228,9 +293,14 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
     int64_t consumed;
     int ret, flags = s->flags;
 
+    double t0, t1;
+    if (!avpkt->size)                                      /* end of stream: hand out what is still in flight */
+        return b200j2k_output_oldest(avctx, s, picture, got_frame);
+    t0 = b200j2k_now();
     /* header pass: everything jpeg2000_read_main_headers() publishes before the picture exists */
     if ((ret = b200j2k_probe(avpkt->data, avpkt->size, flags, &info)) < 0)
         return ret;
+    t1 = b200j2k_now(); s->t_phase[0] += t1 - t0; t0 = t1; s->n_calls++;
     /* the generic layer shifts the dimensions back down by lowres (jpeg2000dec.c:326, utils.c:94-107) */
     if ((ret = ff_set_dimensions(avctx, info.width << avctx->lowres, info.height << avctx->lowres)) < 0)
         return ret;
@@ -256,9 +326,11 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
             /* decode on the GPU the caller's frames live on */
             const int dev = b200j2k_pointer_device(picture->data[0]);
             if (dev >= 0 && dev != s->cur_device) {
+                if ((ret = b200j2k_drain(avctx, s)) < 0)
+                    return ret;
                 b200j2k_destroy(s->dec);
                 s->dec = NULL;
-                if ((ret = b200j2k_create(&s->dec, dev, 1, s->flags)) < 0)
+                if ((ret = b200j2k_create(&s->dec, dev, s->async_depth, s->flags)) < 0)
                     return ret;
                 s->cur_device = dev;
             }
@@ -272,20 +344,56 @@ static int b200j2k_ff_decode(AVCodecContext *avctx, AVFrame *picture, int *got_f
     if (ret < 0)
         return ret;
 have_picture:
+    t1 = b200j2k_now(); s->t_phase[1] += t1 - t0; t0 = t1;
     for (int i = 0; i < info.nplanes; i++) {
         data[i]     = picture->data[i];
         linesize[i] = picture->linesize[i];
     }
     /* pinned frame pools (get_buffer2 backed by b200j2k_host_alloc) receive the DMA directly; ordinary
      * av_malloc'ed frames go through the library's pinned staging buffer */
-    consumed = b200j2k_decode(s->dec, avpkt->data, avpkt->size, data, linesize, &info);
-    if (consumed < 0)
+    if (s->async_depth <= 1) {
+        consumed = b200j2k_decode(s->dec, avpkt->data, avpkt->size, data, linesize, &info);
+        if (consumed < 0)
+            return (int)consumed;
+        t1 = b200j2k_now(); s->t_phase[2] += t1 - t0;
+        /* the reference logs every damaged HT block and carries on with zeros in its place (jpeg2000dec.c:2275-2278) */
+        if (info.nblocks_failed > 0)
+            av_log(avctx, AV_LOG_ERROR, "%d code-blocks could not be decoded (zeros in their place)\n", info.nblocks_failed);
+        *got_frame = 1;
         return (int)consumed;
-    /* the reference logs every damaged HT block and carries on with zeros in its place (jpeg2000dec.c:2275-2278) */
-    if (info.nblocks_failed > 0)
-        av_log(avctx, AV_LOG_ERROR, "%d code-blocks could not be decoded (zeros in their place)\n", info.nblocks_failed);
-    *got_frame = 1;
-    return (int)consumed;
+    }
+    /* pictures in flight: queue this one (host parsing happens here, copies and kernels are asynchronous), then hand out
+     * the oldest one once `async_depth` are under way.  The packet is only read during the call unless it lies in
+     * page-locked memory, in which case the reference held by the queued frame's side keeps it alive: libavcodec
+     * keeps avpkt valid only for the call, so a pinned packet is staged like a pageable one here. */
+    {
+        AVFrame *queued = av_frame_alloc();
+        int slot;
+        if (!queued)
+            return AVERROR(ENOMEM);
+        av_frame_move_ref(queued, picture);
+        slot = b200j2k_submit(s->dec, avpkt->data, avpkt->size, data, linesize, &info);
+        if (slot < 0) {
+            av_frame_free(&queued);
+            return slot;
+        }
+        t1 = b200j2k_now(); s->t_phase[2] += t1 - t0; t0 = t1;
+        /* the packet must not be referenced after this call returns: if the library DMAs straight from a page-locked
+         * packet, wait for the upload before giving the packet back */
+        if (b200j2k_pointer_is_pinned(avpkt->data) && (ret = b200j2k_wait_upload(s->dec, slot)) < 0) {
+            av_frame_free(&queued);
+            return ret;
+        }
+        t1 = b200j2k_now(); s->t_phase[3] += t1 - t0; t0 = t1;
+        s->pending[s->npending].frame = queued;
+        s->pending[s->npending].slot  = slot;
+        s->npending++;
+        consumed = info.bytes_consumed;
+        if (s->npending >= s->async_depth && (ret = b200j2k_output_oldest(avctx, s, picture, got_frame)) < 0)
+            return ret;
+        t1 = b200j2k_now(); s->t_phase[4] += t1 - t0;
+        return (int)consumed;
+    }
 }
 
 #define OFFSET(x) offsetof(B200J2KContext, x)
@@ -298,6 +406,9 @@ static const AVOption b200j2k_options[] = {
     { "pinned_frames", "Take the pictures from a pool of page-locked memory owned by the decoder unless the caller "
                        "installed a get_buffer2",
         OFFSET(pinned_frames), AV_OPT_TYPE_BOOL, { .i64 = 1 }, 0, 1, VD },
+    { "async_depth", "Pictures in flight inside one decoder context (1 = synchronous, like the native decoder; more "
+                     "adds that many minus one frames of delay and overlaps host parsing with the transfers)",
+        OFFSET(async_depth), AV_OPT_TYPE_INT, { .i64 = 1 }, 1, B200J2K_MAX_ASYNC, VD },
     { NULL },
 };
 
@@ -313,10 +424,13 @@ const FFCodec ff_jpeg2000_b200_decoder = {
     CODEC_LONG_NAME("JPEG 2000 (HTJ2K decode path on NVIDIA B200)"),
     .p.type         = AVMEDIA_TYPE_VIDEO,
     .p.id           = AV_CODEC_ID_JPEG2000,
-    .p.capabilities = AV_CODEC_CAP_SLICE_THREADS | AV_CODEC_CAP_FRAME_THREADS | AV_CODEC_CAP_DR1,
+    /* the native decoder's capabilities plus DELAY: only with async_depth > 1 does a frame ever stay behind, but the
+     * flag is what makes libavcodec drain the decoder at the end of the stream */
+    .p.capabilities = AV_CODEC_CAP_SLICE_THREADS | AV_CODEC_CAP_FRAME_THREADS | AV_CODEC_CAP_DR1 | AV_CODEC_CAP_DELAY,
     .priv_data_size = sizeof(B200J2KContext),
     .init           = b200j2k_ff_init,
     .close          = b200j2k_ff_close,
+    .flush          = b200j2k_ff_flush,
     FF_CODEC_DECODE_CB(b200j2k_ff_decode),
     .p.priv_class   = &b200j2k_class,
     .p.max_lowres   = 5,

@@ -170,6 +170,14 @@ void *b200j2k_device_alloc(int device, int64_t bytes);
 void b200j2k_device_free(void *p);
 int b200j2k_device_download(void *dst_host, const void *src_device, int64_t bytes);
 
+/* After b200j2k_submit(): returns once the packet has been read (its host->device copies are done), i.e. when a
+ * packet in page-locked memory may be released although the frame is still being decoded.  A pageable packet has been
+ * copied by the time submit returns.  The FFCodec shim with async_depth > 1 needs it: libavcodec keeps an AVPacket
+ * valid only for the duration of the decode callback. */
+int b200j2k_wait_upload(b200j2k_decoder *dec, int slot);
+/* 1 when the pointer lies in page-locked (cudaHostAlloc'ed or registered) host memory */
+int b200j2k_pointer_is_pinned(const void *p);
+
 /* Device ordinal of the GPU a pointer's memory lives on, -1 for host memory: lets the FFCodec shim put its decoder
  * context next to the AV_PIX_FMT_CUDA frames the caller hands it (AVHWFramesContext, libavutil/hwcontext_cuda.c:204). */
 int b200j2k_pointer_device(const void *p);

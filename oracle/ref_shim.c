@@ -251,6 +251,60 @@ int REF_NAME(decode)(const uint8_t *cs, int64_t len, int bitexact, int64_t *info
     return ret;
 }
 
+/*
+ * A sequence through ONE decoder context, frames collected in output order -- also from a decoder with delay (empty
+ * packets drain it at the end, as libavcodec does for AV_CODEC_CAP_DELAY decoders).  info: 8 words per OUTPUT frame
+ * ([0] width [1] height [2] format [3] bytes written), *nout = frames that came out; out: the frames back to back.
+ */
+int REF_NAME(decode_seq)(const uint8_t *const *cs, const int64_t *len, int n, int bitexact, int64_t *info, int *nout,
+                         uint8_t *out, int64_t cap)
+{
+    AVCodecContext *avctx = ctx_open(bitexact);
+    if (!avctx)
+        return AVERROR(ENOMEM);
+    int ret = 0, k = 0;
+    int64_t pos = 0;
+    for (int i = 0; ret >= 0 && (i < n || k < n); i++) {
+        AVPacket pkt;
+        memset(&pkt, 0, sizeof(pkt));
+        uint8_t *padded = NULL;
+        if (i < n) {
+            padded = av_mallocz(len[i] + AV_INPUT_BUFFER_PADDING_SIZE);
+            memcpy(padded, cs[i], len[i]);
+            pkt.data = padded;
+            pkt.size = (int)len[i];
+        }
+        AVFrame *frame = av_mallocz(sizeof(AVFrame));
+        frame->extended_data = frame->data;
+        int got = 0;
+        avctx->pix_fmt = AV_PIX_FMT_NONE;
+        ret = REF_CODEC.cb.decode(avctx, frame, &got, &pkt);
+        if (ret >= 0 && got) {
+            int64_t *fi = info + 8 * k;
+            fi[0] = frame->width;
+            fi[1] = frame->height;
+            fi[2] = frame->format;
+            if (frame->format >= 0)
+                avctx->pix_fmt = frame->format;
+            const int64_t w = pack_frame(avctx, frame, out + pos, cap - pos);
+            if (w < 0)
+                ret = AVERROR(EINVAL);
+            else {
+                fi[3] = w;
+                pos += w;
+                k++;
+            }
+        } else if (ret >= 0 && i >= n)
+            ret = AVERROR_EOF;                            /* drained dry before every frame came out */
+        release_frame(frame);
+        av_free(frame);
+        av_free(padded);
+    }
+    *nout = k;
+    ctx_close(avctx);
+    return ret < 0 && ret != AVERROR_EOF ? ret : 0;
+}
+
 const char *REF_NAME(pix_fmt_name)(int fmt) { return av_get_pix_fmt_name(fmt); }
 
 #ifndef REF_STAGE_API
@@ -468,6 +522,8 @@ typedef struct BenchJob {
     pthread_barrier_t *start;
 } BenchJob;
 
+/* one packet in, at most one frame out (a decoder with delay -- the shim with async_depth > 1 -- returns the frame of an
+ * earlier packet, or none yet); data == NULL: an empty packet, which drains.  Returns < 0 on error, else got_frame. */
 static int bench_decode_one(AVCodecContext *avctx, const uint8_t *data, int64_t len)
 {
     AVPacket pkt;
@@ -475,12 +531,36 @@ static int bench_decode_one(AVCodecContext *avctx, const uint8_t *data, int64_t 
     pkt.data = (uint8_t *)data;                           /* padded copies made by decode_bench, outside the timing */
     pkt.size = (int)len;
     AVFrame *frame = av_mallocz(sizeof(AVFrame));
+    frame->extended_data = frame->data;
     int got = 0;
     avctx->pix_fmt = AV_PIX_FMT_NONE;
-    const int bad = REF_CODEC.cb.decode(avctx, frame, &got, &pkt) < 0 || !got;
+    const int ret = REF_CODEC.cb.decode(avctx, frame, &got, &pkt);
     release_frame(frame);
     av_free(frame);
-    return bad;
+    return ret < 0 ? ret : got;
+}
+
+/* sends the packets first, first + step, ... `reps` times and drains; errors + missing frames are counted */
+static void bench_decode_run(BenchJob *j, AVCodecContext *avctx, int reps)
+{
+    int sent = 0, got = 0;
+    for (int r = 0; r < reps; r++)
+        for (int i = j->first; i < j->nframes; i += j->step) {
+            const int g = bench_decode_one(avctx, j->cs[i], j->len[i]);
+            sent++;
+            if (g < 0)
+                j->errors++;
+            else
+                got += g;
+        }
+    while (got < sent) {                                  /* frames still inside a decoder with delay */
+        const int g = bench_decode_one(avctx, NULL, 0);
+        if (g <= 0)
+            break;
+        got += g;
+    }
+    if (got != sent)
+        j->errors++;
 }
 
 static void *bench_worker(void *arg)
@@ -489,16 +569,18 @@ static void *bench_worker(void *arg)
     AVCodecContext *avctx = ctx_open(j->bitexact);
     /* steady state is what is measured: opening the context and the first frame of a sequence (tables, buffers
      * that grow once) happen before the clock starts, for the reference and for the shim alike */
-    if (j->first < j->nframes)
-        j->errors += bench_decode_one(avctx, j->cs[j->first], j->len[j->first]);
+    if (j->first < j->nframes) {
+        BenchJob warm = *j;
+        warm.nframes = j->first + 1;
+        bench_decode_run(&warm, avctx, 1);                /* buffers, tables */
+        bench_decode_run(&warm, avctx, 5);                /* frame pools at their steady-state depth */
+        j->errors += warm.errors;
+    }
     pthread_barrier_wait(j->start);
-    for (int r = 0; r < j->reps; r++)
-        for (int i = j->first; i < j->nframes; i += j->step)
-            j->errors += bench_decode_one(avctx, j->cs[i], j->len[i]);
+    bench_decode_run(j, avctx, j->reps);
     ctx_close(avctx);
     return NULL;
 }
-
 
 /* decodes every codestream `reps` times using `threads` decoder contexts; returns seconds (<0 on error).
  * REF_PINNED_PACKETS=1 (shim build only): the packets live in page-locked memory, as a caller's own AVBuffer pool

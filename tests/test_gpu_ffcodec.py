@@ -185,3 +185,42 @@ def test_ffcodec_shim_cuda_frames(kw):
                 assert fi[2] == AV_PIX_FMT_CUDA and fi[2] != i1[2]
             else:
                 assert fi[4] == 0 and fi[2] == i1[2]
+
+
+def decode_seq(lib, prefix, streams, flags=0):
+    n = len(streams)
+    bufs = [np.frombuffer(s, np.uint8) for s in streams]
+    ptrs = (ctypes.c_void_p * n)(*[b.ctypes.data for b in bufs])
+    lens = (ctypes.c_int64 * n)(*[b.size for b in bufs])
+    info = (ctypes.c_int64 * (8 * n))()
+    nout = ctypes.c_int(0)
+    out = np.zeros(1 << 26, np.uint8)
+    fn = getattr(lib, prefix + "decode_seq")
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int64),
+                   ctypes.POINTER(ctypes.c_int), ctypes.c_void_p, ctypes.c_int64]
+    ret = fn(ptrs, lens, n, flags, info, ctypes.byref(nout), out.ctypes.data, out.size)
+    frames, pos = [], 0
+    for i in range(nout.value):
+        fi = list(info[8 * i: 8 * i + 8])
+        frames.append((fi[:3], out[pos: pos + fi[3]].copy()))
+        pos += fi[3]
+    return ret, frames
+
+
+@pytest.mark.parametrize("depth", [1, 2, 4])
+def test_ffcodec_shim_pictures_in_flight(depth, monkeypatch):
+    """Private option async_depth: up to that many pictures in flight inside one decoder context, the frame of packet
+    N comes out while packet N + depth - 1 goes in, the rest when the stream is drained (AV_CODEC_CAP_DELAY).  Seven
+    frames of changing content AND size through one context: every frame, in order, equals the reference decoder's."""
+    from helpers import ref
+    streams = []
+    for i, (w, h) in enumerate([(300, 200)] * 3 + [(208, 144)] * 2 + [(300, 200)] * 2):
+        planes = j2kgen.synth_image(w, h, 3, 12, seed=40 + i)
+        streams.append(j2kgen.encode(planes, 12, j2kgen.EncParams(levels=3, tile=(128, 128) if i % 2 else (0, 0))))
+    r1, want = decode_seq(ref(), "ref_", streams)
+    assert r1 == 0 and len(want) == len(streams)
+    monkeypatch.setenv("REF_OPT_async_depth", str(depth))
+    r2, got = decode_seq(ctypes.CDLL(str(SHIM)), "b200shim_", streams)
+    assert r2 == 0 and len(got) == len(streams)
+    for (i1, o1), (i2, o2) in zip(want, got):
+        assert i1 == i2 and np.array_equal(o1, o2)
