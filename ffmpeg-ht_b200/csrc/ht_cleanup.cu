@@ -419,7 +419,7 @@ __device__ __forceinline__ void zero_block(uint32_t *dst, uint32_t dstride, int 
 
 /* dequantisation variants selected per block (warp-uniform): the two common cases skip the ROI / step-size
  * branches of dequant() */
-enum { DQ_GENERIC = 0, DQ_INT53 = 1, DQ_FLOAT97 = 2 };
+enum { DQ_GENERIC = 0, DQ_INT53 = 1, DQ_FLOAT97 = 2, DQ_INT53_DN = 3 };    /* DQ_INT53(_DN): see magsgn_block */
 
 template <int DQ>
 __device__ __forceinline__ uint32_t dq(uint32_t mu, int sh53, float fscale, int mode, int M_b, int roi_shift, const BandDesc &bd)
@@ -458,10 +458,16 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
     const int Pcup = d.Lcup - Scup;
     const int sh53 = 31 - M_b;
     const float fscale = bd.fscale;
-    /* DQ_INT53: (x << pLSB | half) >> sh53 as x << dq_up >> dq_dn | dq_half (mag << pLSB never overflows a
-     * valid sample: U <= maxbp keeps it below bit 31) */
-    const int dq_up = pLSB > sh53 ? pLSB - sh53 : 0, dq_dn = pLSB < sh53 ? sh53 - pLSB : 0;
+    /* DQ_INT53 / DQ_INT53_DN: (x << pLSB | half) >> sh53 with per-block constants, written as MULTIPLICATIONS.  ncu
+     * (profiles/r2_ncu_full_summary.md): this kernel is bound by the integer ALU pipe (shifts, logic, compares, selects:
+     * one warp instruction per two cycles and scheduler), the multiply-add pipe beside it is half empty.  So
+     *   pLSB >= sh53 (DQ_INT53):    r = mag * 2^(pLSB - sh53) + half        one IMAD
+     *   pLSB <  sh53 (DQ_INT53_DN): r = umulhi(mag, 2^(32 - (sh53 - pLSB)))  one IMAD.HI  (= mag >> (sh53 - pLSB))
+     * and the sign and the "no MagSgn bits: zero" select become a factor of -1 / 0 / +1 (two's complement wraps
+     * exactly like the shifts did: mag << pLSB of a valid sample stays below bit 31, U <= maxbp). */
+    uint32_t dq_mul = pLSB >= sh53 ? 1u << (pLSB - sh53) : 1u << (32 - (sh53 - pLSB));
     const uint32_t dq_half = pLSB - 1 >= sh53 ? 1u << (pLSB - 1 - sh53) : 0;
+    asm("" : "+r"(dq_mul));          /* opaque: else the compiler turns the multiplications back into shifts */
 
     /* un-stuffed MagSgn bits in shared memory; past the end the decoder reads ones */
     const int ms_words = (Pcup + 3) / 4 + 2;
@@ -528,23 +534,29 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
             const int mm = (int)((mB >> (8 * i)) & 0xFF);
             const uint32_t p = min(pos0 + ((preB >> (8 * i)) & 0xFF), ms_bits);   /* past the end: ones */
             J2K_BOUNDS((int)(p >> 5) + 1 < ms_words);
-            uint32_t v = ms_read(ms, p, mm) | (((e1B >> (8 * i)) & 1u) << mm);
+            /* the mm-bit field at bit p, plus the implicit leading one (emb_1) on top of it: the mask and the placing
+             * of that bit as arithmetic on 2^mm (multiply-add pipe) instead of two more shifts */
+            uint32_t pow2 = 1u << mm;
+            asm("" : "+r"(pow2));
+            const uint32_t wi = p >> 5;
+            const uint32_t field = __funnelshift_r(ms[wi], ms[wi + 1], p) & (pow2 - 1u);
+            uint32_t v = ((e1B >> (8 * i)) & 1u) * pow2 + field;
             const unsigned E = 32 - __clz(v | 1);        /* :419-425 */
             if (i == 1) E1 = mm ? E : 0;
             if (i == 3) E3 = mm ? E : 0;
             uint32_t val;
-            if (DQ == DQ_INT53 && !REFINE) {
-                /* mu >> (31 - M_b) with mu = ((v >> 1) + 1) << pLSB | 1 << (pLSB - 1), then the sign: the
-                 * shifts are per-block constants (dequantization_int, jpeg2000dec.c:2120-2151) */
+            if ((DQ == DQ_INT53 || DQ == DQ_INT53_DN) && !REFINE) {
                 const uint32_t mag = (v >> 1) + 1;
-                const int32_t r = (int32_t)(((mag << dq_up) >> dq_dn) | dq_half);
-                val = (uint32_t)((v & 1u) ? -r : r);
+                const uint32_t r = DQ == DQ_INT53 ? mag * dq_mul + dq_half : __umulhi(mag, dq_mul);
+                const uint32_t sgnz = (uint32_t)min(mm, 1) * (1u - 2u * (v & 1u));     /* -1, 0 or +1 */
+                val = r * sgnz;
             } else {
                 val = ((v >> 1) + 1) << pLSB;
                 val |= 1u << (pLSB - 1);
                 val |= (v & 1u) << 31;
+                val = mm ? val : 0u;
             }
-            mu[i] = mm ? val : 0u;
+            mu[i] = val;
         }
         pE1 = E1;
         pE3 = E3;
@@ -566,7 +578,7 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
                 prev_sg = sg;
         }
         if (act) {
-            constexpr bool RAW = REFINE || DQ == DQ_INT53;   /* already final (or finished later) */
+            constexpr bool RAW = REFINE || DQ == DQ_INT53 || DQ == DQ_INT53_DN;   /* already final (or finished later) */
             const uint32_t o0 = RAW ? mu[0] : dq<DQ>(mu[0], sh53, fscale, mode, M_b, roi_shift, bd),
                            o1 = RAW ? mu[1] : dq<DQ>(mu[1], sh53, fscale, mode, M_b, roi_shift, bd),
                            o2 = RAW ? mu[2] : dq<DQ>(mu[2], sh53, fscale, mode, M_b, roi_shift, bd),
@@ -633,7 +645,12 @@ ht_magsgn_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict_
         uint8_t *sigb = reinterpret_cast<uint8_t *>(const_cast<uint32_t *>(scratch) + scr_off[bi] + rl.sig);
         magsgn_block<DQ_GENERIC, true>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane, sigb);
     } else if (d.roi_shift == 0 && mode == J2K_DWT53 && bd.i_stepsize == 32768) {
-        magsgn_block<DQ_INT53, false>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane, nullptr);
+        const int rem = d.npasses % 3;
+        const int S_blk = ((rem ? d.npasses - rem : d.npasses - 3) / 3 + d.zbp) & 0xFF;
+        if (30 - S_blk >= 31 - d.M_b)
+            magsgn_block<DQ_INT53, false>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane, nullptr);
+        else
+            magsgn_block<DQ_INT53_DN, false>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane, nullptr);
     } else if (d.roi_shift == 0 && mode == J2K_DWT97) {
         magsgn_block<DQ_FLOAT97, false>(d, bi, Scup, Dcup, bd, q, ms, dst, status, lane, nullptr);
     } else {
