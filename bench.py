@@ -762,7 +762,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=64)
     ap.add_argument("--distinct", type=int, default=4, help="distinct synthetic frames that are cycled")
-    ap.add_argument("--slots", type=int, default=12, help="frames in flight in the kernel-only leg")
+    ap.add_argument("--slots", type=int, default=16, help="frames in flight in the kernel-only leg")
     ap.add_argument("--host-threads", type=int, default=4, help="decoder contexts (host threads) in the e2e leg")
     ap.add_argument("--slots-e2e", type=int, default=2)
     ap.add_argument("--scale", type=int, default=1, help="shrink the frame by this factor (debugging only)")

@@ -14,10 +14,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <condition_variable>
 #include <mutex>
 #include <new>
-#include <thread>
 #include <utility>
 #include <vector>
 
@@ -124,72 +122,6 @@ struct HostBuf {
 };
 
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
-
-/* A pageable packet has to be copied into page-locked staging before the copy engine can take it: 23 MB per 4K
- * frame, 3.3 ms for one host thread on the GPU boxes' CPUs -- more than everything else a frame costs the host.  One
- * helper thread per decoder context takes the second half of every piece. */
-class CopyHelper {
-public:
-    ~CopyHelper()
-    {
-        if (th_.joinable()) {
-            {
-                std::lock_guard<std::mutex> g(m_);
-                quit_ = true;
-            }
-            cv_.notify_all();
-            th_.join();
-        }
-    }
-    /* memcpy(dst, src, n) with the helper's hand */
-    void copy(uint8_t *dst, const uint8_t *src, size_t n)
-    {
-        if (n < ((size_t)256 << 10)) {
-            memcpy(dst, src, n);
-            return;
-        }
-        if (!th_.joinable())
-            th_ = std::thread([this] { run(); });
-        const size_t half = (n / 2) & ~(size_t)63;
-        {
-            std::lock_guard<std::mutex> g(m_);
-            dst_ = dst + half;
-            src_ = src + half;
-            n_ = n - half;
-            pending_ = true;
-        }
-        cv_.notify_all();
-        memcpy(dst, src, half);
-        std::unique_lock<std::mutex> g(m_);
-        done_.wait(g, [this] { return !pending_; });
-    }
-
-private:
-    void run()
-    {
-        std::unique_lock<std::mutex> g(m_);
-        for (;;) {
-            cv_.wait(g, [this] { return pending_ || quit_; });
-            if (quit_)
-                return;
-            uint8_t *d = dst_;
-            const uint8_t *s = src_;
-            const size_t n = n_;
-            g.unlock();
-            memcpy(d, s, n);
-            g.lock();
-            pending_ = false;
-            done_.notify_all();
-        }
-    }
-    std::thread th_;
-    std::mutex m_;
-    std::condition_variable cv_, done_;
-    uint8_t *dst_ = nullptr;
-    const uint8_t *src_ = nullptr;
-    size_t n_ = 0;
-    bool pending_ = false, quit_ = false;
-};
 
 /* How the code-blocks of one frame are spread over the HT kernels.  order[] lists descriptor indices as
  * [refine | coded | zero | wide | rwide | mq]:
@@ -345,7 +277,6 @@ struct b200j2k_decoder {
     int flags = 0;
     std::vector<Slot> slots;
     uint64_t seq = 0;
-    CopyHelper copier;
 };
 
 namespace {
@@ -487,7 +418,7 @@ int stage_frame(b200j2k_decoder *dec, Slot &s, const uint8_t *pkt, int64_t size,
         const size_t piece = (size_t)4 << 20;
         for (size_t at = at0; at < at0 + len && e == cudaSuccess; at += piece) {
             const size_t n = at0 + len - at < piece ? at0 + len - at : piece;
-            dec->copier.copy(h + s.off_bytes + at, pkt + at, n);
+            memcpy(h + s.off_bytes + at, pkt + at, n);
             e = cudaMemcpyAsync(dblob + s.off_bytes + at, h + s.off_bytes + at, n, cudaMemcpyHostToDevice, s.stream);
         }
     }
