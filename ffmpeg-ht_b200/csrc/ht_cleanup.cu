@@ -353,6 +353,7 @@ ht_vlc_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__restrict__ o
     for (int i = threadIdx.x; i < 256; i += blockDim.x)
         uvtab[i] = uvlc_pair_entry(i);
     __syncthreads();
+    asm volatile("griddepcontrol.wait;" ::: "memory");   /* the tables were staged beside the un-stuff kernel's tail */
     /* `active` lanes of the warp own a block each, the others only helped with the tables: every lane walks its
      * own control flow (MEL events, U-VLC cases), so the warp pays for the union of its lanes' paths */
     const int gt = blockIdx.x * active + threadIdx.x;
@@ -476,6 +477,9 @@ __device__ __forceinline__ void magsgn_block(const CblkDesc &d, uint32_t bi, int
     __syncwarp();
     const uint32_t ms_bits = unstuff<US_MAGSGN>(Dcup, Pcup, ms, lane);
     ones_behind(ms, ms_bits, ms_words, lane);
+    /* launched as a programmatic dependent of the VLC kernel: everything above reads only the packet bytes, the quad
+     * words below are that kernel's output (a no-op in a plain launch) */
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const int QW = (w + 1) >> 1, QH = (h + 1) >> 1;
     const bool act = lane < QW;
@@ -932,6 +936,24 @@ uint32_t ht_cleanup_scratch_words(const CblkDesc &d)
     return (uint32_t)((2 * ht_stream_words(S) + QW * QH + 1) & ~1);
 }
 
+/* launch as a programmatic dependent of the kernel before it in the stream: the kernel may start while that one
+ * drains and holds at its griddepcontrol.wait until the predecessor's memory is visible */
+template <class... P, class... A>
+static void launch_dependent(void (*kernel)(P...), int grid, int block, size_t smem, cudaStream_t stream, A... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 static int set_smem(const void *fn, size_t bytes)
 {
     if (bytes > 227 * 1024)
@@ -950,6 +972,7 @@ int launch_ht_cleanup(cudaStream_t stream, const CblkDesc *descs, const uint32_t
     const int n_vlc = n_refine + n_coded;
     uint32_t *scr = (uint32_t *)scratch;
     static const int skip = getenv("B200J2K_SKIP") ? atoi(getenv("B200J2K_SKIP")) : 0;   /* tuning: marginal cost of a kernel */
+    static const int chain = getenv("B200J2K_HT_PDL") ? atoi(getenv("B200J2K_HT_PDL")) : 0;  /* tuning: 1 VLC, 2 MagSgn */
     if (n_vlc > 0 && !(skip & 1)) {
         const int warp_words = 2 * ht_stream_words(max_Lcup < 4079 ? max_Lcup : 4079);
         const size_t smem0 = (size_t)warp_words * 4 * WARPS_PER_CTA;
@@ -976,8 +999,12 @@ int launch_ht_cleanup(cudaStream_t stream, const CblkDesc *descs, const uint32_t
             const int a = e ? atoi(e) : VLC_ACTIVE_LANES;
             return a >= 1 && a <= VLC_LANES_PER_CTA ? a : VLC_ACTIVE_LANES;
         }();
-        ht_vlc_kernel<<<(n_vlc + active - 1) / active, VLC_LANES_PER_CTA, 0, stream>>>(
-            descs, order, scr_off, n_vlc, bytes, scr, active);
+        if (!(chain & 1) || n_refine > 0 || after_unstuff || (skip & 1))   /* not directly behind the un-stuff kernel */
+            ht_vlc_kernel<<<(n_vlc + active - 1) / active, VLC_LANES_PER_CTA, 0, stream>>>(
+                descs, order, scr_off, n_vlc, bytes, scr, active);
+        else
+            launch_dependent(ht_vlc_kernel, (n_vlc + active - 1) / active, VLC_LANES_PER_CTA, 0, stream, descs, order,
+                             scr_off, n_vlc, bytes, scr, active);
         launches++;
     }
     if (after_vlc)
@@ -987,8 +1014,14 @@ int launch_ht_cleanup(cudaStream_t stream, const CblkDesc *descs, const uint32_t
         const size_t smem2 = (size_t)stream_words * 4 * WARPS_PER_CTA;
         if ((r = set_smem((const void *)ht_magsgn_kernel<false>, smem2)) < 0)
             return r;
-        ht_magsgn_kernel<false><<<(n_coded + n_zero + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, smem2, stream>>>(
-            descs, order + n_refine, scr_off, n_coded + n_zero, bytes, bands, scr, (uint32_t *)coef, status, stream_words);
+        const int grid2 = (n_coded + n_zero + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+        if (!(chain & 2) || n_vlc == 0 || after_vlc || (skip & 2))          /* not directly behind the VLC kernel */
+            ht_magsgn_kernel<false><<<grid2, WARPS_PER_CTA * 32, smem2, stream>>>(
+                descs, order + n_refine, scr_off, n_coded + n_zero, bytes, bands, scr, (uint32_t *)coef, status, stream_words);
+        else
+            launch_dependent(ht_magsgn_kernel<false>, grid2, WARPS_PER_CTA * 32, smem2, stream, descs, order + n_refine,
+                             scr_off, n_coded + n_zero, bytes, bands, (const uint32_t *)scr, (uint32_t *)coef, status,
+                             stream_words);
         launches++;
     }
     return cudaGetLastError() == cudaSuccess ? launches : -3;

@@ -836,8 +836,9 @@ bool idwt_stream_final_ok(const IdwtFrame &f, int type, int *ncomp)
 
 namespace {
 
-template <class K> void launch_item(cudaStream_t stream, K kernel, int smem, const IdwtStreamCache::Item &it)
+template <class K> void launch_item(cudaStream_t stream, K kernel, int smem, const IdwtStreamCache::Item &it, bool first = false)
 {
+    static const int pdl = getenv("B200J2K_IDWT_PDL") ? atoi(getenv("B200J2K_IDWT_PDL")) : 1;   /* tuning: 0 plain launches */
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = it.grid;
@@ -848,7 +849,7 @@ template <class K> void launch_item(cudaStream_t stream, K kernel, int smem, con
     attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr.val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = &attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl == 1 || (pdl == 2 && !first) ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, it.p);
 }
 
@@ -860,7 +861,7 @@ int run_items(cudaStream_t stream, K kernel, int smem, IdwtStreamCache *cache, s
         /* same geometry, same buffers: the items of this call were recorded in the same order */
         while (cache->cursor < cache->items.size()) {
             IdwtStreamCache::Item &it = cache->items[cache->cursor++];
-            launch_item(stream, kernel, smem, it);
+            launch_item(stream, kernel, smem, it, cache->cursor == 1);
             launches++;
             if (it.last)
                 break;

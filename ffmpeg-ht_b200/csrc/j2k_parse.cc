@@ -44,9 +44,7 @@ int parse_cox(const uint8_t *p, const uint8_t *end, CodSty *c, int flags)
     if (c->l2cw > 10 || c->l2ch > 10 || c->l2cw + c->l2ch > 12)
         return B200J2K_ERR_INVALIDDATA;
     c->cblk_style = p[3];
-    c->transform = p[4];
-    if (c->transform > 1)
-        return B200J2K_ERR_INVALIDDATA;
+    c->transform = p[4];                                  /* an unknown one fails when a tile is set up with it */
     if ((flags & B200J2K_FLAG_BITEXACT) && c->transform == J2K_DWT97)
         c->transform = J2K_DWT97_INT;
     p += 5;
@@ -67,21 +65,28 @@ int parse_cox(const uint8_t *p, const uint8_t *end, CodSty *c, int flags)
     return 0;
 }
 
-int parse_qcx(const uint8_t *p, int n, QntSty *q)
+/* Sqcd / Sqcc and the step sizes behind it (get_qcx, jpeg2000dec.c:675-717).  n: bytes the segment declares for
+ * this part, avail: bytes to the end of the packet -- the reference reads by what the STYLE needs, checked against
+ * the packet only, and the caller then compares what was consumed with the declared length (:2629).
+ * -> bytes consumed, or an error. */
+int parse_qcx(const uint8_t *p, int n, int64_t avail, QntSty *q)
 {
-    if (n < 1)
+    if (avail < 1)
         return B200J2K_ERR_INVALIDDATA;
     q->nguard = p[0] >> 5;
     q->style = p[0] & 31;
     p++;
-    n--;
+    avail--;
     if (q->style == 0) {
-        if (n > 96)
+        const int m = n - 1;
+        if (avail < m || m > 96)
             return B200J2K_ERR_INVALIDDATA;
-        for (int i = 0; i < n; i++)
+        for (int i = 0; i < m; i++)
             q->expn[i] = p[i] >> 3;
-    } else if (q->style == 1) {
-        if (n < 2)
+        return 1 + (m > 0 ? m : 0);
+    }
+    if (q->style == 1) {
+        if (avail < 2)
             return B200J2K_ERR_INVALIDDATA;
         unsigned x = rd16(p);
         q->expn[0] = x >> 11;
@@ -90,17 +95,18 @@ int parse_qcx(const uint8_t *p, int n, QntSty *q)
             q->expn[i] = (uint8_t)imax(0, q->expn[0] - (i - 1) / 3);
             q->mant[i] = q->mant[0];
         }
-    } else {
-        n >>= 1;
-        if (n > 96)
-            return B200J2K_ERR_INVALIDDATA;
-        for (int i = 0; i < n; i++) {
-            unsigned x = rd16(p + 2 * i);
-            q->expn[i] = x >> 11;
-            q->mant[i] = x & 0x7FF;
-        }
+        return 3;
     }
-    return 0;
+    /* style 2, and every undefined one (their bands get a step size of zero, band_stepsize) */
+    const int m = (n - 1) >> 1;
+    if (avail < 2 * m || m > 96)
+        return B200J2K_ERR_INVALIDDATA;
+    for (int i = 0; i < m; i++) {
+        unsigned x = rd16(p + 2 * i);
+        q->expn[i] = x >> 11;
+        q->mant[i] = x & 0x7FF;
+    }
+    return 1 + (m > 0 ? 2 * m : 0);
 }
 
 /* ---- pixel format selection (get_siz, jpeg2000dec.c:134-193, :328-412) --------------------------------
@@ -390,11 +396,13 @@ float band_stepsize(const CodSty &c, const QntSty &q, int bandno, int gbandno, i
     float f;
     if (q.style == 0) {
         f = 1;
-    } else {
+    } else if (q.style <= 2) {
         union { uint32_t u; float f; } e;
         e.u = (uint32_t)((cbps - q.expn[gbandno]) + 127) << 23;
         f = e.f;
         f *= q.mant[gbandno] / 2048.0 + 1.0;
+    } else {
+        f = 0;                                            /* "Unknown quantization format" (jpeg2000.c:246-249) */
     }
     if (c.transform != J2K_DWT53) {
         int lband = 0;
@@ -511,8 +519,12 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 hend = hp + n;
                 ppm_pos += n;
             }
-            if (has_ppt_[cur_tile] && cur_tp == 0)
+            /* the tile's packed headers become readable HERE, as much of them as has arrived (:2474-2476); a tile
+             * whose first tile-part never reaches its SOD reads an empty header stream: all packets empty */
+            if (has_ppt_[cur_tile] && cur_tp == 0) {
                 ppt_pos_[cur_tile] = 0;
+                ppt_live_[cur_tile] = ppt_[cur_tile].size();
+            }
             pv[cur_tp] = TilePart{ p, tp_end, p, hp, hend };
             p = tp_end;
             continue;
@@ -567,6 +579,7 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             ppt_.assign((size_t)h.ntx * h.nty, {});
             has_ppt_.assign((size_t)h.ntx * h.nty, 0);
             ppt_pos_.assign((size_t)h.ntx * h.nty, 0);
+            ppt_live_.assign((size_t)h.ntx * h.nty, 0);
             const int red = B200J2K_FLAG_GET_LOWRES(flags);
             if (red && (h.X0 || h.Y0))
                 return B200J2K_ERR_PATCHWELCOME;          /* jpeg2000dec.c:256-259 */
@@ -667,8 +680,9 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 return B200J2K_ERR_INVALIDDATA;
             QntSty tmp;
             memset(&tmp, 0, sizeof(tmp));
-            if ((ret = parse_qcx(seg, len - 2, &tmp)) < 0)
+            if ((ret = parse_qcx(seg, len - 2, end - seg, &tmp)) < 0)
                 return ret;
+            seg += ret;
             for (int c = 0; c < h.ncomp; c++) {
                 if (cur_tile >= 0) {
                     if (!tsty_[cur_tile].had_qcc[c])
@@ -678,7 +692,6 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             }
             if (cur_tile >= 0)
                 note_tile_segment(cur_tile, marker_pos, segend);
-            seg = segend;
             break;
         }
         case 0xFF5D: {
@@ -694,9 +707,9 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
                 note_tile_segment(cur_tile, marker_pos, segend);
             } else
                 h.had_qcc[c] = 1;
-            if ((ret = parse_qcx(seg + 1, len - 3, cur_tile >= 0 ? &tsty_[cur_tile].qnt[c] : &h.qnt[c])) < 0)
+            if ((ret = parse_qcx(seg + 1, len - 3, end - (seg + 1), cur_tile >= 0 ? &tsty_[cur_tile].qnt[c] : &h.qnt[c])) < 0)
                 return ret;
-            seg = segend;
+            seg += 1 + ret;
             break;
         }
         case 0xFF5E: {                                    /* RGN (get_rgn, jpeg2000dec.c:641-672; :2530-2534) */
@@ -814,7 +827,7 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             break;
         }
         if (seg != segend)
-            return -1;
+            return B200J2K_ERR_UNSPECIFIED;              /* declared length != what was consumed (:2629-2633) */
         p = segend;
     }
     consumed = (int64_t)(p - pkt);
@@ -1290,13 +1303,17 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
         select_header(tileno, tp);
     else if (ppt) {
         bp_ = ppt_[tileno].data() + ppt_pos_[tileno];
-        bend_ = ppt_[tileno].data() + ppt_[tileno].size();
+        bend_ = ppt_[tileno].data() + ppt_live_[tileno];
     } else
         select_part(tileno, tp, cs.csty);
 
-    struct Inc { uint32_t cb; int nseg; uint32_t seg[6]; };
+    /* blocks this packet contributes to, each with its run of segment lengths in `seglen` (as many as the
+     * contribution has segments: the reference sizes lengthinc[] by the pass count, jpeg2000dec.c:1227) */
+    struct Inc { uint32_t cb; uint32_t first, nseg; };
     static thread_local std::vector<Inc> incs;
+    static thread_local std::vector<uint16_t> seglen;
     incs.clear();
+    seglen.clear();
 
     if (!bits(1)) {
         flush();
@@ -1351,14 +1368,31 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                 if (cb.lblock + llen + ilog2((unsigned)newpasses) > 16)
                     return B200J2K_ERR_PATCHWELCOME;
                 cb.lblock = (uint8_t)(cb.lblock + llen);
-                incs.push_back(Inc{ pg.cblk_base + (uint32_t)k, 0, { 0 } });
+                incs.push_back(Inc{ pg.cblk_base + (uint32_t)k, (uint32_t)seglen.size(), 0 });
                 Inc &in = incs.back();
 
-                int segment_passes, next_segment_passes = 0, nb;
-                unsigned segment_bytes = 0;
-                /* a MIXED block (SPcod bit 7) that the length rules unmask as a Part-1 block: HT bit off for good
-                 * (:1271-1274, :1303-1305, :1331-1333); no bypass / termination on each pass */
-                auto turns_part1 = [&]() -> bool {
+                /* Codeword-segment lengths of this contribution (jpeg2000dec.c:1256-1362; T.800 B.10.7):
+                 * every length is a field of lblock + floor(log2(passes in the segment)) bits.  What differs between
+                 * the three kinds of block is only how the `left` passes are cut into segments:
+                 *   Part-1, style 0     one segment with all of them;
+                 *   HT                  the passes come in sets of three -- cleanup | SigProp MagRef -- and a segment
+                 *                       ends with the cleanup pass and with the set: HT_RUN[position in the set];
+                 *   HT, placeholder     nothing of the block has bytes yet (all passes so far were empty sets): the
+                 *                       segment runs up to the last cleanup pass of the contribution, and its length
+                 *                       decides what the block is (below). */
+                static const uint8_t HT_RUN[3] = { 1, 2, 1 };
+                const bool mixed = (cb.modes & 0x80) != 0;
+                int left = newpasses;
+                auto field = [&](int passes) { return cb.lblock + ilog2((unsigned)passes); };
+                auto take = [&](int passes, unsigned len) {
+                    cb.npasses = (uint8_t)(cb.npasses + passes);
+                    left -= passes;
+                    seglen.push_back((uint16_t)len);
+                    in.nseg++;
+                };
+                /* a MIXED block (SPcod bit 7) whose lengths show Part-1 passes: HT bit off for good (:1271-1274,
+                 * :1303-1305, :1331-1333); bypass / termination on each pass are not served for those */
+                auto unmask_part1 = [&]() -> bool {
                     if (cs.cblk_style & 0x05)
                         return false;
                     cb.plhd = 0;
@@ -1366,93 +1400,46 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                     return true;
                 };
                 if (cb.plhd) {
-                    int href = (cb.npasses + newpasses - 1) % 3;
-                    segment_passes = newpasses - href;
-                    int pass_bound = 2;
-                    nb = cb.lblock;
-                    if (segment_passes < 1) {
-                        segment_passes = newpasses;
-                        while (pass_bound <= segment_passes) { nb++; pass_bound += pass_bound; }
-                        segment_bytes = (unsigned)bits(nb);
-                        if (segment_bytes && (cb.modes & 0x80) && !turns_part1())
+                    const int behind = (cb.npasses + left - 1) % 3;    /* refinement passes behind the last cleanup */
+                    const int upto = left - behind;                    /* passes up to and including that cleanup */
+                    unsigned len;
+                    if (upto < 1) {
+                        /* no cleanup pass in here: HT has nothing to say (zero), bytes mean Part-1 passes */
+                        len = (unsigned)bits(field(left));
+                        if (len && mixed && !unmask_part1())
                             return B200J2K_ERR_PATCHWELCOME;
+                        take(left, len);
                     } else {
-                        while (pass_bound <= segment_passes) { nb++; pass_bound += pass_bound; }
-                        segment_bytes = (unsigned)bits(nb);
-                        if (segment_bytes) {
-                            if (!(cb.modes & 0x80) ||
-                                (cb.lblock > 3 && segment_bytes > 1 && (segment_bytes >> (nb - 1)) == 0)) {
-                                next_segment_passes = 2;          /* the first HT cleanup pass */
-                                cb.plhd = 0;
-                                cb.Lcup = segment_bytes;
-                            } else {                              /* an original (Part-1) coding pass */
-                                if (!turns_part1())
-                                    return B200J2K_ERR_PATCHWELCOME;
-                                segment_passes = newpasses;
-                                while (pass_bound <= segment_passes) {
-                                    nb++;
-                                    pass_bound += pass_bound;
-                                    segment_bytes = (segment_bytes << 1) + (unsigned)bits(1);
-                                }
-                            }
+                        const int nb = field(upto);
+                        len = (unsigned)bits(nb);
+                        /* the first HT cleanup with bytes: always so in an HT-only stream; in a MIXED one the
+                         * reference tells by the field -- grown lblock, more than one byte, top bit clear */
+                        const bool cleanup = len && (!mixed || (cb.lblock > 3 && len > 1 && (len >> (nb - 1)) == 0));
+                        if (cleanup) {
+                            cb.plhd = 0;
+                            cb.Lcup = len;
+                            take(upto, len);
                         } else {
-                            segment_passes = newpasses;
-                            if (pass_bound <= segment_passes) {
-                                for (;;) {
-                                    nb++;
-                                    pass_bound += pass_bound;
-                                    segment_bytes = (segment_bytes << 1) + (unsigned)bits(1);
-                                    if (pass_bound > segment_passes)
-                                        break;
-                                }
-                                if (segment_bytes && (cb.modes & 0x80) && !turns_part1())
-                                    return B200J2K_ERR_PATCHWELCOME;
-                            }
+                            /* the field was that of ALL the passes: the missing low bits follow */
+                            const bool bytes_seen = len != 0;
+                            if (bytes_seen && !unmask_part1())
+                                return B200J2K_ERR_PATCHWELCOME;
+                            const int more = field(left) - nb;
+                            len = (len << more) | (unsigned)bits(more);
+                            if (!bytes_seen && len && mixed && !unmask_part1())
+                                return B200J2K_ERR_PATCHWELCOME;
+                            take(left, len);
                         }
                     }
                 } else if (!(cb.modes & 0x40)) {
-                    /* Part-1 block, style 0: one codeword segment, one length of lblock + floor(log2(passes))
-                     * bits per packet (jpeg2000dec.c:1364-1368) */
-                    segment_bytes = (unsigned)bits(cb.lblock + ilog2((unsigned)newpasses));
-                    segment_passes = newpasses;
-                } else {
-                    segment_passes = cb.npasses % 3;
-                    nb = 0;
-                    if (segment_passes == 0) {
-                        segment_passes = 1;
-                        next_segment_passes = 2;
-                    } else {
-                        segment_passes = newpasses > 1 ? 3 - segment_passes : 1;
-                        next_segment_passes = 1;
-                        nb = ilog2((unsigned)segment_passes);
-                    }
-                    nb += cb.lblock;
-                    segment_bytes = (unsigned)bits(nb);
-                    cb.Lref += segment_bytes;
+                    take(left, (unsigned)bits(field(left)));            /* :1364-1368 */
                 }
-                cb.npasses = (uint8_t)(cb.npasses + segment_passes);
-                in.seg[in.nseg++] = segment_bytes & 0xFFFF;
-                newpasses -= segment_passes & 0xFF;
-                if ((cb.modes & 0x40) && !cb.plhd) {
-                    while (newpasses > 0) {
-                        segment_passes = newpasses > 1 ? next_segment_passes : 1;
-                        next_segment_passes = 3 - next_segment_passes;
-                        nb = cb.lblock + ilog2((unsigned)segment_passes);
-                        segment_bytes = (unsigned)bits(nb);
-                        newpasses -= segment_passes;
-                        cb.Lref += segment_bytes;
-                        cb.npasses = (uint8_t)(cb.npasses + segment_passes);
-                        if (in.nseg < 6)
-                            in.seg[in.nseg++] = segment_bytes & 0xFFFF;
-                    }
-                } else {
-                    while (newpasses > 0) {
-                        segment_bytes = (unsigned)bits(cb.lblock);
-                        newpasses -= 1;
-                        cb.npasses = (uint8_t)(cb.npasses + 1);
-                        if (in.nseg < 6)
-                            in.seg[in.nseg++] = segment_bytes & 0xFFFF;
-                    }
+                /* HT block past its placeholders (possibly since two lines ago): cut by sets */
+                while (left > 0) {
+                    const int run = HT_RUN[cb.npasses % 3] < left ? HT_RUN[cb.npasses % 3] : left;
+                    const unsigned len = (unsigned)bits(field(run));
+                    cb.Lref += len;
+                    take(run, len);
                 }
             }
         }
@@ -1476,8 +1463,8 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
      * is gathered into `extra` so that Dcup||Dref stays contiguous for the kernel */
     for (const Inc &in : incs) {
         CblkState &cb = state_[in.cb];
-        for (int s = 0; s < in.nseg; s++) {
-            uint32_t n = in.seg[s];
+        for (uint32_t s = 0; s < in.nseg; s++) {
+            uint32_t n = seglen[in.first + s];
             if ((uint32_t)(bend_ - bp_) < n || cb.length + n > 65535)
                 return B200J2K_ERR_INVALIDDATA;
             if (n) {
@@ -1732,6 +1719,11 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
          * init_tile fails on !codsty->init (jpeg2000dec.c:1054-1055) and the frame with it */
         if (!tile_first_[tileno])
             return B200J2K_ERR_INVALIDDATA;
+        /* a transform byte other than 0 / 1: ff_jpeg2000_dwt_init has no such type and init_tile fails with its
+         * bare -1 (jpeg2000dwt.c:551-591 via jpeg2000.c:477) */
+        for (int c = 0; c < hdr.ncomp; c++)
+            if (tsty_[tileno].cod[c].transform > J2K_DWT97_INT)
+                return B200J2K_ERR_UNSPECIFIED;
         if (!tile_selected(flags, tileno))
             continue;                                     /* another context's tile: its packets are not even read */
         if (tile_subset)

@@ -169,6 +169,7 @@ private:
     int roi_of(int tileno, int c) const { return tsty_[tileno].roi[c] ? tsty_[tileno].roi[c] : hdr.roi[c]; }
     std::vector<uint8_t> tile_first_;          /* per tile: a tile-part with TPsot == 0 was seen */
     std::vector<size_t> ppt_pos_;             /* tile->packed_headers_stream as an offset into ppt_[tile] */
+    std::vector<size_t> ppt_live_;            /* ... and its size: what had arrived at the SOD of the first tile-part */
 
     /* packet-header bit reader */
     const uint8_t *bp_ = nullptr, *bend_ = nullptr;

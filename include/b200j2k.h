@@ -32,6 +32,8 @@ extern "C" {
 #define B200J2K_ERR_PATCHWELCOME (-1163346256)   /* AVERROR_PATCHWELCOME */
 #define B200J2K_ERR_NOMEM        (-12)           /* AVERROR(ENOMEM) */
 #define B200J2K_ERR_EINVAL       (-22)           /* AVERROR(EINVAL) */
+#define B200J2K_ERR_UNSPECIFIED  (-1)            /* the reference's bare -1: marker segment length mismatch
+                                                  * (jpeg2000dec.c:2633), unknown wavelet type (jpeg2000dwt.c:590) */
 #define B200J2K_ERR_DEVICE       (-19)           /* AVERROR(ENODEV): no usable CUDA device / CUDA failure */
 
 /* b200j2k_create flags */

@@ -99,6 +99,7 @@ typedef struct Tile {
     struct { int RS, CS, LYE, RE, CE, P; } poc[32];
     int has_ppt;
     uint8_t *ppt;
+    size_t ppt_live;                                /* size of it when that stream was set up (SOD of tile-part 0) */
     size_t ppt_size, ppt_pos;                       /* ppt_pos = tile->packed_headers_stream */
 } Tile;
 
@@ -251,40 +252,46 @@ static int parse_cox(Dec *d, const uint8_t *p, const uint8_t *end, CodSty *c)
     return 0;
 }
 
-static int parse_qcx(const uint8_t *p, int n, QntSty *q)
+/* get_qcx (jpeg2000dec.c:675-717).  n = bytes the segment declares for Sqcx + step sizes, avail = bytes to the end
+ * of the packet: what is read depends on the style alone and is checked against the packet; the marker loop then
+ * compares the consumption with the declared length (:2629).  -> bytes consumed or an error */
+static int parse_qcx(const uint8_t *p, int n, int64_t avail, QntSty *q)
 {
-    if (n < 1)
+    if (avail < 1)
         return ORACLE_ERR_INVALID;
     q->nguard = p[0] >> 5;
     q->style = p[0] & 31;
     p++;
-    n--;
+    avail--;
+    int used = 1;
     if (q->style == 0) {
-        if (n > 96)
+        n -= 1;
+        if (avail < n || n > 96)
             return ORACLE_ERR_INVALID;
-        for (int i = 0; i < n; i++)
+        for (int i = 0; i < n; i++, used++)
             q->expn[i] = p[i] >> 3;
     } else if (q->style == 1) {
-        if (n < 2)
+        if (avail < 2)
             return ORACLE_ERR_INVALID;
         unsigned x = rd16(p);
+        used += 2;
         q->expn[0] = x >> 11;
         q->mant[0] = x & 0x7FF;
         for (int i = 1; i < 96; i++) {
             q->expn[i] = imax(0, q->expn[0] - (i - 1) / 3);
             q->mant[i] = q->mant[0];
         }
-    } else {
-        n >>= 1;
-        if (n > 96)
+    } else {                                              /* 2 and the undefined styles alike */
+        n = (n - 1) >> 1;
+        if (avail < 2 * n || n > 96)
             return ORACLE_ERR_INVALID;
-        for (int i = 0; i < n; i++) {
+        for (int i = 0; i < n; i++, used += 2) {
             unsigned x = rd16(p + 2 * i);
             q->expn[i] = x >> 11;
             q->mant[i] = x & 0x7FF;
         }
     }
-    return 0;
+    return used;
 }
 
 /* pixel format choice for a raw codestream (jpeg2000dec.c:134-193, :335-363) */
@@ -599,8 +606,10 @@ static int parse_headers(Dec *d)
                 t->part[cur_tp].hend = t->part[cur_tp].hp + n;
                 d->ppm_pos += n;
             }
-            if (t->has_ppt && cur_tp == 0)                /* :2474-2476 */
+            if (t->has_ppt && cur_tp == 0) {              /* :2474-2476: the packed headers go live here */
                 t->ppt_pos = 0;
+                t->ppt_live = t->ppt_size;
+            }
             t->part[cur_tp].p = p;
             t->part[cur_tp].end = tp_end;
             if (cur_tp + 1 > t->nparts)
@@ -753,8 +762,9 @@ static int parse_headers(Dec *d)
                 return ORACLE_ERR_INVALID;
             QntSty tmp;
             memset(&tmp, 0, sizeof(tmp));
-            if ((ret = parse_qcx(seg, len - 2, &tmp)) < 0)
+            if ((ret = parse_qcx(seg, len - 2, d->end - seg, &tmp)) < 0)
                 return ret;
+            seg += ret;
             for (int c = 0; c < d->ncomp; c++) {
                 if (cur_tile >= 0) {
                     if (!d->tile[cur_tile].had_qcc[c])
@@ -762,7 +772,6 @@ static int parse_headers(Dec *d)
                 } else if (!d->had_qcc[c])
                     d->qnt[c] = tmp;
             }
-            seg = segend;
             break;
         }
         case 0xFF5D: {                                    /* QCC */
@@ -777,9 +786,9 @@ static int parse_headers(Dec *d)
                 d->tile[cur_tile].had_qcc[c] = 1;
             else
                 d->had_qcc[c] = 1;
-            if ((ret = parse_qcx(seg + 1, len - 3, cur_tile >= 0 ? &d->tile[cur_tile].qnt[c] : &d->qnt[c])) < 0)
+            if ((ret = parse_qcx(seg + 1, len - 3, d->end - (seg + 1), cur_tile >= 0 ? &d->tile[cur_tile].qnt[c] : &d->qnt[c])) < 0)
                 return ret;
-            seg = segend;
+            seg += 1 + ret;
             break;
         }
         case 0xFF5E: {                                    /* RGN (get_rgn, :641-672) */
@@ -912,11 +921,13 @@ static void band_stepsize(Band *b, const CodSty *c, const QntSty *q, int bandno,
     float f;
     if (q->style == 0) {
         f = 1;
-    } else {
+    } else if (q->style <= 2) {
         union { uint32_t u; float f; } e;
         e.u = (uint32_t)((cbps - q->expn[gbandno]) + 127) << 23;
         f = e.f;
         f *= q->mant[gbandno] / 2048.0 + 1.0;
+    } else {
+        f = 0;                                            /* "Unknown quantization format" (jpeg2000.c:246-249) */
     }
     if (c->transform != ORACLE_DWT53) {
         int lband = 0;
@@ -974,6 +985,8 @@ static int init_tile(Dec *d, int tileno)
         comp->cr.y1 = ceildivpow2(comp->c.y1, d->red);
         if (cs->nres - d->red <= 0)
             return ORACLE_ERR_EINVAL;
+        if (cs->transform > ORACLE_DWT97_INT)             /* ff_jpeg2000_dwt_init: "default: return -1" (jpeg2000dwt.c:590) */
+            return -1;
         const int cw = comp->cr.x1 - comp->cr.x0, ch = comp->cr.y1 - comp->cr.y0;
         if (cw > 32768 || ch > 32768)
             return ORACLE_ERR_PATCH;
@@ -1092,15 +1105,15 @@ static void select_part(Dec *d, PktState *ps, int csty)
     Tile *t = ps->t;
     d->bp = t->part[ps->tp].p;
     d->bend = t->part[ps->tp].end;
+    /* an exhausted or missing tile-part: on to the next slot, over gaps in the TPsot numbering as well, up to the
+     * last slot of the array (:1117-1126) */
     while (d->bp >= d->bend && d->bit_index == 8 && ps->tp < 31) {
         ps->tp++;
         d->bp = t->part[ps->tp].p;
         d->bend = t->part[ps->tp].end;
-        if (!d->bp) {
-            d->bp = d->bend = d->end;
-            break;
-        }
     }
+    if (!d->bp)
+        d->bp = d->bend = d->end;
     if (csty & 2)                                         /* SOP */
         if (d->bend - d->bp >= 6 && rd32(d->bp) == 0xFF910004u)
             d->bp += 6;
@@ -1147,11 +1160,11 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
         select_header(d, ps);
     else if (pt->has_ppt) {
         d->bp = pt->ppt + pt->ppt_pos;
-        d->bend = pt->ppt + pt->ppt_size;
+        d->bend = pt->ppt + pt->ppt_live;
     } else
         select_part(d, ps, cs->csty);
 
-    struct Inc { Cblk *cb; int nseg; int seg[8]; } *incs = NULL;
+    struct Inc { Cblk *cb; int nseg; int seg[100]; } *incs = NULL;
     int ninc = 0, capinc = 0;
     int ret = 0;
 
@@ -1298,7 +1311,7 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
                     newpasses -= segment_passes;
                     cb->Lref += segment_bytes;
                     cb->npasses = (cb->npasses + segment_passes) & 0xFF;
-                    if (in->nseg < 8)
+                    if (in->nseg < 100)
                         in->seg[in->nseg++] = segment_bytes;
                 }
             } else {
@@ -1306,7 +1319,7 @@ static int decode_packet(Dec *d, PktState *ps, const CodSty *cs, Res *rl, int pr
                     segment_bytes = hb_bits(d, cb->lblock);
                     newpasses -= 1;
                     cb->npasses = (cb->npasses + 1) & 0xFF;
-                    if (in->nseg < 8)
+                    if (in->nseg < 100)
                         in->seg[in->nseg++] = segment_bytes;
                 }
             }

@@ -1,0 +1,69 @@
+#!/usr/bin/env python3
+"""Generates tests/golden/frames_fuzz.npz with the REFERENCE (oracle/_ref/libj2kref.so built from /root/reference):
+the damaged streams on which tools/fuzz_host.py (reference vs oracle vs product, differentially) found the oracle or
+the product's parser deviating from the reference in round 2 -- each a generated stream plus a few damaged bytes --
+with the reference's verdict and a SHA-1 digest of its picture.  Same layout as frames_tiles.npz (key = name|flags).
+What each one pinned down:
+  segs     more than six / eight codeword segments in one contribution of a block (lengthinc[] is as long as the
+           pass count, jpeg2000dec.c:1227)
+  qcd_len  a QCD whose style reads fewer bytes than the segment declares: the bare -1 of the marker loop (:2629-2633)
+  qsty     an undefined quantisation style: parsed like style 2, step size 0 (jpeg2000.c:246-249)
+  dwt      a wavelet byte that is neither 0 nor 1: accepted by get_cox, refused with -1 when the tile is set up
+           (jpeg2000dwt.c:590)
+  ppt_sod  packed packet headers of a tile whose first tile-part never reaches its SOD: an empty header stream
+           (:2474-2476), every packet of the tile is empty
+  tp_gap   a gap in the TPsot numbering: select_stream walks over empty slots (:1117-1126)
+  lost     36 bytes lost in a tile-part header plus two damaged bytes
+Run where the reference is mounted:  python tests/golden/make_fuzz_golden.py"""
+import hashlib
+import importlib.util
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path[:0] = [str(ROOT), str(ROOT / "tools"), str(ROOT / "tests")]
+from helpers import ref_decode  # noqa: E402
+
+spec = importlib.util.spec_from_file_location("fuzz_host", ROOT / "tools" / "fuzz_host.py")
+fuzz_host = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(fuzz_host)
+
+# name: (family of tools/fuzz_host.py, index in it, operations in order: ("set", position, byte) / ("del", position, count))
+CASES = {
+    "segs": ("ht_sets", 2, [("set", 42009, 83)]),
+    "qcd_len": ("plain", 19, [("set", 73, 146), ("set", 93, 244)]),
+    "qsty": ("plain", 21, [("set", 73, 255), ("set", 107, 154), ("set", 116, 22)]),
+    "dwt": ("plain", 19, [("set", 68, 9), ("set", 127, 64)]),
+    "ppt_sod": ("packed", 4, [("set", 49370, 138)]),
+    "tp_gap": ("tile_styles", 7, [("set", 5050, 3), ("set", 6200, 255), ("set", 15763, 238)]),
+    "lost": ("tile_parts", 3, [("del", 472, 36), ("set", 3991, 68), ("set", 4614, 34)]),
+}
+
+
+def main():
+    families = {}
+    pack = {}
+    for name, (fam, idx, ops) in CASES.items():
+        if fam not in families:
+            families[fam] = fuzz_host.family(fam)
+        cs = bytearray(families[fam][idx])
+        for op, pos, v in ops:
+            if op == "set":
+                cs[pos] = v
+            else:
+                del cs[pos: pos + v]
+        cs = bytes(cs)
+        r, info, out, pix = ref_decode(cs, 0)
+        k = f"{name}|0"
+        pack[k + "|cs"] = np.frombuffer(cs, np.uint8)
+        pack[k + "|meta"] = np.array([info[0], info[1], r], np.int64)
+        pack[k + "|pix"] = np.frombuffer((pix or "none").encode(), np.uint8)
+        pack[k + "|out"] = np.frombuffer(hashlib.sha1(out.tobytes()).digest(), np.uint8) if r == 0 else np.zeros(0, np.uint8)
+        print(f"{name}: {len(cs)} bytes, reference {r}" + (f", {info[0]}x{info[1]} {pix}" if r == 0 else ""))
+    np.savez_compressed(ROOT / "tests" / "golden" / "frames_fuzz.npz", **pack)
+
+
+if __name__ == "__main__":
+    main()

@@ -57,10 +57,11 @@ def test_golden_frames_packed():
     assert n >= 25
 
 
-@pytest.mark.parametrize("name", ["frames_part1.npz", "frames_tiles.npz", "frames_htsets.npz"])
+@pytest.mark.parametrize("name", ["frames_part1.npz", "frames_tiles.npz", "frames_htsets.npz", "frames_fuzz.npz"])
 def test_golden_frames_part1_and_tiles(name):
     """Part-1 (EBCOT / MQ) streams from OpenJPEG, plain and damaged; several tile-parts per tile, tiles with their own
-    COD / QCD / POC, damaged tile-header markers: reference verdicts + pixels"""
+    COD / QCD / POC, damaged tile-header markers; the findings of the differential fuzzer (tests/golden/
+    make_fuzz_golden.py): reference verdicts + pixels"""
     import hashlib
     z = np.load(GOLDEN / name)
     n = 0
@@ -75,7 +76,7 @@ def test_golden_frames_part1_and_tiles(name):
             else:
                 assert np.array_equal(got, out), key
         n += 1
-    assert n >= 25
+    assert n >= (7 if name == "frames_fuzz.npz" else 25)
 
 
 def test_golden_kat_values():

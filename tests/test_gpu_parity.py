@@ -255,7 +255,8 @@ def test_golden_frames_wide():
     assert n >= 35
 
 
-@pytest.mark.parametrize("name", ["frames_packed.npz", "frames_part1.npz", "frames_tiles.npz", "frames_htsets.npz"])
+@pytest.mark.parametrize("name", ["frames_packed.npz", "frames_part1.npz", "frames_tiles.npz", "frames_htsets.npz",
+                                  "frames_fuzz.npz"])
 def test_golden_frames_packed_and_part1(name):
     """Reference-generated vectors: packed packet headers (PPT / PPM), damaged PPT / PPM markers, missing tiles;
     Part-1 (EBCOT / MQ) streams from OpenJPEG, plain and damaged."""
@@ -276,7 +277,7 @@ def test_golden_frames_packed_and_part1(name):
                 else:
                     assert np.array_equal(got, out), key
         n += 1
-    assert n >= 25
+    assert n >= (7 if name == "frames_fuzz.npz" else 25)
 
 
 @pytest.mark.parametrize("cfg", STREAMS, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items())[:60])

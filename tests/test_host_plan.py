@@ -545,3 +545,23 @@ def test_component_must_fit_its_output_plane():
             with pytest.raises(fb.DecodeError) as e:
                 fb.plan(bad, 0)
             assert e.value.code == fb.ERR_INVALIDDATA
+
+
+def test_plan_of_fuzz_findings_matches_reference():
+    """tests/golden/frames_fuzz.npz: the damaged streams on which the differential fuzzer (tools/fuzz_host.py) caught the
+    parser deviating from the reference -- verdict and picture of the REFERENCE, reproduced from the product's tables."""
+    import hashlib
+    z = np.load(ROOT / "tests" / "golden" / "frames_fuzz.npz")
+    n = 0
+    for key in sorted(k[:-3] for k in z.files if k.endswith("|cs")):
+        cs, meta, out = z[key + "|cs"].tobytes(), z[key + "|meta"], z[key + "|out"]
+        if meta[2] < 0:
+            with pytest.raises(fb.DecodeError) as e:
+                picture_from_plan(cs, 0)
+            assert e.value.code == meta[2], key                  # the bare -1 of the reference, too
+        else:
+            info, pic = picture_from_plan(cs, 0)
+            assert (info.width, info.height) == (meta[0], meta[1]), key
+            assert hashlib.sha1(pic.tobytes()).digest() == out.tobytes(), key
+        n += 1
+    assert n == 7
