@@ -949,6 +949,19 @@ int b200j2k_ht_blocks(int device, const uint8_t *data, int64_t data_size, const 
             ret = B200J2K_ERR_DEVICE;
         }
     }
+    if (ret == 0 && getenv("B200J2K_DUMP_SCRATCH")) {
+        /* kernel debugging: the intermediate per-block scratch (un-stuffed VLC / MEL bits, quad words) of this
+         * call, as [n][scr_off...][words...] 32-bit words */
+        std::vector<uint32_t> h(hp.scratch_words + 64);
+        cudaMemcpy(h.data(), d_scratch, hp.scratch_words * 4, cudaMemcpyDeviceToHost);
+        if (FILE *f = fopen(getenv("B200J2K_DUMP_SCRATCH"), "wb")) {
+            const uint32_t hdr[2] = { (uint32_t)n, (uint32_t)hp.scratch_words };
+            fwrite(hdr, 4, 2, f);
+            fwrite(hp.scr_off.data(), 4, (size_t)n, f);
+            fwrite(h.data(), 4, hp.scratch_words, f);
+            fclose(f);
+        }
+    }
     cudaFree(d_bytes_alloc); cudaFree(d_descs); cudaFree(d_order); cudaFree(d_scr); cudaFree(d_out); cudaFree(d_scratch);
     cudaFree(d_band); cudaFree(d_status);
     cudaStreamDestroy(st);

@@ -675,6 +675,10 @@ ht_unstuff_ref_kernel(const CblkDesc *__restrict__ descs, const uint32_t *__rest
         return;
     const uint32_t bi = order[gw];
     const CblkDesc d = descs[bi];
+    /* a block whose cleanup segment cannot be decoded gets zeros and no refinement; with Lcup < 2 it does not even
+     * own scratch (ht_cleanup_scratch_words): writing its streams would land in another block's words */
+    if (ht_block_scup(d, bytes + d.data_off) <= 0)
+        return;
     const RefLayout rl = ref_layout(d);
     const uint8_t *Dref = bytes + d.data_off + d.Lcup;
     const int Lref = d.Lref;

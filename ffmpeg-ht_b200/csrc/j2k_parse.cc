@@ -891,7 +891,7 @@ int Parser::build_geometry(int flags)
 {
     const Header &h = hdr;
     tiles_.clear(); res_.clear(); precs_.clear(); cblk_template_.clear();
-    bands.clear(); tcs.clear(); groups.clear();
+    bands.clear(); band_negative_Mb_.clear(); tcs.clear(); groups.clear();
     tag_total_ = 0;
     coef_elems = 0;
     ll_elems = 0;
@@ -999,8 +999,10 @@ int Parser::build_geometry(int flags)
                     bd.empty = bd.c.x0 == bd.c.x1 || bd.c.y0 == bd.c.y1;
                     const int l2cw = imin(cs.l2cw, bppx), l2ch = imin(cs.l2ch, bppy);
                     const int M_b = qs.expn[gband] + qs.nguard - 1;
-                    if (!bd.empty && (M_b >= 31 || M_b < 0))
+                    if (!bd.empty && M_b >= 31)
                         return B200J2K_ERR_PATCHWELCOME;   /* jpeg2000dec.c:2246-2249 */
+                    /* M_b < 0 (no QCD at all: zero exponents, zero guard bits): nothing in the reference minds until
+                     * a block of the band decodes -- and then it shifts by 32; refused once tier 2 finds such a block */
                     /* dequantisation constants: D1-D3 */
                     BandDesc bdesc;
                     memset(&bdesc, 0, sizeof(bdesc));
@@ -1018,6 +1020,7 @@ int Parser::build_geometry(int flags)
                     }
                     bd.band_index = (int)bands.size();
                     bands.push_back(bdesc);
+                    band_negative_Mb_.push_back(M_b < 0);
                     bd.prec_base = (uint32_t)precs_.size();
                     const int nprec = rl.npx * rl.npy;
                     /* Mallat placement of the band inside the plane (jpeg2000.c:365-376) */
@@ -1750,6 +1753,8 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
         d.npasses = s.npasses;
         d.zbp = s.zbp;
         d.length = s.length;
+        if (s.npasses && !(d.flags & J2K_CBLK_SKIP) && band_negative_Mb_[d.band])
+            return B200J2K_ERR_PATCHWELCOME;
         if ((d.flags & J2K_CBLK_MQ) || (s.incl && !(s.modes & 0x40))) {
             d.flags |= J2K_CBLK_MQ;                       /* also the Part-1 blocks of a MIXED set */
             d.Lref = d.pad;

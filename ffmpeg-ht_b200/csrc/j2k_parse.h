@@ -119,6 +119,7 @@ public:
     Header hdr;
     std::vector<CblkDesc> cblk;
     std::vector<BandDesc> bands;
+    std::vector<uint8_t> band_negative_Mb_;   /* per entry of bands: exponent + guard bits - 1 < 0 */
     std::vector<TileCompDesc> tcs;
     std::vector<PackGroup> groups;
     std::vector<uint8_t> extra;       /* gathered multi-contribution segments, addressed at pkt_size + offset */

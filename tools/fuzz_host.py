@@ -9,7 +9,9 @@ prints the cases that differ and writes them to gpurun_out/fuzz_<seed>_<n>.j2k.
 
   python tools/fuzz_host.py [--seconds 300] [--seed 1] [--families ht_sets,layered,...]"""
 import argparse
+import hashlib
 import random
+import subprocess
 import sys
 import time
 from pathlib import Path
@@ -55,6 +57,15 @@ def family(name):
     raise SystemExit("unknown family " + name)
 
 
+def fresh_reference_sha1(cs: bytes) -> str:
+    """SHA-1 of the reference's picture decoded in a process of its own ('' when it fails there)"""
+    code = ("import sys,hashlib; sys.path[:0]=[%r,%r]; from helpers import ref_decode; "
+            "r=ref_decode(sys.stdin.buffer.read()); print(hashlib.sha1(r[2].tobytes()).hexdigest() if r[0]==0 else '')"
+            % (str(ROOT / "tests"), str(ROOT)))
+    out = subprocess.run([sys.executable, "-c", code], input=cs, capture_output=True, timeout=120)
+    return out.stdout.decode().strip()
+
+
 def damage(rng, src):
     cs = bytearray(src)
     where = []
@@ -92,7 +103,7 @@ def main():
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
     t0 = time.time()
-    n = pictures = errors = bad = stricter = 0
+    n = pictures = errors = bad = stricter = unstable = 0
     PATCHWELCOME = -1163346256
     while time.time() - t0 < a.seconds:
         fam, idx, src = rng.choice(srcs)
@@ -116,6 +127,11 @@ def main():
             what.append(f"oracle {ro} / product {rp}")
         if use_ref:
             rr, _, rpic, _ = ref_decode(cs)
+            if rr == 0 and ro == 0 and not np.array_equal(rpic, opic) and fresh_reference_sha1(cs) != hashlib.sha1(rpic.tobytes()).hexdigest():
+                # damaged lengths make the reference read heap bytes behind a block's data: what it returns then
+                # depends on what this process decoded before (a fresh process is the yardstick)
+                unstable += 1
+                continue
             if (rr == 0) != (ro == 0) or (rr == 0 and not np.array_equal(rpic, opic)):
                 what.append(f"reference {rr} / oracle {ro}")
             if (rr == 0) != (rp == 0) or (rr == 0 and rp == 0 and not np.array_equal(rpic, ppic)):
@@ -130,7 +146,8 @@ def main():
         else:
             errors += 1
     print(f"{n} cases in {time.time() - t0:.0f} s: {pictures} pictures equal, {errors} rejected by all, "
-          f"{stricter} refused where the reference hands out an unfinished frame, {bad} differ")
+          f"{stricter} refused where the reference hands out an unfinished frame, {unstable} where the reference "
+          f"itself depends on heap contents, {bad} differ")
     return 1 if bad else 0
 
 
