@@ -638,7 +638,7 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             CodSty tmp;
             tmp.csty = seg[0];
             tmp.prog = seg[1];
-            tmp.nlayers = (int)rd16(seg + 2);
+            tmp.nlayers = (int)(rd16(seg + 2) & 0xFF);          /* the reference keeps it in a uint8_t (jpeg2000.h:152) */
             tmp.mct = seg[4];
             if (tmp.mct && h.ncomp < 3)
                 return B200J2K_ERR_INVALIDDATA;
@@ -1468,7 +1468,7 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
         CblkState &cb = state_[in.cb];
         for (uint32_t s = 0; s < in.nseg; s++) {
             uint32_t n = seglen[in.first + s];
-            if ((uint32_t)(bend_ - bp_) < n || cb.length + n > 65535)
+            if ((uint32_t)(bend_ - bp_) < n)
                 return B200J2K_ERR_INVALIDDATA;
             if (n) {
                 const uint32_t here = (uint32_t)(bp_ - pkt_);
@@ -1484,7 +1484,9 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                     extra.resize((extra.size() + 15) & ~(size_t)15);
                     cb.data_off = (uint32_t)(pkt_size_ + at);
                 }
-                cb.length += n;
+                /* cblk->length is a uint16_t (jpeg2000.h:188): past 65535 bytes the count wraps, the block is what
+                 * its first `length` bytes say and the next segment lands on top of the rest */
+                cb.length = (cb.length + n) & 0xFFFF;
                 bp_ += n;
             }
         }

@@ -719,7 +719,7 @@ static int parse_headers(Dec *d)
             memset(&tmp, 0, sizeof(tmp));
             tmp.csty = seg[0];
             tmp.prog = seg[1];
-            tmp.nlayers = rd16(seg + 2);
+            tmp.nlayers = rd16(seg + 2) & 0xFF;           /* uint8_t nlayers (jpeg2000.h:152): 256 layers are none */
             tmp.mct = seg[4];
             if (tmp.mct && d->ncomp < 3)
                 return ORACLE_ERR_INVALID;
@@ -1342,7 +1342,7 @@ finish:
         Cblk *cb = incs[i].cb;
         for (int s = 0; s < incs[i].nseg; s++) {
             int n = incs[i].seg[s];
-            if (d->bend - d->bp < n || cb->length + n > 65535) {
+            if (d->bend - d->bp < n) {
                 ret = ORACLE_ERR_INVALID;
                 goto fail;
             }
@@ -1352,7 +1352,8 @@ finish:
             }
             memcpy(cb->data + cb->length, d->bp, (size_t)n);
             d->bp += n;
-            cb->length += n;
+            cb->length = (cb->length + n) & 0xFFFF;       /* uint16_t length (jpeg2000.h:188): the bytes are all there,
+                                                           * the count wraps, the next segment lands on top of them */
         }
     }
     ps->t->part[ps->tp].p = d->bp;

@@ -14,6 +14,7 @@ What each one pinned down:
            (:2474-2476), every packet of the tile is empty
   tp_gap   a gap in the TPsot numbering: select_stream walks over empty slots (:1117-1126)
   lost     36 bytes lost in a tile-part header plus two damaged bytes
+  layers   a layer count of 0xFF01: the reference keeps SGcod's 16-bit field in a uint8_t (jpeg2000.h:152) -- one layer
   noqcd    no QCD at all (exponents and guard bits zero: M_b = -1) and no SOD: nothing decodes, the picture is the
            DC level -- not an error
 Run where the reference is mounted:  python tests/golden/make_fuzz_golden.py"""
@@ -42,6 +43,7 @@ CASES = {
     "tp_gap": ("tile_styles", 7, [("set", 5050, 3), ("set", 6200, 255), ("set", 15763, 238)]),
     "lost": ("tile_parts", 3, [("del", 472, 36), ("set", 3991, 68), ("set", 4614, 34)]),
     "noqcd": ("plain", 18, [("set", 69, 53), ("set", 88, 131)]),
+    "layers": ("part1", 13, [("set", 136, 255), ("set", 595, 11)]),
 }
 
 

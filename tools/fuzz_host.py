@@ -54,6 +54,14 @@ def family(name):
         return [bytes(T.poc_stream(t)[0]) for t in T.POC_STREAMS]
     if name == "tile_styles":
         return [bytes(T.tile_style_stream(t)[0]) for t in T.TILE_STYLES]
+    if name == "part1":                         # EBCOT / MQ streams from OpenJPEG (Pillow), raw and in a JP2 file
+        return [bytes(T.part1_stream(t, jp2)) for t in T.PART1[:12] for jp2 in (False, True)]
+    if name == "subsampled":
+        out = []
+        for i, (_, subs, bd) in enumerate(T.SUBSAMPLED):
+            w, h, kw = T.SUBSAMPLED_GEOMS[i % len(T.SUBSAMPLED_GEOMS)]
+            out.append(bytes(T.subsampled_stream(subs, bd, w, h, kw)[0]))
+        return out
     raise SystemExit("unknown family " + name)
 
 
