@@ -478,9 +478,9 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
     if (size >= 12 && rd32(p) == 12 && rd32(p + 4) == 0x6A502020u && rd32(p + 8) == 0x0D0A870Au) {
         /* JP2 / JPH file (jpeg2000dec.c:2842-2854) */
         Cursor g = { pkt, 12, size };
+        /* "if (!jp2_find_codestream(s))" (:2846): the error code an absurd box size produces is not zero, so the
+         * reference carries on and looks for SOC behind the box header it has read (the cursor stands there) */
         const int r = jp2_find_codestream(g, h);
-        if (r < 0)
-            return r;
         if (!r)
             return B200J2K_ERR_INVALIDDATA;               /* "Could not find Jpeg2000 codestream atom." */
         p = pkt + g.pos;

@@ -470,12 +470,16 @@ static int jp2_find_codestream(Dec *d, int64_t *ppos)
             if (jp2_be(d, &pos, 4))
                 return 0;
             atom_size = jp2_be(d, &pos, 4);
-            if (atom_size < 16 || pos + atom_size - 16 > INT32_MAX)
+            if (atom_size < 16 || pos + atom_size - 16 > INT32_MAX) {
+                *ppos = pos;
                 return ORACLE_ERR_INVALID;
+            }
             atom_end = (uint32_t)(pos + atom_size - 16);
         } else {
-            if (atom_size < 8 || pos + atom_size - 8 > INT32_MAX)
+            if (atom_size < 8 || pos + atom_size - 8 > INT32_MAX) {
+                *ppos = pos;
                 return ORACLE_ERR_INVALID;
+            }
             atom_end = (uint32_t)(pos + atom_size - 8);
         }
         if (atom == 0x6A703263u) {                  /* jp2c */
@@ -569,9 +573,9 @@ static int parse_headers(Dec *d)
         d->cdef[i] = -1;                            /* jpeg2000dec.c:2834 */
     if (d->end - p >= 12 && rd32(p) == 12 && rd32(p + 4) == 0x6A502020u && rd32(p + 8) == 0x0D0A870Au) {
         int64_t pos = 12;                           /* JP2 / JPH file (:2842-2854) */
+        /* "if (!jp2_find_codestream(s))" (:2846): an absurd box size makes it return an error code, which is not
+         * zero -- the search for SOC simply goes on behind the box header that was read */
         const int r = jp2_find_codestream(d, &pos);
-        if (r < 0)
-            return r;
         if (!r)
             return ORACLE_ERR_INVALID;
         p = d->cs + pos;

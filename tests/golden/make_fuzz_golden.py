@@ -15,6 +15,8 @@ What each one pinned down:
   tp_gap   a gap in the TPsot numbering: select_stream walks over empty slots (:1117-1126)
   lost     36 bytes lost in a tile-part header plus two damaged bytes
   layers   a layer count of 0xFF01: the reference keeps SGcod's 16-bit field in a uint8_t (jpeg2000.h:152) -- one layer
+  jp2size  a JP2 box of absurd size: jp2_find_codestream returns an error code, which its caller takes for "found"
+           (:2846) -- the codestream is then found by the scan for SOC
   noqcd    no QCD at all (exponents and guard bits zero: M_b = -1) and no SOD: nothing decodes, the picture is the
            DC level -- not an error
 Run where the reference is mounted:  python tests/golden/make_fuzz_golden.py"""
@@ -44,6 +46,7 @@ CASES = {
     "lost": ("tile_parts", 3, [("del", 472, 36), ("set", 3991, 68), ("set", 4614, 34)]),
     "noqcd": ("plain", 18, [("set", 69, 53), ("set", 88, 131)]),
     "layers": ("part1", 13, [("set", 136, 255), ("set", 595, 11)]),
+    "jp2size": ("part1", 13, [("set", 32, 255)]),
 }
 
 
