@@ -839,8 +839,7 @@ namespace {
 template <class K> void launch_item(cudaStream_t stream, K kernel, int smem, const IdwtStreamCache::Item &it, bool first = false)
 {
     static const int pdl = getenv("B200J2K_IDWT_PDL") ? atoi(getenv("B200J2K_IDWT_PDL")) : 1;   /* tuning: 0 plain launches */
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = it.grid;
     cfg.blockDim = dim3(SWARPS * 32);
     cfg.dynamicSmemBytes = (size_t)smem;
@@ -913,8 +912,7 @@ int stream_level(cudaStream_t stream, const IdwtFrame &f, int j, int max_w, int 
         for (int i = 0; i < f.ntcs; i++)
             ndom += f.h_tcs[i].transform == T && j < f.h_tcs[i].nlevels - 1;
         const int seg = pick_seg(strips * ndom, max_h, cap), segs = (max_h + 1 + seg - 1) / seg;
-        IdwtStreamCache::Item it;
-        memset(&it, 0, sizeof(it));
+        IdwtStreamCache::Item it = {};
         int nd = 0;
         for (int i = 0; i < f.ntcs; i++) {
             const TileCompDesc *tc = &f.h_tcs[i];
@@ -948,8 +946,7 @@ int stream_final(cudaStream_t stream, const IdwtFrame &f, int max_w, int max_h)
         for (int i = 0; i < f.ngroups; i++)
             ndom += f.h_tcs[f.h_groups[i].tc[0]].transform == T;
         const int seg = pick_seg(strips * ndom, max_h, cap), segs = (max_h + 1 + seg - 1) / seg;
-        IdwtStreamCache::Item it;
-        memset(&it, 0, sizeof(it));
+        IdwtStreamCache::Item it = {};
         int nd = 0;
         for (int i = 0; i < f.ngroups; i++) {
             const PackGroup &g = f.h_groups[i];
