@@ -505,20 +505,33 @@ def run_ours(args):
     failed = [0] * T
     last = {}                                   # (thread, buffer) -> index of the frame decoded into it last
 
+    # N > 1: end to end a GPU is as fast as its PCIe path, and those differ by up to half on an 8-GPU host (the probe below
+    # measures it): with equal shares every rank waits for the slowest one.  So the timed end-to-end legs draw runs of
+    # frames from ONE counter shared by all ranks (ffmpeg_ht_b200.sharding.FrameQueue, a torch.distributed store key;
+    # no collective) -- the same total, B * K * world frames; --e2e-sharding static restores equal shares.
+    from ffmpeg_ht_b200 import sharding as _sharding
+    dynamic = world > 1 and args.e2e_sharding == "dynamic"
+    store = _sharding.default_store() if dynamic else None
+    queue_box = [None]
+    legs_run = [0]
+    frames_done = [0] * T
+
     def e2e_worker(t, nsteps, outs):
         torch.cuda.set_device(local)
         d, pf = decs[t], outs[t]
         pending = []
-        for _ in range(nsteps):
-            for n, i in enumerate(per_thread[t]):
-                if len(pending) == len(pf):
-                    s0 = pending.pop(0)
-                    d.wait(s0)
-                    failed[t] += d.blocks_failed(s0)
-                slot = d.submit(pkts[i % D], pf[n % len(pf)])
-                last[(t, n % len(pf))] = i % D
-                pending.append(slot)
-                h2d_seen[t] = d.h2d_bytes(slot)
+        fq = queue_box[0]
+        seq = fq if fq is not None else (i for _ in range(nsteps) for i in per_thread[t])
+        for n, i in enumerate(seq):
+            if len(pending) == len(pf):
+                s0 = pending.pop(0)
+                d.wait(s0)
+                failed[t] += d.blocks_failed(s0)
+            slot = d.submit(pkts[i % D], pf[n % len(pf)])
+            last[(t, n % len(pf))] = i % D
+            pending.append(slot)
+            h2d_seen[t] = d.h2d_bytes(slot)
+            frames_done[t] += 1
         for s in pending:
             d.wait(s)
             failed[t] += d.blocks_failed(s)
@@ -538,15 +551,24 @@ def run_ours(args):
         last.clear()
         e2e_run(warm, outs)
         torch.cuda.synchronize()
+        legs_run[0] += 1
+        if dynamic:
+            queue_box[0] = _sharding.FrameQueue(store, "e2e_leg%d" % legs_run[0], B * K * world, args.e2e_chunk)
+        for t in range(T):
+            frames_done[t] = 0
         barrier()
         t0 = time.perf_counter()
         e2e_run(K, outs)
         torch.cuda.synchronize()
         sec = time.perf_counter() - t0
         barrier()
+        queue_box[0] = None
         return max_over_ranks(sec), verify(outs, fetch)
 
     e2e_s, ok = timed_leg(pins, lambda f: f.buffer, max(1, min(Wm, 3)))
+    e2e_frames_this_rank = sum(frames_done)
+    e2e_frames_min, e2e_frames_max = reduce(e2e_frames_this_rank, "min"), reduce(e2e_frames_this_rank, "max")
+    assert reduce(e2e_frames_this_rank, "sum") == B * K * world
     chk_idx = last.get((0, 0), 0)                 # the frame whose picture sits in thread 0's first buffer
     clocks = sampler.stop()                       # sampled across both timed regions (kernel-only and end to end)
     # row N2 (zero-copy output): the same calls with the output planes in DEVICE memory, as AV_PIX_FMT_CUDA
@@ -661,7 +683,13 @@ def run_ours(args):
                        "pcie_bare_copies_all_ranks_at_once": pcie,
                        "e2e_device_frames_fps": frames_total / e2e_dev_s,
                        "tiles_of_one_frame_over_the_gpus": tile_leg,
-                       "e2e_d2h_gbs_all_ranks": d2h_step * K * world / e2e_s / 1e9},
+                       "e2e_d2h_gbs_all_ranks": d2h_step * K * world / e2e_s / 1e9,
+                       "e2e_sharding": ("frames drawn in runs of %d from one counter shared by all ranks "
+                                        "(sharding.FrameQueue; same total, no collective): a rank decodes as many as "
+                                        "its PCIe path lets it" % args.e2e_chunk) if dynamic
+                       else "equal shares per rank" if world > 1 else "one rank",
+                       "e2e_frames_per_rank": {"this_rank": e2e_frames_this_rank, "min_rank": int(e2e_frames_min),
+                                               "max_rank": int(e2e_frames_max), "equal_share": B * K}},
             "e2e": {"value": e2e, "unit": "Mpixel/s", "fps": frames_total / e2e_s,
                     "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step), "output_check": ok,
                     "d2h_gbs_achieved": d2h_step * K / e2e_s / 1e9, "h2d_gbs_achieved": h2d_step * K / e2e_s / 1e9,
@@ -765,6 +793,9 @@ def main():
     ap.add_argument("--slots", type=int, default=16, help="frames in flight in the kernel-only leg")
     ap.add_argument("--host-threads", type=int, default=4, help="decoder contexts (host threads) in the e2e leg")
     ap.add_argument("--slots-e2e", type=int, default=2)
+    ap.add_argument("--e2e-sharding", choices=("dynamic", "static"), default="dynamic",
+                    help="N > 1, end-to-end legs: frames drawn from one shared counter (default) or equal shares per rank")
+    ap.add_argument("--e2e-chunk", type=int, default=4, help="frames per draw from the shared counter")
     ap.add_argument("--scale", type=int, default=1, help="shrink the frame by this factor (debugging only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE workloads (8K, 9/7) at N=1")

@@ -5,7 +5,10 @@ independent frame-thread contexts (libavcodec/pthread_frame.c:248-295) and indep
 (jpeg2000_decode_tile, libavcodec/jpeg2000dec.c:2368-2395, :2894).  Here they are sharded round-robin over GPUs with
 NO data-path collective:
 
-  frames   rank r of N decodes frames r, r + N, ...            (shard_indices; bench.py's main legs)
+  frames   rank r of N decodes frames r, r + N, ...            (shard_indices; bench.py's kernel-only leg), or
+           the ranks draw runs of frames from one counter        (FrameQueue; bench.py's end-to-end legs at N > 1:
+           end to end a GPU is as fast as its PCIe path, and on an 8-GPU host those differ by half -- equal shares
+           wait for the slowest one)
   tiles    context r of N decodes tiles r, r + N, ... of EVERY frame: a decoder context created with
            B200J2K_FLAG_TILES(r, N) parses only its tiles' packets, uploads only their tile-parts, reconstructs
            only them and writes only their rectangles of the output planes (tile_flags; TileShardedDecoder drives
@@ -61,6 +64,45 @@ class TileShardedDecoder:
 
     def __exit__(self, *exc):
         self.close()
+
+
+class FrameQueue:
+    """Frames of a sequence handed out in runs of `chunk` from one counter shared by all ranks: whoever is free takes
+    the next run, so a GPU behind a faster PCIe path decodes more frames than one behind a contended switch.  The
+    counter lives in a torch.distributed store (TCPStore / FileStore / HashStore: `add` is atomic there); no
+    collective, nothing on the data path.  One queue per pass over the sequence: `name` must be new each time."""
+
+    def __init__(self, store, name: str, total: int, chunk: int = 4):
+        if total < 0 or chunk < 1:
+            raise ValueError("bad total/chunk")
+        self.store, self.key, self.total, self.chunk = store, "framequeue/" + name, int(total), int(chunk)
+
+    def take(self):
+        """-> range of frame indices to decode next, or None when the sequence is handed out."""
+        if self.store is None:                         # single process: a local counter does
+            start = getattr(self, "_next", 0)
+            self._next = start + self.chunk
+        else:
+            start = int(self.store.add(self.key, self.chunk)) - self.chunk
+        if start >= self.total:
+            return None
+        return range(start, min(start + self.chunk, self.total))
+
+    def __iter__(self):
+        while True:
+            r = self.take()
+            if r is None:
+                return
+            yield from r
+
+
+def default_store():
+    """The store torch.distributed was initialised with (None without a process group)."""
+    import torch.distributed as dist
+    if not dist.is_available() or not dist.is_initialized():
+        return None
+    from torch.distributed import distributed_c10d
+    return distributed_c10d._get_default_store()
 
 
 def reduce_stats(elapsed_s: float, units_done: int, dist=None, device=None):

@@ -132,3 +132,57 @@ def test_shard_indices_properties():
                 assert u in sharding.shard_indices(n, sharding.owner(u, world), world)
     with pytest.raises(ValueError):
         sharding.shard_indices(4, 2, 2)
+
+
+def _queue_worker(rank, world, port, nframes, q):
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    import threading
+    import time
+    import torch.distributed as dist
+    from ffmpeg_ht_b200 import sharding
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fq = sharding.FrameQueue(sharding.default_store(), "pass0", nframes, chunk=3)
+    mine, lock = [], threading.Lock()
+
+    def work():                                   # two host threads per rank draw from the same queue
+        for i in fq:
+            time.sleep(0.002 * (1 + 3 * rank))    # rank 1 is four times slower: it must end up with fewer frames
+            with lock:
+                mine.append(i)
+
+    dist.barrier()
+    th = [threading.Thread(target=work) for _ in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert fq.take() is None
+    q.put((rank, sorted(mine)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_draw_frames_from_one_queue():
+    """FrameQueue: every frame exactly once over all ranks and threads, and the faster rank takes more."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    nframes, world = 200, 2
+    procs = [ctx.Process(target=_queue_worker, args=(r, world, port, nframes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(res[0] + res[1]) == list(range(nframes))
+    assert len(res[0]) > 1.5 * len(res[1])
+
+
+def test_frame_queue_single_process():
+    from ffmpeg_ht_b200 import sharding
+    fq = sharding.FrameQueue(None, "x", 10, chunk=4)
+    assert [list(fq.take()), list(fq.take()), list(fq.take()), fq.take()] == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9], None]
