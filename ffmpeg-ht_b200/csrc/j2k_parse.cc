@@ -923,11 +923,9 @@ int Parser::build_geometry(int flags)
                 return B200J2K_ERR_INVALIDDATA;
             if (h.isHT && h.cap_b14 != (cs.cblk_style >> 6) && h.cap_b14 != 0)
                 return B200J2K_ERR_INVALIDDATA;
-            if (!(cs.cblk_style & 0xC0) && (cs.cblk_style & 0x05))
-                return B200J2K_ERR_PATCHWELCOME;          /* Part-1 blocks with arithmetic-coding bypass or termination
-                                                           * on each pass (several codeword segments per block) are not
-                                                           * served; for the Part-1 blocks of a MIXED stream tier 2
-                                                           * checks that */
+            /* Part-1 blocks with arithmetic-coding bypass or termination on each pass (several codeword segments per
+             * block) are not served: refused in tier 2, when the first such block contributes to a packet -- a stream
+             * that only announces the style decodes like in the reference */
             /* cc = comp->coord_o: every resolution, band, precinct and code-block is laid out from it;
              * cr = comp->coord = cc reduced by lowres: the plane, the DWT and the output use it
              * (jpeg2000dec.c:1047-1050, jpeg2000.c:483-530) */
@@ -1435,6 +1433,8 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
                         }
                     }
                 } else if (!(cb.modes & 0x40)) {
+                    if (cs.cblk_style & 0x05)                           /* bypass / termination on each pass: not served */
+                        return B200J2K_ERR_PATCHWELCOME;
                     take(left, (unsigned)bits(field(left)));            /* :1364-1368 */
                 }
                 /* HT block past its placeholders (possibly since two lines ago): cut by sets */

@@ -17,6 +17,8 @@ What each one pinned down:
   layers   a layer count of 0xFF01: the reference keeps SGcod's 16-bit field in a uint8_t (jpeg2000.h:152) -- one layer
   jp2size  a JP2 box of absurd size: jp2_find_codestream returns an error code, which its caller takes for "found"
            (:2846) -- the codestream is then found by the scan for SOC
+  bypass0  a Part-1 style with arithmetic-coding bypass announced, but no block ever contributes (no SOD): the style is
+           only refused (PATCHWELCOME, not served) when a block of it is met in a packet
   noqcd    no QCD at all (exponents and guard bits zero: M_b = -1) and no SOD: nothing decodes, the picture is the
            DC level -- not an error
 Run where the reference is mounted:  python tests/golden/make_fuzz_golden.py"""
@@ -47,6 +49,7 @@ CASES = {
     "noqcd": ("plain", 18, [("set", 69, 53), ("set", 88, 131)]),
     "layers": ("part1", 13, [("set", 136, 255), ("set", 595, 11)]),
     "jp2size": ("part1", 13, [("set", 32, 255)]),
+    "bypass0": ("plain", 18, [("set", 67, 19), ("set", 87, 247), ("set", 95, 255)]),
 }
 
 
