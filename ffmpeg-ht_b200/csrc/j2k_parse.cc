@@ -822,7 +822,26 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             ppt_[cur_tile].insert(ppt_[cur_tile].end(), seg + 1, segend);
             seg = segend;
             break;
-        default:
+        case 0xFF55: {                                    /* TLM: only walked over (get_tlm, jpeg2000dec.c:901-934) */
+            const unsigned stlm = end - seg > 1 ? seg[1] : 0;
+            const int st = (stlm >> 4) & 3, sp = (stlm >> 6) & 1;
+            if (st == 3)
+                return B200J2K_ERR_INVALIDDATA;
+            const int entry = (sp + 1) * 2 + st;
+            seg += 2 + (int)(uint8_t)((len - 4) / entry) * entry;   /* the entry count lives in a uint8_t */
+            break;
+        }
+        case 0xFF58:                                      /* PLT (get_plt, :936-955): its last byte ends a length */
+            if (len < 4 || (segend[-1] & 0x80))
+                return B200J2K_ERR_INVALIDDATA;
+            seg = segend;
+            break;
+        case 0xFF63:                                      /* CRG (read_crg, :875-883) */
+            if (h.ncomp * 4 != len - 2)
+                return B200J2K_ERR_INVALIDDATA;
+            seg = segend;
+            break;
+        default:                                          /* COM, PLM, CPF, unknown markers: skipped */
             seg = segend;
             break;
         }

@@ -906,7 +906,26 @@ static int parse_headers(Dec *d)
             seg = segend;
             break;
         }
-        default:                                          /* COM, TLM, PLT, PLM, CRG, CPF, unknown: skipped */
+        case 0xFF55: {                                    /* TLM: only walked over (get_tlm, :901-934) */
+            const unsigned stlm = d->end - seg > 1 ? seg[1] : 0;
+            const int st = (stlm >> 4) & 3, sp = (stlm >> 6) & 1;
+            if (st == 3)
+                return ORACLE_ERR_INVALID;
+            const int entry = (sp + 1) * 2 + st;
+            seg += 2 + (int)(uint8_t)((len - 4) / entry) * entry;   /* the entry count lives in a uint8_t */
+            break;
+        }
+        case 0xFF58:                                      /* PLT (get_plt, :936-955): the last byte ends a length */
+            if (len < 4 || (segend[-1] & 0x80))
+                return ORACLE_ERR_INVALID;
+            seg = segend;
+            break;
+        case 0xFF63:                                      /* CRG (read_crg, :875-883) */
+            if (d->ncomp * 4 != len - 2)
+                return ORACLE_ERR_INVALID;
+            seg = segend;
+            break;
+        default:                                          /* COM, PLM, CPF, unknown: skipped */
             seg = segend;
             break;
         }

@@ -19,6 +19,7 @@ What each one pinned down:
            (:2846) -- the codestream is then found by the scan for SOC
   bypass0  a Part-1 style with arithmetic-coding bypass announced, but no block ever contributes (no SOD): the style is
            only refused (PATCHWELCOME, not served) when a block of it is met in a packet
+  plt      a PPT marker turned into a PLT whose last byte has the continuation bit set: get_plt refuses it (:951)
   noqcd    no QCD at all (exponents and guard bits zero: M_b = -1) and no SOD: nothing decodes, the picture is the
            DC level -- not an error
 Run where the reference is mounted:  python tests/golden/make_fuzz_golden.py"""
@@ -49,8 +50,32 @@ CASES = {
     "noqcd": ("plain", 18, [("set", 69, 53), ("set", 88, 131)]),
     "layers": ("part1", 13, [("set", 136, 255), ("set", 595, 11)]),
     "jp2size": ("part1", 13, [("set", 32, 255)]),
+    "plt": ("packed", 4, [("set", 37122, 0x58)]),
     "bypass0": ("plain", 18, [("set", 67, 19), ("set", 87, 247), ("set", 95, 255)]),
 }
+
+
+def marker(code, payload):
+    return bytes([0xFF, code]) + (len(payload) + 2).to_bytes(2, "big") + bytes(payload)
+
+
+# TLM / PLT / CRG segments spliced in front of the first SOT of a three-component stream: the reference only walks over
+# them, but checks what it walks over (get_tlm :901-934 with its uint8_t entry count, get_plt :936-955, read_crg :875-883)
+SPLICED = {
+    "tlm_ok": marker(0x55, [0, 0x40] + [0] * 4 * 3),             # Stlm: ST 0, SP 1 -> 4-byte entries
+    "tlm_st3": marker(0x55, [0, 0x30] + [0] * 6),                # ST = 3
+    "tlm_odd": marker(0x55, [0, 0x10] + [0] * 7),                # 3-byte entries, 7 bytes: consumption != length -> -1
+    "tlm_300": marker(0x55, [0, 0x00] + [0] * 2 * 300),          # 300 entries: the count wraps to 44 -> -1
+    "plt_ok": marker(0x58, [0, 0x81, 0x02, 0x7F]),
+    "plt_open": marker(0x58, [0, 0x05, 0x81]),                   # last length not terminated
+    "plt_short": marker(0x58, [0]),                              # n < 4
+    "crg_ok": marker(0x63, [0] * 12),
+    "crg_bad": marker(0x63, [0] * 8),
+    "cpf": marker(0x59, [0, 1]),
+    "plm": marker(0x57, [0, 2, 1, 1]),
+}
+for _name, _seg in SPLICED.items():
+    CASES[_name] = ("plain", 20, [("ins_before_sot", 0, _seg)])
 
 
 def main():
@@ -63,6 +88,9 @@ def main():
         for op, pos, v in ops:
             if op == "set":
                 cs[pos] = v
+            elif op == "ins_before_sot":
+                at = bytes(cs).index(b"\xff\x90")
+                cs[at:at] = v
             else:
                 del cs[pos: pos + v]
         cs = bytes(cs)

@@ -65,11 +65,11 @@ def family(name):
     raise SystemExit("unknown family " + name)
 
 
-def fresh_reference_sha1(cs: bytes) -> str:
+def fresh_reference_sha1(cs: bytes, mode: int = 0) -> str:
     """SHA-1 of the reference's picture decoded in a process of its own ('' when it fails there)"""
     code = ("import sys,hashlib; sys.path[:0]=[%r,%r]; from helpers import ref_decode; "
-            "r=ref_decode(sys.stdin.buffer.read()); print(hashlib.sha1(r[2].tobytes()).hexdigest() if r[0]==0 else '')"
-            % (str(ROOT / "tests"), str(ROOT)))
+            "r=ref_decode(sys.stdin.buffer.read(), %d); print(hashlib.sha1(r[2].tobytes()).hexdigest() if r[0]==0 else '')"
+            % (str(ROOT / "tests"), str(ROOT), mode))
     out = subprocess.run([sys.executable, "-c", code], input=cs, capture_output=True, timeout=120)
     return out.stdout.decode().strip()
 
@@ -117,9 +117,13 @@ def main():
         fam, idx, src = rng.choice(srcs)
         cs, where = damage(rng, src)
         n += 1
-        ro, _, opic = oracle_decode(cs)
+        # now and then with AV_CODEC_FLAG_BITEXACT (fixed-point 9/7) and / or AVCodecContext.lowres = 1, 2
+        bitexact = int(rng.random() < 0.2)
+        lowres = rng.choice((0, 0, 0, 0, 1, 2))
+        mode = bitexact | (lowres << 8)
+        ro, _, opic = oracle_decode(cs, mode)
         try:
-            _, ppic = picture_from_plan(cs, 0)
+            _, ppic = picture_from_plan(cs, (fb.FLAG_BITEXACT if bitexact else 0) | fb.flag_lowres(lowres))
             rp = 0
         except fb.DecodeError as e:
             rp, ppic = e.code, None
@@ -128,14 +132,14 @@ def main():
             # the documented class (quirks): Part-1 blocks with bypass / termination on each pass, and
             # errors inside a tile job (M_b >= 31 ...) -- the reference drops the job's return value and hands out a
             # frame whose tile was never written; oracle and product refuse the frame
-            if ref_decode(cs)[0] == 0:
+            if ref_decode(cs, mode)[0] == 0:
                 stricter += 1
                 continue
         if (ro == 0) != (rp == 0) or (ro == 0 and not np.array_equal(opic, ppic)):
             what.append(f"oracle {ro} / product {rp}")
         if use_ref:
-            rr, _, rpic, _ = ref_decode(cs)
-            if rr == 0 and ro == 0 and not np.array_equal(rpic, opic) and fresh_reference_sha1(cs) != hashlib.sha1(rpic.tobytes()).hexdigest():
+            rr, _, rpic, _ = ref_decode(cs, mode)
+            if rr == 0 and ro == 0 and not np.array_equal(rpic, opic) and fresh_reference_sha1(cs, mode) != hashlib.sha1(rpic.tobytes()).hexdigest():
                 # damaged lengths make the reference read heap bytes behind a block's data: what it returns then
                 # depends on what this process decoded before (a fresh process is the yardstick)
                 unstable += 1
@@ -148,7 +152,7 @@ def main():
             bad += 1
             name = out / f"fuzz_{a.seed}_{n}.j2k"
             name.write_bytes(cs)
-            print(f"DIFFER case {n} ({fam}[{idx}], damage at {where}): {'; '.join(what)} -> {name.name}", flush=True)
+            print(f"DIFFER case {n} ({fam}[{idx}], bitexact {bitexact} lowres {lowres}, damage at {where}): {'; '.join(what)} -> {name.name}", flush=True)
         elif ro == 0:
             pictures += 1
         else:
