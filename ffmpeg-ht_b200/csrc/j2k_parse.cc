@@ -546,7 +546,10 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
             h.W = (int)rd32(seg + 2); h.H = (int)rd32(seg + 6); h.X0 = (int)rd32(seg + 10); h.Y0 = (int)rd32(seg + 14);
             h.TW = (int)rd32(seg + 18); h.TH = (int)rd32(seg + 22); h.TX0 = (int)rd32(seg + 26); h.TY0 = (int)rd32(seg + 30);
             int nc = (int)rd16(seg + 34);
-            if (h.W <= 0 || h.H <= 0 || (int64_t)h.W * h.H > INT32_MAX)
+            /* av_image_check_size2() without a pixel format (imgutils.c:289-316): rows of 8 bytes per pixel plus
+             * padding, 128 rows of padding, all below INT_MAX; then max_pixels = INT_MAX */
+            if (h.W <= 0 || h.H <= 0 || 8LL * h.W + 1024 >= INT32_MAX ||
+                (uint64_t)(8LL * h.W + 1024) * ((uint64_t)h.H + 128) >= (uint64_t)INT32_MAX || (int64_t)h.W * h.H > INT32_MAX)
                 return B200J2K_ERR_PATCHWELCOME;
             if (nc <= 0)
                 return B200J2K_ERR_INVALIDDATA;

@@ -640,7 +640,9 @@ static int parse_headers(Dec *d)
             d->W = rd32(seg + 2); d->H = rd32(seg + 6); d->X0 = rd32(seg + 10); d->Y0 = rd32(seg + 14);
             d->TW = rd32(seg + 18); d->TH = rd32(seg + 22); d->TX0 = rd32(seg + 26); d->TY0 = rd32(seg + 30);
             int nc = rd16(seg + 34);
-            if (d->W <= 0 || d->H <= 0 || (int64_t)d->W * d->H > INT32_MAX)
+            /* av_image_check_size2(w, h, max_pixels = INT_MAX, AV_PIX_FMT_NONE) (imgutils.c:289-316) */
+            if (d->W <= 0 || d->H <= 0 || 8LL * d->W + 1024 >= INT32_MAX ||
+                (uint64_t)(8LL * d->W + 1024) * ((uint64_t)d->H + 128) >= (uint64_t)INT32_MAX || (int64_t)d->W * d->H > INT32_MAX)
                 return ORACLE_ERR_PATCH;
             if (nc <= 0)
                 return ORACLE_ERR_INVALID;
