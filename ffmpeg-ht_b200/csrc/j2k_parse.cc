@@ -1019,7 +1019,7 @@ int Parser::build_geometry(int flags)
                     bd.empty = bd.c.x0 == bd.c.x1 || bd.c.y0 == bd.c.y1;
                     const int l2cw = imin(cs.l2cw, bppx), l2ch = imin(cs.l2ch, bppy);
                     const int M_b = qs.expn[gband] + qs.nguard - 1;
-                    if (!bd.empty && M_b >= 31)
+                    if (!bd.empty && M_b >= 31 && r < nres2decode)   /* tile_codeblocks only walks the levels it decodes */
                         return B200J2K_ERR_PATCHWELCOME;   /* jpeg2000dec.c:2246-2249 */
                     /* M_b < 0 (no QCD at all: zero exponents, zero guard bits): nothing in the reference minds until
                      * a block of the band decodes -- and then it shifts by 32; refused once tier 2 finds such a block */

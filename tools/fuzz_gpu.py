@@ -42,17 +42,20 @@ def main():
         srcs += [(f, i, s) for i, s in enumerate(fuzz_host.family(f))]
     out = ROOT / "gpurun_out"
     out.mkdir(exist_ok=True)
-    decs = {0: fb.Jpeg2000Decoder(device=0, slots=1), 1: fb.Jpeg2000Decoder(device=0, slots=1, bitexact=True)}
+    # one decoder context per mode: (bit-exact flag, AVCodecContext.lowres)
+    decs = {(be, lr): fb.Jpeg2000Decoder(device=0, slots=1, bitexact=bool(be), flags=fb.flag_lowres(lr))
+            for be in (0, 1) for lr in (0, 1, 2)}
     t0 = time.time()
     n = pictures = errors = bad = failed_blocks = 0
     while time.time() - t0 < a.seconds:
         fam, idx, src = rng.choice(srcs)
         cs, where = fuzz_host.damage(rng, src)
-        be = 1 if irreversible(src) else 0
+        be = 1 if irreversible(src) else int(rng.random() < 0.1)
+        lr = rng.choice((0, 0, 0, 0, 1, 2))
         n += 1
-        ro, _, opic = oracle_decode(cs, be)
+        ro, _, opic = oracle_decode(cs, be | (lr << 8))
         try:
-            info, pic = decs[be].decode(cs)
+            info, pic = decs[(be, lr)].decode(cs)
             rp = 0
             failed_blocks += info.nblocks_failed
         except fb.DecodeError as e:
@@ -61,7 +64,7 @@ def main():
             bad += 1
             name = out / f"fuzzgpu_{a.seed}_{n}.j2k"
             name.write_bytes(cs)
-            print(f"DIFFER case {n} ({fam}[{idx}], bitexact {be}, damage at {where}): oracle {ro} / product {rp} -> {name.name}",
+            print(f"DIFFER case {n} ({fam}[{idx}], bitexact {be} lowres {lr}, damage at {where}): oracle {ro} / product {rp} -> {name.name}",
                   flush=True)
         elif ro == 0:
             pictures += 1
