@@ -34,7 +34,7 @@ int parse_cox(const uint8_t *p, const uint8_t *end, CodSty *c, int flags)
     if (end - p < 5)
         return B200J2K_ERR_INVALIDDATA;
     c->nres = p[0] + 1;
-    if (c->nres > J2K_MAX_LEVELS)
+    if (c->nres > J2K_MAX_LEVELS + 1)                     /* JPEG2000_MAX_RESLEVELS = 34: up to 32 decomposition levels */
         return B200J2K_ERR_INVALIDDATA;
     /* lowres (jpeg2000dec.c:509-520): more levels dropped than the stream has is an error */
     if (c->nres <= B200J2K_FLAG_GET_LOWRES(flags))
@@ -79,7 +79,7 @@ int parse_qcx(const uint8_t *p, int n, int64_t avail, QntSty *q)
     avail--;
     if (q->style == 0) {
         const int m = n - 1;
-        if (avail < m || m > 96)
+        if (avail < m || m > 99)                          /* JPEG2000_MAX_DECLEVELS * 3 */
             return B200J2K_ERR_INVALIDDATA;
         for (int i = 0; i < m; i++)
             q->expn[i] = p[i] >> 3;
@@ -91,7 +91,7 @@ int parse_qcx(const uint8_t *p, int n, int64_t avail, QntSty *q)
         unsigned x = rd16(p);
         q->expn[0] = x >> 11;
         q->mant[0] = x & 0x7FF;
-        for (int i = 1; i < 96; i++) {
+        for (int i = 1; i < 99; i++) {
             q->expn[i] = (uint8_t)imax(0, q->expn[0] - (i - 1) / 3);
             q->mant[i] = q->mant[0];
         }
@@ -99,7 +99,7 @@ int parse_qcx(const uint8_t *p, int n, int64_t avail, QntSty *q)
     }
     /* style 2, and every undefined one (their bands get a step size of zero, band_stepsize) */
     const int m = (n - 1) >> 1;
-    if (avail < 2 * m || m > 96)
+    if (avail < 2 * m || m > 99)
         return B200J2K_ERR_INVALIDDATA;
     for (int i = 0; i < m; i++) {
         unsigned x = rd16(p + 2 * i);

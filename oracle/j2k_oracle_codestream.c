@@ -222,7 +222,7 @@ static int parse_cox(Dec *d, const uint8_t *p, const uint8_t *end, CodSty *c)
     if (end - p < 5)
         return ORACLE_ERR_INVALID;
     c->nres = p[0] + 1;
-    if (c->nres >= MAXRES)
+    if (c->nres > MAXRES)                           /* JPEG2000_MAX_RESLEVELS = 34: up to 32 decomposition levels */
         return ORACLE_ERR_INVALID;
     if (c->nres <= d->red)                          /* "reduction_factor too large for this bitstream" (:509-517) */
         return ORACLE_ERR_EINVAL;
@@ -266,7 +266,7 @@ static int parse_qcx(const uint8_t *p, int n, int64_t avail, QntSty *q)
     int used = 1;
     if (q->style == 0) {
         n -= 1;
-        if (avail < n || n > 96)
+        if (avail < n || n > 99)
             return ORACLE_ERR_INVALID;
         for (int i = 0; i < n; i++, used++)
             q->expn[i] = p[i] >> 3;
@@ -277,13 +277,13 @@ static int parse_qcx(const uint8_t *p, int n, int64_t avail, QntSty *q)
         used += 2;
         q->expn[0] = x >> 11;
         q->mant[0] = x & 0x7FF;
-        for (int i = 1; i < 96; i++) {
+        for (int i = 1; i < 99; i++) {
             q->expn[i] = imax(0, q->expn[0] - (i - 1) / 3);
             q->mant[i] = q->mant[0];
         }
     } else {                                              /* 2 and the undefined styles alike */
         n = (n - 1) >> 1;
-        if (avail < 2 * n || n > 96)
+        if (avail < 2 * n || n > 99)
             return ORACLE_ERR_INVALID;
         for (int i = 0; i < n; i++, used += 2) {
             unsigned x = rd16(p + 2 * i);

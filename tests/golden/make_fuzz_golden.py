@@ -20,6 +20,7 @@ What each one pinned down:
   bypass0  a Part-1 style with arithmetic-coding bypass announced, but no block ever contributes (no SOD): the style is
            only refused (PATCHWELCOME, not served) when a block of it is met in a packet
   plt      a PPT marker turned into a PLT whose last byte has the continuation bit set: get_plt refuses it (:951)
+  levels32 32 decomposition levels (of a 1 x 1 picture): the reference's limit is JPEG2000_MAX_RESLEVELS = 34, not 33
   noqcd    no QCD at all (exponents and guard bits zero: M_b = -1) and no SOD: nothing decodes, the picture is the
            DC level -- not an error
 Run where the reference is mounted:  python tests/golden/make_fuzz_golden.py"""
@@ -50,6 +51,7 @@ CASES = {
     "noqcd": ("plain", 18, [("set", 69, 53), ("set", 88, 131)]),
     "layers": ("part1", 13, [("set", 136, 255), ("set", 595, 11)]),
     "jp2size": ("part1", 13, [("set", 32, 255)]),
+    "levels32": ("plain", 18, [("set", 64, 0x20)]),
     "plt": ("packed", 4, [("set", 37122, 0x58)]),
     "bypass0": ("plain", 18, [("set", 67, 19), ("set", 87, 247), ("set", 95, 255)]),
 }

@@ -564,4 +564,4 @@ def test_plan_of_fuzz_findings_matches_reference():
             assert (info.width, info.height) == (meta[0], meta[1]), key
             assert hashlib.sha1(pic.tobytes()).digest() == out.tobytes(), key
         n += 1
-    assert n == 23
+    assert n == 24
