@@ -88,8 +88,13 @@ def damage(rng, src):
             cs[p] ^= 1 << rng.randrange(8)
         elif kind < 0.95:
             cs[p] = 0xFF
-        else:
+        elif kind < 0.97:
             del cs[p: p + rng.randint(1, 40)]          # bytes lost
+        elif kind < 0.985:
+            del cs[p:]                                 # the rest of the frame never arrived
+        else:
+            n = rng.randint(2, 200)                    # a run of bytes arrives twice
+            cs[p:p] = cs[p: p + n]
         where.append(p)
     return bytes(cs), where
 
