@@ -1286,21 +1286,22 @@ void Parser::select_header(int tileno, int *tp)
 
 void Parser::select_part(int tileno, int *tp, int csty)
 {
+    /* select_stream (jpeg2000dec.c:1111-1134): the tile's parts are 32 slots indexed by TPsot, a slot that never saw
+     * its SOD is an empty stream; an exhausted or empty one hands over to the next slot, over gaps in the numbering,
+     * up to the last slot.  What the decoder reports as consumed at the end is the position in the stream selected
+     * last -- zero for an empty slot. */
     auto &pv = parts_[tileno];
-    if (pv.empty() || *tp >= (int)pv.size()) {            /* no such tile-part: an empty stream */
-        bp_ = bend_ = pkt_ + pkt_size_;
-        return;
+    auto slot = [&](int i) -> const TilePart * { return i < (int)pv.size() && pv[i].p ? &pv[i] : nullptr; };
+    const TilePart *cur = slot(*tp);
+    while ((!cur || cur->p >= cur->end) && bit_index_ == 8 && *tp < 31)
+        cur = slot(++*tp);
+    if (cur) {
+        bp_ = cur->p;
+        bend_ = cur->end;
+        cur_part_start_ = cur->start;
+    } else {
+        bp_ = bend_ = cur_part_start_ = pkt_ + pkt_size_;
     }
-    bp_ = pv[*tp].p;
-    bend_ = pv[*tp].end;
-    while ((!bp_ || bp_ >= bend_) && bit_index_ == 8 && *tp + 1 < (int)pv.size()) {
-        ++*tp;
-        bp_ = pv[*tp].p;
-        bend_ = pv[*tp].end;
-    }
-    cur_part_start_ = pv[*tp].start;
-    if (!bp_)
-        bp_ = bend_ = pkt_ + pkt_size_;
     if (csty & 2)
         if (bend_ - bp_ >= 6 && rd32(bp_) == 0xFF910004u)
             bp_ += 6;
@@ -1513,7 +1514,7 @@ int Parser::decode_packet(int tileno, int c, int r, int precno, int layno, int *
             }
         }
     }
-    if (*tp < (int)parts_[tileno].size())
+    if (*tp < (int)parts_[tileno].size() && parts_[tileno][*tp].start)      /* an empty slot stays empty */
         parts_[tileno][*tp].p = bp_;
     return 0;
 }

@@ -127,8 +127,9 @@ def main():
         lowres = rng.choice((0, 0, 0, 0, 1, 2))
         mode = bitexact | (lowres << 8)
         ro, _, opic = oracle_decode(cs, mode)
+        pinfo = None
         try:
-            _, ppic = picture_from_plan(cs, (fb.FLAG_BITEXACT if bitexact else 0) | fb.flag_lowres(lowres))
+            pinfo, ppic = picture_from_plan(cs, (fb.FLAG_BITEXACT if bitexact else 0) | fb.flag_lowres(lowres))
             rp = 0
         except fb.DecodeError as e:
             rp, ppic = e.code, None
@@ -143,7 +144,7 @@ def main():
         if (ro == 0) != (rp == 0) or (ro == 0 and not np.array_equal(opic, ppic)):
             what.append(f"oracle {ro} / product {rp}")
         if use_ref:
-            rr, _, rpic, _ = ref_decode(cs, mode)
+            rr, rinfo, rpic, rname = ref_decode(cs, mode)
             if rr == 0 and ro == 0 and not np.array_equal(rpic, opic) and fresh_reference_sha1(cs, mode) != hashlib.sha1(rpic.tobytes()).hexdigest():
                 # damaged lengths make the reference read heap bytes behind a block's data: what it returns then
                 # depends on what this process decoded before (a fresh process is the yardstick)
@@ -153,6 +154,13 @@ def main():
                 what.append(f"reference {rr} / oracle {ro}")
             if (rr == 0) != (rp == 0) or (rr == 0 and rp == 0 and not np.array_equal(rpic, ppic)):
                 what.append(f"reference {rr} / product {rp}")
+            elif rr == 0:
+                # what the caller sees besides the picture: size, format, how far the decoder read (the return value
+                # of FFCodec.cb.decode)
+                got = (pinfo.width, pinfo.height, pinfo.pix_name, pinfo.bytes_consumed)
+                want = (rinfo[0], rinfo[1], rname, rinfo[4])
+                if got != want:
+                    what.append(f"frame info: reference {want} / product {got}")
         if what:
             bad += 1
             name = out / f"fuzz_{a.seed}_{n}.j2k"
