@@ -34,6 +34,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cases", type=int, default=0, help="stop after this many cases instead of after --seconds")
     ap.add_argument("--families", default="ht_sets,layered,plain,packed,tile_parts,poc,tile_styles")
     a = ap.parse_args()
     rng = random.Random(a.seed)
@@ -47,7 +48,7 @@ def main():
             for be in (0, 1) for lr in (0, 1, 2)}
     t0 = time.time()
     n = pictures = errors = bad = failed_blocks = 0
-    while time.time() - t0 < a.seconds:
+    while (n < a.cases) if a.cases else (time.time() - t0 < a.seconds):
         fam, idx, src = rng.choice(srcs)
         cs, where = fuzz_host.damage(rng, src)
         be = 1 if irreversible(src) else int(rng.random() < 0.1)

@@ -103,6 +103,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seconds", type=float, default=300)
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cases", type=int, default=0, help="stop after this many cases instead of after --seconds")
     ap.add_argument("--families", default="ht_sets,layered,plain,packed,tile_parts,poc,tile_styles")
     a = ap.parse_args()
     rng = random.Random(a.seed)
@@ -118,7 +119,7 @@ def main():
     t0 = time.time()
     n = pictures = errors = bad = stricter = unstable = 0
     PATCHWELCOME = -1163346256
-    while time.time() - t0 < a.seconds:
+    while (n < a.cases) if a.cases else (time.time() - t0 < a.seconds):
         fam, idx, src = rng.choice(srcs)
         cs, where = damage(rng, src)
         n += 1
