@@ -62,6 +62,14 @@ def family(name):
             w, h, kw = T.SUBSAMPLED_GEOMS[i % len(T.SUBSAMPLED_GEOMS)]
             out.append(bytes(T.subsampled_stream(subs, bd, w, h, kw)[0]))
         return out
+    if name == "jp2":                           # JP2 wrappers: palettes (PAL8), colour specifications, D-Cinema profiles,
+        out = []                                # resolution boxes
+        for bd, csp, pal in T.PAL8_CASES:
+            out.append(bytes(T.pal8_file(bd, csp, pal)[0]))
+            out.append(bytes(T.pal8_file(bd, csp, pal, tile=(64, 32))[0]))
+        out += [bytes(c) for _, c in T.dcinema_cases()]
+        out += [bytes(T.res_box_file(r)) for r in T.RES_BOXES]
+        return out
     raise SystemExit("unknown family " + name)
 
 
