@@ -47,6 +47,10 @@ int main(int argc, char **argv)
         // exact-size heap copy so that ASAN sees any over-read (the library contract asks for no padding)
         uint8_t *p = (uint8_t *)malloc(d.size()); memcpy(p, d.data(), d.size());
         int flags = (rnd() & 1) | ((rnd() % 8 == 0 ? rnd() % 4 : 0) << 8);
+        if (rnd() % 5 == 0) {                       // a context that owns every step-th tile (B200J2K_FLAG_TILES)
+            const int step = 2 + rnd() % 4;
+            flags |= B200J2K_FLAG_TILES(rnd() % step, step);
+        }
         int r = P.parse(p, (int64_t)d.size(), flags, false);
         if (r >= 0) {
             ok++;
