@@ -35,7 +35,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=120)
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cases", type=int, default=0, help="stop after this many cases instead of after --seconds")
-    ap.add_argument("--families", default="ht_sets,layered,plain,packed,tile_parts,poc,tile_styles")
+    ap.add_argument("--families", default="ht_sets,layered,plain,packed,tile_parts,poc,tile_styles,jp2")
     a = ap.parse_args()
     rng = random.Random(a.seed)
     srcs = []
@@ -54,13 +54,15 @@ def main():
         be = 1 if irreversible(src) else int(rng.random() < 0.1)
         lr = rng.choice((0, 0, 0, 0, 1, 2))
         n += 1
-        ro, _, opic = oracle_decode(cs, be | (lr << 8))
+        ro, oinfo, opic = oracle_decode(cs, be | (lr << 8))
         try:
             info, pic = decs[(be, lr)].decode(cs)
             rp = 0
             failed_blocks += info.nblocks_failed
         except fb.DecodeError as e:
             rp, pic = e.code, None
+        if ro == 0 and rp == 0 and (info.width, info.height) != (oinfo[0], oinfo[1]):
+            pic = None                                  # counts as a difference below
         if (ro == 0) != (rp == 0) or (ro == 0 and not np.array_equal(opic, pic)):
             bad += 1
             name = out / f"fuzzgpu_{a.seed}_{n}.j2k"
