@@ -21,6 +21,8 @@ What each one pinned down:
            only refused (PATCHWELCOME, not served) when a block of it is met in a packet
   plt      a PPT marker turned into a PLT whose last byte has the continuation bit set: get_plt refuses it (:951)
   levels32 32 decomposition levels (of a 1 x 1 picture): the reference's limit is JPEG2000_MAX_RESLEVELS = 34, not 33
+  nosod    the only tile-part never reaches its SOD: the picture is the DC level and the decoder reports 0 bytes consumed
+           (the position in the tile-part stream selected last: an empty slot, :1111-1134, :2903)
   noqcd    no QCD at all (exponents and guard bits zero: M_b = -1) and no SOD: nothing decodes, the picture is the
            DC level -- not an error
 Run where the reference is mounted:  python tests/golden/make_fuzz_golden.py"""
@@ -51,6 +53,7 @@ CASES = {
     "noqcd": ("plain", 18, [("set", 69, 53), ("set", 88, 131)]),
     "layers": ("part1", 13, [("set", 136, 255), ("set", 595, 11)]),
     "jp2size": ("part1", 13, [("set", 32, 255)]),
+    "nosod": ("plain", 18, [("set", 88, 254)]),
     "levels32": ("plain", 18, [("set", 64, 0x20)]),
     "plt": ("packed", 4, [("set", 37122, 0x58)]),
     "bypass0": ("plain", 18, [("set", 67, 19), ("set", 87, 247), ("set", 95, 255)]),
@@ -99,7 +102,7 @@ def main():
         r, info, out, pix = ref_decode(cs, 0)
         k = f"{name}|0"
         pack[k + "|cs"] = np.frombuffer(cs, np.uint8)
-        pack[k + "|meta"] = np.array([info[0], info[1], r], np.int64)
+        pack[k + "|meta"] = np.array([info[0], info[1], r, info[4]], np.int64)     # [3]: bytes consumed (decode's return)
         pack[k + "|pix"] = np.frombuffer((pix or "none").encode(), np.uint8)
         pack[k + "|out"] = np.frombuffer(hashlib.sha1(out.tobytes()).digest(), np.uint8) if r == 0 else np.zeros(0, np.uint8)
         print(f"{name}: {len(cs)} bytes, reference {r}" + (f", {info[0]}x{info[1]} {pix}" if r == 0 else ""))

@@ -563,5 +563,6 @@ def test_plan_of_fuzz_findings_matches_reference():
             info, pic = picture_from_plan(cs, 0)
             assert (info.width, info.height) == (meta[0], meta[1]), key
             assert hashlib.sha1(pic.tobytes()).digest() == out.tobytes(), key
+            assert info.bytes_consumed == meta[3], key           # what FFCodec.cb.decode returns
         n += 1
-    assert n == 24
+    assert n == 25
