@@ -1739,14 +1739,20 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
     tags_.assign(tag_total_, TagNodeState{ 0, 0 });
     decoded_layers_.assign(precs_.size(), 0);
     extra.clear();
-    cur_part_start_ = nullptr;
+    /* s->g of the reference, whose position is what decode() returns in the end (jpeg2000dec.c:2903): the packet as the
+     * marker loop left it, until a tile selects one of its tile-part streams (select_part) */
+    cur_part_start_ = pkt_;
+    bp_ = pkt_ + consumed;
+    bend_ = pkt_ + pkt_size_;
     tile_subset = B200J2K_FLAG_GET_TILE_STEP(flags) > 1;
     needed_ranges.clear();
     for (int tileno = 0; tileno < hdr.ntx * hdr.nty; tileno++) {
-        /* a tile whose first tile-part (TPsot = 0) never showed up has no coding style in the reference:
-         * init_tile fails on !codsty->init (jpeg2000dec.c:1054-1055) and the frame with it */
-        if (!tile_first_[tileno])
-            return B200J2K_ERR_INVALIDDATA;
+        /* a tile whose first tile-part (TPsot = 0) never showed up did not inherit the main header's coding styles:
+         * unless a COD of its own filled them in, init_tile fails on !codsty->init (jpeg2000dec.c:1054-1055) and the
+         * frame with it */
+        for (int c = 0; c < hdr.ncomp; c++)
+            if (!tsty_[tileno].cod[c].init)
+                return B200J2K_ERR_INVALIDDATA;
         /* a transform byte other than 0 / 1: ff_jpeg2000_dwt_init has no such type and init_tile fails with its
          * bare -1 (jpeg2000dwt.c:551-591 via jpeg2000.c:477) */
         for (int c = 0; c < hdr.ncomp; c++)
@@ -1760,13 +1766,14 @@ int Parser::parse(const uint8_t *pkt, int64_t size, int flags, bool headers_only
                     needed_ranges.emplace_back((uint32_t)(tp.start - pkt), (uint32_t)(tp.end - tp.start));
         if ((ret = decode_packets(tileno)) < 0)
             return ret;
+        /* "EOC marker reached": every tile ends with bytestream2_skip(&s->g, 2) on whatever stream is current -- the
+         * tile-part stream its last packet came from, or still the previous one when the tile had no packet to read
+         * (:1865-1866) */
+        if (bp_ && bend_ > bp_)
+            bp_ += bend_ - bp_ < 2 ? bend_ - bp_ : 2;
     }
-    /* the reference returns bytestream2_tell() of the LAST tile-part sub-stream it read, after skipping
-     * the 2 EOC bytes if they are inside that sub-stream (jpeg2000dec.c:1865-1866, :2903) */
-    if (cur_part_start_ && bp_ && bp_ >= cur_part_start_) {
-        int64_t left = bend_ - bp_;
-        consumed = (int64_t)(bp_ - cur_part_start_) + (left < 2 ? (left < 0 ? 0 : left) : 2);
-    }
+    if (cur_part_start_ && bp_ && bp_ >= cur_part_start_)
+        consumed = (int64_t)(bp_ - cur_part_start_);
     /* emit the descriptor table */
     cblk = cblk_template_;
     max_Lcup = max_Lref = 0;

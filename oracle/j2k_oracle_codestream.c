@@ -978,10 +978,8 @@ static void band_stepsize(Band *b, const CodSty *c, const QntSty *q, int bandno,
 static int init_tile(Dec *d, int tileno)
 {
     Tile *t = &d->tile[tileno];
-    /* a tile whose first tile-part never showed up has no coding style: init_tile fails on !codsty->init
-     * (jpeg2000dec.c:1054-1055) and with it the whole frame */
-    if (!t->first_seen)
-        return ORACLE_ERR_INVALID;
+    /* a tile whose first tile-part never showed up has no coding style unless a COD of its own supplies one: the
+     * per-component check on cs->init below (jpeg2000dec.c:1054-1055) fails the frame then */
     const int tx = tileno % d->ntx, ty = tileno / d->ntx;
     t->c.x0 = clip64((int64_t)tx * d->TW + d->TX0, d->X0, d->W);
     t->c.x1 = clip64((int64_t)(tx + 1) * d->TW + d->TX0, d->X0, d->W);

@@ -23,6 +23,9 @@ What each one pinned down:
   levels32 32 decomposition levels (of a 1 x 1 picture): the reference's limit is JPEG2000_MAX_RESLEVELS = 34, not 33
   nosod    the only tile-part never reaches its SOD: the picture is the DC level and the decoder reports 0 bytes consumed
            (the position in the tile-part stream selected last: an empty slot, :1111-1134, :2903)
+  tp1cod   a tile whose only tile-part says TPsot = 1 but carries its own COD / QCD: the styles are initialised, it decodes
+  eoc2     an unknown progression order (no packet is read) and a run of bytes behind EOC: every tile still ends with
+           the 2-byte EOC skip on the stream that is current -- here the whole packet: 184 bytes consumed, not 182
   noqcd    no QCD at all (exponents and guard bits zero: M_b = -1) and no SOD: nothing decodes, the picture is the
            DC level -- not an error
 Run where the reference is mounted:  python tests/golden/make_fuzz_golden.py"""
@@ -54,6 +57,8 @@ CASES = {
     "layers": ("part1", 13, [("set", 136, 255), ("set", 595, 11)]),
     "jp2size": ("part1", 13, [("set", 32, 255)]),
     "nosod": ("plain", 18, [("set", 88, 254)]),
+    "tp1cod": ("tile_styles", 1, [("set", 6809, 1)]),
+    "eoc2": ("plain", 21, [("dup", 113, 69), ("set", 60, 197), ("set", 105, 80)]),
     "levels32": ("plain", 18, [("set", 64, 0x20)]),
     "plt": ("packed", 4, [("set", 37122, 0x58)]),
     "bypass0": ("plain", 18, [("set", 67, 19), ("set", 87, 247), ("set", 95, 255)]),
@@ -93,6 +98,8 @@ def main():
         for op, pos, v in ops:
             if op == "set":
                 cs[pos] = v
+            elif op == "dup":
+                cs[pos:pos] = cs[pos: pos + v]
             elif op == "ins_before_sot":
                 at = bytes(cs).index(b"\xff\x90")
                 cs[at:at] = v
