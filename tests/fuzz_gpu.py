@@ -1,10 +1,10 @@
 #!/usr/bin/env python3
-"""Differential fuzzing on the GPU box: the damaged streams of tools/fuzz_host.py decoded by the product through the
+"""Differential fuzzing on the GPU box: the damaged streams of tests/fuzz_host.py decoded by the product through the
 C ABI (kernels and all) and by the oracle; verdict and every byte of the picture must agree.  Reversible streams as
 they are, irreversible ones with the bit-exact flag (integer 9/7) so that the comparison is exact.  Test
 infrastructure; cases that differ are written to gpurun_out/fuzzgpu_<seed>_<n>.j2k.
 
-  python tools/fuzz_gpu.py [--seconds 120] [--seed 1] [--families ...]"""
+  python tests/fuzz_gpu.py [--seconds 120] [--seed 1] [--families ...]"""
 import argparse
 import importlib.util
 import random
@@ -19,7 +19,7 @@ import numpy as np  # noqa: E402
 import ffmpeg_ht_b200 as fb  # noqa: E402
 from helpers import oracle_decode  # noqa: E402
 
-spec = importlib.util.spec_from_file_location("fuzz_host", ROOT / "tools" / "fuzz_host.py")
+spec = importlib.util.spec_from_file_location("fuzz_host", ROOT / "tests" / "fuzz_host.py")
 fuzz_host = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(fuzz_host)
 

@@ -7,7 +7,7 @@
 They must agree on the verdict (picture or error) and, for a picture, on every byte.  Test infrastructure:
 prints the cases that differ and writes them to gpurun_out/fuzz_<seed>_<n>.j2k.
 
-  python tools/fuzz_host.py [--seconds 300] [--seed 1] [--families ht_sets,layered,...]"""
+  python tests/fuzz_host.py [--seconds 300] [--seed 1] [--families ht_sets,layered,...]"""
 import argparse
 import hashlib
 import random

@@ -1,8 +1,8 @@
 #!/usr/bin/env python3
-"""Triage of tools/fuzz_gpu.py findings on the GPU box: for every saved case, the HT code-blocks of the product's
+"""Triage of tests/fuzz_gpu.py findings on the GPU box: for every saved case, the HT code-blocks of the product's
 plan go through the stage-level entry (b200j2k_ht_blocks: same kernels as a frame) and through oracle_ht_block; the
 blocks that differ are printed and saved (gpurun_out/fuzz_blocks.npz) for a closer look on the CPU.
-  python tools/fuzz_triage_gpu.py gpurun_out/fuzzgpu_*.j2k"""
+  python tests/fuzz_triage_gpu.py gpurun_out/fuzzgpu_*.j2k"""
 import sys
 from pathlib import Path
 

@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Generates tests/golden/frames_fuzz.npz with the REFERENCE (oracle/_ref/libj2kref.so built from /root/reference):
-the damaged streams on which tools/fuzz_host.py (reference vs oracle vs product, differentially) found the oracle or
+the damaged streams on which tests/fuzz_host.py (reference vs oracle vs product, differentially) found the oracle or
 the product's parser deviating from the reference in round 2 -- each a generated stream plus a few damaged bytes --
 with the reference's verdict and a SHA-1 digest of its picture.  Same layout as frames_tiles.npz (key = name|flags).
 What each one pinned down:
@@ -40,11 +40,11 @@ ROOT = Path(__file__).resolve().parents[2]
 sys.path[:0] = [str(ROOT), str(ROOT / "tools"), str(ROOT / "tests")]
 from helpers import ref_decode  # noqa: E402
 
-spec = importlib.util.spec_from_file_location("fuzz_host", ROOT / "tools" / "fuzz_host.py")
+spec = importlib.util.spec_from_file_location("fuzz_host", ROOT / "tests" / "fuzz_host.py")
 fuzz_host = importlib.util.module_from_spec(spec)
 spec.loader.exec_module(fuzz_host)
 
-# name: (family of tools/fuzz_host.py, index in it, operations in order: ("set", position, byte) / ("del", position, count))
+# name: (family of tests/fuzz_host.py, index in it, operations in order: ("set", position, byte) / ("del", position, count))
 CASES = {
     "segs": ("ht_sets", 2, [("set", 42009, 83)]),
     "qcd_len": ("plain", 19, [("set", 73, 146), ("set", 93, 244)]),

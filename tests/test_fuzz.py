@@ -1,4 +1,4 @@
-"""Bounded runs of the differential fuzzers (tools/fuzz_host.py, tools/fuzz_gpu.py): a fixed seed and a fixed number of
+"""Bounded runs of the differential fuzzers (tests/fuzz_host.py, tests/fuzz_gpu.py): a fixed seed and a fixed number of
 cases each (the same cases every time), a few seconds.
 The long runs and what they found: DESIGN.md section 5.1; the findings themselves are pinned in tests/golden/frames_fuzz.npz."""
 import subprocess
@@ -10,7 +10,7 @@ from helpers import ROOT
 
 
 def run(tool, *args):
-    p = subprocess.run([sys.executable, str(ROOT / "tools" / tool), *args], capture_output=True, text=True, timeout=600)
+    p = subprocess.run([sys.executable, str(ROOT / "tests" / tool), *args], capture_output=True, text=True, timeout=600)
     tail = p.stdout.strip().splitlines()[-1] if p.stdout.strip() else p.stderr[-400:]
     return p.returncode, tail, p.stdout
 

@@ -89,7 +89,7 @@ def test_blocks_vs_oracle(npasses):
 
 
 def test_refinement_block_without_cleanup_bytes_leaves_its_neighbours_alone():
-    """Found by tools/fuzz_gpu.py: a block that announces refinement passes but no cleanup bytes (npasses 6, Lcup 0) owns
+    """Found by tests/fuzz_gpu.py: a block that announces refinement passes but no cleanup bytes (npasses 6, Lcup 0) owns
     no scratch; the refinement un-stuffing kernel wrote its (empty) streams anyway -- into the un-stuffed VLC bits of
     whatever block sat at that offset.  The three blocks of the smallest reproducer, and the same next to ordinary
     blocks with refinement passes."""

@@ -548,7 +548,7 @@ def test_component_must_fit_its_output_plane():
 
 
 def test_plan_of_fuzz_findings_matches_reference():
-    """tests/golden/frames_fuzz.npz: the damaged streams on which the differential fuzzer (tools/fuzz_host.py) caught the
+    """tests/golden/frames_fuzz.npz: the damaged streams on which the differential fuzzer (tests/fuzz_host.py) caught the
     parser deviating from the reference -- verdict and picture of the REFERENCE, reproduced from the product's tables."""
     import hashlib
     z = np.load(ROOT / "tests" / "golden" / "frames_fuzz.npz")
