@@ -531,11 +531,17 @@ int Parser::parse_headers(const uint8_t *pkt, int64_t size, int flags, size_t *m
         }
         if (marker == 0xFFD9)
             break;
-        if (end - p < 2)
+        /* "Missing EOC Marker" (:2485-2494): the length field has been read (a checked read: short of two bytes it
+         * moves to the end) before the loop gives up -- the position counts for the bytes consumed */
+        if (end - p < 2) {
+            p = end;
             break;
+        }
         int len = (int)rd16(p);
-        if (len < 2 || end - p < len)
+        if (len < 2 || end - p < len) {
+            p += 2;
             break;
+        }
         const uint8_t *seg = p + 2, *segend = p + len;
         int ret = 0;
         switch (marker) {
@@ -1010,10 +1016,10 @@ int Parser::build_geometry(int flags)
                         bppx = rl.ppx; bppy = rl.ppy;
                     } else {
                         const int xo = (b + 1) & 1, yo = ((b + 1) >> 1) & 1;
-                        bd.c.x0 = ceildivpow2(cc.x0 - (xo << (decl - 1)), decl);
-                        bd.c.x1 = ceildivpow2(cc.x1 - (xo << (decl - 1)), decl);
-                        bd.c.y0 = ceildivpow2(cc.y0 - (yo << (decl - 1)), decl);
-                        bd.c.y1 = ceildivpow2(cc.y1 - (yo << (decl - 1)), decl);
+                        bd.c.x0 = ceildivpow2((int)(cc.x0 - ((int64_t)xo << (decl - 1))), decl);
+                        bd.c.x1 = ceildivpow2((int)(cc.x1 - ((int64_t)xo << (decl - 1))), decl);
+                        bd.c.y0 = ceildivpow2((int)(cc.y0 - ((int64_t)yo << (decl - 1))), decl);
+                        bd.c.y1 = ceildivpow2((int)(cc.y1 - ((int64_t)yo << (decl - 1))), decl);
                         bppx = rl.ppx - 1; bppy = rl.ppy - 1;
                     }
                     bd.empty = bd.c.x0 == bd.c.x1 || bd.c.y0 == bd.c.y1;

@@ -1038,10 +1038,10 @@ static int init_tile(Dec *d, int tileno)
                     bppy = rl->ppy;
                 } else {
                     const int xo = (b + 1) & 1, yo = ((b + 1) >> 1) & 1;
-                    bd->c.x0 = ceildivpow2(comp->c.x0 - (xo << (decl - 1)), decl);
-                    bd->c.x1 = ceildivpow2(comp->c.x1 - (xo << (decl - 1)), decl);
-                    bd->c.y0 = ceildivpow2(comp->c.y0 - (yo << (decl - 1)), decl);
-                    bd->c.y1 = ceildivpow2(comp->c.y1 - (yo << (decl - 1)), decl);
+                    bd->c.x0 = ceildivpow2((int)(comp->c.x0 - ((int64_t)xo << (decl - 1))), decl);
+                    bd->c.x1 = ceildivpow2((int)(comp->c.x1 - ((int64_t)xo << (decl - 1))), decl);
+                    bd->c.y0 = ceildivpow2((int)(comp->c.y0 - ((int64_t)yo << (decl - 1))), decl);
+                    bd->c.y1 = ceildivpow2((int)(comp->c.y1 - ((int64_t)yo << (decl - 1))), decl);
                     bppx = rl->ppx - 1;
                     bppy = rl->ppy - 1;
                 }
