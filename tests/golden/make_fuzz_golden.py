@@ -26,6 +26,8 @@ What each one pinned down:
   tp1cod   a tile whose only tile-part says TPsot = 1 but carries its own COD / QCD: the styles are initialised, it decodes
   eoc2     an unknown progression order (no packet is read) and a run of bytes behind EOC: every tile still ends with
            the 2-byte EOC skip on the stream that is current -- here the whole packet: 184 bytes consumed, not 182
+  badlen   no packet is read (unknown progression order) and the marker loop gives up on a length field behind the
+           tile-part: the two bytes of that field count as consumed (:2485-2494)
   noqcd    no QCD at all (exponents and guard bits zero: M_b = -1) and no SOD: nothing decodes, the picture is the
            DC level -- not an error
 Run where the reference is mounted:  python tests/golden/make_fuzz_golden.py"""
@@ -57,6 +59,7 @@ CASES = {
     "layers": ("part1", 13, [("set", 136, 255), ("set", 595, 11)]),
     "jp2size": ("part1", 13, [("set", 32, 255)]),
     "nosod": ("plain", 18, [("set", 88, 254)]),
+    "badlen": ("part1", 23, [("dup", 782, 145), ("set", 160, 248)]),
     "tp1cod": ("tile_styles", 1, [("set", 6809, 1)]),
     "eoc2": ("plain", 21, [("dup", 113, 69), ("set", 60, 197), ("set", 105, 80)]),
     "levels32": ("plain", 18, [("set", 64, 0x20)]),

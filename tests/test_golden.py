@@ -76,7 +76,7 @@ def test_golden_frames_part1_and_tiles(name):
             else:
                 assert np.array_equal(got, out), key
         n += 1
-    assert n >= (27 if name == "frames_fuzz.npz" else 25)
+    assert n >= (28 if name == "frames_fuzz.npz" else 25)
 
 
 def test_golden_kat_values():

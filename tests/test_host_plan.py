@@ -565,4 +565,4 @@ def test_plan_of_fuzz_findings_matches_reference():
             assert hashlib.sha1(pic.tobytes()).digest() == out.tobytes(), key
             assert info.bytes_consumed == meta[3], key           # what FFCodec.cb.decode returns
         n += 1
-    assert n == 27
+    assert n == 28
